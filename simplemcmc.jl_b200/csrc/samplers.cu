@@ -1,0 +1,490 @@
+// Lockstep samplers: every chain advances through the same kernel sequence; per-chain control flow
+// (early trajectory stop, accept/reject) is a mask.  Replaces the main loops of
+// /root/reference/src/samplers.jl: simpleHMC :146-167 (+ leapFrog :50-59, update! :47),
+// simpleRWM :89-113 (Vihola's robust adaptive Metropolis).  State layout: [M][Cpad], one thread per chain
+// or per (component, chain) so that every access is coalesced over chains.
+#include <math.h>
+#include <algorithm>
+#include <vector>
+#include "smc_internal.h"
+#include "philox.cuh"
+
+namespace {
+
+struct Arena {
+  std::vector<void*> ptrs;
+  ~Arena() { for (void* p : ptrs) cudaFree(p); }
+  template <typename T>
+  int alloc(T** out, size_t n) {
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T));
+    if (e != cudaSuccess) { smc_set_error("cudaMalloc of %zu bytes failed: %s", n * sizeof(T), cudaGetErrorString(e)); return SMC_ERR_CUDA; }
+    ptrs.push_back(p);
+    *out = (T*)p;
+    return SMC_OK;
+  }
+};
+
+struct RngSrc {
+  unsigned long long seed;
+  long long chain_offset;
+  const double* inj_n;  // [steps][C][M] or null
+  const double* inj_u;  // [steps][C][nu] or null
+  long long nu;
+};
+
+__device__ __forceinline__ double rng_uniform(const RngSrc& r, long long step, long long c, long long C, int k) {
+  if (r.inj_u) return r.inj_u[(step * C + c) * r.nu + k];
+  return smc_uniform(r.seed, (unsigned long long)(c + r.chain_offset), (unsigned long long)step, (uint32_t)k);
+}
+
+// v[j][c] ~ N(0,1), j < M ; returns sum v^2
+__device__ __forceinline__ double draw_normals(const RngSrc& r, long long step, long long c, long long C, long long M,
+                                               long long Cpad, double* v) {
+  double ss = 0.0;
+  if (r.inj_n) {
+    const double* src = r.inj_n + (step * C + c) * M;
+    for (long long j = 0; j < M; j++) { double z = src[j]; v[j * Cpad + c] = z; ss += z * z; }
+  } else {
+    for (long long j = 0; j < M; j += 2) {
+      double z0, z1;
+      smc_normal_pair(r.seed, (unsigned long long)(c + r.chain_offset), (unsigned long long)step, (uint32_t)(j >> 1), z0, z1);
+      v[j * Cpad + c] = z0; ss += z0 * z0;
+      if (j + 1 < M) { v[(j + 1) * Cpad + c] = z1; ss += z1 * z1; }
+    }
+  }
+  return ss;
+}
+
+struct Recorder {
+  double* draws;   // [samples][M][Cpad]
+  double* loglik;  // [samples][Cpad]
+  double* accept;  // [samples][Cpad]
+  double* mean;    // [M][Cpad]
+  double* m2;      // [M][Cpad]
+  double* nacc;    // [Cpad]
+  long long burnin;
+};
+
+__device__ __forceinline__ void record(const Recorder& R, long long step, long long c, long long M, long long Cpad,
+                                       const double* beta, double ll, bool accepted) {
+  if (step < R.burnin) return;
+  long long s = step - R.burnin;
+  if (R.loglik) R.loglik[s * Cpad + c] = ll;
+  if (R.accept) R.accept[s * Cpad + c] = accepted ? 1.0 : 0.0;
+  R.nacc[c] += accepted ? 1.0 : 0.0;
+  double n = (double)(s + 1);
+  for (long long j = 0; j < M; j++) {
+    double x = beta[j * Cpad + c];
+    if (R.draws) R.draws[(s * M + j) * Cpad + c] = x;
+    double mu = R.mean[j * Cpad + c], d = x - mu;
+    mu += d / n;
+    R.mean[j * Cpad + c] = mu;
+    R.m2[j * Cpad + c] += d * (x - mu);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- HMC
+// state0.v = randn ; update!(state0) ; state = state0     (src/samplers.jl:151-153)
+__global__ void k_hmc_begin(RngSrc rng, long long step, long long C, long long M, long long Cpad, const double* b0,
+                            const double* g0, const double* l0, double* beta, double* grad, double* logp, double* v,
+                            double* H0, double* H, int* active) {
+  long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double ss = draw_normals(rng, step, c, C, M, Cpad, v);
+  for (long long j = 0; j < M; j++) {
+    beta[j * Cpad + c] = b0[j * Cpad + c];
+    grad[j * Cpad + c] = g0[j * Cpad + c];
+  }
+  double ll = l0[c];
+  logp[c] = ll;
+  H0[c] = ll - ss / 2.0;
+  H[c] = H0[c];
+  active[c] = isfinite(ll) ? 1 : 0;
+}
+
+// n.v += n.grad * ve / 2 ; n.beta += ve * n.v          (src/samplers.jl:52-53)
+__global__ void k_leapfrog_pre(long long C, long long M, long long Cpad, double eps, const int* active, double* beta,
+                               const double* grad, double* v) {
+  long long total = C * M;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long j = i / C, c = i - j * C;
+    if (!active[c]) continue;
+    long long o = j * Cpad + c;
+    double vv = v[o] + grad[o] * eps / 2.0;
+    v[o] = vv;
+    beta[o] += eps * vv;
+  }
+}
+
+// n.v += n.grad * ve / 2 ; update!(n) ; loop condition isfinite(state.llik)   (src/samplers.jl:55-56,156)
+__global__ void k_leapfrog_post(long long C, long long M, long long Cpad, double eps, int* active, const double* grad,
+                                const double* logp, double* v, double* H, unsigned long long* nleap) {
+  long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C || !active[c]) return;
+  double ss = 0.0;
+  for (long long j = 0; j < M; j++) {
+    long long o = j * Cpad + c;
+    double vv = v[o] + grad[o] * eps / 2.0;
+    v[o] = vv;
+    ss += vv * vv;
+  }
+  double ll = logp[c];
+  H[c] = ll - ss / 2.0;
+  if (!isfinite(ll)) active[c] = 0;
+  nleap[c] += 1ull;
+}
+
+// if rand() < exp(state.H - state0.H): state0 = state ; addToRes!   (src/samplers.jl:162-166)
+__global__ void k_hmc_accept(RngSrc rng, long long step, long long C, long long M, long long Cpad, const double* beta,
+                             const double* grad, const double* logp, const double* H, const double* H0, double* b0,
+                             double* g0, double* l0, Recorder R) {
+  long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double u = rng_uniform(rng, step, c, C, 0);
+  bool acc = u < exp(H[c] - H0[c]);
+  if (acc) {
+    for (long long j = 0; j < M; j++) {
+      b0[j * Cpad + c] = beta[j * Cpad + c];
+      g0[j * Cpad + c] = grad[j * Cpad + c];
+    }
+    l0[c] = logp[c];
+  }
+  record(R, step, c, M, Cpad, b0, l0[c], acc);
+}
+
+// ---------------------------------------------------------------------------------------------- RWM
+// jump = randn ; beta += S * jump                      (src/samplers.jl:93-95)
+__global__ void k_rwm_propose(RngSrc rng, long long step, long long C, long long M, long long Cpad, const double* b0,
+                              const double* S, double* jump, double* beta) {
+  long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  draw_normals(rng, step, c, C, M, Cpad, jump);
+  for (long long i = 0; i < M; i++) {
+    double acc = 0.0;
+    for (long long k = 0; k <= i; k++) acc += S[(i + k * M) * Cpad + c] * jump[k * Cpad + c];  // S lower triangular
+    beta[i * Cpad + c] = b0[i * Cpad + c] + acc;
+  }
+}
+
+// accept/reject + robust adaptive Metropolis update of S (src/samplers.jl:99-112).
+// chol(S (I + a u u') S')' == chol(S S' + a (S u)(S u)')' : rank-one update (a > 0) / downdate (a < 0) of the lower factor.
+__global__ void k_rwm_accept(RngSrc rng, long long step, long long C, long long M, long long Cpad, const double* beta,
+                             const double* logp, double* b0, double* l0, double* S, const double* jump, double* w,
+                             Recorder R) {
+  long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double lnew = logp[c], lold = l0[c];
+  double alpha = fmin(1.0, exp(lnew - lold));
+  double u = rng_uniform(rng, step, c, C, 0);
+  bool rejected = u > alpha;
+  if (!rejected) {
+    for (long long j = 0; j < M; j++) b0[j * Cpad + c] = beta[j * Cpad + c];
+    l0[c] = lnew;
+  }
+  double lcur = l0[c];
+  record(R, step, c, M, Cpad, b0, lcur, lold != lcur);
+  // adaptation
+  double i1 = (double)(step + 1);
+  double eta = fmin(1.0, (double)M * pow(i1, -2.0 / 3.0));
+  double jj = 0.0;
+  for (long long k = 0; k < M; k++) { double z = jump[k * Cpad + c]; jj += z * z; }
+  double a = eta * (alpha - 0.234) / jj;  // S (I + a * jump jump') S'
+  if (!(a == a) || jj == 0.0) return;
+  double sgn = a >= 0.0 ? 1.0 : -1.0, sa = sqrt(fabs(a));
+  for (long long i = 0; i < M; i++) {
+    double acc = 0.0;
+    for (long long k = 0; k <= i; k++) acc += S[(i + k * M) * Cpad + c] * jump[k * Cpad + c];
+    w[i * Cpad + c] = sa * acc;
+  }
+  for (long long k = 0; k < M; k++) {
+    double Lkk = S[(k + k * M) * Cpad + c], wk = w[k * Cpad + c];
+    double r2 = Lkk * Lkk + sgn * wk * wk;
+    double r = sqrt(r2);
+    double cc = r / Lkk, ss = wk / Lkk;
+    S[(k + k * M) * Cpad + c] = r;
+    for (long long i = k + 1; i < M; i++) {
+      double Lik = (S[(i + k * M) * Cpad + c] + sgn * ss * w[i * Cpad + c]) / cc;
+      S[(i + k * M) * Cpad + c] = Lik;
+      w[i * Cpad + c] = cc * w[i * Cpad + c] - ss * Lik;
+    }
+  }
+}
+
+__global__ void k_set_identity(double* S, long long C, long long M, long long Cpad) {
+  long long total = C * M * M;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long e = i / C, c = i - e * C;
+    S[e * Cpad + c] = (e % M == e / M) ? 1.0 : 0.0;
+  }
+}
+
+__global__ void k_copy_state(long long C, long long M, long long Cpad, const double* beta, const double* grad,
+                             const double* logp, double* b0, double* g0, double* l0) {
+  long long total = C * (M + 1);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long j = i / C, c = i - j * C;
+    if (j == M) l0[c] = logp[c];
+    else {
+      b0[j * Cpad + c] = beta[j * Cpad + c];
+      if (g0) g0[j * Cpad + c] = grad[j * Cpad + c];
+    }
+  }
+}
+
+__global__ void k_in_rows_to_cols(const double* in, double* out, long long C, long long M, long long Cpad, int shared_init) {
+  long long total = C * M;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long j = i / C, c = i - j * C;
+    out[j * Cpad + c] = shared_init ? in[j] : in[c * M + j];
+  }
+}
+// [rows][Cpad] x nblocks  ->  [nblocks][C][rows]
+__global__ void k_out_cols_to_rows(const double* in, double* out, long long nblocks, long long C, long long rows, long long Cpad) {
+  long long total = nblocks * C * rows;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long j = i % rows, c = (i / rows) % C, b = i / (rows * C);
+    out[i] = in[(b * rows + j) * Cpad + c];
+  }
+}
+__global__ void k_div(double* p, long long n, double d) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] /= d;
+}
+
+inline unsigned gridc(long long n, int block = 128) { return (unsigned)std::max<long long>(1, (n + block - 1) / block); }
+inline unsigned gride(long long n) { return (unsigned)std::max<long long>(1, std::min<long long>((n + 255) / 256, 148LL * 32)); }
+
+struct Run {
+  smc_model_s* m;
+  const smc_sampler_config* cfg;
+  smc_run_output* out;
+  long long C, M, Cpad, samples;
+  Arena A;
+  RngSrc rng;
+  Recorder R;
+  double *b0 = nullptr, *g0 = nullptr, *l0 = nullptr;
+  unsigned long long* nleap = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  int64_t launches0 = 0;
+};
+
+int run_setup(Run& r, const double* init, bool need_grad, long long nu) {
+  smc_model_s* m = r.m;
+  const smc_sampler_config* cfg = r.cfg;
+  if (!m->finalized) { smc_set_error("model is not finalized"); return SMC_ERR_INVALID; }
+  if (r.C < 1 || r.C > m->Cmax) { smc_set_error("chains %lld outside [1, %lld]", r.C, (long long)m->Cmax); return SMC_ERR_INVALID; }
+  if (cfg->burnin < 0) { smc_set_error("Burnin rounds (%lld) should be >= 0", (long long)cfg->burnin); return SMC_ERR_INVALID; }   // src/samplers.jl:325
+  if (cfg->steps <= cfg->burnin) { smc_set_error("Steps (%lld) should be > to burnin (%lld)", (long long)cfg->steps, (long long)cfg->burnin); return SMC_ERR_INVALID; }  // :326
+  cudaSetDevice(m->ctx->device);
+  cudaStream_t st = m->ctx->stream;
+  r.M = m->M; r.Cpad = m->Cpad; r.samples = cfg->steps - cfg->burnin;
+  long long C = r.C, M = r.M, Cpad = r.Cpad;
+  r.launches0 = m->ctx->launches;
+  SMC_TRY(r.A.alloc(&r.b0, M * Cpad));
+  SMC_TRY(r.A.alloc(&r.g0, M * Cpad));
+  SMC_TRY(r.A.alloc(&r.l0, Cpad));
+  SMC_TRY(r.A.alloc(&r.nleap, Cpad));
+  SMC_CUDA(cudaMemsetAsync(r.nleap, 0, Cpad * sizeof(unsigned long long), st));
+  r.R.burnin = cfg->burnin;
+  r.R.draws = r.R.loglik = r.R.accept = nullptr;
+  if (cfg->store_draws && r.out->draws) SMC_TRY(r.A.alloc(&r.R.draws, r.samples * M * Cpad));
+  if (r.out->loglik) SMC_TRY(r.A.alloc(&r.R.loglik, r.samples * Cpad));
+  if (r.out->accept) SMC_TRY(r.A.alloc(&r.R.accept, r.samples * Cpad));
+  SMC_TRY(r.A.alloc(&r.R.mean, M * Cpad));
+  SMC_TRY(r.A.alloc(&r.R.m2, M * Cpad));
+  SMC_TRY(r.A.alloc(&r.R.nacc, Cpad));
+  SMC_CUDA(cudaMemsetAsync(r.R.mean, 0, M * Cpad * sizeof(double), st));
+  SMC_CUDA(cudaMemsetAsync(r.R.m2, 0, M * Cpad * sizeof(double), st));
+  SMC_CUDA(cudaMemsetAsync(r.R.nacc, 0, Cpad * sizeof(double), st));
+  r.rng.seed = cfg->seed; r.rng.chain_offset = cfg->chain_offset; r.rng.inj_n = nullptr; r.rng.inj_u = nullptr; r.rng.nu = nu;
+  if (cfg->inject_normals) {
+    double* d;
+    size_t n = (size_t)cfg->steps * C * M;
+    SMC_TRY(r.A.alloc(&d, n));
+    SMC_CUDA(cudaMemcpyAsync(d, cfg->inject_normals, n * sizeof(double), cudaMemcpyHostToDevice, st));
+    r.rng.inj_n = d;
+  }
+  if (cfg->inject_uniforms) {
+    if (cfg->inject_uniforms_per_step < nu) { smc_set_error("inject_uniforms_per_step must be >= %lld for this sampler", nu); return SMC_ERR_INVALID; }
+    r.rng.nu = cfg->inject_uniforms_per_step;
+    double* d;
+    size_t n = (size_t)cfg->steps * C * r.rng.nu;
+    SMC_TRY(r.A.alloc(&d, n));
+    SMC_CUDA(cudaMemcpyAsync(d, cfg->inject_uniforms, n * sizeof(double), cudaMemcpyHostToDevice, st));
+    r.rng.inj_u = d;
+  }
+  // initial state
+  double* stage;
+  size_t ninit = cfg->init_per_chain ? (size_t)C * M : (size_t)M;
+  SMC_TRY(r.A.alloc(&stage, ninit));
+  SMC_CUDA(cudaMemcpyAsync(stage, init, ninit * sizeof(double), cudaMemcpyHostToDevice, st));
+  k_in_rows_to_cols<<<gride(C * M), 256, 0, st>>>(stage, m->beta, C, M, Cpad, cfg->init_per_chain ? 0 : 1);
+  m->ctx->launches++;
+  SMC_TRY(smc_model_eval_device(m, C, need_grad));  // calc!(state0, ll_func), src/samplers.jl:142
+  k_copy_state<<<gride(C * (M + 1)), 256, 0, st>>>(C, M, Cpad, m->beta, need_grad ? m->grad : nullptr, m->logp, r.b0,
+                                                  need_grad ? r.g0 : nullptr, r.l0);
+  m->ctx->launches++;
+  // assert(isfinite(state0.llik), "Initial values out of model support, try other values")  src/samplers.jl:143
+  std::vector<double> l0h(C);
+  SMC_CUDA(cudaMemcpyAsync(l0h.data(), r.l0, C * sizeof(double), cudaMemcpyDeviceToHost, st));
+  SMC_CUDA(cudaStreamSynchronize(st));
+  for (long long c = 0; c < C; c++)
+    if (!isfinite(l0h[c])) {
+      smc_set_error("Initial values out of model support, try other values (chain %lld, log-density %g)", c, l0h[c]);
+      return SMC_ERR_SUPPORT;
+    }
+  SMC_CUDA(cudaEventCreate(&r.e0));
+  SMC_CUDA(cudaEventCreate(&r.e1));
+  SMC_CUDA(cudaEventRecord(r.e0, st));
+  return SMC_OK;
+}
+
+int copy_out_blocks(Run& r, const double* dev, double* host, long long nblocks, long long rows) {
+  // dev [nblocks][rows][Cpad] -> host [nblocks][C][rows], staged in chunks
+  if (!host || !dev) return SMC_OK;
+  cudaStream_t st = r.m->ctx->stream;
+  long long per = r.C * rows;
+  long long chunk = std::max<long long>(1, std::min<long long>(nblocks, (64LL << 20) / std::max<long long>(per, 1)));
+  double* stage;
+  Arena local;
+  SMC_TRY(local.alloc(&stage, chunk * per));
+  for (long long b = 0; b < nblocks; b += chunk) {
+    long long nb = std::min(chunk, nblocks - b);
+    k_out_cols_to_rows<<<gride(nb * per), 256, 0, st>>>(dev + b * rows * r.Cpad, stage, nb, r.C, rows, r.Cpad);
+    r.m->ctx->launches++;
+    SMC_CUDA(cudaMemcpyAsync(host + b * per, stage, nb * per * sizeof(double), cudaMemcpyDeviceToHost, st));
+    SMC_CUDA(cudaStreamSynchronize(st));
+  }
+  return SMC_OK;
+}
+
+int run_finish(Run& r, int64_t n_evals) {
+  smc_model_s* m = r.m;
+  cudaStream_t st = m->ctx->stream;
+  SMC_CUDA(cudaEventRecord(r.e1, st));
+  SMC_CUDA(cudaEventSynchronize(r.e1));
+  float ms = 0.f;
+  SMC_CUDA(cudaEventElapsedTime(&ms, r.e0, r.e1));
+  SMC_CUDA(cudaGetLastError());
+  r.out->device_ms = ms;
+  r.out->n_evals = n_evals;
+  cudaEventDestroy(r.e0);
+  cudaEventDestroy(r.e1);
+  std::vector<unsigned long long> nl(r.C);
+  SMC_CUDA(cudaMemcpyAsync(nl.data(), r.nleap, r.C * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  SMC_CUDA(cudaStreamSynchronize(st));
+  unsigned long long tot = 0;
+  for (auto x : nl) tot += x;
+  r.out->n_leapfrogs = (int64_t)tot;
+  SMC_TRY(copy_out_blocks(r, r.R.draws, r.out->draws, r.samples, r.M));
+  SMC_TRY(copy_out_blocks(r, r.R.loglik, r.out->loglik, r.samples, 1));
+  SMC_TRY(copy_out_blocks(r, r.R.accept, r.out->accept, r.samples, 1));
+  SMC_TRY(copy_out_blocks(r, r.b0, r.out->final_state, 1, r.M));
+  SMC_TRY(copy_out_blocks(r, r.R.mean, r.out->mean, 1, r.M));
+  SMC_TRY(copy_out_blocks(r, r.R.m2, r.out->m2, 1, r.M));
+  if (r.out->accept_rate) {
+    k_div<<<gride(r.C), 256, 0, st>>>(r.R.nacc, r.C, (double)r.samples);
+    m->ctx->launches++;
+    SMC_TRY(copy_out_blocks(r, r.R.nacc, r.out->accept_rate, 1, 1));
+  }
+  r.out->n_kernel_launches = m->ctx->launches - r.launches0;
+  return SMC_OK;
+}
+
+}  // namespace
+
+extern "C" int smc_hmc_run(smc_model_t m, const smc_sampler_config* cfg, const double* init, int64_t C, smc_run_output* out) {
+  if (!m || !cfg || !init || !out) { smc_set_error("smc_hmc_run: NULL argument"); return SMC_ERR_INVALID; }
+  if (cfg->isteps < 1) { smc_set_error("smc_hmc_run: isteps must be >= 1"); return SMC_ERR_INVALID; }
+  Run r;
+  r.m = m; r.cfg = cfg; r.out = out; r.C = C;
+  SMC_TRY(run_setup(r, init, true, 1));
+  cudaStream_t st = m->ctx->stream;
+  long long M = r.M, Cpad = r.Cpad;
+  double *v, *H0, *H;
+  int* active;
+  SMC_TRY(r.A.alloc(&v, M * Cpad));
+  SMC_TRY(r.A.alloc(&H0, Cpad));
+  SMC_TRY(r.A.alloc(&H, Cpad));
+  SMC_TRY(r.A.alloc(&active, Cpad));
+  int64_t evals = 1;
+  for (long long i = 0; i < cfg->steps; i++) {
+    k_hmc_begin<<<gridc(C), 128, 0, st>>>(r.rng, i, C, M, Cpad, r.b0, r.g0, r.l0, m->beta, m->grad, m->logp, v, H0, H, active);
+    for (long long j = 0; j < cfg->isteps; j++) {
+      k_leapfrog_pre<<<gride(C * M), 256, 0, st>>>(C, M, Cpad, cfg->stepsize, active, m->beta, m->grad, v);
+      m->ctx->launches += 1;
+      SMC_TRY(smc_model_eval_device(m, C, true));
+      k_leapfrog_post<<<gridc(C), 128, 0, st>>>(C, M, Cpad, cfg->stepsize, active, m->grad, m->logp, v, H, r.nleap);
+      m->ctx->launches += 1;
+      evals++;
+    }
+    k_hmc_accept<<<gridc(C), 128, 0, st>>>(r.rng, i, C, M, Cpad, m->beta, m->grad, m->logp, H, H0, r.b0, r.g0, r.l0, r.R);
+    m->ctx->launches += 2;
+  }
+  return run_finish(r, evals);
+}
+
+extern "C" int smc_rwm_run(smc_model_t m, const smc_sampler_config* cfg, const double* init, int64_t C, smc_run_output* out) {
+  if (!m || !cfg || !init || !out) { smc_set_error("smc_rwm_run: NULL argument"); return SMC_ERR_INVALID; }
+  Run r;
+  r.m = m; r.cfg = cfg; r.out = out; r.C = C;
+  SMC_TRY(run_setup(r, init, false, 1));
+  cudaStream_t st = m->ctx->stream;
+  long long M = r.M, Cpad = r.Cpad;
+  double *S, *jump, *w;
+  SMC_TRY(r.A.alloc(&S, M * M * Cpad));
+  SMC_TRY(r.A.alloc(&jump, M * Cpad));
+  SMC_TRY(r.A.alloc(&w, M * Cpad));
+  k_set_identity<<<gride(C * M * M), 256, 0, st>>>(S, C, M, Cpad);  // S = eye(nparams), src/samplers.jl:89
+  m->ctx->launches++;
+  int64_t evals = 1;
+  for (long long i = 0; i < cfg->steps; i++) {
+    k_rwm_propose<<<gridc(C), 128, 0, st>>>(r.rng, i, C, M, Cpad, r.b0, S, jump, m->beta);
+    SMC_TRY(smc_model_eval_device(m, C, false));
+    evals++;
+    k_rwm_accept<<<gridc(C), 128, 0, st>>>(r.rng, i, C, M, Cpad, m->beta, m->logp, r.b0, r.l0, S, jump, w, r.R);
+    m->ctx->launches += 2;
+  }
+  return run_finish(r, evals);
+}
+
+// ---------------------------------------------------------------------------------------------- RNG test hooks
+namespace {
+__global__ void k_philox_normals(unsigned long long seed, long long chain, long long step, long long n, double* out) {
+  long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (2 * b >= n) return;
+  double z0, z1;
+  smc_normal_pair(seed, (unsigned long long)chain, (unsigned long long)step, (uint32_t)b, z0, z1);
+  out[2 * b] = z0;
+  if (2 * b + 1 < n) out[2 * b + 1] = z1;
+}
+__global__ void k_philox_uniforms(unsigned long long seed, long long chain, long long step, long long n, double* out) {
+  long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) out[k] = smc_uniform(seed, (unsigned long long)chain, (unsigned long long)step, (uint32_t)k);
+}
+}  // namespace
+
+extern "C" int smc_philox_normals(uint64_t seed, int64_t chain, int64_t step, int32_t stream, int64_t n, double* out) {
+  (void)stream;
+  if (!out || n < 0) return SMC_ERR_INVALID;
+  double* d = nullptr;
+  SMC_CUDA(cudaMalloc(&d, std::max<int64_t>(n, 1) * sizeof(double)));
+  k_philox_normals<<<(unsigned)((n / 2 + 128) / 128), 128>>>(seed, chain, step, n, d);
+  cudaError_t e = cudaMemcpy(out, d, n * sizeof(double), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  SMC_CUDA(e);
+  return SMC_OK;
+}
+extern "C" int smc_philox_uniforms(uint64_t seed, int64_t chain, int64_t step, int32_t stream, int64_t n, double* out) {
+  (void)stream;
+  if (!out || n < 0) return SMC_ERR_INVALID;
+  double* d = nullptr;
+  SMC_CUDA(cudaMalloc(&d, std::max<int64_t>(n, 1) * sizeof(double)));
+  k_philox_uniforms<<<(unsigned)((n + 127) / 128), 128>>>(seed, chain, step, n, d);
+  cudaError_t e = cudaMemcpy(out, d, n * sizeof(double), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  SMC_CUDA(e);
+  return SMC_OK;
+}
+
+// NUTS lives in nuts.cu

@@ -1,0 +1,692 @@
+// libsimplemcmc_cuda.so core: contexts, tape loading, register allocation, the generic statement
+// executor (one launch per 3-address statement, every chain in lockstep) and smc_eval.
+// Reference path replaced: the generated closure of /root/reference/src/parsing.jl:409-492.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+#include "smc_internal.h"
+#include "dists.cuh"
+
+static thread_local char g_err[1024] = "";
+void smc_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+extern "C" const char* smc_last_error(void) { return g_err; }
+extern "C" int smc_abi_version(void) { return SMC_ABI_VERSION; }
+
+// ------------------------------------------------------------------------------------------ context
+extern "C" int smc_ctx_create(int device, smc_ctx_t* out) {
+  if (!out) { smc_set_error("smc_ctx_create: out is NULL"); return SMC_ERR_INVALID; }
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    smc_set_error("smc_ctx_create: no CUDA device (%s); libsimplemcmc_cuda has no CPU fallback", cudaGetErrorString(e));
+    return SMC_ERR_CUDA;
+  }
+  if (device < 0 || device >= n) { smc_set_error("smc_ctx_create: device %d out of range (%d devices)", device, n); return SMC_ERR_INVALID; }
+  SMC_CUDA(cudaSetDevice(device));
+  smc_ctx_s* c = new smc_ctx_s();
+  c->device = device;
+  cudaDeviceProp p;
+  SMC_CUDA(cudaGetDeviceProperties(&p, device));
+  c->sm_count = p.multiProcessorCount;
+  SMC_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  *out = c;
+  return SMC_OK;
+}
+
+int smc_comm_destroy(smc_ctx_s* c);  // smc_comm.cu
+extern "C" int smc_ctx_destroy(smc_ctx_t c) {
+  if (!c) return SMC_OK;
+  cudaSetDevice(c->device);
+  smc_comm_destroy(c);
+  if (c->flush_buf) cudaFree(c->flush_buf);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return SMC_OK;
+}
+
+// ------------------------------------------------------------------------------------------ tape loading
+static int64_t reg_numel(const smc_tape_reg& r) { return (int64_t)std::max(1u, r.rows) * (int64_t)std::max(1u, r.cols); }
+
+extern "C" int smc_model_compile(smc_ctx_t ctx, const void* tape, size_t nbytes, smc_model_t* out) {
+  if (!ctx || !tape || !out) { smc_set_error("smc_model_compile: NULL argument"); return SMC_ERR_INVALID; }
+  const uint8_t* p = (const uint8_t*)tape;
+  const uint8_t* end = p + nbytes;
+  if (nbytes < sizeof(smc_tape_header)) { smc_set_error("tape: truncated header"); return SMC_ERR_INVALID; }
+  smc_model_s* m = new smc_model_s();
+  m->ctx = ctx;
+  memcpy(&m->hdr, p, sizeof(smc_tape_header));
+  p += sizeof(smc_tape_header);
+  const smc_tape_header& h = m->hdr;
+  if (h.magic != SMC_TAPE_MAGIC || h.version != SMC_TAPE_VERSION) {
+    smc_set_error("tape: bad magic/version (%08x v%u, expected v%u)", h.magic, h.version, SMC_TAPE_VERSION);
+    delete m;
+    return SMC_ERR_INVALID;
+  }
+  size_t need = (size_t)h.n_regs * sizeof(smc_tape_reg) + (size_t)h.n_stmts * sizeof(smc_tape_stmt) +
+                (size_t)h.n_data * sizeof(smc_tape_data);
+  if ((size_t)(end - p) < need) { smc_set_error("tape: truncated tables"); delete m; return SMC_ERR_INVALID; }
+  m->regs.resize(h.n_regs);
+  for (uint32_t i = 0; i < h.n_regs; i++) {
+    memcpy(&m->regs[i].d, p, sizeof(smc_tape_reg));
+    p += sizeof(smc_tape_reg);
+    m->regs[i].numel = reg_numel(m->regs[i].d);
+    if (m->regs[i].d.kind > SMC_REG_GRAD) { smc_set_error("tape: register %u has unknown kind", i); delete m; return SMC_ERR_INVALID; }
+  }
+  m->stmts.resize(h.n_stmts);
+  for (uint32_t i = 0; i < h.n_stmts; i++) {
+    memcpy(&m->stmts[i], p, sizeof(smc_tape_stmt));
+    p += sizeof(smc_tape_stmt);
+    const smc_tape_stmt& s = m->stmts[i];
+    bool ok = s.dst < h.n_regs && s.nsrc <= 4;
+    for (uint32_t k = 0; ok && k < s.nsrc; k++) ok = s.src[k] < h.n_regs;
+    if (s.op == SMC_OP_GLM) ok = ok && s.aux2 < h.n_regs && s.nsrc == 3;
+    if (!ok) { smc_set_error("tape: statement %u references a register out of range", i); delete m; return SMC_ERR_INVALID; }
+    uint32_t dk = m->regs[s.dst].d.kind;
+    if (dk == SMC_REG_HDR) m->hdr_stmts.push_back((int)i);
+    else if (dk == SMC_REG_CHAIN || dk == SMC_REG_GRAD) m->body_stmts.push_back((int)i);
+    else { smc_set_error("tape: statement %u writes a read-only register", i); delete m; return SMC_ERR_INVALID; }
+  }
+  m->data.resize(h.n_data);
+  for (uint32_t i = 0; i < h.n_data; i++) {
+    smc_tape_data d;
+    memcpy(&d, p, sizeof(d));
+    p += sizeof(d);
+    d.name[sizeof(d.name) - 1] = 0;
+    m->data[i].name = d.name;
+    m->data[i].rows = d.rows;
+    m->data[i].cols = d.cols;
+  }
+  for (uint32_t i = 0; i < h.n_regs; i++)
+    if (m->regs[i].d.kind == SMC_REG_DATA) {
+      int64_t slot = m->regs[i].d.aux;
+      if (slot < 0 || slot >= (int64_t)h.n_data) { smc_set_error("tape: data register %u has a bad slot", i); delete m; return SMC_ERR_INVALID; }
+      m->data[slot].reg = (int)i;
+    }
+  cudaSetDevice(ctx->device);
+  for (uint32_t i = 0; i < h.n_idx; i++) {
+    if ((size_t)(end - p) < 8) { smc_set_error("tape: truncated index table"); delete m; return SMC_ERR_INVALID; }
+    uint32_t n;
+    memcpy(&n, p, 4);
+    p += 8;
+    size_t bytes = (size_t)((n + 1) & ~1u) * 4;
+    if ((size_t)(end - p) < bytes) { smc_set_error("tape: truncated index table"); delete m; return SMC_ERR_INVALID; }
+    int32_t* d = nullptr;
+    SMC_CUDA(cudaMalloc(&d, std::max<size_t>(bytes, 8)));
+    SMC_CUDA(cudaMemcpy(d, p, (size_t)n * 4, cudaMemcpyHostToDevice));
+    p += bytes;
+    m->idx_dev.push_back(d);
+    m->idx_len.push_back(n);
+  }
+  if (h.result_reg >= h.n_regs) { smc_set_error("tape: bad result register"); delete m; return SMC_ERR_INVALID; }
+  m->M = h.n_params;
+  *out = m;
+  return SMC_OK;
+}
+
+extern "C" int smc_model_nparams(smc_model_t m, int64_t* out) {
+  if (!m || !out) return SMC_ERR_INVALID;
+  *out = m->M;
+  return SMC_OK;
+}
+
+extern "C" int smc_model_destroy(smc_model_t m) {
+  if (!m) return SMC_OK;
+  cudaSetDevice(m->ctx->device);
+  cudaStreamSynchronize(m->ctx->stream);
+  for (auto& r : m->regs) if (r.owned && r.dev) cudaFree(r.dev);
+  for (auto d : m->idx_dev) cudaFree(d);
+  for (auto& g : m->glm) smc_glm_release(g);
+  if (m->beta) cudaFree(m->beta);
+  if (m->grad) cudaFree(m->grad);
+  if (m->logp) cudaFree(m->logp);
+  if (m->bad) cudaFree(m->bad);
+  if (m->scratch) cudaFree(m->scratch);
+  if (m->host_stage) cudaFreeHost(m->host_stage);
+  if (m->ev0) cudaEventDestroy(m->ev0);
+  if (m->ev1) cudaEventDestroy(m->ev1);
+  delete m;
+  return SMC_OK;
+}
+
+extern "C" int smc_model_bind_data(smc_model_t m, const char* name, const double* host, const int64_t* dims, int ndims) {
+  if (!m || !name || !host || ndims < 0 || ndims > 2) { smc_set_error("smc_model_bind_data: bad argument"); return SMC_ERR_INVALID; }
+  cudaSetDevice(m->ctx->device);
+  for (auto& d : m->data) {
+    if (d.name != name) continue;
+    int64_t rows = ndims >= 1 ? dims[0] : 1, cols = ndims >= 2 ? dims[1] : 1;
+    if (rows * cols != d.rows * d.cols) {
+      smc_set_error("smc_model_bind_data: '%s' has %lld elements, the tape was compiled for %lld", name,
+                    (long long)(rows * cols), (long long)(d.rows * d.cols));
+      return SMC_ERR_INVALID;
+    }
+    SmcReg& r = m->regs[d.reg];
+    if (!r.dev) { SMC_CUDA(cudaMalloc(&r.dev, std::max<int64_t>(r.numel, 1) * sizeof(double))); r.owned = true; }
+    SMC_CUDA(cudaMemcpyAsync(r.dev, host, r.numel * sizeof(double), cudaMemcpyHostToDevice, m->ctx->stream));
+    SMC_CUDA(cudaStreamSynchronize(m->ctx->stream));
+    d.bound = true;
+    m->finalized = false;
+    return SMC_OK;
+  }
+  smc_set_error("smc_model_bind_data: the tape has no external variable named '%s'", name);
+  return SMC_ERR_INVALID;
+}
+
+// ------------------------------------------------------------------------------------------ generic executor
+struct Opd {
+  const double* p;
+  long long se;  // element stride
+  int sc;        // chain stride (0 = shared by all chains)
+  int is_imm;
+  double imm;
+};
+struct Dst {
+  double* p;
+  long long se;
+  int sc;
+};
+struct EwArgs {
+  int op, dist, darg, nsrc, acc;
+  Opd s[4];
+  Dst d;
+  long long n, C;
+  int* bad;
+  int bad_stride;  // 1: per chain, 0: header phase
+};
+
+__device__ __forceinline__ double opd_ld(const Opd& o, long long e, long long c) {
+  return o.is_imm ? o.imm : __ldg(o.p + e * o.se + c * o.sc);
+}
+
+__device__ __forceinline__ double smc_apply(int op, int dist, int k, double a, double b, double c) {
+  switch (op) {
+    case SMC_OP_COPY: return a;
+    case SMC_OP_NEG: return -a;
+    case SMC_OP_EXP: return exp(a);
+    case SMC_OP_LOG: return log(a);
+    case SMC_OP_SIN: return sin(a);
+    case SMC_OP_COS: return cos(a);
+    case SMC_OP_ABS: return fabs(a);
+    case SMC_OP_SIGN: return a > 0.0 ? 1.0 : (a < 0.0 ? -1.0 : a);
+    case SMC_OP_DIGAMMA: return smc_digamma(a);
+    case SMC_OP_ZERO: return 0.0;
+    case SMC_OP_SQRT: return sqrt(a);
+    case SMC_OP_ADD: return a + b;
+    case SMC_OP_SUB: return a - b;
+    case SMC_OP_MUL: return a * b;
+    case SMC_OP_DIV: return a / b;
+    case SMC_OP_POW: return pow(a, b);
+    case SMC_OP_MAX: return fmax(a, b);
+    case SMC_OP_MIN: return fmin(a, b);
+    case SMC_OP_GT: return a > b ? 1.0 : 0.0;
+    case SMC_OP_LT: return a < b ? 1.0 : 0.0;
+    case SMC_OP_GE: return a >= b ? 1.0 : 0.0;
+    case SMC_OP_LE: return a <= b ? 1.0 : 0.0;
+    case SMC_OP_EQ: return a == b ? 1.0 : 0.0;
+    case SMC_OP_LOGPDF: return smc_logpdf(dist, a, b, c);
+    case SMC_OP_DLOGPDF: return smc_dlogpdf(dist, k, a, b, c);
+  }
+  return nan("");
+}
+
+__device__ __forceinline__ double ew_value(const EwArgs& a, long long e, long long c) {
+  double x0 = a.nsrc > 0 ? opd_ld(a.s[0], e, c) : 0.0;
+  double x1 = a.nsrc > 1 ? opd_ld(a.s[1], e, c) : 0.0;
+  double x2 = a.nsrc > 2 ? opd_ld(a.s[2], e, c) : 0.0;
+  double v = smc_apply(a.op, a.dist, a.darg, x0, x1, x2);
+  if (a.op == SMC_OP_LOGPDF && (v == -INFINITY || isnan(v))) {  // "give up eval", src/distribs.jl:69-70
+    a.bad[c * a.bad_stride] = 1;
+    v = 0.0;
+  }
+  return v;
+}
+
+__global__ void __launch_bounds__(256) k_elementwise(EwArgs a) {
+  long long total = a.n * a.C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long e = i / a.C, c = i - e * a.C;
+    double v = ew_value(a, e, c);
+    double* q = a.d.p + e * a.d.se + c * a.d.sc;
+    *q = a.acc ? (*q + v) : v;
+  }
+}
+
+// chain-parallel reduction: thread = (chain, split); sums its element range left to right
+__global__ void __launch_bounds__(256) k_reduce_chains(EwArgs a, double* partial, long long chunk) {
+  long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= a.C) return;
+  long long s = blockIdx.y, e0 = s * chunk, e1 = min(a.n, e0 + chunk);
+  double acc = 0.0;
+  for (long long e = e0; e < e1; e++) acc += ew_value(a, e, c);
+  partial[s * a.C + c] = acc;
+}
+
+// element-parallel reduction: block = (split, chain)
+__global__ void __launch_bounds__(256) k_reduce_elems(EwArgs a, double* partial, long long chunk) {
+  long long c = blockIdx.y, s = blockIdx.x, e0 = s * chunk, e1 = min(a.n, e0 + chunk);
+  double acc = 0.0;
+  for (long long e = e0 + threadIdx.x; e < e1; e += blockDim.x) acc += ew_value(a, e, c);
+  __shared__ double sh[8];
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += sh[w];
+    partial[s * a.C + c] = t;
+  }
+}
+
+// dst[o][c] (=|+=) sum_s partial[s][o][c], fixed order -> deterministic
+__global__ void k_reduce_final(const double* partial, long long S, long long outn, long long C, Dst d, int acc) {
+  long long total = outn * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long o = i / C, c = i - o * C;
+    double t = 0.0;
+    for (long long s = 0; s < S; s++) t += partial[(s * outn + o) * C + c];
+    double* q = d.p + o * d.se + c * d.sc;
+    *q = acc ? (*q + t) : t;
+  }
+}
+
+struct MmArgs {
+  Opd A, B;
+  long long ar, br;  // stored leading dimension (rows) of A and B
+  int tA, tB;
+  long long r, k, n, C;
+};
+// out(i,j) = sum_l A(i,l) B(l,j), column major, split over l; partial[s][i + j*r][c]
+__global__ void __launch_bounds__(256) k_matmul(MmArgs a, double* partial, long long chunk) {
+  long long total = a.r * a.n * a.C;
+  long long s = blockIdx.y, l0 = s * chunk, l1 = min(a.k, l0 + chunk);
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    long long o = idx / a.C, c = idx - o * a.C;
+    long long i = o % a.r, j = o / a.r;
+    double acc = 0.0;
+    for (long long l = l0; l < l1; l++) {
+      long long ea = a.tA ? (l + i * a.ar) : (i + l * a.ar);
+      long long eb = a.tB ? (j + l * a.br) : (l + j * a.br);
+      acc += opd_ld(a.A, ea, c) * opd_ld(a.B, eb, c);
+    }
+    partial[(s * a.r * a.n + o) * a.C + c] = acc;
+  }
+}
+
+__global__ void k_transpose(Opd src, Dst d, long long rows, long long cols, long long C, int acc) {
+  long long total = rows * cols * C;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    long long e = idx / C, c = idx - e * C;
+    long long i = e % rows, j = e / rows;  // element (i,j) of src -> (j,i) of dst
+    double v = opd_ld(src, e, c);
+    double* q = d.p + (j + i * cols) * d.se + c * d.sc;
+    *q = acc ? (*q + v) : v;
+  }
+}
+
+__global__ void k_gather(Opd src, Dst d, const int32_t* idx, long long n, long long C, int acc) {
+  long long total = n * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long e = i / C, c = i - e * C;
+    double v = opd_ld(src, idx[e], c);
+    double* q = d.p + e * d.se + c * d.sc;
+    *q = acc ? (*q + v) : v;
+  }
+}
+
+// sequential over the index list per chain: repeated indices resolve in list order (deterministic)
+__global__ void k_scatter(Opd src, Dst d, const int32_t* idx, long long n, long long C, int add) {
+  long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  for (long long e = 0; e < n; e++) {
+    double v = opd_ld(src, e, c);
+    double* q = d.p + (long long)idx[e] * d.se + c * d.sc;
+    *q = add ? (*q + v) : v;
+  }
+}
+
+__global__ void k_fill(double* p, long long n, double v) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
+}
+__global__ void k_fill_int(int* p, long long n, int v) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
+}
+
+// logp[c] = bad ? -inf : result ; grad[:,c] = bad ? 0 : grad   (src/parsing.jl:465-467)
+__global__ void k_finish_eval(const double* result, long long rse, int rsc, const int* bad, double* logp, double* grad,
+                              long long M, long long C, long long Cpad, int with_grad) {
+  long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  int b = bad[c];
+  double r = result[c * rsc];
+  logp[c] = b ? -INFINITY : r;
+  if (b && with_grad)
+    for (long long j = 0; j < M; j++) grad[j * Cpad + c] = 0.0;
+}
+
+// [C][M] row major  <->  [M][Cpad]
+__global__ void k_rows_to_cols(const double* in, double* out, long long C, long long M, long long Cpad, int shared_init) {
+  long long total = C * M;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long j = i / C, c = i - j * C;
+    out[j * Cpad + c] = shared_init ? in[j] : in[c * M + j];
+  }
+}
+__global__ void k_cols_to_rows(const double* in, double* out, long long C, long long M, long long Cpad) {
+  long long total = C * M;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long c = i / M, j = i - c * M;
+    out[i] = in[j * Cpad + c];
+  }
+}
+
+static inline unsigned grid_for(long long total, int block = 256, long long cap = 148LL * 32) {
+  long long g = (total + block - 1) / block;
+  return (unsigned)std::max<long long>(1, std::min<long long>(g, cap));
+}
+
+static int scratch_reserve(smc_model_s* m, int64_t doubles) {
+  if (doubles <= m->scratch_cap) return SMC_OK;
+  if (m->scratch) cudaFree(m->scratch);
+  m->scratch = nullptr;
+  m->scratch_cap = 0;
+  SMC_CUDA(cudaMalloc(&m->scratch, doubles * sizeof(double)));
+  m->scratch_cap = doubles;
+  return SMC_OK;
+}
+
+int smc_stage_reserve(smc_model_s* m, int64_t doubles) {
+  if (doubles <= m->host_stage_cap) return SMC_OK;
+  if (m->host_stage) cudaFreeHost(m->host_stage);
+  m->host_stage = nullptr;
+  m->host_stage_cap = 0;
+  SMC_CUDA(cudaMallocHost(&m->host_stage, doubles * sizeof(double)));
+  m->host_stage_cap = doubles;
+  return SMC_OK;
+}
+
+static Opd make_opd(const smc_model_s* m, uint32_t r, bool header) {
+  const SmcReg& g = m->regs[r];
+  Opd o;
+  o.p = nullptr; o.se = 0; o.sc = 0; o.is_imm = 0; o.imm = 0.0;
+  switch (g.d.kind) {
+    case SMC_REG_IMM: o.is_imm = 1; o.imm = g.d.imm; break;
+    case SMC_REG_DATA:
+    case SMC_REG_HDR: o.p = g.dev; o.se = g.numel > 1 ? 1 : 0; break;
+    case SMC_REG_CHAIN: o.p = g.dev; o.se = g.numel > 1 ? m->Cpad : 0; o.sc = 1; break;
+    case SMC_REG_PARAM: o.p = m->beta + g.d.aux * m->Cpad; o.se = g.numel > 1 ? m->Cpad : 0; o.sc = 1; break;
+    case SMC_REG_GRAD: o.p = m->grad + g.d.aux * m->Cpad; o.se = g.numel > 1 ? m->Cpad : 0; o.sc = 1; break;
+  }
+  (void)header;
+  return o;
+}
+static Dst make_dst(const smc_model_s* m, uint32_t r) {
+  Opd o = make_opd(m, r, false);
+  Dst d;
+  d.p = const_cast<double*>(o.p);
+  d.se = o.se;
+  d.sc = o.sc;
+  // a scalar destination still needs a valid element stride of 0 and chain stride as computed
+  return d;
+}
+
+static int run_statement(smc_model_s* m, const smc_tape_stmt& s, int64_t C, bool header) {
+  cudaStream_t st = m->ctx->stream;
+  const SmcReg& dreg = m->regs[s.dst];
+  Dst d = make_dst(m, s.dst);
+  int acc = (s.flags & SMC_F_ACC) ? 1 : 0;
+  int* bad = header ? (m->bad + m->Cpad) : m->bad;  // slot Cpad = header flag
+  switch (s.op) {
+    case SMC_OP_MATMUL: {
+      MmArgs a;
+      a.A = make_opd(m, s.src[0], header);
+      a.B = make_opd(m, s.src[1], header);
+      a.tA = (s.flags & SMC_F_TRANS_A) ? 1 : 0;
+      a.tB = (s.flags & SMC_F_TRANS_B) ? 1 : 0;
+      a.r = s.aux0; a.k = s.aux1; a.n = (long long)s.imm; a.C = C;
+      a.ar = a.tA ? a.k : a.r;
+      a.br = a.tB ? a.n : a.k;
+      // element strides of the operands are per flat element: fold them in by scaling se (already 1 or Cpad)
+      long long outn = a.r * a.n;
+      long long S = 1;
+      long long par = outn * C;
+      if (par < 148LL * 512 && a.k >= 256) S = std::min<long long>((148LL * 512 + par - 1) / par, (a.k + 63) / 64);
+      long long chunk = (a.k + S - 1) / S;
+      SMC_TRY(scratch_reserve(m, S * outn * C));
+      dim3 grid(grid_for(par), (unsigned)S);
+      k_matmul<<<grid, 256, 0, st>>>(a, m->scratch, chunk);
+      k_reduce_final<<<grid_for(par), 256, 0, st>>>(m->scratch, S, outn, C, d, acc);
+      m->ctx->launches += 2;
+      break;
+    }
+    case SMC_OP_TRANSPOSE: {
+      Opd src = make_opd(m, s.src[0], header);
+      long long rows = s.aux0, cols = s.aux1;
+      k_transpose<<<grid_for(rows * cols * C), 256, 0, st>>>(src, d, rows, cols, C, acc);
+      m->ctx->launches++;
+      break;
+    }
+    case SMC_OP_GATHER: {
+      Opd src = make_opd(m, s.src[0], header);
+      long long n = m->idx_len[s.aux0];
+      k_gather<<<grid_for(n * C), 256, 0, st>>>(src, d, m->idx_dev[s.aux0], n, C, acc);
+      m->ctx->launches++;
+      break;
+    }
+    case SMC_OP_SCATTER_SET:
+    case SMC_OP_SCATTER_ADD: {
+      Opd src = make_opd(m, s.src[0], header);
+      long long n = m->idx_len[s.aux0];
+      k_scatter<<<(unsigned)((C + 127) / 128), 128, 0, st>>>(src, d, m->idx_dev[s.aux0], n, C, s.op == SMC_OP_SCATTER_ADD);
+      m->ctx->launches++;
+      break;
+    }
+    case SMC_OP_GLM: {
+      for (auto& g : m->glm)
+        if (&m->stmts[g.stmt] == &s) return smc_glm_launch(m, g, C);
+      smc_set_error("internal: GLM statement without a plan");
+      return SMC_ERR_INVALID;
+    }
+    default: {
+      EwArgs a;
+      a.op = s.op; a.dist = s.aux0; a.darg = s.aux1; a.nsrc = s.nsrc; a.acc = acc;
+      long long nsrc_el = 1;
+      for (uint32_t k = 0; k < s.nsrc; k++) {
+        a.s[k] = make_opd(m, s.src[k], header);
+        nsrc_el = std::max<long long>(nsrc_el, m->regs[s.src[k]].numel);
+      }
+      for (uint32_t k = s.nsrc; k < 4; k++) a.s[k] = a.s[0];
+      if (s.op == SMC_OP_LOGPDF) nsrc_el = s.aux1;  // length of the first array argument (src/distribs.jl:99)
+      long long n = nsrc_el;
+      a.d = d; a.C = C; a.bad = bad; a.bad_stride = header ? 0 : 1;
+      if (dreg.numel == nsrc_el || nsrc_el == 1) {
+        // elementwise; scalar operands (and a scalar result of the operands) broadcast over the destination
+        n = dreg.numel;
+        a.n = n;
+        k_elementwise<<<grid_for(n * C), 256, 0, st>>>(a);
+        m->ctx->launches++;
+      } else if (dreg.numel == 1) {
+        a.n = n;
+        long long S;
+        if (C >= 4096 || n < 512) {
+          S = 1;
+          if (C < 148LL * 256) S = std::max<long long>(1, std::min<long long>((148LL * 256) / C, n / 32));
+          long long chunk = (n + S - 1) / S;
+          S = (n + chunk - 1) / chunk;
+          SMC_TRY(scratch_reserve(m, S * C));
+          dim3 grid((unsigned)((C + 255) / 256), (unsigned)S);
+          k_reduce_chains<<<grid, 256, 0, st>>>(a, m->scratch, chunk);
+        } else {
+          S = std::max<long long>(1, std::min<long long>((n + 2047) / 2048, std::max<long long>(1, (148LL * 16) / C)));
+          long long chunk = (n + S - 1) / S;
+          S = (n + chunk - 1) / chunk;
+          SMC_TRY(scratch_reserve(m, S * C));
+          dim3 grid((unsigned)S, (unsigned)C);
+          k_reduce_elems<<<grid, 256, 0, st>>>(a, m->scratch, chunk);
+        }
+        k_reduce_final<<<grid_for(C), 256, 0, st>>>(m->scratch, S, 1, C, d, acc);
+        m->ctx->launches += 2;
+      } else {
+        smc_set_error("tape: statement with op %u has incompatible shapes (dst %lld, operands %lld)", s.op,
+                      (long long)dreg.numel, nsrc_el);
+        return SMC_ERR_INVALID;
+      }
+    }
+  }
+  return SMC_OK;
+}
+
+extern "C" int smc_model_finalize(smc_model_t m, int64_t max_chains, int row_shard) {
+  if (!m || max_chains < 1) { smc_set_error("smc_model_finalize: bad argument"); return SMC_ERR_INVALID; }
+  cudaSetDevice(m->ctx->device);
+  for (auto& d : m->data)
+    if (!d.bound) { smc_set_error("external variable '%s' is used by the model but was never bound", d.name.c_str()); return SMC_ERR_UNBOUND; }
+  cudaStream_t st = m->ctx->stream;
+  int64_t Cpad = (max_chains + 31) / 32 * 32;
+  bool realloc_chain = (Cpad != m->Cpad);
+  m->Cmax = max_chains;
+  m->row_shard = row_shard;
+  if (realloc_chain) {
+    for (auto& r : m->regs)
+      if (r.d.kind == SMC_REG_CHAIN && r.dev) { cudaFree(r.dev); r.dev = nullptr; }
+    if (m->beta) cudaFree(m->beta);
+    if (m->grad) cudaFree(m->grad);
+    if (m->logp) cudaFree(m->logp);
+    if (m->bad) cudaFree(m->bad);
+    m->beta = m->grad = m->logp = nullptr;
+    m->bad = nullptr;
+    m->Cpad = Cpad;
+    size_t free_b = 0, total_b = 0;
+    SMC_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    double need = 0;
+    for (auto& r : m->regs)
+      if (r.d.kind == SMC_REG_CHAIN) need += (double)r.numel * Cpad * 8.0;
+    if (need > 0.85 * (double)free_b) {
+      smc_set_error("the generic executor needs %.1f GB of per-chain registers for %lld chains (%.1f GB free): "
+                    "reduce `chains` or use a model the fused kernels cover", need / 1e9, (long long)max_chains, free_b / 1e9);
+      return SMC_ERR_MEMORY;
+    }
+    for (auto& r : m->regs)
+      if (r.d.kind == SMC_REG_CHAIN) {
+        SMC_CUDA(cudaMalloc(&r.dev, (size_t)r.numel * Cpad * sizeof(double)));
+        r.owned = true;
+      }
+    SMC_CUDA(cudaMalloc(&m->beta, (size_t)std::max<int64_t>(m->M, 1) * Cpad * sizeof(double)));
+    SMC_CUDA(cudaMalloc(&m->grad, (size_t)std::max<int64_t>(m->M, 1) * Cpad * sizeof(double)));
+    SMC_CUDA(cudaMalloc(&m->logp, (size_t)Cpad * sizeof(double)));
+    SMC_CUDA(cudaMalloc(&m->bad, (size_t)(Cpad + 32) * sizeof(int)));
+    SMC_CUDA(cudaMemsetAsync(m->beta, 0, (size_t)std::max<int64_t>(m->M, 1) * Cpad * sizeof(double), st));
+    SMC_CUDA(cudaMemsetAsync(m->grad, 0, (size_t)std::max<int64_t>(m->M, 1) * Cpad * sizeof(double), st));
+  }
+  for (auto& r : m->regs)
+    if (r.d.kind == SMC_REG_HDR && !r.dev) {
+      SMC_CUDA(cudaMalloc(&r.dev, (size_t)r.numel * sizeof(double)));
+      r.owned = true;
+    }
+  if (!m->ev0) { SMC_CUDA(cudaEventCreate(&m->ev0)); SMC_CUDA(cudaEventCreate(&m->ev1)); }
+  // the let-header: parameter independent statements, evaluated once (src/parsing.jl:432-442)
+  SMC_CUDA(cudaMemsetAsync(m->bad, 0, (size_t)(Cpad + 32) * sizeof(int), st));
+  for (int si : m->hdr_stmts) SMC_TRY(run_statement(m, m->stmts[si], 1, true));
+  int hbad = 0;
+  SMC_CUDA(cudaMemcpyAsync(&hbad, m->bad + Cpad, sizeof(int), cudaMemcpyDeviceToHost, st));
+  SMC_CUDA(cudaStreamSynchronize(st));
+  if (hbad) { smc_set_error("Initial values out of model support, try other values (a parameter-independent density is zero)"); return SMC_ERR_SUPPORT; }
+  // fused GLM statements
+  for (auto& g : m->glm) smc_glm_release(g);
+  m->glm.clear();
+  for (int si : m->body_stmts)
+    if (m->stmts[si].op == SMC_OP_GLM) {
+      SmcGlmPlan g;
+      g.stmt = si;
+      SMC_TRY(smc_glm_prepare(m, g));
+      m->glm.push_back(g);
+    }
+  SMC_CUDA(cudaStreamSynchronize(st));
+  SMC_CUDA(cudaGetLastError());
+  m->finalized = true;
+  return SMC_OK;
+}
+
+// beta[M][Cpad] (device) -> logp[Cpad], grad[M][Cpad] (device)
+int smc_model_eval_device(smc_model_s* m, int64_t C, bool with_grad) {
+  if (!m->finalized) { smc_set_error("model is not finalized (call smc_model_finalize after binding data)"); return SMC_ERR_INVALID; }
+  if (C < 1 || C > m->Cmax) { smc_set_error("chains %lld outside [1, %lld] given to smc_model_finalize", (long long)C, (long long)m->Cmax); return SMC_ERR_INVALID; }
+  cudaStream_t st = m->ctx->stream;
+  m->C = C;
+  k_fill_int<<<grid_for(C), 256, 0, st>>>(m->bad, C, 0);
+  m->ctx->launches++;
+  const int n_fwd = (int)m->hdr.reserved[0];  // statements past this index only serve the gradient
+  for (int si : m->body_stmts) {
+    const smc_tape_stmt& s = m->stmts[si];
+    if (!with_grad && (si >= n_fwd || m->regs[s.dst].d.kind == SMC_REG_GRAD)) continue;
+    SMC_TRY(run_statement(m, s, C, false));
+  }
+  const SmcReg& rr = m->regs[m->hdr.result_reg];
+  Opd ro = make_opd(m, m->hdr.result_reg, false);
+  if (ro.is_imm || rr.numel != 1) { smc_set_error("tape: result register must be a computed scalar"); return SMC_ERR_INVALID; }
+  // row-sharded models all-reduce inside the GLM statement (its (L, G) are the only row sums), so every
+  // rank finishes with identical (logp, grad) here
+  k_finish_eval<<<grid_for(C), 256, 0, st>>>(ro.p, ro.se, ro.sc, m->bad, m->logp, m->grad, m->M, C, m->Cpad, with_grad ? 1 : 0);
+  m->ctx->launches++;
+  return SMC_OK;
+}
+
+extern "C" int smc_eval(smc_model_t m, const double* beta, int64_t C, double* logp, double* grad) {
+  if (!m || !beta || !logp) { smc_set_error("smc_eval: NULL argument"); return SMC_ERR_INVALID; }
+  if (!m->finalized) { smc_set_error("model is not finalized (call smc_model_finalize after binding data)"); return SMC_ERR_INVALID; }
+  if (C < 1 || C > m->Cmax) { smc_set_error("smc_eval: chains %lld outside [1, %lld]", (long long)C, (long long)m->Cmax); return SMC_ERR_INVALID; }
+  cudaSetDevice(m->ctx->device);
+  cudaStream_t st = m->ctx->stream;
+  int64_t M = m->M;
+  SMC_TRY(scratch_reserve(m, std::max<int64_t>(C * M, 1)));
+  SMC_CUDA(cudaMemcpyAsync(m->scratch, beta, (size_t)C * M * sizeof(double), cudaMemcpyHostToDevice, st));
+  k_rows_to_cols<<<grid_for(C * M), 256, 0, st>>>(m->scratch, m->beta, C, M, m->Cpad, 0);
+  m->ctx->launches++;
+  SMC_TRY(smc_model_eval_device(m, C, grad != nullptr));
+  SMC_CUDA(cudaMemcpyAsync(logp, m->logp, (size_t)C * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (grad) {
+    SMC_TRY(scratch_reserve(m, std::max<int64_t>(C * M, 1)));
+    k_cols_to_rows<<<grid_for(C * M), 256, 0, st>>>(m->grad, m->scratch, C, M, m->Cpad);
+    m->ctx->launches++;
+    SMC_CUDA(cudaMemcpyAsync(grad, m->scratch, (size_t)C * M * sizeof(double), cudaMemcpyDeviceToHost, st));
+  }
+  SMC_CUDA(cudaStreamSynchronize(st));
+  SMC_CUDA(cudaGetLastError());
+  return SMC_OK;
+}
+
+extern "C" int smc_eval_timed(smc_model_t m, int reps, int flush_l2, double* ms_eval, double* ms_glm_kernel) {
+  if (!m || reps < 1 || !m->finalized || m->C < 1) { smc_set_error("smc_eval_timed: call smc_eval first"); return SMC_ERR_INVALID; }
+  cudaSetDevice(m->ctx->device);
+  cudaStream_t st = m->ctx->stream;
+  const size_t flush_bytes = 256u << 20;
+  if (flush_l2 && !m->ctx->flush_buf) SMC_CUDA(cudaMalloc(&m->ctx->flush_buf, flush_bytes));
+  double tot = 0.0, glm = 0.0;
+  for (int r = 0; r < reps; r++) {
+    if (flush_l2) SMC_CUDA(cudaMemsetAsync(m->ctx->flush_buf, r & 0xff, flush_bytes, st));
+    m->time_glm = 1;
+    for (auto& g : m->glm) g.last_ms = 0.f;
+    cudaEvent_t e0, e1;
+    SMC_CUDA(cudaEventCreate(&e0));
+    SMC_CUDA(cudaEventCreate(&e1));
+    SMC_CUDA(cudaEventRecord(e0, st));
+    int rc = smc_model_eval_device(m, m->C, true);
+    SMC_CUDA(cudaEventRecord(e1, st));
+    SMC_CUDA(cudaEventSynchronize(e1));
+    m->time_glm = 0;
+    if (rc != SMC_OK) return rc;
+    float ms = 0.f;
+    SMC_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    tot += ms;
+    for (auto& g : m->glm) glm += g.last_ms;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+  }
+  if (ms_eval) *ms_eval = tot / reps;
+  if (ms_glm_kernel) *ms_glm_kernel = glm / reps;
+  return SMC_OK;
+}

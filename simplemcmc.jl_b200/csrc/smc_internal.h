@@ -1,0 +1,101 @@
+// Internal structures of libsimplemcmc_cuda.so (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/simplemcmc.h"
+#include "../../include/simplemcmc_tape.h"
+
+void smc_set_error(const char* fmt, ...);
+
+#define SMC_CUDA(call)                                                                          \
+  do {                                                                                          \
+    cudaError_t e_ = (call);                                                                    \
+    if (e_ != cudaSuccess) {                                                                    \
+      smc_set_error("CUDA error '%s' at %s:%d (%s)", cudaGetErrorString(e_), __FILE__, __LINE__, #call); \
+      return SMC_ERR_CUDA;                                                                      \
+    }                                                                                           \
+  } while (0)
+
+#define SMC_TRY(call)           \
+  do {                          \
+    int rc_ = (call);           \
+    if (rc_ != SMC_OK) return rc_; \
+  } while (0)
+
+struct smc_ctx_s {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  void* nccl_comm = nullptr;  // ncclComm_t
+  int rank = 0, nranks = 1;
+  void* flush_buf = nullptr;  // L2 flush scratch (256 MB), allocated on demand
+  int64_t launches = 0;       // kernels launched by this library on this context
+};
+
+struct SmcReg {
+  smc_tape_reg d;
+  int64_t numel = 1;
+  double* dev = nullptr;  // DATA/HDR: [numel]; CHAIN: [numel][Cpad]
+  bool owned = false;
+};
+
+struct SmcData {
+  std::string name;
+  int64_t rows = 0, cols = 0;
+  int reg = -1;
+  bool bound = false;
+};
+
+struct SmcGlmPlan {  // one SMC_OP_GLM statement, prepared at finalize
+  int stmt = -1;
+  int family = 0;
+  int sign_neg = 0;
+  double par = 0.0;
+  int64_t N = 0;       // local rows
+  int M = 0, MP = 0;   // columns and columns padded to a multiple of 8
+  double* Xrm = nullptr;  // [N][MP] row major, zero padded
+  const double* y = nullptr;
+  int64_t y_len = 0;
+  double y_scalar = 0.0;
+  double* part = nullptr;  // partial (L,G) buffers [RS][MP+1][Cpad]
+  int64_t part_cap = 0;
+  float last_ms = 0.f;
+};
+
+struct smc_model_s {
+  smc_ctx_s* ctx = nullptr;
+  smc_tape_header hdr;
+  std::vector<SmcReg> regs;
+  std::vector<smc_tape_stmt> stmts;
+  std::vector<int> hdr_stmts, body_stmts;
+  std::vector<SmcData> data;
+  std::vector<int32_t*> idx_dev;
+  std::vector<uint32_t> idx_len;
+  std::vector<SmcGlmPlan> glm;
+  bool finalized = false;
+  int row_shard = 0;
+  int64_t M = 0;       // n_params
+  int64_t Cmax = 0, Cpad = 0;
+  int64_t C = 0;       // chains of the current evaluation
+  double* beta = nullptr;  // [M][Cpad]  evaluation input (PARAM views)
+  double* grad = nullptr;  // [M][Cpad]  evaluation output (GRAD views)
+  double* logp = nullptr;  // [Cpad]
+  int* bad = nullptr;      // [Cpad] "give up eval" flags (src/distribs.jl:15,17,32,70)
+  double* scratch = nullptr;  // partial sums of reductions
+  int64_t scratch_cap = 0;
+  double* host_stage = nullptr;  // pinned staging
+  int64_t host_stage_cap = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int time_glm = 0;
+};
+
+// smc_core.cu
+int smc_model_eval_device(smc_model_s* m, int64_t C, bool with_grad);  // beta -> logp, grad (device resident)
+int smc_stage_reserve(smc_model_s* m, int64_t doubles);
+
+// glm_fused.cu
+int smc_glm_prepare(smc_model_s* m, SmcGlmPlan& g);
+int smc_glm_launch(smc_model_s* m, SmcGlmPlan& g, int64_t C);
+void smc_glm_release(SmcGlmPlan& g);

@@ -22,7 +22,7 @@ from . import capi
 from .lowering import Lowering, ModelError
 
 RESERVED = ("steps", "burnin", "isteps", "stepsize", "maxiter", "precision", "gradient", "debug", "chains", "seed",
-            "device", "data", "shard", "ref_adjoint", "store_draws", "comm")
+            "device", "data", "shard", "ref_adjoint", "store_draws", "comm", "chain_offset")
 
 
 class _DataLookup(dict):
@@ -190,7 +190,7 @@ def _sample(kind, model, kw, defaults):
     try:
         raw = dev.run(kind, np.array(low.init), chains, steps, burnin, isteps=int(round(opts.get("isteps", 1))),
                       stepsize=float(opts.get("stepsize", 0.0)), seed=int(opts.get("seed", 1)), store_draws=store,
-                      chain_offset=int(opts.get("chain_offset", 0)) if "chain_offset" in opts else 0)
+                      chain_offset=int(opts.get("chain_offset", 0)))
     except capi.SMCError as e:
         if e.status == -4:
             raise AssertionError(str(e))

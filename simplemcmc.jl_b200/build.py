@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsimplemcmc_cuda.so")
-SOURCES = ["smc_core.cu", "glm_fused.cu", "samplers.cu", "nuts.cu", "smc_comm.cu"]
+SOURCES = ["smc_core.cu", "glm_fused.cu", "samplers.cu", "smc_comm.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
               "-Xcompiler", "-fvisibility=default", "--use_fast_math=false"]
 
@@ -46,7 +46,7 @@ def build(force=False, verbose=False):
     if failed:
         raise RuntimeError("nvcc compilation failed")
     if force or procs or _stale(LIB, objs):
-        cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcudart", "-ldl"]
+        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-lcudart", "-ldl"]
         subprocess.check_call(cmd)
     return LIB
 

@@ -487,4 +487,305 @@ extern "C" int smc_philox_uniforms(uint64_t seed, int64_t chain, int64_t step, i
   return SMC_OK;
 }
 
-// NUTS lives in nuts.cu
+// ---------------------------------------------------------------------------------------------- NUTS
+// Efficient NUTS (Hoffman & Gelman) as the reference codes it: /root/reference/src/samplers.jl:199-310.
+// The recursive buildTree (:224-257) becomes an iteration over the 2^j leaves of a doubling; completed
+// sub-trees wait on a per-chain stack indexed by level (a binary counter), merged exactly where the recursion
+// would return.  Chains run in lockstep one leapfrog per round; a chain whose tree is finished idles (masked)
+// until every chain is done.  Uniform draws are consumed in the reference's order (slice, direction, one per
+// merge, one per accepted doubling) from the chain's (step, k) counter stream.
+namespace {
+
+constexpr int kMaxDepth = 8;    // `while s && j < 8`, src/samplers.jl:279
+constexpr double kDeltaMax = 100.0;
+
+struct Nuts {
+  // outer tree
+  double *mb, *mv, *mg, *ml, *pb, *pv, *pg, *pl;  // minus / plus edge states
+  double *sb, *sg, *sl;                             // selected state of the iteration
+  // trajectory velocity (position/grad/logp of the trajectory live in the model's eval buffers)
+  double* tv;
+  // sub-tree under construction ("current") and the stack of completed sub-trees
+  double *cnb, *cnv, *csb, *csg, *csl;  // current: near edge (beta, v), selected (beta, grad, logp)
+  double *knb, *knv, *ksb, *ksg;        // stack[level][M][Cpad]
+  double *ksl, *kn, *ka, *kna;          // stack[level][Cpad]
+  double *u, *H0, *eps, *hbar, *lebar, *alast, *nalast, *ntot;
+  int *j, *leaf, *dir, *active, *newdbl, *ucount, *moved;
+  int* n_active;
+  unsigned long long* rounds_active;
+};
+
+__device__ __forceinline__ bool uturn_dev(const double* minus_b, const double* minus_v, const double* plus_b,
+                                          const double* plus_v, long long c, long long M, long long Cpad) {
+  double d1 = 0.0, d2 = 0.0;   // dot(s2.beta - s1.beta, s1.v) < 0 || dot(s2.beta - s1.beta, s2.v) < 0   (src/samplers.jl:48)
+  for (long long k = 0; k < M; k++) {
+    double db = plus_b[k * Cpad + c] - minus_b[k * Cpad + c];
+    d1 += db * minus_v[k * Cpad + c];
+    d2 += db * plus_v[k * Cpad + c];
+  }
+  return d1 < 0.0 || d2 < 0.0;
+}
+
+__device__ __forceinline__ void copy_vec(double* dst, const double* src, long long c, long long M, long long Cpad) {
+  for (long long k = 0; k < M; k++) dst[k * Cpad + c] = src[k * Cpad + c];
+}
+
+__global__ void k_nuts_init(long long C, Nuts T) {
+  long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  T.eps[c] = 1.0;       // the initial-epsilon search of :199-210 never runs (state0.H is NaN): epsilon0 = 1
+  T.hbar[c] = 0.0;
+  T.lebar[c] = 0.0;
+}
+
+__global__ void k_nuts_begin(RngSrc rng, long long step, long long C, long long M, long long Cpad, const double* b0,
+                             const double* g0, const double* l0, Nuts T) {
+  long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double ss = draw_normals(rng, step, c, C, M, Cpad, T.mv);
+  for (long long k = 0; k < M; k++) {
+    long long o = k * Cpad + c;
+    double b = b0[o], g = g0[o];
+    T.pv[o] = T.mv[o];
+    T.mb[o] = b; T.pb[o] = b; T.sb[o] = b;
+    T.mg[o] = g; T.pg[o] = g; T.sg[o] = g;
+  }
+  double ll = l0[c];
+  T.ml[c] = ll; T.pl[c] = ll; T.sl[c] = ll;
+  double H0 = ll - ss / 2.0;
+  T.H0[c] = H0;
+  T.u[c] = log(rng_uniform(rng, step, c, C, 0)) + H0;   // u_slice = log(rand()) + state0.H, :272
+  T.ucount[c] = 1;
+  T.j[c] = 0;
+  T.ntot[c] = 1.0;
+  T.active[c] = 1;
+  T.newdbl[c] = 1;
+  T.moved[c] = 0;
+  T.alast[c] = 0.0;
+  T.nalast[c] = 1.0;
+}
+
+__global__ void k_nuts_pre(RngSrc rng, long long step, long long C, long long M, long long Cpad, double* beta,
+                           double* grad, double* logp, Nuts T) {
+  long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C || !T.active[c]) return;
+  if (T.newdbl[c]) {
+    int k = T.ucount[c];
+    double r = rng_uniform(rng, step, c, C, k);
+    T.ucount[c] = k + 1;
+    int dir = (r > 0.5) ? 1 : -1;   // dir = (rand() > 0.5) * 2. - 1., :280
+    T.dir[c] = dir;
+    const double* eb = dir < 0 ? T.mb : T.pb;
+    const double* ev = dir < 0 ? T.mv : T.pv;
+    const double* eg = dir < 0 ? T.mg : T.pg;
+    for (long long q = 0; q < M; q++) {
+      long long o = q * Cpad + c;
+      beta[o] = eb[o]; T.tv[o] = ev[o]; grad[o] = eg[o];
+    }
+    logp[c] = dir < 0 ? T.ml[c] : T.pl[c];
+    T.leaf[c] = 0;
+    T.newdbl[c] = 0;
+  }
+  double ve = T.dir[c] * T.eps[c];
+  for (long long q = 0; q < M; q++) {   // leapFrog, :52-53
+    long long o = q * Cpad + c;
+    double vv = T.tv[o] + grad[o] * ve / 2.0;
+    T.tv[o] = vv;
+    beta[o] += ve * vv;
+  }
+}
+
+__global__ void k_nuts_post(RngSrc rng, long long step, long long C, long long M, long long Cpad, const double* beta,
+                            const double* grad, const double* logp, Nuts T, unsigned long long* nleap) {
+  long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C || !T.active[c]) return;
+  const long long LS = M * Cpad;  // stride between stack levels
+  const int dir = T.dir[c];
+  double ve = dir * T.eps[c];
+  double ss = 0.0;
+  for (long long q = 0; q < M; q++) {   // second half kick + update!, :55-56
+    long long o = q * Cpad + c;
+    double vv = T.tv[o] + grad[o] * ve / 2.0;
+    T.tv[o] = vv;
+    ss += vv * vv;
+  }
+  double ll = logp[c];
+  double H = ll - ss / 2.0;
+  nleap[c] += 1ull;
+  // ---- leaf (buildTree with j == 0, :230-236)
+  const double u = T.u[c];
+  double n2 = (u <= H) ? 1.0 : 0.0;
+  bool s2 = u < (kDeltaMax + H);
+  double a2 = fmin(1.0, exp(H - T.H0[c]));
+  double na2 = 1.0;
+  copy_vec(T.cnb, beta, c, M, Cpad);
+  copy_vec(T.cnv, T.tv, c, M, Cpad);
+  copy_vec(T.csb, beta, c, M, Cpad);
+  copy_vec(T.csg, grad, c, M, Cpad);
+  T.csl[c] = ll;
+  // ---- merges where the recursion returns (:238-256): levels = trailing one bits of the leaf index
+  const int leaf = T.leaf[c];
+  const int j = T.j[c];
+  int level = 0;
+  int ucount = T.ucount[c];
+  while ((leaf >> level) & 1) {
+    const long long so = (long long)level * LS, sc = (long long)level * Cpad + c;
+    double n1 = T.kn[sc];
+    double r = rng_uniform(rng, step, c, C, ucount++);
+    bool take_second = r <= n2 / (n2 + n1);   // NaN (0/0) compares false, as in the reference
+    if (!take_second) {
+      copy_vec(T.csb, T.ksb + so, c, M, Cpad);
+      copy_vec(T.csg, T.ksg + so, c, M, Cpad);
+      T.csl[c] = T.ksl[sc];
+    }
+    copy_vec(T.cnb, T.knb + so, c, M, Cpad);   // the merged sub-tree starts where the first one started
+    copy_vec(T.cnv, T.knv + so, c, M, Cpad);
+    a2 += T.ka[sc];
+    na2 += T.kna[sc];
+    if (s2) {
+      bool ut = dir > 0 ? uturn_dev(T.cnb, T.cnv, beta, T.tv, c, M, Cpad) : uturn_dev(beta, T.tv, T.cnb, T.cnv, c, M, Cpad);
+      s2 = !ut;
+    }
+    n2 += n1;
+    level++;
+  }
+  bool done = (!s2) || (leaf == (1 << j) - 1);
+  if (!done) {
+    const long long so = (long long)level * LS, sc = (long long)level * Cpad + c;
+    copy_vec(T.knb + so, T.cnb, c, M, Cpad);
+    copy_vec(T.knv + so, T.cnv, c, M, Cpad);
+    copy_vec(T.ksb + so, T.csb, c, M, Cpad);
+    copy_vec(T.ksg + so, T.csg, c, M, Cpad);
+    T.ksl[sc] = T.csl[c];
+    T.kn[sc] = n2; T.ka[sc] = a2; T.kna[sc] = na2;
+    T.leaf[c] = leaf + 1;
+    T.ucount[c] = ucount;
+    atomicAdd(T.n_active, 1);
+    return;
+  }
+  // ---- the doubling is complete (or was cut): outer loop body, :281-291
+  double* eb = dir < 0 ? T.mb : T.pb;
+  double* ev = dir < 0 ? T.mv : T.pv;
+  double* eg = dir < 0 ? T.mg : T.pg;
+  for (long long q = 0; q < M; q++) {
+    long long o = q * Cpad + c;
+    eb[o] = beta[o]; ev[o] = T.tv[o]; eg[o] = grad[o];
+  }
+  (dir < 0 ? T.ml : T.pl)[c] = ll;
+  double ntot = T.ntot[c];
+  if (s2) {
+    double r = rng_uniform(rng, step, c, C, ucount++);
+    if (r < n2 / ntot) {   // state = state1
+      copy_vec(T.sb, T.csb, c, M, Cpad);
+      copy_vec(T.sg, T.csg, c, M, Cpad);
+      T.sl[c] = T.csl[c];
+      T.moved[c] = 1;
+    }
+  }
+  T.ntot[c] = ntot + n2;
+  T.j[c] = j + 1;
+  T.alast[c] = a2;
+  T.nalast[c] = na2;
+  T.ucount[c] = ucount;
+  bool s = s2 && !uturn_dev(T.mb, T.mv, T.pb, T.pv, c, M, Cpad);
+  if (s && j + 1 < kMaxDepth) {
+    T.newdbl[c] = 1;
+    atomicAdd(T.n_active, 1);
+  } else {
+    T.active[c] = 0;
+  }
+}
+
+// dual averaging of epsilon (:294-302), addToRes! (:305), misc (:307-308), state0 = state (:310)
+__global__ void k_nuts_end(long long step, long long C, long long M, long long Cpad, double* b0, double* g0, double* l0,
+                           Nuts T, Recorder R, double* eps_out, double* jmax_out) {
+  long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double delta = 0.7, gam = 0.05, kappa = 0.75, t0 = 10.0;
+  const long long nadapt = 1000;
+  double i1 = (double)(step + 1);
+  double eps;
+  if (step + 1 <= nadapt) {
+    double mu = log(10.0 * 1.0);
+    double hbar = T.hbar[c] * (1.0 - 1.0 / (i1 + t0)) + (delta - T.alast[c] / T.nalast[c]) / (i1 + t0);
+    double le = mu - sqrt(i1) / gam * hbar;
+    double w = pow(i1, -kappa);
+    T.lebar[c] = w * le + (1.0 - w) * T.lebar[c];
+    T.hbar[c] = hbar;
+    eps = exp(le);
+  } else {
+    eps = exp(T.lebar[c]);
+  }
+  T.eps[c] = eps;
+  copy_vec(b0, T.sb, c, M, Cpad);
+  copy_vec(g0, T.sg, c, M, Cpad);
+  l0[c] = T.sl[c];
+  record(R, step, c, M, Cpad, b0, l0[c], T.moved[c] != 0);
+  if (eps_out) eps_out[step * Cpad + c] = eps;
+  if (jmax_out) jmax_out[step * Cpad + c] = (double)T.j[c];
+}
+
+}  // namespace
+
+extern "C" int smc_nuts_run(smc_model_t m, const smc_sampler_config* cfg, const double* init, int64_t C, smc_run_output* out) {
+  if (!m || !cfg || !init || !out) { smc_set_error("smc_nuts_run: NULL argument"); return SMC_ERR_INVALID; }
+  Run r;
+  r.m = m; r.cfg = cfg; r.out = out; r.C = C;
+  // worst case uniforms per step: 1 slice + per doubling (1 direction + merges + 1 accept) = 1 + 8*2 + 247
+  const long long max_uniforms = 1 + 2 * kMaxDepth + ((1 << kMaxDepth) - 1 - kMaxDepth);
+  SMC_TRY(run_setup(r, init, true, max_uniforms));
+  cudaStream_t st = m->ctx->stream;
+  long long M = r.M, Cpad = r.Cpad, V = M * Cpad;
+  Nuts T;
+  double** vecs[] = {&T.mb, &T.mv, &T.mg, &T.pb, &T.pv, &T.pg, &T.sb, &T.sg, &T.tv, &T.cnb, &T.cnv, &T.csb, &T.csg};
+  for (auto pp : vecs) SMC_TRY(r.A.alloc(pp, V));
+  double** stacks[] = {&T.knb, &T.knv, &T.ksb, &T.ksg};
+  for (auto pp : stacks) SMC_TRY(r.A.alloc(pp, V * kMaxDepth));
+  double** sstacks[] = {&T.ksl, &T.kn, &T.ka, &T.kna};
+  for (auto pp : sstacks) SMC_TRY(r.A.alloc(pp, Cpad * kMaxDepth));
+  double** scal[] = {&T.ml, &T.pl, &T.sl, &T.csl, &T.u, &T.H0, &T.eps, &T.hbar, &T.lebar, &T.alast, &T.nalast, &T.ntot};
+  for (auto pp : scal) SMC_TRY(r.A.alloc(pp, Cpad));
+  int** ints[] = {&T.j, &T.leaf, &T.dir, &T.active, &T.newdbl, &T.ucount, &T.moved};
+  for (auto pp : ints) SMC_TRY(r.A.alloc(pp, Cpad));
+  SMC_TRY(r.A.alloc(&T.n_active, 4));
+  SMC_TRY(r.A.alloc(&T.rounds_active, 4));
+  SMC_CUDA(cudaMemsetAsync(T.rounds_active, 0, 4 * sizeof(unsigned long long), st));
+  double *eps_dev = nullptr, *jmax_dev = nullptr;
+  if (out->epsilon) SMC_TRY(r.A.alloc(&eps_dev, cfg->steps * Cpad));
+  if (out->jmax) SMC_TRY(r.A.alloc(&jmax_dev, cfg->steps * Cpad));
+  k_nuts_init<<<gridc(C), 128, 0, st>>>(C, T);
+  m->ctx->launches++;
+  int64_t evals = 1;
+  int* h_active = nullptr;
+  SMC_CUDA(cudaMallocHost(&h_active, sizeof(int)));
+  int rc = SMC_OK;
+  for (long long i = 0; i < cfg->steps && rc == SMC_OK; i++) {
+    k_nuts_begin<<<gridc(C), 128, 0, st>>>(r.rng, i, C, M, Cpad, r.b0, r.g0, r.l0, T);
+    m->ctx->launches++;
+    int rounds = 0;
+    while (true) {
+      cudaMemsetAsync(T.n_active, 0, sizeof(int), st);
+      k_nuts_pre<<<gridc(C), 128, 0, st>>>(r.rng, i, C, M, Cpad, m->beta, m->grad, m->logp, T);
+      m->ctx->launches++;
+      rc = smc_model_eval_device(m, C, true);
+      if (rc != SMC_OK) break;
+      evals++;
+      k_nuts_post<<<gridc(C), 128, 0, st>>>(r.rng, i, C, M, Cpad, m->beta, m->grad, m->logp, T, r.nleap);
+      m->ctx->launches++;
+      cudaMemcpyAsync(h_active, T.n_active, sizeof(int), cudaMemcpyDeviceToHost, st);
+      cudaError_t e = cudaStreamSynchronize(st);
+      if (e != cudaSuccess) { smc_set_error("CUDA error '%s' in the NUTS loop", cudaGetErrorString(e)); rc = SMC_ERR_CUDA; break; }
+      rounds++;
+      if (*h_active == 0 || rounds >= (1 << kMaxDepth)) break;
+    }
+    if (rc != SMC_OK) break;
+    k_nuts_end<<<gridc(C), 128, 0, st>>>(i, C, M, Cpad, r.b0, r.g0, r.l0, T, r.R, eps_dev, jmax_dev);
+    m->ctx->launches++;
+  }
+  cudaFreeHost(h_active);
+  if (rc != SMC_OK) return rc;
+  SMC_TRY(run_finish(r, evals));
+  SMC_TRY(copy_out_blocks(r, eps_dev, out->epsilon, cfg->steps, 1));
+  SMC_TRY(copy_out_blocks(r, jmax_dev, out->jmax, cfg->steps, 1));
+  return SMC_OK;
+}

@@ -1,0 +1,177 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle: log-density and gradient to 1e-12 relative in FP64
+on identical inputs (BASELINE.json north_star).  Gradients are compared relative to max|g| (components near a mode
+cancel to ~0)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle.refmodel import generate_model_function  # noqa: E402
+from rule_cases import all_cases  # noqa: E402
+from util import (HIERARCHICAL, LINEAR, LOGISTIC, ORNSTEIN, SLEEPSTUDY2, hierarchical_data, linear_data, logistic_data,  # noqa: E402
+                  ou_data, relerr, sleepstudy_data)
+
+TOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def smc():
+    from smc_pkg import load_package
+    return load_package()
+
+
+def _check(lp, g, lp0, g0, tol=TOL):
+    assert abs(lp - lp0) <= tol * max(abs(lp0), 1e-300), (lp, lp0)
+    if np.max(np.abs(g0)) > 0:
+        assert relerr(g, g0) <= tol, (g, g0)
+    else:
+        assert np.max(np.abs(g)) == 0
+
+
+def test_rule_matrix(smc):
+    """the op x shape-pattern matrix of test/test.jl:142-224, device vs oracle"""
+    worst = 0.0
+    for ex, data, x0 in all_cases():
+        model = "sum(%s)" % ex
+        ref = generate_model_function(model, data=data, gradient=True, x=x0)
+        f, n, pars, init = smc.generateModelFunction(model, gradient=True, data=data, x=x0)
+        lp, g = f(init)
+        lp0, g0 = ref(init)
+        _check(lp, g, lp0, g0)
+        worst = max(worst, relerr(g, g0) if np.max(np.abs(g0)) > 0 else 0.0)
+    assert worst <= TOL
+
+
+@pytest.mark.parametrize("fuse", [True, False])
+@pytest.mark.parametrize("C", [1, 7, 64, 200])
+def test_linear_cfg1(smc, fuse, C):
+    from simplemcmc_jl_b200 import api
+    X, Y, _ = linear_data()
+    data = dict(X=X, Y=Y)
+    ref = generate_model_function(LINEAR, data=data, gradient=True, beta=np.zeros(10))
+    low, dev = api._build(LINEAR, [("beta", np.zeros(10))], data, True, C, 0, "assign", fuse=fuse)
+    assert low.n_fused == (1 if fuse else 0)
+    betas = 0.3 * np.random.default_rng(C).standard_normal((C, 10))
+    lp, g = dev.eval(betas)
+    for c in range(C):
+        _check(lp[c], g[c], *ref(betas[c]))
+    lp2, _ = dev.eval(betas, gradient=False)
+    assert np.array_equal(lp, lp2)
+
+
+@pytest.mark.parametrize("fuse", [True, False])
+@pytest.mark.parametrize("N,M", [(1000, 10), (777, 3), (4099, 33), (300, 64)])
+def test_logistic_cfg3_shapes(smc, fuse, N, M):
+    """ragged sizes: rows not a multiple of the row tile, widths that need padding to 16/32/64"""
+    from simplemcmc_jl_b200 import api
+    X, Y, _ = logistic_data(N, M)
+    data = dict(X=X, Y=Y)
+    ref = generate_model_function(LOGISTIC, data=data, gradient=True, vars=np.zeros(M))
+    C = 19
+    low, dev = api._build(LOGISTIC, [("vars", np.zeros(M))], data, True, C, 0, "assign", fuse=fuse)
+    betas = 0.2 * np.random.default_rng(N).standard_normal((C, M))
+    lp, g = dev.eval(betas)
+    for c in range(C):
+        _check(lp[c], g[c], *ref(betas[c]))
+
+
+def test_normal_glm_variants(smc):
+    """the GLM matcher must keep signs straight for every way of writing the same likelihood"""
+    X, Y, _ = linear_data(500, 6)
+    data = dict(X=X, Y=Y)
+    b = 0.2 * np.random.default_rng(3).standard_normal((5, 6))
+    for lik in ("resid = Y - X * beta\nresid ~ Normal(0, 2.0)", "resid = X * beta - Y\nresid ~ Normal(0, 2.0)",
+                "Y ~ Normal(X * beta, 0.5)", "eta = X * beta\neta ~ Normal(Y, 1.5)"):
+        model = "beta ~ Normal(0, 1.0)\n" + lik
+        ref = generate_model_function(model, data=data, gradient=True, beta=np.zeros(6))
+        f, *_ = smc.generateModelFunction(model, gradient=True, chains=5, data=data, beta=np.zeros(6))
+        assert f.lowered.n_fused == 1
+        lp, g = f(b)
+        for c in range(5):
+            _check(lp[c], g[c], *ref(b[c]))
+
+
+def test_ornstein_cfg5(smc):
+    x = ou_data(1000)
+    ref = generate_model_function(ORNSTEIN, data=dict(x=x), gradient=True, tau=20.0, mu=10.0, sigma=0.1)
+    f, n, pars, init = smc.generateModelFunction(ORNSTEIN, gradient=True, chains=16, data=dict(x=x), tau=20.0, mu=10.0, sigma=0.1)
+    assert [p.sym for p in pars] == ["tau", "mu", "sigma"] and n == 3
+    rng = np.random.default_rng(0)
+    b = init[None, :] * (1 + 0.05 * rng.standard_normal((16, 3)))
+    lp, g = f(b)
+    for c in range(16):
+        _check(lp[c], g[c], *ref(b[c]), tol=1e-11)   # r = x_t - fac*x_(t-1) - mu(1-fac) cancels ~3 digits
+
+
+def test_sleepstudy_cfg4(smc):
+    data, nsub = sleepstudy_data()
+    init = dict(intercept=250.0, slope=10.0, rand_int=np.zeros(nsub), rand_slope=np.zeros(nsub))
+    ref = generate_model_function(SLEEPSTUDY2, data=data, gradient=True, init=list(init.items()))
+    f, n, pars, b0 = smc.generateModelFunction(SLEEPSTUDY2, gradient=True, chains=8, data=data, **init)
+    assert n == 38
+    b = b0[None, :] + np.random.default_rng(1).standard_normal((8, 38))
+    lp, g = f(b)
+    for c in range(8):
+        _check(lp[c], g[c], *ref(b[c]))
+
+
+def test_hierarchical_cfg4_both_gather_adjoints(smc):
+    """`assign` reproduces the reference's overwrite (parsing.jl:277-281), `add` is the corrected scatter-add"""
+    data, (N, D, L) = hierarchical_data()
+    init = dict(mu=np.zeros((1, L)), sigma=np.ones((1, L)), beta=np.zeros((D, L)))
+    ref = generate_model_function(HIERARCHICAL, data=data, gradient=True, init=list(init.items()))
+    rng = np.random.default_rng(2)
+    b = ref.init + 0.05 * rng.standard_normal(len(ref.init))
+    b[L:2 * L] = np.abs(b[L:2 * L]) + 0.5
+    f, n, pars, _ = smc.generateModelFunction(HIERARCHICAL, gradient=True, data=data, ref_adjoint="assign", **init)
+    assert n == 30 and [tuple(p.size) for p in pars] == [(1, L), (1, L), (D, L)]
+    lp, g = f(b)
+    _check(lp, g, *ref(b))
+    f2, *_ = smc.generateModelFunction(HIERARCHICAL, gradient=True, data=data, ref_adjoint="add", **init)
+    lp2, g2 = f2(b)
+    gn = np.zeros_like(b)
+    for i in range(len(b)):
+        bp, bm = b.copy(), b.copy()
+        bp[i] += 1e-6
+        bm[i] -= 1e-6
+        gn[i] = (ref(bp)[0] - ref(bm)[0]) / 2e-6
+    assert lp2 == lp
+    assert np.allclose(g2, gn, rtol=1e-5, atol=1e-6)
+
+
+def test_out_of_support_chain_gets_minus_inf_and_zero_gradient(smc):
+    """src/parsing.jl:465-467 per chain; the other chains are unaffected"""
+    model = "x ~ Uniform(0, 1)\ny = x * 2\ny ~ Normal(0, 1)"
+    f, *_ = smc.generateModelFunction(model, gradient=True, chains=4, x=0.5)
+    lp, g = f(np.array([[0.25], [1.5], [0.75], [-0.1]]))
+    assert lp[1] == -np.inf and lp[3] == -np.inf and np.all(g[[1, 3]] == 0)
+    ref = generate_model_function(model, gradient=True, x=0.5)
+    _check(lp[0], g[0], *ref(np.array([0.25])))
+    _check(lp[2], g[2], *ref(np.array([0.75])))
+
+
+def test_bernoulli_glm_certain_contradiction_gives_up(smc):
+    X, Y, _ = logistic_data(256, 4)
+    f, *_ = smc.generateModelFunction(LOGISTIC, gradient=True, chains=2, data=dict(X=X, Y=Y), vars=np.zeros(4))
+    lp, g = f(np.array([[0.1, 0.0, 0.0, 0.0], [800.0, 0.0, 0.0, 0.0]]))   # exp overflows: prob == 0 with some Y == 1
+    assert np.isfinite(lp[0]) and lp[1] == -np.inf and np.all(g[1] == 0)
+
+
+def test_error_behaviour(smc):
+    from simplemcmc_jl_b200 import ModelError
+    for ex in ("logpdfBernoulli(1, x)", "logpdfPoisson(1, x)", "logpdfBinomial(3, 0.5, x)", "logpdfBinomial(x, 0.5, 2)"):
+        with pytest.raises(ModelError):        # test/test.jl:199-208
+            smc.generateModelFunction("sum(%s)" % ex, gradient=True, x=np.array([0.0]))
+    with pytest.raises(ModelError):
+        smc.generateModelFunction("x ~ Uniform(0, 1)", gradient=True, x=1.5)   # initial values out of support
+    with pytest.raises(ModelError):
+        smc.generateModelFunction("y = 2 * x\nz ~ Normal(0, 1)", gradient=True, data=dict(z=np.ones(3)), x=1.0)
+    with pytest.raises(AssertionError):
+        smc.simpleHMC("x ~ Normal(0,1)", steps=10, burnin=20, x=0.0)          # checkSteps, src/samplers.jl:324-327
+
+
+def test_no_gradient_closure_and_kwarg_order(smc):
+    f, n, pars, init = smc.generateModelFunction("a ~ Normal(0,1)\nb ~ Normal(a, 2.0)", gradient=False, b=np.array([1.0, 2.0]), a=0.5)
+    assert [p.sym for p in pars] == ["b", "a"] and list(init) == [1.0, 2.0, 0.5]    # kwarg order, parsing.jl:303-334
+    ref = generate_model_function("a ~ Normal(0,1)\nb ~ Normal(a, 2.0)", gradient=False, init=[("b", np.array([1.0, 2.0])), ("a", 0.5)])
+    assert abs(f(init) - ref(init)) < 1e-13

@@ -1,0 +1,165 @@
+"""Sampler parity: first-K-step trajectories against the oracle when both consume the same normals/uniforms
+(BASELINE.json north_star), the device Philox stream against its NumPy restatement, KS tests on the 17 targets of
+test/test2.jl, posterior moments within Monte-Carlo error."""
+import math
+
+import numpy as np
+import pytest
+from scipy import stats
+
+pytestmark = pytest.mark.gpu
+
+from oracle import philox as ophilox  # noqa: E402
+from oracle.refmodel import generate_model_function  # noqa: E402
+from oracle.samplers import ReplayRNG, simple_hmc, simple_nuts, simple_rwm  # noqa: E402
+from util import LINEAR, LOGISTIC, ORNSTEIN, linear_data, logistic_data, ou_data, relerr, sleepstudy_data, SLEEPSTUDY2  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def smc():
+    from smc_pkg import load_package
+    return load_package()
+
+
+def test_device_philox_matches_oracle(smc):
+    from simplemcmc_jl_b200 import capi
+    for seed, chain, step in [(1, 0, 0), (12345678901234, 77, 3), (2 ** 63 + 5, 2 ** 33 + 1, 2 ** 32 + 7)]:
+        u_dev = capi.philox_uniforms(seed, chain, step, 33)
+        u_ref = ophilox.uniforms(seed, chain, step, 33)
+        assert np.array_equal(u_dev, u_ref)                       # integer -> double conversion is exact
+        z_dev = capi.philox_normals(seed, chain, step, 33)
+        z_ref = ophilox.normals(seed, chain, step, 33)
+        assert np.allclose(z_dev, z_ref, rtol=1e-13, atol=1e-15)  # log / sincos may differ in the last ulp
+
+
+def _build(model, init, data, C, gradient=True):
+    from simplemcmc_jl_b200 import api
+    return api._build(model, init, data, gradient, C, 0, "assign")
+
+
+def test_hmc_trajectory_parity_linear(smc):
+    X, Y, _ = linear_data()
+    data = dict(X=X, Y=Y)
+    ref = generate_model_function(LINEAR, data=data, gradient=True, beta=np.zeros(10))
+    steps, burnin, C = 40, 5, 4
+    rng = np.random.default_rng(11)
+    normals, unif = rng.standard_normal((steps, C, 10)), rng.random((steps, C, 1))
+    low, dev = _build(LINEAR, [("beta", np.zeros(10))], data, C)
+    raw = dev.run("hmc", np.zeros(10), C, steps, burnin, isteps=2, stepsize=0.05, inject_normals=normals, inject_uniforms=unif)
+    for c in range(C):
+        o = simple_hmc(ref, np.zeros(10), ReplayRNG(normals[:, c], unif[:, c]), steps, burnin, 2, 0.05)
+        assert relerr(raw["draws"][:, c], o["draws"]) < 1e-12
+        assert relerr(raw["loglik"][:, c], o["loglik"]) < 1e-12
+        assert np.array_equal(raw["accept"][:, c], o["accept"])
+    assert raw["n_leapfrogs"] == C * steps * 2
+
+
+def test_hmc_stops_trajectory_outside_support(smc):
+    """src/samplers.jl:156: the inner loop ends at a non-finite log-density and the proposal is rejected"""
+    model = "x ~ Uniform(0, 1)"
+    ref = generate_model_function(model, gradient=True, x=0.5)
+    steps, C = 25, 3
+    rng = np.random.default_rng(5)
+    normals, unif = rng.standard_normal((steps, C, 1)), rng.random((steps, C, 1))
+    low, dev = _build(model, [("x", 0.5)], {}, C)
+    raw = dev.run("hmc", np.array([0.5]), C, steps, 0, isteps=3, stepsize=0.3, inject_normals=normals, inject_uniforms=unif)
+    tot = 0
+    for c in range(C):
+        o = simple_hmc(ref, np.array([0.5]), ReplayRNG(normals[:, c], unif[:, c]), steps, 0, 3, 0.3)
+        assert relerr(raw["draws"][:, c], o["draws"]) < 1e-12
+        assert np.array_equal(raw["accept"][:, c], o["accept"])
+        tot += o["nleap"]
+    assert raw["n_leapfrogs"] == tot and tot < C * steps * 3
+    assert np.all((raw["draws"] > 0) & (raw["draws"] < 1))
+
+
+def test_rwm_trajectory_parity_logistic(smc):
+    X, Y, _ = logistic_data(500, 6)
+    data = dict(X=X, Y=Y)
+    ref = generate_model_function(LOGISTIC, data=data, gradient=False, vars=np.zeros(6))
+    steps, burnin, C = 60, 10, 3
+    rng = np.random.default_rng(12)
+    normals, unif = rng.standard_normal((steps, C, 6)), rng.random((steps, C, 1))
+    low, dev = _build(LOGISTIC, [("vars", np.zeros(6))], data, C, gradient=False)
+    raw = dev.run("rwm", np.zeros(6), C, steps, burnin, inject_normals=normals, inject_uniforms=unif)
+    for c in range(C):
+        o = simple_rwm(ref, np.zeros(6), ReplayRNG(normals[:, c], unif[:, c]), steps, burnin)
+        # the device updates the Cholesky factor by a rank-one update instead of refactorising: equal up to rounding
+        assert relerr(raw["draws"][:, c], o["draws"]) < 1e-9
+        assert np.array_equal(raw["accept"][:, c], o["accept"])
+
+
+def test_nuts_trajectory_parity(smc):
+    data, nsub = sleepstudy_data()
+    X, Y, _ = linear_data(200, 5)
+    cases = [(LINEAR, [("beta", np.zeros(5))], dict(X=X, Y=Y)),
+             ("x ~ Normal(1, 2)\ny ~ Gamma(2, 1)", [("x", 0.5), ("y", 1.0)], {})]
+    for model, init, dat in cases:
+        ref = generate_model_function(model, data=dat, gradient=True, init=init)
+        M = len(ref.init)
+        steps, burnin, C, NU = 30, 5, 3, 270
+        rng = np.random.default_rng(13)
+        normals, unif = rng.standard_normal((steps, C, M)), rng.random((steps, C, NU))
+        low, dev = _build(model, init, dat, C)
+        raw = dev.run("nuts", ref.init, C, steps, burnin, inject_normals=normals, inject_uniforms=unif)
+        tot = 0
+        for c in range(C):
+            o = simple_nuts(ref, ref.init, ReplayRNG(normals[:, c], unif[:, c]), steps, burnin)
+            assert np.array_equal(raw["jmax"][:, c], o["jmax"]), (raw["jmax"][:, c], o["jmax"])
+            assert relerr(raw["epsilon"][:, c], o["epsilon"]) < 1e-9
+            assert relerr(raw["draws"][:, c], o["draws"]) < 1e-9
+            assert np.array_equal(raw["accept"][:, c], o["accept"])
+            tot += o["nleap"]
+        assert raw["n_leapfrogs"] == tot
+
+
+def test_posterior_moments_linear(smc):
+    """posterior mean / variance of the conjugate model within Monte-Carlo standard error"""
+    X, Y, _ = linear_data()
+    M = 10
+    P = np.linalg.inv(X.T @ X + np.eye(M))
+    mean, var = P @ X.T @ Y, np.diag(P)
+    for kind, kw in (("hmc", dict(isteps=4, stepsize=0.03)), ("nuts", {}), ("rwm", {})):
+        fn = dict(hmc=smc.simpleHMC, nuts=smc.simpleNUTS, rwm=smc.simpleRWM)[kind]
+        steps, burnin = (3000, 1000) if kind != "rwm" else (6000, 3000)
+        res = fn(LINEAR, steps=steps, burnin=burnin, chains=128, seed=3, data=dict(X=X, Y=Y), beta=np.zeros(M), **kw)
+        d = res.params["beta"]                       # M x samples x chains
+        ess = max(res.ess[0], 200.0)
+        assert np.all(np.abs(d.mean(axis=(1, 2)) - mean) < 6 * np.sqrt(var / ess)), kind
+        assert np.all(np.abs(d.var(axis=(1, 2)) / var - 1) < 0.15), kind
+        assert np.all(res.misc["rhat"] < 1.1), kind
+
+
+# test/test2.jl:61-85: 17 univariate targets; KS statistic sqrt(n) * max|ECDF - CDF| below the reference's threshold 5
+TARGETS = [("Normal(1, 1)", stats.norm(1, 1), 0.0), ("Normal(3, 12)", stats.norm(3, 12), 3.0),
+           ("Weibull(1, 1)", stats.weibull_min(1, scale=1), 1.0), ("Weibull(3, 1)", stats.weibull_min(3, scale=1), 1.0),
+           ("Uniform(0, 2)", stats.uniform(0, 2), 1.0), ("TDist(2.2)", stats.t(2.2), 0.0), ("TDist(4)", stats.t(4), 0.0),
+           ("Beta(1, 2)", stats.beta(1, 2), 0.5), ("Beta(3, 2)", stats.beta(3, 2), 0.5),
+           ("Gamma(1, 2)", stats.gamma(1, scale=2), 1.0), ("Gamma(3, 0.2)", stats.gamma(3, scale=0.2), 1.0),
+           ("Cauchy(0, 1)", stats.cauchy(0, 1), 0.0), ("Cauchy(-1, 0.2)", stats.cauchy(-1, 0.2), -1.0),
+           ("Exponential(3)", stats.expon(scale=3), 1.0), ("Exponential(0.2)", stats.expon(scale=0.2), 1.0),
+           ("logNormal(-1, 1)", stats.lognorm(1, scale=math.exp(-1)), 1.0), ("logNormal(2, 0.1)", stats.lognorm(0.1, scale=math.exp(2)), 7.0)]
+
+
+def _ks(sample, dist):
+    x = np.sort(sample)
+    n = len(x)
+    cdf = dist.cdf(x)
+    return math.sqrt(n) * max(np.max(np.abs(np.arange(1, n + 1) / n - cdf)), np.max(np.abs(np.arange(0, n) / n - cdf)))
+
+
+@pytest.mark.parametrize("sampler", ["rwm", "hmc", "nuts"])
+def test_ks_univariate_targets(smc, sampler):
+    """test/test2.jl:25-55 with 64 chains: every chain separately must pass the reference's threshold on thinned draws"""
+    for spec, dist, x0 in TARGETS:
+        model = "x ~ %s" % spec
+        std = dist.std() if np.isfinite(dist.std()) else 1.0
+        if sampler == "hmc":
+            res = smc.simpleHMC(model, steps=10000, burnin=1000, isteps=2, stepsize=std / 5, chains=64, seed=1, x=x0)   # test2.jl:44
+        elif sampler == "nuts":
+            res = smc.simpleNUTS(model, steps=3000, burnin=1000, chains=64, seed=1, x=x0)
+        else:
+            res = smc.simpleRWM(model, steps=10000, burnin=1000, chains=64, seed=1, x=x0)
+        d = res.params["x"]                  # samples x chains
+        ks = [_ks(d[:, c], dist) for c in range(0, 64, 8)]
+        assert np.median(ks) < 5.0, (sampler, spec, ks)     # threshold of test2.jl:13-14 (autocorrelated draws)

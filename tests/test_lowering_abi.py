@@ -1,0 +1,119 @@
+"""Host logic of the product (no GPU needed): model -> tape lowering, tape serialisation against the C header,
+GLM fusion, and that the C-ABI library loads and exports every symbol include/simplemcmc.h declares."""
+import ctypes
+import os
+import re
+import struct
+
+import numpy as np
+import pytest
+
+from smc_pkg import load_package
+from util import HIERARCHICAL, LINEAR, LOGISTIC, ORNSTEIN, SLEEPSTUDY2, hierarchical_data, linear_data, logistic_data, ou_data, sleepstudy_data
+
+load_package()
+from simplemcmc_jl_b200 import capi, lowering  # noqa: E402
+from simplemcmc_jl_b200.lowering import Lowering, ModelError  # noqa: E402
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_enums(path):
+    txt = open(path).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return {m.group(1): int(m.group(2)) for m in re.finditer(r"\b(SMC_[A-Z0-9_]+)\s*=\s*(\d+)", txt)}
+
+
+def test_python_constants_match_the_c_header():
+    e = _header_enums(os.path.join(ROOT, "include", "simplemcmc_tape.h"))
+    for name, val in lowering.OP.items():
+        assert e["SMC_OP_" + name] == val, name
+    for name, val in lowering.DIST.items():
+        assert e["SMC_DIST_" + name.upper()] == val, name
+    assert (e["SMC_REG_IMM"], e["SMC_REG_DATA"], e["SMC_REG_HDR"], e["SMC_REG_CHAIN"], e["SMC_REG_PARAM"], e["SMC_REG_GRAD"]) == (0, 1, 2, 3, 4, 5)
+    assert e["SMC_GLM_NORMAL"] == lowering.GLM_NORMAL and e["SMC_GLM_BERNOULLI"] == lowering.GLM_BERNOULLI
+    txt = open(os.path.join(ROOT, "include", "simplemcmc_tape.h")).read()
+    assert "#define SMC_TAPE_VERSION %du" % lowering.TAPE_VERSION in txt
+
+
+def test_library_loads_and_exports_the_whole_abi():
+    hdr = open(os.path.join(ROOT, "include", "simplemcmc.h")).read()
+    declared = set(re.findall(r"\b(smc_[a-z_0-9]+)\s*\(", hdr))
+    lib = capi.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert declared == set(capi.EXPORTS)
+    assert lib.smc_abi_version() == 1
+    assert ctypes.sizeof(capi.SamplerConfig) == 80 and ctypes.sizeof(capi.RunOutput) == 104
+
+
+def test_ctx_create_fails_loudly_without_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(capi.SMCError) as e:
+        capi.Context(0)
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_linear_lowering_fuses_the_glm():
+    X, Y, _ = linear_data()
+    low = Lowering(LINEAR, [("beta", np.zeros(10))], dict(X=X, Y=Y))
+    fw, bw = low.statements()
+    assert low.n_fused == 1 and [s.op for s in fw].count(lowering.OP["GLM"]) == 1
+    assert not any(s.dst.numel == 1000 for s in fw + bw)          # no length-N per-chain register survives
+    tape, bound = low.serialise()
+    magic, ver, nreg, nst, npar, ndata, nidx, res, flags, nfwd, _, _ = struct.unpack_from("<12I", tape)
+    assert (magic, ver, npar, ndata, nfwd) == (0x54434D53, 2, 10, 2, len(fw))
+    assert len(tape) == 48 + 32 * nreg + 56 * nst + 64 * ndata
+    assert sorted(n for n, _ in bound) == ["X", "Y"]
+    unf = Lowering(LINEAR, [("beta", np.zeros(10))], dict(X=X, Y=Y), fuse=False)
+    assert unf.n_fused == 0 and any(s.op == lowering.OP["MATMUL"] and s.flags & lowering.F_TRANS_A for s in unf.bwd)
+
+
+def test_logistic_lowering_fuses_with_the_reference_sign():
+    X, Y, _ = logistic_data()
+    low = Lowering(LOGISTIC, [("vars", np.zeros(10))], dict(X=X, Y=Y))
+    glm = [s for s in low.fwd if s.op == lowering.OP["GLM"]]
+    assert len(glm) == 1 and glm[0].aux0 == lowering.GLM_BERNOULLI and glm[0].aux1 == 0    # prob = 1/(1+exp(+eta))
+    low2 = Lowering("v ~ Normal(0,1)\nprob = 1. / (1. + exp(-(X * v)))\nY ~ Bernoulli(prob)", [("v", np.zeros(10))], dict(X=X, Y=Y))
+    glm2 = [s for s in low2.fwd if s.op == lowering.OP["GLM"]]
+    assert len(glm2) == 1 and glm2[0].aux1 == 1
+
+
+def test_example_models_lower():
+    x = ou_data(200)
+    low = Lowering(ORNSTEIN, [("tau", 20.0), ("mu", 10.0), ("sigma", 0.1)], dict(x=x))
+    assert low.bsize == 3 and len(low.idx_tables) == 2
+    hdr = [s for s in low.fwd if s.dst.kind == lowering.REG_HDR]
+    assert len(hdr) == 2                                           # x[2:end], x[1:end-1] are hoisted (parsing.jl:432-442)
+    data, (N, D, L) = hierarchical_data()
+    low = Lowering(HIERARCHICAL, [("mu", np.zeros((1, L))), ("sigma", np.ones((1, L))), ("beta", np.zeros((D, L)))], data)
+    assert low.bsize == 30 and [p.start for p in low.pars] == [0, 5, 10]
+    assert any(s.op == lowering.OP["SCATTER_SET"] for s in low.bwd)
+    low = Lowering(HIERARCHICAL, [("mu", np.zeros((1, L))), ("sigma", np.ones((1, L))), ("beta", np.zeros((D, L)))], data, ref_adjoint="add")
+    assert any(s.op == lowering.OP["SCATTER_ADD"] for s in low.bwd)
+    data, nsub = sleepstudy_data()
+    low = Lowering(SLEEPSTUDY2, [("intercept", 250.0), ("slope", 10.0), ("rand_int", np.zeros(nsub)), ("rand_slope", np.zeros(nsub))], data)
+    assert low.bsize == 38
+
+
+def test_reference_error_cases():
+    with pytest.raises(ModelError):
+        Lowering("sum(logpdfBernoulli(1, x))", [("x", np.array([0.0]))], {})
+    with pytest.raises(ModelError):
+        Lowering("y = 2 * x\nz ~ Normal(0, 1)", [("x", 1.0)], dict(z=np.ones(3)))
+    with pytest.raises(ModelError):
+        Lowering("x ~ Normal(0, 1)", [], {})
+    with pytest.raises(ModelError):
+        Lowering("x ~ Normal(w, 1)", [("x", 1.0)], {})             # undefined external variable
+    with pytest.raises(ModelError):
+        Lowering("y = x .* z\ny ~ Normal(0, 1)", [("x", np.zeros(3))], dict(z=np.ones(4)))   # dimension mismatch
+
+
+def test_parameter_packing_is_keyword_order_column_major():
+    """setInit!, src/parsing.jl:303-334"""
+    m = np.arange(6.0).reshape(2, 3)
+    low = Lowering("a ~ Normal(0,1)\nb ~ Normal(0,1)\nc ~ Normal(0,1)", [("b", m), ("a", 1.5), ("c", np.array([7.0, 8.0]))], {})
+    assert low.init == [0.0, 3.0, 1.0, 4.0, 2.0, 5.0, 1.5, 7.0, 8.0]
+    assert [(p.sym, p.start, p.count) for p in low.pars] == [("b", 0, 6), ("a", 6, 1), ("c", 7, 2)]

@@ -628,7 +628,14 @@ __global__ void k_nuts_post(RngSrc rng, long long step, long long C, long long M
   const int j = T.j[c];
   int level = 0;
   int ucount = T.ucount[c];
-  while ((leaf >> level) & 1) {
+  for (;; level++) {
+    if (level >= j) break;
+    if (!((leaf >> level) & 1)) {
+      // this sub-tree is a first child here: complete trees wait on the stack; a cut tree is handed up unchanged
+      // (`if s1` is false, :239) and may still be merged, as a second child, further up
+      if (s2) break;
+      continue;
+    }
     const long long so = (long long)level * LS, sc = (long long)level * Cpad + c;
     double n1 = T.kn[sc];
     double r = rng_uniform(rng, step, c, C, ucount++);
@@ -647,7 +654,6 @@ __global__ void k_nuts_post(RngSrc rng, long long step, long long C, long long M
       s2 = !ut;
     }
     n2 += n1;
-    level++;
   }
   bool done = (!s2) || (leaf == (1 << j) - 1);
   if (!done) {

@@ -1,0 +1,85 @@
+"""Secondary measurements for the other BASELINE.json configs (device-resident, CUDA-event timed inside the library):
+cfg1 linear N=1000 M=10 with many chains, cfg3 logistic (one GPU, all rows), cfg4 NUTS on the sleepstudy model,
+cfg5 Ornstein-Uhlenbeck RWM/HMC/NUTS sweep.  Writes one JSON object to stdout."""
+import json, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np
+from smc_pkg import load_package
+load_package()
+from simplemcmc_jl_b200 import api
+from util import LINEAR, LOGISTIC, ORNSTEIN, SLEEPSTUDY2, linear_data, ou_data, sleepstudy_data
+
+out = {}
+which = sys.argv[1:] or ["cfg1", "cfg3", "cfg4", "cfg5"]
+
+if "cfg1" in which:
+    X, Y, _ = linear_data(1000, 10, 1)
+    mode = np.linalg.solve(X.T @ X + np.eye(10), X.T @ Y)
+    rows = []
+    for C in (1, 1024, 65536, 1 << 20):
+        low, dev = api._build(LINEAR, [("beta", np.zeros(10))], dict(X=X, Y=Y), True, C, 0, "assign")
+        steps = 2000 if C == 1 else (200 if C <= 65536 else 40)
+        dev.run("hmc", mode, C, 5, 0, isteps=2, stepsize=0.05, seed=1, store_draws=False, want=())
+        raw = dev.run("hmc", mode, C, steps, 0, isteps=2, stepsize=0.05, seed=2, store_draws=False, want=())
+        dev.eval(np.tile(mode, (C, 1)))
+        ms_eval, ms_glm = dev.eval_timed(5, False)
+        rows.append(dict(chains=C, steps=steps, leapfrog_chain_steps_per_s=raw["n_leapfrogs"] / (raw["device_ms"] * 1e-3),
+                         accept=float(raw["accept_rate"].mean()), ms_eval=ms_eval, ms_glm=ms_glm,
+                         glm_tflops_algorithmic=4.0 * 1000 * 10 * C / (ms_glm * 1e-3) / 1e12, launches=raw["n_kernel_launches"]))
+        dev.close()
+    out["cfg1_linear_N1000_M10_hmc"] = rows
+
+if "cfg3" in which:
+    rng = np.random.default_rng(3)
+    N, M = 10_000_000, 10
+    X = np.empty((M, N)).T
+    X[:, 0] = 1.0
+    for j in range(1, M):
+        X[:, j] = rng.standard_normal(N)
+    b0 = rng.standard_normal(M)
+    Y = (rng.random(N) < 1.0 / (1.0 + np.exp(X @ b0))).astype(np.float64)
+    rows = []
+    for C in (1, 8, 64):
+        low, dev = api._build(LOGISTIC, [("vars", np.zeros(M))], dict(X=X, Y=Y), True, C, 0, "assign")
+        init = b0[None, :] + 1e-3 * rng.standard_normal((C, M))
+        raw = dev.run("hmc", init, C, 10, 0, isteps=2, stepsize=0.1 / np.sqrt(N / 1000), seed=1, store_draws=False, want=())
+        dev.eval(init)
+        ms_eval, ms_glm = dev.eval_timed(5, True)
+        bytes_alg = 8.0 * N * M + 8.0 * N
+        rows.append(dict(chains=C, leapfrog_chain_steps_per_s=raw["n_leapfrogs"] / (raw["device_ms"] * 1e-3),
+                         accept=float(raw["accept_rate"].mean()), ms_eval=ms_eval, ms_glm=ms_glm,
+                         glm_gbs_algorithmic=bytes_alg / (ms_glm * 1e-3) / 1e9, glm_gbs_padded=(8.0 * N * 16 + 8.0 * N) / (ms_glm * 1e-3) / 1e9))
+        dev.close()
+    out["cfg3_logistic_N1e7_M10_hmc_1gpu"] = rows
+
+if "cfg4" in which:
+    data, nsub = sleepstudy_data()
+    init = [("intercept", 250.0), ("slope", 10.0), ("rand_int", np.zeros(nsub)), ("rand_slope", np.zeros(nsub))]
+    rows = []
+    for C in (1024, 16384):
+        low, dev = api._build(SLEEPSTUDY2, init, data, True, C, 0, "assign")
+        steps = 60
+        t0 = time.time()
+        raw = dev.run("nuts", np.array(low.init), C, steps, 0, seed=1, store_draws=False, want=())
+        rows.append(dict(chains=C, steps=steps, leapfrogs_per_s=raw["n_leapfrogs"] / (raw["device_ms"] * 1e-3),
+                         iterations_per_s=C * steps / (raw["device_ms"] * 1e-3), evals=raw["n_evals"],
+                         active_lane_fraction=raw["n_leapfrogs"] / (max(raw["n_evals"] - 1, 1) * C), wall_s=time.time() - t0,
+                         mean_jmax=float(raw["jmax"].mean()), launches=raw["n_kernel_launches"]))
+        dev.close()
+    out["cfg4_sleepstudy_38params_nuts"] = rows
+
+if "cfg5" in which:
+    x = ou_data(1_000_000, 5)
+    init = [("tau", 20.0), ("mu", 10.0), ("sigma", 0.1)]
+    rows = []
+    for C in (1, 64):
+        for kind, kw, steps in (("rwm", {}, 20), ("hmc", dict(isteps=2, stepsize=1e-4), 10), ("nuts", {}, 4)):
+            low, dev = api._build(ORNSTEIN, init, dict(x=x), kind != "rwm", C, 0, "assign")
+            raw = dev.run(kind, np.array(low.init), C, steps, 0, seed=1, store_draws=False, want=(), **kw)
+            rows.append(dict(sampler=kind, chains=C, steps=steps, chain_steps_per_s=C * steps / (raw["device_ms"] * 1e-3),
+                             evals_per_s=C * (raw["n_evals"] - 1) / (raw["device_ms"] * 1e-3), accept=float(raw["accept_rate"].mean()),
+                             launches=raw["n_kernel_launches"]))
+            dev.close()
+    out["cfg5_ornstein_T1e6"] = rows
+
+print(json.dumps(out, indent=1))

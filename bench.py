@@ -18,7 +18,6 @@ import json
 import os
 import subprocess
 import sys
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -64,33 +63,55 @@ def posterior_mode(X, Y):
     return np.linalg.solve(X.T @ X + np.eye(m), X.T @ Y)
 
 
-class ClockSampler(threading.Thread):
-    def __init__(self, gpu_index):
-        threading.Thread.__init__(self, daemon=True)
-        self.gpu, self.rows, self.stop_flag = gpu_index, [], False
+class ClockSampler(object):
+    """one long-lived `nvidia-smi -lms` process (the recipe of B200_PROFILING.md): started before the warm-up, so that
+    no process is spawned inside the timed region, killed after it"""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def run(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
-            except Exception:
-                pass
-            time.sleep(0.1)
+    def __init__(self, gpu_index):
+        self.t_start = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=timestamp," + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def mark(self):
+        """samples taken after this call belong to the timed region"""
+        self.t_start = time.time()
 
     def summary(self):
-        self.stop_flag = True
-        if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        t_end = time.time()
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out = self.proc.communicate(timeout=5)[0]
+        except Exception:
+            out = ""
+        rows = []
+        import datetime
+        for ln in out.strip().splitlines():
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+            except Exception:
+                ts = None
+            rows.append((ts, parts[1:]))
+        timed = [r for ts, r in rows if ts is not None and self.t_start is not None and self.t_start - 0.05 <= ts <= t_end + 0.05]
+        use = timed if timed else [r for _, r in rows[-5:]]
+        if not use:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(float(r[0]) for r in use if r[0].replace(".", "").isdigit())
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for k, n in enumerate(names) if any(len(r) > 2 + k and r[2 + k].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
-                "samples": len(self.rows)}
+        reasons = [n for k, n in enumerate(names) if any(r[2 + k].lower().startswith("active") for r in use)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(use[0][1]), "reasons": reasons,
+                "samples_in_timed_region": len(timed), "samples_total": len(rows)}
 
 
 def fp64_peak():
@@ -162,16 +183,16 @@ def run_ours(args):
     # ---------------- device-resident throughput: data bound once, K steps timed with CUDA events in the library
     ctx = capi.Context.default(local)
     low, dev = api._build(MODEL, [("beta", np.zeros(N_COLS))], data, True, C, local, "assign", comm=ctx)
+    clocks = ClockSampler(local)
     dev.run("hmc", init, C, W, 0, isteps=ISTEPS, stepsize=STEPSIZE, seed=5, chain_offset=rank * C, store_draws=False,
             want=())                                                                   # warm-up steps
-    clocks = ClockSampler(local)
-    clocks.start()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
     barrier()
+    clocks.mark()
     t0 = time.time()
     raw = dev.run("hmc", init, C, K, 0, isteps=ISTEPS, stepsize=STEPSIZE, seed=6, chain_offset=rank * C, store_draws=False,
                   want=())

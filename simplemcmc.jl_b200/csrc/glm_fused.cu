@@ -22,14 +22,15 @@ namespace {
 
 struct GlmArgs {
   const double* X;     // [N][MP] row major, zero padded
-  const double* y;     // [N] or nullptr (then y_scalar)
+  const double* y;     // [N] response as consumed by the family (sign-normalised)
   const double* beta;  // [M][Cpad]
   double* part;        // [RS][MP+1][Cpad]
   int* bad;
   long long N, rows_per_split, C, Cpad;
   int M;
-  double par, y_scalar;
-  int sa_neg, sb_neg;  // NORMAL: z = sa*eta + sb*y ; BERNOULLI: u = sa*eta
+  double par;
+  int neg_beta;  // BERNOULLI with prob = 1/(1+exp(-eta)): the contraction runs on -beta, so it yields u = -eta directly
+  int neg_out;   // ... and G = X' dl/deta = -(X' dl/du)
 };
 
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
@@ -49,34 +50,43 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
+// NORMAL.  The reference computes z = x - mu with x/mu = +-eta, -+y; with w = eta - ytilde
+// (ytilde = y, or -y when eta and y enter with the same sign: prepared on the host side of the launch) z = +-w, so
+//   l = -r*r/2 - log(sigma) - log(sqrt(2pi)),  r = w/sigma            (src/distribs.jl:23-28)
+//   dl/deta = -w/sigma^2                                               (src/diff.jl:99 through the +- of diff.jl:36-38)
+// The constant -log(sigma) - log(sqrt(2pi)) is added once per row split in the epilogue; zero-filled tail rows
+// (X = 0, y = 0) contribute w = 0.
+// BERNOULLI.  prob = 1/(1+exp(u)), l = y ? log(prob) : log(1-prob)   (examples/binomial.jl:15, src/distribs.jl:12-21)
+//   dl/du = exp(u) * (-1/t4^2) * 1/(prob-(1-y)) = y ? -e*prob : prob   (src/diff.jl:166,73,45)
 template <int FAM>
-__device__ __forceinline__ void family_eval(double eta, double y, const GlmArgs& a, double inv_s, double c0, double& l,
+__device__ __forceinline__ void family_eval(double eta, double y, double inv_s, double neg_inv_s2, bool valid, double& lacc,
                                             double& d) {
   if (FAM == SMC_GLM_NORMAL) {
-    // z = x - mu ; r = z/sigma ; l = -r*r/2 - log(sigma) - log(sqrt(2pi))  (src/distribs.jl:23-28)
-    double z = (a.sa_neg ? -eta : eta) + (a.sb_neg ? -y : y);
-    double r = z * inv_s;
-    l = -r * r * 0.5 + c0;
-    double dz = -z * (inv_s * inv_s);  // (mu - x)/(sigma*sigma), src/diff.jl:99
-    d = a.sa_neg ? -dz : dz;
+    double w = eta - y;
+    double r = w * inv_s;
+    lacc = fma(r, r, lacc);   // accumulates sum r^2 ; scaled by -1/2 in the epilogue
+    d = w * neg_inv_s2;
   } else {
-    // prob = 1/(1+exp(u)) ; l = y ? log(prob) : log(1-prob)   (examples/binomial.jl:15, src/distribs.jl:12-21)
-    double u = a.sa_neg ? -eta : eta;
-    double e = exp(u), t4 = 1.0 + e, p = 1.0 / t4;
+    double e = exp(eta), t4 = 1.0 + e, p = 1.0 / t4;
     bool one = (y == 1.0);
-    l = one ? log(p) : log(1.0 - p);
-    double du = one ? -e * p : p;  // exp(u) * (-1/t4^2) * 1/(p-(1-y)), src/diff.jl:166,73,45
-    d = a.sa_neg ? -du : du;
-    if (!(y == 0.0 || y == 1.0)) l = nan("");
+    double l = log(one ? p : 1.0 - p);
+    d = one ? -e * p : p;
+    lacc += valid ? l : 0.0;
   }
 }
+
+// Row r of an 8-row block sits at MMA column n with r = n < 4 ? n : n ^ 1.  With rows padded to LD = MP + 4 doubles
+// (LD mod 16 in {4, 12}) this makes both operand reads bank-conflict free: product 1 reads rows {rowmap(g)} x 4
+// consecutive columns per half-warp, product 2 reads rows {rowmap(2q+s)} x 4 consecutive columns.
+__device__ __forceinline__ int rowmap(int n) { return n < 4 ? n : (n ^ 1); }
 
 template <int FAM, int MT, int NWC, int NWR, int MP8>
 __global__ void __launch_bounds__(NWC* NWR * 32, 1) k_glm(GlmArgs a) {
   constexpr int MP = MP8 * 8, LD = MP + 4, NT = NWC * NWR * 32;
   constexpr int RT = (MP8 >= 4) ? 64 : 128;  // rows per tile
-  constexpr int NST = 3;
-  constexpr int TC = NWC * MT * 8;  // chains per CTA
+  constexpr int NST = 4, PD = 1;             // stages / prefetch distance (see the software pipeline below)
+  constexpr int TC = NWC * MT * 8;           // chains per CTA
+  constexpr int BPW = RT / 8 / NWR;          // 8-row blocks per warp per tile
   static_assert(RT % (8 * NWR) == 0, "row tile must split evenly over the row warps");
   extern __shared__ __align__(16) double smem[];
   double* Xs = smem;                  // [NST][RT][LD]
@@ -98,22 +108,22 @@ __global__ void __launch_bounds__(NWC* NWR * 32, 1) k_glm(GlmArgs a) {
 #pragma unroll
     for (int ks = 0; ks < MP / 4; ks++) {
       int j = ks * 4 + q;
-      bfr[mt][ks] = (j < a.M && c < a.C) ? __ldg(a.beta + (long long)j * a.Cpad + c) : 0.0;
+      double bv = (j < a.M && c < a.C) ? __ldg(a.beta + (long long)j * a.Cpad + c) : 0.0;
+      bfr[mt][ks] = a.neg_beta ? -bv : bv;
     }
   }
   double G[MT][MP8][2];
   double lsum[MT];
-  int badmask = 0;
 #pragma unroll
   for (int mt = 0; mt < MT; mt++) {
     lsum[mt] = 0.0;
 #pragma unroll
     for (int nt = 0; nt < MP8; nt++) G[mt][nt][0] = G[mt][nt][1] = 0.0;
   }
-  double inv_s = 1.0, c0 = 0.0;
+  double inv_s = 1.0, neg_inv_s2 = 0.0;
   if (FAM == SMC_GLM_NORMAL) {
     inv_s = 1.0 / a.par;
-    c0 = -log(a.par) - SMC_LOG_SQRT_2PI;
+    neg_inv_s2 = -1.0 / (a.par * a.par);
   }
 
   auto load_tile = [&](int t) {
@@ -128,68 +138,99 @@ __global__ void __launch_bounds__(NWC* NWR * 32, 1) k_glm(GlmArgs a) {
         bool ok = row < row_end;
         cp_async16(xs + r * LD + ch * 2, a.X + (ok ? row : 0) * MP + ch * 2, ok ? 16 : 0);
       }
-      if (a.y)
-        for (int r = tid; r < RT; r += NT) {
-          long long row = r0 + r;
-          bool ok = row < row_end;
-          cp_async8(yy + r, a.y + (ok ? row : 0), ok ? 8 : 0);
-        }
+      for (int r = tid; r < RT; r += NT) {
+        long long row = r0 + r;
+        bool ok = row < row_end;
+        cp_async8(yy + r, a.y + (ok ? row : 0), ok ? 8 : 0);
+      }
     }
     cp_async_commit();
   };
-
-#pragma unroll
-  for (int s = 0; s < NST - 1; s++) load_tile(s);
-
-  for (int t = 0; t < ntiles; t++) {
-    cp_async_wait<NST - 2>();
+  // tile t has landed for every thread; the stage of tile t-3 is free again
+  auto tile_begin = [&](int t) {
+    cp_async_wait<PD - 1>();
     __syncthreads();
-    load_tile(t + NST - 1);
-    const double* xs = Xs + (t % NST) * RT * LD;
+    load_tile(t + PD);
+  };
+  // product 1 on the block `gb` of this warp: acc[mt][s] = eta(chain cbase+mt*8+g, row rowmap(2q+s))
+  auto gemm1 = [&](int gb, double (&acc)[MT][2]) {
+    const int t = gb / BPW, rb = (wr + (gb % BPW) * NWR) * 8;
+    const double* xrow = Xs + (t % NST) * RT * LD + (rb + rowmap(g)) * LD + q;
+#pragma unroll
+    for (int mt = 0; mt < MT; mt++) acc[mt][0] = acc[mt][1] = 0.0;
+#pragma unroll
+    for (int ks = 0; ks < MP / 4; ks++) {
+      double xb = xrow[ks * 4];
+#pragma unroll
+      for (int mt = 0; mt < MT; mt++) dmma884(acc[mt][0], acc[mt][1], bfr[mt][ks], xb);
+    }
+  };
+
+  // family stage of block gb (registers only): d[mt][s] = dl/deta, lsum += l
+  auto family = [&](int gb, const double (&acc)[MT][2], double (&dd)[MT][2]) {
+    const int t = gb / BPW, rb = (wr + (gb % BPW) * NWR) * 8;
     const double* yy = ys + (t % NST) * RT;
     const long long r0 = row_begin + (long long)t * RT;
-#pragma unroll 1
-    for (int b = wr; b < RT / 8; b += NWR) {
-      const int rb = b * 8;
-      if (r0 + rb >= row_end) break;
-      double acc[MT][2];
 #pragma unroll
-      for (int mt = 0; mt < MT; mt++) acc[mt][0] = acc[mt][1] = 0.0;
-      const double* xrow = xs + (rb + g) * LD + q;
+    for (int s = 0; s < 2; s++) {
+      int r = rb + rowmap(2 * q + s);
+      bool valid = (r0 + r) < row_end;
+      double y = yy[r];
 #pragma unroll
-      for (int ks = 0; ks < MP / 4; ks++) {
-        double xb = xrow[ks * 4];
+      for (int mt = 0; mt < MT; mt++) family_eval<FAM>(acc[mt][s], y, inv_s, neg_inv_s2, valid, lsum[mt], dd[mt][s]);
+    }
+  };
+  // product 2 on block gb: G[chain][j] += d[chain][row] * X[row][j]
+  auto gemm2 = [&](int gb, const double (&dd)[MT][2]) {
+    const int t = gb / BPW, rb = (wr + (gb % BPW) * NWR) * 8;
+    const double* xs = Xs + (t % NST) * RT * LD;
 #pragma unroll
-        for (int mt = 0; mt < MT; mt++) dmma884(acc[mt][0], acc[mt][1], bfr[mt][ks], xb);
-      }
-      // acc[mt][s] = eta(chain cbase+mt*8+g, row rb+2q+s)
-      double dd[MT][2];
+    for (int s = 0; s < 2; s++) {
+      const double* xr2 = xs + (rb + rowmap(2 * q + s)) * LD + g;
 #pragma unroll
-      for (int s = 0; s < 2; s++) {
-        int r = rb + 2 * q + s;
-        bool valid = (r0 + r) < row_end;
-        double y = a.y ? yy[r] : a.y_scalar;
+      for (int nt = 0; nt < MP8; nt++) {
+        double xb = xr2[nt * 8];
 #pragma unroll
-        for (int mt = 0; mt < MT; mt++) {
-          double l, d;
-          family_eval<FAM>(acc[mt][s], y, a, inv_s, c0, l, d);
-          if (!valid) { l = 0.0; d = 0.0; }
-          if (l == -INFINITY || isnan(l)) { badmask |= (1 << mt); l = 0.0; d = 0.0; }
-          lsum[mt] += l;
-          dd[mt][s] = d;
-        }
-      }
-#pragma unroll
-      for (int s = 0; s < 2; s++) {
-        const double* xr2 = xs + (rb + 2 * q + s) * LD + g;
-#pragma unroll
-        for (int nt = 0; nt < MP8; nt++) {
-          double xb = xr2[nt * 8];
-#pragma unroll
-          for (int mt = 0; mt < MT; mt++) dmma884(G[mt][nt][0], G[mt][nt][1], dd[mt][s], xb);
-        }
+        for (int mt = 0; mt < MT; mt++) dmma884(G[mt][nt][0], G[mt][nt][1], dd[mt][s], xb);
       }
     }
+  };
+
+  // Software pipeline over this warp's 8-row blocks, depth 2: iteration gb issues product 2 of block gb-1 and product 1 of
+  // block gb+1 (64 DMMAs) and, in their issue shadow, the family stage of block gb, whose result is only consumed one
+  // iteration later -- so no FP64-pipe time is lost to the elementwise stage.  Block counts are uniform over the CTA
+  // (tail blocks are zero filled); a tile's stage is reused 3 tiles later (NST = 4, prefetch distance 1).
+  const int total = ntiles * BPW;
+  load_tile(0);
+  if (total > 0) {
+    int tile_ready = -1;
+    auto need_tile = [&](int gb) {
+      int t = gb / BPW;
+      if (t > tile_ready) { tile_begin(t); tile_ready = t; }
+    };
+    double accA[MT][2], accB[MT][2], ddP[MT][2], ddC[MT][2];
+    need_tile(0);
+    gemm1(0, accA);
+    family(0, accA, ddP);
+    {
+      const int nxt = min(1, total - 1);
+      need_tile(nxt);
+      gemm1(nxt, accA);
+    }
+#pragma unroll 1
+    for (int gb = 1; gb < total; gb++) {
+      const int nxt = min(gb + 1, total - 1);
+      need_tile(nxt);
+      gemm2(gb - 1, ddP);
+      gemm1(nxt, accB);
+      family(gb, accA, ddC);
+#pragma unroll
+      for (int mt = 0; mt < MT; mt++) {
+        accA[mt][0] = accB[mt][0]; accA[mt][1] = accB[mt][1];
+        ddP[mt][0] = ddC[mt][0]; ddP[mt][1] = ddC[mt][1];
+      }
+    }
+    gemm2(total - 1, ddP);
   }
   cp_async_wait<0>();
   __syncthreads();
@@ -198,15 +239,12 @@ __global__ void __launch_bounds__(NWC* NWR * 32, 1) k_glm(GlmArgs a) {
   double* Gs = smem;             // [MP+1][TC]  (row MP = L)
   int* bs = (int*)(smem + (MP + 1) * TC);  // [TC]
   for (int i = tid; i < (MP + 1) * TC; i += NT) Gs[i] = 0.0;
-  for (int i = tid; i < TC; i += NT) bs[i] = 0;
   __syncthreads();
 #pragma unroll
   for (int mt = 0; mt < MT; mt++) {
     lsum[mt] += __shfl_xor_sync(0xffffffffu, lsum[mt], 1);
     lsum[mt] += __shfl_xor_sync(0xffffffffu, lsum[mt], 2);
   }
-  badmask |= __shfl_xor_sync(0xffffffffu, badmask, 1);
-  badmask |= __shfl_xor_sync(0xffffffffu, badmask, 2);
   for (int w = 0; w < NWR; w++) {
     if (wr == w) {
 #pragma unroll
@@ -217,23 +255,30 @@ __global__ void __launch_bounds__(NWC* NWR * 32, 1) k_glm(GlmArgs a) {
           Gs[(nt * 8 + 2 * q) * TC + cl] += G[mt][nt][0];
           Gs[(nt * 8 + 2 * q + 1) * TC + cl] += G[mt][nt][1];
         }
-        if (q == 0) {
-          Gs[MP * TC + cl] += lsum[mt];
-          if (badmask & (1 << mt)) bs[cl] = 1;
-        }
+        if (q == 0) Gs[MP * TC + cl] += lsum[mt];
       }
     }
     __syncthreads();
   }
   double* part = a.part + (long long)blockIdx.y * (MP + 1) * a.Cpad;
   const long long ct0 = (long long)blockIdx.x * TC;
+  const double nrows = (double)(row_end > row_begin ? row_end - row_begin : 0);
+  const double lconst = FAM == SMC_GLM_NORMAL ? nrows * (-log(a.par) - SMC_LOG_SQRT_2PI) : 0.0;
   for (int i = tid; i < (MP + 1) * TC; i += NT) {
     int j = i / TC, cl = i - j * TC;
     long long c = ct0 + cl;
-    if (c < a.C) part[(long long)j * a.Cpad + c] = Gs[i];
+    if (c >= a.C) continue;
+    double v = Gs[i];
+    if (j == MP) {
+      if (FAM == SMC_GLM_NORMAL) v = -0.5 * v + lconst;
+      // a -inf / NaN sum means some observation had zero density ("give up eval", src/distribs.jl:15,17)
+      if (!(v > -INFINITY)) a.bad[c] = 1;
+    } else if (a.neg_out) {
+      v = -v;
+    }
+    part[(long long)j * a.Cpad + c] = v;
   }
-  for (int cl = tid; cl < TC; cl += NT)
-    if (bs[cl] && ct0 + cl < a.C) a.bad[ct0 + cl] = 1;
+  (void)bs;
 }
 
 // out[j][c] = sum_rs part[rs][j][c]  (j = MP row is L); a chain flagged bad gets L = -inf so that the flag
@@ -244,7 +289,7 @@ __global__ void k_glm_reduce(const double* part, int RS, int MP, long long C, lo
     long long j = i / C, c = i - j * C;
     double t = 0.0;
     for (int r = 0; r < RS; r++) t += part[((long long)r * (MP + 1) + j) * Cpad + c];
-    if (j == MP && bad[c]) t = -INFINITY;
+    if (j == MP && (bad[c] || !(t > -INFINITY))) t = -INFINITY;
     out[j * Cpad + c] = t;
   }
 }
@@ -265,6 +310,14 @@ __global__ void k_glm_publish(const double* out, int M, int MP, long long C, lon
   }
 }
 
+// ytilde[i] = scale * (src ? (bcast ? src[0] : src[i]) : imm)   (bcast carries the immediate when src is null)
+__global__ void k_fill_y(const double* src, double imm_or_bcast, double scale, double* out, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    double v = src ? (imm_or_bcast != 0.0 ? src[0] : src[i]) : imm_or_bcast;
+    out[i] = scale * v;
+  }
+}
+
 __global__ void k_to_row_major(const double* Xcm, double* Xrm, long long N, int M, int MP) {
   long long total = N * MP;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -276,7 +329,7 @@ __global__ void k_to_row_major(const double* Xcm, double* Xrm, long long N, int 
 
 template <int FAM, int MT, int NWC, int NWR, int MP8>
 int launch_cfg(const GlmArgs& a, int RS, cudaStream_t st) {
-  constexpr int MP = MP8 * 8, LD = MP + 4, RT = (MP8 >= 4) ? 64 : 128, NST = 3, TC = NWC * MT * 8;
+  constexpr int MP = MP8 * 8, LD = MP + 4, RT = (MP8 >= 4) ? 64 : 128, NST = 4, TC = NWC * MT * 8;
   size_t pipe = (size_t)NST * RT * (LD + 1) * sizeof(double);
   size_t epi = (size_t)(MP + 1) * TC * sizeof(double) + TC * sizeof(int);
   size_t smem = std::max(pipe, epi);
@@ -356,22 +409,31 @@ int smc_glm_prepare(smc_model_s* m, SmcGlmPlan& g) {
   SMC_CUDA(cudaMalloc(&g.Xrm, (size_t)g.N * g.MP * sizeof(double)));
   k_to_row_major<<<(unsigned)std::min<long long>((g.N * g.MP + 255) / 256, 148LL * 64), 256, 0, st>>>(X.dev, g.Xrm, g.N, g.M, g.MP);
   m->ctx->launches++;
-  if (Y.d.kind == SMC_REG_IMM) { g.y = nullptr; g.y_scalar = Y.d.imm; }
-  else if (Y.numel == 1) {
-    SMC_CUDA(cudaMemcpyAsync(&g.y_scalar, Y.dev, sizeof(double), cudaMemcpyDeviceToHost, st));
-    SMC_CUDA(cudaStreamSynchronize(st));
-    g.y = nullptr;
-  } else {
-    if (Y.numel < g.N) { smc_set_error("GLM: response has %lld elements, X has %lld rows", (long long)Y.numel, (long long)g.N); return SMC_ERR_INVALID; }
-    g.y = Y.dev;
-    g.y_len = Y.numel;
+  // ytilde[N]: the response as the kernel consumes it (negated when eta and y enter the residual with the same sign,
+  // broadcast when the model uses a scalar)
+  double scale = 1.0;
+  if (g.family == SMC_GLM_NORMAL) {
+    int sa_neg = g.sign_neg & 1, sb_neg = (g.sign_neg >> 1) & 1;
+    scale = (sa_neg != sb_neg) ? 1.0 : -1.0;   // ytilde = -sa*sb*y
   }
+  SMC_CUDA(cudaMalloc(&g.ybuf, (size_t)g.N * sizeof(double)));
+  if (Y.d.kind == SMC_REG_IMM) {
+    k_fill_y<<<(unsigned)std::min<long long>((g.N + 255) / 256, 148LL * 32), 256, 0, st>>>(nullptr, Y.d.imm, scale, g.ybuf, g.N);
+  } else {
+    if (Y.numel != 1 && Y.numel < g.N) { smc_set_error("GLM: response has %lld elements, X has %lld rows", (long long)Y.numel, (long long)g.N); return SMC_ERR_INVALID; }
+    k_fill_y<<<(unsigned)std::min<long long>((g.N + 255) / 256, 148LL * 32), 256, 0, st>>>(Y.dev, Y.numel == 1 ? 1.0 : 0.0, scale, g.ybuf, g.N);
+  }
+  m->ctx->launches++;
+  g.y = g.ybuf;
+  g.y_len = g.N;
   return SMC_OK;
 }
 
 void smc_glm_release(SmcGlmPlan& g) {
   if (g.Xrm) cudaFree(g.Xrm);
   if (g.part) cudaFree(g.part);
+  if (g.ybuf) cudaFree(g.ybuf);
+  g.ybuf = nullptr;
   g.Xrm = nullptr;
   g.part = nullptr;
 }
@@ -397,8 +459,8 @@ int smc_glm_launch(smc_model_s* m, SmcGlmPlan& g, int64_t C) {
   if (m->regs[s.src[1]].d.kind != SMC_REG_PARAM) a.beta = m->regs[s.src[1]].dev;
   a.part = g.part; a.bad = m->bad;
   a.N = g.N; a.rows_per_split = rows_per_split; a.C = C; a.Cpad = m->Cpad; a.M = g.M;
-  a.par = g.par; a.y_scalar = g.y_scalar;
-  a.sa_neg = g.sign_neg & 1; a.sb_neg = (g.sign_neg >> 1) & 1;
+  a.par = g.par;
+  a.neg_beta = a.neg_out = (g.family == SMC_GLM_BERNOULLI && (g.sign_neg & 1)) ? 1 : 0;
   if (m->time_glm) SMC_CUDA(cudaEventRecord(m->ev0, st));
   int rc = g.family == SMC_GLM_NORMAL ? launch_fam<SMC_GLM_NORMAL>(a, g.MP, tc, RS, st)
                                       : launch_fam<SMC_GLM_BERNOULLI>(a, g.MP, tc, RS, st);

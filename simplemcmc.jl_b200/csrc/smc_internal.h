@@ -57,6 +57,7 @@ struct SmcGlmPlan {  // one SMC_OP_GLM statement, prepared at finalize
   int M = 0, MP = 0;   // columns and columns padded to a multiple of 8
   double* Xrm = nullptr;  // [N][MP] row major, zero padded
   const double* y = nullptr;
+  double* ybuf = nullptr;  // response as the kernel consumes it (sign-normalised, broadcast)
   int64_t y_len = 0;
   double y_scalar = 0.0;
   double* part = nullptr;  // partial (L,G) buffers [RS][MP+1][Cpad]

@@ -491,7 +491,10 @@ class Lowering(object):
         if lp is None or lp.op != OP["LOGPDF"] or lp.aux0 != DIST["Bernoulli"] or lp.srcs[0] is not div.dst:
             return None
         y = lp.srcs[1]
-        if y.varying or y.numel != N:
+        if y.kind != REG_DATA or y.numel != N:
+            return None
+        yv = self.data_slots[y.slot][1]
+        if not np.all((yv == 0.0) | (yv == 1.0)):    # the fused kernel assumes a 0/1 response (src/distribs.jl:18-19 errors otherwise)
             return None
         return GLM_BERNOULLI, sign, 0.0, y, lp, dead
 

@@ -155,9 +155,14 @@ def _finish(res, pars, raw, chains, t0, store_draws):
                 arr = arr[:, :, 0]
             res.params[p.sym] = arr.reshape(shape, order="F") if len(p.size) == 2 else arr.reshape(shape)
         if n >= 3:
-            per_comp = np.zeros(d.shape[2])
-            for j in range(d.shape[2]):
-                per_comp[j] = sum(_ess(d[:, c, j]) for c in range(min(chains, 64))) * (chains / min(chains, 64))
+            # lag-1 ESS of every (chain, component) series at once (calcStats!, src/samplers.jl:352-374); chains add up
+            a, b = d[1:], d[:-1]
+            cov = np.sum((a - a.mean(0)) * (b - b.mean(0)), axis=0) / (n - 2)
+            var = np.var(d, axis=0, ddof=1)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                fac = np.abs(cov) / var
+                ess = np.where(var > 0, n * np.maximum(0.0, 1.0 - fac) / (1.0 + fac), 0.0)
+            per_comp = ess.sum(axis=0)
             lo, hi = per_comp.min(), per_comp.max()
             res.ess = (lo, hi)
             res.essBySec = (lo / res.time, hi / res.time)

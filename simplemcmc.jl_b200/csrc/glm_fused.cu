@@ -12,6 +12,7 @@
 //
 // Grid: (chain tiles, row splits).  Each CTA writes a partial (L, G); a second kernel sums the row
 // splits in fixed order (deterministic) and publishes into the tape registers.
+#include <stdlib.h>
 #include <algorithm>
 #include "smc_internal.h"
 #include "dists.cuh"
@@ -347,7 +348,7 @@ int launch_cfg(const GlmArgs& a, int RS, cudaStream_t st) {
 template <int FAM, int MP8>
 int launch_mp(const GlmArgs& a, int tc, int RS, cudaStream_t st) {
   switch (tc) {
-    case 128: return launch_cfg<FAM, 2, 8, 1, MP8>(a, RS, st);
+    case 128: return launch_cfg<FAM, 2, 8, 1, MP8>(a, RS, st);   // (a 16-warp MT=1 variant measured 86.5% vs 88.0%)
     case 64: return launch_cfg<FAM, 2, 4, 2, MP8>(a, RS, st);
     case 32: return launch_cfg<FAM, 2, 2, 4, MP8>(a, RS, st);
     case 16: return launch_cfg<FAM, 2, 1, 8, MP8>(a, RS, st);

@@ -546,7 +546,8 @@ extern "C" int smc_model_finalize(smc_model_t m, int64_t max_chains, int row_sha
   for (auto& d : m->data)
     if (!d.bound) { smc_set_error("external variable '%s' is used by the model but was never bound", d.name.c_str()); return SMC_ERR_UNBOUND; }
   cudaStream_t st = m->ctx->stream;
-  int64_t Cpad = (max_chains + 31) / 32 * 32;
+  // chains are the contiguous axis of every per-chain array; pad to 32 only when that does not waste bandwidth
+  int64_t Cpad = max_chains >= 32 ? (max_chains + 31) / 32 * 32 : max_chains;
   bool realloc_chain = (Cpad != m->Cpad);
   m->Cmax = max_chains;
   m->row_shard = row_shard;

@@ -8,14 +8,15 @@
  * (/root/reference/src/diff.jl:94-174).
  *
  * blob := smc_tape_header, smc_tape_reg[n_regs], smc_tape_stmt[n_stmts], smc_tape_data[n_data],
- *         index tables: { uint32 n; uint32 pad; int32 idx[n rounded up to even] } * n_idx
+ *         index tables: { uint32 n; uint32 pad; int32 idx[n rounded up to even] } * n_idx,
+ *         programs (header.reserved[1] of them): see smc_prog_header
  */
 #ifndef SIMPLEMCMC_TAPE_H
 #define SIMPLEMCMC_TAPE_H
 #include <stdint.h>
 
 #define SMC_TAPE_MAGIC 0x54434D53u /* "SMCT" */
-#define SMC_TAPE_VERSION 2u
+#define SMC_TAPE_VERSION 3u
 
 /* register kinds */
 enum {
@@ -46,8 +47,20 @@ enum {
   SMC_OP_GATHER = 42,    /* dst[e] = src[idx[e]], aux0 = index table */
   SMC_OP_SCATTER_SET = 43, /* dst[idx[e]] = src[e]  -- the reference's ref adjoint (parsing.jl:277-281) */
   SMC_OP_SCATTER_ADD = 44, /* dst[idx[e]] += src[e] -- the corrected adjoint (TODO.md:11) */
-  SMC_OP_GLM = 48        /* fused  eta = X*beta ; L = sum_i l(eta_i, y_i) ; G = X' * dl/deta  (see smc_tape_stmt) */
+  SMC_OP_GLM = 48,       /* fused  eta = X*beta ; L = sum_i l(eta_i, y_i) ; G = X' * dl/deta  (see smc_tape_stmt) */
+  SMC_OP_FUSED = 49      /* a run of elementwise / reducing statements over one index space, executed as one register
+                            program (smc_prog_instr) without materialising its temporaries; aux0 = program, aux1 = n */
 };
+
+/* program-only opcodes (besides the elementwise opcodes above, which then act on program-local registers) */
+enum {
+  SMC_P_LOADV = 100,  /* local[dst] = tape register `reg` at the current element (and chain) */
+  SMC_P_LOADS = 101,  /* local[dst] = scalar tape register `reg` (prologue: once per thread) */
+  SMC_P_STOREV = 102, /* tape register `reg` at the current element = local[src0] */
+  SMC_P_REDUCE = 103  /* reduction slot aux0 += local[src0] */
+};
+#define SMC_PROG_MAX_LOCALS 48
+#define SMC_PROG_MAX_REDUCE 8
 
 /* distribution ids (src/distribs.jl:40-51) */
 enum {
@@ -71,7 +84,7 @@ typedef struct {
   uint32_t n_data, n_idx;
   uint32_t result_reg; /* scalar register holding the final accumulator */
   uint32_t flags;
-  uint32_t reserved[3]; /* reserved[0] = number of forward statements (the rest only serve the gradient) */
+  uint32_t reserved[3]; /* reserved[0] = number of forward statements (the rest only serve the gradient), reserved[1] = number of programs */
 } smc_tape_header;
 
 typedef struct {
@@ -91,5 +104,23 @@ typedef struct {
   char name[56];
   uint32_t rows, cols;
 } smc_tape_data;
+
+/* program := smc_prog_header, smc_prog_instr[n_instr] (the first n_prologue run once per thread), smc_prog_red[n_red] */
+typedef struct {
+  uint32_t n_instr, n_prologue, n_red, n;
+} smc_prog_header;
+
+typedef struct {
+  uint16_t op;
+  uint8_t dst, nsrc;
+  uint8_t src[3];
+  uint8_t flags; /* SMC_F_ACC: local[dst] += value */
+  uint16_t aux0, aux1;
+  uint32_t reg;
+} smc_prog_instr;
+
+typedef struct {
+  uint32_t reg, acc; /* destination scalar register of a reduction slot; acc: dst += total */
+} smc_prog_red;
 
 #endif

@@ -67,8 +67,8 @@ class ModelFunction(object):
         return (logp, grad) if self.gradient else logp
 
 
-def _build(model, init, data, gradient, chains, device, ref_adjoint, shard=None, comm=None, fuse=True):
-    low = Lowering(model, init, data, gradient=gradient, ref_adjoint=ref_adjoint, fuse=fuse)
+def _build(model, init, data, gradient, chains, device, ref_adjoint, shard=None, comm=None, fuse=True, fuse_statements=True):
+    low = Lowering(model, init, data, gradient=gradient, ref_adjoint=ref_adjoint, fuse=fuse, fuse_statements=fuse_statements)
     tape, bound = low.serialise()
     ctx = comm if isinstance(comm, capi.Context) else capi.Context.default(device)
     row_shard = (shard == "rows")

@@ -82,7 +82,7 @@ __device__ __forceinline__ void family_eval(double eta, double y, double inv_s, 
 __device__ __forceinline__ int rowmap(int n) { return n < 4 ? n : (n ^ 1); }
 
 template <int FAM, int MT, int NWC, int NWR, int MP8>
-__global__ void __launch_bounds__(NWC* NWR * 32, 1) k_glm(GlmArgs a) {
+__global__ void __launch_bounds__(NWC* NWR * 32, (MP8 <= 2 ? 2 : 1)) k_glm(GlmArgs a) {
   constexpr int MP = MP8 * 8, LD = MP + 4, NT = NWC * NWR * 32;
   constexpr int RT = (MP8 >= 4) ? 64 : 128;  // rows per tile
   constexpr int NST = 4, PD = 1;             // stages / prefetch distance (see the software pipeline below)
@@ -445,7 +445,7 @@ int smc_glm_launch(smc_model_s* m, SmcGlmPlan& g, int64_t C) {
   int tc = chain_tile_for(C);
   long long chain_tiles = (C + tc - 1) / tc;
   int RT = g.MP >= 32 ? 64 : 128;
-  int RS = row_splits_for(chain_tiles, g.N, RT, m->ctx->sm_count);
+  int RS = row_splits_for(chain_tiles, g.N, RT, m->ctx->sm_count * (g.MP <= 16 ? 2 : 1));  // narrow models run 2 CTAs per SM
   long long rows_per_split = ((g.N + RS - 1) / RS + RT - 1) / RT * RT;
   RS = (int)((g.N + rows_per_split - 1) / rows_per_split);
   int64_t need = (int64_t)(RS + 1) * (g.MP + 1) * m->Cpad;

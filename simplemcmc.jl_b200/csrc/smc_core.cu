@@ -123,6 +123,35 @@ extern "C" int smc_model_compile(smc_ctx_t ctx, const void* tape, size_t nbytes,
     m->idx_dev.push_back(d);
     m->idx_len.push_back(n);
   }
+  for (uint32_t i = 0; i < h.reserved[1]; i++) {
+    SmcProgram pr;
+    if ((size_t)(end - p) < sizeof(smc_prog_header)) { smc_set_error("tape: truncated program"); delete m; return SMC_ERR_INVALID; }
+    memcpy(&pr.h, p, sizeof(smc_prog_header));
+    p += sizeof(smc_prog_header);
+    size_t bytes = (size_t)pr.h.n_instr * sizeof(smc_prog_instr) + (size_t)pr.h.n_red * sizeof(smc_prog_red);
+    if ((size_t)(end - p) < bytes || pr.h.n_red > SMC_PROG_MAX_REDUCE || pr.h.n_prologue > pr.h.n_instr || pr.h.n_instr > 1024) {
+      smc_set_error("tape: malformed program %u", i); delete m; return SMC_ERR_INVALID;
+    }
+    pr.instr.resize(pr.h.n_instr);
+    memcpy(pr.instr.data(), p, (size_t)pr.h.n_instr * sizeof(smc_prog_instr));
+    p += (size_t)pr.h.n_instr * sizeof(smc_prog_instr);
+    pr.red.resize(pr.h.n_red);
+    memcpy(pr.red.data(), p, (size_t)pr.h.n_red * sizeof(smc_prog_red));
+    p += (size_t)pr.h.n_red * sizeof(smc_prog_red);
+    for (auto& in : pr.instr) {
+      bool ok = in.reg < h.n_regs && in.dst < SMC_PROG_MAX_LOCALS && in.nsrc <= 3;
+      for (int k = 0; ok && k < in.nsrc; k++) ok = in.src[k] < SMC_PROG_MAX_LOCALS;
+      if (in.op == SMC_P_REDUCE) ok = ok && in.aux0 < pr.h.n_red;
+      if (!ok) { smc_set_error("tape: program %u has an operand out of range", i); delete m; return SMC_ERR_INVALID; }
+    }
+    for (auto& r : pr.red)
+      if (r.reg >= h.n_regs) { smc_set_error("tape: program %u reduces into a bad register", i); delete m; return SMC_ERR_INVALID; }
+    SMC_CUDA(cudaMalloc(&pr.dev_instr, std::max<size_t>(1, pr.instr.size()) * sizeof(smc_prog_instr)));
+    SMC_CUDA(cudaMemcpy(pr.dev_instr, pr.instr.data(), pr.instr.size() * sizeof(smc_prog_instr), cudaMemcpyHostToDevice));
+    m->programs.push_back(pr);
+  }
+  for (auto& s : m->stmts)
+    if (s.op == SMC_OP_FUSED && s.aux0 >= m->programs.size()) { smc_set_error("tape: FUSED statement without a program"); delete m; return SMC_ERR_INVALID; }
   if (h.result_reg >= h.n_regs) { smc_set_error("tape: bad result register"); delete m; return SMC_ERR_INVALID; }
   m->M = h.n_params;
   *out = m;
@@ -142,6 +171,8 @@ extern "C" int smc_model_destroy(smc_model_t m) {
   for (auto& r : m->regs) if (r.owned && r.dev) cudaFree(r.dev);
   for (auto d : m->idx_dev) cudaFree(d);
   for (auto& g : m->glm) smc_glm_release(g);
+  for (auto& pr : m->programs) if (pr.dev_instr) cudaFree(pr.dev_instr);
+  if (m->dev_opds) cudaFree(m->dev_opds);
   if (m->beta) cudaFree(m->beta);
   if (m->grad) cudaFree(m->grad);
   if (m->logp) cudaFree(m->logp);
@@ -384,6 +415,95 @@ __global__ void k_cols_to_rows(const double* in, double* out, long long C, long 
   }
 }
 
+
+// ------------------------------------------------------------------------------------------ fused register programs
+// One launch runs a whole group of elementwise / reducing statements: thread = (chain lane, element lane); every
+// intermediate lives in the thread's register file R[] (local memory, L1 resident) instead of an [n][C] array in HBM.
+// Lanes map to chains first (coalesced per-chain operands, broadcast data operands), the rest of the block strides
+// over elements; reductions accumulate per thread, then over the element lanes in shared memory in fixed order, then
+// over element chunks in k_fused_final -- deterministic.
+struct FusedArgs {
+  const smc_prog_instr* prog;
+  const Opd* opds;  // indexed by tape register
+  int n_instr, n_pro, n_red, tcc;
+  long long n, C, chunk;
+  int* bad;
+  double* partial;  // [n_red][S][C]
+  int S;
+};
+
+__global__ void __launch_bounds__(256) k_fused(FusedArgs a) {
+  extern __shared__ __align__(16) unsigned char fsm[];
+  smc_prog_instr* ins = (smc_prog_instr*)fsm;
+  double* red = (double*)(fsm + ((a.n_instr * sizeof(smc_prog_instr) + 15) / 16) * 16);
+  for (int i = threadIdx.x; i < a.n_instr * 4; i += blockDim.x) ((uint32_t*)ins)[i] = ((const uint32_t*)a.prog)[i];
+  __syncthreads();
+  const int tcc = a.tcc, eyn = blockDim.x / tcc;
+  const int cx = threadIdx.x % tcc, ey = threadIdx.x / tcc;
+  const long long c = (long long)blockIdx.x * tcc + cx;
+  const bool active = c < a.C;
+  double R[SMC_PROG_MAX_LOCALS];
+  double racc[SMC_PROG_MAX_REDUCE];
+#pragma unroll
+  for (int k = 0; k < SMC_PROG_MAX_REDUCE; k++) racc[k] = 0.0;
+  if (active) {
+    for (int i = 0; i < a.n_pro; i++) R[ins[i].dst] = opd_ld(a.opds[ins[i].reg], 0, c);
+    const long long e0 = (long long)blockIdx.y * a.chunk, e1 = min(a.n, e0 + a.chunk);
+    for (long long e = e0 + ey; e < e1; e += eyn) {
+      for (int i = a.n_pro; i < a.n_instr; i++) {
+        const smc_prog_instr in = ins[i];
+        if (in.op == SMC_P_LOADV) {
+          R[in.dst] = opd_ld(a.opds[in.reg], e, c);
+        } else if (in.op == SMC_P_LOADS) {
+          R[in.dst] = opd_ld(a.opds[in.reg], 0, c);
+        } else if (in.op == SMC_P_STOREV) {
+          const Opd& o = a.opds[in.reg];
+          const_cast<double*>(o.p)[e * o.se + c * o.sc] = R[in.src[0]];
+        } else if (in.op == SMC_P_REDUCE) {
+          racc[in.aux0] += R[in.src[0]];
+        } else {
+          double x0 = in.nsrc > 0 ? R[in.src[0]] : 0.0;
+          double x1 = in.nsrc > 1 ? R[in.src[1]] : 0.0;
+          double x2 = in.nsrc > 2 ? R[in.src[2]] : 0.0;
+          double v = smc_apply(in.op, in.aux0, in.aux1, x0, x1, x2);
+          if (in.op == SMC_OP_LOGPDF && (v == -INFINITY || isnan(v))) { a.bad[c] = 1; v = 0.0; }
+          R[in.dst] = (in.flags & SMC_F_ACC) ? R[in.dst] + v : v;
+        }
+      }
+    }
+  }
+  if (a.n_red > 0) {
+    for (int k = 0; k < a.n_red; k++) red[k * blockDim.x + threadIdx.x] = racc[k];
+    __syncthreads();
+    if (ey == 0 && active) {
+      for (int k = 0; k < a.n_red; k++) {
+        double t = 0.0;
+        for (int y = 0; y < eyn; y++) t += red[k * blockDim.x + y * tcc + cx];
+        a.partial[((long long)k * a.S + blockIdx.y) * a.C + c] = t;
+      }
+    }
+  }
+}
+
+struct FusedFinalArgs {
+  const double* partial;
+  int n_red, S;
+  long long C;
+  Dst d[SMC_PROG_MAX_REDUCE];
+  int acc[SMC_PROG_MAX_REDUCE];
+};
+__global__ void k_fused_final(FusedFinalArgs a) {
+  long long total = (long long)a.n_red * a.C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int k = (int)(i / a.C);
+    long long c = i - (long long)k * a.C;
+    double t = 0.0;
+    for (int s = 0; s < a.S; s++) t += a.partial[((long long)k * a.S + s) * a.C + c];
+    double* q = a.d[k].p + c * a.d[k].sc;
+    *q = a.acc[k] ? (*q + t) : t;
+  }
+}
+
 static inline unsigned grid_for(long long total, int block = 256, long long cap = 148LL * 32) {
   long long g = (total + block - 1) / block;
   return (unsigned)std::max<long long>(1, std::min<long long>(g, cap));
@@ -483,6 +603,36 @@ static int run_statement(smc_model_s* m, const smc_tape_stmt& s, int64_t C, bool
       long long n = m->idx_len[s.aux0];
       k_scatter<<<(unsigned)((C + 127) / 128), 128, 0, st>>>(src, d, m->idx_dev[s.aux0], n, C, s.op == SMC_OP_SCATTER_ADD);
       m->ctx->launches++;
+      break;
+    }
+    case SMC_OP_FUSED: {
+      const SmcProgram& pr = m->programs[s.aux0];
+      FusedArgs a;
+      a.prog = pr.dev_instr; a.opds = (const Opd*)m->dev_opds;
+      a.n_instr = (int)pr.h.n_instr; a.n_pro = (int)pr.h.n_prologue; a.n_red = (int)pr.h.n_red;
+      a.n = pr.h.n; a.C = C; a.bad = bad;
+      int tcc = 1;
+      while (tcc < C && tcc < (a.n == 1 ? 256 : 32)) tcc <<= 1;
+      a.tcc = tcc;
+      int eyn = 256 / tcc;
+      long long chain_tiles = (C + tcc - 1) / tcc;
+      long long S = std::max<long long>(1, std::min<long long>((296 + chain_tiles - 1) / chain_tiles, (a.n + eyn * 4 - 1) / (eyn * 4)));
+      a.chunk = (a.n + S - 1) / S;
+      S = (a.n + a.chunk - 1) / a.chunk;
+      a.S = (int)S;
+      if (a.n_red > 0) SMC_TRY(scratch_reserve(m, (int64_t)a.n_red * S * C));
+      a.partial = m->scratch;
+      size_t smem = ((pr.h.n_instr * sizeof(smc_prog_instr) + 15) / 16) * 16 + (size_t)a.n_red * 256 * sizeof(double);
+      dim3 grid((unsigned)chain_tiles, (unsigned)S);
+      k_fused<<<grid, 256, smem, st>>>(a);
+      m->ctx->launches++;
+      if (a.n_red > 0) {
+        FusedFinalArgs f;
+        f.partial = m->scratch; f.n_red = a.n_red; f.S = (int)S; f.C = C;
+        for (int k = 0; k < a.n_red; k++) { f.d[k] = make_dst(m, pr.red[k].reg); f.acc[k] = (int)pr.red[k].acc; }
+        k_fused_final<<<grid_for((long long)a.n_red * C), 256, 0, st>>>(f);
+        m->ctx->launches++;
+      }
       break;
     }
     case SMC_OP_GLM: {
@@ -589,6 +739,13 @@ extern "C" int smc_model_finalize(smc_model_t m, int64_t max_chains, int row_sha
       r.owned = true;
     }
   if (!m->ev0) { SMC_CUDA(cudaEventCreate(&m->ev0)); SMC_CUDA(cudaEventCreate(&m->ev1)); }
+  {
+    std::vector<Opd> opds(m->regs.size());
+    for (size_t i = 0; i < m->regs.size(); i++) opds[i] = make_opd(m, (uint32_t)i, false);
+    if (!m->dev_opds) SMC_CUDA(cudaMalloc(&m->dev_opds, std::max<size_t>(1, opds.size()) * sizeof(Opd)));
+    SMC_CUDA(cudaMemcpyAsync(m->dev_opds, opds.data(), opds.size() * sizeof(Opd), cudaMemcpyHostToDevice, st));
+    SMC_CUDA(cudaStreamSynchronize(st));
+  }
   // the let-header: parameter independent statements, evaluated once (src/parsing.jl:432-442)
   SMC_CUDA(cudaMemsetAsync(m->bad, 0, (size_t)(Cpad + 32) * sizeof(int), st));
   for (int si : m->hdr_stmts) SMC_TRY(run_statement(m, m->stmts[si], 1, true));

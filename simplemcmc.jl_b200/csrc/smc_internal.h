@@ -65,6 +65,13 @@ struct SmcGlmPlan {  // one SMC_OP_GLM statement, prepared at finalize
   float last_ms = 0.f;
 };
 
+struct SmcProgram {  // one SMC_OP_FUSED register program
+  smc_prog_header h;
+  std::vector<smc_prog_instr> instr;
+  std::vector<smc_prog_red> red;
+  smc_prog_instr* dev_instr = nullptr;
+};
+
 struct smc_model_s {
   smc_ctx_s* ctx = nullptr;
   smc_tape_header hdr;
@@ -75,6 +82,8 @@ struct smc_model_s {
   std::vector<int32_t*> idx_dev;
   std::vector<uint32_t> idx_len;
   std::vector<SmcGlmPlan> glm;
+  std::vector<SmcProgram> programs;
+  void* dev_opds = nullptr;  // Opd[n_regs]: operand descriptors of every tape register (rebuilt at finalize)
   bool finalized = false;
   int row_shard = 0;
   int64_t M = 0;       // n_params

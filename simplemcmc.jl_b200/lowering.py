@@ -15,7 +15,7 @@ import numpy as np
 from .jlsyntax import read_model
 
 # ---- numbers from include/simplemcmc_tape.h (tests/test_abi.py checks they agree)
-TAPE_MAGIC, TAPE_VERSION = 0x54434D53, 2
+TAPE_MAGIC, TAPE_VERSION = 0x54434D53, 3
 REG_IMM, REG_DATA, REG_HDR, REG_CHAIN, REG_PARAM, REG_GRAD = range(6)
 F_ACC, F_TRANS_A, F_TRANS_B = 1, 2, 4
 OP = dict(COPY=0, NEG=1, EXP=2, LOG=3, SIN=4, COS=5, ABS=6, SIGN=7, DIGAMMA=8, ZERO=9, SQRT=10,
@@ -63,14 +63,15 @@ class Val(object):
 
 
 class Stmt(object):
-    __slots__ = ("op", "dst", "srcs", "flags", "aux0", "aux1", "aux2", "imm")
+    __slots__ = ("op", "dst", "srcs", "flags", "aux0", "aux1", "aux2", "imm", "clone", "touched")
 
     def __init__(self, op, dst, srcs, flags=0, aux0=0, aux1=0, aux2=None, imm=0.0):
         self.op, self.dst, self.srcs, self.flags = op, dst, list(srcs), flags
         self.aux0, self.aux1, self.aux2, self.imm = aux0, aux1, aux2, imm
+        self.clone, self.touched = False, None
 
     def __repr__(self):
-        name = [k for k, v in OP.items() if v == self.op][0]
+        name = ([k for k, v in OP.items() if v == self.op] + ["FUSED"])[0]
         return "%r %s %s(%s)%s" % (self.dst, "+=" if self.flags & F_ACC else "=", name,
                                   ", ".join(repr(s) for s in self.srcs),
                                   "" if not (self.aux0 or self.aux1) else " aux=%s,%s" % (self.aux0, self.aux1))
@@ -91,11 +92,12 @@ _ELEMENTWISE_UNARY = {"exp": "EXP", "log": "LOG", "sin": "SIN", "cos": "COS", "a
 
 
 class Lowering(object):
-    def __init__(self, model, init, data, gradient=True, ref_adjoint="assign", fuse=True):
+    def __init__(self, model, init, data, gradient=True, ref_adjoint="assign", fuse=True, fuse_statements=True):
         self.vals, self.fwd, self.bwd = [], [], []
         self.env, self.data_slots, self.idx_tables = {}, [], []
         self.imm_cache = {}
         self.gradient, self.ref_adjoint, self.fuse = gradient, ref_adjoint, fuse
+        self.fuse_statements = fuse_statements
         self.pars, self.bsize, self.init = [], 0, []
         self.data = data
         self._set_init(init)
@@ -662,7 +664,12 @@ class Lowering(object):
         return list(self.fwd), list(self.bwd)
 
     def serialise(self):
-        stmts = self.fwd + self.bwd
+        fwd, bwd, programs = self.fwd, self.bwd, []
+        if self.fuse_statements:
+            from . import fusion
+            fwd, bwd, programs = fusion.fuse(self)
+        self.tape_fwd, self.tape_bwd, self.programs = fwd, bwd, programs
+        stmts = fwd + bwd
         used = []
         seen = set()
 
@@ -676,13 +683,16 @@ class Lowering(object):
             use(st.dst)
             if st.op == OP["GLM"]:
                 use(st.aux2)
+            if st.touched:
+                for v in st.touched:
+                    use(v)
         use(self.result)
         data_used = sorted({v.slot for v in used if v.kind == REG_DATA})
         slot_map = {s: i for i, s in enumerate(data_used)}
         for i, v in enumerate(used):
             v.reg = i
         out = [struct.pack("<12I", TAPE_MAGIC, TAPE_VERSION, len(used), len(stmts), self.bsize, len(data_used),
-                           len(self.idx_tables), self.result.reg, 0, len(self.fwd), 0, 0)]
+                           len(self.idx_tables), self.result.reg, 0, len(fwd), len(programs), 0)]
         for v in used:
             if len(v.shape) == 0:
                 rows, cols = 1, 1
@@ -706,4 +716,7 @@ class Lowering(object):
         for t in self.idx_tables:
             pad = t if len(t) % 2 == 0 else np.concatenate([t, np.zeros(1, np.int32)])
             out.append(struct.pack("<2I", len(t), 0) + pad.astype("<i4").tobytes())
+        regmap = {v.vid: v.reg for v in used}
+        for prog in programs:
+            out.append(prog.pack(regmap))
         return b"".join(out), bound

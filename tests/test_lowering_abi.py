@@ -62,10 +62,15 @@ def test_linear_lowering_fuses_the_glm():
     fw, bw = low.statements()
     assert low.n_fused == 1 and [s.op for s in fw].count(lowering.OP["GLM"]) == 1
     assert not any(s.dst.numel == 1000 for s in fw + bw)          # no length-N per-chain register survives
+    low.fuse_statements = False
     tape, bound = low.serialise()
-    magic, ver, nreg, nst, npar, ndata, nidx, res, flags, nfwd, _, _ = struct.unpack_from("<12I", tape)
-    assert (magic, ver, npar, ndata, nfwd) == (0x54434D53, 2, 10, 2, len(fw))
+    magic, ver, nreg, nst, npar, ndata, nidx, res, flags, nfwd, nprog, _ = struct.unpack_from("<12I", tape)
+    assert (magic, ver, npar, ndata, nfwd, nprog) == (0x54434D53, lowering.TAPE_VERSION, 10, 2, len(fw), 0)
     assert len(tape) == 48 + 32 * nreg + 56 * nst + 64 * ndata
+    low.fuse_statements = True
+    tape2, _ = low.serialise()
+    nst2, nprog2 = struct.unpack_from("<12I", tape2)[3], struct.unpack_from("<12I", tape2)[10]
+    assert nprog2 >= 1 and nst2 < nst                          # the prior / adjoint statements collapse into programs
     assert sorted(n for n, _ in bound) == ["X", "Y"]
     unf = Lowering(LINEAR, [("beta", np.zeros(10))], dict(X=X, Y=Y), fuse=False)
     assert unf.n_fused == 0 and any(s.op == lowering.OP["MATMUL"] and s.flags & lowering.F_TRANS_A for s in unf.bwd)
@@ -96,6 +101,22 @@ def test_example_models_lower():
     data, nsub = sleepstudy_data()
     low = Lowering(SLEEPSTUDY2, [("intercept", 250.0), ("slope", 10.0), ("rand_int", np.zeros(nsub)), ("rand_slope", np.zeros(nsub))], data)
     assert low.bsize == 38
+
+
+def test_statement_fusion_of_the_ornstein_tape():
+    """cfg5: the 46 statements become a handful of register programs; no length-T per-chain register is stored"""
+    from simplemcmc_jl_b200 import fusion
+    x = ou_data(500)
+    low = Lowering(ORNSTEIN, [("tau", 20.0), ("mu", 10.0), ("sigma", 0.1)], dict(x=x))
+    low.serialise()
+    stmts = low.tape_fwd + low.tape_bwd
+    assert len(stmts) <= 12 and len(low.programs) >= 4
+    stored = {ins[6] for pr in low.programs for ins in pr.body if ins[0] == fusion.P_STOREV}
+    assert all(low.vals[v].numel == 1 for v in stored)          # resid & co. are rematerialised, never written to HBM
+    for pr in low.programs:                                     # prologue scalars never share a slot with body values
+        pinned = {ins[1] for ins in pr.prologue}
+        written = {ins[1] for ins in pr.body if ins[0] not in (fusion.P_STOREV, fusion.P_REDUCE)}
+        assert not (pinned & written)
 
 
 def test_reference_error_cases():

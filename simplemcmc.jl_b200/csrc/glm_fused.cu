@@ -450,6 +450,8 @@ int smc_glm_launch(smc_model_s* m, SmcGlmPlan& g, int64_t C) {
   RS = (int)((g.N + rows_per_split - 1) / rows_per_split);
   int64_t need = (int64_t)(RS + 1) * (g.MP + 1) * m->Cpad;
   if (need > g.part_cap) {
+    m->graphs_stale = true;
+    m->realloc_epoch++;
     if (g.part) cudaFree(g.part);
     g.part = nullptr;
     SMC_CUDA(cudaMalloc(&g.part, (size_t)need * sizeof(double)));

@@ -3,6 +3,7 @@
 // Reference path replaced: the generated closure of /root/reference/src/parsing.jl:409-492.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include "smc_internal.h"
@@ -168,6 +169,7 @@ extern "C" int smc_model_destroy(smc_model_t m) {
   if (!m) return SMC_OK;
   cudaSetDevice(m->ctx->device);
   cudaStreamSynchronize(m->ctx->stream);
+  smc_graphs_invalidate(m);
   for (auto& r : m->regs) if (r.owned && r.dev) cudaFree(r.dev);
   for (auto d : m->idx_dev) cudaFree(d);
   for (auto& g : m->glm) smc_glm_release(g);
@@ -509,8 +511,17 @@ static inline unsigned grid_for(long long total, int block = 256, long long cap 
   return (unsigned)std::max<long long>(1, std::min<long long>(g, cap));
 }
 
+void smc_graphs_invalidate(smc_model_s* m) {
+  for (auto& g : m->graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+  m->graphs.clear();
+  m->graphs_stale = false;
+}
+
 static int scratch_reserve(smc_model_s* m, int64_t doubles) {
   if (doubles <= m->scratch_cap) return SMC_OK;
+  m->graphs_stale = true;  // captured evaluations hold the old pointer
+  m->realloc_epoch++;
   if (m->scratch) cudaFree(m->scratch);
   m->scratch = nullptr;
   m->scratch_cap = 0;
@@ -696,6 +707,12 @@ extern "C" int smc_model_finalize(smc_model_t m, int64_t max_chains, int row_sha
   for (auto& d : m->data)
     if (!d.bound) { smc_set_error("external variable '%s' is used by the model but was never bound", d.name.c_str()); return SMC_ERR_UNBOUND; }
   cudaStream_t st = m->ctx->stream;
+  SMC_CUDA(cudaStreamSynchronize(st));
+  smc_graphs_invalidate(m);
+  {
+    const char* ng = getenv("SMC_NO_GRAPHS");
+    m->graphs_enabled = (ng && ng[0] == '1') ? 0 : 1;
+  }
   // chains are the contiguous axis of every per-chain array; pad to 32 only when that does not waste bandwidth
   int64_t Cpad = max_chains >= 32 ? (max_chains + 31) / 32 * 32 : max_chains;
   bool realloc_chain = (Cpad != m->Cpad);
@@ -769,12 +786,9 @@ extern "C" int smc_model_finalize(smc_model_t m, int64_t max_chains, int row_sha
   return SMC_OK;
 }
 
-// beta[M][Cpad] (device) -> logp[Cpad], grad[M][Cpad] (device)
-int smc_model_eval_device(smc_model_s* m, int64_t C, bool with_grad) {
-  if (!m->finalized) { smc_set_error("model is not finalized (call smc_model_finalize after binding data)"); return SMC_ERR_INVALID; }
-  if (C < 1 || C > m->Cmax) { smc_set_error("chains %lld outside [1, %lld] given to smc_model_finalize", (long long)C, (long long)m->Cmax); return SMC_ERR_INVALID; }
+// the launch sequence of one evaluation: every body statement of the tape, all chains in lockstep
+static int eval_body(smc_model_s* m, int64_t C, bool with_grad) {
   cudaStream_t st = m->ctx->stream;
-  m->C = C;
   k_fill_int<<<grid_for(C), 256, 0, st>>>(m->bad, C, 0);
   m->ctx->launches++;
   const int n_fwd = (int)m->hdr.reserved[0];  // statements past this index only serve the gradient
@@ -791,6 +805,63 @@ int smc_model_eval_device(smc_model_s* m, int64_t C, bool with_grad) {
   k_finish_eval<<<grid_for(C), 256, 0, st>>>(ro.p, ro.se, ro.sc, m->bad, m->logp, m->grad, m->M, C, m->Cpad, with_grad ? 1 : 0);
   m->ctx->launches++;
   return SMC_OK;
+}
+
+// beta[M][Cpad] (device) -> logp[Cpad], grad[M][Cpad] (device).
+// The statement sequence of a (chain count, gradient) pair is fixed, so its second evaluation is captured into a
+// CUDA graph and every later one is a single graph launch: the sampler loops (one evaluation per leapfrog) stop
+// paying one host launch per tape statement.  Row-sharded models (NCCL inside the sequence) and timed evaluations
+// stay eager.
+int smc_model_eval_device(smc_model_s* m, int64_t C, bool with_grad) {
+  if (!m->finalized) { smc_set_error("model is not finalized (call smc_model_finalize after binding data)"); return SMC_ERR_INVALID; }
+  if (C < 1 || C > m->Cmax) { smc_set_error("chains %lld outside [1, %lld] given to smc_model_finalize", (long long)C, (long long)m->Cmax); return SMC_ERR_INVALID; }
+  cudaStream_t st = m->ctx->stream;
+  m->C = C;
+  if (!m->graphs_enabled || m->time_glm || (m->row_shard && m->ctx->nranks > 1)) return eval_body(m, C, with_grad);
+  if (m->graphs_stale) smc_graphs_invalidate(m);
+  int gi = -1;
+  for (size_t i = 0; i < m->graphs.size(); i++)
+    if (m->graphs[i].C == C && m->graphs[i].with_grad == (with_grad ? 1 : 0)) { gi = (int)i; break; }
+  if (gi < 0) {  // first evaluation of this shape: eager, sizes every scratch buffer
+    SmcEvalGraph g;
+    g.C = C; g.with_grad = with_grad ? 1 : 0; g.state = 1;
+    SMC_TRY(eval_body(m, C, with_grad));
+    if (!m->graphs_stale) m->graphs.push_back(g);
+    return SMC_OK;
+  }
+  if (m->graphs[gi].state == 1) {
+    const int64_t epoch = m->realloc_epoch, l0 = m->ctx->launches;
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+      cudaGetLastError();
+      m->graphs[gi].state = 3;
+      return eval_body(m, C, with_grad);
+    }
+    int rc = eval_body(m, C, with_grad);
+    cudaError_t e = cudaStreamEndCapture(st, &graph);
+    bool ok = (rc == SMC_OK && e == cudaSuccess && graph && epoch == m->realloc_epoch);
+    cudaGraphExec_t exec = nullptr;
+    if (ok && cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) ok = false;
+    if (graph) cudaGraphDestroy(graph);
+    if (!ok) {
+      cudaGetLastError();
+      m->ctx->launches = l0;
+      if (m->graphs_stale) smc_graphs_invalidate(m);
+      else m->graphs[gi].state = 3;
+      return eval_body(m, C, with_grad);
+    }
+    m->graphs[gi].exec = exec;
+    m->graphs[gi].launches = m->ctx->launches - l0;
+    m->graphs[gi].state = 2;
+    SMC_CUDA(cudaGraphLaunch(exec, st));
+    return SMC_OK;
+  }
+  if (m->graphs[gi].state == 2) {
+    SMC_CUDA(cudaGraphLaunch(m->graphs[gi].exec, st));
+    m->ctx->launches += m->graphs[gi].launches;
+    return SMC_OK;
+  }
+  return eval_body(m, C, with_grad);
 }
 
 extern "C" int smc_eval(smc_model_t m, const double* beta, int64_t C, double* logp, double* grad) {

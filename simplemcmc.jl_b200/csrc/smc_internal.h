@@ -72,6 +72,14 @@ struct SmcProgram {  // one SMC_OP_FUSED register program
   smc_prog_instr* dev_instr = nullptr;
 };
 
+struct SmcEvalGraph {  // one captured evaluation (all statements of the tape for a chain count), replayed with one launch
+  int64_t C = 0;
+  int with_grad = 0;
+  int state = 0;  // 1: ran once eagerly (buffers sized), 2: captured, 3: capture failed -> stays eager
+  cudaGraphExec_t exec = nullptr;
+  int64_t launches = 0;  // kernel nodes in the graph
+};
+
 struct smc_model_s {
   smc_ctx_s* ctx = nullptr;
   smc_tape_header hdr;
@@ -99,11 +107,16 @@ struct smc_model_s {
   int64_t host_stage_cap = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int time_glm = 0;
+  std::vector<SmcEvalGraph> graphs;
+  int graphs_enabled = 1;
+  bool graphs_stale = false;   // a buffer captured graphs point at was reallocated
+  int64_t realloc_epoch = 0;
 };
 
 // smc_core.cu
 int smc_model_eval_device(smc_model_s* m, int64_t C, bool with_grad);  // beta -> logp, grad (device resident)
 int smc_stage_reserve(smc_model_s* m, int64_t doubles);
+void smc_graphs_invalidate(smc_model_s* m);
 
 // glm_fused.cu
 int smc_glm_prepare(smc_model_s* m, SmcGlmPlan& g);

@@ -157,6 +157,8 @@ class Program(object):
         out = [struct.pack("<4I", len(self.prologue) + len(self.body), len(self.prologue), len(self.reductions), self.n)]
         for (op, dst, srcs, flags, aux0, aux1, vid) in self.prologue + self.body:
             s = list(srcs) + [0] * (3 - len(srcs))
+            if op == L.OP["LOGPDF"]:
+                aux1 = 0        # the statement's aux1 is its index-space length; the program header carries it as `n`
             out.append(struct.pack("<HBB3BBHHI", op, dst, len(srcs), s[0], s[1], s[2], flags, aux0, aux1,
                                    regmap[vid] if vid is not None else 0))
         for vid, acc in self.reductions:

@@ -1,0 +1,26 @@
+"""Short runs of the secondary configs for `ncu --metrics gpu__time_duration.sum` launch lists:
+  python tools/prof_cfg.py cfg4 [chains] | cfg5 [chains] [sampler]"""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np
+from smc_pkg import load_package
+load_package()
+from simplemcmc_jl_b200 import api
+from util import ORNSTEIN, SLEEPSTUDY2, ou_data, sleepstudy_data
+
+which = sys.argv[1]
+C = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+if which == "cfg4":
+    C = C or 16384
+    data, nsub = sleepstudy_data()
+    init = [("intercept", 250.0), ("slope", 10.0), ("rand_int", np.zeros(nsub)), ("rand_slope", np.zeros(nsub))]
+    low, dev = api._build(SLEEPSTUDY2, init, data, True, C, 0, "assign")
+    raw = dev.run("nuts", np.array(low.init), C, 3, 0, seed=1, store_draws=False, want=())
+else:
+    C = C or 64
+    kind = sys.argv[3] if len(sys.argv) > 3 else "hmc"
+    x = ou_data(1_000_000, 5)
+    init = [("tau", 20.0), ("mu", 10.0), ("sigma", 0.1)]
+    low, dev = api._build(ORNSTEIN, init, dict(x=x), kind != "rwm", C, 0, "assign")
+    raw = dev.run(kind, np.array(low.init), C, 6, 0, seed=1, store_draws=False, want=(), **(dict(isteps=2, stepsize=1e-4) if kind == "hmc" else {}))
+print(which, C, "device_ms", raw["device_ms"], "evals", raw["n_evals"], "launches", raw["n_kernel_launches"])

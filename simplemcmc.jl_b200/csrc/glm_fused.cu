@@ -328,6 +328,132 @@ __global__ void k_to_row_major(const double* Xcm, double* Xrm, long long N, int 
   }
 }
 
+
+// ---- few chains (C <= 4): HBM stream of X ------------------------------------------------------------------------
+// With one to four chains the contraction is a matrix-vector product and the DMMA tile (8 chains) would spend 7/8 of
+// the family stage (exp / log / divide per row and chain) on padding lanes.  Here a thread owns a row: it reads the
+// row's M values from the column-major X the caller bound (consecutive threads = consecutive rows: every load is a
+// full coalesced line, no padded columns are read), forms eta for CT chains, evaluates the family and accumulates
+// G[j][chain] += d * x[j] in registers.  Algorithmic bytes = bytes moved: 8*N*M + 8*N per evaluation.
+struct GlmStreamArgs {
+  const double* X;     // [M][N] column major
+  const double* y;     // [N] sign-normalised response
+  const double* beta;  // [M][Cpad]
+  double* part;        // [gridDim.x][MP+1][Cpad]
+  int* bad;
+  long long N, C, Cpad;
+  int M, MP;
+  double par;
+  int neg_beta, neg_out;
+};
+
+template <int FAM, int MB, int CT>
+__global__ void __launch_bounds__(256) k_glm_stream(GlmStreamArgs a) {
+  __shared__ double bs[MB * CT];
+  __shared__ double red[8][(MB + 1) * CT];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long c0 = (long long)blockIdx.y * CT;
+  for (int i = tid; i < MB * CT; i += 256) {
+    int j = i / CT, ct = i - j * CT;
+    double bv = (j < a.M && c0 + ct < a.C) ? __ldg(a.beta + (long long)j * a.Cpad + c0 + ct) : 0.0;
+    bs[i] = a.neg_beta ? -bv : bv;
+  }
+  __syncthreads();
+  double G[MB][CT], lsum[CT];
+#pragma unroll
+  for (int ct = 0; ct < CT; ct++) {
+    lsum[ct] = 0.0;
+#pragma unroll
+    for (int j = 0; j < MB; j++) G[j][ct] = 0.0;
+  }
+  double inv_s = 1.0, neg_inv_s2 = 0.0;
+  if (FAM == SMC_GLM_NORMAL) {
+    inv_s = 1.0 / a.par;
+    neg_inv_s2 = -1.0 / (a.par * a.par);
+  }
+  const long long stride = (long long)gridDim.x * 256;
+  for (long long r = (long long)blockIdx.x * 256 + tid; r < a.N; r += stride) {
+    double x[MB];
+#pragma unroll
+    for (int j = 0; j < MB; j++) x[j] = (j < a.M) ? __ldg(a.X + (long long)j * a.N + r) : 0.0;
+    const double y = __ldg(a.y + r);
+#pragma unroll
+    for (int ct = 0; ct < CT; ct++) {
+      double eta = 0.0;
+#pragma unroll
+      for (int j = 0; j < MB; j++) eta = fma(x[j], bs[j * CT + ct], eta);
+      double d;
+      family_eval<FAM>(eta, y, inv_s, neg_inv_s2, true, lsum[ct], d);
+#pragma unroll
+      for (int j = 0; j < MB; j++) G[j][ct] = fma(d, x[j], G[j][ct]);
+    }
+  }
+  // block reduction: shuffle tree inside each warp, then the 8 warps in order
+#pragma unroll
+  for (int ct = 0; ct < CT; ct++) {
+#pragma unroll
+    for (int j = 0; j <= MB; j++) {
+      double v = j < MB ? G[j < MB ? j : 0][ct] : lsum[ct];
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) red[warp][j * CT + ct] = v;
+    }
+  }
+  __syncthreads();
+  double* part = a.part + (long long)blockIdx.x * (a.MP + 1) * a.Cpad;
+  for (int i = tid; i < (MB + 1) * CT; i += 256) {
+    int j = i / CT, ct = i - j * CT;
+    long long c = c0 + ct;
+    if (c >= a.C || (j < MB && j >= a.M)) continue;
+    double v = 0.0;
+    for (int w = 0; w < 8; w++) v += red[w][i];
+    if (j == MB) {
+      if (FAM == SMC_GLM_NORMAL) {
+        v = -0.5 * v;
+        if (blockIdx.x == 0) v += (double)a.N * (-log(a.par) - SMC_LOG_SQRT_2PI);
+      }
+      if (!(v > -INFINITY)) a.bad[c] = 1;
+      part[(long long)a.MP * a.Cpad + c] = v;
+    } else {
+      part[(long long)j * a.Cpad + c] = a.neg_out ? -v : v;
+    }
+  }
+}
+
+// out[j][c] = sum_rs part[rs][j][c] with one warp per output: lanes stride the row splits, fixed shuffle tree
+__global__ void k_glm_reduce_warp(const double* part, int RS, int M, int MP, long long C, long long Cpad, const int* bad, double* out) {
+  const int lane = threadIdx.x & 31;
+  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w >= (long long)(M + 1) * C) return;
+  long long jj = w / C, c = w - jj * C;
+  long long j = jj == M ? MP : jj;
+  double t = 0.0;
+  for (int r = lane; r < RS; r += 32) t += part[((long long)r * (MP + 1) + j) * Cpad + c];
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  if (lane == 0) {
+    if (j == MP && (bad[c] || !(t > -INFINITY))) t = -INFINITY;
+    out[j * Cpad + c] = t;
+  }
+}
+
+template <int FAM, int MB>
+int launch_stream_ct(const GlmStreamArgs& a, int CT, dim3 grid, cudaStream_t st) {
+  if (CT == 1) k_glm_stream<FAM, MB, 1><<<grid, 256, 0, st>>>(a);
+  else if (CT == 2) k_glm_stream<FAM, MB, 2><<<grid, 256, 0, st>>>(a);
+  else k_glm_stream<FAM, MB, 4><<<grid, 256, 0, st>>>(a);
+  return SMC_OK;
+}
+template <int FAM>
+int launch_stream(const GlmStreamArgs& a, int MB, int CT, dim3 grid, cudaStream_t st) {
+  if (MB == 8) return launch_stream_ct<FAM, 8>(a, CT, grid, st);
+  if (MB == 16) return launch_stream_ct<FAM, 16>(a, CT, grid, st);
+  if (CT > 1) { smc_set_error("GLM stream kernel: unsupported shape"); return SMC_ERR_INVALID; }
+  k_glm_stream<FAM, 32, 1><<<grid, 256, 0, st>>>(a);
+  return SMC_OK;
+}
+
+// the stream path covers M <= 16 with up to 4 chains and M <= 32 with one chain (register budget: x[MB] + G[MB][CT])
+bool use_stream(int M, long long C) { return (M <= 16 && C <= 4) || (M <= 32 && C == 1); }
+
 template <int FAM, int MT, int NWC, int NWR, int MP8>
 int launch_cfg(const GlmArgs& a, int RS, cudaStream_t st) {
   constexpr int MP = MP8 * 8, LD = MP + 4, RT = (MP8 >= 4) ? 64 : 128, NST = 4, TC = NWC * MT * 8;
@@ -407,9 +533,7 @@ int smc_glm_prepare(smc_model_s* m, SmcGlmPlan& g) {
   if (g.family != SMC_GLM_NORMAL && g.family != SMC_GLM_BERNOULLI) { smc_set_error("GLM: family %d is not implemented", g.family); return SMC_ERR_INVALID; }
   g.MP = g.M <= 16 ? 16 : (g.M <= 32 ? 32 : 64);
   cudaStream_t st = m->ctx->stream;
-  SMC_CUDA(cudaMalloc(&g.Xrm, (size_t)g.N * g.MP * sizeof(double)));
-  k_to_row_major<<<(unsigned)std::min<long long>((g.N * g.MP + 255) / 256, 148LL * 64), 256, 0, st>>>(X.dev, g.Xrm, g.N, g.M, g.MP);
-  m->ctx->launches++;
+  g.Xcm = X.dev;   // the row-major padded copy for the DMMA kernel is built on its first launch (smc_glm_launch)
   // ytilde[N]: the response as the kernel consumes it (negated when eta and y enter the residual with the same sign,
   // broadcast when the model uses a scalar)
   double scale = 1.0;
@@ -442,12 +566,19 @@ void smc_glm_release(SmcGlmPlan& g) {
 int smc_glm_launch(smc_model_s* m, SmcGlmPlan& g, int64_t C) {
   const smc_tape_stmt& s = m->stmts[g.stmt];
   cudaStream_t st = m->ctx->stream;
+  const bool stream = use_stream(g.M, C);
+  if (!stream && !g.Xrm) {
+    SMC_CUDA(cudaMalloc(&g.Xrm, (size_t)g.N * g.MP * sizeof(double)));
+    k_to_row_major<<<(unsigned)std::min<long long>((g.N * g.MP + 255) / 256, 148LL * 64), 256, 0, st>>>(g.Xcm, g.Xrm, g.N, g.M, g.MP);
+    m->ctx->launches++;
+  }
   int tc = chain_tile_for(C);
   long long chain_tiles = (C + tc - 1) / tc;
   int RT = g.MP >= 32 ? 64 : 128;
   int RS = row_splits_for(chain_tiles, g.N, RT, m->ctx->sm_count * (g.MP <= 16 ? 2 : 1));  // narrow models run 2 CTAs per SM
   long long rows_per_split = ((g.N + RS - 1) / RS + RT - 1) / RT * RT;
   RS = (int)((g.N + rows_per_split - 1) / rows_per_split);
+  if (stream) RS = (int)std::max<long long>(1, std::min<long long>((g.N + 255) / 256, 2LL * m->ctx->sm_count));
   int64_t need = (int64_t)(RS + 1) * (g.MP + 1) * m->Cpad;
   if (need > g.part_cap) {
     m->graphs_stale = true;
@@ -465,8 +596,21 @@ int smc_glm_launch(smc_model_s* m, SmcGlmPlan& g, int64_t C) {
   a.par = g.par;
   a.neg_beta = a.neg_out = (g.family == SMC_GLM_BERNOULLI && (g.sign_neg & 1)) ? 1 : 0;
   if (m->time_glm) SMC_CUDA(cudaEventRecord(m->ev0, st));
-  int rc = g.family == SMC_GLM_NORMAL ? launch_fam<SMC_GLM_NORMAL>(a, g.MP, tc, RS, st)
-                                      : launch_fam<SMC_GLM_BERNOULLI>(a, g.MP, tc, RS, st);
+  int rc;
+  if (stream) {
+    GlmStreamArgs sa;
+    sa.X = g.Xcm; sa.y = a.y; sa.beta = a.beta; sa.part = a.part; sa.bad = a.bad;
+    sa.N = g.N; sa.C = C; sa.Cpad = m->Cpad; sa.M = g.M; sa.MP = g.MP; sa.par = g.par;
+    sa.neg_beta = a.neg_beta; sa.neg_out = a.neg_out;
+    const int MB = g.M <= 8 ? 8 : (g.M <= 16 ? 16 : 32);
+    const int CT = C == 1 ? 1 : (C == 2 ? 2 : 4);
+    dim3 grid((unsigned)RS, (unsigned)((C + CT - 1) / CT));
+    rc = g.family == SMC_GLM_NORMAL ? launch_stream<SMC_GLM_NORMAL>(sa, MB, CT, grid, st)
+                                    : launch_stream<SMC_GLM_BERNOULLI>(sa, MB, CT, grid, st);
+  } else {
+    rc = g.family == SMC_GLM_NORMAL ? launch_fam<SMC_GLM_NORMAL>(a, g.MP, tc, RS, st)
+                                    : launch_fam<SMC_GLM_BERNOULLI>(a, g.MP, tc, RS, st);
+  }
   if (rc != SMC_OK) return rc;
   if (m->time_glm) {
     SMC_CUDA(cudaEventRecord(m->ev1, st));
@@ -478,7 +622,10 @@ int smc_glm_launch(smc_model_s* m, SmcGlmPlan& g, int64_t C) {
   SMC_CUDA(cudaGetLastError());
   double* out = g.part + (int64_t)RS * (g.MP + 1) * m->Cpad;
   long long tot = (long long)(g.MP + 1) * C;
-  k_glm_reduce<<<(unsigned)std::min<long long>((tot + 255) / 256, 148LL * 16), 256, 0, st>>>(g.part, RS, g.MP, C, m->Cpad, m->bad, out);
+  if ((long long)(g.M + 1) * C <= 1024 && RS >= 16)
+    k_glm_reduce_warp<<<(unsigned)(((long long)(g.M + 1) * C * 32 + 255) / 256), 256, 0, st>>>(g.part, RS, g.M, g.MP, C, m->Cpad, m->bad, out);
+  else
+    k_glm_reduce<<<(unsigned)std::min<long long>((tot + 255) / 256, 148LL * 16), 256, 0, st>>>(g.part, RS, g.MP, C, m->Cpad, m->bad, out);
   if (m->row_shard && m->ctx->nranks > 1) SMC_TRY(smc_comm_allreduce_device(m->ctx, out, (int64_t)(g.MP + 1) * m->Cpad));
   const SmcReg& Lr = m->regs[s.dst];
   const SmcReg& Gr = m->regs[s.aux2];

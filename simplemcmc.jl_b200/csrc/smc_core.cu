@@ -8,6 +8,7 @@
 #include <algorithm>
 #include "smc_internal.h"
 #include "dists.cuh"
+#include "exec_common.cuh"
 
 static thread_local char g_err[1024] = "";
 void smc_set_error(const char* fmt, ...) {
@@ -147,8 +148,7 @@ extern "C" int smc_model_compile(smc_ctx_t ctx, const void* tape, size_t nbytes,
     }
     for (auto& r : pr.red)
       if (r.reg >= h.n_regs) { smc_set_error("tape: program %u reduces into a bad register", i); delete m; return SMC_ERR_INVALID; }
-    SMC_CUDA(cudaMalloc(&pr.dev_instr, std::max<size_t>(1, pr.instr.size()) * sizeof(smc_prog_instr)));
-    SMC_CUDA(cudaMemcpy(pr.dev_instr, pr.instr.data(), pr.instr.size() * sizeof(smc_prog_instr), cudaMemcpyHostToDevice));
+    if (smc_vm_plan(m, pr) != SMC_OK) { delete m; return SMC_ERR_INVALID; }
     m->programs.push_back(pr);
   }
   for (auto& s : m->stmts)
@@ -173,8 +173,7 @@ extern "C" int smc_model_destroy(smc_model_t m) {
   for (auto& r : m->regs) if (r.owned && r.dev) cudaFree(r.dev);
   for (auto d : m->idx_dev) cudaFree(d);
   for (auto& g : m->glm) smc_glm_release(g);
-  for (auto& pr : m->programs) if (pr.dev_instr) cudaFree(pr.dev_instr);
-  if (m->dev_opds) cudaFree(m->dev_opds);
+  for (auto& pr : m->programs) if (pr.dev_tables) cudaFree(pr.dev_tables);
   if (m->beta) cudaFree(m->beta);
   if (m->grad) cudaFree(m->grad);
   if (m->logp) cudaFree(m->logp);
@@ -211,18 +210,6 @@ extern "C" int smc_model_bind_data(smc_model_t m, const char* name, const double
 }
 
 // ------------------------------------------------------------------------------------------ generic executor
-struct Opd {
-  const double* p;
-  long long se;  // element stride
-  int sc;        // chain stride (0 = shared by all chains)
-  int is_imm;
-  double imm;
-};
-struct Dst {
-  double* p;
-  long long se;
-  int sc;
-};
 struct EwArgs {
   int op, dist, darg, nsrc, acc;
   Opd s[4];
@@ -231,41 +218,6 @@ struct EwArgs {
   int* bad;
   int bad_stride;  // 1: per chain, 0: header phase
 };
-
-__device__ __forceinline__ double opd_ld(const Opd& o, long long e, long long c) {
-  return o.is_imm ? o.imm : __ldg(o.p + e * o.se + c * o.sc);
-}
-
-__device__ __forceinline__ double smc_apply(int op, int dist, int k, double a, double b, double c) {
-  switch (op) {
-    case SMC_OP_COPY: return a;
-    case SMC_OP_NEG: return -a;
-    case SMC_OP_EXP: return exp(a);
-    case SMC_OP_LOG: return log(a);
-    case SMC_OP_SIN: return sin(a);
-    case SMC_OP_COS: return cos(a);
-    case SMC_OP_ABS: return fabs(a);
-    case SMC_OP_SIGN: return a > 0.0 ? 1.0 : (a < 0.0 ? -1.0 : a);
-    case SMC_OP_DIGAMMA: return smc_digamma(a);
-    case SMC_OP_ZERO: return 0.0;
-    case SMC_OP_SQRT: return sqrt(a);
-    case SMC_OP_ADD: return a + b;
-    case SMC_OP_SUB: return a - b;
-    case SMC_OP_MUL: return a * b;
-    case SMC_OP_DIV: return a / b;
-    case SMC_OP_POW: return pow(a, b);
-    case SMC_OP_MAX: return fmax(a, b);
-    case SMC_OP_MIN: return fmin(a, b);
-    case SMC_OP_GT: return a > b ? 1.0 : 0.0;
-    case SMC_OP_LT: return a < b ? 1.0 : 0.0;
-    case SMC_OP_GE: return a >= b ? 1.0 : 0.0;
-    case SMC_OP_LE: return a <= b ? 1.0 : 0.0;
-    case SMC_OP_EQ: return a == b ? 1.0 : 0.0;
-    case SMC_OP_LOGPDF: return smc_logpdf(dist, a, b, c);
-    case SMC_OP_DLOGPDF: return smc_dlogpdf(dist, k, a, b, c);
-  }
-  return nan("");
-}
 
 __device__ __forceinline__ double ew_value(const EwArgs& a, long long e, long long c) {
   double x0 = a.nsrc > 0 ? opd_ld(a.s[0], e, c) : 0.0;
@@ -350,6 +302,78 @@ __global__ void __launch_bounds__(256) k_matmul(MmArgs a, double* partial, long 
   }
 }
 
+// MATMUL with a chain-independent left operand (data or header matrix) and a per-chain right operand -- the `X * beta`
+// and `transpose(X) * ds` of the generated code (src/diff.jl:52-55) outside the fused GLM pattern.  With the chains as
+// the contiguous axis this is the GEMM  out[r x (n*C)] = Aop[r x k] * B[k x (n*C)]: thread = chain (coalesced B and out),
+// RI output rows per thread in registers, the A tile staged in shared memory and read as broadcast double2.
+struct MmDcArgs {
+  const double* A;
+  long long ar;   // stored leading dimension of A
+  int tA;
+  const double* B;
+  double* out;
+  long long Bse, Ose;   // element strides (Cpad)
+  long long r, k, n, C, chunk;
+  int acc, S;
+  double* partial;      // [S][r*n][C] when S > 1
+};
+template <int RI>
+__global__ void __launch_bounds__(256) k_matmul_dc(MmDcArgs a) {
+  constexpr int TK = 32;
+  extern __shared__ __align__(16) double As[];   // [ty][RI][TK]
+  const int tcx = blockDim.x, ty = blockDim.y, tid = threadIdx.y * tcx + threadIdx.x;
+  const long long c = (long long)blockIdx.x * tcx + threadIdx.x;
+  const long long groups = (a.r + RI - 1) / RI;
+  const long long gtiles = (groups + ty - 1) / ty;
+  const long long j = blockIdx.y / gtiles;                      // output column
+  const long long g0 = (blockIdx.y - j * gtiles) * ty;          // first row group of this block
+  const long long i0 = (g0 + threadIdx.y) * RI;
+  const long long l0 = (long long)blockIdx.z * a.chunk, l1 = min(a.k, l0 + a.chunk);
+  double acc[RI];
+#pragma unroll
+  for (int ii = 0; ii < RI; ii++) acc[ii] = 0.0;
+  const bool cok = c < a.C;
+  const double* Bc = a.B + (j * a.k) * a.Bse + (cok ? c : 0);
+  for (long long lb = l0; lb < l1; lb += TK) {
+    __syncthreads();
+    for (int t = tid; t < ty * RI * TK; t += 256) {
+      int ll = t % TK, ii = (t / TK) % RI, y = t / (TK * RI);
+      long long i = (g0 + y) * RI + ii, l = lb + ll;
+      double v = 0.0;
+      if (i < a.r && l < l1) v = __ldg(a.A + (a.tA ? (l + i * a.ar) : (i + l * a.ar)));
+      As[t] = v;
+    }
+    __syncthreads();
+    const double* as = As + threadIdx.y * RI * TK;
+    const int lim = (int)min((long long)TK, l1 - lb);
+    if (cok && i0 < a.r) {
+      for (int ll = 0; ll < lim; ll += 2) {
+        const double b0 = __ldg(Bc + (lb + ll) * a.Bse);
+        const double b1 = (ll + 1 < lim) ? __ldg(Bc + (lb + ll + 1) * a.Bse) : 0.0;
+#pragma unroll
+        for (int ii = 0; ii < RI; ii++) {
+          const double2 a2 = *(const double2*)(as + ii * TK + ll);
+          acc[ii] = fma(a2.x, b0, acc[ii]);
+          acc[ii] = fma(a2.y, b1, acc[ii]);
+        }
+      }
+    }
+  }
+  if (!cok) return;
+#pragma unroll
+  for (int ii = 0; ii < RI; ii++) {
+    long long i = i0 + ii;
+    if (i >= a.r) break;
+    long long o = i + j * a.r;
+    if (a.S > 1) {
+      a.partial[((long long)blockIdx.z * a.r * a.n + o) * a.C + c] = acc[ii];
+    } else {
+      double* q = a.out + o * a.Ose + c;
+      *q = a.acc ? (*q + acc[ii]) : acc[ii];
+    }
+  }
+}
+
 __global__ void k_transpose(Opd src, Dst d, long long rows, long long cols, long long C, int acc) {
   long long total = rows * cols * C;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
@@ -418,94 +442,6 @@ __global__ void k_cols_to_rows(const double* in, double* out, long long C, long 
 }
 
 
-// ------------------------------------------------------------------------------------------ fused register programs
-// One launch runs a whole group of elementwise / reducing statements: thread = (chain lane, element lane); every
-// intermediate lives in the thread's register file R[] (local memory, L1 resident) instead of an [n][C] array in HBM.
-// Lanes map to chains first (coalesced per-chain operands, broadcast data operands), the rest of the block strides
-// over elements; reductions accumulate per thread, then over the element lanes in shared memory in fixed order, then
-// over element chunks in k_fused_final -- deterministic.
-struct FusedArgs {
-  const smc_prog_instr* prog;
-  const Opd* opds;  // indexed by tape register
-  int n_instr, n_pro, n_red, tcc;
-  long long n, C, chunk;
-  int* bad;
-  double* partial;  // [n_red][S][C]
-  int S;
-};
-
-__global__ void __launch_bounds__(256) k_fused(FusedArgs a) {
-  extern __shared__ __align__(16) unsigned char fsm[];
-  smc_prog_instr* ins = (smc_prog_instr*)fsm;
-  double* red = (double*)(fsm + ((a.n_instr * sizeof(smc_prog_instr) + 15) / 16) * 16);
-  for (int i = threadIdx.x; i < a.n_instr * 4; i += blockDim.x) ((uint32_t*)ins)[i] = ((const uint32_t*)a.prog)[i];
-  __syncthreads();
-  const int tcc = a.tcc, eyn = blockDim.x / tcc;
-  const int cx = threadIdx.x % tcc, ey = threadIdx.x / tcc;
-  const long long c = (long long)blockIdx.x * tcc + cx;
-  const bool active = c < a.C;
-  double R[SMC_PROG_MAX_LOCALS];
-  double racc[SMC_PROG_MAX_REDUCE];
-#pragma unroll
-  for (int k = 0; k < SMC_PROG_MAX_REDUCE; k++) racc[k] = 0.0;
-  if (active) {
-    for (int i = 0; i < a.n_pro; i++) R[ins[i].dst] = opd_ld(a.opds[ins[i].reg], 0, c);
-    const long long e0 = (long long)blockIdx.y * a.chunk, e1 = min(a.n, e0 + a.chunk);
-    for (long long e = e0 + ey; e < e1; e += eyn) {
-      for (int i = a.n_pro; i < a.n_instr; i++) {
-        const smc_prog_instr in = ins[i];
-        if (in.op == SMC_P_LOADV) {
-          R[in.dst] = opd_ld(a.opds[in.reg], e, c);
-        } else if (in.op == SMC_P_LOADS) {
-          R[in.dst] = opd_ld(a.opds[in.reg], 0, c);
-        } else if (in.op == SMC_P_STOREV) {
-          const Opd& o = a.opds[in.reg];
-          const_cast<double*>(o.p)[e * o.se + c * o.sc] = R[in.src[0]];
-        } else if (in.op == SMC_P_REDUCE) {
-          racc[in.aux0] += R[in.src[0]];
-        } else {
-          double x0 = in.nsrc > 0 ? R[in.src[0]] : 0.0;
-          double x1 = in.nsrc > 1 ? R[in.src[1]] : 0.0;
-          double x2 = in.nsrc > 2 ? R[in.src[2]] : 0.0;
-          double v = smc_apply(in.op, in.aux0, in.aux1, x0, x1, x2);
-          if (in.op == SMC_OP_LOGPDF && (v == -INFINITY || isnan(v))) { a.bad[c] = 1; v = 0.0; }
-          R[in.dst] = (in.flags & SMC_F_ACC) ? R[in.dst] + v : v;
-        }
-      }
-    }
-  }
-  if (a.n_red > 0) {
-    for (int k = 0; k < a.n_red; k++) red[k * blockDim.x + threadIdx.x] = racc[k];
-    __syncthreads();
-    if (ey == 0 && active) {
-      for (int k = 0; k < a.n_red; k++) {
-        double t = 0.0;
-        for (int y = 0; y < eyn; y++) t += red[k * blockDim.x + y * tcc + cx];
-        a.partial[((long long)k * a.S + blockIdx.y) * a.C + c] = t;
-      }
-    }
-  }
-}
-
-struct FusedFinalArgs {
-  const double* partial;
-  int n_red, S;
-  long long C;
-  Dst d[SMC_PROG_MAX_REDUCE];
-  int acc[SMC_PROG_MAX_REDUCE];
-};
-__global__ void k_fused_final(FusedFinalArgs a) {
-  long long total = (long long)a.n_red * a.C;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int k = (int)(i / a.C);
-    long long c = i - (long long)k * a.C;
-    double t = 0.0;
-    for (int s = 0; s < a.S; s++) t += a.partial[((long long)k * a.S + s) * a.C + c];
-    double* q = a.d[k].p + c * a.d[k].sc;
-    *q = a.acc[k] ? (*q + t) : t;
-  }
-}
-
 static inline unsigned grid_for(long long total, int block = 256, long long cap = 148LL * 32) {
   long long g = (total + block - 1) / block;
   return (unsigned)std::max<long long>(1, std::min<long long>(g, cap));
@@ -518,7 +454,7 @@ void smc_graphs_invalidate(smc_model_s* m) {
   m->graphs_stale = false;
 }
 
-static int scratch_reserve(smc_model_s* m, int64_t doubles) {
+int smc_scratch_reserve(smc_model_s* m, int64_t doubles) {
   if (doubles <= m->scratch_cap) return SMC_OK;
   m->graphs_stale = true;  // captured evaluations hold the old pointer
   m->realloc_epoch++;
@@ -540,7 +476,7 @@ int smc_stage_reserve(smc_model_s* m, int64_t doubles) {
   return SMC_OK;
 }
 
-static Opd make_opd(const smc_model_s* m, uint32_t r, bool header) {
+Opd smc_make_opd(const smc_model_s* m, uint32_t r) {
   const SmcReg& g = m->regs[r];
   Opd o;
   o.p = nullptr; o.se = 0; o.sc = 0; o.is_imm = 0; o.imm = 0.0;
@@ -552,11 +488,10 @@ static Opd make_opd(const smc_model_s* m, uint32_t r, bool header) {
     case SMC_REG_PARAM: o.p = m->beta + g.d.aux * m->Cpad; o.se = g.numel > 1 ? m->Cpad : 0; o.sc = 1; break;
     case SMC_REG_GRAD: o.p = m->grad + g.d.aux * m->Cpad; o.se = g.numel > 1 ? m->Cpad : 0; o.sc = 1; break;
   }
-  (void)header;
   return o;
 }
-static Dst make_dst(const smc_model_s* m, uint32_t r) {
-  Opd o = make_opd(m, r, false);
+Dst smc_make_dst(const smc_model_s* m, uint32_t r) {
+  Opd o = smc_make_opd(m, r);
   Dst d;
   d.p = const_cast<double*>(o.p);
   d.se = o.se;
@@ -568,26 +503,66 @@ static Dst make_dst(const smc_model_s* m, uint32_t r) {
 static int run_statement(smc_model_s* m, const smc_tape_stmt& s, int64_t C, bool header) {
   cudaStream_t st = m->ctx->stream;
   const SmcReg& dreg = m->regs[s.dst];
-  Dst d = make_dst(m, s.dst);
+  Dst d = smc_make_dst(m, s.dst);
   int acc = (s.flags & SMC_F_ACC) ? 1 : 0;
   int* bad = header ? (m->bad + m->Cpad) : m->bad;  // slot Cpad = header flag
   switch (s.op) {
     case SMC_OP_MATMUL: {
       MmArgs a;
-      a.A = make_opd(m, s.src[0], header);
-      a.B = make_opd(m, s.src[1], header);
+      a.A = smc_make_opd(m, s.src[0]);
+      a.B = smc_make_opd(m, s.src[1]);
       a.tA = (s.flags & SMC_F_TRANS_A) ? 1 : 0;
       a.tB = (s.flags & SMC_F_TRANS_B) ? 1 : 0;
       a.r = s.aux0; a.k = s.aux1; a.n = (long long)s.imm; a.C = C;
       a.ar = a.tA ? a.k : a.r;
       a.br = a.tB ? a.n : a.k;
-      // element strides of the operands are per flat element: fold them in by scaling se (already 1 or Cpad)
       long long outn = a.r * a.n;
+      if (!a.A.is_imm && a.A.sc == 0 && !a.B.is_imm && a.B.sc == 1 && !a.tB && C >= 32 && d.sc == 1) {
+        // data matrix x per-chain matrix: tiled kernel, thread = chain
+        MmDcArgs g;
+        g.A = a.A.p; g.ar = a.ar; g.tA = a.tA; g.B = a.B.p; g.out = d.p; g.Bse = a.B.se; g.Ose = d.se;
+        g.r = a.r; g.k = a.k; g.n = a.n; g.C = C; g.acc = acc;
+        int RI = 16;
+        {
+          long long best = -1;
+          for (int cand : {4, 8, 16}) {
+            long long cost = ((a.r + cand - 1) / cand) * (cand + 4);
+            if (best < 0 || cost <= best) { best = cost; RI = cand; }
+          }
+        }
+        int tcx = 32;
+        while (tcx < 256 && tcx < C) tcx <<= 1;
+        int ty = 256 / tcx;
+        long long groups = (a.r + RI - 1) / RI;
+        while (ty > 1 && ty / 2 >= groups) ty >>= 1, tcx = std::min(256, tcx * 2);
+        long long gtiles = (groups + ty - 1) / ty;
+        long long ctiles = (C + tcx - 1) / tcx;
+        long long S = 1;
+        long long blocks = ctiles * gtiles * a.n;
+        if (blocks < 2LL * m->ctx->sm_count && a.k >= 512)
+          S = std::min<long long>((2LL * m->ctx->sm_count + blocks - 1) / blocks, (a.k + 127) / 128);
+        g.chunk = ((a.k + S - 1) / S + 31) / 32 * 32;
+        S = (a.k + g.chunk - 1) / g.chunk;
+        g.S = (int)S;
+        if (S > 1) SMC_TRY(smc_scratch_reserve(m, S * outn * C));
+        g.partial = m->scratch;
+        dim3 grid((unsigned)ctiles, (unsigned)(gtiles * a.n), (unsigned)S), block(tcx, ty);
+        size_t smem = (size_t)ty * RI * 32 * sizeof(double);
+        if (RI == 4) k_matmul_dc<4><<<grid, block, smem, st>>>(g);
+        else if (RI == 8) k_matmul_dc<8><<<grid, block, smem, st>>>(g);
+        else k_matmul_dc<16><<<grid, block, smem, st>>>(g);
+        m->ctx->launches++;
+        if (S > 1) {
+          k_reduce_final<<<grid_for(outn * C), 256, 0, st>>>(m->scratch, S, outn, C, d, acc);
+          m->ctx->launches++;
+        }
+        break;
+      }
       long long S = 1;
       long long par = outn * C;
       if (par < 148LL * 512 && a.k >= 256) S = std::min<long long>((148LL * 512 + par - 1) / par, (a.k + 63) / 64);
       long long chunk = (a.k + S - 1) / S;
-      SMC_TRY(scratch_reserve(m, S * outn * C));
+      SMC_TRY(smc_scratch_reserve(m, S * outn * C));
       dim3 grid(grid_for(par), (unsigned)S);
       k_matmul<<<grid, 256, 0, st>>>(a, m->scratch, chunk);
       k_reduce_final<<<grid_for(par), 256, 0, st>>>(m->scratch, S, outn, C, d, acc);
@@ -595,14 +570,14 @@ static int run_statement(smc_model_s* m, const smc_tape_stmt& s, int64_t C, bool
       break;
     }
     case SMC_OP_TRANSPOSE: {
-      Opd src = make_opd(m, s.src[0], header);
+      Opd src = smc_make_opd(m, s.src[0]);
       long long rows = s.aux0, cols = s.aux1;
       k_transpose<<<grid_for(rows * cols * C), 256, 0, st>>>(src, d, rows, cols, C, acc);
       m->ctx->launches++;
       break;
     }
     case SMC_OP_GATHER: {
-      Opd src = make_opd(m, s.src[0], header);
+      Opd src = smc_make_opd(m, s.src[0]);
       long long n = m->idx_len[s.aux0];
       k_gather<<<grid_for(n * C), 256, 0, st>>>(src, d, m->idx_dev[s.aux0], n, C, acc);
       m->ctx->launches++;
@@ -610,42 +585,14 @@ static int run_statement(smc_model_s* m, const smc_tape_stmt& s, int64_t C, bool
     }
     case SMC_OP_SCATTER_SET:
     case SMC_OP_SCATTER_ADD: {
-      Opd src = make_opd(m, s.src[0], header);
+      Opd src = smc_make_opd(m, s.src[0]);
       long long n = m->idx_len[s.aux0];
       k_scatter<<<(unsigned)((C + 127) / 128), 128, 0, st>>>(src, d, m->idx_dev[s.aux0], n, C, s.op == SMC_OP_SCATTER_ADD);
       m->ctx->launches++;
       break;
     }
-    case SMC_OP_FUSED: {
-      const SmcProgram& pr = m->programs[s.aux0];
-      FusedArgs a;
-      a.prog = pr.dev_instr; a.opds = (const Opd*)m->dev_opds;
-      a.n_instr = (int)pr.h.n_instr; a.n_pro = (int)pr.h.n_prologue; a.n_red = (int)pr.h.n_red;
-      a.n = pr.h.n; a.C = C; a.bad = bad;
-      int tcc = 1;
-      while (tcc < C && tcc < (a.n == 1 ? 256 : 32)) tcc <<= 1;
-      a.tcc = tcc;
-      int eyn = 256 / tcc;
-      long long chain_tiles = (C + tcc - 1) / tcc;
-      long long S = std::max<long long>(1, std::min<long long>((296 + chain_tiles - 1) / chain_tiles, (a.n + eyn * 4 - 1) / (eyn * 4)));
-      a.chunk = (a.n + S - 1) / S;
-      S = (a.n + a.chunk - 1) / a.chunk;
-      a.S = (int)S;
-      if (a.n_red > 0) SMC_TRY(scratch_reserve(m, (int64_t)a.n_red * S * C));
-      a.partial = m->scratch;
-      size_t smem = ((pr.h.n_instr * sizeof(smc_prog_instr) + 15) / 16) * 16 + (size_t)a.n_red * 256 * sizeof(double);
-      dim3 grid((unsigned)chain_tiles, (unsigned)S);
-      k_fused<<<grid, 256, smem, st>>>(a);
-      m->ctx->launches++;
-      if (a.n_red > 0) {
-        FusedFinalArgs f;
-        f.partial = m->scratch; f.n_red = a.n_red; f.S = (int)S; f.C = C;
-        for (int k = 0; k < a.n_red; k++) { f.d[k] = make_dst(m, pr.red[k].reg); f.acc[k] = (int)pr.red[k].acc; }
-        k_fused_final<<<grid_for((long long)a.n_red * C), 256, 0, st>>>(f);
-        m->ctx->launches++;
-      }
-      break;
-    }
+    case SMC_OP_FUSED:
+      return smc_vm_launch(m, m->programs[s.aux0], C, bad);
     case SMC_OP_GLM: {
       for (auto& g : m->glm)
         if (&m->stmts[g.stmt] == &s) return smc_glm_launch(m, g, C);
@@ -657,7 +604,7 @@ static int run_statement(smc_model_s* m, const smc_tape_stmt& s, int64_t C, bool
       a.op = s.op; a.dist = s.aux0; a.darg = s.aux1; a.nsrc = s.nsrc; a.acc = acc;
       long long nsrc_el = 1;
       for (uint32_t k = 0; k < s.nsrc; k++) {
-        a.s[k] = make_opd(m, s.src[k], header);
+        a.s[k] = smc_make_opd(m, s.src[k]);
         nsrc_el = std::max<long long>(nsrc_el, m->regs[s.src[k]].numel);
       }
       for (uint32_t k = s.nsrc; k < 4; k++) a.s[k] = a.s[0];
@@ -678,14 +625,14 @@ static int run_statement(smc_model_s* m, const smc_tape_stmt& s, int64_t C, bool
           if (C < 148LL * 256) S = std::max<long long>(1, std::min<long long>((148LL * 256) / C, n / 32));
           long long chunk = (n + S - 1) / S;
           S = (n + chunk - 1) / chunk;
-          SMC_TRY(scratch_reserve(m, S * C));
+          SMC_TRY(smc_scratch_reserve(m, S * C));
           dim3 grid((unsigned)((C + 255) / 256), (unsigned)S);
           k_reduce_chains<<<grid, 256, 0, st>>>(a, m->scratch, chunk);
         } else {
           S = std::max<long long>(1, std::min<long long>((n + 2047) / 2048, std::max<long long>(1, (148LL * 16) / C)));
           long long chunk = (n + S - 1) / S;
           S = (n + chunk - 1) / chunk;
-          SMC_TRY(scratch_reserve(m, S * C));
+          SMC_TRY(smc_scratch_reserve(m, S * C));
           dim3 grid((unsigned)S, (unsigned)C);
           k_reduce_elems<<<grid, 256, 0, st>>>(a, m->scratch, chunk);
         }
@@ -756,13 +703,7 @@ extern "C" int smc_model_finalize(smc_model_t m, int64_t max_chains, int row_sha
       r.owned = true;
     }
   if (!m->ev0) { SMC_CUDA(cudaEventCreate(&m->ev0)); SMC_CUDA(cudaEventCreate(&m->ev1)); }
-  {
-    std::vector<Opd> opds(m->regs.size());
-    for (size_t i = 0; i < m->regs.size(); i++) opds[i] = make_opd(m, (uint32_t)i, false);
-    if (!m->dev_opds) SMC_CUDA(cudaMalloc(&m->dev_opds, std::max<size_t>(1, opds.size()) * sizeof(Opd)));
-    SMC_CUDA(cudaMemcpyAsync(m->dev_opds, opds.data(), opds.size() * sizeof(Opd), cudaMemcpyHostToDevice, st));
-    SMC_CUDA(cudaStreamSynchronize(st));
-  }
+  for (auto& pr : m->programs) SMC_TRY(smc_vm_prepare(m, pr));  // operand tables of the register programs (device pointers)
   // the let-header: parameter independent statements, evaluated once (src/parsing.jl:432-442)
   SMC_CUDA(cudaMemsetAsync(m->bad, 0, (size_t)(Cpad + 32) * sizeof(int), st));
   for (int si : m->hdr_stmts) SMC_TRY(run_statement(m, m->stmts[si], 1, true));
@@ -798,7 +739,7 @@ static int eval_body(smc_model_s* m, int64_t C, bool with_grad) {
     SMC_TRY(run_statement(m, s, C, false));
   }
   const SmcReg& rr = m->regs[m->hdr.result_reg];
-  Opd ro = make_opd(m, m->hdr.result_reg, false);
+  Opd ro = smc_make_opd(m, m->hdr.result_reg);
   if (ro.is_imm || rr.numel != 1) { smc_set_error("tape: result register must be a computed scalar"); return SMC_ERR_INVALID; }
   // row-sharded models all-reduce inside the GLM statement (its (L, G) are the only row sums), so every
   // rank finishes with identical (logp, grad) here
@@ -871,14 +812,14 @@ extern "C" int smc_eval(smc_model_t m, const double* beta, int64_t C, double* lo
   cudaSetDevice(m->ctx->device);
   cudaStream_t st = m->ctx->stream;
   int64_t M = m->M;
-  SMC_TRY(scratch_reserve(m, std::max<int64_t>(C * M, 1)));
+  SMC_TRY(smc_scratch_reserve(m, std::max<int64_t>(C * M, 1)));
   SMC_CUDA(cudaMemcpyAsync(m->scratch, beta, (size_t)C * M * sizeof(double), cudaMemcpyHostToDevice, st));
   k_rows_to_cols<<<grid_for(C * M), 256, 0, st>>>(m->scratch, m->beta, C, M, m->Cpad, 0);
   m->ctx->launches++;
   SMC_TRY(smc_model_eval_device(m, C, grad != nullptr));
   SMC_CUDA(cudaMemcpyAsync(logp, m->logp, (size_t)C * sizeof(double), cudaMemcpyDeviceToHost, st));
   if (grad) {
-    SMC_TRY(scratch_reserve(m, std::max<int64_t>(C * M, 1)));
+    SMC_TRY(smc_scratch_reserve(m, std::max<int64_t>(C * M, 1)));
     k_cols_to_rows<<<grid_for(C * M), 256, 0, st>>>(m->grad, m->scratch, C, M, m->Cpad);
     m->ctx->launches++;
     SMC_CUDA(cudaMemcpyAsync(grad, m->scratch, (size_t)C * M * sizeof(double), cudaMemcpyDeviceToHost, st));

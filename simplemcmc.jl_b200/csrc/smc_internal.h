@@ -55,7 +55,8 @@ struct SmcGlmPlan {  // one SMC_OP_GLM statement, prepared at finalize
   double par = 0.0;
   int64_t N = 0;       // local rows
   int M = 0, MP = 0;   // columns and columns padded to a multiple of 8
-  double* Xrm = nullptr;  // [N][MP] row major, zero padded
+  double* Xrm = nullptr;  // [N][MP] row major, zero padded (DMMA kernel; built lazily)
+  const double* Xcm = nullptr;  // [M][N] column major as bound (stream kernel)
   const double* y = nullptr;
   double* ybuf = nullptr;  // response as the kernel consumes it (sign-normalised, broadcast)
   int64_t y_len = 0;
@@ -65,11 +66,35 @@ struct SmcGlmPlan {  // one SMC_OP_GLM statement, prepared at finalize
   float last_ms = 0.f;
 };
 
+// Micro-operation of the register-program VM (vm_exec.cu): the tape's LOADV/LOADS/STOREV/REDUCE instructions are
+// folded into operand modes / side effects of the computing instruction at plan time.
+enum { VM_NONE = 0, VM_LOCAL = 1, VM_SCAL = 2, VM_ARRAY = 3 };
+enum { VMF_ACC = 1, VMF_WRITE = 2, VMF_STORE = 4, VMF_REDUCE = 8 };
+struct VmUop {       // 32 bytes
+  uint8_t op, dist, darg, flags;
+  uint8_t mode[4];   // operands 0..2 and [3] = the accumulate operand (VMF_ACC)
+  uint16_t idx[4];   // local slot / scalar slot / array descriptor
+  uint16_t dst, store, red, nsrc;
+  uint32_t pad[2];
+};
+struct VmDesc {      // 32 bytes; p == NULL: immediate
+  const double* p;
+  long long se, sc;
+  double imm;
+};
+
 struct SmcProgram {  // one SMC_OP_FUSED register program
   smc_prog_header h;
   std::vector<smc_prog_instr> instr;
   std::vector<smc_prog_red> red;
-  smc_prog_instr* dev_instr = nullptr;
+  // plan (pointer independent, built at compile time)
+  std::vector<VmUop> uops;
+  std::vector<uint32_t> desc_regs;  // tape register of every array descriptor (loads and stores)
+  std::vector<uint32_t> scal_regs;  // tape register of every per-chain scalar input (staged once per block)
+  int n_loc = 0;
+  // device tables (built at finalize): VmUop[n_uops] | VmDesc[n_descs] | VmDesc[n_scal]
+  void* dev_tables = nullptr;
+  size_t dev_tables_bytes = 0;
 };
 
 struct SmcEvalGraph {  // one captured evaluation (all statements of the tape for a chain count), replayed with one launch
@@ -91,7 +116,6 @@ struct smc_model_s {
   std::vector<uint32_t> idx_len;
   std::vector<SmcGlmPlan> glm;
   std::vector<SmcProgram> programs;
-  void* dev_opds = nullptr;  // Opd[n_regs]: operand descriptors of every tape register (rebuilt at finalize)
   bool finalized = false;
   int row_shard = 0;
   int64_t M = 0;       // n_params
@@ -117,6 +141,11 @@ struct smc_model_s {
 int smc_model_eval_device(smc_model_s* m, int64_t C, bool with_grad);  // beta -> logp, grad (device resident)
 int smc_stage_reserve(smc_model_s* m, int64_t doubles);
 void smc_graphs_invalidate(smc_model_s* m);
+
+// vm_exec.cu
+int smc_vm_plan(smc_model_s* m, SmcProgram& pr);      // instruction list -> micro-ops
+int smc_vm_prepare(smc_model_s* m, SmcProgram& pr);   // device tables (after registers are allocated)
+int smc_vm_launch(smc_model_s* m, SmcProgram& pr, int64_t C, int* bad);
 
 // glm_fused.cu
 int smc_glm_prepare(smc_model_s* m, SmcGlmPlan& g);

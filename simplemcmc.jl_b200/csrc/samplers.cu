@@ -38,19 +38,69 @@ __device__ __forceinline__ double rng_uniform(const RngSrc& r, long long step, l
   return smc_uniform(r.seed, (unsigned long long)(c + r.chain_offset), (unsigned long long)step, (uint32_t)k);
 }
 
-// v[j][c] ~ N(0,1), j < M ; returns sum v^2
+// Thread layout of the per-chain sampler kernels: block = (32 chains) x (LY component lanes).  A warp is 32 consecutive
+// chains of one lane, so every [M][Cpad] access is a coalesced line; lane ly owns components q = ly, ly + LY, ... of
+// its chain (momentum pairs p = ly, ly + LY, ... when drawing normals).  Per-chain scalars are read by all lanes into
+// registers, recomputed identically, and committed by lane 0; sums over components go through shared memory in lane
+// order (deterministic).
+constexpr int LY = 8;
+constexpr int CXB = 32;
+
+struct Ln {
+  long long c;
+  int ly;
+  bool in;
+};
+__device__ __forceinline__ Ln lanes(long long C) {
+  Ln L;
+  L.c = (long long)blockIdx.x * CXB + threadIdx.x;
+  L.ly = threadIdx.y;
+  L.in = L.c < C;
+  return L;
+}
+__device__ __forceinline__ double ysum(double v, double* sh) {   // sh[LY * CXB]; call from every thread of the block
+  sh[threadIdx.y * CXB + threadIdx.x] = v;
+  __syncthreads();
+  double t = 0.0;
+#pragma unroll
+  for (int y = 0; y < LY; y++) t += sh[y * CXB + threadIdx.x];
+  __syncthreads();
+  return t;
+}
+__device__ __forceinline__ void ysum2(double& a, double& b, double* sh) {   // sh[2 * LY * CXB]
+  sh[threadIdx.y * CXB + threadIdx.x] = a;
+  sh[LY * CXB + threadIdx.y * CXB + threadIdx.x] = b;
+  __syncthreads();
+  double ta = 0.0, tb = 0.0;
+#pragma unroll
+  for (int y = 0; y < LY; y++) { ta += sh[y * CXB + threadIdx.x]; tb += sh[LY * CXB + y * CXB + threadIdx.x]; }
+  __syncthreads();
+  a = ta; b = tb;
+}
+
+// this lane's share of v[j][c] ~ N(0,1), j < M (also stored to v2 when given); returns its part of sum v^2
 __device__ __forceinline__ double draw_normals(const RngSrc& r, long long step, long long c, long long C, long long M,
-                                               long long Cpad, double* v) {
+                                               long long Cpad, double* v, double* v2, int ly) {
   double ss = 0.0;
   if (r.inj_n) {
     const double* src = r.inj_n + (step * C + c) * M;
-    for (long long j = 0; j < M; j++) { double z = src[j]; v[j * Cpad + c] = z; ss += z * z; }
+    for (long long j = ly; j < M; j += LY) {
+      double z = src[j];
+      v[j * Cpad + c] = z;
+      if (v2) v2[j * Cpad + c] = z;
+      ss += z * z;
+    }
   } else {
-    for (long long j = 0; j < M; j += 2) {
+    for (long long p = ly; 2 * p < M; p += LY) {
+      const long long j = 2 * p;
       double z0, z1;
-      smc_normal_pair(r.seed, (unsigned long long)(c + r.chain_offset), (unsigned long long)step, (uint32_t)(j >> 1), z0, z1);
+      smc_normal_pair(r.seed, (unsigned long long)(c + r.chain_offset), (unsigned long long)step, (uint32_t)p, z0, z1);
       v[j * Cpad + c] = z0; ss += z0 * z0;
-      if (j + 1 < M) { v[(j + 1) * Cpad + c] = z1; ss += z1 * z1; }
+      if (v2) v2[j * Cpad + c] = z0;
+      if (j + 1 < M) {
+        v[(j + 1) * Cpad + c] = z1; ss += z1 * z1;
+        if (v2) v2[(j + 1) * Cpad + c] = z1;
+      }
     }
   }
   return ss;
@@ -66,15 +116,18 @@ struct Recorder {
   long long burnin;
 };
 
+// addToRes! (src/samplers.jl:342-350) + per-chain Welford moments; lane ly records its components of beta
 __device__ __forceinline__ void record(const Recorder& R, long long step, long long c, long long M, long long Cpad,
-                                       const double* beta, double ll, bool accepted) {
+                                       const double* beta, double ll, bool accepted, int ly) {
   if (step < R.burnin) return;
   long long s = step - R.burnin;
-  if (R.loglik) R.loglik[s * Cpad + c] = ll;
-  if (R.accept) R.accept[s * Cpad + c] = accepted ? 1.0 : 0.0;
-  R.nacc[c] += accepted ? 1.0 : 0.0;
+  if (ly == 0) {
+    if (R.loglik) R.loglik[s * Cpad + c] = ll;
+    if (R.accept) R.accept[s * Cpad + c] = accepted ? 1.0 : 0.0;
+    R.nacc[c] += accepted ? 1.0 : 0.0;
+  }
   double n = (double)(s + 1);
-  for (long long j = 0; j < M; j++) {
+  for (long long j = ly; j < M; j += LY) {
     double x = beta[j * Cpad + c];
     if (R.draws) R.draws[(s * M + j) * Cpad + c] = x;
     double mu = R.mean[j * Cpad + c], d = x - mu;
@@ -86,21 +139,28 @@ __device__ __forceinline__ void record(const Recorder& R, long long step, long l
 
 // ---------------------------------------------------------------------------------------------- HMC
 // state0.v = randn ; update!(state0) ; state = state0     (src/samplers.jl:151-153)
-__global__ void k_hmc_begin(RngSrc rng, long long step, long long C, long long M, long long Cpad, const double* b0,
-                            const double* g0, const double* l0, double* beta, double* grad, double* logp, double* v,
-                            double* H0, double* H, int* active) {
-  long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double ss = draw_normals(rng, step, c, C, M, Cpad, v);
-  for (long long j = 0; j < M; j++) {
-    beta[j * Cpad + c] = b0[j * Cpad + c];
-    grad[j * Cpad + c] = g0[j * Cpad + c];
+__global__ void __launch_bounds__(CXB * LY) k_hmc_begin(RngSrc rng, long long step, long long C, long long M, long long Cpad,
+                                                      const double* b0, const double* g0, const double* l0, double* beta,
+                                                      double* grad, double* logp, double* v, double* H0, double* H, int* active) {
+  __shared__ double sh[LY * CXB];
+  const Ln L = lanes(C);
+  const long long c = L.c;
+  double ss = 0.0;
+  if (L.in) {
+    ss = draw_normals(rng, step, c, C, M, Cpad, v, nullptr, L.ly);
+    for (long long j = L.ly; j < M; j += LY) {
+      beta[j * Cpad + c] = b0[j * Cpad + c];
+      grad[j * Cpad + c] = g0[j * Cpad + c];
+    }
   }
-  double ll = l0[c];
-  logp[c] = ll;
-  H0[c] = ll - ss / 2.0;
-  H[c] = H0[c];
-  active[c] = isfinite(ll) ? 1 : 0;
+  ss = ysum(ss, sh);
+  if (L.in && L.ly == 0) {
+    double ll = l0[c];
+    logp[c] = ll;
+    H0[c] = ll - ss / 2.0;
+    H[c] = H0[c];
+    active[c] = isfinite(ll) ? 1 : 0;
+  }
 }
 
 // n.v += n.grad * ve / 2 ; n.beta += ve * n.v          (src/samplers.jl:52-53)
@@ -118,39 +178,54 @@ __global__ void k_leapfrog_pre(long long C, long long M, long long Cpad, double 
 }
 
 // n.v += n.grad * ve / 2 ; update!(n) ; loop condition isfinite(state.llik)   (src/samplers.jl:55-56,156)
-__global__ void k_leapfrog_post(long long C, long long M, long long Cpad, double eps, int* active, const double* grad,
-                                const double* logp, double* v, double* H, unsigned long long* nleap) {
-  long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C || !active[c]) return;
+__global__ void __launch_bounds__(CXB * LY) k_leapfrog_post(long long C, long long M, long long Cpad, double eps, int* active,
+                                                          const double* grad, const double* logp, double* v, double* H,
+                                                          unsigned long long* nleap) {
+  __shared__ double sh[LY * CXB];
+  const Ln L = lanes(C);
+  const long long c = L.c;
+  const bool act = L.in && active[c];
   double ss = 0.0;
-  for (long long j = 0; j < M; j++) {
-    long long o = j * Cpad + c;
-    double vv = v[o] + grad[o] * eps / 2.0;
-    v[o] = vv;
-    ss += vv * vv;
+  if (act)
+    for (long long j = L.ly; j < M; j += LY) {
+      long long o = j * Cpad + c;
+      double vv = v[o] + grad[o] * eps / 2.0;
+      v[o] = vv;
+      ss += vv * vv;
+    }
+  ss = ysum(ss, sh);   // (also orders every lane's read of active[c] before lane 0 clears it)
+  if (act && L.ly == 0) {
+    double ll = logp[c];
+    H[c] = ll - ss / 2.0;
+    if (!isfinite(ll)) active[c] = 0;
+    nleap[c] += 1ull;
   }
-  double ll = logp[c];
-  H[c] = ll - ss / 2.0;
-  if (!isfinite(ll)) active[c] = 0;
-  nleap[c] += 1ull;
 }
 
 // if rand() < exp(state.H - state0.H): state0 = state ; addToRes!   (src/samplers.jl:162-166)
-__global__ void k_hmc_accept(RngSrc rng, long long step, long long C, long long M, long long Cpad, const double* beta,
-                             const double* grad, const double* logp, const double* H, const double* H0, double* b0,
-                             double* g0, double* l0, Recorder R) {
-  long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double u = rng_uniform(rng, step, c, C, 0);
-  bool acc = u < exp(H[c] - H0[c]);
-  if (acc) {
-    for (long long j = 0; j < M; j++) {
-      b0[j * Cpad + c] = beta[j * Cpad + c];
-      g0[j * Cpad + c] = grad[j * Cpad + c];
+__global__ void __launch_bounds__(CXB * LY) k_hmc_accept(RngSrc rng, long long step, long long C, long long M, long long Cpad,
+                                                       const double* beta, const double* grad, const double* logp,
+                                                       const double* H, const double* H0, double* b0, double* g0, double* l0,
+                                                       Recorder R) {
+  const Ln L = lanes(C);
+  const long long c = L.c;
+  bool acc = false;
+  double ll = 0.0;
+  if (L.in) {
+    double u = rng_uniform(rng, step, c, C, 0);
+    acc = u < exp(H[c] - H0[c]);
+    ll = acc ? logp[c] : l0[c];
+    if (acc) {
+      for (long long j = L.ly; j < M; j += LY) {
+        b0[j * Cpad + c] = beta[j * Cpad + c];
+        g0[j * Cpad + c] = grad[j * Cpad + c];
+      }
     }
-    l0[c] = logp[c];
   }
-  record(R, step, c, M, Cpad, b0, l0[c], acc);
+  __syncthreads();   // every lane has read l0[c]
+  if (!L.in) return;
+  if (acc && L.ly == 0) l0[c] = ll;
+  record(R, step, c, M, Cpad, b0, ll, acc, L.ly);
 }
 
 // ---------------------------------------------------------------------------------------------- RWM
@@ -159,7 +234,7 @@ __global__ void k_rwm_propose(RngSrc rng, long long step, long long C, long long
                               const double* S, double* jump, double* beta) {
   long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  draw_normals(rng, step, c, C, M, Cpad, jump);
+  for (int y = 0; y < LY; y++) draw_normals(rng, step, c, C, M, Cpad, jump, nullptr, y);   // thread per chain here
   for (long long i = 0; i < M; i++) {
     double acc = 0.0;
     for (long long k = 0; k <= i; k++) acc += S[(i + k * M) * Cpad + c] * jump[k * Cpad + c];  // S lower triangular
@@ -183,7 +258,7 @@ __global__ void k_rwm_accept(RngSrc rng, long long step, long long C, long long 
     l0[c] = lnew;
   }
   double lcur = l0[c];
-  record(R, step, c, M, Cpad, b0, lcur, lold != lcur);
+  for (int y = 0; y < LY; y++) record(R, step, c, M, Cpad, b0, lcur, lold != lcur, y);
   // adaptation
   double i1 = (double)(step + 1);
   double eta = fmin(1.0, (double)M * pow(i1, -2.0 / 3.0));
@@ -252,6 +327,8 @@ __global__ void k_div(double* p, long long n, double d) {
 }
 
 inline unsigned gridc(long long n, int block = 128) { return (unsigned)std::max<long long>(1, (n + block - 1) / block); }
+inline dim3 lgrid(long long C) { return dim3((unsigned)((C + CXB - 1) / CXB)); }   // lane-parallel kernels: (32 chains) x (LY lanes)
+inline dim3 lblock() { return dim3(CXB, LY); }
 inline unsigned gride(long long n) { return (unsigned)std::max<long long>(1, std::min<long long>((n + 255) / 256, 148LL * 32)); }
 
 struct Run {
@@ -409,16 +486,16 @@ extern "C" int smc_hmc_run(smc_model_t m, const smc_sampler_config* cfg, const d
   SMC_TRY(r.A.alloc(&active, Cpad));
   int64_t evals = 1;
   for (long long i = 0; i < cfg->steps; i++) {
-    k_hmc_begin<<<gridc(C), 128, 0, st>>>(r.rng, i, C, M, Cpad, r.b0, r.g0, r.l0, m->beta, m->grad, m->logp, v, H0, H, active);
+    k_hmc_begin<<<lgrid(C), lblock(), 0, st>>>(r.rng, i, C, M, Cpad, r.b0, r.g0, r.l0, m->beta, m->grad, m->logp, v, H0, H, active);
     for (long long j = 0; j < cfg->isteps; j++) {
       k_leapfrog_pre<<<gride(C * M), 256, 0, st>>>(C, M, Cpad, cfg->stepsize, active, m->beta, m->grad, v);
       m->ctx->launches += 1;
       SMC_TRY(smc_model_eval_device(m, C, true));
-      k_leapfrog_post<<<gridc(C), 128, 0, st>>>(C, M, Cpad, cfg->stepsize, active, m->grad, m->logp, v, H, r.nleap);
+      k_leapfrog_post<<<lgrid(C), lblock(), 0, st>>>(C, M, Cpad, cfg->stepsize, active, m->grad, m->logp, v, H, r.nleap);
       m->ctx->launches += 1;
       evals++;
     }
-    k_hmc_accept<<<gridc(C), 128, 0, st>>>(r.rng, i, C, M, Cpad, m->beta, m->grad, m->logp, H, H0, r.b0, r.g0, r.l0, r.R);
+    k_hmc_accept<<<lgrid(C), lblock(), 0, st>>>(r.rng, i, C, M, Cpad, m->beta, m->grad, m->logp, H, H0, r.b0, r.g0, r.l0, r.R);
     m->ctx->launches += 2;
   }
   return run_finish(r, evals);
@@ -515,19 +592,20 @@ struct Nuts {
   unsigned long long* rounds_active;
 };
 
-__device__ __forceinline__ bool uturn_dev(const double* minus_b, const double* minus_v, const double* plus_b,
-                                          const double* plus_v, long long c, long long M, long long Cpad) {
-  double d1 = 0.0, d2 = 0.0;   // dot(s2.beta - s1.beta, s1.v) < 0 || dot(s2.beta - s1.beta, s2.v) < 0   (src/samplers.jl:48)
-  for (long long k = 0; k < M; k++) {
+// this lane's share of the two U-turn dot products (src/samplers.jl:48):
+//   d1 = dot(s2.beta - s1.beta, s1.v),  d2 = dot(s2.beta - s1.beta, s2.v)      (s1 = minus edge, s2 = plus edge)
+__device__ __forceinline__ void uturn_part(const double* minus_b, const double* minus_v, const double* plus_b,
+                                           const double* plus_v, long long c, long long M, long long Cpad, int ly,
+                                           double& d1, double& d2) {
+  for (long long k = ly; k < M; k += LY) {
     double db = plus_b[k * Cpad + c] - minus_b[k * Cpad + c];
     d1 += db * minus_v[k * Cpad + c];
     d2 += db * plus_v[k * Cpad + c];
   }
-  return d1 < 0.0 || d2 < 0.0;
 }
 
-__device__ __forceinline__ void copy_vec(double* dst, const double* src, long long c, long long M, long long Cpad) {
-  for (long long k = 0; k < M; k++) dst[k * Cpad + c] = src[k * Cpad + c];
+__device__ __forceinline__ void copy_vec(double* dst, const double* src, long long c, long long M, long long Cpad, int ly) {
+  for (long long k = ly; k < M; k += LY) dst[k * Cpad + c] = src[k * Cpad + c];
 }
 
 __global__ void k_nuts_init(long long C, Nuts T) {
@@ -538,18 +616,23 @@ __global__ void k_nuts_init(long long C, Nuts T) {
   T.lebar[c] = 0.0;
 }
 
-__global__ void k_nuts_begin(RngSrc rng, long long step, long long C, long long M, long long Cpad, const double* b0,
-                             const double* g0, const double* l0, Nuts T) {
-  long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double ss = draw_normals(rng, step, c, C, M, Cpad, T.mv);
-  for (long long k = 0; k < M; k++) {
-    long long o = k * Cpad + c;
-    double b = b0[o], g = g0[o];
-    T.pv[o] = T.mv[o];
-    T.mb[o] = b; T.pb[o] = b; T.sb[o] = b;
-    T.mg[o] = g; T.pg[o] = g; T.sg[o] = g;
+__global__ void __launch_bounds__(CXB * LY) k_nuts_begin(RngSrc rng, long long step, long long C, long long M, long long Cpad,
+                                                       const double* b0, const double* g0, const double* l0, Nuts T) {
+  __shared__ double sh[LY * CXB];
+  const Ln L = lanes(C);
+  const long long c = L.c;
+  double ss = 0.0;
+  if (L.in) {
+    ss = draw_normals(rng, step, c, C, M, Cpad, T.mv, T.pv, L.ly);
+    for (long long k = L.ly; k < M; k += LY) {
+      long long o = k * Cpad + c;
+      double b = b0[o], g = g0[o];
+      T.mb[o] = b; T.pb[o] = b; T.sb[o] = b;
+      T.mg[o] = g; T.pg[o] = g; T.sg[o] = g;
+    }
   }
+  ss = ysum(ss, sh);
+  if (!L.in || L.ly != 0) return;
   double ll = l0[c];
   T.ml[c] = ll; T.pl[c] = ll; T.sl[c] = ll;
   double H0 = ll - ss / 2.0;
@@ -565,29 +648,45 @@ __global__ void k_nuts_begin(RngSrc rng, long long step, long long C, long long 
   T.nalast[c] = 1.0;
 }
 
-__global__ void k_nuts_pre(RngSrc rng, long long step, long long C, long long M, long long Cpad, double* beta,
-                           double* grad, double* logp, Nuts T) {
-  long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C || !T.active[c]) return;
-  if (T.newdbl[c]) {
-    int k = T.ucount[c];
-    double r = rng_uniform(rng, step, c, C, k);
-    T.ucount[c] = k + 1;
-    int dir = (r > 0.5) ? 1 : -1;   // dir = (rand() > 0.5) * 2. - 1., :280
-    T.dir[c] = dir;
+__global__ void __launch_bounds__(CXB * LY) k_nuts_pre(RngSrc rng, long long step, long long C, long long M, long long Cpad,
+                                                     double* beta, double* grad, double* logp, Nuts T) {
+  const Ln L = lanes(C);
+  const long long c = L.c;
+  const bool act = L.in && T.active[c];
+  int newdbl = 0, dir = 0, k = 0;
+  double eps = 0.0, lp_edge = 0.0;
+  if (act) {
+    newdbl = T.newdbl[c];
+    eps = T.eps[c];
+    if (newdbl) {
+      k = T.ucount[c];
+      double r = rng_uniform(rng, step, c, C, k);
+      dir = (r > 0.5) ? 1 : -1;   // dir = (rand() > 0.5) * 2. - 1., :280
+      lp_edge = dir < 0 ? T.ml[c] : T.pl[c];
+    } else {
+      dir = T.dir[c];
+    }
+  }
+  __syncthreads();   // every lane holds the chain's scalars before lane 0 updates them
+  if (!act) return;
+  if (newdbl) {
     const double* eb = dir < 0 ? T.mb : T.pb;
     const double* ev = dir < 0 ? T.mv : T.pv;
     const double* eg = dir < 0 ? T.mg : T.pg;
-    for (long long q = 0; q < M; q++) {
+    for (long long q = L.ly; q < M; q += LY) {
       long long o = q * Cpad + c;
       beta[o] = eb[o]; T.tv[o] = ev[o]; grad[o] = eg[o];
     }
-    logp[c] = dir < 0 ? T.ml[c] : T.pl[c];
-    T.leaf[c] = 0;
-    T.newdbl[c] = 0;
+    if (L.ly == 0) {
+      T.ucount[c] = k + 1;
+      T.dir[c] = dir;
+      logp[c] = lp_edge;
+      T.leaf[c] = 0;
+      T.newdbl[c] = 0;
+    }
   }
-  double ve = T.dir[c] * T.eps[c];
-  for (long long q = 0; q < M; q++) {   // leapFrog, :52-53
+  double ve = dir * eps;
+  for (long long q = L.ly; q < M; q += LY) {   // leapFrog, :52-53
     long long o = q * Cpad + c;
     double vv = T.tv[o] + grad[o] * ve / 2.0;
     T.tv[o] = vv;
@@ -595,105 +694,135 @@ __global__ void k_nuts_pre(RngSrc rng, long long step, long long C, long long M,
   }
 }
 
-__global__ void k_nuts_post(RngSrc rng, long long step, long long C, long long M, long long Cpad, const double* beta,
-                            const double* grad, const double* logp, Nuts T, unsigned long long* nleap) {
-  long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C || !T.active[c]) return;
+__global__ void __launch_bounds__(CXB * LY) k_nuts_post(RngSrc rng, long long step, long long C, long long M, long long Cpad,
+                                                      const double* beta, const double* grad, const double* logp, Nuts T,
+                                                      unsigned long long* nleap) {
+  __shared__ double sh[2 * LY * CXB];
+  const Ln L = lanes(C);
+  const long long c = L.c;
+  const int ly = L.ly;
+  const bool act = L.in && T.active[c];
   const long long LS = M * Cpad;  // stride between stack levels
-  const int dir = T.dir[c];
-  double ve = dir * T.eps[c];
-  double ss = 0.0;
-  for (long long q = 0; q < M; q++) {   // second half kick + update!, :55-56
-    long long o = q * Cpad + c;
-    double vv = T.tv[o] + grad[o] * ve / 2.0;
-    T.tv[o] = vv;
-    ss += vv * vv;
+  int dir = 1, leaf = 0, j = 0, ucount = 0;
+  double eps = 0.0, u = 0.0, H0 = 0.0, ll = 0.0, ntot = 1.0;
+  if (act) {
+    dir = T.dir[c]; eps = T.eps[c]; u = T.u[c]; H0 = T.H0[c]; ll = logp[c];
+    leaf = T.leaf[c]; j = T.j[c]; ucount = T.ucount[c]; ntot = T.ntot[c];
   }
-  double ll = logp[c];
-  double H = ll - ss / 2.0;
-  nleap[c] += 1ull;
+  const double ve = dir * eps;
+  double ss = 0.0;
+  if (act)
+    for (long long q = ly; q < M; q += LY) {   // second half kick + update!, :55-56
+      long long o = q * Cpad + c;
+      double vv = T.tv[o] + grad[o] * ve / 2.0;
+      T.tv[o] = vv;
+      ss += vv * vv;
+    }
+  ss = ysum(ss, sh);
+  const double H = ll - ss / 2.0;
   // ---- leaf (buildTree with j == 0, :230-236)
-  const double u = T.u[c];
   double n2 = (u <= H) ? 1.0 : 0.0;
   bool s2 = u < (kDeltaMax + H);
-  double a2 = fmin(1.0, exp(H - T.H0[c]));
+  double a2 = fmin(1.0, exp(H - H0));
   double na2 = 1.0;
-  copy_vec(T.cnb, beta, c, M, Cpad);
-  copy_vec(T.cnv, T.tv, c, M, Cpad);
-  copy_vec(T.csb, beta, c, M, Cpad);
-  copy_vec(T.csg, grad, c, M, Cpad);
-  T.csl[c] = ll;
-  // ---- merges where the recursion returns (:238-256): levels = trailing one bits of the leaf index
-  const int leaf = T.leaf[c];
-  const int j = T.j[c];
-  int level = 0;
-  int ucount = T.ucount[c];
-  for (;; level++) {
-    if (level >= j) break;
-    if (!((leaf >> level) & 1)) {
-      // this sub-tree is a first child here: complete trees wait on the stack; a cut tree is handed up unchanged
-      // (`if s1` is false, :239) and may still be merged, as a second child, further up
-      if (s2) break;
-      continue;
-    }
-    const long long so = (long long)level * LS, sc = (long long)level * Cpad + c;
-    double n1 = T.kn[sc];
-    double r = rng_uniform(rng, step, c, C, ucount++);
-    bool take_second = r <= n2 / (n2 + n1);   // NaN (0/0) compares false, as in the reference
-    if (!take_second) {
-      copy_vec(T.csb, T.ksb + so, c, M, Cpad);
-      copy_vec(T.csg, T.ksg + so, c, M, Cpad);
-      T.csl[c] = T.ksl[sc];
-    }
-    copy_vec(T.cnb, T.knb + so, c, M, Cpad);   // the merged sub-tree starts where the first one started
-    copy_vec(T.cnv, T.knv + so, c, M, Cpad);
-    a2 += T.ka[sc];
-    na2 += T.kna[sc];
-    if (s2) {
-      bool ut = dir > 0 ? uturn_dev(T.cnb, T.cnv, beta, T.tv, c, M, Cpad) : uturn_dev(beta, T.tv, T.cnb, T.cnv, c, M, Cpad);
-      s2 = !ut;
-    }
-    n2 += n1;
+  double csl = ll;
+  if (act) {
+    copy_vec(T.cnb, beta, c, M, Cpad, ly);
+    copy_vec(T.cnv, T.tv, c, M, Cpad, ly);
+    copy_vec(T.csb, beta, c, M, Cpad, ly);
+    copy_vec(T.csg, grad, c, M, Cpad, ly);
   }
-  bool done = (!s2) || (leaf == (1 << j) - 1);
-  if (!done) {
-    const long long so = (long long)level * LS, sc = (long long)level * Cpad + c;
-    copy_vec(T.knb + so, T.cnb, c, M, Cpad);
-    copy_vec(T.knv + so, T.cnv, c, M, Cpad);
-    copy_vec(T.ksb + so, T.csb, c, M, Cpad);
-    copy_vec(T.ksg + so, T.csg, c, M, Cpad);
-    T.ksl[sc] = T.csl[c];
-    T.kn[sc] = n2; T.ka[sc] = a2; T.kna[sc] = na2;
-    T.leaf[c] = leaf + 1;
-    T.ucount[c] = ucount;
-    atomicAdd(T.n_active, 1);
-    return;
+  // ---- merges where the recursion returns (:238-256): levels = trailing one bits of the leaf index.  The loop is
+  // uniform over the block (the U-turn test needs every lane); a chain leaves it at `stop_level`.
+  bool merging = act;
+  int stop_level = kMaxDepth;
+  for (int level = 0; level < kMaxDepth; level++) {
+    bool do_merge = false;
+    if (merging) {
+      if (level >= j) { merging = false; stop_level = level; }
+      else if (!((leaf >> level) & 1)) {
+        // this sub-tree is a first child here: complete trees wait on the stack; a cut tree is handed up unchanged
+        // (`if s1` is false, :239) and may still be merged, as a second child, further up
+        if (s2) { merging = false; stop_level = level; }
+      } else {
+        do_merge = true;
+      }
+    }
+    if (!__syncthreads_or(merging ? 1 : 0)) break;
+    if (!__syncthreads_or(do_merge ? 1 : 0)) continue;
+    double d1 = 0.0, d2 = 0.0;
+    bool test_uturn = false;
+    if (do_merge) {
+      const long long so = (long long)level * LS, sc = (long long)level * Cpad + c;
+      double n1 = T.kn[sc];
+      double r = rng_uniform(rng, step, c, C, ucount++);
+      bool take_second = r <= n2 / (n2 + n1);   // NaN (0/0) compares false, as in the reference
+      if (!take_second) {
+        copy_vec(T.csb, T.ksb + so, c, M, Cpad, ly);
+        copy_vec(T.csg, T.ksg + so, c, M, Cpad, ly);
+        csl = T.ksl[sc];
+      }
+      copy_vec(T.cnb, T.knb + so, c, M, Cpad, ly);   // the merged sub-tree starts where the first one started
+      copy_vec(T.cnv, T.knv + so, c, M, Cpad, ly);
+      a2 += T.ka[sc];
+      na2 += T.kna[sc];
+      if (s2) {
+        test_uturn = true;
+        if (dir > 0) uturn_part(T.cnb, T.cnv, beta, T.tv, c, M, Cpad, ly, d1, d2);
+        else uturn_part(beta, T.tv, T.cnb, T.cnv, c, M, Cpad, ly, d1, d2);
+      }
+      n2 += n1;
+    }
+    ysum2(d1, d2, sh);
+    if (test_uturn) s2 = !(d1 < 0.0 || d2 < 0.0);
+  }
+  const bool done = act && ((!s2) || (leaf == (1 << j) - 1));
+  if (act && !done) {
+    const long long so = (long long)stop_level * LS, sc = (long long)stop_level * Cpad + c;
+    copy_vec(T.knb + so, T.cnb, c, M, Cpad, ly);
+    copy_vec(T.knv + so, T.cnv, c, M, Cpad, ly);
+    copy_vec(T.ksb + so, T.csb, c, M, Cpad, ly);
+    copy_vec(T.ksg + so, T.csg, c, M, Cpad, ly);
+    if (ly == 0) {
+      T.ksl[sc] = csl;
+      T.kn[sc] = n2; T.ka[sc] = a2; T.kna[sc] = na2;
+      T.leaf[c] = leaf + 1;
+      T.ucount[c] = ucount;
+      nleap[c] += 1ull;
+      atomicAdd(T.n_active, 1);
+    }
   }
   // ---- the doubling is complete (or was cut): outer loop body, :281-291
-  double* eb = dir < 0 ? T.mb : T.pb;
-  double* ev = dir < 0 ? T.mv : T.pv;
-  double* eg = dir < 0 ? T.mg : T.pg;
-  for (long long q = 0; q < M; q++) {
-    long long o = q * Cpad + c;
-    eb[o] = beta[o]; ev[o] = T.tv[o]; eg[o] = grad[o];
+  double d1 = 0.0, d2 = 0.0;
+  if (done) {
+    double* eb = dir < 0 ? T.mb : T.pb;
+    double* ev = dir < 0 ? T.mv : T.pv;
+    double* eg = dir < 0 ? T.mg : T.pg;
+    for (long long q = ly; q < M; q += LY) {
+      long long o = q * Cpad + c;
+      eb[o] = beta[o]; ev[o] = T.tv[o]; eg[o] = grad[o];
+    }
+    uturn_part(T.mb, T.mv, T.pb, T.pv, c, M, Cpad, ly, d1, d2);
   }
-  (dir < 0 ? T.ml : T.pl)[c] = ll;
-  double ntot = T.ntot[c];
+  ysum2(d1, d2, sh);
+  if (!done) return;
   if (s2) {
     double r = rng_uniform(rng, step, c, C, ucount++);
     if (r < n2 / ntot) {   // state = state1
-      copy_vec(T.sb, T.csb, c, M, Cpad);
-      copy_vec(T.sg, T.csg, c, M, Cpad);
-      T.sl[c] = T.csl[c];
-      T.moved[c] = 1;
+      copy_vec(T.sb, T.csb, c, M, Cpad, ly);
+      copy_vec(T.sg, T.csg, c, M, Cpad, ly);
+      if (ly == 0) { T.sl[c] = csl; T.moved[c] = 1; }
     }
   }
+  if (ly != 0) return;
+  (dir < 0 ? T.ml : T.pl)[c] = ll;
   T.ntot[c] = ntot + n2;
   T.j[c] = j + 1;
   T.alast[c] = a2;
   T.nalast[c] = na2;
   T.ucount[c] = ucount;
-  bool s = s2 && !uturn_dev(T.mb, T.mv, T.pb, T.pv, c, M, Cpad);
+  nleap[c] += 1ull;
+  bool s = s2 && !(d1 < 0.0 || d2 < 0.0);
   if (s && j + 1 < kMaxDepth) {
     T.newdbl[c] = 1;
     atomicAdd(T.n_active, 1);
@@ -703,10 +832,18 @@ __global__ void k_nuts_post(RngSrc rng, long long step, long long C, long long M
 }
 
 // dual averaging of epsilon (:294-302), addToRes! (:305), misc (:307-308), state0 = state (:310)
-__global__ void k_nuts_end(long long step, long long C, long long M, long long Cpad, double* b0, double* g0, double* l0,
-                           Nuts T, Recorder R, double* eps_out, double* jmax_out) {
-  long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+__global__ void __launch_bounds__(CXB * LY) k_nuts_end(long long step, long long C, long long M, long long Cpad, double* b0,
+                                                     double* g0, double* l0, Nuts T, Recorder R, double* eps_out,
+                                                     double* jmax_out) {
+  const Ln L = lanes(C);
+  const long long c = L.c;
+  if (!L.in) return;
+  const int ly = L.ly;
+  copy_vec(b0, T.sb, c, M, Cpad, ly);
+  copy_vec(g0, T.sg, c, M, Cpad, ly);
+  const double sl = T.sl[c];
+  record(R, step, c, M, Cpad, b0, sl, T.moved[c] != 0, ly);
+  if (ly != 0) return;
   const double delta = 0.7, gam = 0.05, kappa = 0.75, t0 = 10.0;
   const long long nadapt = 1000;
   double i1 = (double)(step + 1);
@@ -723,10 +860,7 @@ __global__ void k_nuts_end(long long step, long long C, long long M, long long C
     eps = exp(T.lebar[c]);
   }
   T.eps[c] = eps;
-  copy_vec(b0, T.sb, c, M, Cpad);
-  copy_vec(g0, T.sg, c, M, Cpad);
-  l0[c] = T.sl[c];
-  record(R, step, c, M, Cpad, b0, l0[c], T.moved[c] != 0);
+  l0[c] = sl;
   if (eps_out) eps_out[step * Cpad + c] = eps;
   if (jmax_out) jmax_out[step * Cpad + c] = (double)T.j[c];
 }
@@ -766,17 +900,17 @@ extern "C" int smc_nuts_run(smc_model_t m, const smc_sampler_config* cfg, const 
   SMC_CUDA(cudaMallocHost(&h_active, sizeof(int)));
   int rc = SMC_OK;
   for (long long i = 0; i < cfg->steps && rc == SMC_OK; i++) {
-    k_nuts_begin<<<gridc(C), 128, 0, st>>>(r.rng, i, C, M, Cpad, r.b0, r.g0, r.l0, T);
+    k_nuts_begin<<<lgrid(C), lblock(), 0, st>>>(r.rng, i, C, M, Cpad, r.b0, r.g0, r.l0, T);
     m->ctx->launches++;
     int rounds = 0;
     while (true) {
       cudaMemsetAsync(T.n_active, 0, sizeof(int), st);
-      k_nuts_pre<<<gridc(C), 128, 0, st>>>(r.rng, i, C, M, Cpad, m->beta, m->grad, m->logp, T);
+      k_nuts_pre<<<lgrid(C), lblock(), 0, st>>>(r.rng, i, C, M, Cpad, m->beta, m->grad, m->logp, T);
       m->ctx->launches++;
       rc = smc_model_eval_device(m, C, true);
       if (rc != SMC_OK) break;
       evals++;
-      k_nuts_post<<<gridc(C), 128, 0, st>>>(r.rng, i, C, M, Cpad, m->beta, m->grad, m->logp, T, r.nleap);
+      k_nuts_post<<<lgrid(C), lblock(), 0, st>>>(r.rng, i, C, M, Cpad, m->beta, m->grad, m->logp, T, r.nleap);
       m->ctx->launches++;
       cudaMemcpyAsync(h_active, T.n_active, sizeof(int), cudaMemcpyDeviceToHost, st);
       cudaError_t e = cudaStreamSynchronize(st);
@@ -785,7 +919,7 @@ extern "C" int smc_nuts_run(smc_model_t m, const smc_sampler_config* cfg, const 
       if (*h_active == 0 || rounds >= (1 << kMaxDepth)) break;
     }
     if (rc != SMC_OK) break;
-    k_nuts_end<<<gridc(C), 128, 0, st>>>(i, C, M, Cpad, r.b0, r.g0, r.l0, T, r.R, eps_dev, jmax_dev);
+    k_nuts_end<<<lgrid(C), lblock(), 0, st>>>(i, C, M, Cpad, r.b0, r.g0, r.l0, T, r.R, eps_dev, jmax_dev);
     m->ctx->launches++;
   }
   cudaFreeHost(h_active);

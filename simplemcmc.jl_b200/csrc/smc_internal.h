@@ -92,7 +92,8 @@ struct SmcProgram {  // one SMC_OP_FUSED register program
   std::vector<uint32_t> desc_regs;  // tape register of every array descriptor (loads and stores)
   std::vector<uint32_t> scal_regs;  // tape register of every per-chain scalar input (staged once per block)
   int n_loc = 0;
-  // device tables (built at finalize): VmUop[n_uops] | VmDesc[n_descs] | VmDesc[n_scal]
+  int n_ot = 0;   // operand-table entries (device form)
+  // device tables (built at finalize, vm_exec.cu): micro-ops | operand table | scalar input descriptors
   void* dev_tables = nullptr;
   size_t dev_tables_bytes = 0;
 };

@@ -21,11 +21,29 @@ namespace {
 
 constexpr int NT = 256;  // threads per block
 
+// device forms (built by smc_vm_prepare from the plan)
+struct VmDevUop {   // 16 bytes
+  uint8_t op, dist, darg, flags;
+  uint8_t o[4];     // operand-table entries of the sources 0..2 and of the accumulate operand
+  uint8_t dst, store, red, pad0;   // operand-table entries of the local / array destinations, reduction slot
+  uint32_t pad1;
+};
+struct VmDevOpd {   // 32 bytes: one distinct operand of the program
+  int kind, idx;    // VM_LOCAL: slot; VM_SCAL: scalar slot; VM_ARRAY: p / se / sc
+  const double* p;
+  long long se, sc;
+};
+struct VmOt {       // operand table entry resolved for this block (shared memory):
+  const double* base;   //   address of element v of a thread's pass = base + tid*A + cx*B + eb*Cc + v*S
+  int A, B;
+  long long Cc, S;
+};
+
 struct VmArgs {
-  const VmUop* uops;
-  const VmDesc* descs;
+  const VmDevUop* uops;
+  const VmDevOpd* ot;
   const VmDesc* scal;
-  int n_uops, n_descs, n_scal, n_loc, n_red, tcc, S, direct;
+  int n_uops, n_ot, n_scal, n_loc, n_red, tcc, S, direct, V;
   long long n, C, chunk;
   int* bad;
   double* partial;  // [n_red][S][C]
@@ -33,31 +51,73 @@ struct VmArgs {
   int racc[SMC_PROG_MAX_REDUCE];
 };
 
-// the heavy operations (densities, their adjoints, pow, trigonometry, ...) are called, not inlined V times
+// the heavy operations (densities, their adjoints, pow, trigonometry, ...) are called, not inlined
 __device__ __noinline__ double vm_apply_slow(int op, int dist, int k, double a, double b, double c) {
   return smc_apply(op, dist, k, a, b, c);
 }
 
-template <int V>
+// One pass of a micro-op over the vc elements a thread owns (element v at pointer + v * stride).  Operands are read
+// four elements at a time before anything is written, so destination / source slots may coincide and the loads of a
+// batch are independent of each other.
+#define VM_BODY(EXPR)                                                                                   \
+  {                                                                                                     \
+    int v = 0;                                                                                          \
+    if (fl == VMF_WRITE) {                                                                              \
+      for (; v + 4 <= vc; v += 4) {                                                                     \
+        const double p_0 = p0[(v + 0) * s0], p_1 = p0[(v + 1) * s0], p_2 = p0[(v + 2) * s0], p_3 = p0[(v + 3) * s0]; \
+        const double q_0 = p1[(v + 0) * s1], q_1 = p1[(v + 1) * s1], q_2 = p1[(v + 2) * s1], q_3 = p1[(v + 3) * s1]; \
+        double r_0, r_1, r_2, r_3;                                                                      \
+        { const double p = p_0, q = q_0; (void)p; (void)q; r_0 = (EXPR); }                                       \
+        { const double p = p_1, q = q_1; (void)p; (void)q; r_1 = (EXPR); }                                       \
+        { const double p = p_2, q = q_2; (void)p; (void)q; r_2 = (EXPR); }                                       \
+        { const double p = p_3, q = q_3; (void)p; (void)q; r_3 = (EXPR); }                                       \
+        pd[(v + 0) * NT] = r_0; pd[(v + 1) * NT] = r_1; pd[(v + 2) * NT] = r_2; pd[(v + 3) * NT] = r_3; \
+      }                                                                                                 \
+      for (; v < vc; v++) {                                                                             \
+        const double p = p0[v * s0], q = p1[v * s1];                                                    \
+        (void)p; (void)q;                                                                               \
+        pd[v * NT] = (EXPR);                                                                            \
+      }                                                                                                 \
+    } else {                                                                                            \
+      double rsum = 0.0;                                                                                \
+      for (; v < vc; v++) {                                                                             \
+        const double p = p0[v * s0], q = p1[v * s1];                                                    \
+        (void)p; (void)q;                                                                               \
+        double r = (EXPR);                                                                              \
+        if (fl & VMF_ACC) r = pa[v * sa] + r;                                                           \
+        if (fl & VMF_WRITE) pd[v * NT] = r;                                                             \
+        if (fl & VMF_STORE) ps[v * ss] = r;                                                             \
+        rsum += r;                                                                                      \
+      }                                                                                                 \
+      if (fl & VMF_REDUCE) Rd[uo.red * NT + tid] += rsum;                                               \
+    }                                                                                                   \
+  }                                                                                                     \
+  break;
+
 __global__ void __launch_bounds__(NT) k_vm(VmArgs a) {
   extern __shared__ __align__(16) unsigned char vsm[];
-  VmUop* U = (VmUop*)vsm;
-  VmDesc* D = (VmDesc*)(U + a.n_uops);
-  double* Sc = (double*)(D + a.n_descs);   // [n_scal][tcc]
-  double* Lc = Sc + a.n_scal * a.tcc;      // [n_loc][V][NT]
-  double* Rd = Lc + (size_t)a.n_loc * V * NT;  // [n_red][NT]
-  const int tid = threadIdx.x;
-  {
-    const uint4* src = (const uint4*)a.uops;   // uops and descs are contiguous in the device table
-    uint4* dst = (uint4*)vsm;
-    const int words = (a.n_uops + a.n_descs) * 2;
-    for (int i = tid; i < words; i += NT) dst[i] = src[i];
-  }
+  VmDevUop* U = (VmDevUop*)vsm;                                   // [n_uops]
+  VmOt* OT = (VmOt*)(vsm + (size_t)((a.n_uops + 1) & ~1) * 16);   // [n_ot]
+  double* Sc = (double*)(OT + a.n_ot);                            // [max(1, n_scal)][tcc]
+  double* Lc = Sc + (size_t)max(1, a.n_scal) * a.tcc;             // [n_loc][V][NT]
+  double* Rd = Lc + (size_t)a.n_loc * a.V * NT;                   // [n_red][NT]
+  const int tid = threadIdx.x, V = a.V;
   const int tcc = a.tcc, eyn = NT / tcc;
   const int cx = tid % tcc, ey = tid / tcc;
   const long long cbase = (long long)blockIdx.x * tcc;
   const long long c = cbase + cx;
   const bool active = c < a.C;
+  for (int i = tid; i < a.n_uops * 4; i += NT) ((uint32_t*)U)[i] = ((const uint32_t*)a.uops)[i];
+  for (int i = tid; i < a.n_ot; i += NT) {
+    const VmDevOpd d = a.ot[i];
+    VmOt t;
+    t.base = Sc; t.A = 0; t.B = 0; t.Cc = 0; t.S = 0;
+    if (d.kind == VM_LOCAL) { t.base = Lc + (size_t)d.idx * V * NT; t.A = 1; t.S = NT; }
+    else if (d.kind == VM_SCAL) { t.base = Sc + (size_t)d.idx * tcc; t.B = 1; }
+    else if (d.kind == VM_ARRAY) { t.base = d.p + cbase * d.sc; t.B = (int)d.sc; t.Cc = d.se; t.S = (long long)eyn * d.se; }
+    OT[i] = t;
+  }
+  if (tid == 0 && a.n_scal == 0) Sc[0] = 0.0;
   for (int i = tid; i < a.n_scal * tcc; i += NT) {
     const int k = i / tcc, cl = i - k * tcc;
     const VmDesc d = a.scal[k];
@@ -70,94 +130,60 @@ __global__ void __launch_bounds__(NT) k_vm(VmArgs a) {
   if (active) {
     const long long e0 = (long long)blockIdx.y * a.chunk, e1 = min(a.n, e0 + a.chunk);
     for (long long eb = e0 + ey; eb < e1; eb += (long long)eyn * V) {
-      long long ev[V];
-      bool ok[V];
-#pragma unroll
-      for (int v = 0; v < V; v++) {
-        long long e = eb + (long long)v * eyn;
-        ok[v] = e < e1;
-        ev[v] = ok[v] ? e : e1 - 1;   // tail lanes recompute the last element; their side effects are masked
-      }
-      auto fetch = [&](int mode, int idx, double (&x)[V]) {
-        if (mode == VM_LOCAL) {
-          const double* p = Lc + (size_t)idx * V * NT + tid;
-#pragma unroll
-          for (int v = 0; v < V; v++) x[v] = p[v * NT];
-        } else if (mode == VM_SCAL) {
-          const double t = Sc[idx * tcc + cx];
-#pragma unroll
-          for (int v = 0; v < V; v++) x[v] = t;
-        } else if (mode == VM_ARRAY) {
-          const VmDesc d = D[idx];
-          const double* p = d.p + c * d.sc;
-#pragma unroll
-          for (int v = 0; v < V; v++) x[v] = __ldg(p + ev[v] * d.se);
-        } else {
-#pragma unroll
-          for (int v = 0; v < V; v++) x[v] = 0.0;
-        }
-      };
+      const int vc = (int)min((long long)V, (e1 - eb + eyn - 1) / eyn);   // elements eb + v*eyn, v < vc
       for (int u = 0; u < a.n_uops; u++) {
-        const VmUop uo = U[u];
-        double x0[V], x1[V], r[V];
-        fetch(uo.mode[0], uo.idx[0], x0);
-        fetch(uo.mode[1], uo.idx[1], x1);
-#define VM_EACH(expr)                        \
-  _Pragma("unroll") for (int v = 0; v < V; v++) { \
-    const double p = x0[v], q = x1[v];       \
-    (void)q;                                 \
-    r[v] = (expr);                           \
-  }                                          \
-  break;
+        const VmDevUop uo = U[u];
+        const int fl = uo.flags;
+        const double *p0, *p1, *pa;
+        double *pd, *ps;
+        long long s0, s1, sa, ss;
+        {
+          const VmOt t = OT[uo.o[0]];
+          p0 = t.base + (tid * t.A + cx * t.B) + eb * t.Cc; s0 = t.S;
+        }
+        {
+          const VmOt t = OT[uo.o[1]];
+          p1 = t.base + (tid * t.A + cx * t.B) + eb * t.Cc; s1 = t.S;
+        }
+        {
+          const VmOt t = OT[uo.o[3]];
+          pa = t.base + (tid * t.A + cx * t.B) + eb * t.Cc; sa = t.S;
+        }
+        pd = const_cast<double*>(OT[uo.dst].base) + tid;
+        {
+          const VmOt t = OT[uo.store];
+          ps = const_cast<double*>(t.base) + (tid * t.A + cx * t.B) + eb * t.Cc; ss = t.S;
+        }
         switch (uo.op) {
-          case SMC_OP_COPY: VM_EACH(p)
-          case SMC_OP_NEG: VM_EACH(-p)
-          case SMC_OP_ADD: VM_EACH(p + q)
-          case SMC_OP_SUB: VM_EACH(p - q)
-          case SMC_OP_MUL: VM_EACH(p * q)
-          case SMC_OP_DIV: VM_EACH(p / q)
-          case SMC_OP_EXP: VM_EACH(exp(p))
-          case SMC_OP_LOG: VM_EACH(log(p))
-          case SMC_OP_ZERO: VM_EACH(0.0)
+          case SMC_OP_COPY: VM_BODY(p)
+          case SMC_OP_NEG: VM_BODY(-p)
+          case SMC_OP_ADD: VM_BODY(p + q)
+          case SMC_OP_SUB: VM_BODY(p - q)
+          case SMC_OP_MUL: VM_BODY(p * q)
+          case SMC_OP_DIV: VM_BODY(p / q)
+          case SMC_OP_EXP: VM_BODY(exp(p))
+          case SMC_OP_LOG: VM_BODY(log(p))
+          case SMC_OP_ZERO: VM_BODY(0.0)
           default: {
-            double x2[V];
-            fetch(uo.mode[2], uo.idx[2], x2);
-#pragma unroll
-            for (int v = 0; v < V; v++) {
-              double t = vm_apply_slow(uo.op, uo.dist, uo.darg, x0[v], x1[v], x2[v]);
-              if (uo.op == SMC_OP_LOGPDF && (t == -INFINITY || isnan(t))) {   // "give up eval", src/distribs.jl:69-70
-                if (ok[v]) a.bad[c] = 1;
-                t = 0.0;
+            const VmOt t = OT[uo.o[2]];
+            const double* p2 = t.base + (tid * t.A + cx * t.B) + eb * t.Cc;
+            const long long s2 = t.S;
+            double rsum = 0.0;
+            bool gaveup = false;
+            for (int v = 0; v < vc; v++) {
+              double r = vm_apply_slow(uo.op, uo.dist, uo.darg, p0[v * s0], p1[v * s1], p2[v * s2]);
+              if (uo.op == SMC_OP_LOGPDF && (r == -INFINITY || isnan(r))) {   // "give up eval", src/distribs.jl:69-70
+                gaveup = true;
+                r = 0.0;
               }
-              r[v] = t;
+              if (fl & VMF_ACC) r = pa[v * sa] + r;
+              if (fl & VMF_WRITE) pd[v * NT] = r;
+              if (fl & VMF_STORE) ps[v * ss] = r;
+              rsum += r;
             }
+            if (gaveup) a.bad[c] = 1;
+            if (fl & VMF_REDUCE) Rd[uo.red * NT + tid] += rsum;
           }
-        }
-#undef VM_EACH
-        if (uo.flags & VMF_ACC) {
-          double xa[V];
-          fetch(uo.mode[3], uo.idx[3], xa);
-#pragma unroll
-          for (int v = 0; v < V; v++) r[v] = xa[v] + r[v];
-        }
-        if (uo.flags & VMF_WRITE) {
-          double* p = Lc + (size_t)uo.dst * V * NT + tid;
-#pragma unroll
-          for (int v = 0; v < V; v++) p[v * NT] = r[v];
-        }
-        if (uo.flags & VMF_STORE) {
-          const VmDesc d = D[uo.store];
-          double* p = const_cast<double*>(d.p) + c * d.sc;
-#pragma unroll
-          for (int v = 0; v < V; v++)
-            if (ok[v]) p[ev[v] * d.se] = r[v];
-        }
-        if (uo.flags & VMF_REDUCE) {
-          double t = Rd[uo.red * NT + tid];
-#pragma unroll
-          for (int v = 0; v < V; v++)
-            if (ok[v]) t += r[v];
-          Rd[uo.red * NT + tid] = t;
         }
       }
     }
@@ -182,6 +208,7 @@ __global__ void __launch_bounds__(NT) k_vm(VmArgs a) {
     }
   }
 }
+#undef VM_BODY
 
 struct VmFinalArgs {
   const double* partial;
@@ -346,17 +373,49 @@ static VmDesc desc_of(const smc_model_s* m, uint32_t reg) {
   return d;
 }
 
+// device tables: VmDevUop[n_uops (padded to even)] | VmDevOpd[n_ot] | VmDesc[n_scal]
 int smc_vm_prepare(smc_model_s* m, SmcProgram& pr) {
-  const size_t nu = pr.uops.size(), nd = pr.desc_regs.size(), ns = pr.scal_regs.size();
-  const size_t bytes = nu * sizeof(VmUop) + (nd + ns) * sizeof(VmDesc);
-  std::vector<unsigned char> host(std::max<size_t>(bytes, 32));
-  if (nu) memcpy(host.data(), pr.uops.data(), nu * sizeof(VmUop));
-  VmDesc* D = (VmDesc*)(host.data() + nu * sizeof(VmUop));
-  for (size_t i = 0; i < nd; i++) {
-    D[i] = desc_of(m, pr.desc_regs[i]);
-    if (!D[i].p) { smc_set_error("program: an immediate is used as an array operand"); return SMC_ERR_INVALID; }
+  const size_t nu = pr.uops.size(), ns = pr.scal_regs.size();
+  std::vector<VmDevOpd> ot(1);
+  memset(&ot[0], 0, sizeof(VmDevOpd));   // entry 0: "no operand" (reads a valid dummy)
+  auto entry = [&](int kind, int idx) -> int {
+    if (kind == VM_NONE) return 0;
+    for (size_t i = 1; i < ot.size(); i++)
+      if (ot[i].kind == kind && ot[i].idx == idx) return (int)i;
+    VmDevOpd d;
+    memset(&d, 0, sizeof(d));
+    d.kind = kind; d.idx = idx;
+    if (kind == VM_ARRAY) {
+      VmDesc a = desc_of(m, pr.desc_regs[idx]);
+      d.p = a.p; d.se = a.se; d.sc = a.sc;
+    }
+    ot.push_back(d);
+    return (int)ot.size() - 1;
+  };
+  std::vector<VmDevUop> du(nu);
+  for (size_t i = 0; i < nu; i++) {
+    const VmUop& u = pr.uops[i];
+    VmDevUop d;
+    memset(&d, 0, sizeof(d));
+    d.op = u.op; d.dist = u.dist; d.darg = u.darg; d.flags = u.flags;
+    for (int k = 0; k < 4; k++) {
+      if (u.mode[k] == VM_ARRAY && !desc_of(m, pr.desc_regs[u.idx[k]]).p) { smc_set_error("program: an immediate is used as an array operand"); return SMC_ERR_INVALID; }
+      d.o[k] = (uint8_t)entry(u.mode[k], u.idx[k]);
+    }
+    d.dst = (uint8_t)((u.flags & VMF_WRITE) ? entry(VM_LOCAL, u.dst) : 0);
+    d.store = (uint8_t)((u.flags & VMF_STORE) ? entry(VM_ARRAY, u.store) : 0);
+    d.red = (uint8_t)u.red;
+    du[i] = d;
+    if (ot.size() > 255) { smc_set_error("program: more than 255 distinct operands"); return SMC_ERR_INVALID; }
   }
-  for (size_t i = 0; i < ns; i++) D[nd + i] = desc_of(m, pr.scal_regs[i]);
+  pr.n_ot = (int)ot.size();
+  const size_t nu2 = (nu + 1) & ~(size_t)1;
+  const size_t bytes = nu2 * sizeof(VmDevUop) + ot.size() * sizeof(VmDevOpd) + ns * sizeof(VmDesc);
+  std::vector<unsigned char> host(std::max<size_t>(bytes, 32), 0);
+  if (nu) memcpy(host.data(), du.data(), nu * sizeof(VmDevUop));
+  memcpy(host.data() + nu2 * sizeof(VmDevUop), ot.data(), ot.size() * sizeof(VmDevOpd));
+  VmDesc* D = (VmDesc*)(host.data() + nu2 * sizeof(VmDevUop) + ot.size() * sizeof(VmDevOpd));
+  for (size_t i = 0; i < ns; i++) D[i] = desc_of(m, pr.scal_regs[i]);
   if (!pr.dev_tables || pr.dev_tables_bytes < host.size()) {
     if (pr.dev_tables) cudaFree(pr.dev_tables);
     pr.dev_tables = nullptr;
@@ -371,45 +430,47 @@ int smc_vm_prepare(smc_model_s* m, SmcProgram& pr) {
 int smc_vm_launch(smc_model_s* m, SmcProgram& pr, int64_t C, int* bad) {
   cudaStream_t st = m->ctx->stream;
   static bool attr_done = false;
+  const size_t smem_max = 200 * 1024;
   if (!attr_done) {
-    SMC_CUDA(cudaFuncSetAttribute(k_vm<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    SMC_CUDA(cudaFuncSetAttribute(k_vm<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    SMC_CUDA(cudaFuncSetAttribute(k_vm<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    SMC_CUDA(cudaFuncSetAttribute(k_vm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
     attr_done = true;
   }
   VmArgs a;
   memset(&a, 0, sizeof(a));
-  const size_t nu = pr.uops.size(), nd = pr.desc_regs.size(), ns = pr.scal_regs.size();
-  a.uops = (const VmUop*)pr.dev_tables;
-  a.descs = (const VmDesc*)((const unsigned char*)pr.dev_tables + nu * sizeof(VmUop));
-  a.scal = a.descs + nd;
-  a.n_uops = (int)nu; a.n_descs = (int)nd; a.n_scal = (int)ns; a.n_loc = pr.n_loc; a.n_red = (int)pr.h.n_red;
+  const size_t nu = pr.uops.size(), ns = pr.scal_regs.size();
+  const size_t nu2 = (nu + 1) & ~(size_t)1;
+  a.uops = (const VmDevUop*)pr.dev_tables;
+  a.ot = (const VmDevOpd*)((const unsigned char*)pr.dev_tables + nu2 * sizeof(VmDevUop));
+  a.scal = (const VmDesc*)(a.ot + pr.n_ot);
+  a.n_uops = (int)nu; a.n_ot = pr.n_ot; a.n_scal = (int)ns; a.n_loc = pr.n_loc; a.n_red = (int)pr.h.n_red;
   a.n = pr.h.n; a.C = C; a.bad = bad;
   int tcc = 1;
   while (tcc < C && tcc < (a.n == 1 ? NT : 32)) tcc <<= 1;
   a.tcc = tcc;
   const int eyn = NT / tcc;
-  int V = 1;
-  const size_t loc_budget = 64 * 1024;
-  if (a.n >= (long long)eyn * 4 && (size_t)pr.n_loc * 4 * NT * 8 <= loc_budget) V = 4;
-  else if (a.n >= (long long)eyn * 2 && (size_t)pr.n_loc * 2 * NT * 8 <= loc_budget) V = 2;
   const long long chain_tiles = (C + tcc - 1) / tcc;
-  const long long per_pass = (long long)eyn * V;
+  // element chunks: two blocks per SM when the index space allows, at least 4 elements per thread
   long long S = std::max<long long>(1, std::min<long long>((2LL * m->ctx->sm_count + chain_tiles - 1) / chain_tiles,
-                                                           (a.n + per_pass * 2 - 1) / (per_pass * 2)));
+                                                           (a.n + (long long)eyn * 4 - 1) / ((long long)eyn * 4)));
   a.chunk = (a.n + S - 1) / S;
   S = (a.n + a.chunk - 1) / a.chunk;
   a.S = (int)S;
+  // V = elements a thread processes per decode of a micro-op: as many as the locals' shared-memory budget allows
+  const long long per_thread = (a.chunk + eyn - 1) / eyn;
+  const size_t fixed = nu2 * 16 + (size_t)pr.n_ot * 32 + std::max<size_t>(1, ns) * tcc * 8 + (size_t)a.n_red * NT * 8;
+  const size_t budget = 96 * 1024;
+  long long vmax = pr.n_loc > 0 ? (long long)((budget > fixed ? budget - fixed : 0) / ((size_t)pr.n_loc * NT * 8)) : 32;
+  vmax = std::max<long long>(1, std::min<long long>(vmax, 32));
+  long long passes = (per_thread + vmax - 1) / vmax;
+  a.V = (int)std::max<long long>(1, (per_thread + passes - 1) / passes);
   a.direct = (S == 1) ? 1 : 0;
   for (int k = 0; k < a.n_red; k++) { a.rd[k] = smc_make_dst(m, pr.red[k].reg); a.racc[k] = (int)pr.red[k].acc; }
   if (a.n_red > 0 && !a.direct) SMC_TRY(smc_scratch_reserve(m, (int64_t)a.n_red * S * C));
   a.partial = m->scratch;
-  const size_t smem = (nu + nd) * 32 + (size_t)ns * tcc * 8 + (size_t)pr.n_loc * V * NT * 8 + (size_t)a.n_red * NT * 8;
-  if (smem > 200 * 1024) { smc_set_error("program needs %zu bytes of shared memory", smem); return SMC_ERR_MEMORY; }
+  const size_t smem = fixed + (size_t)pr.n_loc * a.V * NT * 8;
+  if (smem > smem_max) { smc_set_error("program needs %zu bytes of shared memory", smem); return SMC_ERR_MEMORY; }
   dim3 grid((unsigned)chain_tiles, (unsigned)S);
-  if (V == 4) k_vm<4><<<grid, NT, smem, st>>>(a);
-  else if (V == 2) k_vm<2><<<grid, NT, smem, st>>>(a);
-  else k_vm<1><<<grid, NT, smem, st>>>(a);
+  k_vm<<<grid, NT, smem, st>>>(a);
   m->ctx->launches++;
   if (a.n_red > 0 && !a.direct) {
     VmFinalArgs f;

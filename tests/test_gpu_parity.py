@@ -75,6 +75,31 @@ def test_logistic_cfg3_shapes(smc, fuse, N, M):
         _check(lp[c], g[c], *ref(betas[c]))
 
 
+@pytest.mark.parametrize("C", [1, 2, 3, 4])
+@pytest.mark.parametrize("N,M", [(1000, 10), (777, 3), (4099, 16), (515, 29)])
+def test_glm_few_chains_stream_path(smc, N, M, C):
+    """1-4 chains take the HBM-stream kernel (column-major X, thread per row) for M <= 16 (one chain: M <= 32); both
+    families, both link signs, plus the same model evaluated with 19 chains (DMMA kernel) must agree with each other"""
+    from simplemcmc_jl_b200 import api
+    X, Y, _ = logistic_data(N, M)
+    Xl, Yl, _ = linear_data(N, M)
+    rng = np.random.default_rng(N + C)
+    betas = 0.2 * rng.standard_normal((C, M))
+    neg = LOGISTIC.replace("exp(X * vars)", "exp(-(X * vars))")
+    for model, data, par in ((LOGISTIC, dict(X=X, Y=Y), "vars"), (neg, dict(X=X, Y=Y), "vars"),
+                             (LINEAR, dict(X=Xl, Y=Yl), "beta")):
+        ref = generate_model_function(model, data=data, gradient=True, **{par: np.zeros(M)})
+        low, dev = api._build(model, [(par, np.zeros(M))], data, True, C, 0, "assign")
+        assert low.n_fused == 1
+        lp, g = dev.eval(betas)
+        for c in range(C):
+            _check(lp[c], g[c], *ref(betas[c]))
+        low2, dev2 = api._build(model, [(par, np.zeros(M))], data, True, 19, 0, "assign")
+        lp19, g19 = dev2.eval(np.vstack([betas, np.zeros((19 - C, M))]))
+        assert np.allclose(lp19[:C], lp, rtol=1e-13, atol=0) and relerr(g19[:C], g) <= 1e-12
+        dev.close(); dev2.close()
+
+
 def test_normal_glm_variants(smc):
     """the GLM matcher must keep signs straight for every way of writing the same likelihood"""
     X, Y, _ = linear_data(500, 6)

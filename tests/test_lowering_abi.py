@@ -119,6 +119,17 @@ def test_statement_fusion_of_the_ornstein_tape():
         assert not (pinned & written)
 
 
+def test_programs_pack_for_index_spaces_beyond_16_bits():
+    """cfg5 at T = 1e6: a program's index-space length lives in its header, not in a 16-bit instruction field"""
+    import struct
+    x = ou_data(100_000)
+    low = Lowering(ORNSTEIN, [("tau", 20.0), ("mu", 10.0), ("sigma", 0.1)], dict(x=x))
+    tape, bound = low.serialise()
+    assert any(pr.n == 99_999 for pr in low.programs)
+    blob = low.programs[[pr.n for pr in low.programs].index(99_999)].pack({v.vid: v.reg for v in low.vals if v.reg is not None})
+    assert struct.unpack("<4I", blob[:16])[3] == 99_999
+
+
 def test_reference_error_cases():
     with pytest.raises(ModelError):
         Lowering("sum(logpdfBernoulli(1, x))", [("x", np.array([0.0]))], {})

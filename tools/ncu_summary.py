@@ -75,5 +75,23 @@ def full(path, out):
         print(it["kernel"], {k: v for k, v in it.items() if k in ("gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "launch__registers_per_thread")})
 
 
+def traffic(path, out):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the captured kernel (one launch) -> the file bench.py reads for roofline.traffic"""
+    txt = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rd = list(csv.reader(io.StringIO(txt)))
+    hdr, units, row = rd[0], rd[1], rd[2]
+    d, u = dict(zip(hdr, row)), dict(zip(hdr, units))
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+
+    def val(k):
+        return float(d[k].replace(",", "")) * scale[u[k]]
+    res = {"kernel": d["Kernel Name"].split("(")[0], "dram_bytes_read": val("dram__bytes_read.sum"), "dram_bytes_write": val("dram__bytes_write.sum"),
+           "dram_bytes_per_launch": val("dram__bytes_read.sum") + val("dram__bytes_write.sum"),
+           "duration_ms_under_ncu": float(d["gpu__time_duration.sum"].replace(",", "")) * {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(u["gpu__time_duration.sum"], 1e-6),
+           "source": "ncu --set full --clock-control none, one launch: " + path}
+    json.dump(res, open(out, "w"), indent=1)
+    print(res)
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2], sys.argv[3])

@@ -282,16 +282,38 @@ __global__ void __launch_bounds__(NWC* NWR * 32, (MP8 <= 2 ? 2 : 1)) k_glm(GlmAr
   (void)bs;
 }
 
-// out[j][c] = sum_rs part[rs][j][c]  (j = MP row is L); a chain flagged bad gets L = -inf so that the flag
-// survives a cross-rank sum
-__global__ void k_glm_reduce(const double* part, int RS, int MP, long long C, long long Cpad, const int* bad, double* out) {
+// Sum of the row-split partials in fixed order (deterministic), then either
+//   publish: write (L, G) straight into the tape registers (one kernel per GLM statement on a single rank), or
+//   stage:   out[j][c] = sum (j = MP row is L) for the NCCL all-reduce of row-sharded models; a chain flagged bad gets
+//            L = -inf there so that the flag survives the cross-rank sum.
+struct GlmPub {
+  double* Ldst;
+  double* Gdst;
+  int acc, on;
+};
+__device__ __forceinline__ void glm_emit(double t, long long j, long long c, int M, int MP, long long Cpad, int* bad, double* out,
+                                         const GlmPub& pub) {
+  if (pub.on) {
+    if (j == MP) {
+      if (bad[c] || !(t > -INFINITY)) { bad[c] = 1; t = 0.0; }
+      pub.Ldst[c] = pub.acc ? pub.Ldst[c] + t : t;
+    } else if (j < M) {
+      pub.Gdst[j * Cpad + c] = t;
+    }
+  } else {
+    if (j == MP && (bad[c] || !(t > -INFINITY))) t = -INFINITY;
+    out[j * Cpad + c] = t;
+  }
+}
+
+__global__ void k_glm_reduce(const double* part, int RS, int M, int MP, long long C, long long Cpad, int* bad, double* out, GlmPub pub) {
   long long total = (long long)(MP + 1) * C;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     long long j = i / C, c = i - j * C;
+    if (pub.on && j >= M && j < MP) continue;
     double t = 0.0;
     for (int r = 0; r < RS; r++) t += part[((long long)r * (MP + 1) + j) * Cpad + c];
-    if (j == MP && (bad[c] || !(t > -INFINITY))) t = -INFINITY;
-    out[j * Cpad + c] = t;
+    glm_emit(t, j, c, M, MP, Cpad, bad, out, pub);
   }
 }
 
@@ -419,8 +441,8 @@ __global__ void __launch_bounds__(256) k_glm_stream(GlmStreamArgs a) {
   }
 }
 
-// out[j][c] = sum_rs part[rs][j][c] with one warp per output: lanes stride the row splits, fixed shuffle tree
-__global__ void k_glm_reduce_warp(const double* part, int RS, int M, int MP, long long C, long long Cpad, const int* bad, double* out) {
+// the same with one warp per output (few chains, many row splits): lanes stride the row splits, fixed shuffle tree
+__global__ void k_glm_reduce_warp(const double* part, int RS, int M, int MP, long long C, long long Cpad, int* bad, double* out, GlmPub pub) {
   const int lane = threadIdx.x & 31;
   const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (w >= (long long)(M + 1) * C) return;
@@ -429,10 +451,7 @@ __global__ void k_glm_reduce_warp(const double* part, int RS, int M, int MP, lon
   double t = 0.0;
   for (int r = lane; r < RS; r += 32) t += part[((long long)r * (MP + 1) + j) * Cpad + c];
   for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-  if (lane == 0) {
-    if (j == MP && (bad[c] || !(t > -INFINITY))) t = -INFINITY;
-    out[j * Cpad + c] = t;
-  }
+  if (lane == 0) glm_emit(t, j, c, M, MP, Cpad, bad, out, pub);
 }
 
 template <int FAM, int MB>
@@ -621,17 +640,24 @@ int smc_glm_launch(smc_model_s* m, SmcGlmPlan& g, int64_t C) {
   }
   SMC_CUDA(cudaGetLastError());
   double* out = g.part + (int64_t)RS * (g.MP + 1) * m->Cpad;
-  long long tot = (long long)(g.MP + 1) * C;
-  if ((long long)(g.M + 1) * C <= 1024 && RS >= 16)
-    k_glm_reduce_warp<<<(unsigned)(((long long)(g.M + 1) * C * 32 + 255) / 256), 256, 0, st>>>(g.part, RS, g.M, g.MP, C, m->Cpad, m->bad, out);
-  else
-    k_glm_reduce<<<(unsigned)std::min<long long>((tot + 255) / 256, 148LL * 16), 256, 0, st>>>(g.part, RS, g.MP, C, m->Cpad, m->bad, out);
-  if (m->row_shard && m->ctx->nranks > 1) SMC_TRY(smc_comm_allreduce_device(m->ctx, out, (int64_t)(g.MP + 1) * m->Cpad));
   const SmcReg& Lr = m->regs[s.dst];
   const SmcReg& Gr = m->regs[s.aux2];
-  long long tot2 = (long long)(g.M + 1) * C;
-  k_glm_publish<<<(unsigned)std::min<long long>((tot2 + 255) / 256, 148LL * 16), 256, 0, st>>>(
-      out, g.M, g.MP, C, m->Cpad, m->bad, Lr.dev, Gr.dev, (s.flags & SMC_F_ACC) ? 1 : 0);
-  m->ctx->launches += 3;
+  const bool sharded = m->row_shard && m->ctx->nranks > 1;
+  GlmPub pub;
+  pub.Ldst = Lr.dev; pub.Gdst = Gr.dev; pub.acc = (s.flags & SMC_F_ACC) ? 1 : 0; pub.on = sharded ? 0 : 1;
+  long long tot = (long long)(g.MP + 1) * C;
+  if ((long long)(g.M + 1) * C <= 1024 && RS >= 16)
+    k_glm_reduce_warp<<<(unsigned)(((long long)(g.M + 1) * C * 32 + 255) / 256), 256, 0, st>>>(g.part, RS, g.M, g.MP, C, m->Cpad, m->bad, out, pub);
+  else
+    k_glm_reduce<<<(unsigned)std::min<long long>((tot + 255) / 256, 148LL * 16), 256, 0, st>>>(g.part, RS, g.M, g.MP, C, m->Cpad, m->bad, out, pub);
+  m->ctx->launches += 2;
+  if (sharded) {
+    // rows are split over ranks: sum the (L, G) block over the communicator, then publish
+    SMC_TRY(smc_comm_allreduce_device(m->ctx, out, (int64_t)(g.MP + 1) * m->Cpad));
+    long long tot2 = (long long)(g.M + 1) * C;
+    k_glm_publish<<<(unsigned)std::min<long long>((tot2 + 255) / 256, 148LL * 16), 256, 0, st>>>(
+        out, g.M, g.MP, C, m->Cpad, m->bad, Lr.dev, Gr.dev, pub.acc);
+    m->ctx->launches++;
+  }
   return SMC_OK;
 }

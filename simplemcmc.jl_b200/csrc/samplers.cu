@@ -896,32 +896,59 @@ extern "C" int smc_nuts_run(smc_model_t m, const smc_sampler_config* cfg, const 
   k_nuts_init<<<gridc(C), 128, 0, st>>>(C, T);
   m->ctx->launches++;
   int64_t evals = 1;
+  // Every round ends with "is any chain still building its tree?".  Waiting for that answer before issuing the next
+  // round leaves the GPU idle for a host round trip per leapfrog, so when the previous iteration's trees were long the
+  // next round is issued before the answer is known (one round in flight ahead): if the answer turns out to be "none",
+  // the extra round finds every chain inactive and changes nothing -- at most one wasted evaluation per iteration.
   int* h_active = nullptr;
-  SMC_CUDA(cudaMallocHost(&h_active, sizeof(int)));
+  SMC_CUDA(cudaMallocHost(&h_active, 2 * sizeof(int)));
+  cudaEvent_t ev[2];
+  SMC_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
+  SMC_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
   int rc = SMC_OK;
+  const int max_rounds = 1 << kMaxDepth;
+  int prev_rounds = 0;
   for (long long i = 0; i < cfg->steps && rc == SMC_OK; i++) {
     k_nuts_begin<<<lgrid(C), lblock(), 0, st>>>(r.rng, i, C, M, Cpad, r.b0, r.g0, r.l0, T);
     m->ctx->launches++;
-    int rounds = 0;
-    while (true) {
+    int launched = 0, rounds = 0;
+    auto launch_round = [&]() -> int {
+      const int slot = launched & 1;
       cudaMemsetAsync(T.n_active, 0, sizeof(int), st);
       k_nuts_pre<<<lgrid(C), lblock(), 0, st>>>(r.rng, i, C, M, Cpad, m->beta, m->grad, m->logp, T);
       m->ctx->launches++;
-      rc = smc_model_eval_device(m, C, true);
-      if (rc != SMC_OK) break;
+      int e = smc_model_eval_device(m, C, true);
+      if (e != SMC_OK) return e;
       evals++;
       k_nuts_post<<<lgrid(C), lblock(), 0, st>>>(r.rng, i, C, M, Cpad, m->beta, m->grad, m->logp, T, r.nleap);
       m->ctx->launches++;
-      cudaMemcpyAsync(h_active, T.n_active, sizeof(int), cudaMemcpyDeviceToHost, st);
-      cudaError_t e = cudaStreamSynchronize(st);
+      cudaMemcpyAsync(h_active + slot, T.n_active, sizeof(int), cudaMemcpyDeviceToHost, st);
+      cudaEventRecord(ev[slot], st);
+      launched++;
+      return SMC_OK;
+    };
+    const bool speculate = prev_rounds >= 16 && !cfg->inject_uniforms;
+    rc = launch_round();
+    while (rc == SMC_OK) {
+      const int slot = rounds & 1;
+      if (speculate && launched == rounds + 1 && launched < max_rounds) {
+        rc = launch_round();
+        if (rc != SMC_OK) break;
+      }
+      cudaError_t e = cudaEventSynchronize(ev[slot]);
       if (e != cudaSuccess) { smc_set_error("CUDA error '%s' in the NUTS loop", cudaGetErrorString(e)); rc = SMC_ERR_CUDA; break; }
       rounds++;
-      if (*h_active == 0 || rounds >= (1 << kMaxDepth)) break;
+      if (h_active[slot] == 0 || rounds >= max_rounds) break;
+      if (launched == rounds) rc = launch_round();
     }
     if (rc != SMC_OK) break;
+    prev_rounds = rounds;
     k_nuts_end<<<lgrid(C), lblock(), 0, st>>>(i, C, M, Cpad, r.b0, r.g0, r.l0, T, r.R, eps_dev, jmax_dev);
     m->ctx->launches++;
   }
+  cudaStreamSynchronize(st);
+  cudaEventDestroy(ev[0]);
+  cudaEventDestroy(ev[1]);
   cudaFreeHost(h_active);
   if (rc != SMC_OK) return rc;
   SMC_TRY(run_finish(r, evals));

@@ -414,12 +414,13 @@ __global__ void k_fill_int(int* p, long long n, int v) {
 }
 
 // logp[c] = bad ? -inf : result ; grad[:,c] = bad ? 0 : grad   (src/parsing.jl:465-467)
-__global__ void k_finish_eval(const double* result, long long rse, int rsc, const int* bad, double* logp, double* grad,
+__global__ void k_finish_eval(const double* result, long long rse, int rsc, int* bad, double* logp, double* grad,
                               long long M, long long C, long long Cpad, int with_grad) {
   long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  int b = bad[c];
   double r = result[c * rsc];
+  int b = bad[c] || !(r > -INFINITY);   // a -Inf / NaN total is a zero density as well ("give up eval")
+  bad[c] = 0;                           // flags are left clean for the next evaluation
   logp[c] = b ? -INFINITY : r;
   if (b && with_grad)
     for (long long j = 0; j < M; j++) grad[j * Cpad + c] = 0.0;
@@ -730,13 +731,16 @@ extern "C" int smc_model_finalize(smc_model_t m, int64_t max_chains, int row_sha
 // the launch sequence of one evaluation: every body statement of the tape, all chains in lockstep
 static int eval_body(smc_model_s* m, int64_t C, bool with_grad) {
   cudaStream_t st = m->ctx->stream;
-  k_fill_int<<<grid_for(C), 256, 0, st>>>(m->bad, C, 0);
-  m->ctx->launches++;
+  // (the "give up eval" flags m->bad are zero here: cleared at finalize and again by every k_finish_eval)
   const int n_fwd = (int)m->hdr.reserved[0];  // statements past this index only serve the gradient
   for (int si : m->body_stmts) {
     const smc_tape_stmt& s = m->stmts[si];
     if (!with_grad && (si >= n_fwd || m->regs[s.dst].d.kind == SMC_REG_GRAD)) continue;
-    SMC_TRY(run_statement(m, s, C, false));
+    int rc = run_statement(m, s, C, false);
+    if (rc != SMC_OK) {
+      cudaMemsetAsync(m->bad, 0, (size_t)m->Cpad * sizeof(int), st);
+      return rc;
+    }
   }
   const SmcReg& rr = m->regs[m->hdr.result_reg];
   Opd ro = smc_make_opd(m, m->hdr.result_reg);

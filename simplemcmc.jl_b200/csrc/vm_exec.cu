@@ -33,10 +33,11 @@ struct VmDevOpd {   // 32 bytes: one distinct operand of the program
   const double* p;
   long long se, sc;
 };
-struct VmOt {       // operand table entry resolved for this block (shared memory):
-  const double* base;   //   address of element v of a thread's pass = base + tid*A + cx*B + eb*Cc + v*S
-  int A, B;
+struct VmOt {       // operand table entry resolved for this block (kept in shared memory), 32 bytes
+  const double* gbase;  // tape array in HBM: element v of a thread's pass = gbase + (flags&2 ? cx : 0) + eb*Cc + v*S; else NULL
   long long Cc, S;
+  int off;              // shared-memory operand: index (doubles) = off + (flags&1 ? tid : 0) + (flags&2 ? cx : 0) + v*(flags&1 ? NT : 0)
+  int flags;
 };
 
 struct VmArgs {
@@ -56,33 +57,52 @@ __device__ __noinline__ double vm_apply_slow(int op, int dist, int k, double a, 
   return smc_apply(op, dist, k, a, b, c);
 }
 
-// One pass of a micro-op over the vc elements a thread owns (element v at pointer + v * stride).  Operands are read
-// four elements at a time before anything is written, so destination / source slots may coincide and the loads of a
-// batch are independent of each other.
-#define VM_BODY(EXPR)                                                                                   \
+// One pass of a micro-op over the vc elements a thread owns (element v at pointer + v * stride).  The two common
+// shapes -- result written to a local, result only reduced -- read the operands of four elements before anything is
+// written, so a destination slot may coincide with a source slot and the loads of a batch are independent.
+// EXPR sees p, q (and w when W3) = operands 0, 1, 2 of the element.  The macros are expanded twice: once where every
+// operand lives in shared memory (32-bit indices into the block's shared array: LDS / STS with cheap addressing),
+// once with generic 64-bit pointers (a tape array in HBM among the operands).
+#define VM_LOAD4(W3, EXPR)                                                                                       \
+  const double p_0 = p0[(v + 0) * s0], p_1 = p0[(v + 1) * s0], p_2 = p0[(v + 2) * s0], p_3 = p0[(v + 3) * s0];   \
+  const double q_0 = p1[(v + 0) * s1], q_1 = p1[(v + 1) * s1], q_2 = p1[(v + 2) * s1], q_3 = p1[(v + 3) * s1];   \
+  const double w_0 = W3 ? p2[(v + 0) * s2] : 0.0, w_1 = W3 ? p2[(v + 1) * s2] : 0.0,                             \
+               w_2 = W3 ? p2[(v + 2) * s2] : 0.0, w_3 = W3 ? p2[(v + 3) * s2] : 0.0;                             \
+  double r_0, r_1, r_2, r_3;                                                                                     \
+  { const double p = p_0, q = q_0, w = w_0; (void)p; (void)q; (void)w; r_0 = (EXPR); }                           \
+  { const double p = p_1, q = q_1, w = w_1; (void)p; (void)q; (void)w; r_1 = (EXPR); }                           \
+  { const double p = p_2, q = q_2, w = w_2; (void)p; (void)q; (void)w; r_2 = (EXPR); }                           \
+  { const double p = p_3, q = q_3, w = w_3; (void)p; (void)q; (void)w; r_3 = (EXPR); }
+#define VM_LOAD1(W3)                                                             \
+  const double p = p0[v * s0], q = p1[v * s1], w = W3 ? p2[v * s2] : 0.0;        \
+  (void)p; (void)q; (void)w;
+#define VM_RUN(W3, EXPR)                                                                                \
   {                                                                                                     \
     int v = 0;                                                                                          \
     if (fl == VMF_WRITE) {                                                                              \
       for (; v + 4 <= vc; v += 4) {                                                                     \
-        const double p_0 = p0[(v + 0) * s0], p_1 = p0[(v + 1) * s0], p_2 = p0[(v + 2) * s0], p_3 = p0[(v + 3) * s0]; \
-        const double q_0 = p1[(v + 0) * s1], q_1 = p1[(v + 1) * s1], q_2 = p1[(v + 2) * s1], q_3 = p1[(v + 3) * s1]; \
-        double r_0, r_1, r_2, r_3;                                                                      \
-        { const double p = p_0, q = q_0; (void)p; (void)q; r_0 = (EXPR); }                                       \
-        { const double p = p_1, q = q_1; (void)p; (void)q; r_1 = (EXPR); }                                       \
-        { const double p = p_2, q = q_2; (void)p; (void)q; r_2 = (EXPR); }                                       \
-        { const double p = p_3, q = q_3; (void)p; (void)q; r_3 = (EXPR); }                                       \
+        VM_LOAD4(W3, EXPR)                                                                              \
         pd[(v + 0) * NT] = r_0; pd[(v + 1) * NT] = r_1; pd[(v + 2) * NT] = r_2; pd[(v + 3) * NT] = r_3; \
       }                                                                                                 \
       for (; v < vc; v++) {                                                                             \
-        const double p = p0[v * s0], q = p1[v * s1];                                                    \
-        (void)p; (void)q;                                                                               \
+        VM_LOAD1(W3)                                                                                    \
         pd[v * NT] = (EXPR);                                                                            \
       }                                                                                                 \
+    } else if (fl == VMF_REDUCE) {                                                                      \
+      double rsum = 0.0;                                                                                \
+      for (; v + 4 <= vc; v += 4) {                                                                     \
+        VM_LOAD4(W3, EXPR)                                                                              \
+        rsum += r_0; rsum += r_1; rsum += r_2; rsum += r_3;                                             \
+      }                                                                                                 \
+      for (; v < vc; v++) {                                                                             \
+        VM_LOAD1(W3)                                                                                    \
+        rsum += (EXPR);                                                                                 \
+      }                                                                                                 \
+      Rd[uo.red * NT + tid] += rsum;                                                                    \
     } else {                                                                                            \
       double rsum = 0.0;                                                                                \
       for (; v < vc; v++) {                                                                             \
-        const double p = p0[v * s0], q = p1[v * s1];                                                    \
-        (void)p; (void)q;                                                                               \
+        VM_LOAD1(W3)                                                                                    \
         double r = (EXPR);                                                                              \
         if (fl & VMF_ACC) r = pa[v * sa] + r;                                                           \
         if (fl & VMF_WRITE) pd[v * NT] = r;                                                             \
@@ -91,15 +111,61 @@ __device__ __noinline__ double vm_apply_slow(int op, int dist, int k, double a, 
       }                                                                                                 \
       if (fl & VMF_REDUCE) Rd[uo.red * NT + tid] += rsum;                                               \
     }                                                                                                   \
-  }                                                                                                     \
-  break;
+  }
+
+// the operation table; p0/p1/p2 (sources), pd (local destination), pa (accumulate operand), ps (array destination) and
+// their strides are in scope
+#define VM_SWITCH                                                                                                   \
+  switch (uo.op) {                                                                                                  \
+    case SMC_OP_COPY: VM_RUN(0, p) break;                                                                           \
+    case SMC_OP_NEG: VM_RUN(0, -p) break;                                                                           \
+    case SMC_OP_ADD: VM_RUN(0, p + q) break;                                                                        \
+    case SMC_OP_SUB: VM_RUN(0, p - q) break;                                                                        \
+    case SMC_OP_MUL: VM_RUN(0, p * q) break;                                                                        \
+    case SMC_OP_DIV: VM_RUN(0, p / q) break;                                                                        \
+    case SMC_OP_EXP: VM_RUN(0, exp(p)) break;                                                                       \
+    case SMC_OP_LOG: VM_RUN(0, log(p)) break;                                                                       \
+    case SMC_OP_ZERO: VM_RUN(0, 0.0) break;                                                                         \
+    default: {                                                                                                      \
+      /* Normal density and its adjoints with one sigma for the whole pass (a per-chain scalar, the usual case): */ \
+      /* 1/sigma, 1/sigma^2 and log(sigma) are formed once per pass, the element loop is multiply-add only       */ \
+      /* (src/distribs.jl:23-28, src/diff.jl:94-99)                                                              */ \
+      if (uo.dist == SMC_DIST_NORMAL && s1 == 0 && (uo.op == SMC_OP_LOGPDF || uo.op == SMC_OP_DLOGPDF) && p1[0] > 0.0) { \
+        const double sg = p1[0], inv = 1.0 / sg, inv2 = 1.0 / (sg * sg);                                            \
+        const double lconst = -log(sg) - SMC_LOG_SQRT_2PI;                                                          \
+        if (uo.op == SMC_OP_LOGPDF) VM_RUN(1, fma(-0.5 * ((w - p) * inv), (w - p) * inv, lconst))                   \
+        else if (uo.darg == 0) VM_RUN(1, (w - p) * inv2)                                                            \
+        else if (uo.darg == 1) VM_RUN(1, ((w - p) * (w - p) * inv2 - 1.0) * inv)                                    \
+        else VM_RUN(1, (p - w) * inv2)                                                                              \
+        break;                                                                                                      \
+      }                                                                                                             \
+      double rsum = 0.0;                                                                                            \
+      bool gaveup = false;                                                                                          \
+      for (int v = 0; v < vc; v++) {                                                                                \
+        double r = vm_apply_slow(uo.op, uo.dist, uo.darg, p0[v * s0], p1[v * s1], p2[v * s2]);                      \
+        if (uo.op == SMC_OP_LOGPDF && (r == -INFINITY || isnan(r))) { /* "give up eval", src/distribs.jl:69-70 */   \
+          gaveup = true;                                                                                            \
+          r = 0.0;                                                                                                  \
+        }                                                                                                           \
+        if (fl & VMF_ACC) r = pa[v * sa] + r;                                                                       \
+        if (fl & VMF_WRITE) pd[v * NT] = r;                                                                         \
+        if (fl & VMF_STORE) ps[v * ss] = r;                                                                         \
+        rsum += r;                                                                                                  \
+      }                                                                                                             \
+      if (gaveup) a.bad[c] = 1;                                                                                     \
+      if (fl & VMF_REDUCE) Rd[uo.red * NT + tid] += rsum;                                                           \
+    }                                                                                                               \
+  }
 
 __global__ void __launch_bounds__(NT) k_vm(VmArgs a) {
-  extern __shared__ __align__(16) unsigned char vsm[];
+  extern __shared__ __align__(16) double vsmd[];
+  unsigned char* vsm = (unsigned char*)vsmd;
   VmDevUop* U = (VmDevUop*)vsm;                                   // [n_uops]
   VmOt* OT = (VmOt*)(vsm + (size_t)((a.n_uops + 1) & ~1) * 16);   // [n_ot]
-  double* Sc = (double*)(OT + a.n_ot);                            // [max(1, n_scal)][tcc]
-  double* Lc = Sc + (size_t)max(1, a.n_scal) * a.tcc;             // [n_loc][V][NT]
+  const int sc_off = (((a.n_uops + 1) & ~1) * 16 + a.n_ot * 32) / 8;   // (indices in doubles from vsmd)
+  const int lc_off = sc_off + max(1, a.n_scal) * a.tcc;
+  double* Sc = vsmd + sc_off;                                     // [max(1, n_scal)][tcc]
+  double* Lc = vsmd + lc_off;                                     // [n_loc][V][NT]
   double* Rd = Lc + (size_t)a.n_loc * a.V * NT;                   // [n_red][NT]
   const int tid = threadIdx.x, V = a.V;
   const int tcc = a.tcc, eyn = NT / tcc;
@@ -111,10 +177,10 @@ __global__ void __launch_bounds__(NT) k_vm(VmArgs a) {
   for (int i = tid; i < a.n_ot; i += NT) {
     const VmDevOpd d = a.ot[i];
     VmOt t;
-    t.base = Sc; t.A = 0; t.B = 0; t.Cc = 0; t.S = 0;
-    if (d.kind == VM_LOCAL) { t.base = Lc + (size_t)d.idx * V * NT; t.A = 1; t.S = NT; }
-    else if (d.kind == VM_SCAL) { t.base = Sc + (size_t)d.idx * tcc; t.B = 1; }
-    else if (d.kind == VM_ARRAY) { t.base = d.p + cbase * d.sc; t.B = (int)d.sc; t.Cc = d.se; t.S = (long long)eyn * d.se; }
+    t.gbase = nullptr; t.Cc = 0; t.S = 0; t.off = sc_off; t.flags = 0;   // "no operand": a valid dummy
+    if (d.kind == VM_LOCAL) { t.off = lc_off + d.idx * V * NT; t.flags = 1; }
+    else if (d.kind == VM_SCAL) { t.off = sc_off + d.idx * tcc; t.flags = 2; }
+    else if (d.kind == VM_ARRAY) { t.gbase = d.p + cbase * d.sc; t.flags = d.sc ? 2 : 0; t.Cc = d.se; t.S = (long long)eyn * d.se; }
     OT[i] = t;
   }
   if (tid == 0 && a.n_scal == 0) Sc[0] = 0.0;
@@ -134,56 +200,33 @@ __global__ void __launch_bounds__(NT) k_vm(VmArgs a) {
       for (int u = 0; u < a.n_uops; u++) {
         const VmDevUop uo = U[u];
         const int fl = uo.flags;
-        const double *p0, *p1, *pa;
-        double *pd, *ps;
-        long long s0, s1, sa, ss;
-        {
-          const VmOt t = OT[uo.o[0]];
-          p0 = t.base + (tid * t.A + cx * t.B) + eb * t.Cc; s0 = t.S;
-        }
-        {
-          const VmOt t = OT[uo.o[1]];
-          p1 = t.base + (tid * t.A + cx * t.B) + eb * t.Cc; s1 = t.S;
-        }
-        {
-          const VmOt t = OT[uo.o[3]];
-          pa = t.base + (tid * t.A + cx * t.B) + eb * t.Cc; sa = t.S;
-        }
-        pd = const_cast<double*>(OT[uo.dst].base) + tid;
-        {
-          const VmOt t = OT[uo.store];
-          ps = const_cast<double*>(t.base) + (tid * t.A + cx * t.B) + eb * t.Cc; ss = t.S;
-        }
-        switch (uo.op) {
-          case SMC_OP_COPY: VM_BODY(p)
-          case SMC_OP_NEG: VM_BODY(-p)
-          case SMC_OP_ADD: VM_BODY(p + q)
-          case SMC_OP_SUB: VM_BODY(p - q)
-          case SMC_OP_MUL: VM_BODY(p * q)
-          case SMC_OP_DIV: VM_BODY(p / q)
-          case SMC_OP_EXP: VM_BODY(exp(p))
-          case SMC_OP_LOG: VM_BODY(log(p))
-          case SMC_OP_ZERO: VM_BODY(0.0)
-          default: {
-            const VmOt t = OT[uo.o[2]];
-            const double* p2 = t.base + (tid * t.A + cx * t.B) + eb * t.Cc;
-            const long long s2 = t.S;
-            double rsum = 0.0;
-            bool gaveup = false;
-            for (int v = 0; v < vc; v++) {
-              double r = vm_apply_slow(uo.op, uo.dist, uo.darg, p0[v * s0], p1[v * s1], p2[v * s2]);
-              if (uo.op == SMC_OP_LOGPDF && (r == -INFINITY || isnan(r))) {   // "give up eval", src/distribs.jl:69-70
-                gaveup = true;
-                r = 0.0;
-              }
-              if (fl & VMF_ACC) r = pa[v * sa] + r;
-              if (fl & VMF_WRITE) pd[v * NT] = r;
-              if (fl & VMF_STORE) ps[v * ss] = r;
-              rsum += r;
-            }
-            if (gaveup) a.bad[c] = 1;
-            if (fl & VMF_REDUCE) Rd[uo.red * NT + tid] += rsum;
-          }
+        const VmOt t0 = OT[uo.o[0]], t1 = OT[uo.o[1]], t2 = OT[uo.o[2]];
+        // shared-memory operands: index of element 0 and stride (0 for a per-chain scalar, NT for a local)
+        const int i0 = t0.off + ((t0.flags & 1) ? tid : 0) + ((t0.flags & 2) ? cx : 0);
+        const int i1 = t1.off + ((t1.flags & 1) ? tid : 0) + ((t1.flags & 2) ? cx : 0);
+        const int i2 = t2.off + ((t2.flags & 1) ? tid : 0) + ((t2.flags & 2) ? cx : 0);
+        double* const pd = vsmd + OT[uo.dst].off + tid;
+        if (!t0.gbase && !t1.gbase && !t2.gbase && (fl == VMF_WRITE || fl == VMF_REDUCE)) {
+          const double *p0 = vsmd + i0, *p1 = vsmd + i1, *p2 = vsmd + i2;
+          const int s0 = (t0.flags & 1) ? NT : 0, s1 = (t1.flags & 1) ? NT : 0, s2 = (t2.flags & 1) ? NT : 0;
+          const double *pa = nullptr;
+          double* ps = nullptr;
+          const int sa = 0, ss = 0;
+          VM_SWITCH
+        } else {
+          const double* p0 = t0.gbase ? t0.gbase + ((t0.flags & 2) ? cx : 0) + eb * t0.Cc : vsmd + i0;
+          const double* p1 = t1.gbase ? t1.gbase + ((t1.flags & 2) ? cx : 0) + eb * t1.Cc : vsmd + i1;
+          const double* p2 = t2.gbase ? t2.gbase + ((t2.flags & 2) ? cx : 0) + eb * t2.Cc : vsmd + i2;
+          const long long s0 = t0.gbase ? t0.S : ((t0.flags & 1) ? NT : 0);
+          const long long s1 = t1.gbase ? t1.S : ((t1.flags & 1) ? NT : 0);
+          const long long s2 = t2.gbase ? t2.S : ((t2.flags & 1) ? NT : 0);
+          const VmOt ta = OT[uo.o[3]], ts = OT[uo.store];
+          const double* pa = ta.gbase ? ta.gbase + ((ta.flags & 2) ? cx : 0) + eb * ta.Cc
+                                      : vsmd + ta.off + ((ta.flags & 1) ? tid : 0) + ((ta.flags & 2) ? cx : 0);
+          const long long sa = ta.gbase ? ta.S : ((ta.flags & 1) ? NT : 0);
+          double* ps = ts.gbase ? const_cast<double*>(ts.gbase) + ((ts.flags & 2) ? cx : 0) + eb * ts.Cc : vsmd + sc_off;
+          const long long ss = ts.S;
+          VM_SWITCH
         }
       }
     }
@@ -208,7 +251,10 @@ __global__ void __launch_bounds__(NT) k_vm(VmArgs a) {
     }
   }
 }
-#undef VM_BODY
+#undef VM_SWITCH
+#undef VM_RUN
+#undef VM_LOAD4
+#undef VM_LOAD1
 
 struct VmFinalArgs {
   const double* partial;

@@ -269,8 +269,8 @@ def fuse(lowered):
     programs = []
     for gi, g in enumerate(all_groups):
         target = out_f if gi < len(gf) else out_b
-        if not g.fusable or len(g.stmts) < 2:
-            target.extend(g.stmts)
+        if not g.fusable or (len(g.stmts) < 2 and not is_reduce(g.stmts[0])):
+            target.extend(g.stmts)           # (a lone reduction still becomes a program: one launch instead of two)
             continue
         outside = set(always)
         for hj, e in enumerate(ext):

@@ -295,7 +295,23 @@ class Lowering(object):
         raise ModelError("dimension mismatch: %s vs %s" % (list(a.shape), list(b.shape)))
 
     def binary(self, op, a, b, back=False):
-        return self.emit(op, [a, b], self._bshape(a, b), back=back)
+        """one 3-address statement -- after the identities the reference lists as TODO ("+0, *1", constant folding:
+        TODO.md:4-9): x+0, 0+x, x-0, x*1, 1*x, x/1 are x itself and literal (op) literal is a literal.  All of them are
+        exact in IEEE arithmetic, so values are unchanged; they only remove statements from the tape."""
+        shape = self._bshape(a, b)
+        ai, bi = a.kind == REG_IMM, b.kind == REG_IMM
+        if ai and bi and op in ("ADD", "SUB", "MUL", "DIV") and not (op == "DIV" and b.imm == 0.0):
+            x, y = a.imm, b.imm
+            return self.imm(x + y if op == "ADD" else x - y if op == "SUB" else x * y if op == "MUL" else x / y)
+        if op == "ADD" and ai and a.imm == 0.0 and b.shape == shape:
+            return b
+        if op in ("ADD", "SUB") and bi and b.imm == 0.0 and a.shape == shape:
+            return a
+        if op == "MUL" and ai and a.imm == 1.0 and b.shape == shape:
+            return b
+        if op in ("MUL", "DIV") and bi and b.imm == 1.0 and a.shape == shape:
+            return a
+        return self.emit(op, [a, b], shape, back=back)
 
     def unary(self, op, a, back=False):
         return self.emit(op, [a], a.shape, back=back)

@@ -59,6 +59,7 @@ if "cfg4" in which:
     for C in (1024, 16384):
         low, dev = api._build(SLEEPSTUDY2, init, data, True, C, 0, "assign")
         steps = 60
+        dev.run("nuts", np.array(low.init), C, 2, 0, seed=3, store_draws=False, want=())   # warm-up
         t0 = time.time()
         raw = dev.run("nuts", np.array(low.init), C, steps, 0, seed=1, store_draws=False, want=())
         rows.append(dict(chains=C, steps=steps, leapfrogs_per_s=raw["n_leapfrogs"] / (raw["device_ms"] * 1e-3),
@@ -72,9 +73,12 @@ if "cfg5" in which:
     x = ou_data(1_000_000, 5)
     init = [("tau", 20.0), ("mu", 10.0), ("sigma", 0.1)]
     rows = []
-    for C in (1, 64):
+    for C in (1, 64, 4096):
         for kind, kw, steps in (("rwm", {}, 20), ("hmc", dict(isteps=2, stepsize=1e-4), 10), ("nuts", {}, 4)):
+            if C == 4096 and kind == "nuts":
+                continue
             low, dev = api._build(ORNSTEIN, init, dict(x=x), kind != "rwm", C, 0, "assign")
+            dev.run(kind, np.array(low.init), C, 2, 0, seed=3, store_draws=False, want=(), **kw)      # warm-up: buffers sized, evaluation graph captured
             raw = dev.run(kind, np.array(low.init), C, steps, 0, seed=1, store_draws=False, want=(), **kw)
             rows.append(dict(sampler=kind, chains=C, steps=steps, chain_steps_per_s=C * steps / (raw["device_ms"] * 1e-3),
                              evals_per_s=C * (raw["n_evals"] - 1) / (raw["device_ms"] * 1e-3), accept=float(raw["accept_rate"].mean()),

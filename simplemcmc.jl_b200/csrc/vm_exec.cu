@@ -314,9 +314,22 @@ int smc_vm_plan(smc_model_s* m, SmcProgram& pr) {
     return (uint16_t)(v.size() - 1);
   };
   auto was_stored = [&](uint32_t reg) { return std::find(stored.begin(), stored.end(), reg) != stored.end(); };
+  // slot d is about to be redefined: every other slot that is just a name for "local d" gets its own copy first
+  auto materialise_aliases = [&](int d) {
+    for (int t = 0; t < SMC_PROG_MAX_LOCALS; t++) {
+      if (t == d || cur[t].mode != VM_LOCAL || cur[t].idx != d) continue;
+      VmUop u;
+      memset(&u, 0, sizeof(u));
+      u.op = SMC_OP_COPY; u.nsrc = 1; u.mode[0] = VM_LOCAL; u.idx[0] = (uint16_t)d; u.dst = (uint16_t)t; u.flags = VMF_WRITE;
+      U.push_back(u);
+      cur[t].idx = (uint16_t)t;
+      last_writer[t] = (int)U.size() - 1;
+    }
+  };
   const int NI = (int)pr.instr.size();
   for (int i = 0; i < NI; i++) {
     const smc_prog_instr& in = pr.instr[i];
+    if (in.op == SMC_P_LOADS || in.op == SMC_P_LOADV) materialise_aliases(in.dst);
     if (in.op == SMC_P_LOADS || (in.op == SMC_P_LOADV && pr.h.n == 1)) {
       if (was_stored(in.reg)) { smc_set_error("program: register %u is reloaded after being stored", in.reg); return SMC_ERR_INVALID; }
       cur[in.dst].mode = VM_SCAL;
@@ -359,9 +372,18 @@ int smc_vm_plan(smc_model_s* m, SmcProgram& pr) {
       } else {
         tgt->red = in.aux0;
       }
+    } else if (in.op == SMC_OP_COPY && !(in.flags & SMC_F_ACC) && in.nsrc == 1 && cur[in.src[0]].mode != VM_NONE &&
+               !(cur[in.src[0]].mode == VM_LOCAL && cur[in.src[0]].idx == in.dst)) {
+      // copy propagation (the pass-through adjoints `dx = dx + ds` of src/diff.jl:29-38 are plain copies): the
+      // destination becomes another name of the source value; it is materialised only if that slot is overwritten
+      // while the name is still in use (see `materialise_aliases`)
+      materialise_aliases(in.dst);
+      cur[in.dst] = cur[in.src[0]];
+      last_writer[in.dst] = -1;
     } else {
       VmUop u;
       memset(&u, 0, sizeof(u));
+      materialise_aliases(in.dst);
       u.op = (uint8_t)in.op; u.dist = (uint8_t)in.aux0; u.darg = (uint8_t)in.aux1; u.nsrc = in.nsrc;
       if (in.op > 255 || in.aux0 > 255 || in.aux1 > 255) { smc_set_error("program: instruction %d has an operand out of range", i); return SMC_ERR_INVALID; }
       for (int k = 0; k < in.nsrc; k++) {
@@ -490,14 +512,18 @@ int smc_vm_launch(smc_model_s* m, SmcProgram& pr, int64_t C, int* bad) {
   a.scal = (const VmDesc*)(a.ot + pr.n_ot);
   a.n_uops = (int)nu; a.n_ot = pr.n_ot; a.n_scal = (int)ns; a.n_loc = pr.n_loc; a.n_red = (int)pr.h.n_red;
   a.n = pr.h.n; a.C = C; a.bad = bad;
+  // Thread geometry.  Chains fill the block first (coalesced per-chain operands); the index space is split over
+  // element lanes of the block and over grid chunks only as far as needed to put ~2 blocks on every SM, so that a
+  // thread keeps as many elements as possible (a micro-op is decoded once per thread and pass).
+  const long long want_threads = 2LL * m->ctx->sm_count * NT;
+  long long lanes = std::max<long long>(1, std::min<long long>((want_threads + C - 1) / C, std::max<long long>(1, a.n / 4)));
   int tcc = 1;
-  while (tcc < C && tcc < (a.n == 1 ? NT : 32)) tcc <<= 1;
+  while (tcc < C && tcc < NT) tcc <<= 1;                 // every chain of a small run in one block ...
+  while (tcc > 32 && NT / tcc < lanes) tcc >>= 1;        // ... but give up chain width for element lanes down to a warp
   a.tcc = tcc;
   const int eyn = NT / tcc;
   const long long chain_tiles = (C + tcc - 1) / tcc;
-  // element chunks: two blocks per SM when the index space allows, at least 4 elements per thread
-  long long S = std::max<long long>(1, std::min<long long>((2LL * m->ctx->sm_count + chain_tiles - 1) / chain_tiles,
-                                                           (a.n + (long long)eyn * 4 - 1) / ((long long)eyn * 4)));
+  long long S = std::max<long long>(1, std::min<long long>((lanes + eyn - 1) / eyn, (a.n + (long long)eyn * 4 - 1) / ((long long)eyn * 4)));
   a.chunk = (a.n + S - 1) / S;
   S = (a.n + a.chunk - 1) / a.chunk;
   a.S = (int)S;

@@ -263,9 +263,24 @@ def fuse(lowered):
         producers.setdefault(s.dst.vid, []).append(s)
     gf = rematerialise(form_groups(body_f), producers)
     gb = rematerialise(form_groups(body_b), producers)
+    always = {lowered.result.vid} | {v.vid for v in lowered.vals if v.kind == L.REG_GRAD}
+    # a statement whose value every consumer now recomputes for itself (rematerialisation) is dead: drop it
+    changed = True
+    while changed:
+        changed = False
+        groups_now = gf + gb
+        ext = [external_inputs(g) for g in groups_now]
+        for gi, g in enumerate(groups_now):
+            if len(g.stmts) != 1 or g.stmts[0].op == L.OP["GLM"]:
+                continue
+            vid = g.stmts[0].dst.vid
+            if vid in always or any(vid in e for hj, e in enumerate(ext) if hj != gi):
+                continue
+            (gf if g in gf else gb).remove(g)
+            changed = True
+            break
     all_groups = gf + gb
     ext = [external_inputs(g) for g in all_groups]
-    always = {lowered.result.vid} | {v.vid for v in lowered.vals if v.kind == L.REG_GRAD}
     programs = []
     for gi, g in enumerate(all_groups):
         target = out_f if gi < len(gf) else out_b

@@ -231,26 +231,30 @@ def run_ours(args):
         return smc.simpleHMC(MODEL, steps=steps, burnin=0, isteps=ISTEPS, stepsize=STEPSIZE, chains=C, seed=seed, data=data,
                              device=local, comm=ctx, chain_offset=rank * C, beta=mode)
     e2e_call(2, 3)
-    barrier()
-    t1 = time.time()
-    res = e2e_call(K, 4)
-    if world > 1:   # the one collective of a chain-sharded run: moments for R-hat
-        mom = torch.tensor(np.stack([res.misc["chain_mean"].sum(0), (res.misc["chain_mean"] ** 2).sum(0),
-                                     res.misc["chain_m2"].sum(0)]), device="cuda")
-        dist.all_reduce(mom)
-    barrier()
-    e2e_wall = time.time() - t1
-    e2e_t = torch.tensor([e2e_wall], dtype=torch.float64, device="cuda")
-    e2e_leap = torch.tensor([float(res.misc["n_leapfrogs"])], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(e2e_leap, op=dist.ReduceOp.SUM)
+    walls, leaps = [], []
+    for rep in range(3):      # a fresh box's host side is noisy (page cache, lazy module loads): median of three complete calls
+        barrier()
+        t1 = time.time()
+        res = e2e_call(K, 4 + rep)
+        if world > 1:   # the one collective of a chain-sharded run: moments for R-hat
+            mom = torch.tensor(np.stack([res.misc["chain_mean"].sum(0), (res.misc["chain_mean"] ** 2).sum(0),
+                                         res.misc["chain_m2"].sum(0)]), device="cuda")
+            dist.all_reduce(mom)
+        barrier()
+        e2e_t = torch.tensor([time.time() - t1], dtype=torch.float64, device="cuda")
+        e2e_leap = torch.tensor([float(res.misc["n_leapfrogs"])], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(e2e_leap, op=dist.ReduceOp.SUM)
+        walls.append(float(e2e_t.item()))
+        leaps.append(float(e2e_leap.item()))
+    mid = sorted(range(3), key=lambda k: walls[k])[1]
     h2d = X.nbytes + Y.nbytes + mode.nbytes
     d2h = sum(v.nbytes for v in res.params.values()) + res.loglik.nbytes + res.accept.nbytes
-    e2e = {"value": float(e2e_leap.item()) / float(e2e_t.item()), "unit": UNIT, "h2d_bytes_per_step": h2d / K,
-           "d2h_bytes_per_step": d2h / K, "wall_s": float(e2e_t.item()),
+    e2e = {"value": leaps[mid] / walls[mid], "unit": UNIT, "h2d_bytes_per_step": h2d / K,
+           "d2h_bytes_per_step": d2h / K, "wall_s": walls[mid], "wall_s_all_calls": walls,
            "what": "one simpleHMC(model, steps=K, chains=4096, ...) call per rank with host (pinned) X, Y: lowering, tape compile, "
-                   "H2D bind, K steps, D2H of all draws"}
+                   "H2D bind, K steps, D2H of all draws; wall clock (max over ranks), median of 3 calls"}
 
     if rank == 0:
         cpu, _ = cpu_baseline(X, Y, mode, 24)

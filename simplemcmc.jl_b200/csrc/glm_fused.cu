@@ -85,7 +85,7 @@ template <int FAM, int MT, int NWC, int NWR, int MP8>
 __global__ void __launch_bounds__(NWC* NWR * 32, (MP8 <= 2 ? 2 : 1)) k_glm(GlmArgs a) {
   constexpr int MP = MP8 * 8, LD = MP + 4, NT = NWC * NWR * 32;
   constexpr int RT = (MP8 >= 4) ? 64 : 128;  // rows per tile
-  constexpr int NST = 4, PD = 1;             // stages / prefetch distance (see the software pipeline below)
+  constexpr int NST = 4;                     // stages; the copy of tile t+1 is in flight while tile t is consumed
   constexpr int TC = NWC * MT * 8;           // chains per CTA
   constexpr int BPW = RT / 8 / NWR;          // 8-row blocks per warp per tile
   static_assert(RT % (8 * NWR) == 0, "row tile must split evenly over the row warps");
@@ -127,6 +127,9 @@ __global__ void __launch_bounds__(NWC* NWR * 32, (MP8 <= 2 ? 2 : 1)) k_glm(GlmAr
     neg_inv_s2 = -1.0 / (a.par * a.par);
   }
 
+  // (issuing this copy a few chunks per row-block iteration instead of in one burst after the barrier was measured
+  // slower: 33.98 vs 32.07 ms per launch on cfg2 -- the extra address arithmetic inside the DMMA loop costs more
+  // than the burst)
   auto load_tile = [&](int t) {
     if (t < ntiles) {
       double* xs = Xs + (t % NST) * RT * LD;
@@ -149,9 +152,9 @@ __global__ void __launch_bounds__(NWC* NWR * 32, (MP8 <= 2 ? 2 : 1)) k_glm(GlmAr
   };
   // tile t has landed for every thread; the stage of tile t-3 is free again
   auto tile_begin = [&](int t) {
-    cp_async_wait<PD - 1>();
+    cp_async_wait<0>();
     __syncthreads();
-    load_tile(t + PD);
+    load_tile(t + 1);
   };
   // product 1 on the block `gb` of this warp: acc[mt][s] = eta(chain cbase+mt*8+g, row rowmap(2q+s))
   auto gemm1 = [&](int gb, double (&acc)[MT][2]) {
@@ -393,12 +396,25 @@ __global__ void __launch_bounds__(256) k_glm_stream(GlmStreamArgs a) {
     inv_s = 1.0 / a.par;
     neg_inv_s2 = -1.0 / (a.par * a.par);
   }
+  // software pipeline over this thread's rows: the loads of the next row are in flight while the family stage
+  // (exp / divide / log) of the current one runs
   const long long stride = (long long)gridDim.x * 256;
-  for (long long r = (long long)blockIdx.x * 256 + tid; r < a.N; r += stride) {
+  long long r = (long long)blockIdx.x * 256 + tid;
+  double xn[MB], yn = 0.0;
+#pragma unroll
+  for (int j = 0; j < MB; j++) xn[j] = (j < a.M && r < a.N) ? __ldg(a.X + (long long)j * a.N + r) : 0.0;
+  if (r < a.N) yn = __ldg(a.y + r);
+  while (r < a.N) {
     double x[MB];
 #pragma unroll
-    for (int j = 0; j < MB; j++) x[j] = (j < a.M) ? __ldg(a.X + (long long)j * a.N + r) : 0.0;
-    const double y = __ldg(a.y + r);
+    for (int j = 0; j < MB; j++) x[j] = xn[j];
+    const double y = yn;
+    const long long rn = r + stride;
+    if (rn < a.N) {
+#pragma unroll
+      for (int j = 0; j < MB; j++) xn[j] = (j < a.M) ? __ldg(a.X + (long long)j * a.N + rn) : 0.0;
+      yn = __ldg(a.y + rn);
+    }
 #pragma unroll
     for (int ct = 0; ct < CT; ct++) {
       double eta = 0.0;
@@ -409,6 +425,7 @@ __global__ void __launch_bounds__(256) k_glm_stream(GlmStreamArgs a) {
 #pragma unroll
       for (int j = 0; j < MB; j++) G[j][ct] = fma(d, x[j], G[j][ct]);
     }
+    r = rn;
   }
   // block reduction: shuffle tree inside each warp, then the 8 warps in order
 #pragma unroll

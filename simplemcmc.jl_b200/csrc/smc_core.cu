@@ -660,6 +660,8 @@ extern "C" int smc_model_finalize(smc_model_t m, int64_t max_chains, int row_sha
   {
     const char* ng = getenv("SMC_NO_GRAPHS");
     m->graphs_enabled = (ng && ng[0] == '1') ? 0 : 1;
+    const char* gn = getenv("SMC_GRAPH_NCCL");   // opt-in: capture the in-sequence NCCL all-reduce of row-sharded models too
+    m->graph_nccl = (gn && gn[0] == '1') ? 1 : 0;
   }
   // chains are the contiguous axis of every per-chain array; pad to 32 only when that does not waste bandwidth
   int64_t Cpad = max_chains >= 32 ? (max_chains + 31) / 32 * 32 : max_chains;
@@ -762,7 +764,7 @@ int smc_model_eval_device(smc_model_s* m, int64_t C, bool with_grad) {
   if (C < 1 || C > m->Cmax) { smc_set_error("chains %lld outside [1, %lld] given to smc_model_finalize", (long long)C, (long long)m->Cmax); return SMC_ERR_INVALID; }
   cudaStream_t st = m->ctx->stream;
   m->C = C;
-  if (!m->graphs_enabled || m->time_glm || (m->row_shard && m->ctx->nranks > 1)) return eval_body(m, C, with_grad);
+  if (!m->graphs_enabled || m->time_glm || (m->row_shard && m->ctx->nranks > 1 && !m->graph_nccl)) return eval_body(m, C, with_grad);
   if (m->graphs_stale) smc_graphs_invalidate(m);
   int gi = -1;
   for (size_t i = 0; i < m->graphs.size(); i++)

@@ -134,6 +134,7 @@ struct smc_model_s {
   int time_glm = 0;
   std::vector<SmcEvalGraph> graphs;
   int graphs_enabled = 1;
+  int graph_nccl = 0;
   bool graphs_stale = false;   // a buffer captured graphs point at was reallocated
   int64_t realloc_epoch = 0;
 };

@@ -119,6 +119,21 @@ def test_statement_fusion_of_the_ornstein_tape():
         assert not (pinned & written)
 
 
+def test_tape_identities_and_dead_statement_elimination():
+    """the reference's TODO.md:4-9 ("+0, *1", constant folding) done at lowering time; values are unchanged (exact identities)"""
+    low = Lowering("y = (x + 0) * 1\nz = y / 1 - 0\nz ~ Normal(0 + 0, 2 * 0.5)", [("x", np.zeros(3))], {})
+    assert [s.op for s in low.fwd] == [lowering.OP["LOGPDF"]]            # only the density is left
+    assert low.fwd[0].srcs[0].imm == 0.0 and low.fwd[0].srcs[1].imm == 1.0 and low.fwd[0].srcs[2].kind == lowering.REG_PARAM
+    # sleepstudy: `intercept + submatrix*rand_int` is recomputed inside the programs that use it, so the stand-alone
+    # statement that would store it as a [180][C] array is dropped
+    data, nsub = sleepstudy_data()
+    low = Lowering(SLEEPSTUDY2, [("intercept", 250.0), ("slope", 10.0), ("rand_int", np.zeros(nsub)), ("rand_slope", np.zeros(nsub))], data)
+    low.serialise()
+    plain = [s for s in low.tape_fwd if s.op not in (lowering.OP["MATMUL"], 49)]
+    assert plain == [], plain
+    assert sum(1 for s in low.tape_fwd + low.tape_bwd if s.op == lowering.OP["MATMUL"]) == 4
+
+
 def test_programs_pack_for_index_spaces_beyond_16_bits():
     """cfg5 at T = 1e6: a program's index-space length lives in its header, not in a 16-bit instruction field"""
     import struct

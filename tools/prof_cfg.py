@@ -1,16 +1,28 @@
-"""Short runs of the secondary configs for `ncu --metrics gpu__time_duration.sum` launch lists:
-  python tools/prof_cfg.py cfg4 [chains] | cfg5 [chains] [sampler]"""
+"""Short runs of the secondary configs for `ncu --metrics gpu__time_duration.sum` launch lists / `ncu --set full` captures:
+  python tools/prof_cfg.py cfg3 [chains] | cfg4 [chains] | cfg5 [chains] [sampler]"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 from smc_pkg import load_package
 load_package()
 from simplemcmc_jl_b200 import api
-from util import ORNSTEIN, SLEEPSTUDY2, ou_data, sleepstudy_data
+from util import LOGISTIC, ORNSTEIN, SLEEPSTUDY2, ou_data, sleepstudy_data
 
 which = sys.argv[1]
 C = int(sys.argv[2]) if len(sys.argv) > 2 else 0
-if which == "cfg4":
+if which == "cfg3":
+    C = C or 1
+    rng = np.random.default_rng(3)
+    N, M = 10_000_000, 10
+    X = np.empty((M, N)).T
+    X[:, 0] = 1.0
+    for j in range(1, M):
+        X[:, j] = rng.standard_normal(N)
+    b0 = rng.standard_normal(M)
+    Y = (rng.random(N) < 1.0 / (1.0 + np.exp(X @ b0))).astype(np.float64)
+    low, dev = api._build(LOGISTIC, [("vars", np.zeros(M))], dict(X=X, Y=Y), True, C, 0, "assign")
+    raw = dev.run("hmc", b0, C, 4, 0, isteps=2, stepsize=0.1 / np.sqrt(N / 1000), seed=1, store_draws=False, want=())
+elif which == "cfg4":
     C = C or 16384
     data, nsub = sleepstudy_data()
     init = [("intercept", 250.0), ("slope", 10.0), ("rand_int", np.zeros(nsub)), ("rand_slope", np.zeros(nsub))]

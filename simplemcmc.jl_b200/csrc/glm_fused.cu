@@ -21,6 +21,10 @@ int smc_comm_allreduce_device(smc_ctx_s* c, double* buf, int64_t n);  // smc_com
 
 namespace {
 
+// rows per shared-memory tile.  (128-row tiles with three stages for MP = 64 -- half the CTA-wide barriers -- measured
+// 32.72 ms per cfg2 launch against 32.07 ms for 64-row tiles with four stages, so the barrier is not what is left.)
+#define SMC_GLM_RT(MP8) ((MP8) >= 4 ? 64 : 128)
+
 struct GlmArgs {
   const double* X;     // [N][MP] row major, zero padded
   const double* y;     // [N] response as consumed by the family (sign-normalised)
@@ -84,8 +88,8 @@ __device__ __forceinline__ int rowmap(int n) { return n < 4 ? n : (n ^ 1); }
 template <int FAM, int MT, int NWC, int NWR, int MP8>
 __global__ void __launch_bounds__(NWC* NWR * 32, (MP8 <= 2 ? 2 : 1)) k_glm(GlmArgs a) {
   constexpr int MP = MP8 * 8, LD = MP + 4, NT = NWC * NWR * 32;
-  constexpr int RT = (MP8 >= 4) ? 64 : 128;  // rows per tile
-  constexpr int NST = 4;                     // stages; the copy of tile t+1 is in flight while tile t is consumed
+  constexpr int RT = SMC_GLM_RT(MP8);        // rows per tile
+  constexpr int NST = 4;    // stages; the copy of tile t+1 is in flight while tile t is consumed
   constexpr int TC = NWC * MT * 8;           // chains per CTA
   constexpr int BPW = RT / 8 / NWR;          // 8-row blocks per warp per tile
   static_assert(RT % (8 * NWR) == 0, "row tile must split evenly over the row warps");
@@ -203,7 +207,7 @@ __global__ void __launch_bounds__(NWC* NWR * 32, (MP8 <= 2 ? 2 : 1)) k_glm(GlmAr
   // Software pipeline over this warp's 8-row blocks, depth 2: iteration gb issues product 2 of block gb-1 and product 1 of
   // block gb+1 (64 DMMAs) and, in their issue shadow, the family stage of block gb, whose result is only consumed one
   // iteration later -- so no FP64-pipe time is lost to the elementwise stage.  Block counts are uniform over the CTA
-  // (tail blocks are zero filled); a tile's stage is reused 3 tiles later (NST = 4, prefetch distance 1).
+  // (tail blocks are zero filled); a tile's stage is reused NST - 1 >= 2 tiles later (prefetch distance 1).
   const int total = ntiles * BPW;
   load_tile(0);
   if (total > 0) {
@@ -492,7 +496,7 @@ bool use_stream(int M, long long C) { return (M <= 16 && C <= 4) || (M <= 32 && 
 
 template <int FAM, int MT, int NWC, int NWR, int MP8>
 int launch_cfg(const GlmArgs& a, int RS, cudaStream_t st) {
-  constexpr int MP = MP8 * 8, LD = MP + 4, RT = (MP8 >= 4) ? 64 : 128, NST = 4, TC = NWC * MT * 8;
+  constexpr int MP = MP8 * 8, LD = MP + 4, RT = SMC_GLM_RT(MP8), NST = 4, TC = NWC * MT * 8;
   size_t pipe = (size_t)NST * RT * (LD + 1) * sizeof(double);
   size_t epi = (size_t)(MP + 1) * TC * sizeof(double) + TC * sizeof(int);
   size_t smem = std::max(pipe, epi);
@@ -610,7 +614,7 @@ int smc_glm_launch(smc_model_s* m, SmcGlmPlan& g, int64_t C) {
   }
   int tc = chain_tile_for(C);
   long long chain_tiles = (C + tc - 1) / tc;
-  int RT = g.MP >= 32 ? 64 : 128;
+  int RT = SMC_GLM_RT(g.MP / 8);
   int RS = row_splits_for(chain_tiles, g.N, RT, m->ctx->sm_count * (g.MP <= 16 ? 2 : 1));  // narrow models run 2 CTAs per SM
   long long rows_per_split = ((g.N + RS - 1) / RS + RT - 1) / RT * RT;
   RS = (int)((g.N + rows_per_split - 1) / rows_per_split);

@@ -172,6 +172,7 @@ extern "C" int smc_model_destroy(smc_model_t m) {
   smc_graphs_invalidate(m);
   for (auto& r : m->regs) if (r.owned && r.dev) cudaFree(r.dev);
   for (auto d : m->idx_dev) cudaFree(d);
+  for (auto& p : m->scatter) { cudaFree(p.ptr); cudaFree(p.list); }
   for (auto& g : m->glm) smc_glm_release(g);
   for (auto& pr : m->programs) if (pr.dev_tables) cudaFree(pr.dev_tables);
   if (m->beta) cudaFree(m->beta);
@@ -395,14 +396,24 @@ __global__ void k_gather(Opd src, Dst d, const int32_t* idx, long long n, long l
   }
 }
 
-// sequential over the index list per chain: repeated indices resolve in list order (deterministic)
-__global__ void k_scatter(Opd src, Dst d, const int32_t* idx, long long n, long long C, int add) {
-  long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  for (long long e = 0; e < n; e++) {
-    double v = opd_ld(src, e, c);
-    double* q = d.p + (long long)idx[e] * d.se + c * d.sc;
-    *q = add ? (*q + v) : v;
+// Scatter through the inverse of the static index table (CSR: for every destination element the source elements that
+// map to it, in list order): thread = (destination element, chain), coalesced over chains.  Repeated indices resolve
+// exactly as a sequential pass over the list would -- `+=` in list order for the corrected adjoint (SCATTER_ADD), last
+// writer wins for the reference's assignment (SCATTER_SET, src/parsing.jl:277-281); untouched elements keep their value.
+__global__ void k_scatter_csr(Opd src, Dst d, const int32_t* ptr, const int32_t* list, long long n_dst, long long C, int add) {
+  long long total = n_dst * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long e = i / C, c = i - e * C;
+    int b = ptr[e], t = ptr[e + 1];
+    if (b == t) continue;
+    double* q = d.p + e * d.se + c * d.sc;
+    if (add) {
+      double acc = *q;
+      for (int k = b; k < t; k++) acc += opd_ld(src, list[k], c);
+      *q = acc;
+    } else {
+      *q = opd_ld(src, list[t - 1], c);
+    }
   }
 }
 
@@ -501,6 +512,32 @@ Dst smc_make_dst(const smc_model_s* m, uint32_t r) {
   return d;
 }
 
+// inverse (CSR) of index table `table` for a destination of n_dst elements, built on first use
+static int scatter_plan(smc_model_s* m, uint32_t table, int64_t n_dst, SmcScatterPlan** out) {
+  for (auto& p : m->scatter)
+    if (p.table == (int)table && p.n_dst == n_dst) { *out = &p; return SMC_OK; }
+  const uint32_t n = m->idx_len[table];
+  std::vector<int32_t> idx(n);
+  SMC_CUDA(cudaMemcpy(idx.data(), m->idx_dev[table], (size_t)n * 4, cudaMemcpyDeviceToHost));
+  std::vector<int32_t> ptr(n_dst + 1, 0), list(std::max<uint32_t>(n, 1));
+  for (uint32_t e = 0; e < n; e++) {
+    if (idx[e] < 0 || idx[e] >= n_dst) { smc_set_error("tape: scatter index out of range"); return SMC_ERR_INVALID; }
+    ptr[idx[e] + 1]++;
+  }
+  for (int64_t k = 0; k < n_dst; k++) ptr[k + 1] += ptr[k];
+  std::vector<int32_t> fill(ptr.begin(), ptr.end() - 1);
+  for (uint32_t e = 0; e < n; e++) list[fill[idx[e]]++] = (int32_t)e;   // stable: list order within a destination
+  SmcScatterPlan p;
+  p.table = (int)table; p.n_dst = n_dst;
+  SMC_CUDA(cudaMalloc(&p.ptr, ptr.size() * 4));
+  SMC_CUDA(cudaMalloc(&p.list, list.size() * 4));
+  SMC_CUDA(cudaMemcpy(p.ptr, ptr.data(), ptr.size() * 4, cudaMemcpyHostToDevice));
+  SMC_CUDA(cudaMemcpy(p.list, list.data(), list.size() * 4, cudaMemcpyHostToDevice));
+  m->scatter.push_back(p);
+  *out = &m->scatter.back();
+  return SMC_OK;
+}
+
 static int run_statement(smc_model_s* m, const smc_tape_stmt& s, int64_t C, bool header) {
   cudaStream_t st = m->ctx->stream;
   const SmcReg& dreg = m->regs[s.dst];
@@ -587,8 +624,9 @@ static int run_statement(smc_model_s* m, const smc_tape_stmt& s, int64_t C, bool
     case SMC_OP_SCATTER_SET:
     case SMC_OP_SCATTER_ADD: {
       Opd src = smc_make_opd(m, s.src[0]);
-      long long n = m->idx_len[s.aux0];
-      k_scatter<<<(unsigned)((C + 127) / 128), 128, 0, st>>>(src, d, m->idx_dev[s.aux0], n, C, s.op == SMC_OP_SCATTER_ADD);
+      SmcScatterPlan* sp = nullptr;
+      SMC_TRY(scatter_plan(m, s.aux0, dreg.numel, &sp));
+      k_scatter_csr<<<grid_for(dreg.numel * C), 256, 0, st>>>(src, d, sp->ptr, sp->list, dreg.numel, C, s.op == SMC_OP_SCATTER_ADD);
       m->ctx->launches++;
       break;
     }

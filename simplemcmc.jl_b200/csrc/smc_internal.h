@@ -98,6 +98,13 @@ struct SmcProgram {  // one SMC_OP_FUSED register program
   size_t dev_tables_bytes = 0;
 };
 
+struct SmcScatterPlan {  // inverse of a static index table for SCATTER statements
+  int table = -1;
+  int64_t n_dst = 0;
+  int32_t* ptr = nullptr;   // [n_dst + 1]
+  int32_t* list = nullptr;  // [n]
+};
+
 struct SmcEvalGraph {  // one captured evaluation (all statements of the tape for a chain count), replayed with one launch
   int64_t C = 0;
   int with_grad = 0;
@@ -117,6 +124,7 @@ struct smc_model_s {
   std::vector<uint32_t> idx_len;
   std::vector<SmcGlmPlan> glm;
   std::vector<SmcProgram> programs;
+  std::vector<SmcScatterPlan> scatter;
   bool finalized = false;
   int row_shard = 0;
   int64_t M = 0;       // n_params

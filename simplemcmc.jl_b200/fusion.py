@@ -252,18 +252,65 @@ def build_program(g, outside):
     return prog
 
 
+def coalesce_accumulator(fwd, bwd, result):
+    """`__acc = __acc + logpdf...` (src/parsing.jl:103-109) leaves a chain of scalar additions a1 = t1 + t2, a2 = a1 + t3, ...
+    whose operands are each produced once and consumed once.  Instead of one statement (one launch) per addition the
+    later producer accumulates straight into the earlier operand's register (`x += value`) and the sum becomes another
+    name for x.  Same additions in the same order, so the value is bit-identical.  -> (fwd, bwd, result)"""
+    fwd, bwd = list(fwd), list(bwd)
+    changed = True
+    while changed:
+        changed = False
+        uses = {}
+        for st in fwd + bwd:
+            for v in st.srcs:
+                uses[v.vid] = uses.get(v.vid, 0) + 1
+        prod = {}
+        for i, st in enumerate(fwd):
+            prod.setdefault(st.dst.vid, []).append(i)
+            if st.op == L.OP["GLM"]:
+                prod.setdefault(st.aux2.vid, []).append(i)
+        for i, st in enumerate(fwd):
+            if st.op != L.OP["ADD"] or st.flags or st.dst.numel != 1 or st.dst.kind != L.REG_CHAIN:
+                continue
+            x, y = st.srcs
+            if x is y or any(v.numel != 1 or v.kind != L.REG_CHAIN or uses.get(v.vid, 0) != 1 for v in (x, y)):
+                continue
+            px, py = prod.get(x.vid, []), prod.get(y.vid, [])
+            if len(py) != 1 or not px or max(px) >= py[0] or py[0] >= i:
+                continue                      # y must have one producer, after every writer of x and before the sum
+            p = fwd[py[0]]
+            if (p.flags & L.F_ACC) or p.dst is not y or not (fusable(p) or p.op == L.OP["GLM"]):
+                continue
+            q = L.Stmt(p.op, x, p.srcs, flags=p.flags | L.F_ACC, aux0=p.aux0, aux1=p.aux1, aux2=p.aux2, imm=p.imm)
+            fwd[py[0]] = q
+            t = st.dst
+            del fwd[i]
+            for other in fwd + bwd:           # the sum is now another name for x
+                if any(v is t for v in other.srcs):
+                    other.srcs = [x if v is t else v for v in other.srcs]
+            if result is t:
+                result = x
+            changed = True
+            break
+    return fwd, bwd, result
+
+
 def fuse(lowered):
     """-> (fwd, bwd, programs): statement lists in which runs of elementwise statements are FUSED statements"""
-    body_f = [s for s in lowered.fwd if s.dst.kind != L.REG_HDR]
-    body_b = [s for s in lowered.bwd if s.dst.kind != L.REG_HDR]
-    out_f = [s for s in lowered.fwd if s.dst.kind == L.REG_HDR]
-    out_b = [s for s in lowered.bwd if s.dst.kind == L.REG_HDR]
+    fwd0 = [L.Stmt(s.op, s.dst, s.srcs, flags=s.flags, aux0=s.aux0, aux1=s.aux1, aux2=s.aux2, imm=s.imm) for s in lowered.fwd]
+    bwd0 = [L.Stmt(s.op, s.dst, s.srcs, flags=s.flags, aux0=s.aux0, aux1=s.aux1, aux2=s.aux2, imm=s.imm) for s in lowered.bwd]
+    fwd0, bwd0, lowered.tape_result = coalesce_accumulator(fwd0, bwd0, lowered.result)
+    body_f = [s for s in fwd0 if s.dst.kind != L.REG_HDR]
+    body_b = [s for s in bwd0 if s.dst.kind != L.REG_HDR]
+    out_f = [s for s in fwd0 if s.dst.kind == L.REG_HDR]
+    out_b = [s for s in bwd0 if s.dst.kind == L.REG_HDR]
     producers = {}
     for s in body_f + body_b:
         producers.setdefault(s.dst.vid, []).append(s)
     gf = rematerialise(form_groups(body_f), producers)
     gb = rematerialise(form_groups(body_b), producers)
-    always = {lowered.result.vid} | {v.vid for v in lowered.vals if v.kind == L.REG_GRAD}
+    always = {lowered.tape_result.vid} | {v.vid for v in lowered.vals if v.kind == L.REG_GRAD}
     # a statement whose value every consumer now recomputes for itself (rematerialisation) is dead: drop it
     changed = True
     while changed:
@@ -271,10 +318,10 @@ def fuse(lowered):
         groups_now = gf + gb
         ext = [external_inputs(g) for g in groups_now]
         for gi, g in enumerate(groups_now):
-            if len(g.stmts) != 1 or g.stmts[0].op == L.OP["GLM"]:
+            if any(st.op == L.OP["GLM"] for st in g.stmts):
                 continue
-            vid = g.stmts[0].dst.vid
-            if vid in always or any(vid in e for hj, e in enumerate(ext) if hj != gi):
+            others = set().union(*[e for hj, e in enumerate(ext) if hj != gi]) if len(ext) > 1 else set()
+            if any(st.dst.vid in always or st.dst.vid in others for st in g.stmts):
                 continue
             (gf if g in gf else gb).remove(g)
             changed = True

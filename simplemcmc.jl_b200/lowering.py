@@ -681,6 +681,7 @@ class Lowering(object):
 
     def serialise(self):
         fwd, bwd, programs = self.fwd, self.bwd, []
+        self.tape_result = self.result
         if self.fuse_statements:
             from . import fusion
             fwd, bwd, programs = fusion.fuse(self)
@@ -702,13 +703,13 @@ class Lowering(object):
             if st.touched:
                 for v in st.touched:
                     use(v)
-        use(self.result)
+        use(self.tape_result)
         data_used = sorted({v.slot for v in used if v.kind == REG_DATA})
         slot_map = {s: i for i, s in enumerate(data_used)}
         for i, v in enumerate(used):
             v.reg = i
         out = [struct.pack("<12I", TAPE_MAGIC, TAPE_VERSION, len(used), len(stmts), self.bsize, len(data_used),
-                           len(self.idx_tables), self.result.reg, 0, len(fwd), len(programs), 0)]
+                           len(self.idx_tables), self.tape_result.reg, 0, len(fwd), len(programs), 0)]
         for v in used:
             if len(v.shape) == 0:
                 rows, cols = 1, 1

@@ -6,7 +6,7 @@ import numpy as np
 from smc_pkg import load_package
 load_package()
 from simplemcmc_jl_b200 import api
-from util import LOGISTIC, ORNSTEIN, SLEEPSTUDY2, ou_data, sleepstudy_data
+from util import HIERARCHICAL, LOGISTIC, ORNSTEIN, SLEEPSTUDY2, hierarchical_data, ou_data, sleepstudy_data
 
 which = sys.argv[1]
 C = int(sys.argv[2]) if len(sys.argv) > 2 else 0
@@ -22,6 +22,12 @@ if which == "cfg3":
     Y = (rng.random(N) < 1.0 / (1.0 + np.exp(X @ b0))).astype(np.float64)
     low, dev = api._build(LOGISTIC, [("vars", np.zeros(M))], dict(X=X, Y=Y), True, C, 0, "assign")
     raw = dev.run("hmc", b0, C, 4, 0, isteps=2, stepsize=0.1 / np.sqrt(N / 1000), seed=1, store_draws=False, want=())
+elif which == "cfg4h":
+    C = C or 16384
+    data, (N, D, L) = hierarchical_data()
+    init = [("mu", np.zeros((1, L))), ("sigma", np.ones((1, L))), ("beta", np.zeros((D, L)))]
+    low, dev = api._build(HIERARCHICAL, init, data, True, C, 0, "add")
+    raw = dev.run("nuts", np.array(low.init), C, 3, 0, seed=1, store_draws=False, want=())
 elif which == "cfg4":
     C = C or 16384
     data, nsub = sleepstudy_data()

@@ -7,7 +7,7 @@ import numpy as np
 from smc_pkg import load_package
 load_package()
 from simplemcmc_jl_b200 import api
-from util import LINEAR, LOGISTIC, ORNSTEIN, SLEEPSTUDY2, linear_data, ou_data, sleepstudy_data
+from util import HIERARCHICAL, LINEAR, LOGISTIC, ORNSTEIN, SLEEPSTUDY2, hierarchical_data, linear_data, ou_data, sleepstudy_data
 
 out = {}
 which = sys.argv[1:] or ["cfg1", "cfg3", "cfg4", "cfg5"]
@@ -68,6 +68,22 @@ if "cfg4" in which:
                          mean_jmax=float(raw["jmax"].mean()), launches=raw["n_kernel_launches"]))
         dev.close()
     out["cfg4_sleepstudy_38params_nuts"] = rows
+    # cfg4 (i): examples/hierarchical.jl, 30 parameters, gather adjoint as scatter-add (the corrected gradient, Appendix C Q2)
+    data, (N, D, L) = hierarchical_data()
+    init = [("mu", np.zeros((1, L))), ("sigma", np.ones((1, L))), ("beta", np.zeros((D, L)))]
+    rows = []
+    for C in (1024, 16384):
+        low, dev = api._build(HIERARCHICAL, init, data, True, C, 0, "add")
+        steps = 60
+        dev.run("nuts", np.array(low.init), C, 2, 0, seed=3, store_draws=False, want=())   # warm-up
+        t0 = time.time()
+        raw = dev.run("nuts", np.array(low.init), C, steps, 0, seed=1, store_draws=False, want=())
+        rows.append(dict(chains=C, steps=steps, leapfrogs_per_s=raw["n_leapfrogs"] / (raw["device_ms"] * 1e-3),
+                         iterations_per_s=C * steps / (raw["device_ms"] * 1e-3), evals=raw["n_evals"],
+                         active_lane_fraction=raw["n_leapfrogs"] / (max(raw["n_evals"] - 1, 1) * C), wall_s=time.time() - t0,
+                         mean_jmax=float(raw["jmax"].mean()), launches=raw["n_kernel_launches"]))
+        dev.close()
+    out["cfg4_hierarchical_30params_nuts"] = rows
 
 if "cfg5" in which:
     x = ou_data(1_000_000, 5)

@@ -71,11 +71,17 @@ enum {
 
 /* GLM families for SMC_OP_GLM (aux0) */
 enum {
-  SMC_GLM_NORMAL = 0,    /* l = logpdfNormal(0, sigma, a*eta + b_i);      imm = sigma, aux1 = sign bit of a      */
+  SMC_GLM_NORMAL = 0,    /* l = logpdfNormal(0, sigma, a*eta + b_i);      imm = sigma, aux1 = sign bits of a, b
+                            (+ SMC_GLM_F_GRAM)                                                                     */
   SMC_GLM_BERNOULLI = 1, /* l = logpdfBernoulli(1/(1+exp(s*eta)), y_i);   aux1 = 1 when s = -1                  */
   SMC_GLM_BINOMIAL = 2,  /* l = logpdfBinomial(n, 1/(1+exp(s*eta)), y_i); imm = n                                */
   SMC_GLM_POISSON = 3    /* l = logpdfPoisson(exp(s*eta), y_i)                                                   */
 };
+
+/* aux1 flag of a NORMAL GLM statement: evaluate from the sufficient statistics X'X, X'y, y'y (computed once when the model
+ * is finalized) instead of streaming X -- an opt-in algebraic rewrite in the spirit of the reference's hoisting of
+ * parameter-independent terms (src/parsing.jl:432-442, TODO.md:4-9); it changes the arithmetic, so hosts must ask for it */
+#define SMC_GLM_F_GRAM 4u
 
 typedef struct {
   uint32_t magic, version;

@@ -11,7 +11,10 @@ Every keyword that is not reserved is a model parameter with its initial value (
 parameter vector in keyword order, matrices column-major (src/parsing.jl:303-334).  External variables are looked
 up by name: first in the reserved keyword `data` (a dict), then in the caller's module globals -- the Python
 stand-in for "globals of Main" (src/parsing.jl:484-485).  New reserved keywords (B200 build): `chains`, `seed`,
-`device`, `data`, `shard`, `ref_adjoint`.  The loops themselves run inside libsimplemcmc_cuda.so.
+`device`, `data`, `shard`, `ref_adjoint`, `store_draws`, `comm`, `chain_offset`, `sufficient_stats` (opt-in: a Normal
+identity-link regression evaluates from X'X, X'y, y'y computed once -- 2*M^2 instead of 4*N*M flops per chain-step; a
+different algorithm from the reference's generated code, so it is never on by default and is reported separately).
+The loops themselves run inside libsimplemcmc_cuda.so.
 """
 import inspect
 import time
@@ -22,7 +25,7 @@ from . import capi
 from .lowering import Lowering, ModelError
 
 RESERVED = ("steps", "burnin", "isteps", "stepsize", "maxiter", "precision", "gradient", "debug", "chains", "seed",
-            "device", "data", "shard", "ref_adjoint", "store_draws", "comm", "chain_offset")
+            "device", "data", "shard", "ref_adjoint", "store_draws", "comm", "chain_offset", "sufficient_stats")
 
 
 class _DataLookup(dict):
@@ -67,8 +70,10 @@ class ModelFunction(object):
         return (logp, grad) if self.gradient else logp
 
 
-def _build(model, init, data, gradient, chains, device, ref_adjoint, shard=None, comm=None, fuse=True, fuse_statements=True):
-    low = Lowering(model, init, data, gradient=gradient, ref_adjoint=ref_adjoint, fuse=fuse, fuse_statements=fuse_statements)
+def _build(model, init, data, gradient, chains, device, ref_adjoint, shard=None, comm=None, fuse=True, fuse_statements=True,
+           sufficient_stats=False):
+    low = Lowering(model, init, data, gradient=gradient, ref_adjoint=ref_adjoint, fuse=fuse, fuse_statements=fuse_statements,
+                   sufficient_stats=bool(sufficient_stats) and shard != "rows")
     tape, bound = low.serialise()
     ctx = comm if isinstance(comm, capi.Context) else capi.Context.default(device)
     row_shard = (shard == "rows")
@@ -77,14 +82,14 @@ def _build(model, init, data, gradient, chains, device, ref_adjoint, shard=None,
 
 
 def generateModelFunction(model, gradient=False, debug=False, chains=1, device=0, data=None, ref_adjoint="assign",
-                          **init):
+                          sufficient_stats=False, **init):
     """-> (f, nparams, pars, init) like src/parsing.jl:492; debug=True returns the statement lists instead of
     compiling (the reference returns the generated Expr)."""
     lookup = _DataLookup(data, _caller_globals())
     if debug:
         low = Lowering(model, list(init.items()), lookup, gradient=gradient, ref_adjoint=ref_adjoint)
         return low.statements()
-    low, dev = _build(model, list(init.items()), lookup, gradient, chains, device, ref_adjoint)
+    low, dev = _build(model, list(init.items()), lookup, gradient, chains, device, ref_adjoint, sufficient_stats=sufficient_stats)
     f = ModelFunction(low, dev, gradient)
     # the reference's preCalculate rejects initial values outside the support (src/parsing.jl:382-383)
     if gradient:
@@ -191,7 +196,8 @@ def _sample(kind, model, kw, defaults):
     store = bool(opts.get("store_draws", True))
     lookup = _DataLookup(opts.get("data"), _caller_globals(3))
     low, dev = _build(model, init, lookup, kind != "rwm", chains, opts.get("device", 0),
-                      opts.get("ref_adjoint", "assign"), shard=opts.get("shard"), comm=opts.get("comm"))
+                      opts.get("ref_adjoint", "assign"), shard=opts.get("shard"), comm=opts.get("comm"),
+                      sufficient_stats=opts.get("sufficient_stats", False))
     try:
         raw = dev.run(kind, np.array(low.init), chains, steps, burnin, isteps=int(round(opts.get("isteps", 1))),
                       stepsize=float(opts.get("stepsize", 0.0)), seed=int(opts.get("seed", 1)), store_draws=store,

@@ -39,7 +39,7 @@ struct GlmArgs {
 };
 
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                : "+d"(d0), "+d"(d1)
                : "d"(a), "d"(b));
 }
@@ -494,6 +494,113 @@ int launch_stream(const GlmStreamArgs& a, int MB, int CT, dim3 grid, cudaStream_
 // the stream path covers M <= 16 with up to 4 chains and M <= 32 with one chain (register budget: x[MB] + G[MB][CT])
 bool use_stream(int M, long long C) { return (M <= 16 && C <= 4) || (M <= 32 && C == 1); }
 
+
+// ---- sufficient statistics (opt-in, SMC_GLM_F_GRAM) -----------------------------------------------------------------
+// For the Normal identity-link family  sum_i (x_i.beta - ytilde_i)^2 = beta'(X'X)beta - 2 beta'(X'ytilde) + ytilde'ytilde,
+// so with Z = [X, ytilde] the (M+1)x(M+1) matrix Z'Z, computed once when the model is finalized, carries everything an
+// evaluation needs: 2*M^2 flops per chain instead of 4*N*M.  This is NOT what the reference's generated code computes
+// (it streams X twice per evaluation); it is the algebraic hoisting SURVEY.md 8(d)/8(f) lists as a separately-labelled
+// extra, never enabled by default, and it loses accuracy by cancellation when the residual is small against |y|.
+struct GramArgs {
+  const double* X;   // [M][N] column major
+  const double* y;   // [N] ytilde
+  long long N, rows_per_block;
+  int M;
+  double* part;      // [gridDim.x][P*P], P = M + 1
+};
+__global__ void __launch_bounds__(256) k_gram_partial(GramArgs a) {
+  constexpr int TR = 64, MAXPAIRS = 17;   // (64+1)^2 = 4225 pairs <= 17 * 256
+  extern __shared__ __align__(16) double zs[];   // [TR][P + 1]
+  const int P = a.M + 1, LDZ = P + 1, tid = threadIdx.x;
+  const long long r_begin = (long long)blockIdx.x * a.rows_per_block, r_end = min(a.N, r_begin + a.rows_per_block);
+  double acc[MAXPAIRS];
+#pragma unroll
+  for (int t = 0; t < MAXPAIRS; t++) acc[t] = 0.0;
+  for (long long r0 = r_begin; r0 < r_end; r0 += TR) {
+    __syncthreads();
+    for (int i = tid; i < TR * P; i += 256) {
+      int col = i / TR, r = i - col * TR;
+      long long row = r0 + r;
+      double v = 0.0;
+      if (row < r_end) v = col < a.M ? __ldg(a.X + (long long)col * a.N + row) : __ldg(a.y + row);
+      zs[r * LDZ + col] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < MAXPAIRS; t++) {
+      int p = tid + t * 256;
+      if (p < P * P) {
+        int j = p / P, k = p - j * P;
+        double s = acc[t];
+        for (int r = 0; r < TR; r++) s = fma(zs[r * LDZ + j], zs[r * LDZ + k], s);
+        acc[t] = s;
+      }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < MAXPAIRS; t++) {
+    int p = tid + t * 256;
+    if (p < P * P) a.part[(long long)blockIdx.x * P * P + p] = acc[t];
+  }
+}
+__global__ void k_gram_reduce(const double* part, int nblocks, int PP, double* out) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= PP) return;
+  double t = 0.0;
+  for (int b = 0; b < nblocks; b++) t += part[(long long)b * PP + p];   // fixed order
+  out[p] = t;
+}
+
+struct GramEvalArgs {
+  const double* ZtZ;   // [P][P]
+  const double* beta;  // [M][Cpad]
+  double* Ldst;
+  double* Gdst;
+  int* bad;
+  long long N, C, Cpad;
+  int M, acc;
+  double par;
+};
+// block = 32 chains x 8 parameter lanes; A = Z'Z and the block's beta tile in shared memory
+__global__ void __launch_bounds__(256) k_glm_gram(GramEvalArgs a) {
+  extern __shared__ __align__(16) double gs[];
+  const int P = a.M + 1;
+  double* A = gs;                  // [P][P]
+  double* bs = gs + P * P;         // [M][32]
+  double* red = bs + a.M * 32;     // [2][8][32]
+  const int cx = threadIdx.x, ly = threadIdx.y, tid = ly * 32 + cx;
+  const long long c = (long long)blockIdx.x * 32 + cx;
+  for (int i = tid; i < P * P; i += 256) A[i] = __ldg(a.ZtZ + i);
+  for (int i = tid; i < a.M * 32; i += 256) {
+    int j = i / 32, cl = i - j * 32;
+    long long cc = (long long)blockIdx.x * 32 + cl;
+    bs[i] = cc < a.C ? __ldg(a.beta + (long long)j * a.Cpad + cc) : 0.0;
+  }
+  __syncthreads();
+  const double inv_s2 = 1.0 / (a.par * a.par);
+  double quad = 0.0, lin = 0.0;
+  for (int j = ly; j < a.M; j += 8) {
+    const double* Aj = A + j * P;
+    double q = 0.0;
+    for (int k = 0; k < a.M; k++) q = fma(Aj[k], bs[k * 32 + cx], q);
+    const double bj = bs[j * 32 + cx], xy = Aj[a.M];
+    quad = fma(bj, q, quad);
+    lin = fma(bj, xy, lin);
+    if (c < a.C) a.Gdst[(long long)j * a.Cpad + c] = -(q - xy) * inv_s2;   // X' dl/deta, dl/deta = -(eta - ytilde)/sigma^2
+  }
+  red[ly * 32 + cx] = quad;
+  red[256 + ly * 32 + cx] = lin;
+  __syncthreads();
+  if (ly == 0 && c < a.C) {
+    double tq = 0.0, tl = 0.0;
+    for (int y = 0; y < 8; y++) { tq += red[y * 32 + cx]; tl += red[256 + y * 32 + cx]; }
+    const double rss = tq - 2.0 * tl + A[a.M * P + a.M];
+    double L = -0.5 * rss * inv_s2 + (double)a.N * (-log(a.par) - SMC_LOG_SQRT_2PI);
+    if (!(L > -INFINITY)) { a.bad[c] = 1; L = 0.0; }
+    a.Ldst[c] = a.acc ? a.Ldst[c] + L : L;
+  }
+}
+
 template <int FAM, int MT, int NWC, int NWR, int MP8>
 int launch_cfg(const GlmArgs& a, int RS, cudaStream_t st) {
   constexpr int MP = MP8 * 8, LD = MP + 4, RT = SMC_GLM_RT(MP8), NST = 4, TC = NWC * MT * 8;
@@ -591,6 +698,24 @@ int smc_glm_prepare(smc_model_s* m, SmcGlmPlan& g) {
   m->ctx->launches++;
   g.y = g.ybuf;
   g.y_len = g.N;
+  g.gram = (g.family == SMC_GLM_NORMAL && (g.sign_neg & SMC_GLM_F_GRAM) && !m->row_shard) ? 1 : 0;
+  if (g.gram) {
+    const int P = g.M + 1, PP = P * P;
+    const int nblocks = (int)std::max<long long>(1, std::min<long long>((g.N + 63) / 64, 2LL * m->ctx->sm_count));
+    GramArgs ga;
+    ga.X = g.Xcm; ga.y = g.y; ga.N = g.N; ga.M = g.M;
+    ga.rows_per_block = ((g.N + nblocks - 1) / nblocks + 63) / 64 * 64;
+    double* part = nullptr;
+    SMC_CUDA(cudaMalloc(&part, (size_t)nblocks * PP * sizeof(double)));
+    SMC_CUDA(cudaMalloc(&g.ZtZ, (size_t)PP * sizeof(double)));
+    ga.part = part;
+    const size_t smem = (size_t)64 * (P + 1) * sizeof(double);
+    k_gram_partial<<<nblocks, 256, smem, st>>>(ga);
+    k_gram_reduce<<<(PP + 255) / 256, 256, 0, st>>>(part, nblocks, PP, g.ZtZ);
+    m->ctx->launches += 2;
+    SMC_CUDA(cudaStreamSynchronize(st));
+    cudaFree(part);
+  }
   return SMC_OK;
 }
 
@@ -598,6 +723,8 @@ void smc_glm_release(SmcGlmPlan& g) {
   if (g.Xrm) cudaFree(g.Xrm);
   if (g.part) cudaFree(g.part);
   if (g.ybuf) cudaFree(g.ybuf);
+  if (g.ZtZ) cudaFree(g.ZtZ);
+  g.ZtZ = nullptr;
   g.ybuf = nullptr;
   g.Xrm = nullptr;
   g.part = nullptr;
@@ -606,6 +733,31 @@ void smc_glm_release(SmcGlmPlan& g) {
 int smc_glm_launch(smc_model_s* m, SmcGlmPlan& g, int64_t C) {
   const smc_tape_stmt& s = m->stmts[g.stmt];
   cudaStream_t st = m->ctx->stream;
+  if (g.gram) {
+    GramEvalArgs e;
+    e.ZtZ = g.ZtZ;
+    e.beta = m->regs[s.src[1]].d.kind == SMC_REG_PARAM ? m->beta + m->regs[s.src[1]].d.aux * m->Cpad : m->regs[s.src[1]].dev;
+    e.Ldst = m->regs[s.dst].dev; e.Gdst = m->regs[s.aux2].dev; e.bad = m->bad;
+    e.N = g.N; e.C = C; e.Cpad = m->Cpad; e.M = g.M; e.acc = (s.flags & SMC_F_ACC) ? 1 : 0; e.par = g.par;
+    const int P = g.M + 1;
+    const size_t smem = ((size_t)P * P + (size_t)g.M * 32 + 512) * sizeof(double);
+    static bool gram_attr = false;
+    if (!gram_attr) {
+      SMC_CUDA(cudaFuncSetAttribute(k_glm_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+      gram_attr = true;
+    }
+    if (m->time_glm) SMC_CUDA(cudaEventRecord(m->ev0, st));
+    k_glm_gram<<<(unsigned)((C + 31) / 32), dim3(32, 8), smem, st>>>(e);
+    m->ctx->launches++;
+    if (m->time_glm) {
+      SMC_CUDA(cudaEventRecord(m->ev1, st));
+      SMC_CUDA(cudaEventSynchronize(m->ev1));
+      float ms = 0.f;
+      SMC_CUDA(cudaEventElapsedTime(&ms, m->ev0, m->ev1));
+      g.last_ms += ms;
+    }
+    return SMC_OK;
+  }
   const bool stream = use_stream(g.M, C);
   if (!stream && !g.Xrm) {
     SMC_CUDA(cudaMalloc(&g.Xrm, (size_t)g.N * g.MP * sizeof(double)));

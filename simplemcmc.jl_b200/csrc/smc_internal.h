@@ -64,6 +64,8 @@ struct SmcGlmPlan {  // one SMC_OP_GLM statement, prepared at finalize
   double* part = nullptr;  // partial (L,G) buffers [RS][MP+1][Cpad]
   int64_t part_cap = 0;
   float last_ms = 0.f;
+  int gram = 0;            // SMC_GLM_F_GRAM: evaluate from Z'Z with Z = [X, ytilde]
+  double* ZtZ = nullptr;   // [(M+1)][(M+1)] row major
 };
 
 // Micro-operation of the register-program VM (vm_exec.cu): the tape's LOADV/LOADS/STOREV/REDUCE instructions are

@@ -92,12 +92,14 @@ _ELEMENTWISE_UNARY = {"exp": "EXP", "log": "LOG", "sin": "SIN", "cos": "COS", "a
 
 
 class Lowering(object):
-    def __init__(self, model, init, data, gradient=True, ref_adjoint="assign", fuse=True, fuse_statements=True):
+    def __init__(self, model, init, data, gradient=True, ref_adjoint="assign", fuse=True, fuse_statements=True,
+                 sufficient_stats=False):
         self.vals, self.fwd, self.bwd = [], [], []
         self.env, self.data_slots, self.idx_tables = {}, [], []
         self.imm_cache = {}
         self.gradient, self.ref_adjoint, self.fuse = gradient, ref_adjoint, fuse
         self.fuse_statements = fuse_statements
+        self.sufficient_stats = sufficient_stats    # opt-in: Normal-identity GLM statements evaluate from X'X, X'y, y'y
         self.pars, self.bsize, self.init = [], 0, []
         self.data = data
         self._set_init(init)
@@ -436,6 +438,8 @@ class Lowering(object):
             if plan is None:
                 continue
             family, sign, par, y, lp_stmt, dead = plan
+            if self.sufficient_stats and family == GLM_NORMAL:
+                sign |= 4       # SMC_GLM_F_GRAM (include/simplemcmc_tape.h)
             G = self.new((M,), REG_CHAIN)
             glm = Stmt(OP["GLM"], lp_stmt.dst, [X, b, y], aux0=family, aux1=sign, aux2=G, imm=par)
             pos = self.fwd.index(lp_stmt)

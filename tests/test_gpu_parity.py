@@ -42,6 +42,27 @@ def test_rule_matrix(smc):
     assert worst <= TOL
 
 
+def test_rule_matrix_many_chains(smc):
+    """every 7th case of the matrix again with 37 chains in lockstep (chain lanes, element lanes and the per-chain
+    scalar staging of the register-program VM all in play): every chain must match the oracle at its own point"""
+    C = 37
+    rng = np.random.default_rng(11)
+    for k, (ex, data, x0) in enumerate(all_cases()):
+        if k % 7:
+            continue
+        model = "sum(%s)" % ex
+        ref = generate_model_function(model, data=data, gradient=True, x=x0)
+        f, n, pars, init = smc.generateModelFunction(model, gradient=True, chains=C, data=data, x=x0)
+        pts = init[None, :] * (1.0 + 1e-3 * rng.standard_normal((C, init.size)))   # stay inside the supports
+        lp, g = f(pts)
+        for c in range(0, C, 6):
+            lp0, g0 = ref(pts[c])
+            if np.isfinite(lp0):
+                _check(lp[c], g[c], lp0, g0)
+            else:
+                assert lp[c] == lp0 or (np.isnan(lp0) and not np.isfinite(lp[c]))
+
+
 @pytest.mark.parametrize("fuse", [True, False])
 @pytest.mark.parametrize("C", [1, 7, 64, 200])
 def test_linear_cfg1(smc, fuse, C):
@@ -98,6 +119,32 @@ def test_glm_few_chains_stream_path(smc, N, M, C):
         lp19, g19 = dev2.eval(np.vstack([betas, np.zeros((19 - C, M))]))
         assert np.allclose(lp19[:C], lp, rtol=1e-13, atol=0) and relerr(g19[:C], g) <= 1e-12
         dev.close(); dev2.close()
+
+
+def test_sufficient_statistics_variant(smc):
+    """opt-in `sufficient_stats=True`: a Normal identity-link regression evaluated from X'X, X'y, y'y (2*M^2 flops per chain
+    instead of 4*N*M).  Not the reference's arithmetic -- the tolerance is 1e-10 (cancellation in beta'X'X beta - 2 beta'X'y + y'y),
+    the default path stays the 1e-12 one -- but the same log-density, gradient and HMC trajectory."""
+    from simplemcmc_jl_b200 import api
+    for N, M, C in ((1000, 10, 7), (4099, 33, 40), (300, 64, 3)):
+        X, Y, _ = linear_data(N, M)
+        data = dict(X=X, Y=Y)
+        b = 0.2 * np.random.default_rng(N).standard_normal((C, M))
+        for lik in ("resid = Y - X * beta\nresid ~ Normal(0, 2.0)", "Y ~ Normal(X * beta, 0.5)", "eta = X * beta\neta ~ Normal(Y, 1.5)"):
+            model = "beta ~ Normal(0, 1.0)\n" + lik
+            ref = generate_model_function(model, data=data, gradient=True, beta=np.zeros(M))
+            low, dev = api._build(model, [("beta", np.zeros(M))], data, True, C, 0, "assign", sufficient_stats=True)
+            assert low.n_fused == 1
+            lp, g = dev.eval(b)
+            for c in range(C):
+                _check(lp[c], g[c], *ref(b[c]), tol=1e-10)
+            dev.close()
+    X, Y, _ = linear_data(2000, 10)
+    kw = dict(steps=40, burnin=0, isteps=3, stepsize=0.02, chains=16, seed=3, data=dict(X=X, Y=Y), beta=np.zeros(10))
+    r0 = smc.simpleHMC(LINEAR, **kw)
+    r1 = smc.simpleHMC(LINEAR, sufficient_stats=True, **kw)
+    assert np.array_equal(r0.accept, r1.accept)
+    assert relerr(r1.params["beta"], r0.params["beta"]) <= 1e-9
 
 
 def test_normal_glm_variants(smc):

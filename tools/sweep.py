@@ -10,7 +10,7 @@ from simplemcmc_jl_b200 import api
 from util import HIERARCHICAL, LINEAR, LOGISTIC, ORNSTEIN, SLEEPSTUDY2, hierarchical_data, linear_data, ou_data, sleepstudy_data
 
 out = {}
-which = sys.argv[1:] or ["cfg1", "cfg3", "cfg4", "cfg5"]
+which = sys.argv[1:] or ["cfg1", "cfg2s", "cfg3", "cfg4", "cfg5"]
 
 if "cfg1" in which:
     X, Y, _ = linear_data(1000, 10, 1)
@@ -28,6 +28,23 @@ if "cfg1" in which:
                          glm_tflops_algorithmic=4.0 * 1000 * 10 * C / (ms_glm * 1e-3) / 1e12, launches=raw["n_kernel_launches"]))
         dev.close()
     out["cfg1_linear_N1000_M10_hmc"] = rows
+
+if "cfg2s" in which:
+    # configs[1] with the opt-in sufficient-statistics rewrite (labelled extra: not the reference's arithmetic)
+    import bench
+    X, Y, _, _ = bench.make_data()
+    mode = bench.posterior_mode(X, Y)
+    rows = []
+    for C in (4096, 65536, 1 << 20):
+        low, dev = api._build(bench.MODEL, [("beta", np.zeros(64))], dict(X=X, Y=Y), True, C, 0, "assign", sufficient_stats=True)
+        init = mode[None, :] + 1e-3 * np.random.default_rng(1).standard_normal((C, 64))
+        steps = 400 if C <= 65536 else 40
+        dev.run("hmc", init, C, 5, 0, isteps=2, stepsize=bench.STEPSIZE, seed=1, store_draws=False, want=())
+        raw = dev.run("hmc", init, C, steps, 0, isteps=2, stepsize=bench.STEPSIZE, seed=2, store_draws=False, want=())
+        rows.append(dict(chains=C, steps=steps, leapfrog_chain_steps_per_s=raw["n_leapfrogs"] / (raw["device_ms"] * 1e-3),
+                         accept=float(raw["accept_rate"].mean()), launches=raw["n_kernel_launches"]))
+        dev.close()
+    out["cfg2_linear_N1e6_M64_hmc_sufficient_statistics"] = rows
 
 if "cfg3" in which:
     rng = np.random.default_rng(3)

@@ -139,10 +139,12 @@ __device__ __forceinline__ void record(const Recorder& R, long long step, long l
 
 // ---------------------------------------------------------------------------------------------- HMC
 // state0.v = randn ; update!(state0) ; state = state0     (src/samplers.jl:151-153)
-__global__ void __launch_bounds__(CXB * LY) k_hmc_begin(RngSrc rng, long long step, long long C, long long M, long long Cpad,
+// (the iteration number lives in device memory so that a whole iteration can be replayed as one CUDA graph)
+__global__ void __launch_bounds__(CXB * LY) k_hmc_begin(RngSrc rng, const long long* stepp, long long C, long long M, long long Cpad,
                                                       const double* b0, const double* g0, const double* l0, double* beta,
                                                       double* grad, double* logp, double* v, double* H0, double* H, int* active) {
   __shared__ double sh[LY * CXB];
+  const long long step = *stepp;
   const Ln L = lanes(C);
   const long long c = L.c;
   double ss = 0.0;
@@ -203,10 +205,11 @@ __global__ void __launch_bounds__(CXB * LY) k_leapfrog_post(long long C, long lo
 }
 
 // if rand() < exp(state.H - state0.H): state0 = state ; addToRes!   (src/samplers.jl:162-166)
-__global__ void __launch_bounds__(CXB * LY) k_hmc_accept(RngSrc rng, long long step, long long C, long long M, long long Cpad,
+__global__ void __launch_bounds__(CXB * LY) k_hmc_accept(RngSrc rng, const long long* stepp, long long C, long long M, long long Cpad,
                                                        const double* beta, const double* grad, const double* logp,
                                                        const double* H, const double* H0, double* b0, double* g0, double* l0,
                                                        Recorder R) {
+  const long long step = *stepp;
   const Ln L = lanes(C);
   const long long c = L.c;
   bool acc = false;
@@ -227,6 +230,8 @@ __global__ void __launch_bounds__(CXB * LY) k_hmc_accept(RngSrc rng, long long s
   if (acc && L.ly == 0) l0[c] = ll;
   record(R, step, c, M, Cpad, b0, ll, acc, L.ly);
 }
+
+__global__ void k_step_inc(long long* stepp) { *stepp += 1; }
 
 // ---------------------------------------------------------------------------------------------- RWM
 // jump = randn ; beta += S * jump                      (src/samplers.jl:93-95)
@@ -484,20 +489,55 @@ extern "C" int smc_hmc_run(smc_model_t m, const smc_sampler_config* cfg, const d
   SMC_TRY(r.A.alloc(&H0, Cpad));
   SMC_TRY(r.A.alloc(&H, Cpad));
   SMC_TRY(r.A.alloc(&active, Cpad));
+  long long* d_step;
+  SMC_TRY(r.A.alloc(&d_step, 1));
+  SMC_CUDA(cudaMemsetAsync(d_step, 0, sizeof(long long), st));
   int64_t evals = 1;
-  for (long long i = 0; i < cfg->steps; i++) {
-    k_hmc_begin<<<lgrid(C), lblock(), 0, st>>>(r.rng, i, C, M, Cpad, r.b0, r.g0, r.l0, m->beta, m->grad, m->logp, v, H0, H, active);
+  // one iteration = begin, isteps x (half kick + drift, evaluation, half kick), accept
+  auto iteration = [&]() -> int {
+    k_hmc_begin<<<lgrid(C), lblock(), 0, st>>>(r.rng, d_step, C, M, Cpad, r.b0, r.g0, r.l0, m->beta, m->grad, m->logp, v, H0, H, active);
     for (long long j = 0; j < cfg->isteps; j++) {
       k_leapfrog_pre<<<gride(C * M), 256, 0, st>>>(C, M, Cpad, cfg->stepsize, active, m->beta, m->grad, v);
-      m->ctx->launches += 1;
       SMC_TRY(smc_model_eval_device(m, C, true));
       k_leapfrog_post<<<lgrid(C), lblock(), 0, st>>>(C, M, Cpad, cfg->stepsize, active, m->grad, m->logp, v, H, r.nleap);
-      m->ctx->launches += 1;
-      evals++;
     }
-    k_hmc_accept<<<lgrid(C), lblock(), 0, st>>>(r.rng, i, C, M, Cpad, m->beta, m->grad, m->logp, H, H0, r.b0, r.g0, r.l0, r.R);
-    m->ctx->launches += 2;
+    k_hmc_accept<<<lgrid(C), lblock(), 0, st>>>(r.rng, d_step, C, M, Cpad, m->beta, m->grad, m->logp, H, H0, r.b0, r.g0, r.l0, r.R);
+    k_step_inc<<<1, 1, 0, st>>>(d_step);
+    m->ctx->launches += 3 + 2 * cfg->isteps;
+    return SMC_OK;
+  };
+  // The first two iterations run eagerly (the evaluation sizes its buffers, then captures its own graph); the third is
+  // captured whole -- the evaluation graph becomes a child node -- and every later iteration is one graph launch.
+  cudaGraphExec_t exec = nullptr;
+  int64_t per_iter = 0;
+  const bool can_graph = m->graphs_enabled && !(m->row_shard && m->ctx->nranks > 1 && !m->graph_nccl);
+  int rc = SMC_OK;
+  for (long long i = 0; i < cfg->steps && rc == SMC_OK; i++) {
+    if (exec) {
+      if (cudaGraphLaunch(exec, st) != cudaSuccess) { smc_set_error("cudaGraphLaunch failed in the HMC loop"); rc = SMC_ERR_CUDA; break; }
+      m->ctx->launches += per_iter;
+      evals += cfg->isteps;
+      continue;
+    }
+    if (i == 2 && can_graph && cfg->steps > 3 && cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
+      const int64_t l0 = m->ctx->launches, epoch = m->realloc_epoch;
+      int brc = iteration();
+      cudaGraph_t graph = nullptr;
+      cudaError_t e = cudaStreamEndCapture(st, &graph);
+      bool ok = (brc == SMC_OK && e == cudaSuccess && graph && epoch == m->realloc_epoch);
+      if (ok && cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) { ok = false; exec = nullptr; }
+      if (graph) cudaGraphDestroy(graph);
+      per_iter = m->ctx->launches - l0;
+      m->ctx->launches = l0;
+      if (ok) { i--; continue; }        // nothing has run yet: replay the captured iteration for this i
+      cudaGetLastError();
+      exec = nullptr;
+    }
+    rc = iteration();
+    evals += cfg->isteps;
   }
+  if (exec) { cudaStreamSynchronize(st); cudaGraphExecDestroy(exec); }
+  if (rc != SMC_OK) return rc;
   return run_finish(r, evals);
 }
 

@@ -158,6 +158,23 @@ def run_reference(args):
 
 
 def run_ours(args):
+    # stdout carries exactly one line (the JSON record): anything libraries print while the benchmark runs -- e.g. the
+    # "NCCL version ..." banner of the first communicator -- is sent to stderr at file-descriptor level
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        line = _run_ours(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
+    if line is not None:
+        print(json.dumps(line))
+        sys.stdout.flush()
+
+
+def _run_ours(args):
     import torch
     import torch.distributed as dist
     rank = int(os.environ.get("RANK", "0"))
@@ -288,9 +305,11 @@ def run_ours(args):
                            "wall_s_timed_region": wall},
                 "clocks": clk, "e2e": e2e, "gpu_launches": int(raw["n_kernel_launches"]), "roofline": roof, "cpu_baseline": cpu,
                 "labelled_extras": extra}
-        print(json.dumps(line))
+    else:
+        line = None
     if world > 1:
         dist.destroy_process_group()
+    return line
 
 
 def main():

@@ -620,8 +620,11 @@ struct Nuts {
   // outer tree
   double *mb, *mv, *mg, *ml, *pb, *pv, *pg, *pl;  // minus / plus edge states
   double *sb, *sg, *sl;                             // selected state of the iteration
-  // trajectory velocity (position/grad/logp of the trajectory live in the model's eval buffers)
-  double* tv;
+  // the trajectory being extended: position, velocity, gradient, log-density of every chain.  The model's evaluation
+  // buffers hold only the chains that are still building a tree, packed densely: chain c evaluates in column slot[c].
+  double *tb, *tv, *tg, *tl;
+  int* slot;
+  int* blocksum;
   // sub-tree under construction ("current") and the stack of completed sub-trees
   double *cnb, *cnv, *csb, *csg, *csl;  // current: near edge (beta, v), selected (beta, grad, logp)
   double *knb, *knv, *ksb, *ksg;        // stack[level][M][Cpad]
@@ -646,6 +649,48 @@ __device__ __forceinline__ void uturn_part(const double* minus_b, const double* 
 
 __device__ __forceinline__ void copy_vec(double* dst, const double* src, long long c, long long M, long long Cpad, int ly) {
   for (long long k = ly; k < M; k += LY) dst[k * Cpad + c] = src[k * Cpad + c];
+}
+
+// dense evaluation slots for the chains that are still building a tree: slot[c] = number of active chains before c
+__global__ void k_slot_count(const int* active, long long C, int* blocksum) {
+  long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int n = __syncthreads_count(c < C && active[c]);
+  if (threadIdx.x == 0) blocksum[blockIdx.x] = n;
+}
+__global__ void k_slot_scan(int* blocksum, int nb) {   // exclusive scan in place, one block
+  __shared__ int sh[1024];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < nb; base += 1024) {
+    int i = base + threadIdx.x;
+    int v = i < nb ? blocksum[i] : 0;
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+      int t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+      __syncthreads();
+      sh[threadIdx.x] += t;
+      __syncthreads();
+    }
+    int incl = sh[threadIdx.x];
+    if (i < nb) blocksum[i] = carry + incl - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += incl;
+    __syncthreads();
+  }
+}
+__global__ void k_slot_assign(const int* active, long long C, const int* blocksum, int* slot) {
+  __shared__ int wsum[8];
+  long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int a = (c < C && active[c]) ? 1 : 0;
+  const unsigned bal = __ballot_sync(0xffffffffu, a);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) wsum[w] = __popc(bal);
+  __syncthreads();
+  int off = blocksum[blockIdx.x];
+  for (int k = 0; k < w; k++) off += wsum[k];
+  if (a) slot[c] = off + __popc(bal & ((1u << lane) - 1u));
 }
 
 __global__ void k_nuts_init(long long C, Nuts T) {
@@ -689,15 +734,17 @@ __global__ void __launch_bounds__(CXB * LY) k_nuts_begin(RngSrc rng, long long s
 }
 
 __global__ void __launch_bounds__(CXB * LY) k_nuts_pre(RngSrc rng, long long step, long long C, long long M, long long Cpad,
-                                                     double* beta, double* grad, double* logp, Nuts T) {
+                                                     double* beta, int use_slots, Nuts T) {
   const Ln L = lanes(C);
   const long long c = L.c;
   const bool act = L.in && T.active[c];
   int newdbl = 0, dir = 0, k = 0;
   double eps = 0.0, lp_edge = 0.0;
+  long long slot = c;
   if (act) {
     newdbl = T.newdbl[c];
     eps = T.eps[c];
+    if (use_slots) slot = T.slot[c];
     if (newdbl) {
       k = T.ucount[c];
       double r = rng_uniform(rng, step, c, C, k);
@@ -715,12 +762,12 @@ __global__ void __launch_bounds__(CXB * LY) k_nuts_pre(RngSrc rng, long long ste
     const double* eg = dir < 0 ? T.mg : T.pg;
     for (long long q = L.ly; q < M; q += LY) {
       long long o = q * Cpad + c;
-      beta[o] = eb[o]; T.tv[o] = ev[o]; grad[o] = eg[o];
+      T.tb[o] = eb[o]; T.tv[o] = ev[o]; T.tg[o] = eg[o];
     }
     if (L.ly == 0) {
       T.ucount[c] = k + 1;
       T.dir[c] = dir;
-      logp[c] = lp_edge;
+      T.tl[c] = lp_edge;
       T.leaf[c] = 0;
       T.newdbl[c] = 0;
     }
@@ -728,14 +775,16 @@ __global__ void __launch_bounds__(CXB * LY) k_nuts_pre(RngSrc rng, long long ste
   double ve = dir * eps;
   for (long long q = L.ly; q < M; q += LY) {   // leapFrog, :52-53
     long long o = q * Cpad + c;
-    double vv = T.tv[o] + grad[o] * ve / 2.0;
+    double vv = T.tv[o] + T.tg[o] * ve / 2.0;
     T.tv[o] = vv;
-    beta[o] += ve * vv;
+    double b = T.tb[o] + ve * vv;
+    T.tb[o] = b;
+    beta[q * Cpad + slot] = b;   // the evaluation's input column of this chain
   }
 }
 
 __global__ void __launch_bounds__(CXB * LY) k_nuts_post(RngSrc rng, long long step, long long C, long long M, long long Cpad,
-                                                      const double* beta, const double* grad, const double* logp, Nuts T,
+                                                      const double* egrad, const double* elogp, int use_slots, Nuts T,
                                                       unsigned long long* nleap) {
   __shared__ double sh[2 * LY * CXB];
   const Ln L = lanes(C);
@@ -745,8 +794,12 @@ __global__ void __launch_bounds__(CXB * LY) k_nuts_post(RngSrc rng, long long st
   const long long LS = M * Cpad;  // stride between stack levels
   int dir = 1, leaf = 0, j = 0, ucount = 0;
   double eps = 0.0, u = 0.0, H0 = 0.0, ll = 0.0, ntot = 1.0;
+  const double* beta = T.tb;    // position and gradient of the trajectory's newest point
+  const double* grad = T.tg;
+  long long slot = c;
   if (act) {
-    dir = T.dir[c]; eps = T.eps[c]; u = T.u[c]; H0 = T.H0[c]; ll = logp[c];
+    if (use_slots) slot = T.slot[c];
+    dir = T.dir[c]; eps = T.eps[c]; u = T.u[c]; H0 = T.H0[c]; ll = elogp[slot];
     leaf = T.leaf[c]; j = T.j[c]; ucount = T.ucount[c]; ntot = T.ntot[c];
   }
   const double ve = dir * eps;
@@ -754,7 +807,9 @@ __global__ void __launch_bounds__(CXB * LY) k_nuts_post(RngSrc rng, long long st
   if (act)
     for (long long q = ly; q < M; q += LY) {   // second half kick + update!, :55-56
       long long o = q * Cpad + c;
-      double vv = T.tv[o] + grad[o] * ve / 2.0;
+      double gq = egrad[q * Cpad + slot];        // the evaluation's output column of this chain
+      T.tg[o] = gq;
+      double vv = T.tv[o] + gq * ve / 2.0;
       T.tv[o] = vv;
       ss += vv * vv;
     }
@@ -824,6 +879,7 @@ __global__ void __launch_bounds__(CXB * LY) k_nuts_post(RngSrc rng, long long st
     copy_vec(T.ksb + so, T.csb, c, M, Cpad, ly);
     copy_vec(T.ksg + so, T.csg, c, M, Cpad, ly);
     if (ly == 0) {
+      T.tl[c] = ll;
       T.ksl[sc] = csl;
       T.kn[sc] = n2; T.ka[sc] = a2; T.kna[sc] = na2;
       T.leaf[c] = leaf + 1;
@@ -917,16 +973,18 @@ extern "C" int smc_nuts_run(smc_model_t m, const smc_sampler_config* cfg, const 
   cudaStream_t st = m->ctx->stream;
   long long M = r.M, Cpad = r.Cpad, V = M * Cpad;
   Nuts T;
-  double** vecs[] = {&T.mb, &T.mv, &T.mg, &T.pb, &T.pv, &T.pg, &T.sb, &T.sg, &T.tv, &T.cnb, &T.cnv, &T.csb, &T.csg};
+  double** vecs[] = {&T.mb, &T.mv, &T.mg, &T.pb, &T.pv, &T.pg, &T.sb, &T.sg, &T.tb, &T.tv, &T.tg, &T.cnb, &T.cnv, &T.csb, &T.csg};
   for (auto pp : vecs) SMC_TRY(r.A.alloc(pp, V));
   double** stacks[] = {&T.knb, &T.knv, &T.ksb, &T.ksg};
   for (auto pp : stacks) SMC_TRY(r.A.alloc(pp, V * kMaxDepth));
   double** sstacks[] = {&T.ksl, &T.kn, &T.ka, &T.kna};
   for (auto pp : sstacks) SMC_TRY(r.A.alloc(pp, Cpad * kMaxDepth));
-  double** scal[] = {&T.ml, &T.pl, &T.sl, &T.csl, &T.u, &T.H0, &T.eps, &T.hbar, &T.lebar, &T.alast, &T.nalast, &T.ntot};
+  double** scal[] = {&T.ml, &T.pl, &T.sl, &T.csl, &T.tl, &T.u, &T.H0, &T.eps, &T.hbar, &T.lebar, &T.alast, &T.nalast, &T.ntot};
   for (auto pp : scal) SMC_TRY(r.A.alloc(pp, Cpad));
-  int** ints[] = {&T.j, &T.leaf, &T.dir, &T.active, &T.newdbl, &T.ucount, &T.moved};
+  int** ints[] = {&T.j, &T.leaf, &T.dir, &T.active, &T.newdbl, &T.ucount, &T.moved, &T.slot};
   for (auto pp : ints) SMC_TRY(r.A.alloc(pp, Cpad));
+  const int slot_blocks = (int)((C + 255) / 256);
+  SMC_TRY(r.A.alloc(&T.blocksum, slot_blocks + 1));
   SMC_TRY(r.A.alloc(&T.n_active, 4));
   SMC_TRY(r.A.alloc(&T.rounds_active, 4));
   SMC_CUDA(cudaMemsetAsync(T.rounds_active, 0, 4 * sizeof(unsigned long long), st));
@@ -948,19 +1006,42 @@ extern "C" int smc_nuts_run(smc_model_t m, const smc_sampler_config* cfg, const 
   int rc = SMC_OK;
   const int max_rounds = 1 << kMaxDepth;
   int prev_rounds = 0;
+  const char* nc = getenv("SMC_NO_COMPACT");
+  // (below a few thousand chains an evaluation is latency bound -- its cost does not shrink with the chain count -- and
+  // the three slot kernels per round would only add to it; SMC_COMPACT=1 forces packing for tests)
+  const char* fc = getenv("SMC_COMPACT");
+  const bool compact = !(nc && nc[0] == '1') && !(m->row_shard && m->ctx->nranks > 1) && (C >= 4096 || (fc && fc[0] == '1'));
+  long long eval_chains = 0;   // chain evaluations actually performed (sum of the evaluated widths)
   for (long long i = 0; i < cfg->steps && rc == SMC_OK; i++) {
     k_nuts_begin<<<lgrid(C), lblock(), 0, st>>>(r.rng, i, C, M, Cpad, r.b0, r.g0, r.l0, T);
     m->ctx->launches++;
     int launched = 0, rounds = 0;
+    // Lockstep evaluation only has to cover the chains that are still building a tree.  Their number never grows within
+    // an iteration, so the last count the host has seen is an upper bound: once it drops below ~2/3 of the chains, the
+    // active ones are given dense evaluation columns (slot[c]) and the tape is evaluated for that many (rounded up to a
+    // bucket so that only a few chain counts, i.e. evaluation graphs, occur).
+    long long active_ub = C;
+    const long long bucket = std::max<long long>(32, ((C + 15) / 16 + 31) / 32 * 32);
     auto launch_round = [&]() -> int {
       const int slot = launched & 1;
+      long long Ceval = C;
+      if (compact && active_ub * 3 <= C * 2) Ceval = std::min<long long>(C, (std::max<long long>(active_ub, 1) + bucket - 1) / bucket * bucket);
+      const int use_slots = Ceval < C ? 1 : 0;
       cudaMemsetAsync(T.n_active, 0, sizeof(int), st);
-      k_nuts_pre<<<lgrid(C), lblock(), 0, st>>>(r.rng, i, C, M, Cpad, m->beta, m->grad, m->logp, T);
+      if (use_slots) {
+        k_slot_count<<<slot_blocks, 256, 0, st>>>(T.active, C, T.blocksum);
+        k_slot_scan<<<1, 1024, 0, st>>>(T.blocksum, slot_blocks);
+        k_slot_assign<<<slot_blocks, 256, 0, st>>>(T.active, C, T.blocksum, T.slot);
+        m->ctx->launches += 3;
+      }
+      k_nuts_pre<<<lgrid(C), lblock(), 0, st>>>(r.rng, i, C, M, Cpad, m->beta, use_slots, T);
       m->ctx->launches++;
-      int e = smc_model_eval_device(m, C, true);
+      int e = smc_model_eval_device(m, Ceval, true);
       if (e != SMC_OK) return e;
       evals++;
-      k_nuts_post<<<lgrid(C), lblock(), 0, st>>>(r.rng, i, C, M, Cpad, m->beta, m->grad, m->logp, T, r.nleap);
+      eval_chains += Ceval;
+      (void)eval_chains;
+      k_nuts_post<<<lgrid(C), lblock(), 0, st>>>(r.rng, i, C, M, Cpad, m->grad, m->logp, use_slots, T, r.nleap);
       m->ctx->launches++;
       cudaMemcpyAsync(h_active + slot, T.n_active, sizeof(int), cudaMemcpyDeviceToHost, st);
       cudaEventRecord(ev[slot], st);
@@ -979,6 +1060,7 @@ extern "C" int smc_nuts_run(smc_model_t m, const smc_sampler_config* cfg, const 
       if (e != cudaSuccess) { smc_set_error("CUDA error '%s' in the NUTS loop", cudaGetErrorString(e)); rc = SMC_ERR_CUDA; break; }
       rounds++;
       if (h_active[slot] == 0 || rounds >= max_rounds) break;
+      active_ub = h_active[slot];
       if (launched == rounds) rc = launch_round();
     }
     if (rc != SMC_OK) break;

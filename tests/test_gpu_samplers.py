@@ -118,6 +118,35 @@ def test_nuts_trajectory_parity(smc):
         assert raw["n_leapfrogs"] == tot
 
 
+def test_nuts_active_chain_compaction_is_invisible(smc):
+    """late rounds of a NUTS iteration evaluate only the chains still building a tree, packed into dense columns.  For a
+    model whose evaluation has no cross-element reduction a chain's result cannot depend on its column, so draws, step
+    sizes, tree depths and leapfrog counts must be bit-identical to evaluating every chain every round; for a model with
+    reductions (their tree depends on the evaluated chain count) the first iterations agree to rounding."""
+    import os
+    def both(model, init, dat, C, steps):
+        out = []
+        os.environ["SMC_COMPACT"] = "1"           # (packing is normally reserved for >= 4096 chains)
+        for flag in ("1", "0"):
+            os.environ["SMC_NO_COMPACT"] = flag
+            low, dev = _build(model, init, dat, C)
+            out.append(dev.run("nuts", np.array(low.init), C, steps, 0, seed=5))
+            dev.close()
+        os.environ.pop("SMC_NO_COMPACT")
+        os.environ.pop("SMC_COMPACT")
+        return out
+    full, packed = both("x ~ Normal(1, 2)\ny ~ Gamma(2, 1)", [("x", 0.5), ("y", 1.0)], {}, 700, 40)
+    assert full["n_evals"] > 40 * 4                                     # trees of several doublings: packing was exercised
+    for k in ("draws", "epsilon", "jmax", "accept", "loglik", "mean", "m2"):
+        assert np.array_equal(full[k], packed[k]), k
+    assert full["n_leapfrogs"] == packed["n_leapfrogs"] and full["n_evals"] == packed["n_evals"]
+    data, nsub = sleepstudy_data()
+    init = [("intercept", 250.0), ("slope", 10.0), ("rand_int", np.zeros(nsub)), ("rand_slope", np.zeros(nsub))]
+    full, packed = both(SLEEPSTUDY2, init, data, 700, 6)
+    assert np.array_equal(full["jmax"][:3], packed["jmax"][:3])
+    assert relerr(packed["draws"][:3], full["draws"][:3]) < 1e-8
+
+
 def test_posterior_moments_linear(smc):
     """posterior mean / variance of the conjugate model within Monte-Carlo standard error"""
     X, Y, _ = linear_data()

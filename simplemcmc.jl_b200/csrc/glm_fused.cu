@@ -85,9 +85,12 @@ __device__ __forceinline__ void family_eval(double eta, double y, double inv_s, 
 // consecutive columns per half-warp, product 2 reads rows {rowmap(2q+s)} x 4 consecutive columns.
 __device__ __forceinline__ int rowmap(int n) { return n < 4 ? n : (n ^ 1); }
 
-template <int FAM, int MT, int NWC, int NWR, int MP8>
+// TRIM: the model has at most MP - 4 columns, so the last k-step of product 1 would multiply zeros and is skipped
+// (M = 10 in a 16-wide tile: 3 k-steps instead of 4, 7 DMMAs per row block instead of 8).
+template <int FAM, int MT, int NWC, int NWR, int MP8, int TRIM>
 __global__ void __launch_bounds__(NWC* NWR * 32, (MP8 <= 2 ? 2 : 1)) k_glm(GlmArgs a) {
   constexpr int MP = MP8 * 8, LD = MP + 4, NT = NWC * NWR * 32;
+  constexpr int KS = MP / 4 - TRIM;          // k-steps of product 1
   constexpr int RT = SMC_GLM_RT(MP8);        // rows per tile
   constexpr int NST = 4;    // stages; the copy of tile t+1 is in flight while tile t is consumed
   constexpr int TC = NWC * MT * 8;           // chains per CTA
@@ -106,12 +109,12 @@ __global__ void __launch_bounds__(NWC* NWR * 32, (MP8 <= 2 ? 2 : 1)) k_glm(GlmAr
   const int ntiles = row_end > row_begin ? (int)((row_end - row_begin + RT - 1) / RT) : 0;
 
   // B fragments: bfr[mt][ks] = beta[j = ks*4+q][chain = cbase + mt*8 + g]
-  double bfr[MT][MP / 4];
+  double bfr[MT][KS];
 #pragma unroll
   for (int mt = 0; mt < MT; mt++) {
     long long c = cbase + mt * 8 + g;
 #pragma unroll
-    for (int ks = 0; ks < MP / 4; ks++) {
+    for (int ks = 0; ks < KS; ks++) {
       int j = ks * 4 + q;
       double bv = (j < a.M && c < a.C) ? __ldg(a.beta + (long long)j * a.Cpad + c) : 0.0;
       bfr[mt][ks] = a.neg_beta ? -bv : bv;
@@ -167,7 +170,7 @@ __global__ void __launch_bounds__(NWC* NWR * 32, (MP8 <= 2 ? 2 : 1)) k_glm(GlmAr
 #pragma unroll
     for (int mt = 0; mt < MT; mt++) acc[mt][0] = acc[mt][1] = 0.0;
 #pragma unroll
-    for (int ks = 0; ks < MP / 4; ks++) {
+    for (int ks = 0; ks < KS; ks++) {
       double xb = xrow[ks * 4];
 #pragma unroll
       for (int mt = 0; mt < MT; mt++) dmma884(acc[mt][0], acc[mt][1], bfr[mt][ks], xb);
@@ -601,13 +604,13 @@ __global__ void __launch_bounds__(256) k_glm_gram(GramEvalArgs a) {
   }
 }
 
-template <int FAM, int MT, int NWC, int NWR, int MP8>
-int launch_cfg(const GlmArgs& a, int RS, cudaStream_t st) {
+template <int FAM, int MT, int NWC, int NWR, int MP8, int TRIM>
+int launch_cfg_t(const GlmArgs& a, int RS, cudaStream_t st) {
   constexpr int MP = MP8 * 8, LD = MP + 4, RT = SMC_GLM_RT(MP8), NST = 4, TC = NWC * MT * 8;
   size_t pipe = (size_t)NST * RT * (LD + 1) * sizeof(double);
   size_t epi = (size_t)(MP + 1) * TC * sizeof(double) + TC * sizeof(int);
   size_t smem = std::max(pipe, epi);
-  auto kern = k_glm<FAM, MT, NWC, NWR, MP8>;
+  auto kern = k_glm<FAM, MT, NWC, NWR, MP8, TRIM>;
   static bool attr_done = false;
   if (!attr_done) {
     SMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -616,6 +619,11 @@ int launch_cfg(const GlmArgs& a, int RS, cudaStream_t st) {
   dim3 grid((unsigned)((a.C + TC - 1) / TC), (unsigned)RS);
   kern<<<grid, NWC * NWR * 32, smem, st>>>(a);
   return SMC_OK;
+}
+
+template <int FAM, int MT, int NWC, int NWR, int MP8>
+int launch_cfg(const GlmArgs& a, int RS, cudaStream_t st) {
+  return a.M <= MP8 * 8 - 4 ? launch_cfg_t<FAM, MT, NWC, NWR, MP8, 1>(a, RS, st) : launch_cfg_t<FAM, MT, NWC, NWR, MP8, 0>(a, RS, st);
 }
 
 template <int FAM, int MP8>

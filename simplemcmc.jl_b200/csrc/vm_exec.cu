@@ -12,6 +12,7 @@
 // Reductions (`sum`, `dot`, vectorised logpdf: src/distribs.jl:97-105) accumulate per thread in element order, then
 // over the element lanes by a fixed tree, then over element chunks in k_vm_final: bit-reproducible for a given chain
 // count.
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
@@ -372,6 +373,9 @@ int smc_vm_plan(smc_model_s* m, SmcProgram& pr) {
       } else {
         tgt->red = in.aux0;
       }
+    } else if (in.op == SMC_OP_COPY && !(in.flags & SMC_F_ACC) && in.nsrc == 1 && cur[in.src[0]].mode == VM_LOCAL &&
+               cur[in.src[0]].idx == in.dst && cur[in.dst].mode == VM_LOCAL && cur[in.dst].idx == in.dst) {
+      // copying a name of slot d back into slot d: nothing to do
     } else if (in.op == SMC_OP_COPY && !(in.flags & SMC_F_ACC) && in.nsrc == 1 && cur[in.src[0]].mode != VM_NONE &&
                !(cur[in.src[0]].mode == VM_LOCAL && cur[in.src[0]].idx == in.dst)) {
       // copy propagation (the pass-through adjoints `dx = dx + ds` of src/diff.jl:29-38 are plain copies): the
@@ -383,9 +387,10 @@ int smc_vm_plan(smc_model_s* m, SmcProgram& pr) {
     } else {
       VmUop u;
       memset(&u, 0, sizeof(u));
-      materialise_aliases(in.dst);
       u.op = (uint8_t)in.op; u.dist = (uint8_t)in.aux0; u.darg = (uint8_t)in.aux1; u.nsrc = in.nsrc;
       if (in.op > 255 || in.aux0 > 255 || in.aux1 > 255) { smc_set_error("program: instruction %d has an operand out of range", i); return SMC_ERR_INVALID; }
+      // operands are resolved before other names of the destination slot get their own copy: the micro-op reads its
+      // operands before it writes, so it may keep reading the slot it is about to overwrite
       for (int k = 0; k < in.nsrc; k++) {
         const Src s = cur[in.src[k]];
         if (s.mode == VM_NONE) { smc_set_error("program: instruction %d reads an undefined local", i); return SMC_ERR_INVALID; }
@@ -398,6 +403,7 @@ int smc_vm_plan(smc_model_s* m, SmcProgram& pr) {
         u.flags |= VMF_ACC; u.mode[3] = s.mode; u.idx[3] = s.idx;
       }
       u.dst = in.dst;
+      materialise_aliases(in.dst);
       U.push_back(u);
       cur[in.dst].mode = VM_LOCAL; cur[in.dst].idx = in.dst;
       last_writer[in.dst] = (int)U.size() - 1;
@@ -429,6 +435,24 @@ int smc_vm_plan(smc_model_s* m, SmcProgram& pr) {
       if (u.flags & VMF_WRITE) u.dst = slot(u.dst);
     }
     pr.n_loc = n;
+  }
+  if (const char* dump = getenv("SMC_VM_DUMP")) {
+    if (dump[0] == '1') {
+      static const char* mode_name[] = {"-", "L", "S", "A"};
+      fprintf(stderr, "[vm] program n=%u: %zu instructions -> %zu micro-ops, %d locals, %zu scalars, %zu arrays\n", pr.h.n,
+              pr.instr.size(), U.size(), pr.n_loc, pr.scal_regs.size(), pr.desc_regs.size());
+      for (auto& u : U) {
+        fprintf(stderr, "[vm]   op %2u", u.op);
+        if (u.op == SMC_OP_LOGPDF || u.op == SMC_OP_DLOGPDF) fprintf(stderr, "(dist %u arg %u)", u.dist, u.darg);
+        for (int k = 0; k < 3; k++)
+          if (u.mode[k]) fprintf(stderr, " %s%u", mode_name[u.mode[k]], u.idx[k]);
+        if (u.flags & VMF_ACC) fprintf(stderr, " +=%s%u", mode_name[u.mode[3]], u.idx[3]);
+        if (u.flags & VMF_WRITE) fprintf(stderr, " -> L%u", u.dst);
+        if (u.flags & VMF_STORE) fprintf(stderr, " -> A%u", u.store);
+        if (u.flags & VMF_REDUCE) fprintf(stderr, " -> R%u", u.red);
+        fprintf(stderr, "\n");
+      }
+    }
   }
   return SMC_OK;
 }

@@ -354,7 +354,88 @@ class Lowering(object):
         for a in arrays:
             if a.numel != n:
                 raise ModelError("logpdf%s: array arguments of different lengths" % dist)
+        if self.sufficient_stats and dist == "Normal" and n >= 64:
+            lp = self._normal_affine(args, n)
+            if lp is not None:
+                return lp
         return self.emit("LOGPDF", args, (), aux0=DIST[dist], aux1=n)
+
+    # ---- opt-in sufficient statistics for a Normal density whose variate is affine in data arrays
+    def _producer(self, v):
+        for st in self.fwd:
+            if st.dst is v:
+                return st
+        return None
+
+    def _affine(self, v, depth=0):
+        """v (an array value) as sum_k coeff_k * D_k with D_k parameter-independent arrays (None = the all-ones array) and
+        coeff_k scalar values; -> list of (D_k, coeff_k) or None when v is not of that form"""
+        if depth > 32:
+            return None
+        if not v.is_array:
+            return [(None, v)]                                   # a scalar broadcast over the index space
+        if not v.varying:
+            return [(v, self.imm(1.0))]                          # data / header array
+        st = self._producer(v)
+        if st is None or st.flags:
+            return None
+        O = OP
+        if st.op in (O["ADD"], O["SUB"]):
+            a, b = self._affine(st.srcs[0], depth + 1), self._affine(st.srcs[1], depth + 1)
+            if a is None or b is None:
+                return None
+            if st.op == O["SUB"]:
+                b = [(d, self.unary("NEG", c) if c.kind != REG_IMM else self.imm(-c.imm)) for d, c in b]
+            return a + b
+        if st.op == O["NEG"]:
+            a = self._affine(st.srcs[0], depth + 1)
+            return None if a is None else [(d, self.unary("NEG", c) if c.kind != REG_IMM else self.imm(-c.imm)) for d, c in a]
+        if st.op in (O["MUL"], O["DIV"]) and st.dst.numel == v.numel:
+            x, y = st.srcs
+            if st.op == O["MUL"] and not x.is_array:
+                x, y = y, x                                       # array * scalar
+            if x.is_array and not y.is_array:
+                a = self._affine(x, depth + 1)
+                return None if a is None else [(d, self.binary("MUL" if st.op == O["MUL"] else "DIV", c, y)) for d, c in a]
+        return None
+
+    def _normal_affine(self, args, n):
+        """sum_e logpdfNormal(mu, sigma, r_e) with scalar mu, sigma and r = sum_k c_k D_k  ==
+        -(c' G c) / (2 sigma^2) - n log(sigma) - n log(sqrt(2 pi)),  G_kl = dot(D_k, D_l) evaluated once in the
+        let-header.  A different arithmetic from the reference's element loop (src/distribs.jl:97-105): opt-in only."""
+        mu, sigma, x = args
+        if mu.is_array or sigma.is_array or not x.is_array or not x.varying:
+            return None
+        nfwd = len(self.fwd)
+        terms = self._affine(x)
+        if terms is not None:
+            terms = terms + [(None, self.unary("NEG", mu) if mu.kind != REG_IMM else self.imm(-mu.imm))]
+            merged = {}
+            for d, c in terms:                                    # one coefficient per distinct array
+                key = None if d is None else d.vid
+                merged[key] = (d, c) if key not in merged else (d, self.binary("ADD", merged[key][1], c))
+            terms = [t for t in merged.values() if not (t[1].kind == REG_IMM and t[1].imm == 0.0)]
+        if terms is None or not (1 <= len(terms) <= 8) or any(d is not None and d.numel != n for d, _ in terms):
+            del self.fwd[nfwd:]                                   # drop the scalar helpers emitted while probing
+            return None
+
+        def gram(a, b):
+            if a is None and b is None:
+                return self.imm(float(n))
+            if a is None or b is None:
+                return self.emit("COPY", [b if a is None else a], ())     # sum(D): parameter independent -> header
+            return self.emit("MUL", [a, b], ())                            # dot(D_k, D_l)
+        q = None
+        for i, (di, ci) in enumerate(terms):
+            for j in range(i, len(terms)):
+                dj, cj = terms[j]
+                t = self.binary("MUL", self.binary("MUL", ci, cj), gram(di, dj))
+                if j > i:
+                    t = self.binary("MUL", self.imm(2.0), t)
+                q = t if q is None else self.binary("ADD", q, t)
+        two_s2 = self.binary("MUL", self.imm(2.0), self.binary("MUL", sigma, sigma))
+        lp = self.binary("SUB", self.unary("NEG", self.binary("DIV", q, two_s2)), self.binary("MUL", self.imm(float(n)), self.unary("LOG", sigma)))
+        return self.binary("SUB", lp, self.imm(float(n) * 0.91893853320467274178))
 
     # ---- refs: static index lists (column major, 0 based)
     def _index_list(self, node, dimlen):

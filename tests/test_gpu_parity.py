@@ -139,6 +139,18 @@ def test_sufficient_statistics_variant(smc):
             for c in range(C):
                 _check(lp[c], g[c], *ref(b[c]), tol=1e-10)
             dev.close()
+    # a Normal density whose variate is affine in data arrays with per-chain scalar coefficients (the Ornstein-Uhlenbeck
+    # residual x[t] - x[t-1]*fac - mu*(1-fac)): the whole likelihood becomes a quadratic form in a 3x3 Gram matrix
+    x = ou_data(5000)
+    ref = generate_model_function(ORNSTEIN, data=dict(x=x), gradient=True, tau=20.0, mu=10.0, sigma=0.1)
+    f, n, pars, init = smc.generateModelFunction(ORNSTEIN, gradient=True, chains=9, data=dict(x=x), sufficient_stats=True,
+                                                 tau=20.0, mu=10.0, sigma=0.1)
+    assert not any(st.op == 32 and st.aux1 > 1 for st in f.lowered.fwd)          # no length-T density statement is left
+    pts = init[None, :] * (1 + 0.05 * np.random.default_rng(2).standard_normal((9, 3)))
+    lp, g = f(pts)
+    for c in range(9):
+        lp0, g0 = ref(pts[c])
+        assert abs(lp[c] - lp0) <= 1e-9 * abs(lp0) and relerr(g[c], g0) <= 1e-7, (lp[c], lp0, g[c], g0)
     X, Y, _ = linear_data(2000, 10)
     kw = dict(steps=40, burnin=0, isteps=3, stepsize=0.02, chains=16, seed=3, data=dict(X=X, Y=Y), beta=np.zeros(10))
     r0 = smc.simpleHMC(LINEAR, **kw)

@@ -118,5 +118,16 @@ if "cfg5" in which:
                              launches=raw["n_kernel_launches"]))
             dev.close()
     out["cfg5_ornstein_T1e6"] = rows
+    # labelled extra: the same model with the opt-in sufficient-statistics rewrite (3x3 Gram matrix of [x[t], x[t-1], 1])
+    rows = []
+    for C in (64, 4096, 65536):
+        low, dev = api._build(ORNSTEIN, init, dict(x=x), True, C, 0, "assign", sufficient_stats=True)
+        kw = dict(isteps=2, stepsize=1e-4)
+        dev.run("hmc", np.array(low.init), C, 3, 0, seed=3, store_draws=False, want=(), **kw)
+        raw = dev.run("hmc", np.array(low.init), C, 200, 0, seed=1, store_draws=False, want=(), **kw)
+        rows.append(dict(sampler="hmc", chains=C, steps=200, evals_per_s=C * (raw["n_evals"] - 1) / (raw["device_ms"] * 1e-3),
+                         accept=float(raw["accept_rate"].mean()), launches=raw["n_kernel_launches"]))
+        dev.close()
+    out["cfg5_ornstein_T1e6_sufficient_statistics"] = rows
 
 print(json.dumps(out, indent=1))

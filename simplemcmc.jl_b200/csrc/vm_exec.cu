@@ -554,7 +554,7 @@ int smc_vm_launch(smc_model_s* m, SmcProgram& pr, int64_t C, int* bad) {
   // V = elements a thread processes per decode of a micro-op: as many as the locals' shared-memory budget allows
   const long long per_thread = (a.chunk + eyn - 1) / eyn;
   const size_t fixed = nu2 * 16 + (size_t)pr.n_ot * 32 + std::max<size_t>(1, ns) * tcc * 8 + (size_t)a.n_red * NT * 8;
-  const size_t budget = 96 * 1024;
+  const size_t budget = 96 * 1024;   // two blocks per SM (three blocks at 80 registers measured slower: spills)
   long long vmax = pr.n_loc > 0 ? (long long)((budget > fixed ? budget - fixed : 0) / ((size_t)pr.n_loc * NT * 8)) : 32;
   vmax = std::max<long long>(1, std::min<long long>(vmax, 32));
   long long passes = (per_thread + vmax - 1) / vmax;

@@ -540,14 +540,15 @@ int smc_vm_launch(smc_model_s* m, SmcProgram& pr, int64_t C, int* bad) {
   // element lanes of the block and over grid chunks only as far as needed to put ~2 blocks on every SM, so that a
   // thread keeps as many elements as possible (a micro-op is decoded once per thread and pass).
   const long long want_threads = 2LL * m->ctx->sm_count * NT;
-  long long lanes = std::max<long long>(1, std::min<long long>((want_threads + C - 1) / C, std::max<long long>(1, a.n / 4)));
+  // (rounded down: one full wave of blocks beats one and a fraction)
+  long long lanes = std::max<long long>(1, std::min<long long>(want_threads / C, std::max<long long>(1, a.n / 4)));
   int tcc = 1;
   while (tcc < C && tcc < NT) tcc <<= 1;                 // every chain of a small run in one block ...
   while (tcc > 32 && NT / tcc < lanes) tcc >>= 1;        // ... but give up chain width for element lanes down to a warp
   a.tcc = tcc;
   const int eyn = NT / tcc;
   const long long chain_tiles = (C + tcc - 1) / tcc;
-  long long S = std::max<long long>(1, std::min<long long>((lanes + eyn - 1) / eyn, (a.n + (long long)eyn * 4 - 1) / ((long long)eyn * 4)));
+  long long S = std::max<long long>(1, std::min<long long>(lanes / eyn, (a.n + (long long)eyn * 4 - 1) / ((long long)eyn * 4)));
   a.chunk = (a.n + S - 1) / S;
   S = (a.n + a.chunk - 1) / a.chunk;
   a.S = (int)S;

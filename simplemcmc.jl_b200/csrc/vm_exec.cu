@@ -58,9 +58,10 @@ __device__ __noinline__ double vm_apply_slow(int op, int dist, int k, double a, 
   return smc_apply(op, dist, k, a, b, c);
 }
 
-// One pass of a micro-op over the vc elements a thread owns (element v at pointer + v * stride).  The two common
-// shapes -- result written to a local, result only reduced -- read the operands of four elements before anything is
-// written, so a destination slot may coincide with a source slot and the loads of a batch are independent.
+// One pass of a micro-op over the vc elements a thread owns (element v at pointer + v * stride).  The operands of four
+// elements are read before anything is written, so a destination slot may coincide with a source slot and the loads of a
+// batch are independent; the side effects (accumulate operand, local write, array store, reduction) are uniform
+// per-micro-op flags.
 // EXPR sees p, q (and w when W3) = operands 0, 1, 2 of the element.  The macros are expanded twice: once where every
 // operand lives in shared memory (32-bit indices into the block's shared array: LDS / STS with cheap addressing),
 // once with generic 64-bit pointers (a tape array in HBM among the operands).
@@ -80,38 +81,26 @@ __device__ __noinline__ double vm_apply_slow(int op, int dist, int k, double a, 
 #define VM_RUN(W3, EXPR)                                                                                \
   {                                                                                                     \
     int v = 0;                                                                                          \
-    if (fl == VMF_WRITE) {                                                                              \
-      for (; v + 4 <= vc; v += 4) {                                                                     \
-        VM_LOAD4(W3, EXPR)                                                                              \
-        pd[(v + 0) * NT] = r_0; pd[(v + 1) * NT] = r_1; pd[(v + 2) * NT] = r_2; pd[(v + 3) * NT] = r_3; \
+    double rsum = 0.0;                                                                                  \
+    for (; v + 4 <= vc; v += 4) {                                                                       \
+      VM_LOAD4(W3, EXPR)                                                                                \
+      if (fl & VMF_ACC) {                                                                               \
+        const double a_0 = pa[(v + 0) * sa], a_1 = pa[(v + 1) * sa], a_2 = pa[(v + 2) * sa], a_3 = pa[(v + 3) * sa]; \
+        r_0 = a_0 + r_0; r_1 = a_1 + r_1; r_2 = a_2 + r_2; r_3 = a_3 + r_3;                             \
       }                                                                                                 \
-      for (; v < vc; v++) {                                                                             \
-        VM_LOAD1(W3)                                                                                    \
-        pd[v * NT] = (EXPR);                                                                            \
-      }                                                                                                 \
-    } else if (fl == VMF_REDUCE) {                                                                      \
-      double rsum = 0.0;                                                                                \
-      for (; v + 4 <= vc; v += 4) {                                                                     \
-        VM_LOAD4(W3, EXPR)                                                                              \
-        rsum += r_0; rsum += r_1; rsum += r_2; rsum += r_3;                                             \
-      }                                                                                                 \
-      for (; v < vc; v++) {                                                                             \
-        VM_LOAD1(W3)                                                                                    \
-        rsum += (EXPR);                                                                                 \
-      }                                                                                                 \
-      Rd[uo.red * NT + tid] += rsum;                                                                    \
-    } else {                                                                                            \
-      double rsum = 0.0;                                                                                \
-      for (; v < vc; v++) {                                                                             \
-        VM_LOAD1(W3)                                                                                    \
-        double r = (EXPR);                                                                              \
-        if (fl & VMF_ACC) r = pa[v * sa] + r;                                                           \
-        if (fl & VMF_WRITE) pd[v * NT] = r;                                                             \
-        if (fl & VMF_STORE) ps[v * ss] = r;                                                             \
-        rsum += r;                                                                                      \
-      }                                                                                                 \
-      if (fl & VMF_REDUCE) Rd[uo.red * NT + tid] += rsum;                                               \
+      if (fl & VMF_WRITE) { pd[(v + 0) * NT] = r_0; pd[(v + 1) * NT] = r_1; pd[(v + 2) * NT] = r_2; pd[(v + 3) * NT] = r_3; } \
+      if (fl & VMF_STORE) { ps[(v + 0) * ss] = r_0; ps[(v + 1) * ss] = r_1; ps[(v + 2) * ss] = r_2; ps[(v + 3) * ss] = r_3; } \
+      if (fl & VMF_REDUCE) { rsum += r_0; rsum += r_1; rsum += r_2; rsum += r_3; }                      \
     }                                                                                                   \
+    for (; v < vc; v++) {                                                                               \
+      VM_LOAD1(W3)                                                                                      \
+      double r = (EXPR);                                                                                \
+      if (fl & VMF_ACC) r = pa[v * sa] + r;                                                             \
+      if (fl & VMF_WRITE) pd[v * NT] = r;                                                               \
+      if (fl & VMF_STORE) ps[v * ss] = r;                                                               \
+      rsum += r;                                                                                        \
+    }                                                                                                   \
+    if (fl & VMF_REDUCE) Rd[uo.red * NT + tid] += rsum;                                                 \
   }
 
 // the operation table; p0/p1/p2 (sources), pd (local destination), pa (accumulate operand), ps (array destination) and

@@ -8,7 +8,8 @@
  *   smc_hmc_run                                the main loop of simpleHMC, src/samplers.jl:146-167
  *   smc_rwm_run                                the main loop of simpleRWM, src/samplers.jl:89-113
  *   smc_nuts_run                               the main loop of simpleNUTS, src/samplers.jl:199-310
- *   smc_chain_moments                          new (many chains): per-chain Welford moments for R-hat
+ *   smc_run_output.mean/m2/first/lag1          setRes/addToRes!/calcStats!, src/samplers.jl:330-374: per-chain Welford
+ *                                              moments and lag-1 sums on the device (ESS, R-hat without the draws)
  * The only FFI the reference itself has is the per-element ccall into libRmath (src/distribs.jl:65-67);
  * those nine densities are device functions inside the library.
  *
@@ -30,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SMC_ABI_VERSION 1
+#define SMC_ABI_VERSION 2
 
 typedef enum {
   SMC_OK = 0,
@@ -102,6 +103,10 @@ typedef struct {
   int64_t n_evals;         /* lockstep evaluations of the tape */
   int64_t n_leapfrogs;     /* sum over chains of leapfrogs actually taken */
   int64_t n_kernel_launches;
+  /* ABI 2: lag-1 statistics accumulated on the device, so that calcStats! (src/samplers.jl:352-374: ESS from the lag-1
+   * autocorrelation) needs no draws on the host.  With x_t the t-th recorded draw:                                    */
+  double* first;   /* [C][M] x_0, or NULL                                                                            */
+  double* lag1;    /* [C][M] sum_{t>=1} (x_t - x_0)(x_{t-1} - x_0), or NULL                                          */
 } smc_run_output;
 
 int smc_hmc_run(smc_model_t m, const smc_sampler_config* cfg, const double* init, int64_t C, smc_run_output* out);

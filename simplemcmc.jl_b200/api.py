@@ -146,6 +146,20 @@ def _finish(res, pars, raw, chains, t0, store_draws):
         B = n * np.var(raw["mean"], axis=0, ddof=1)
         with np.errstate(divide="ignore", invalid="ignore"):
             res.misc["rhat"] = np.sqrt(((n - 1) / n * W + B / n) / W)
+    if n >= 3 and "lag1" in raw:
+        # calcStats! (src/samplers.jl:352-374) from the statistics the device accumulated -- no draws needed.  With
+        # y_t = x_t - x_0:  a = y[1:], b = y[:-1],  cov = (sum a*b - sum(a)*sum(b)/(n-1)) / (n-2),  var = m2/(n-1)
+        sy = n * (raw["mean"] - raw["first"])
+        sb = sy - (raw["final_state"] - raw["first"])
+        cov = (raw["lag1"] - sy * sb / (n - 1)) / (n - 2)
+        var = raw["m2"] / (n - 1)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            fac = np.abs(cov) / var
+            ess = np.where(var > 0, n * np.maximum(0.0, 1.0 - fac) / (1.0 + fac), 0.0)      # [C][M]
+        per_comp = ess.sum(axis=0)
+        res.misc["ess_by_chain"] = ess
+        res.ess = (float(per_comp.min()), float(per_comp.max()))
+        res.essBySec = (res.ess[0] / res.time, res.ess[1] / res.time)
     if "loglik" in raw:
         res.loglik = raw["loglik"][:, 0] if chains == 1 else raw["loglik"]
         res.accept = raw["accept"][:, 0] if chains == 1 else raw["accept"]
@@ -168,6 +182,7 @@ def _finish(res, pars, raw, chains, t0, store_draws):
                 fac = np.abs(cov) / var
                 ess = np.where(var > 0, n * np.maximum(0.0, 1.0 - fac) / (1.0 + fac), 0.0)
             per_comp = ess.sum(axis=0)
+            res.misc["ess_by_chain_from_draws"] = ess
             lo, hi = per_comp.min(), per_comp.max()
             res.ess = (lo, hi)
             res.essBySec = (lo / res.time, hi / res.time)

@@ -30,7 +30,8 @@ class RunOutput(ctypes.Structure):
     _fields_ = [("draws", c_double_p), ("loglik", c_double_p), ("accept", c_double_p), ("final_state", c_double_p),
                 ("accept_rate", c_double_p), ("mean", c_double_p), ("m2", c_double_p), ("epsilon", c_double_p),
                 ("jmax", c_double_p), ("device_ms", ctypes.c_double), ("n_evals", ctypes.c_int64),
-                ("n_leapfrogs", ctypes.c_int64), ("n_kernel_launches", ctypes.c_int64)]
+                ("n_leapfrogs", ctypes.c_int64), ("n_kernel_launches", ctypes.c_int64),
+                ("first", c_double_p), ("lag1", c_double_p)]
 
 
 EXPORTS = ["smc_abi_version", "smc_last_error", "smc_ctx_create", "smc_ctx_destroy", "smc_ctx_comm_init",
@@ -205,8 +206,11 @@ class DeviceModel(object):
         res["accept_rate"] = np.empty(C)
         res["mean"] = np.empty((C, M))
         res["m2"] = np.empty((C, M))
+        res["first"] = np.empty((C, M))
+        res["lag1"] = np.empty((C, M))
         out.final_state, out.accept_rate = dptr(res["final_state"]), dptr(res["accept_rate"])
         out.mean, out.m2 = dptr(res["mean"]), dptr(res["m2"])
+        out.first, out.lag1 = dptr(res["first"]), dptr(res["lag1"])
         if sampler == "nuts":
             res["epsilon"] = np.empty((steps, C))
             res["jmax"] = np.empty((steps, C))

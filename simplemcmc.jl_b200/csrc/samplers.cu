@@ -112,6 +112,9 @@ struct Recorder {
   double* accept;  // [samples][Cpad]
   double* mean;    // [M][Cpad]
   double* m2;      // [M][Cpad]
+  double* first;   // [M][Cpad] first recorded draw x_0
+  double* prev;    // [M][Cpad] previous recorded draw
+  double* lag1;    // [M][Cpad] sum_{t>=1} (x_t - x_0)(x_{t-1} - x_0): lag-1 statistics of calcStats! without the draws
   double* nacc;    // [Cpad]
   long long burnin;
 };
@@ -134,6 +137,13 @@ __device__ __forceinline__ void record(const Recorder& R, long long step, long l
     mu += d / n;
     R.mean[j * Cpad + c] = mu;
     R.m2[j * Cpad + c] += d * (x - mu);
+    if (s == 0) {
+      R.first[j * Cpad + c] = x;
+    } else {
+      double x0 = R.first[j * Cpad + c];
+      R.lag1[j * Cpad + c] += (x - x0) * (R.prev[j * Cpad + c] - x0);
+    }
+    R.prev[j * Cpad + c] = x;
   }
 }
 
@@ -374,6 +384,11 @@ int run_setup(Run& r, const double* init, bool need_grad, long long nu) {
   if (r.out->accept) SMC_TRY(r.A.alloc(&r.R.accept, r.samples * Cpad));
   SMC_TRY(r.A.alloc(&r.R.mean, M * Cpad));
   SMC_TRY(r.A.alloc(&r.R.m2, M * Cpad));
+  SMC_TRY(r.A.alloc(&r.R.first, M * Cpad));
+  SMC_TRY(r.A.alloc(&r.R.prev, M * Cpad));
+  SMC_TRY(r.A.alloc(&r.R.lag1, M * Cpad));
+  SMC_CUDA(cudaMemsetAsync(r.R.first, 0, M * Cpad * sizeof(double), st));
+  SMC_CUDA(cudaMemsetAsync(r.R.lag1, 0, M * Cpad * sizeof(double), st));
   SMC_TRY(r.A.alloc(&r.R.nacc, Cpad));
   SMC_CUDA(cudaMemsetAsync(r.R.mean, 0, M * Cpad * sizeof(double), st));
   SMC_CUDA(cudaMemsetAsync(r.R.m2, 0, M * Cpad * sizeof(double), st));
@@ -464,6 +479,8 @@ int run_finish(Run& r, int64_t n_evals) {
   SMC_TRY(copy_out_blocks(r, r.b0, r.out->final_state, 1, r.M));
   SMC_TRY(copy_out_blocks(r, r.R.mean, r.out->mean, 1, r.M));
   SMC_TRY(copy_out_blocks(r, r.R.m2, r.out->m2, 1, r.M));
+  SMC_TRY(copy_out_blocks(r, r.R.first, r.out->first, 1, r.M));
+  SMC_TRY(copy_out_blocks(r, r.R.lag1, r.out->lag1, 1, r.M));
   if (r.out->accept_rate) {
     k_div<<<gride(r.C), 256, 0, st>>>(r.R.nacc, r.C, (double)r.samples);
     m->ctx->launches++;

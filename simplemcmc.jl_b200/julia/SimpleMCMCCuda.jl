@@ -78,6 +78,7 @@ mutable struct RunOutput        # smc_run_output
     draws::Ptr{Float64}; loglik::Ptr{Float64}; accept::Ptr{Float64}; final_state::Ptr{Float64}; accept_rate::Ptr{Float64}
     mean::Ptr{Float64}; m2::Ptr{Float64}; epsilon::Ptr{Float64}; jmax::Ptr{Float64}
     device_ms::Float64; n_evals::Int64; n_leapfrogs::Int64; n_kernel_launches::Int64
+    first::Ptr{Float64}; lag1::Ptr{Float64}       # ABI 2: lag-1 statistics for calcStats! (ESS) without the draws
 end
 
 for (jl, sym) in ((:hmc_run, :smc_hmc_run), (:rwm_run, :smc_rwm_run), (:nuts_run, :smc_nuts_run))

@@ -43,8 +43,8 @@ def test_library_loads_and_exports_the_whole_abi():
     for name in declared:
         assert hasattr(lib, name), name
     assert declared == set(capi.EXPORTS)
-    assert lib.smc_abi_version() == 1
-    assert ctypes.sizeof(capi.SamplerConfig) == 80 and ctypes.sizeof(capi.RunOutput) == 104
+    assert lib.smc_abi_version() == 2
+    assert ctypes.sizeof(capi.SamplerConfig) == 80 and ctypes.sizeof(capi.RunOutput) == 120
 
 
 def test_ctx_create_fails_loudly_without_a_gpu():

@@ -25,6 +25,12 @@ namespace {
 // 32.72 ms per cfg2 launch against 32.07 ms for 64-row tiles with four stages, so the barrier is not what is left.)
 #define SMC_GLM_RT(MP8) ((MP8) >= 4 ? 64 : 128)
 
+struct GlmPub {    // where (L, G) go when a kernel may write the tape registers itself
+  double* Ldst;
+  double* Gdst;
+  int acc, on;
+};
+
 struct GlmArgs {
   const double* X;     // [N][MP] row major, zero padded
   const double* y;     // [N] response as consumed by the family (sign-normalised)
@@ -36,6 +42,7 @@ struct GlmArgs {
   double par;
   int neg_beta;  // BERNOULLI with prob = 1/(1+exp(-eta)): the contraction runs on -beta, so it yields u = -eta directly
   int neg_out;   // ... and G = X' dl/deta = -(X' dl/du)
+  GlmPub pub;    // single row split on a single rank: the epilogue publishes (L, G) itself, no partial buffer / reduce kernel
 };
 
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
@@ -287,7 +294,16 @@ __global__ void __launch_bounds__(NWC* NWR * 32, (MP8 <= 2 ? 2 : 1)) k_glm(GlmAr
     } else if (a.neg_out) {
       v = -v;
     }
-    part[(long long)j * a.Cpad + c] = v;
+    if (a.pub.on) {
+      if (j == MP) {
+        if (a.bad[c] || !(v > -INFINITY)) { a.bad[c] = 1; v = 0.0; }
+        a.pub.Ldst[c] = a.pub.acc ? a.pub.Ldst[c] + v : v;
+      } else if (j < a.M) {
+        a.pub.Gdst[(long long)j * a.Cpad + c] = v;
+      }
+    } else {
+      part[(long long)j * a.Cpad + c] = v;
+    }
   }
   (void)bs;
 }
@@ -296,11 +312,6 @@ __global__ void __launch_bounds__(NWC* NWR * 32, (MP8 <= 2 ? 2 : 1)) k_glm(GlmAr
 //   publish: write (L, G) straight into the tape registers (one kernel per GLM statement on a single rank), or
 //   stage:   out[j][c] = sum (j = MP row is L) for the NCCL all-reduce of row-sharded models; a chain flagged bad gets
 //            L = -inf there so that the flag survives the cross-rank sum.
-struct GlmPub {
-  double* Ldst;
-  double* Gdst;
-  int acc, on;
-};
 __device__ __forceinline__ void glm_emit(double t, long long j, long long c, int M, int MP, long long Cpad, int* bad, double* out,
                                          const GlmPub& pub) {
   if (pub.on) {
@@ -795,6 +806,9 @@ int smc_glm_launch(smc_model_s* m, SmcGlmPlan& g, int64_t C) {
   a.N = g.N; a.rows_per_split = rows_per_split; a.C = C; a.Cpad = m->Cpad; a.M = g.M;
   a.par = g.par;
   a.neg_beta = a.neg_out = (g.family == SMC_GLM_BERNOULLI && (g.sign_neg & 1)) ? 1 : 0;
+  const bool sharded = m->row_shard && m->ctx->nranks > 1;
+  a.pub.Ldst = m->regs[s.dst].dev; a.pub.Gdst = m->regs[s.aux2].dev; a.pub.acc = (s.flags & SMC_F_ACC) ? 1 : 0;
+  a.pub.on = (!stream && RS == 1 && !sharded) ? 1 : 0;
   if (m->time_glm) SMC_CUDA(cudaEventRecord(m->ev0, st));
   int rc;
   if (stream) {
@@ -823,7 +837,7 @@ int smc_glm_launch(smc_model_s* m, SmcGlmPlan& g, int64_t C) {
   double* out = g.part + (int64_t)RS * (g.MP + 1) * m->Cpad;
   const SmcReg& Lr = m->regs[s.dst];
   const SmcReg& Gr = m->regs[s.aux2];
-  const bool sharded = m->row_shard && m->ctx->nranks > 1;
+  if (a.pub.on) { m->ctx->launches += 1; return SMC_OK; }   // the kernel published (L, G) itself
   GlmPub pub;
   pub.Ldst = Lr.dev; pub.Gdst = Gr.dev; pub.acc = (s.flags & SMC_F_ACC) ? 1 : 0; pub.on = sharded ? 0 : 1;
   long long tot = (long long)(g.MP + 1) * C;

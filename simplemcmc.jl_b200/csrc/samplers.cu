@@ -43,42 +43,48 @@ __device__ __forceinline__ double rng_uniform(const RngSrc& r, long long step, l
 // its chain (momentum pairs p = ly, ly + LY, ... when drawing normals).  Per-chain scalars are read by all lanes into
 // registers, recomputed identically, and committed by lane 0; sums over components go through shared memory in lane
 // order (deterministic).
-constexpr int LY = 8;
-constexpr int CXB = 32;
+// LY is a template parameter: 8 lanes (32 chains per block) up to a few ten thousand chains, where parallelism over the
+// components matters; 1 lane (256 chains per block) beyond, where each row of the state is then read in 2 KB runs per
+// block (measured on cfg1 with 2^20 chains: begin 216 -> 127 us, post 110 -> 51 us).
+#define SMC_CXB (256 / LY)
 
 struct Ln {
   long long c;
   int ly;
   bool in;
 };
+template <int LY>
 __device__ __forceinline__ Ln lanes(long long C) {
   Ln L;
-  L.c = (long long)blockIdx.x * CXB + threadIdx.x;
+  L.c = (long long)blockIdx.x * SMC_CXB + threadIdx.x;
   L.ly = threadIdx.y;
   L.in = L.c < C;
   return L;
 }
-__device__ __forceinline__ double ysum(double v, double* sh) {   // sh[LY * CXB]; call from every thread of the block
-  sh[threadIdx.y * CXB + threadIdx.x] = v;
+template <int LY>
+__device__ __forceinline__ double ysum(double v, double* sh) {   // sh[LY * SMC_CXB]; call from every thread of the block
+  sh[threadIdx.y * SMC_CXB + threadIdx.x] = v;
   __syncthreads();
   double t = 0.0;
 #pragma unroll
-  for (int y = 0; y < LY; y++) t += sh[y * CXB + threadIdx.x];
+  for (int y = 0; y < LY; y++) t += sh[y * SMC_CXB + threadIdx.x];
   __syncthreads();
   return t;
 }
-__device__ __forceinline__ void ysum2(double& a, double& b, double* sh) {   // sh[2 * LY * CXB]
-  sh[threadIdx.y * CXB + threadIdx.x] = a;
-  sh[LY * CXB + threadIdx.y * CXB + threadIdx.x] = b;
+template <int LY>
+__device__ __forceinline__ void ysum2(double& a, double& b, double* sh) {   // sh[2 * LY * SMC_CXB]
+  sh[threadIdx.y * SMC_CXB + threadIdx.x] = a;
+  sh[LY * SMC_CXB + threadIdx.y * SMC_CXB + threadIdx.x] = b;
   __syncthreads();
   double ta = 0.0, tb = 0.0;
 #pragma unroll
-  for (int y = 0; y < LY; y++) { ta += sh[y * CXB + threadIdx.x]; tb += sh[LY * CXB + y * CXB + threadIdx.x]; }
+  for (int y = 0; y < LY; y++) { ta += sh[y * SMC_CXB + threadIdx.x]; tb += sh[LY * SMC_CXB + y * SMC_CXB + threadIdx.x]; }
   __syncthreads();
   a = ta; b = tb;
 }
 
 // this lane's share of v[j][c] ~ N(0,1), j < M (also stored to v2 when given); returns its part of sum v^2
+template <int LY>
 __device__ __forceinline__ double draw_normals(const RngSrc& r, long long step, long long c, long long C, long long M,
                                                long long Cpad, double* v, double* v2, int ly) {
   double ss = 0.0;
@@ -110,16 +116,17 @@ struct Recorder {
   double* draws;   // [samples][M][Cpad]
   double* loglik;  // [samples][Cpad]
   double* accept;  // [samples][Cpad]
-  double* mean;    // [M][Cpad]
-  double* m2;      // [M][Cpad]
-  double* first;   // [M][Cpad] first recorded draw x_0
-  double* prev;    // [M][Cpad] previous recorded draw
-  double* lag1;    // [M][Cpad] sum_{t>=1} (x_t - x_0)(x_{t-1} - x_0): lag-1 statistics of calcStats! without the draws
+  // running statistics of every (chain, component), interleaved so that a warp (32 chains) updates one contiguous
+  // 1.25 KB block per component: stats[((c / 32) * M + j) * 5 + k][c % 32], k = mean, m2 (Welford), x_0 (first recorded
+  // draw), previous draw, sum_{t>=1} (x_t - x_0)(x_{t-1} - x_0) (lag-1 statistics of calcStats! without the draws).
+  // (Five separate [M][Cpad] arrays cost 5x the time at a million chains: every access of a warp fell in another page.)
+  double* stats;
   double* nacc;    // [Cpad]
   long long burnin;
 };
 
 // addToRes! (src/samplers.jl:342-350) + per-chain Welford moments; lane ly records its components of beta
+template <int LY>
 __device__ __forceinline__ void record(const Recorder& R, long long step, long long c, long long M, long long Cpad,
                                        const double* beta, double ll, bool accepted, int ly) {
   if (step < R.burnin) return;
@@ -133,39 +140,41 @@ __device__ __forceinline__ void record(const Recorder& R, long long step, long l
   for (long long j = ly; j < M; j += LY) {
     double x = beta[j * Cpad + c];
     if (R.draws) R.draws[(s * M + j) * Cpad + c] = x;
-    double mu = R.mean[j * Cpad + c], d = x - mu;
+    double* st = R.stats + (((c >> 5) * M + j) * 5) * 32 + (c & 31);
+    double mu = st[0 * 32], d = x - mu;
     mu += d / n;
-    R.mean[j * Cpad + c] = mu;
-    R.m2[j * Cpad + c] += d * (x - mu);
+    st[0 * 32] = mu;
+    st[1 * 32] += d * (x - mu);
     if (s == 0) {
-      R.first[j * Cpad + c] = x;
+      st[2 * 32] = x;
     } else {
-      double x0 = R.first[j * Cpad + c];
-      R.lag1[j * Cpad + c] += (x - x0) * (R.prev[j * Cpad + c] - x0);
+      double x0 = st[2 * 32];
+      st[4 * 32] += (x - x0) * (st[3 * 32] - x0);
     }
-    R.prev[j * Cpad + c] = x;
+    st[3 * 32] = x;
   }
 }
 
 // ---------------------------------------------------------------------------------------------- HMC
 // state0.v = randn ; update!(state0) ; state = state0     (src/samplers.jl:151-153)
 // (the iteration number lives in device memory so that a whole iteration can be replayed as one CUDA graph)
-__global__ void __launch_bounds__(CXB * LY) k_hmc_begin(RngSrc rng, const long long* stepp, long long C, long long M, long long Cpad,
+template <int LY>
+__global__ void __launch_bounds__(256) k_hmc_begin(RngSrc rng, const long long* stepp, long long C, long long M, long long Cpad,
                                                       const double* b0, const double* g0, const double* l0, double* beta,
                                                       double* grad, double* logp, double* v, double* H0, double* H, int* active) {
-  __shared__ double sh[LY * CXB];
+  __shared__ double sh[LY * SMC_CXB];
   const long long step = *stepp;
-  const Ln L = lanes(C);
+  const Ln L = lanes<LY>(C);
   const long long c = L.c;
   double ss = 0.0;
   if (L.in) {
-    ss = draw_normals(rng, step, c, C, M, Cpad, v, nullptr, L.ly);
+    ss = draw_normals<LY>(rng, step, c, C, M, Cpad, v, nullptr, L.ly);
     for (long long j = L.ly; j < M; j += LY) {
       beta[j * Cpad + c] = b0[j * Cpad + c];
       grad[j * Cpad + c] = g0[j * Cpad + c];
     }
   }
-  ss = ysum(ss, sh);
+  ss = ysum<LY>(ss, sh);
   if (L.in && L.ly == 0) {
     double ll = l0[c];
     logp[c] = ll;
@@ -190,11 +199,12 @@ __global__ void k_leapfrog_pre(long long C, long long M, long long Cpad, double 
 }
 
 // n.v += n.grad * ve / 2 ; update!(n) ; loop condition isfinite(state.llik)   (src/samplers.jl:55-56,156)
-__global__ void __launch_bounds__(CXB * LY) k_leapfrog_post(long long C, long long M, long long Cpad, double eps, int* active,
+template <int LY>
+__global__ void __launch_bounds__(256) k_leapfrog_post(long long C, long long M, long long Cpad, double eps, int* active,
                                                           const double* grad, const double* logp, double* v, double* H,
                                                           unsigned long long* nleap) {
-  __shared__ double sh[LY * CXB];
-  const Ln L = lanes(C);
+  __shared__ double sh[LY * SMC_CXB];
+  const Ln L = lanes<LY>(C);
   const long long c = L.c;
   const bool act = L.in && active[c];
   double ss = 0.0;
@@ -205,7 +215,7 @@ __global__ void __launch_bounds__(CXB * LY) k_leapfrog_post(long long C, long lo
       v[o] = vv;
       ss += vv * vv;
     }
-  ss = ysum(ss, sh);   // (also orders every lane's read of active[c] before lane 0 clears it)
+  ss = ysum<LY>(ss, sh);   // (also orders every lane's read of active[c] before lane 0 clears it)
   if (act && L.ly == 0) {
     double ll = logp[c];
     H[c] = ll - ss / 2.0;
@@ -215,12 +225,15 @@ __global__ void __launch_bounds__(CXB * LY) k_leapfrog_post(long long C, long lo
 }
 
 // if rand() < exp(state.H - state0.H): state0 = state ; addToRes!   (src/samplers.jl:162-166)
-__global__ void __launch_bounds__(CXB * LY) k_hmc_accept(RngSrc rng, const long long* stepp, long long C, long long M, long long Cpad,
-                                                       const double* beta, const double* grad, const double* logp,
-                                                       const double* H, const double* H0, double* b0, double* g0, double* l0,
-                                                       Recorder R) {
+// The state copy and the recorder update are done four components at a time with every load issued before the first
+// store: with one component per iteration the kernel had ~1 load in flight per thread and ran at 1.5 TB/s.
+template <int LY>
+__global__ void __launch_bounds__(256) k_hmc_accept(RngSrc rng, const long long* stepp, long long C, long long M, long long Cpad,
+                                                     const double* __restrict__ beta, const double* __restrict__ grad,
+                                                     const double* __restrict__ logp, const double* __restrict__ H,
+                                                     const double* __restrict__ H0, double* b0, double* g0, double* l0, Recorder R) {
   const long long step = *stepp;
-  const Ln L = lanes(C);
+  const Ln L = lanes<LY>(C);
   const long long c = L.c;
   bool acc = false;
   double ll = 0.0;
@@ -228,17 +241,56 @@ __global__ void __launch_bounds__(CXB * LY) k_hmc_accept(RngSrc rng, const long 
     double u = rng_uniform(rng, step, c, C, 0);
     acc = u < exp(H[c] - H0[c]);
     ll = acc ? logp[c] : l0[c];
-    if (acc) {
-      for (long long j = L.ly; j < M; j += LY) {
-        b0[j * Cpad + c] = beta[j * Cpad + c];
-        g0[j * Cpad + c] = grad[j * Cpad + c];
-      }
-    }
   }
   __syncthreads();   // every lane has read l0[c]
   if (!L.in) return;
-  if (acc && L.ly == 0) l0[c] = ll;
-  record(R, step, c, M, Cpad, b0, ll, acc, L.ly);
+  const bool rec = step >= R.burnin;
+  const long long s = step - R.burnin;
+  if (L.ly == 0) {
+    if (acc) l0[c] = ll;
+    if (rec) {
+      if (R.loglik) R.loglik[s * Cpad + c] = ll;
+      if (R.accept) R.accept[s * Cpad + c] = acc ? 1.0 : 0.0;
+      R.nacc[c] += acc ? 1.0 : 0.0;
+    }
+  }
+  if (!acc && !rec) return;
+  const double n = (double)(s + 1);
+  for (long long j0 = L.ly; j0 < M; j0 += 4 * LY) {
+    double x[4], g[4], st0[4], st1[4], st2[4], st3[4], st4[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const long long j = j0 + (long long)k * LY;
+      const bool ok = j < M;
+      const long long o = (ok ? j : 0) * Cpad + c;
+      x[k] = acc ? beta[o] : b0[o];
+      g[k] = acc ? grad[o] : 0.0;
+      st0[k] = st1[k] = st2[k] = st3[k] = st4[k] = 0.0;
+      if (rec && ok) {
+        const double* st = R.stats + (((c >> 5) * M + j) * 5) * 32 + (c & 31);
+        st0[k] = st[0 * 32]; st1[k] = st[1 * 32];
+        if (s > 0) { st2[k] = st[2 * 32]; st3[k] = st[3 * 32]; st4[k] = st[4 * 32]; }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const long long j = j0 + (long long)k * LY;
+      if (j >= M) break;
+      const long long o = j * Cpad + c;
+      if (acc) { b0[o] = x[k]; g0[o] = g[k]; }
+      if (rec) {
+        if (R.draws) R.draws[(s * M + j) * Cpad + c] = x[k];
+        double* st = R.stats + (((c >> 5) * M + j) * 5) * 32 + (c & 31);
+        double mu = st0[k], d = x[k] - mu;
+        mu += d / n;
+        st[0 * 32] = mu;
+        st[1 * 32] = st1[k] + d * (x[k] - mu);
+        if (s == 0) st[2 * 32] = x[k];
+        else st[4 * 32] = st4[k] + (x[k] - st2[k]) * (st3[k] - st2[k]);
+        st[3 * 32] = x[k];
+      }
+    }
+  }
 }
 
 __global__ void k_step_inc(long long* stepp) { *stepp += 1; }
@@ -249,7 +301,7 @@ __global__ void k_rwm_propose(RngSrc rng, long long step, long long C, long long
                               const double* S, double* jump, double* beta) {
   long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  for (int y = 0; y < LY; y++) draw_normals(rng, step, c, C, M, Cpad, jump, nullptr, y);   // thread per chain here
+  for (int y = 0; y < 8; y++) draw_normals<8>(rng, step, c, C, M, Cpad, jump, nullptr, y);   // thread per chain here
   for (long long i = 0; i < M; i++) {
     double acc = 0.0;
     for (long long k = 0; k <= i; k++) acc += S[(i + k * M) * Cpad + c] * jump[k * Cpad + c];  // S lower triangular
@@ -273,7 +325,7 @@ __global__ void k_rwm_accept(RngSrc rng, long long step, long long C, long long 
     l0[c] = lnew;
   }
   double lcur = l0[c];
-  for (int y = 0; y < LY; y++) record(R, step, c, M, Cpad, b0, lcur, lold != lcur, y);
+  for (int y = 0; y < 8; y++) record<8>(R, step, c, M, Cpad, b0, lcur, lold != lcur, y);
   // adaptation
   double i1 = (double)(step + 1);
   double eta = fmin(1.0, (double)M * pow(i1, -2.0 / 3.0));
@@ -342,8 +394,13 @@ __global__ void k_div(double* p, long long n, double d) {
 }
 
 inline unsigned gridc(long long n, int block = 128) { return (unsigned)std::max<long long>(1, (n + block - 1) / block); }
-inline dim3 lgrid(long long C) { return dim3((unsigned)((C + CXB - 1) / CXB)); }   // lane-parallel kernels: (32 chains) x (LY lanes)
-inline dim3 lblock() { return dim3(CXB, LY); }
+// lane-parallel kernels: block = (256 / ly chains) x (ly lanes)
+inline int lanes_for(long long C) { return C >= 32768 ? 1 : 8; }
+#define LAUNCH_LY(kern, ...)                                                                                   \
+  do {                                                                                                         \
+    if (ly == 1) kern<1><<<(unsigned)((C + 255) / 256), dim3(256, 1), 0, st>>>(__VA_ARGS__);                  \
+    else kern<8><<<(unsigned)((C + 31) / 32), dim3(32, 8), 0, st>>>(__VA_ARGS__);                             \
+  } while (0)
 inline unsigned gride(long long n) { return (unsigned)std::max<long long>(1, std::min<long long>((n + 255) / 256, 148LL * 32)); }
 
 struct Run {
@@ -382,16 +439,10 @@ int run_setup(Run& r, const double* init, bool need_grad, long long nu) {
   if (cfg->store_draws && r.out->draws) SMC_TRY(r.A.alloc(&r.R.draws, r.samples * M * Cpad));
   if (r.out->loglik) SMC_TRY(r.A.alloc(&r.R.loglik, r.samples * Cpad));
   if (r.out->accept) SMC_TRY(r.A.alloc(&r.R.accept, r.samples * Cpad));
-  SMC_TRY(r.A.alloc(&r.R.mean, M * Cpad));
-  SMC_TRY(r.A.alloc(&r.R.m2, M * Cpad));
-  SMC_TRY(r.A.alloc(&r.R.first, M * Cpad));
-  SMC_TRY(r.A.alloc(&r.R.prev, M * Cpad));
-  SMC_TRY(r.A.alloc(&r.R.lag1, M * Cpad));
-  SMC_CUDA(cudaMemsetAsync(r.R.first, 0, M * Cpad * sizeof(double), st));
-  SMC_CUDA(cudaMemsetAsync(r.R.lag1, 0, M * Cpad * sizeof(double), st));
+  const size_t nstats = (size_t)((Cpad + 31) / 32) * M * 5 * 32;
+  SMC_TRY(r.A.alloc(&r.R.stats, nstats));
+  SMC_CUDA(cudaMemsetAsync(r.R.stats, 0, nstats * sizeof(double), st));
   SMC_TRY(r.A.alloc(&r.R.nacc, Cpad));
-  SMC_CUDA(cudaMemsetAsync(r.R.mean, 0, M * Cpad * sizeof(double), st));
-  SMC_CUDA(cudaMemsetAsync(r.R.m2, 0, M * Cpad * sizeof(double), st));
   SMC_CUDA(cudaMemsetAsync(r.R.nacc, 0, Cpad * sizeof(double), st));
   r.rng.seed = cfg->seed; r.rng.chain_offset = cfg->chain_offset; r.rng.inj_n = nullptr; r.rng.inj_u = nullptr; r.rng.nu = nu;
   if (cfg->inject_normals) {
@@ -455,6 +506,27 @@ int copy_out_blocks(Run& r, const double* dev, double* host, long long nblocks, 
   return SMC_OK;
 }
 
+// statistic k of the interleaved recorder block -> host [C][M]
+__global__ void k_out_stats(const double* stats, int k, long long C, long long M, double* out) {
+  long long total = C * M;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long c = i / M, j = i - c * M;
+    out[i] = stats[((((c >> 5) * M + j) * 5) + k) * 32 + (c & 31)];
+  }
+}
+int copy_out_stats(Run& r, int k, double* host) {
+  if (!host) return SMC_OK;
+  cudaStream_t st = r.m->ctx->stream;
+  double* stage;
+  Arena local;
+  SMC_TRY(local.alloc(&stage, r.C * r.M));
+  k_out_stats<<<gride(r.C * r.M), 256, 0, st>>>(r.R.stats, k, r.C, r.M, stage);
+  r.m->ctx->launches++;
+  SMC_CUDA(cudaMemcpyAsync(host, stage, (size_t)r.C * r.M * sizeof(double), cudaMemcpyDeviceToHost, st));
+  SMC_CUDA(cudaStreamSynchronize(st));
+  return SMC_OK;
+}
+
 int run_finish(Run& r, int64_t n_evals) {
   smc_model_s* m = r.m;
   cudaStream_t st = m->ctx->stream;
@@ -477,10 +549,10 @@ int run_finish(Run& r, int64_t n_evals) {
   SMC_TRY(copy_out_blocks(r, r.R.loglik, r.out->loglik, r.samples, 1));
   SMC_TRY(copy_out_blocks(r, r.R.accept, r.out->accept, r.samples, 1));
   SMC_TRY(copy_out_blocks(r, r.b0, r.out->final_state, 1, r.M));
-  SMC_TRY(copy_out_blocks(r, r.R.mean, r.out->mean, 1, r.M));
-  SMC_TRY(copy_out_blocks(r, r.R.m2, r.out->m2, 1, r.M));
-  SMC_TRY(copy_out_blocks(r, r.R.first, r.out->first, 1, r.M));
-  SMC_TRY(copy_out_blocks(r, r.R.lag1, r.out->lag1, 1, r.M));
+  SMC_TRY(copy_out_stats(r, 0, r.out->mean));
+  SMC_TRY(copy_out_stats(r, 1, r.out->m2));
+  SMC_TRY(copy_out_stats(r, 2, r.out->first));
+  SMC_TRY(copy_out_stats(r, 4, r.out->lag1));
   if (r.out->accept_rate) {
     k_div<<<gride(r.C), 256, 0, st>>>(r.R.nacc, r.C, (double)r.samples);
     m->ctx->launches++;
@@ -506,19 +578,20 @@ extern "C" int smc_hmc_run(smc_model_t m, const smc_sampler_config* cfg, const d
   SMC_TRY(r.A.alloc(&H0, Cpad));
   SMC_TRY(r.A.alloc(&H, Cpad));
   SMC_TRY(r.A.alloc(&active, Cpad));
+  const int ly = lanes_for(C);
   long long* d_step;
   SMC_TRY(r.A.alloc(&d_step, 1));
   SMC_CUDA(cudaMemsetAsync(d_step, 0, sizeof(long long), st));
   int64_t evals = 1;
   // one iteration = begin, isteps x (half kick + drift, evaluation, half kick), accept
   auto iteration = [&]() -> int {
-    k_hmc_begin<<<lgrid(C), lblock(), 0, st>>>(r.rng, d_step, C, M, Cpad, r.b0, r.g0, r.l0, m->beta, m->grad, m->logp, v, H0, H, active);
+    LAUNCH_LY(k_hmc_begin, r.rng, d_step, C, M, Cpad, r.b0, r.g0, r.l0, m->beta, m->grad, m->logp, v, H0, H, active);
     for (long long j = 0; j < cfg->isteps; j++) {
       k_leapfrog_pre<<<gride(C * M), 256, 0, st>>>(C, M, Cpad, cfg->stepsize, active, m->beta, m->grad, v);
       SMC_TRY(smc_model_eval_device(m, C, true));
-      k_leapfrog_post<<<lgrid(C), lblock(), 0, st>>>(C, M, Cpad, cfg->stepsize, active, m->grad, m->logp, v, H, r.nleap);
+      LAUNCH_LY(k_leapfrog_post, C, M, Cpad, cfg->stepsize, active, m->grad, m->logp, v, H, r.nleap);
     }
-    k_hmc_accept<<<lgrid(C), lblock(), 0, st>>>(r.rng, d_step, C, M, Cpad, m->beta, m->grad, m->logp, H, H0, r.b0, r.g0, r.l0, r.R);
+    LAUNCH_LY(k_hmc_accept, r.rng, d_step, C, M, Cpad, m->beta, m->grad, m->logp, H, H0, r.b0, r.g0, r.l0, r.R);
     k_step_inc<<<1, 1, 0, st>>>(d_step);
     m->ctx->launches += 3 + 2 * cfg->isteps;
     return SMC_OK;
@@ -654,6 +727,7 @@ struct Nuts {
 
 // this lane's share of the two U-turn dot products (src/samplers.jl:48):
 //   d1 = dot(s2.beta - s1.beta, s1.v),  d2 = dot(s2.beta - s1.beta, s2.v)      (s1 = minus edge, s2 = plus edge)
+template <int LY>
 __device__ __forceinline__ void uturn_part(const double* minus_b, const double* minus_v, const double* plus_b,
                                            const double* plus_v, long long c, long long M, long long Cpad, int ly,
                                            double& d1, double& d2) {
@@ -664,6 +738,7 @@ __device__ __forceinline__ void uturn_part(const double* minus_b, const double* 
   }
 }
 
+template <int LY>
 __device__ __forceinline__ void copy_vec(double* dst, const double* src, long long c, long long M, long long Cpad, int ly) {
   for (long long k = ly; k < M; k += LY) dst[k * Cpad + c] = src[k * Cpad + c];
 }
@@ -718,14 +793,15 @@ __global__ void k_nuts_init(long long C, Nuts T) {
   T.lebar[c] = 0.0;
 }
 
-__global__ void __launch_bounds__(CXB * LY) k_nuts_begin(RngSrc rng, long long step, long long C, long long M, long long Cpad,
+template <int LY>
+__global__ void __launch_bounds__(256) k_nuts_begin(RngSrc rng, long long step, long long C, long long M, long long Cpad,
                                                        const double* b0, const double* g0, const double* l0, Nuts T) {
-  __shared__ double sh[LY * CXB];
-  const Ln L = lanes(C);
+  __shared__ double sh[LY * SMC_CXB];
+  const Ln L = lanes<LY>(C);
   const long long c = L.c;
   double ss = 0.0;
   if (L.in) {
-    ss = draw_normals(rng, step, c, C, M, Cpad, T.mv, T.pv, L.ly);
+    ss = draw_normals<LY>(rng, step, c, C, M, Cpad, T.mv, T.pv, L.ly);
     for (long long k = L.ly; k < M; k += LY) {
       long long o = k * Cpad + c;
       double b = b0[o], g = g0[o];
@@ -733,7 +809,7 @@ __global__ void __launch_bounds__(CXB * LY) k_nuts_begin(RngSrc rng, long long s
       T.mg[o] = g; T.pg[o] = g; T.sg[o] = g;
     }
   }
-  ss = ysum(ss, sh);
+  ss = ysum<LY>(ss, sh);
   if (!L.in || L.ly != 0) return;
   double ll = l0[c];
   T.ml[c] = ll; T.pl[c] = ll; T.sl[c] = ll;
@@ -750,9 +826,10 @@ __global__ void __launch_bounds__(CXB * LY) k_nuts_begin(RngSrc rng, long long s
   T.nalast[c] = 1.0;
 }
 
-__global__ void __launch_bounds__(CXB * LY) k_nuts_pre(RngSrc rng, long long step, long long C, long long M, long long Cpad,
+template <int LY>
+__global__ void __launch_bounds__(256) k_nuts_pre(RngSrc rng, long long step, long long C, long long M, long long Cpad,
                                                      double* beta, int use_slots, Nuts T) {
-  const Ln L = lanes(C);
+  const Ln L = lanes<LY>(C);
   const long long c = L.c;
   const bool act = L.in && T.active[c];
   int newdbl = 0, dir = 0, k = 0;
@@ -800,11 +877,12 @@ __global__ void __launch_bounds__(CXB * LY) k_nuts_pre(RngSrc rng, long long ste
   }
 }
 
-__global__ void __launch_bounds__(CXB * LY) k_nuts_post(RngSrc rng, long long step, long long C, long long M, long long Cpad,
+template <int LY>
+__global__ void __launch_bounds__(256) k_nuts_post(RngSrc rng, long long step, long long C, long long M, long long Cpad,
                                                       const double* egrad, const double* elogp, int use_slots, Nuts T,
                                                       unsigned long long* nleap) {
-  __shared__ double sh[2 * LY * CXB];
-  const Ln L = lanes(C);
+  __shared__ double sh[2 * LY * SMC_CXB];
+  const Ln L = lanes<LY>(C);
   const long long c = L.c;
   const int ly = L.ly;
   const bool act = L.in && T.active[c];
@@ -830,7 +908,7 @@ __global__ void __launch_bounds__(CXB * LY) k_nuts_post(RngSrc rng, long long st
       T.tv[o] = vv;
       ss += vv * vv;
     }
-  ss = ysum(ss, sh);
+  ss = ysum<LY>(ss, sh);
   const double H = ll - ss / 2.0;
   // ---- leaf (buildTree with j == 0, :230-236)
   double n2 = (u <= H) ? 1.0 : 0.0;
@@ -839,10 +917,10 @@ __global__ void __launch_bounds__(CXB * LY) k_nuts_post(RngSrc rng, long long st
   double na2 = 1.0;
   double csl = ll;
   if (act) {
-    copy_vec(T.cnb, beta, c, M, Cpad, ly);
-    copy_vec(T.cnv, T.tv, c, M, Cpad, ly);
-    copy_vec(T.csb, beta, c, M, Cpad, ly);
-    copy_vec(T.csg, grad, c, M, Cpad, ly);
+    copy_vec<LY>(T.cnb, beta, c, M, Cpad, ly);
+    copy_vec<LY>(T.cnv, T.tv, c, M, Cpad, ly);
+    copy_vec<LY>(T.csb, beta, c, M, Cpad, ly);
+    copy_vec<LY>(T.csg, grad, c, M, Cpad, ly);
   }
   // ---- merges where the recursion returns (:238-256): levels = trailing one bits of the leaf index.  The loop is
   // uniform over the block (the U-turn test needs every lane); a chain leaves it at `stop_level`.
@@ -870,31 +948,31 @@ __global__ void __launch_bounds__(CXB * LY) k_nuts_post(RngSrc rng, long long st
       double r = rng_uniform(rng, step, c, C, ucount++);
       bool take_second = r <= n2 / (n2 + n1);   // NaN (0/0) compares false, as in the reference
       if (!take_second) {
-        copy_vec(T.csb, T.ksb + so, c, M, Cpad, ly);
-        copy_vec(T.csg, T.ksg + so, c, M, Cpad, ly);
+        copy_vec<LY>(T.csb, T.ksb + so, c, M, Cpad, ly);
+        copy_vec<LY>(T.csg, T.ksg + so, c, M, Cpad, ly);
         csl = T.ksl[sc];
       }
-      copy_vec(T.cnb, T.knb + so, c, M, Cpad, ly);   // the merged sub-tree starts where the first one started
-      copy_vec(T.cnv, T.knv + so, c, M, Cpad, ly);
+      copy_vec<LY>(T.cnb, T.knb + so, c, M, Cpad, ly);   // the merged sub-tree starts where the first one started
+      copy_vec<LY>(T.cnv, T.knv + so, c, M, Cpad, ly);
       a2 += T.ka[sc];
       na2 += T.kna[sc];
       if (s2) {
         test_uturn = true;
-        if (dir > 0) uturn_part(T.cnb, T.cnv, beta, T.tv, c, M, Cpad, ly, d1, d2);
-        else uturn_part(beta, T.tv, T.cnb, T.cnv, c, M, Cpad, ly, d1, d2);
+        if (dir > 0) uturn_part<LY>(T.cnb, T.cnv, beta, T.tv, c, M, Cpad, ly, d1, d2);
+        else uturn_part<LY>(beta, T.tv, T.cnb, T.cnv, c, M, Cpad, ly, d1, d2);
       }
       n2 += n1;
     }
-    ysum2(d1, d2, sh);
+    ysum2<LY>(d1, d2, sh);
     if (test_uturn) s2 = !(d1 < 0.0 || d2 < 0.0);
   }
   const bool done = act && ((!s2) || (leaf == (1 << j) - 1));
   if (act && !done) {
     const long long so = (long long)stop_level * LS, sc = (long long)stop_level * Cpad + c;
-    copy_vec(T.knb + so, T.cnb, c, M, Cpad, ly);
-    copy_vec(T.knv + so, T.cnv, c, M, Cpad, ly);
-    copy_vec(T.ksb + so, T.csb, c, M, Cpad, ly);
-    copy_vec(T.ksg + so, T.csg, c, M, Cpad, ly);
+    copy_vec<LY>(T.knb + so, T.cnb, c, M, Cpad, ly);
+    copy_vec<LY>(T.knv + so, T.cnv, c, M, Cpad, ly);
+    copy_vec<LY>(T.ksb + so, T.csb, c, M, Cpad, ly);
+    copy_vec<LY>(T.ksg + so, T.csg, c, M, Cpad, ly);
     if (ly == 0) {
       T.tl[c] = ll;
       T.ksl[sc] = csl;
@@ -915,15 +993,15 @@ __global__ void __launch_bounds__(CXB * LY) k_nuts_post(RngSrc rng, long long st
       long long o = q * Cpad + c;
       eb[o] = beta[o]; ev[o] = T.tv[o]; eg[o] = grad[o];
     }
-    uturn_part(T.mb, T.mv, T.pb, T.pv, c, M, Cpad, ly, d1, d2);
+    uturn_part<LY>(T.mb, T.mv, T.pb, T.pv, c, M, Cpad, ly, d1, d2);
   }
-  ysum2(d1, d2, sh);
+  ysum2<LY>(d1, d2, sh);
   if (!done) return;
   if (s2) {
     double r = rng_uniform(rng, step, c, C, ucount++);
     if (r < n2 / ntot) {   // state = state1
-      copy_vec(T.sb, T.csb, c, M, Cpad, ly);
-      copy_vec(T.sg, T.csg, c, M, Cpad, ly);
+      copy_vec<LY>(T.sb, T.csb, c, M, Cpad, ly);
+      copy_vec<LY>(T.sg, T.csg, c, M, Cpad, ly);
       if (ly == 0) { T.sl[c] = csl; T.moved[c] = 1; }
     }
   }
@@ -945,17 +1023,18 @@ __global__ void __launch_bounds__(CXB * LY) k_nuts_post(RngSrc rng, long long st
 }
 
 // dual averaging of epsilon (:294-302), addToRes! (:305), misc (:307-308), state0 = state (:310)
-__global__ void __launch_bounds__(CXB * LY) k_nuts_end(long long step, long long C, long long M, long long Cpad, double* b0,
+template <int LY>
+__global__ void __launch_bounds__(256) k_nuts_end(long long step, long long C, long long M, long long Cpad, double* b0,
                                                      double* g0, double* l0, Nuts T, Recorder R, double* eps_out,
                                                      double* jmax_out) {
-  const Ln L = lanes(C);
+  const Ln L = lanes<LY>(C);
   const long long c = L.c;
   if (!L.in) return;
   const int ly = L.ly;
-  copy_vec(b0, T.sb, c, M, Cpad, ly);
-  copy_vec(g0, T.sg, c, M, Cpad, ly);
+  copy_vec<LY>(b0, T.sb, c, M, Cpad, ly);
+  copy_vec<LY>(g0, T.sg, c, M, Cpad, ly);
   const double sl = T.sl[c];
-  record(R, step, c, M, Cpad, b0, sl, T.moved[c] != 0, ly);
+  record<LY>(R, step, c, M, Cpad, b0, sl, T.moved[c] != 0, ly);
   if (ly != 0) return;
   const double delta = 0.7, gam = 0.05, kappa = 0.75, t0 = 10.0;
   const long long nadapt = 1000;
@@ -1008,6 +1087,7 @@ extern "C" int smc_nuts_run(smc_model_t m, const smc_sampler_config* cfg, const 
   double *eps_dev = nullptr, *jmax_dev = nullptr;
   if (out->epsilon) SMC_TRY(r.A.alloc(&eps_dev, cfg->steps * Cpad));
   if (out->jmax) SMC_TRY(r.A.alloc(&jmax_dev, cfg->steps * Cpad));
+  const int ly = lanes_for(C);
   k_nuts_init<<<gridc(C), 128, 0, st>>>(C, T);
   m->ctx->launches++;
   int64_t evals = 1;
@@ -1030,7 +1110,7 @@ extern "C" int smc_nuts_run(smc_model_t m, const smc_sampler_config* cfg, const 
   const bool compact = !(nc && nc[0] == '1') && !(m->row_shard && m->ctx->nranks > 1) && (C >= 4096 || (fc && fc[0] == '1'));
   long long eval_chains = 0;   // chain evaluations actually performed (sum of the evaluated widths)
   for (long long i = 0; i < cfg->steps && rc == SMC_OK; i++) {
-    k_nuts_begin<<<lgrid(C), lblock(), 0, st>>>(r.rng, i, C, M, Cpad, r.b0, r.g0, r.l0, T);
+    LAUNCH_LY(k_nuts_begin, r.rng, i, C, M, Cpad, r.b0, r.g0, r.l0, T);
     m->ctx->launches++;
     int launched = 0, rounds = 0;
     // Lockstep evaluation only has to cover the chains that are still building a tree.  Their number never grows within
@@ -1051,14 +1131,14 @@ extern "C" int smc_nuts_run(smc_model_t m, const smc_sampler_config* cfg, const 
         k_slot_assign<<<slot_blocks, 256, 0, st>>>(T.active, C, T.blocksum, T.slot);
         m->ctx->launches += 3;
       }
-      k_nuts_pre<<<lgrid(C), lblock(), 0, st>>>(r.rng, i, C, M, Cpad, m->beta, use_slots, T);
+      LAUNCH_LY(k_nuts_pre, r.rng, i, C, M, Cpad, m->beta, use_slots, T);
       m->ctx->launches++;
       int e = smc_model_eval_device(m, Ceval, true);
       if (e != SMC_OK) return e;
       evals++;
       eval_chains += Ceval;
       (void)eval_chains;
-      k_nuts_post<<<lgrid(C), lblock(), 0, st>>>(r.rng, i, C, M, Cpad, m->grad, m->logp, use_slots, T, r.nleap);
+      LAUNCH_LY(k_nuts_post, r.rng, i, C, M, Cpad, m->grad, m->logp, use_slots, T, r.nleap);
       m->ctx->launches++;
       cudaMemcpyAsync(h_active + slot, T.n_active, sizeof(int), cudaMemcpyDeviceToHost, st);
       cudaEventRecord(ev[slot], st);
@@ -1082,7 +1162,7 @@ extern "C" int smc_nuts_run(smc_model_t m, const smc_sampler_config* cfg, const 
     }
     if (rc != SMC_OK) break;
     prev_rounds = rounds;
-    k_nuts_end<<<lgrid(C), lblock(), 0, st>>>(i, C, M, Cpad, r.b0, r.g0, r.l0, T, r.R, eps_dev, jmax_dev);
+    LAUNCH_LY(k_nuts_end, i, C, M, Cpad, r.b0, r.g0, r.l0, T, r.R, eps_dev, jmax_dev);
     m->ctx->launches++;
   }
   cudaStreamSynchronize(st);

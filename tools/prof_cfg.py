@@ -6,11 +6,17 @@ import numpy as np
 from smc_pkg import load_package
 load_package()
 from simplemcmc_jl_b200 import api
-from util import HIERARCHICAL, LOGISTIC, ORNSTEIN, SLEEPSTUDY2, hierarchical_data, ou_data, sleepstudy_data
+from util import HIERARCHICAL, LINEAR, LOGISTIC, ORNSTEIN, SLEEPSTUDY2, hierarchical_data, linear_data, ou_data, sleepstudy_data
 
 which = sys.argv[1]
 C = int(sys.argv[2]) if len(sys.argv) > 2 else 0
-if which == "cfg3":
+if which == "cfg1":
+    C = C or (1 << 20)
+    X, Y, _ = linear_data(1000, 10, 1)
+    mode = np.linalg.solve(X.T @ X + np.eye(10), X.T @ Y)
+    low, dev = api._build(LINEAR, [("beta", np.zeros(10))], dict(X=X, Y=Y), True, C, 0, "assign")
+    raw = dev.run("hmc", mode, C, 4, 0, isteps=2, stepsize=0.05, seed=1, store_draws=False, want=())
+elif which == "cfg3":
     C = C or 1
     rng = np.random.default_rng(3)
     N, M = 10_000_000, 10

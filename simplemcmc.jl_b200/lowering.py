@@ -611,8 +611,33 @@ class Lowering(object):
             self.adj_init[v.vid] = False
         return self.adj[v.vid]
 
+    def _own_adjoint(self, target):
+        """copy on write: an adjoint that so far was only another name for a value gets its own register"""
+        if target.vid in self.adj_alias:
+            alias = self.adj.pop(target.vid)
+            self.adj_alias.discard(target.vid)
+            dst = self._adjoint_target(target)
+            self.bwd.append(Stmt(OP["COPY"], dst, [alias]))
+            self.adj_init[target.vid] = True
+
     def contrib(self, target, op, srcs, **kw):
-        """adjoint(target) += op(srcs)   -- the `dv = dv + ...` statement of src/diff.jl:214"""
+        """adjoint(target) += op(srcs)   -- the `dv = dv + ...` statement of src/diff.jl:214.
+        The seed d(finalacc) = 1.0 (src/parsing.jl:419) travels down the accumulator chain as a literal: `x * 1.0` is x,
+        and a first contribution that is a plain same-shape copy makes the adjoint another name for its source instead
+        of a statement (exact identities; they remove the all-ones per-chain registers the literal derivation creates)."""
+        if op == "MUL" and not kw and len(srcs) == 2:
+            a, b = srcs
+            if b.kind == REG_IMM and b.imm == 1.0:
+                op, srcs = "COPY", [a]
+            elif a.kind == REG_IMM and a.imm == 1.0:
+                op, srcs = "COPY", [b]
+        if (op == "COPY" and not kw and target.kind != REG_PARAM and target.vid not in self.adj
+                and srcs[0].shape == target.shape):
+            self.adj[target.vid] = srcs[0]
+            self.adj_init[target.vid] = True
+            self.adj_alias.add(target.vid)
+            return
+        self._own_adjoint(target)
         dst = self._adjoint_target(target)
         n = max([s.numel for s in srcs] + [1])
         if op not in ("MATMUL", "TRANSPOSE") and not (dst.numel == n or dst.numel == 1 or n == 1):
@@ -630,7 +655,7 @@ class Lowering(object):
         return self.emit(op, list(srcs), shape, back=True, **kw)
 
     def _reverse_sweep(self):
-        self.adj, self.adj_init = {}, {}
+        self.adj, self.adj_init, self.adj_alias = {}, {}, set()
         needed = set()
         # active = descendants of parameters that are ancestors of the accumulator (src/parsing.jl:291)
         anc = {self.result.vid}
@@ -714,6 +739,7 @@ class Lowering(object):
         elif op == O["TRANSPOSE"]:
             self.contrib(x, "TRANSPOSE", [ds], aux0=st.aux1, aux1=st.aux0)
         elif op == O["GATHER"]:
+            self._own_adjoint(x)
             if x.vid not in self.adj or not self.adj_init[x.vid]:
                 self.contrib(x, "ZERO", [x])
             dst = self.adj[x.vid]

@@ -119,7 +119,8 @@ struct Recorder {
   // running statistics of every (chain, component), interleaved so that a warp (32 chains) updates one contiguous
   // 1.25 KB block per component: stats[((c / 32) * M + j) * 5 + k][c % 32], k = mean, m2 (Welford), x_0 (first recorded
   // draw), previous draw, sum_{t>=1} (x_t - x_0)(x_{t-1} - x_0) (lag-1 statistics of calcStats! without the draws).
-  // (Five separate [M][Cpad] arrays cost 5x the time at a million chains: every access of a warp fell in another page.)
+  // (Measured at 2^20 chains: the layout alone changed little, 795 -> 707 us for the accept kernel; what mattered was
+  // issuing all loads of four components before the first store, 707 -> 191 us -- see k_hmc_accept.)
   double* stats;
   double* nacc;    // [Cpad]
   long long burnin;

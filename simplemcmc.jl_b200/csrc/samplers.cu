@@ -741,7 +741,20 @@ __device__ __forceinline__ void uturn_part(const double* minus_b, const double* 
 
 template <int LY>
 __device__ __forceinline__ void copy_vec(double* dst, const double* src, long long c, long long M, long long Cpad, int ly) {
-  for (long long k = ly; k < M; k += LY) dst[k * Cpad + c] = src[k * Cpad + c];
+  // four loads in flight before the first store (dst and src may be any of the state vectors: no restrict)
+  for (long long k0 = ly; k0 < M; k0 += 4 * LY) {
+    double t[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const long long k = k0 + (long long)u * LY;
+      t[u] = k < M ? src[k * Cpad + c] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const long long k = k0 + (long long)u * LY;
+      if (k < M) dst[k * Cpad + c] = t[u];
+    }
+  }
 }
 
 // dense evaluation slots for the chains that are still building a tree: slot[c] = number of active chains before c

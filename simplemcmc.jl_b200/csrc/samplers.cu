@@ -732,6 +732,7 @@ template <int LY>
 __device__ __forceinline__ void uturn_part(const double* minus_b, const double* minus_v, const double* plus_b,
                                            const double* plus_v, long long c, long long M, long long Cpad, int ly,
                                            double& d1, double& d2) {
+#pragma unroll 4
   for (long long k = ly; k < M; k += LY) {
     double db = plus_b[k * Cpad + c] - minus_b[k * Cpad + c];
     d1 += db * minus_v[k * Cpad + c];
@@ -881,13 +882,24 @@ __global__ void __launch_bounds__(256) k_nuts_pre(RngSrc rng, long long step, lo
     }
   }
   double ve = dir * eps;
-  for (long long q = L.ly; q < M; q += LY) {   // leapFrog, :52-53
-    long long o = q * Cpad + c;
-    double vv = T.tv[o] + T.tg[o] * ve / 2.0;
-    T.tv[o] = vv;
-    double b = T.tb[o] + ve * vv;
-    T.tb[o] = b;
-    beta[q * Cpad + slot] = b;   // the evaluation's input column of this chain
+  for (long long q0 = L.ly; q0 < M; q0 += 4 * LY) {   // leapFrog, :52-53 (four components' loads before the stores)
+    double v4[4], g4[4], b4[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const long long q = q0 + (long long)u * LY, o = (q < M ? q : 0) * Cpad + c;
+      v4[u] = T.tv[o]; g4[u] = T.tg[o]; b4[u] = T.tb[o];
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const long long q = q0 + (long long)u * LY;
+      if (q >= M) break;
+      const long long o = q * Cpad + c;
+      double vv = v4[u] + g4[u] * ve / 2.0;
+      T.tv[o] = vv;
+      double b = b4[u] + ve * vv;
+      T.tb[o] = b;
+      beta[q * Cpad + slot] = b;   // the evaluation's input column of this chain
+    }
   }
 }
 
@@ -914,13 +926,24 @@ __global__ void __launch_bounds__(256) k_nuts_post(RngSrc rng, long long step, l
   const double ve = dir * eps;
   double ss = 0.0;
   if (act)
-    for (long long q = ly; q < M; q += LY) {   // second half kick + update!, :55-56
-      long long o = q * Cpad + c;
-      double gq = egrad[q * Cpad + slot];        // the evaluation's output column of this chain
-      T.tg[o] = gq;
-      double vv = T.tv[o] + gq * ve / 2.0;
-      T.tv[o] = vv;
-      ss += vv * vv;
+    for (long long q0 = ly; q0 < M; q0 += 4 * LY) {   // second half kick + update!, :55-56
+      double g4[4], v4[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const long long q = q0 + (long long)u * LY, qq = q < M ? q : 0;
+        g4[u] = egrad[qq * Cpad + slot];          // the evaluation's output column of this chain
+        v4[u] = T.tv[qq * Cpad + c];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const long long q = q0 + (long long)u * LY;
+        if (q >= M) break;
+        const long long o = q * Cpad + c;
+        T.tg[o] = g4[u];
+        double vv = v4[u] + g4[u] * ve / 2.0;
+        T.tv[o] = vv;
+        ss += vv * vv;
+      }
     }
   ss = ysum<LY>(ss, sh);
   const double H = ll - ss / 2.0;

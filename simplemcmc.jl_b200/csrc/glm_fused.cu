@@ -94,7 +94,10 @@ __device__ __forceinline__ int rowmap(int n) { return n < 4 ? n : (n ^ 1); }
 
 // TRIM: the model has at most MP - 4 columns, so the last k-step of product 1 would multiply zeros and is skipped
 // (M = 10 in a 16-wide tile: 3 k-steps instead of 4, 7 DMMAs per row block instead of 8).
-template <int FAM, int MT, int NWC, int NWR, int MP8, int TRIM>
+// PUB: one row split covers all rows (small N) on a single rank -- the epilogue writes (L, G) into the tape registers
+// itself.  (A compile-time switch: as a run-time branch it changed the register allocation of the main loop and cost
+// 2.5 % on cfg2, 32.9 vs 32.1 ms per launch.)
+template <int FAM, int MT, int NWC, int NWR, int MP8, int TRIM, int PUB>
 __global__ void __launch_bounds__(NWC* NWR * 32, (MP8 <= 2 ? 2 : 1)) k_glm(GlmArgs a) {
   constexpr int MP = MP8 * 8, LD = MP + 4, NT = NWC * NWR * 32;
   constexpr int KS = MP / 4 - TRIM;          // k-steps of product 1
@@ -294,7 +297,7 @@ __global__ void __launch_bounds__(NWC* NWR * 32, (MP8 <= 2 ? 2 : 1)) k_glm(GlmAr
     } else if (a.neg_out) {
       v = -v;
     }
-    if (a.pub.on) {
+    if (PUB) {
       if (j == MP) {
         if (a.bad[c] || !(v > -INFINITY)) { a.bad[c] = 1; v = 0.0; }
         a.pub.Ldst[c] = a.pub.acc ? a.pub.Ldst[c] + v : v;
@@ -615,13 +618,13 @@ __global__ void __launch_bounds__(256) k_glm_gram(GramEvalArgs a) {
   }
 }
 
-template <int FAM, int MT, int NWC, int NWR, int MP8, int TRIM>
-int launch_cfg_t(const GlmArgs& a, int RS, cudaStream_t st) {
+template <int FAM, int MT, int NWC, int NWR, int MP8, int TRIM, int PUB>
+int launch_cfg_tp(const GlmArgs& a, int RS, cudaStream_t st) {
   constexpr int MP = MP8 * 8, LD = MP + 4, RT = SMC_GLM_RT(MP8), NST = 4, TC = NWC * MT * 8;
   size_t pipe = (size_t)NST * RT * (LD + 1) * sizeof(double);
   size_t epi = (size_t)(MP + 1) * TC * sizeof(double) + TC * sizeof(int);
   size_t smem = std::max(pipe, epi);
-  auto kern = k_glm<FAM, MT, NWC, NWR, MP8, TRIM>;
+  auto kern = k_glm<FAM, MT, NWC, NWR, MP8, TRIM, PUB>;
   static bool attr_done = false;
   if (!attr_done) {
     SMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -630,6 +633,11 @@ int launch_cfg_t(const GlmArgs& a, int RS, cudaStream_t st) {
   dim3 grid((unsigned)((a.C + TC - 1) / TC), (unsigned)RS);
   kern<<<grid, NWC * NWR * 32, smem, st>>>(a);
   return SMC_OK;
+}
+
+template <int FAM, int MT, int NWC, int NWR, int MP8, int TRIM>
+int launch_cfg_t(const GlmArgs& a, int RS, cudaStream_t st) {
+  return a.pub.on ? launch_cfg_tp<FAM, MT, NWC, NWR, MP8, TRIM, 1>(a, RS, st) : launch_cfg_tp<FAM, MT, NWC, NWR, MP8, TRIM, 0>(a, RS, st);
 }
 
 template <int FAM, int MT, int NWC, int NWR, int MP8>

@@ -144,9 +144,12 @@ __global__ void __launch_bounds__(NWC* NWR * 32, (MP8 <= 2 ? 2 : 1)) k_glm(GlmAr
     neg_inv_s2 = -1.0 / (a.par * a.par);
   }
 
-  // (issuing this copy a few chunks per row-block iteration instead of in one burst after the barrier was measured
-  // slower: 33.98 vs 32.07 ms per launch on cfg2 -- the extra address arithmetic inside the DMMA loop costs more
-  // than the burst)
+  // Measured alternatives that did NOT help on cfg2 (32.07 ms per launch as written):
+  //  * issuing this copy a few chunks per row-block iteration instead of in one burst after the barrier: 33.98 ms
+  //    (the extra address arithmetic inside the DMMA loop costs more than the burst);
+  //  * full/empty mbarriers (cp.async.mbarrier.arrive) with two tiles in flight instead of the CTA-wide barrier, with
+  //    and without starting the upper half of the warps 0.2-3 us late so that the two warps of a scheduler run out of
+  //    phase: 32.9 ms at 254 registers, independent of the skew.
   auto load_tile = [&](int t) {
     if (t < ntiles) {
       double* xs = Xs + (t % NST) * RT * LD;

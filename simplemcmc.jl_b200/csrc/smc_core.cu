@@ -6,6 +6,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <cmath>
 #include "smc_internal.h"
 #include "dists.cuh"
 #include "exec_common.cuh"
@@ -173,6 +174,7 @@ extern "C" int smc_model_destroy(smc_model_t m) {
   for (auto& r : m->regs) if (r.owned && r.dev) cudaFree(r.dev);
   for (auto d : m->idx_dev) cudaFree(d);
   for (auto& p : m->scatter) { cudaFree(p.ptr); cudaFree(p.list); }
+  for (auto& p : m->sparse) { if (p.ptr) cudaFree(p.ptr); if (p.col) cudaFree(p.col); if (p.val) cudaFree(p.val); }
   for (auto& g : m->glm) smc_glm_release(g);
   for (auto& pr : m->programs) if (pr.dev_tables) cudaFree(pr.dev_tables);
   if (m->beta) cudaFree(m->beta);
@@ -375,6 +377,22 @@ __global__ void __launch_bounds__(256) k_matmul_dc(MmDcArgs a) {
   }
 }
 
+// MATMUL whose parameter-independent left operand is sparse (a one-hot design matrix such as sleepstudy's `submatrix`:
+// one non-zero per row): CSR of op(A), thread = (output element, chain).  The non-zeros of a row are summed in column
+// order, i.e. the dense sum with its exact +0.0 terms dropped.
+__global__ void k_spmm_dc(const int32_t* ptr, const int32_t* col, const double* val, const double* B, long long Bse, double* out,
+                          long long Ose, long long r, long long n, long long k, long long C, int acc) {
+  long long total = r * n * C;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    long long o = idx / C, c = idx - o * C;
+    long long i = o % r, j = o / r;
+    double t = 0.0;
+    for (int p = ptr[i]; p < ptr[i + 1]; p++) t = fma(val[p], __ldg(B + ((long long)col[p] + j * k) * Bse + c), t);
+    double* q = out + o * Ose + c;
+    *q = acc ? (*q + t) : t;
+  }
+}
+
 __global__ void k_transpose(Opd src, Dst d, long long rows, long long cols, long long C, int acc) {
   long long total = rows * cols * C;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
@@ -538,6 +556,47 @@ static int scatter_plan(smc_model_s* m, uint32_t table, int64_t n_dst, SmcScatte
   return SMC_OK;
 }
 
+// CSR of op(A) for a data / header matrix operand, built on first use; matrices with more than 15 % non-zeros (or too
+// large to inspect cheaply) stay on the dense kernels
+static int sparse_plan(smc_model_s* m, uint32_t reg, int tA, long long r, long long k, long long ar, SmcSparse** out) {
+  for (auto& p : m->sparse)
+    if (p.reg == (int)reg && p.tA == tA) { *out = &p; return SMC_OK; }
+  SmcSparse sp;
+  sp.reg = (int)reg; sp.tA = tA; sp.r = r; sp.k = k;
+  const long long numel = r * k;
+  if (numel >= 64 && numel <= (4LL << 20)) {
+    std::vector<double> A(numel);
+    SMC_CUDA(cudaMemcpy(A.data(), m->regs[reg].dev, (size_t)numel * sizeof(double), cudaMemcpyDeviceToHost));
+    auto at = [&](long long i, long long l) { return A[tA ? (l + i * ar) : (i + l * ar)]; };
+    long long nnz = 0;
+    for (double v : A) nnz += (v != 0.0);
+    bool finite = true;
+    for (double v : A) finite = finite && std::isfinite(v);
+    if (finite && nnz * 100 <= numel * 15) {
+      std::vector<int32_t> ptr(r + 1, 0), col;
+      std::vector<double> val;
+      col.reserve(nnz); val.reserve(nnz);
+      for (long long i = 0; i < r; i++) {
+        for (long long l = 0; l < k; l++) {
+          double v = at(i, l);
+          if (v != 0.0) { col.push_back((int32_t)l); val.push_back(v); }
+        }
+        ptr[i + 1] = (int32_t)col.size();
+      }
+      SMC_CUDA(cudaMalloc(&sp.ptr, ptr.size() * 4));
+      SMC_CUDA(cudaMalloc(&sp.col, std::max<size_t>(col.size(), 1) * 4));
+      SMC_CUDA(cudaMalloc(&sp.val, std::max<size_t>(val.size(), 1) * 8));
+      SMC_CUDA(cudaMemcpy(sp.ptr, ptr.data(), ptr.size() * 4, cudaMemcpyHostToDevice));
+      SMC_CUDA(cudaMemcpy(sp.col, col.data(), col.size() * 4, cudaMemcpyHostToDevice));
+      SMC_CUDA(cudaMemcpy(sp.val, val.data(), val.size() * 8, cudaMemcpyHostToDevice));
+      sp.sparse = true;
+    }
+  }
+  m->sparse.push_back(sp);
+  *out = &m->sparse.back();
+  return SMC_OK;
+}
+
 static int run_statement(smc_model_s* m, const smc_tape_stmt& s, int64_t C, bool header) {
   cudaStream_t st = m->ctx->stream;
   const SmcReg& dreg = m->regs[s.dst];
@@ -555,6 +614,16 @@ static int run_statement(smc_model_s* m, const smc_tape_stmt& s, int64_t C, bool
       a.ar = a.tA ? a.k : a.r;
       a.br = a.tB ? a.n : a.k;
       long long outn = a.r * a.n;
+      if (!a.A.is_imm && a.A.sc == 0 && !a.B.is_imm && a.B.sc == 1 && !a.tB && d.sc == 1 && !header &&
+          m->regs[s.src[0]].numel == a.r * a.k) {
+        SmcSparse* sp = nullptr;
+        SMC_TRY(sparse_plan(m, s.src[0], a.tA, a.r, a.k, a.ar, &sp));
+        if (sp->sparse) {
+          k_spmm_dc<<<grid_for(outn * C), 256, 0, st>>>(sp->ptr, sp->col, sp->val, a.B.p, a.B.se, d.p, d.se, a.r, a.n, a.k, C, acc);
+          m->ctx->launches++;
+          break;
+        }
+      }
       if (!a.A.is_imm && a.A.sc == 0 && !a.B.is_imm && a.B.sc == 1 && !a.tB && C >= 32 && d.sc == 1) {
         // data matrix x per-chain matrix: tiled kernel, thread = chain
         MmDcArgs g;
@@ -698,6 +767,8 @@ extern "C" int smc_model_finalize(smc_model_t m, int64_t max_chains, int row_sha
   cudaStream_t st = m->ctx->stream;
   SMC_CUDA(cudaStreamSynchronize(st));
   smc_graphs_invalidate(m);
+  for (auto& p : m->sparse) { if (p.ptr) cudaFree(p.ptr); if (p.col) cudaFree(p.col); if (p.val) cudaFree(p.val); }
+  m->sparse.clear();   // (data may have been bound again)
   {
     const char* ng = getenv("SMC_NO_GRAPHS");
     m->graphs_enabled = (ng && ng[0] == '1') ? 0 : 1;

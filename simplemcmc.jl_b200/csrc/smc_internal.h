@@ -107,6 +107,15 @@ struct SmcScatterPlan {  // inverse of a static index table for SCATTER statemen
   int32_t* list = nullptr;  // [n]
 };
 
+struct SmcSparse {  // a sparse parameter-independent matrix operand of MATMUL (e.g. a one-hot design matrix), as CSR of op(A)
+  int reg = -1, tA = 0;
+  bool sparse = false;       // false: looked at, dense enough to stay on the dense kernel
+  int64_t r = 0, k = 0;      // op(A) is r x k
+  int32_t* ptr = nullptr;    // [r + 1]
+  int32_t* col = nullptr;    // [nnz]
+  double* val = nullptr;     // [nnz]
+};
+
 struct SmcEvalGraph {  // one captured evaluation (all statements of the tape for a chain count), replayed with one launch
   int64_t C = 0;
   int with_grad = 0;
@@ -127,6 +136,7 @@ struct smc_model_s {
   std::vector<SmcGlmPlan> glm;
   std::vector<SmcProgram> programs;
   std::vector<SmcScatterPlan> scatter;
+  std::vector<SmcSparse> sparse;
   bool finalized = false;
   int row_shard = 0;
   int64_t M = 0;       // n_params

@@ -41,6 +41,15 @@ struct VmOt {       // operand table entry resolved for this block (kept in shar
   int flags;
 };
 
+struct VmDec {       // a micro-op pre-decoded for this block (shared memory), 32 bytes: all the shared-memory fast path reads
+  uint32_t w0;       // op | dist << 8 | darg << 16 | flags << 24
+  uint32_t w1;       // reduction slot | gen << 8 (bit k: operand k is a tape array in HBM) | sel << 16 (2 bits per operand:
+                     //   1 = "+ tid, stride NT" (local), 2 = "+ chain lane" (per-chain scalar))
+  int b0, b1, b2, bd;   // shared-memory indices of operands 0..2 and of the local destination, before the per-thread term
+  uint32_t ot;       // operand-table entries o[0] | o[1] << 8 | o[2] << 16 | o[3] << 24 (generic path)
+  uint32_t st;       // operand-table entry of the array destination
+};
+
 struct VmArgs {
   const VmDevUop* uops;
   const VmDevOpd* ot;
@@ -151,8 +160,9 @@ __global__ void __launch_bounds__(NT) k_vm(VmArgs a) {
   extern __shared__ __align__(16) double vsmd[];
   unsigned char* vsm = (unsigned char*)vsmd;
   VmDevUop* U = (VmDevUop*)vsm;                                   // [n_uops]
-  VmOt* OT = (VmOt*)(vsm + (size_t)((a.n_uops + 1) & ~1) * 16);   // [n_ot]
-  const int sc_off = (((a.n_uops + 1) & ~1) * 16 + a.n_ot * 32) / 8;   // (indices in doubles from vsmd)
+  VmDec* DEC = (VmDec*)(vsm + (size_t)((a.n_uops + 1) & ~1) * 16);   // [n_uops]
+  VmOt* OT = (VmOt*)(DEC + a.n_uops);                             // [n_ot]
+  const int sc_off = (((a.n_uops + 1) & ~1) * 16 + a.n_uops * 32 + a.n_ot * 32) / 8;   // (indices in doubles from vsmd)
   const int lc_off = sc_off + max(1, a.n_scal) * a.tcc;
   double* Sc = vsmd + sc_off;                                     // [max(1, n_scal)][tcc]
   double* Lc = vsmd + lc_off;                                     // [n_loc][V][NT]
@@ -182,35 +192,52 @@ __global__ void __launch_bounds__(NT) k_vm(VmArgs a) {
   }
   for (int k = 0; k < a.n_red; k++) Rd[k * NT + tid] = 0.0;
   __syncthreads();
+  for (int u = tid; u < a.n_uops; u += NT) {
+    const VmDevUop uo = U[u];
+    const VmOt t0 = OT[uo.o[0]], t1 = OT[uo.o[1]], t2 = OT[uo.o[2]];
+    VmDec d;
+    d.w0 = (uint32_t)uo.op | ((uint32_t)uo.dist << 8) | ((uint32_t)uo.darg << 16) | ((uint32_t)uo.flags << 24);
+    const uint32_t gen = (t0.gbase ? 1u : 0u) | (t1.gbase ? 2u : 0u) | (t2.gbase ? 4u : 0u);
+    const uint32_t sel = (uint32_t)(t0.flags & 3) | ((uint32_t)(t1.flags & 3) << 2) | ((uint32_t)(t2.flags & 3) << 4);
+    d.w1 = (uint32_t)uo.red | (gen << 8) | (sel << 16);
+    d.b0 = t0.off; d.b1 = t1.off; d.b2 = t2.off; d.bd = OT[uo.dst].off;
+    d.ot = (uint32_t)uo.o[0] | ((uint32_t)uo.o[1] << 8) | ((uint32_t)uo.o[2] << 16) | ((uint32_t)uo.o[3] << 24);
+    d.st = uo.store;
+    DEC[u] = d;
+  }
+  __syncthreads();
 
   if (active) {
     const long long e0 = (long long)blockIdx.y * a.chunk, e1 = min(a.n, e0 + a.chunk);
     for (long long eb = e0 + ey; eb < e1; eb += (long long)eyn * V) {
       const int vc = (int)min((long long)V, (e1 - eb + eyn - 1) / eyn);   // elements eb + v*eyn, v < vc
       for (int u = 0; u < a.n_uops; u++) {
-        const VmDevUop uo = U[u];
-        const int fl = uo.flags;
-        const VmOt t0 = OT[uo.o[0]], t1 = OT[uo.o[1]], t2 = OT[uo.o[2]];
+        const uint4 wa = ((const uint4*)DEC)[2 * u], wb = ((const uint4*)DEC)[2 * u + 1];
+        struct { int op, dist, darg, red; } uo;
+        uo.op = wa.x & 0xff; uo.dist = (wa.x >> 8) & 0xff; uo.darg = (wa.x >> 16) & 0xff; uo.red = wa.y & 0xff;
+        const int fl = wa.x >> 24;
+        const int gen = (wa.y >> 8) & 0xff, sel = (wa.y >> 16) & 0xff;
         // shared-memory operands: index of element 0 and stride (0 for a per-chain scalar, NT for a local)
-        const int i0 = t0.off + ((t0.flags & 1) ? tid : 0) + ((t0.flags & 2) ? cx : 0);
-        const int i1 = t1.off + ((t1.flags & 1) ? tid : 0) + ((t1.flags & 2) ? cx : 0);
-        const int i2 = t2.off + ((t2.flags & 1) ? tid : 0) + ((t2.flags & 2) ? cx : 0);
-        double* const pd = vsmd + OT[uo.dst].off + tid;
-        if (!t0.gbase && !t1.gbase && !t2.gbase && (fl == VMF_WRITE || fl == VMF_REDUCE)) {
+        const int i0 = (int)wa.z + ((sel & 1) ? tid : 0) + ((sel & 2) ? cx : 0);
+        const int i1 = (int)wa.w + ((sel & 4) ? tid : 0) + ((sel & 8) ? cx : 0);
+        const int i2 = (int)wb.x + ((sel & 16) ? tid : 0) + ((sel & 32) ? cx : 0);
+        double* const pd = vsmd + (int)wb.y + tid;
+        if (gen == 0 && (fl == VMF_WRITE || fl == VMF_REDUCE)) {
           const double *p0 = vsmd + i0, *p1 = vsmd + i1, *p2 = vsmd + i2;
-          const int s0 = (t0.flags & 1) ? NT : 0, s1 = (t1.flags & 1) ? NT : 0, s2 = (t2.flags & 1) ? NT : 0;
+          const int s0 = (sel & 1) ? NT : 0, s1 = (sel & 4) ? NT : 0, s2 = (sel & 16) ? NT : 0;
           const double *pa = nullptr;
           double* ps = nullptr;
           const int sa = 0, ss = 0;
           VM_SWITCH
         } else {
+          const VmOt t0 = OT[wb.z & 0xff], t1 = OT[(wb.z >> 8) & 0xff], t2 = OT[(wb.z >> 16) & 0xff];
           const double* p0 = t0.gbase ? t0.gbase + ((t0.flags & 2) ? cx : 0) + eb * t0.Cc : vsmd + i0;
           const double* p1 = t1.gbase ? t1.gbase + ((t1.flags & 2) ? cx : 0) + eb * t1.Cc : vsmd + i1;
           const double* p2 = t2.gbase ? t2.gbase + ((t2.flags & 2) ? cx : 0) + eb * t2.Cc : vsmd + i2;
           const long long s0 = t0.gbase ? t0.S : ((t0.flags & 1) ? NT : 0);
           const long long s1 = t1.gbase ? t1.S : ((t1.flags & 1) ? NT : 0);
           const long long s2 = t2.gbase ? t2.S : ((t2.flags & 1) ? NT : 0);
-          const VmOt ta = OT[uo.o[3]], ts = OT[uo.store];
+          const VmOt ta = OT[(wb.z >> 24) & 0xff], ts = OT[wb.w & 0xff];
           const double* pa = ta.gbase ? ta.gbase + ((ta.flags & 2) ? cx : 0) + eb * ta.Cc
                                       : vsmd + ta.off + ((ta.flags & 1) ? tid : 0) + ((ta.flags & 2) ? cx : 0);
           const long long sa = ta.gbase ? ta.S : ((ta.flags & 1) ? NT : 0);
@@ -543,7 +570,7 @@ int smc_vm_launch(smc_model_s* m, SmcProgram& pr, int64_t C, int* bad) {
   a.S = (int)S;
   // V = elements a thread processes per decode of a micro-op: as many as the locals' shared-memory budget allows
   const long long per_thread = (a.chunk + eyn - 1) / eyn;
-  const size_t fixed = nu2 * 16 + (size_t)pr.n_ot * 32 + std::max<size_t>(1, ns) * tcc * 8 + (size_t)a.n_red * NT * 8;
+  const size_t fixed = nu2 * 16 + nu * 32 + (size_t)pr.n_ot * 32 + std::max<size_t>(1, ns) * tcc * 8 + (size_t)a.n_red * NT * 8;
   const size_t budget = 96 * 1024;   // two blocks per SM (three blocks at 80 registers measured slower: spills)
   long long vmax = pr.n_loc > 0 ? (long long)((budget > fixed ? budget - fixed : 0) / ((size_t)pr.n_loc * NT * 8)) : 32;
   vmax = std::max<long long>(1, std::min<long long>(vmax, 32));

@@ -90,15 +90,17 @@ for (jl, sym) in ((:hmc_run, :smc_hmc_run), (:rwm_run, :smc_rwm_run), (:nuts_run
         rate   = Vector{Float64}(undef, chains)
         eps    = Array{Float64}(undef, chains, steps)
         jmax   = Array{Float64}(undef, chains, steps)
+        final, mean, m2, first, lag1 = (Array{Float64}(undef, M, chains) for _ in 1:5)   # = [C][M] in C order
         cfg = Ref(SamplerConfig(steps, burnin, isteps, stepsize, seed, 0, 1, 0, C_NULL, C_NULL, 0))
-        out = RunOutput(pointer(draws), pointer(loglik), pointer(accept), C_NULL, pointer(rate), C_NULL, C_NULL,
-                        pointer(eps), pointer(jmax), 0.0, 0, 0, 0)
-        GC.@preserve draws loglik accept rate eps jmax begin
+        out = RunOutput(pointer(draws), pointer(loglik), pointer(accept), pointer(final), pointer(rate), pointer(mean), pointer(m2),
+                        pointer(eps), pointer(jmax), 0.0, 0, 0, 0, pointer(first), pointer(lag1))
+        GC.@preserve draws loglik accept rate eps jmax final mean m2 first lag1 begin
             check(ccall(($(QuoteNode(sym)), lib), Cint, (Ptr{Cvoid}, Ref{SamplerConfig}, Ptr{Float64}, Int64, Ref{RunOutput}),
                         m.h, cfg, init, chains, out))
         end
-        (draws=draws, loglik=loglik, accept=accept, accept_rate=rate, epsilon=eps, jmax=jmax,
-         device_ms=out.device_ms, n_leapfrogs=out.n_leapfrogs)
+        # calcStats! (src/samplers.jl:352-374) needs only mean, m2, first, lag1 and final (see api.py::_finish for the formula)
+        (draws=draws, loglik=loglik, accept=accept, accept_rate=rate, epsilon=eps, jmax=jmax, final_state=final,
+         mean=mean, m2=m2, first=first, lag1=lag1, device_ms=out.device_ms, n_leapfrogs=out.n_leapfrogs)
     end
 end
 

@@ -647,10 +647,8 @@ static int run_statement(smc_model_s* m, const smc_tape_stmt& s, int64_t C, bool
         // split the contraction when the output alone gives each SM fewer than ~32 warps of work (e.g. transpose(X) * ds
         // with few output rows: every thread would walk the whole k loop alone, latency bound)
         long long S = 1;
-        long long blocks = ctiles * gtiles * a.n;
         const long long warps = C * groups * a.n / 32, want = 32LL * m->ctx->sm_count;
         if (warps < want && a.k >= 64) S = std::min<long long>((want + warps - 1) / std::max<long long>(warps, 1), a.k / 32);
-        (void)blocks;
         g.chunk = ((a.k + S - 1) / S + 31) / 32 * 32;
         S = (a.k + g.chunk - 1) / g.chunk;
         g.S = (int)S;

@@ -74,10 +74,13 @@ template <int FAM>
 __device__ __forceinline__ void family_eval(double eta, double y, double inv_s, double neg_inv_s2, bool valid, double& lacc,
                                             double& d) {
   if (FAM == SMC_GLM_NORMAL) {
+    // Two FP64 instructions per (row, chain): DMMA and DFMA/DMUL share the FP64 pipe (ncu: tensor-FP64 % + pipe_fp64 % =
+    // SM throughput), so every multiply here is DMMA time.  The 1/sigma^2 factors of both l and dl/deta are applied
+    // once per chain in the epilogues: lacc accumulates sum w^2, the second product runs on w itself.
     double w = eta - y;
-    double r = w * inv_s;
-    lacc = fma(r, r, lacc);   // accumulates sum r^2 ; scaled by -1/2 in the epilogue
-    d = w * neg_inv_s2;
+    lacc = fma(w, w, lacc);
+    d = w;
+    (void)inv_s; (void)neg_inv_s2;
   } else {
     double e = exp(eta), t4 = 1.0 + e, p = 1.0 / t4;
     bool one = (y == 1.0);
@@ -294,9 +297,11 @@ __global__ void __launch_bounds__(NWC* NWR * 32, (MP8 <= 2 ? 2 : 1)) k_glm(GlmAr
     if (c >= a.C) continue;
     double v = Gs[i];
     if (j == MP) {
-      if (FAM == SMC_GLM_NORMAL) v = -0.5 * v + lconst;
+      if (FAM == SMC_GLM_NORMAL) v = 0.5 * neg_inv_s2 * v + lconst;   // -sum (w/sigma)^2 / 2 - n log(sigma sqrt(2 pi))
       // a -inf / NaN sum means some observation had zero density ("give up eval", src/distribs.jl:15,17)
       if (!(v > -INFINITY)) a.bad[c] = 1;
+    } else if (FAM == SMC_GLM_NORMAL) {
+      v *= neg_inv_s2;                                                  // X' dl/deta = -(X' w) / sigma^2
     } else if (a.neg_out) {
       v = -v;
     }
@@ -471,13 +476,13 @@ __global__ void __launch_bounds__(256) k_glm_stream(GlmStreamArgs a) {
     for (int w = 0; w < 8; w++) v += red[w][i];
     if (j == MB) {
       if (FAM == SMC_GLM_NORMAL) {
-        v = -0.5 * v;
+        v = 0.5 * neg_inv_s2 * v;
         if (blockIdx.x == 0) v += (double)a.N * (-log(a.par) - SMC_LOG_SQRT_2PI);
       }
       if (!(v > -INFINITY)) a.bad[c] = 1;
       part[(long long)a.MP * a.Cpad + c] = v;
     } else {
-      part[(long long)j * a.Cpad + c] = a.neg_out ? -v : v;
+      part[(long long)j * a.Cpad + c] = FAM == SMC_GLM_NORMAL ? v * neg_inv_s2 : (a.neg_out ? -v : v);
     }
   }
 }

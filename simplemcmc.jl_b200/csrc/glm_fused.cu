@@ -152,7 +152,9 @@ __global__ void __launch_bounds__(NWC* NWR * 32, (MP8 <= 2 ? 2 : 1)) k_glm(GlmAr
   //    (the extra address arithmetic inside the DMMA loop costs more than the burst);
   //  * full/empty mbarriers (cp.async.mbarrier.arrive) with two tiles in flight instead of the CTA-wide barrier, with
   //    and without starting the upper half of the warps 0.2-3 us late so that the two warps of a scheduler run out of
-  //    phase: 32.9 ms at 254 registers, independent of the skew.
+  //    phase: 32.9 ms at 254 registers, independent of the skew;
+  //  * even / odd k-steps of product 1 on separate accumulators (four independent DMMA chains per warp instead of
+  //    two): 32.4 ms -- the dependent-DMMA latency is not what leaves the pipe idle.
   auto load_tile = [&](int t) {
     if (t < ntiles) {
       double* xs = Xs + (t % NST) * RT * LD;

@@ -134,6 +134,32 @@ def test_tape_identities_and_dead_statement_elimination():
     assert sum(1 for s in low.tape_fwd + low.tape_bwd if s.op == lowering.OP["MATMUL"]) == 4
 
 
+def test_linear_tape_is_three_statements_after_the_host_rewrites():
+    """accumulator coalescing + literal seed + adjoint names (fusion.py, lowering.py): prior program, GLM (accumulating),
+    gradient program -- and the result register is the one both forward statements write"""
+    X, Y, _ = linear_data()
+    low = Lowering(LINEAR, [("beta", np.zeros(10))], dict(X=X, Y=Y))
+    low.serialise()
+    assert [s.op for s in low.tape_fwd] == [49, lowering.OP["GLM"]] and [s.op for s in low.tape_bwd] == [49]
+    assert low.tape_fwd[0].dst is low.tape_result and low.tape_fwd[1].dst is low.tape_result
+    assert low.tape_fwd[1].flags & lowering.F_ACC and not (low.tape_fwd[0].flags & lowering.F_ACC)
+    assert low.tape_bwd[0].dst.kind == lowering.REG_GRAD
+
+
+def test_sufficient_statistics_rewrite_of_the_ornstein_likelihood():
+    """opt-in: the length-T Normal density becomes scalar arithmetic on five header dot products (x.x, x.x', sum x, ...)"""
+    x = ou_data(500)
+    low = Lowering(ORNSTEIN, [("tau", 20.0), ("mu", 10.0), ("sigma", 0.1)], dict(x=x), sufficient_stats=True)
+    low.serialise()
+    hdr = [s for s in low.tape_fwd if s.dst.kind == lowering.REG_HDR]
+    assert sum(1 for s in hdr if s.dst.numel == 1) == 5                       # G = [[x1.x1, x1.x0, sum x1], [., x0.x0, sum x0], [., ., n]]
+    body = [s for s in low.tape_fwd + low.tape_bwd if s.dst.kind != lowering.REG_HDR]
+    assert all(s.op == 49 for s in body) and all(pr.n == 1 for pr in low.programs)   # only scalar programs are left
+    plain = Lowering(ORNSTEIN, [("tau", 20.0), ("mu", 10.0), ("sigma", 0.1)], dict(x=x))
+    plain.serialise()
+    assert any(pr.n == 499 for pr in plain.programs)                            # the default keeps the element-wise tape
+
+
 def test_programs_pack_for_index_spaces_beyond_16_bits():
     """cfg5 at T = 1e6: a program's index-space length lives in its header, not in a 16-bit instruction field"""
     import struct

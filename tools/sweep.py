@@ -18,7 +18,7 @@ if "cfg1" in which:
     rows = []
     for C in (1, 1024, 65536, 1 << 20):
         low, dev = api._build(LINEAR, [("beta", np.zeros(10))], dict(X=X, Y=Y), True, C, 0, "assign")
-        steps = 2000 if C == 1 else (200 if C <= 65536 else 40)
+        steps = 2000 if C == 1 else (200 if C <= 65536 else 120)
         dev.run("hmc", mode, C, 5, 0, isteps=2, stepsize=0.05, seed=1, store_draws=False, want=())
         raw = dev.run("hmc", mode, C, steps, 0, isteps=2, stepsize=0.05, seed=2, store_draws=False, want=())
         dev.eval(np.tile(mode, (C, 1)))

@@ -74,8 +74,8 @@ enum {
   SMC_GLM_NORMAL = 0,    /* l = logpdfNormal(0, sigma, a*eta + b_i);      imm = sigma, aux1 = sign bits of a, b
                             (+ SMC_GLM_F_GRAM)                                                                     */
   SMC_GLM_BERNOULLI = 1, /* l = logpdfBernoulli(1/(1+exp(s*eta)), y_i);   aux1 = 1 when s = -1                  */
-  SMC_GLM_BINOMIAL = 2,  /* l = logpdfBinomial(n, 1/(1+exp(s*eta)), y_i); imm = n                                */
-  SMC_GLM_POISSON = 3    /* l = logpdfPoisson(exp(s*eta), y_i)                                                   */
+  SMC_GLM_BINOMIAL = 2,  /* l = logpdfBinomial(n, 1/(1+exp(s*eta)), y_i); imm = n, aux1 = 1 when s = -1                */
+  SMC_GLM_POISSON = 3    /* l = logpdfPoisson(exp(s*eta), y_i)   (reserved: not emitted by the host yet)               */
 };
 
 /* aux1 flag of a NORMAL GLM statement: evaluate from the sufficient statistics X'X, X'y, y'y (computed once when the model

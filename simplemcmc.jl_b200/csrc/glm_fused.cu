@@ -42,6 +42,7 @@ struct GlmArgs {
   double par;
   int neg_beta;  // BERNOULLI with prob = 1/(1+exp(-eta)): the contraction runs on -beta, so it yields u = -eta directly
   int neg_out;   // ... and G = X' dl/deta = -(X' dl/du)
+  double lc_sum;  // BINOMIAL: sum over this rank's rows of lchoose(n, y_i)
   GlmPub pub;    // single row split on a single rank: the epilogue publishes (L, G) itself, no partial buffer / reduce kernel
 };
 
@@ -81,11 +82,20 @@ __device__ __forceinline__ void family_eval(double eta, double y, double inv_s, 
     lacc = fma(w, w, lacc);
     d = w;
     (void)inv_s; (void)neg_inv_s2;
-  } else {
+  } else if (FAM == SMC_GLM_BERNOULLI) {
     double e = exp(eta), t4 = 1.0 + e, p = 1.0 / t4;
     bool one = (y == 1.0);
     double l = log(one ? p : 1.0 - p);
     d = one ? -e * p : p;
+    lacc += valid ? l : 0.0;
+  } else {
+    // BINOMIAL counts, n trials (passed in inv_s): l = lchoose(n, y) + y log p + (n - y) log(1 - p)   (dbinom, src/distribs.jl:43);
+    // lchoose does not depend on the chain: its sum over the rows is added once per chain in the epilogue.
+    //   dl/du = exp(u) * (-1/t4^2) * (y/p - (n-y)/(1-p)) = n p - y                        (src/diff.jl:169-170,73,45)
+    const double n = inv_s;
+    double e = exp(eta), t4 = 1.0 + e, p = 1.0 / t4;
+    double l = smc_xlogy(y, p) + smc_xlog1py(n - y, -p);
+    d = n * p - y;
     lacc += valid ? l : 0.0;
   }
 }
@@ -146,6 +156,7 @@ __global__ void __launch_bounds__(NWC* NWR * 32, (MP8 <= 2 ? 2 : 1)) k_glm(GlmAr
     inv_s = 1.0 / a.par;
     neg_inv_s2 = -1.0 / (a.par * a.par);
   }
+  if (FAM == SMC_GLM_BINOMIAL) inv_s = a.par;   // number of trials
 
   // Measured alternatives that did NOT help on cfg2 (32.07 ms per launch as written):
   //  * issuing this copy a few chunks per row-block iteration instead of in one burst after the barrier: 33.98 ms
@@ -300,6 +311,7 @@ __global__ void __launch_bounds__(NWC* NWR * 32, (MP8 <= 2 ? 2 : 1)) k_glm(GlmAr
     double v = Gs[i];
     if (j == MP) {
       if (FAM == SMC_GLM_NORMAL) v = 0.5 * neg_inv_s2 * v + lconst;   // -sum (w/sigma)^2 / 2 - n log(sigma sqrt(2 pi))
+      if (FAM == SMC_GLM_BINOMIAL && blockIdx.y == 0) v += a.lc_sum;
       // a -inf / NaN sum means some observation had zero density ("give up eval", src/distribs.jl:15,17)
       if (!(v > -INFINITY)) a.bad[c] = 1;
     } else if (FAM == SMC_GLM_NORMAL) {
@@ -375,6 +387,21 @@ __global__ void k_fill_y(const double* src, double imm_or_bcast, double scale, d
   }
 }
 
+// partial sums of lchoose(n, y_i) (one per block, summed in order on the host at prepare time)
+__global__ void __launch_bounds__(256) k_binom_const(const double* y, long long N, double n, double* part) {
+  __shared__ double sh[256];
+  double t = 0.0;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < N; i += (long long)gridDim.x * 256)
+    t += lgamma(n + 1.0) - lgamma(y[i] + 1.0) - lgamma(n - y[i] + 1.0);
+  sh[threadIdx.x] = t;
+  __syncthreads();
+  for (int h = 128; h >= 1; h >>= 1) {
+    if ((int)threadIdx.x < h) sh[threadIdx.x] += sh[threadIdx.x + h];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) part[blockIdx.x] = sh[0];
+}
+
 __global__ void k_to_row_major(const double* Xcm, double* Xrm, long long N, int M, int MP) {
   long long total = N * MP;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -392,6 +419,7 @@ __global__ void k_to_row_major(const double* Xcm, double* Xrm, long long N, int 
 // full coalesced line, no padded columns are read), forms eta for CT chains, evaluates the family and accumulates
 // G[j][chain] += d * x[j] in registers.  Algorithmic bytes = bytes moved: 8*N*M + 8*N per evaluation.
 struct GlmStreamArgs {
+  double lc_sum;       // BINOMIAL: sum of lchoose(n, y_i) over the rows
   const double* X;     // [M][N] column major
   const double* y;     // [N] sign-normalised response
   const double* beta;  // [M][Cpad]
@@ -427,6 +455,7 @@ __global__ void __launch_bounds__(256) k_glm_stream(GlmStreamArgs a) {
     inv_s = 1.0 / a.par;
     neg_inv_s2 = -1.0 / (a.par * a.par);
   }
+  if (FAM == SMC_GLM_BINOMIAL) inv_s = a.par;
   // software pipeline over this thread's rows: the loads of the next row are in flight while the family stage
   // (exp / divide / log) of the current one runs
   const long long stride = (long long)gridDim.x * 256;
@@ -481,6 +510,7 @@ __global__ void __launch_bounds__(256) k_glm_stream(GlmStreamArgs a) {
         v = 0.5 * neg_inv_s2 * v;
         if (blockIdx.x == 0) v += (double)a.N * (-log(a.par) - SMC_LOG_SQRT_2PI);
       }
+      if (FAM == SMC_GLM_BINOMIAL && blockIdx.x == 0) v += a.lc_sum;
       if (!(v > -INFINITY)) a.bad[c] = 1;
       part[(long long)a.MP * a.Cpad + c] = v;
     } else {
@@ -714,7 +744,7 @@ int smc_glm_prepare(smc_model_s* m, SmcGlmPlan& g) {
   g.N = X.d.rows;
   g.M = (int)X.d.cols;
   if (g.M < 1 || g.M > 64 || (int64_t)B.numel != g.M) { smc_set_error("GLM: unsupported width M=%d (1..64)", g.M); return SMC_ERR_INVALID; }
-  if (g.family != SMC_GLM_NORMAL && g.family != SMC_GLM_BERNOULLI) { smc_set_error("GLM: family %d is not implemented", g.family); return SMC_ERR_INVALID; }
+  if (g.family != SMC_GLM_NORMAL && g.family != SMC_GLM_BERNOULLI && g.family != SMC_GLM_BINOMIAL) { smc_set_error("GLM: family %d is not implemented", g.family); return SMC_ERR_INVALID; }
   g.MP = g.M <= 16 ? 16 : (g.M <= 32 ? 32 : 64);
   cudaStream_t st = m->ctx->stream;
   g.Xcm = X.dev;   // the row-major padded copy for the DMMA kernel is built on its first launch (smc_glm_launch)
@@ -735,6 +765,19 @@ int smc_glm_prepare(smc_model_s* m, SmcGlmPlan& g) {
   m->ctx->launches++;
   g.y = g.ybuf;
   g.y_len = g.N;
+  g.lc_sum = 0.0;
+  if (g.family == SMC_GLM_BINOMIAL) {
+    const int nb = (int)std::max<long long>(1, std::min<long long>((g.N + 255) / 256, 2LL * m->ctx->sm_count));
+    double* part = nullptr;
+    SMC_CUDA(cudaMalloc(&part, (size_t)nb * sizeof(double)));
+    k_binom_const<<<nb, 256, 0, st>>>(g.y, g.N, g.par, part);
+    m->ctx->launches++;
+    std::vector<double> h(nb);
+    SMC_CUDA(cudaMemcpyAsync(h.data(), part, (size_t)nb * sizeof(double), cudaMemcpyDeviceToHost, st));
+    SMC_CUDA(cudaStreamSynchronize(st));
+    cudaFree(part);
+    for (double v : h) g.lc_sum += v;
+  }
   g.gram = (g.family == SMC_GLM_NORMAL && (g.sign_neg & SMC_GLM_F_GRAM) && !m->row_shard) ? 1 : 0;
   if (g.gram) {
     const int P = g.M + 1, PP = P * P;
@@ -823,7 +866,8 @@ int smc_glm_launch(smc_model_s* m, SmcGlmPlan& g, int64_t C) {
   a.part = g.part; a.bad = m->bad;
   a.N = g.N; a.rows_per_split = rows_per_split; a.C = C; a.Cpad = m->Cpad; a.M = g.M;
   a.par = g.par;
-  a.neg_beta = a.neg_out = (g.family == SMC_GLM_BERNOULLI && (g.sign_neg & 1)) ? 1 : 0;
+  a.neg_beta = a.neg_out = (g.family != SMC_GLM_NORMAL && (g.sign_neg & 1)) ? 1 : 0;
+  a.lc_sum = g.lc_sum;
   const bool sharded = m->row_shard && m->ctx->nranks > 1;
   a.pub.Ldst = m->regs[s.dst].dev; a.pub.Gdst = m->regs[s.aux2].dev; a.pub.acc = (s.flags & SMC_F_ACC) ? 1 : 0;
   a.pub.on = (!stream && RS == 1 && !sharded) ? 1 : 0;
@@ -833,15 +877,17 @@ int smc_glm_launch(smc_model_s* m, SmcGlmPlan& g, int64_t C) {
     GlmStreamArgs sa;
     sa.X = g.Xcm; sa.y = a.y; sa.beta = a.beta; sa.part = a.part; sa.bad = a.bad;
     sa.N = g.N; sa.C = C; sa.Cpad = m->Cpad; sa.M = g.M; sa.MP = g.MP; sa.par = g.par;
-    sa.neg_beta = a.neg_beta; sa.neg_out = a.neg_out;
+    sa.neg_beta = a.neg_beta; sa.neg_out = a.neg_out; sa.lc_sum = g.lc_sum;
     const int MB = g.M <= 8 ? 8 : (g.M <= 16 ? 16 : 32);
     const int CT = C == 1 ? 1 : (C == 2 ? 2 : 4);
     dim3 grid((unsigned)RS, (unsigned)((C + CT - 1) / CT));
-    rc = g.family == SMC_GLM_NORMAL ? launch_stream<SMC_GLM_NORMAL>(sa, MB, CT, grid, st)
-                                    : launch_stream<SMC_GLM_BERNOULLI>(sa, MB, CT, grid, st);
+    rc = g.family == SMC_GLM_NORMAL      ? launch_stream<SMC_GLM_NORMAL>(sa, MB, CT, grid, st)
+         : g.family == SMC_GLM_BERNOULLI ? launch_stream<SMC_GLM_BERNOULLI>(sa, MB, CT, grid, st)
+                                         : launch_stream<SMC_GLM_BINOMIAL>(sa, MB, CT, grid, st);
   } else {
-    rc = g.family == SMC_GLM_NORMAL ? launch_fam<SMC_GLM_NORMAL>(a, g.MP, tc, RS, st)
-                                    : launch_fam<SMC_GLM_BERNOULLI>(a, g.MP, tc, RS, st);
+    rc = g.family == SMC_GLM_NORMAL      ? launch_fam<SMC_GLM_NORMAL>(a, g.MP, tc, RS, st)
+         : g.family == SMC_GLM_BERNOULLI ? launch_fam<SMC_GLM_BERNOULLI>(a, g.MP, tc, RS, st)
+                                         : launch_fam<SMC_GLM_BINOMIAL>(a, g.MP, tc, RS, st);
   }
   if (rc != SMC_OK) return rc;
   if (m->time_glm) {

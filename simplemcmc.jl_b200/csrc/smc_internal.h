@@ -64,6 +64,7 @@ struct SmcGlmPlan {  // one SMC_OP_GLM statement, prepared at finalize
   double* part = nullptr;  // partial (L,G) buffers [RS][MP+1][Cpad]
   int64_t part_cap = 0;
   float last_ms = 0.f;
+  double lc_sum = 0.0;     // BINOMIAL: sum_i lchoose(n, y_i) over the local rows
   int gram = 0;            // SMC_GLM_F_GRAM: evaluate from Z'Z with Z = [X, ytilde]
   double* ZtZ = nullptr;   // [(M+1)][(M+1)] row major
 };

@@ -27,7 +27,7 @@ DIST_ARITY = dict(Normal=3, Uniform=3, Weibull=3, Beta=3, TDist=2, Exponential=2
                   Bernoulli=2, Binomial=3, Poisson=2, TestDiff=1)
 # arguments with no adjoint: integer-valued ones (src/diff.jl:164-174)
 DIST_NODERIV = dict(Bernoulli={1}, Binomial={0, 2}, Poisson={1})
-GLM_NORMAL, GLM_BERNOULLI = 0, 1
+GLM_NORMAL, GLM_BERNOULLI, GLM_BINOMIAL = 0, 1, 2
 
 ACC_SYM = "__acc"   # src/SimpleMCMC.jl:14
 
@@ -591,6 +591,15 @@ class Lowering(object):
             return None
         dead.append(div)
         lp = self._single_use(div.dst)
+        if lp is not None and lp.op == OP["LOGPDF"] and lp.aux0 == DIST["Binomial"] and lp.srcs[1] is div.dst:
+            # counts: logpdfBinomial(n, prob, Y) with a literal number of trials (src/distribs.jl:43, adjoint src/diff.jl:169-170)
+            ntr, _, y = lp.srcs
+            if not is_const(ntr) or ntr.imm < 0 or ntr.imm != round(ntr.imm) or y.kind != REG_DATA or y.numel != N:
+                return None
+            yv = self.data_slots[y.slot][1]
+            if not np.all((yv >= 0) & (yv <= ntr.imm) & (yv == np.round(yv))):     # outside the support: leave it to the generic path
+                return None
+            return GLM_BINOMIAL, sign, ntr.imm, y, lp, dead
         if lp is None or lp.op != OP["LOGPDF"] or lp.aux0 != DIST["Bernoulli"] or lp.srcs[0] is not div.dst:
             return None
         y = lp.srcs[1]

@@ -121,6 +121,29 @@ def test_glm_few_chains_stream_path(smc, N, M, C):
         dev.close(); dev2.close()
 
 
+@pytest.mark.parametrize("C", [1, 3, 19])
+@pytest.mark.parametrize("N,M", [(1000, 10), (4099, 33)])
+def test_binomial_count_glm(smc, N, M, C):
+    """cfg3's count variant: Y ~ Binomial(20, 1/(1+exp(+-X*vars))) runs on the fused GLM kernels (stream kernel for few
+    chains, DMMA kernel otherwise); lchoose(n, y) is summed once per model, not per chain"""
+    from simplemcmc_jl_b200 import api
+    rng = np.random.default_rng(N + C)
+    X = np.column_stack([np.ones(N), rng.standard_normal((N, M - 1))])
+    b0 = 0.3 * rng.standard_normal(M)
+    Y = rng.binomial(20, 1.0 / (1.0 + np.exp(X @ b0))).astype(np.float64)
+    data = dict(X=X, Y=Y)
+    betas = b0[None, :] + 0.1 * rng.standard_normal((C, M))
+    for link in ("exp(X * vars)", "exp(-(X * vars))"):
+        model = "vars ~ Normal(0, 1.0)\nprob = 1 / (1. + %s)\nY ~ Binomial(20, prob)" % link
+        ref = generate_model_function(model, data=data, gradient=True, vars=np.zeros(M))
+        low, dev = api._build(model, [("vars", np.zeros(M))], data, True, C, 0, "assign")
+        assert low.n_fused == 1
+        lp, g = dev.eval(betas)
+        for c in range(C):
+            _check(lp[c], g[c], *ref(betas[c]))
+        dev.close()
+
+
 def test_sufficient_statistics_variant(smc):
     """opt-in `sufficient_stats=True`: a Normal identity-link regression evaluated from X'X, X'y, y'y (2*M^2 flops per chain
     instead of 4*N*M).  Not the reference's arithmetic -- the tolerance is 1e-10 (cancellation in beta'X'X beta - 2 beta'X'y + y'y),

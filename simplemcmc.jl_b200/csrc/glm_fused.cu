@@ -677,7 +677,10 @@ int launch_cfg_tp(const GlmArgs& a, int RS, cudaStream_t st) {
 
 template <int FAM, int MT, int NWC, int NWR, int MP8, int TRIM>
 int launch_cfg_t(const GlmArgs& a, int RS, cudaStream_t st) {
-  return a.pub.on ? launch_cfg_tp<FAM, MT, NWC, NWR, MP8, TRIM, 1>(a, RS, st) : launch_cfg_tp<FAM, MT, NWC, NWR, MP8, TRIM, 0>(a, RS, st);
+  if constexpr (MP8 == 2) {   // (the self-publishing variant is only built for narrow models: it matters for small N)
+    if (a.pub.on) return launch_cfg_tp<FAM, MT, NWC, NWR, MP8, TRIM, 1>(a, RS, st);
+  }
+  return launch_cfg_tp<FAM, MT, NWC, NWR, MP8, TRIM, 0>(a, RS, st);
 }
 
 template <int FAM, int MT, int NWC, int NWR, int MP8>
@@ -870,7 +873,7 @@ int smc_glm_launch(smc_model_s* m, SmcGlmPlan& g, int64_t C) {
   a.lc_sum = g.lc_sum;
   const bool sharded = m->row_shard && m->ctx->nranks > 1;
   a.pub.Ldst = m->regs[s.dst].dev; a.pub.Gdst = m->regs[s.aux2].dev; a.pub.acc = (s.flags & SMC_F_ACC) ? 1 : 0;
-  a.pub.on = (!stream && RS == 1 && !sharded) ? 1 : 0;
+  a.pub.on = (!stream && RS == 1 && !sharded && g.MP == 16) ? 1 : 0;
   if (m->time_glm) SMC_CUDA(cudaEventRecord(m->ev0, st));
   int rc;
   if (stream) {

@@ -68,6 +68,21 @@ if "cfg3" in which:
                          glm_gbs_algorithmic=bytes_alg / (ms_glm * 1e-3) / 1e9, glm_gbs_padded=(8.0 * N * 16 + 8.0 * N) / (ms_glm * 1e-3) / 1e9))
         dev.close()
     out["cfg3_logistic_N1e7_M10_hmc_1gpu"] = rows
+    # the count variant of SURVEY.md 8(d): Y ~ Binomial(20, prob)
+    Yb = rng.binomial(20, 1.0 / (1.0 + np.exp(X @ b0))).astype(np.float64)
+    BINOM = "vars ~ Normal(0, 1.0)\nprob = 1 / (1. + exp(X * vars))\nY ~ Binomial(20, prob)"
+    rows = []
+    for C in (1, 64):
+        low, dev = api._build(BINOM, [("vars", np.zeros(M))], dict(X=X, Y=Yb), True, C, 0, "assign")
+        init = b0[None, :] + 1e-3 * rng.standard_normal((C, M))
+        raw = dev.run("hmc", init, C, 10, 0, isteps=2, stepsize=0.02 / np.sqrt(N / 1000), seed=1, store_draws=False, want=())
+        dev.eval(init)
+        ms_eval, ms_glm = dev.eval_timed(5, True)
+        rows.append(dict(chains=C, leapfrog_chain_steps_per_s=raw["n_leapfrogs"] / (raw["device_ms"] * 1e-3),
+                         accept=float(raw["accept_rate"].mean()), ms_eval=ms_eval, ms_glm=ms_glm,
+                         glm_gbs_algorithmic=(8.0 * N * M + 8.0 * N) / (ms_glm * 1e-3) / 1e9))
+        dev.close()
+    out["cfg3_binomial_counts_N1e7_M10_hmc_1gpu"] = rows
 
 if "cfg4" in which:
     data, nsub = sleepstudy_data()

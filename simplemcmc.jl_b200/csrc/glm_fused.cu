@@ -758,7 +758,7 @@ int smc_glm_prepare(smc_model_s* m, SmcGlmPlan& g) {
     int sa_neg = g.sign_neg & 1, sb_neg = (g.sign_neg >> 1) & 1;
     scale = (sa_neg != sb_neg) ? 1.0 : -1.0;   // ytilde = -sa*sb*y
   }
-  SMC_CUDA(cudaMalloc(&g.ybuf, (size_t)g.N * sizeof(double)));
+  SMC_CUDA(smc_dev_alloc(&g.ybuf, (size_t)g.N * sizeof(double), st));
   if (Y.d.kind == SMC_REG_IMM) {
     k_fill_y<<<(unsigned)std::min<long long>((g.N + 255) / 256, 148LL * 32), 256, 0, st>>>(nullptr, Y.d.imm, scale, g.ybuf, g.N);
   } else {
@@ -772,13 +772,13 @@ int smc_glm_prepare(smc_model_s* m, SmcGlmPlan& g) {
   if (g.family == SMC_GLM_BINOMIAL) {
     const int nb = (int)std::max<long long>(1, std::min<long long>((g.N + 255) / 256, 2LL * m->ctx->sm_count));
     double* part = nullptr;
-    SMC_CUDA(cudaMalloc(&part, (size_t)nb * sizeof(double)));
+    SMC_CUDA(smc_dev_alloc(&part, (size_t)nb * sizeof(double), st));
     k_binom_const<<<nb, 256, 0, st>>>(g.y, g.N, g.par, part);
     m->ctx->launches++;
     std::vector<double> h(nb);
     SMC_CUDA(cudaMemcpyAsync(h.data(), part, (size_t)nb * sizeof(double), cudaMemcpyDeviceToHost, st));
     SMC_CUDA(cudaStreamSynchronize(st));
-    cudaFree(part);
+    smc_dev_free(part, st);
     for (double v : h) g.lc_sum += v;
   }
   g.gram = (g.family == SMC_GLM_NORMAL && (g.sign_neg & SMC_GLM_F_GRAM) && !m->row_shard) ? 1 : 0;
@@ -789,24 +789,24 @@ int smc_glm_prepare(smc_model_s* m, SmcGlmPlan& g) {
     ga.X = g.Xcm; ga.y = g.y; ga.N = g.N; ga.M = g.M;
     ga.rows_per_block = ((g.N + nblocks - 1) / nblocks + 63) / 64 * 64;
     double* part = nullptr;
-    SMC_CUDA(cudaMalloc(&part, (size_t)nblocks * PP * sizeof(double)));
-    SMC_CUDA(cudaMalloc(&g.ZtZ, (size_t)PP * sizeof(double)));
+    SMC_CUDA(smc_dev_alloc(&part, (size_t)nblocks * PP * sizeof(double), st));
+    SMC_CUDA(smc_dev_alloc(&g.ZtZ, (size_t)PP * sizeof(double), st));
     ga.part = part;
     const size_t smem = (size_t)64 * (P + 1) * sizeof(double);
     k_gram_partial<<<nblocks, 256, smem, st>>>(ga);
     k_gram_reduce<<<(PP + 255) / 256, 256, 0, st>>>(part, nblocks, PP, g.ZtZ);
     m->ctx->launches += 2;
     SMC_CUDA(cudaStreamSynchronize(st));
-    cudaFree(part);
+    smc_dev_free(part, st);
   }
   return SMC_OK;
 }
 
-void smc_glm_release(SmcGlmPlan& g) {
-  if (g.Xrm) cudaFree(g.Xrm);
-  if (g.part) cudaFree(g.part);
-  if (g.ybuf) cudaFree(g.ybuf);
-  if (g.ZtZ) cudaFree(g.ZtZ);
+void smc_glm_release(SmcGlmPlan& g, cudaStream_t st) {
+  if (g.Xrm) smc_dev_free(g.Xrm, st);
+  if (g.part) smc_dev_free(g.part, st);
+  if (g.ybuf) smc_dev_free(g.ybuf, st);
+  if (g.ZtZ) smc_dev_free(g.ZtZ, st);
   g.ZtZ = nullptr;
   g.ybuf = nullptr;
   g.Xrm = nullptr;
@@ -843,7 +843,7 @@ int smc_glm_launch(smc_model_s* m, SmcGlmPlan& g, int64_t C) {
   }
   const bool stream = use_stream(g.M, C);
   if (!stream && !g.Xrm) {
-    SMC_CUDA(cudaMalloc(&g.Xrm, (size_t)g.N * g.MP * sizeof(double)));
+    SMC_CUDA(smc_dev_alloc(&g.Xrm, (size_t)g.N * g.MP * sizeof(double), st));
     k_to_row_major<<<(unsigned)std::min<long long>((g.N * g.MP + 255) / 256, 148LL * 64), 256, 0, st>>>(g.Xcm, g.Xrm, g.N, g.M, g.MP);
     m->ctx->launches++;
   }
@@ -858,9 +858,9 @@ int smc_glm_launch(smc_model_s* m, SmcGlmPlan& g, int64_t C) {
   if (need > g.part_cap) {
     m->graphs_stale = true;
     m->realloc_epoch++;
-    if (g.part) cudaFree(g.part);
+    if (g.part) smc_dev_free(g.part, st);
     g.part = nullptr;
-    SMC_CUDA(cudaMalloc(&g.part, (size_t)need * sizeof(double)));
+    SMC_CUDA(smc_dev_alloc(&g.part, (size_t)need * sizeof(double), st));
     g.part_cap = need;
   }
   GlmArgs a;

@@ -11,14 +11,15 @@
 
 namespace {
 
-struct Arena {
+struct Arena {  // buffers of one sampler call, returned to the context's pool (stream ordered) when the call ends
   std::vector<void*> ptrs;
-  ~Arena() { for (void* p : ptrs) cudaFree(p); }
+  cudaStream_t st = nullptr;
+  ~Arena() { for (void* p : ptrs) smc_dev_free(p, st); }
   template <typename T>
   int alloc(T** out, size_t n) {
     void* p = nullptr;
-    cudaError_t e = cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T));
-    if (e != cudaSuccess) { smc_set_error("cudaMalloc of %zu bytes failed: %s", n * sizeof(T), cudaGetErrorString(e)); return SMC_ERR_CUDA; }
+    cudaError_t e = smc_dev_alloc(&p, std::max<size_t>(n, 1) * sizeof(T), st);
+    if (e != cudaSuccess) { smc_set_error("device allocation of %zu bytes failed: %s", n * sizeof(T), cudaGetErrorString(e)); return SMC_ERR_CUDA; }
     ptrs.push_back(p);
     *out = (T*)p;
     return SMC_OK;
@@ -430,6 +431,7 @@ int run_setup(Run& r, const double* init, bool need_grad, long long nu) {
   r.M = m->M; r.Cpad = m->Cpad; r.samples = cfg->steps - cfg->burnin;
   long long C = r.C, M = r.M, Cpad = r.Cpad;
   r.launches0 = m->ctx->launches;
+  r.A.st = st;
   SMC_TRY(r.A.alloc(&r.b0, M * Cpad));
   SMC_TRY(r.A.alloc(&r.g0, M * Cpad));
   SMC_TRY(r.A.alloc(&r.l0, Cpad));
@@ -496,6 +498,7 @@ int copy_out_blocks(Run& r, const double* dev, double* host, long long nblocks, 
   long long chunk = std::max<long long>(1, std::min<long long>(nblocks, (64LL << 20) / std::max<long long>(per, 1)));
   double* stage;
   Arena local;
+  local.st = st;
   SMC_TRY(local.alloc(&stage, chunk * per));
   for (long long b = 0; b < nblocks; b += chunk) {
     long long nb = std::min(chunk, nblocks - b);
@@ -520,6 +523,7 @@ int copy_out_stats(Run& r, int k, double* host) {
   cudaStream_t st = r.m->ctx->stream;
   double* stage;
   Arena local;
+  local.st = st;
   SMC_TRY(local.alloc(&stage, r.C * r.M));
   k_out_stats<<<gride(r.C * r.M), 256, 0, st>>>(r.R.stats, k, r.C, r.M, stage);
   r.m->ctx->launches++;

@@ -94,13 +94,13 @@ extern "C" int smc_ctx_allreduce(smc_ctx_t ctx, double* host_inout, int64_t n) {
   if (ctx->nranks <= 1 || n == 0) return SMC_OK;
   cudaSetDevice(ctx->device);
   double* d = nullptr;
-  SMC_CUDA(cudaMalloc(&d, (size_t)n * sizeof(double)));
+  SMC_CUDA(smc_dev_alloc(&d, (size_t)n * sizeof(double), ctx->stream));
   SMC_CUDA(cudaMemcpyAsync(d, host_inout, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   int rc = smc_comm_allreduce_device(ctx, d, n);
   if (rc == SMC_OK) {
     SMC_CUDA(cudaMemcpyAsync(host_inout, d, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     SMC_CUDA(cudaStreamSynchronize(ctx->stream));
   }
-  cudaFree(d);
+  smc_dev_free(d, ctx->stream);
   return rc;
 }

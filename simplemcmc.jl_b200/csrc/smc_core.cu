@@ -7,6 +7,7 @@
 #include <string.h>
 #include <algorithm>
 #include <cmath>
+#include <mutex>
 #include "smc_internal.h"
 #include "dists.cuh"
 #include "exec_common.cuh"
@@ -20,6 +21,79 @@ void smc_set_error(const char* fmt, ...) {
 }
 extern "C" const char* smc_last_error(void) { return g_err; }
 extern "C" int smc_abi_version(void) { return SMC_ABI_VERSION; }
+
+// ------------------------------------------------------------------------------------------ device memory
+namespace {
+std::mutex g_pool_mu;
+std::vector<void*> g_deferred_free;  // frees requested while the stream was capturing
+int g_pool_mode = -1;                // -1 not decided, 0 cudaMalloc/cudaFree, 1 stream-ordered pool
+bool g_pool_ready[64] = {};
+
+bool pool_enabled() {
+  if (g_pool_mode < 0) {
+    const char* e = getenv("SMC_NO_POOL");
+    g_pool_mode = (e && e[0] && e[0] != '0') ? 0 : 1;
+  }
+  return g_pool_mode == 1;
+}
+void pool_configure() {  // once per device: keep freed blocks in the pool instead of returning them to the driver
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || g_pool_ready[dev]) return;
+  g_pool_ready[dev] = true;
+  int supported = 0;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetAttribute(&supported, cudaDevAttrMemoryPoolsSupported, dev) != cudaSuccess || !supported ||
+      cudaDeviceGetDefaultMemPool(&pool, dev) != cudaSuccess) {
+    cudaGetLastError();
+    g_pool_mode = 0;
+    return;
+  }
+  uint64_t keep = 8ull << 30;
+  if (const char* e = getenv("SMC_POOL_KEEP_MB")) keep = (uint64_t)std::max(0ll, atoll(e)) << 20;
+  cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+}
+bool stream_capturing(cudaStream_t st) {
+  cudaStreamCaptureStatus s = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &s) != cudaSuccess) { cudaGetLastError(); return false; }
+  return s != cudaStreamCaptureStatusNone;
+}
+}  // namespace
+
+cudaError_t smc_dev_alloc_bytes(void** p, size_t bytes, cudaStream_t st) {
+  bytes = std::max<size_t>(bytes, 8);
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  if (pool_enabled()) pool_configure();
+  if (!pool_enabled() || stream_capturing(st)) return cudaMalloc(p, bytes);
+  if (!g_deferred_free.empty()) {
+    for (void* q : g_deferred_free) cudaFree(q);
+    g_deferred_free.clear();
+  }
+  cudaError_t e = cudaMallocAsync(p, bytes, st);
+  if (e == cudaErrorMemoryAllocation) {  // give cached blocks back to the driver and retry once
+    cudaGetLastError();
+    cudaStreamSynchronize(st);
+    int dev = 0;
+    cudaMemPool_t pool;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+    e = cudaMallocAsync(p, bytes, st);
+  }
+  return e;
+}
+
+void smc_dev_free(void* p, cudaStream_t st) {
+  if (!p) return;
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  if (!pool_enabled()) { cudaFree(p); return; }
+  if (stream_capturing(st)) { g_deferred_free.push_back(p); return; }
+  if (cudaFreeAsync(p, st) != cudaSuccess) { cudaGetLastError(); cudaFree(p); }
+}
+
+cudaError_t smc_copy_sync(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind, cudaStream_t st) {
+  if (bytes == 0) return cudaSuccess;
+  if (stream_capturing(st)) return cudaMemcpy(dst, src, bytes, kind);  // a capture cannot be synchronised
+  cudaError_t e = cudaMemcpyAsync(dst, src, bytes, kind, st);
+  return e != cudaSuccess ? e : cudaStreamSynchronize(st);
+}
 
 // ------------------------------------------------------------------------------------------ context
 extern "C" int smc_ctx_create(int device, smc_ctx_t* out) {
@@ -47,7 +121,7 @@ extern "C" int smc_ctx_destroy(smc_ctx_t c) {
   if (!c) return SMC_OK;
   cudaSetDevice(c->device);
   smc_comm_destroy(c);
-  if (c->flush_buf) cudaFree(c->flush_buf);
+  if (c->flush_buf) smc_dev_free(c->flush_buf, c->stream);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
   return SMC_OK;
@@ -120,8 +194,8 @@ extern "C" int smc_model_compile(smc_ctx_t ctx, const void* tape, size_t nbytes,
     size_t bytes = (size_t)((n + 1) & ~1u) * 4;
     if ((size_t)(end - p) < bytes) { smc_set_error("tape: truncated index table"); delete m; return SMC_ERR_INVALID; }
     int32_t* d = nullptr;
-    SMC_CUDA(cudaMalloc(&d, std::max<size_t>(bytes, 8)));
-    SMC_CUDA(cudaMemcpy(d, p, (size_t)n * 4, cudaMemcpyHostToDevice));
+    SMC_CUDA(smc_dev_alloc(&d, std::max<size_t>(bytes, 8), ctx->stream));
+    SMC_CUDA(smc_copy_sync(d, p, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
     p += bytes;
     m->idx_dev.push_back(d);
     m->idx_len.push_back(n);
@@ -171,17 +245,17 @@ extern "C" int smc_model_destroy(smc_model_t m) {
   cudaSetDevice(m->ctx->device);
   cudaStreamSynchronize(m->ctx->stream);
   smc_graphs_invalidate(m);
-  for (auto& r : m->regs) if (r.owned && r.dev) cudaFree(r.dev);
-  for (auto d : m->idx_dev) cudaFree(d);
-  for (auto& p : m->scatter) { cudaFree(p.ptr); cudaFree(p.list); }
-  for (auto& p : m->sparse) { if (p.ptr) cudaFree(p.ptr); if (p.col) cudaFree(p.col); if (p.val) cudaFree(p.val); }
-  for (auto& g : m->glm) smc_glm_release(g);
-  for (auto& pr : m->programs) if (pr.dev_tables) cudaFree(pr.dev_tables);
-  if (m->beta) cudaFree(m->beta);
-  if (m->grad) cudaFree(m->grad);
-  if (m->logp) cudaFree(m->logp);
-  if (m->bad) cudaFree(m->bad);
-  if (m->scratch) cudaFree(m->scratch);
+  for (auto& r : m->regs) if (r.owned && r.dev) smc_dev_free(r.dev, m->ctx->stream);
+  for (auto d : m->idx_dev) smc_dev_free(d, m->ctx->stream);
+  for (auto& p : m->scatter) { smc_dev_free(p.ptr, m->ctx->stream); smc_dev_free(p.list, m->ctx->stream); }
+  for (auto& p : m->sparse) { if (p.ptr) smc_dev_free(p.ptr, m->ctx->stream); if (p.col) smc_dev_free(p.col, m->ctx->stream); if (p.val) smc_dev_free(p.val, m->ctx->stream); }
+  for (auto& g : m->glm) smc_glm_release(g, m->ctx->stream);
+  for (auto& pr : m->programs) if (pr.dev_tables) smc_dev_free(pr.dev_tables, m->ctx->stream);
+  if (m->beta) smc_dev_free(m->beta, m->ctx->stream);
+  if (m->grad) smc_dev_free(m->grad, m->ctx->stream);
+  if (m->logp) smc_dev_free(m->logp, m->ctx->stream);
+  if (m->bad) smc_dev_free(m->bad, m->ctx->stream);
+  if (m->scratch) smc_dev_free(m->scratch, m->ctx->stream);
   if (m->host_stage) cudaFreeHost(m->host_stage);
   if (m->ev0) cudaEventDestroy(m->ev0);
   if (m->ev1) cudaEventDestroy(m->ev1);
@@ -201,7 +275,7 @@ extern "C" int smc_model_bind_data(smc_model_t m, const char* name, const double
       return SMC_ERR_INVALID;
     }
     SmcReg& r = m->regs[d.reg];
-    if (!r.dev) { SMC_CUDA(cudaMalloc(&r.dev, std::max<int64_t>(r.numel, 1) * sizeof(double))); r.owned = true; }
+    if (!r.dev) { SMC_CUDA(smc_dev_alloc(&r.dev, std::max<int64_t>(r.numel, 1) * sizeof(double), m->ctx->stream)); r.owned = true; }
     SMC_CUDA(cudaMemcpyAsync(r.dev, host, r.numel * sizeof(double), cudaMemcpyHostToDevice, m->ctx->stream));
     SMC_CUDA(cudaStreamSynchronize(m->ctx->stream));
     d.bound = true;
@@ -488,10 +562,10 @@ int smc_scratch_reserve(smc_model_s* m, int64_t doubles) {
   if (doubles <= m->scratch_cap) return SMC_OK;
   m->graphs_stale = true;  // captured evaluations hold the old pointer
   m->realloc_epoch++;
-  if (m->scratch) cudaFree(m->scratch);
+  if (m->scratch) smc_dev_free(m->scratch, m->ctx->stream);
   m->scratch = nullptr;
   m->scratch_cap = 0;
-  SMC_CUDA(cudaMalloc(&m->scratch, doubles * sizeof(double)));
+  SMC_CUDA(smc_dev_alloc(&m->scratch, doubles * sizeof(double), m->ctx->stream));
   m->scratch_cap = doubles;
   return SMC_OK;
 }
@@ -536,7 +610,7 @@ static int scatter_plan(smc_model_s* m, uint32_t table, int64_t n_dst, SmcScatte
     if (p.table == (int)table && p.n_dst == n_dst) { *out = &p; return SMC_OK; }
   const uint32_t n = m->idx_len[table];
   std::vector<int32_t> idx(n);
-  SMC_CUDA(cudaMemcpy(idx.data(), m->idx_dev[table], (size_t)n * 4, cudaMemcpyDeviceToHost));
+  SMC_CUDA(smc_copy_sync(idx.data(), m->idx_dev[table], (size_t)n * 4, cudaMemcpyDeviceToHost, m->ctx->stream));
   std::vector<int32_t> ptr(n_dst + 1, 0), list(std::max<uint32_t>(n, 1));
   for (uint32_t e = 0; e < n; e++) {
     if (idx[e] < 0 || idx[e] >= n_dst) { smc_set_error("tape: scatter index out of range"); return SMC_ERR_INVALID; }
@@ -547,10 +621,10 @@ static int scatter_plan(smc_model_s* m, uint32_t table, int64_t n_dst, SmcScatte
   for (uint32_t e = 0; e < n; e++) list[fill[idx[e]]++] = (int32_t)e;   // stable: list order within a destination
   SmcScatterPlan p;
   p.table = (int)table; p.n_dst = n_dst;
-  SMC_CUDA(cudaMalloc(&p.ptr, ptr.size() * 4));
-  SMC_CUDA(cudaMalloc(&p.list, list.size() * 4));
-  SMC_CUDA(cudaMemcpy(p.ptr, ptr.data(), ptr.size() * 4, cudaMemcpyHostToDevice));
-  SMC_CUDA(cudaMemcpy(p.list, list.data(), list.size() * 4, cudaMemcpyHostToDevice));
+  SMC_CUDA(smc_dev_alloc(&p.ptr, ptr.size() * 4, m->ctx->stream));
+  SMC_CUDA(smc_dev_alloc(&p.list, list.size() * 4, m->ctx->stream));
+  SMC_CUDA(smc_copy_sync(p.ptr, ptr.data(), ptr.size() * 4, cudaMemcpyHostToDevice, m->ctx->stream));
+  SMC_CUDA(smc_copy_sync(p.list, list.data(), list.size() * 4, cudaMemcpyHostToDevice, m->ctx->stream));
   m->scatter.push_back(p);
   *out = &m->scatter.back();
   return SMC_OK;
@@ -566,7 +640,7 @@ static int sparse_plan(smc_model_s* m, uint32_t reg, int tA, long long r, long l
   const long long numel = r * k;
   if (numel >= 64 && numel <= (4LL << 20)) {
     std::vector<double> A(numel);
-    SMC_CUDA(cudaMemcpy(A.data(), m->regs[reg].dev, (size_t)numel * sizeof(double), cudaMemcpyDeviceToHost));
+    SMC_CUDA(smc_copy_sync(A.data(), m->regs[reg].dev, (size_t)numel * sizeof(double), cudaMemcpyDeviceToHost, m->ctx->stream));
     auto at = [&](long long i, long long l) { return A[tA ? (l + i * ar) : (i + l * ar)]; };
     long long nnz = 0;
     for (double v : A) nnz += (v != 0.0);
@@ -583,12 +657,12 @@ static int sparse_plan(smc_model_s* m, uint32_t reg, int tA, long long r, long l
         }
         ptr[i + 1] = (int32_t)col.size();
       }
-      SMC_CUDA(cudaMalloc(&sp.ptr, ptr.size() * 4));
-      SMC_CUDA(cudaMalloc(&sp.col, std::max<size_t>(col.size(), 1) * 4));
-      SMC_CUDA(cudaMalloc(&sp.val, std::max<size_t>(val.size(), 1) * 8));
-      SMC_CUDA(cudaMemcpy(sp.ptr, ptr.data(), ptr.size() * 4, cudaMemcpyHostToDevice));
-      SMC_CUDA(cudaMemcpy(sp.col, col.data(), col.size() * 4, cudaMemcpyHostToDevice));
-      SMC_CUDA(cudaMemcpy(sp.val, val.data(), val.size() * 8, cudaMemcpyHostToDevice));
+      SMC_CUDA(smc_dev_alloc(&sp.ptr, ptr.size() * 4, m->ctx->stream));
+      SMC_CUDA(smc_dev_alloc(&sp.col, std::max<size_t>(col.size(), 1) * 4, m->ctx->stream));
+      SMC_CUDA(smc_dev_alloc(&sp.val, std::max<size_t>(val.size(), 1) * 8, m->ctx->stream));
+      SMC_CUDA(smc_copy_sync(sp.ptr, ptr.data(), ptr.size() * 4, cudaMemcpyHostToDevice, m->ctx->stream));
+      SMC_CUDA(smc_copy_sync(sp.col, col.data(), col.size() * 4, cudaMemcpyHostToDevice, m->ctx->stream));
+      SMC_CUDA(smc_copy_sync(sp.val, val.data(), val.size() * 8, cudaMemcpyHostToDevice, m->ctx->stream));
       sp.sparse = true;
     }
   }
@@ -765,7 +839,7 @@ extern "C" int smc_model_finalize(smc_model_t m, int64_t max_chains, int row_sha
   cudaStream_t st = m->ctx->stream;
   SMC_CUDA(cudaStreamSynchronize(st));
   smc_graphs_invalidate(m);
-  for (auto& p : m->sparse) { if (p.ptr) cudaFree(p.ptr); if (p.col) cudaFree(p.col); if (p.val) cudaFree(p.val); }
+  for (auto& p : m->sparse) { if (p.ptr) smc_dev_free(p.ptr, m->ctx->stream); if (p.col) smc_dev_free(p.col, m->ctx->stream); if (p.val) smc_dev_free(p.val, m->ctx->stream); }
   m->sparse.clear();   // (data may have been bound again)
   {
     const char* ng = getenv("SMC_NO_GRAPHS");
@@ -780,11 +854,11 @@ extern "C" int smc_model_finalize(smc_model_t m, int64_t max_chains, int row_sha
   m->row_shard = row_shard;
   if (realloc_chain) {
     for (auto& r : m->regs)
-      if (r.d.kind == SMC_REG_CHAIN && r.dev) { cudaFree(r.dev); r.dev = nullptr; }
-    if (m->beta) cudaFree(m->beta);
-    if (m->grad) cudaFree(m->grad);
-    if (m->logp) cudaFree(m->logp);
-    if (m->bad) cudaFree(m->bad);
+      if (r.d.kind == SMC_REG_CHAIN && r.dev) { smc_dev_free(r.dev, m->ctx->stream); r.dev = nullptr; }
+    if (m->beta) smc_dev_free(m->beta, m->ctx->stream);
+    if (m->grad) smc_dev_free(m->grad, m->ctx->stream);
+    if (m->logp) smc_dev_free(m->logp, m->ctx->stream);
+    if (m->bad) smc_dev_free(m->bad, m->ctx->stream);
     m->beta = m->grad = m->logp = nullptr;
     m->bad = nullptr;
     m->Cpad = Cpad;
@@ -800,19 +874,19 @@ extern "C" int smc_model_finalize(smc_model_t m, int64_t max_chains, int row_sha
     }
     for (auto& r : m->regs)
       if (r.d.kind == SMC_REG_CHAIN) {
-        SMC_CUDA(cudaMalloc(&r.dev, (size_t)r.numel * Cpad * sizeof(double)));
+        SMC_CUDA(smc_dev_alloc(&r.dev, (size_t)r.numel * Cpad * sizeof(double), m->ctx->stream));
         r.owned = true;
       }
-    SMC_CUDA(cudaMalloc(&m->beta, (size_t)std::max<int64_t>(m->M, 1) * Cpad * sizeof(double)));
-    SMC_CUDA(cudaMalloc(&m->grad, (size_t)std::max<int64_t>(m->M, 1) * Cpad * sizeof(double)));
-    SMC_CUDA(cudaMalloc(&m->logp, (size_t)Cpad * sizeof(double)));
-    SMC_CUDA(cudaMalloc(&m->bad, (size_t)(Cpad + 32) * sizeof(int)));
+    SMC_CUDA(smc_dev_alloc(&m->beta, (size_t)std::max<int64_t>(m->M, 1) * Cpad * sizeof(double), m->ctx->stream));
+    SMC_CUDA(smc_dev_alloc(&m->grad, (size_t)std::max<int64_t>(m->M, 1) * Cpad * sizeof(double), m->ctx->stream));
+    SMC_CUDA(smc_dev_alloc(&m->logp, (size_t)Cpad * sizeof(double), m->ctx->stream));
+    SMC_CUDA(smc_dev_alloc(&m->bad, (size_t)(Cpad + 32) * sizeof(int), m->ctx->stream));
     SMC_CUDA(cudaMemsetAsync(m->beta, 0, (size_t)std::max<int64_t>(m->M, 1) * Cpad * sizeof(double), st));
     SMC_CUDA(cudaMemsetAsync(m->grad, 0, (size_t)std::max<int64_t>(m->M, 1) * Cpad * sizeof(double), st));
   }
   for (auto& r : m->regs)
     if (r.d.kind == SMC_REG_HDR && !r.dev) {
-      SMC_CUDA(cudaMalloc(&r.dev, (size_t)r.numel * sizeof(double)));
+      SMC_CUDA(smc_dev_alloc(&r.dev, (size_t)r.numel * sizeof(double), m->ctx->stream));
       r.owned = true;
     }
   if (!m->ev0) { SMC_CUDA(cudaEventCreate(&m->ev0)); SMC_CUDA(cudaEventCreate(&m->ev1)); }
@@ -825,7 +899,7 @@ extern "C" int smc_model_finalize(smc_model_t m, int64_t max_chains, int row_sha
   SMC_CUDA(cudaStreamSynchronize(st));
   if (hbad) { smc_set_error("Initial values out of model support, try other values (a parameter-independent density is zero)"); return SMC_ERR_SUPPORT; }
   // fused GLM statements
-  for (auto& g : m->glm) smc_glm_release(g);
+  for (auto& g : m->glm) smc_glm_release(g, m->ctx->stream);
   m->glm.clear();
   for (int si : m->body_stmts)
     if (m->stmts[si].op == SMC_OP_GLM) {
@@ -950,7 +1024,7 @@ extern "C" int smc_eval_timed(smc_model_t m, int reps, int flush_l2, double* ms_
   cudaSetDevice(m->ctx->device);
   cudaStream_t st = m->ctx->stream;
   const size_t flush_bytes = 256u << 20;
-  if (flush_l2 && !m->ctx->flush_buf) SMC_CUDA(cudaMalloc(&m->ctx->flush_buf, flush_bytes));
+  if (flush_l2 && !m->ctx->flush_buf) SMC_CUDA(smc_dev_alloc(&m->ctx->flush_buf, flush_bytes, m->ctx->stream));
   double tot = 0.0, glm = 0.0;
   for (int r = 0; r < reps; r++) {
     if (flush_l2) SMC_CUDA(cudaMemsetAsync(m->ctx->flush_buf, r & 0xff, flush_bytes, st));

@@ -24,6 +24,18 @@ void smc_set_error(const char* fmt, ...);
     if (rc_ != SMC_OK) return rc_; \
   } while (0)
 
+// Device memory comes from the device's stream-ordered pool (cudaMallocAsync) on the context's stream, with a release
+// threshold so that the blocks one sampler call frees are what the next one gets: a simpleHMC call makes ~60
+// allocations, and as plain cudaMalloc/cudaFree those took 0.1-1.1 s of host time on a busy box (tools/e2e_breakdown.py).
+// SMC_NO_POOL=1 restores cudaMalloc/cudaFree.  Inside a stream capture both fall back to the synchronous calls (the
+// free is deferred), so that no allocation ever belongs to a graph.
+cudaError_t smc_dev_alloc_bytes(void** p, size_t bytes, cudaStream_t st);
+void smc_dev_free(void* p, cudaStream_t st);
+template <typename T>
+static inline cudaError_t smc_dev_alloc(T** p, size_t bytes, cudaStream_t st) { return smc_dev_alloc_bytes((void**)p, bytes, st); }
+// blocking copy ordered on `st` (the pool's allocations are ordered on that stream, not on the legacy default stream)
+cudaError_t smc_copy_sync(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind, cudaStream_t st);
+
 struct smc_ctx_s {
   int device = 0;
   int sm_count = 148;
@@ -173,4 +185,4 @@ int smc_vm_launch(smc_model_s* m, SmcProgram& pr, int64_t C, int* bad);
 // glm_fused.cu
 int smc_glm_prepare(smc_model_s* m, SmcGlmPlan& g);
 int smc_glm_launch(smc_model_s* m, SmcGlmPlan& g, int64_t C);
-void smc_glm_release(SmcGlmPlan& g);
+void smc_glm_release(SmcGlmPlan& g, cudaStream_t st);

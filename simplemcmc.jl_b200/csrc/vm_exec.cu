@@ -525,9 +525,9 @@ int smc_vm_prepare(smc_model_s* m, SmcProgram& pr) {
   VmDesc* D = (VmDesc*)(host.data() + nu2 * sizeof(VmDevUop) + ot.size() * sizeof(VmDevOpd));
   for (size_t i = 0; i < ns; i++) D[i] = desc_of(m, pr.scal_regs[i]);
   if (!pr.dev_tables || pr.dev_tables_bytes < host.size()) {
-    if (pr.dev_tables) cudaFree(pr.dev_tables);
+    if (pr.dev_tables) smc_dev_free(pr.dev_tables, m->ctx->stream);
     pr.dev_tables = nullptr;
-    SMC_CUDA(cudaMalloc(&pr.dev_tables, host.size()));
+    SMC_CUDA(smc_dev_alloc(&pr.dev_tables, host.size(), m->ctx->stream));
     pr.dev_tables_bytes = host.size();
   }
   SMC_CUDA(cudaMemcpyAsync(pr.dev_tables, host.data(), host.size(), cudaMemcpyHostToDevice, m->ctx->stream));

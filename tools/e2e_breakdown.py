@@ -12,7 +12,7 @@ X, Y, beta0, hold = bench.make_data(pinned=True)
 mode = bench.posterior_mode(X, Y)
 C, K = bench.CHAINS_PER_GPU, int(sys.argv[1]) if len(sys.argv) > 1 else 10
 ctx = capi.Context.default(0)
-for rep in range(2):
+for rep in range(6):
     t = [time.time()]
     low = Lowering(bench.MODEL, [("beta", mode)], dict(X=X, Y=Y)); t.append(time.time())
     tape, bound = low.serialise(); t.append(time.time())

@@ -131,6 +131,19 @@ def _ess(series):
     return len(series) * max(0.0, 1.0 - fac) / (1.0 + fac)
 
 
+def ess_from_draws(d):
+    """calcStats! (src/samplers.jl:352-374) on stored draws d[samples][C][M] -> ess[C][M]: the lag-1 formula for every
+    (chain, component) series at once.  The samplers use the statistics accumulated on the device instead (`_finish`);
+    this is the same formula on the host, for checking them."""
+    n = d.shape[0]
+    a, b = d[1:], d[:-1]
+    cov = np.sum((a - a.mean(0)) * (b - b.mean(0)), axis=0) / (n - 2)
+    var = np.var(d, axis=0, ddof=1)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        fac = np.abs(cov) / var
+        return np.where(var > 0, n * np.maximum(0.0, 1.0 - fac) / (1.0 + fac), 0.0)
+
+
 def _finish(res, pars, raw, chains, t0, store_draws):
     res.time = time.time() - t0
     res.acceptRate = float(np.mean(raw["accept_rate"]))
@@ -165,7 +178,7 @@ def _finish(res, pars, raw, chains, t0, store_draws):
         res.accept = raw["accept"][:, 0] if chains == 1 else raw["accept"]
     if store_draws and "draws" in raw:
         d = raw["draws"]            # [samples][C][M]
-        lo, hi = np.inf, -np.inf
+        res.misc["draws_scm"] = d   # the ABI layout, as received (res.params holds views of it)
         for p in pars:
             block = d[:, :, p.start:p.start + p.count]             # samples x C x count
             arr = np.transpose(block, (2, 0, 1))                      # count x samples x C
@@ -173,19 +186,11 @@ def _finish(res, pars, raw, chains, t0, store_draws):
             if chains == 1:
                 arr = arr[:, :, 0]
             res.params[p.sym] = arr.reshape(shape, order="F") if len(p.size) == 2 else arr.reshape(shape)
-        if n >= 3:
-            # lag-1 ESS of every (chain, component) series at once (calcStats!, src/samplers.jl:352-374); chains add up
-            a, b = d[1:], d[:-1]
-            cov = np.sum((a - a.mean(0)) * (b - b.mean(0)), axis=0) / (n - 2)
-            var = np.var(d, axis=0, ddof=1)
-            with np.errstate(divide="ignore", invalid="ignore"):
-                fac = np.abs(cov) / var
-                ess = np.where(var > 0, n * np.maximum(0.0, 1.0 - fac) / (1.0 + fac), 0.0)
+        if n >= 3 and "lag1" not in raw:
+            res.misc["ess_by_chain"] = ess = ess_from_draws(d)
             per_comp = ess.sum(axis=0)
-            res.misc["ess_by_chain_from_draws"] = ess
-            lo, hi = per_comp.min(), per_comp.max()
-            res.ess = (lo, hi)
-            res.essBySec = (lo / res.time, hi / res.time)
+            res.ess = (float(per_comp.min()), float(per_comp.max()))
+            res.essBySec = (res.ess[0] / res.time, res.ess[1] / res.time)
     return res
 
 

@@ -85,12 +85,23 @@ struct SmcGlmPlan {  // one SMC_OP_GLM statement, prepared at finalize
 // folded into operand modes / side effects of the computing instruction at plan time.
 enum { VM_NONE = 0, VM_LOCAL = 1, VM_SCAL = 2, VM_ARRAY = 3 };
 enum { VMF_ACC = 1, VMF_WRITE = 2, VMF_STORE = 4, VMF_REDUCE = 8 };
+// A chain micro-op (planner only, never on a tape): r = operand 0, then up to three stages r = stage_k(r, operand k) whose
+// intermediate values stay in registers instead of going through a local slot.  dist / darg / code3 hold the stage codes;
+// operand 3 is a source (chains never accumulate).  A Normal density stage ends the chain and takes operands k (the
+// other one of mean / variate) and k + 1 (sigma, a per-chain scalar).
+enum { VM_OP_CHAIN = 254 };
+enum { VM_CH_END = 0, VM_CH_ADD, VM_CH_SUB, VM_CH_RSUB, VM_CH_MUL, VM_CH_DIV, VM_CH_RDIV, VM_CH_NEG,
+       VM_CH_NLOG,     // Normal log-density of (r - o) / sigma
+       VM_CH_ND_RMO,   // (r - o) / sigma^2
+       VM_CH_ND_OMR,   // (o - r) / sigma^2
+       VM_CH_ND_SIG }; // ((r - o)^2 / sigma^2 - 1) / sigma
 struct VmUop {       // 32 bytes
   uint8_t op, dist, darg, flags;
-  uint8_t mode[4];   // operands 0..2 and [3] = the accumulate operand (VMF_ACC)
+  uint8_t mode[4];   // operands 0..2 and [3] = the accumulate operand (VMF_ACC) / fourth source of a chain
   uint16_t idx[4];   // local slot / scalar slot / array descriptor
   uint16_t dst, store, red, nsrc;
-  uint32_t pad[2];
+  uint32_t code3;    // third stage of a chain
+  uint32_t pad;
 };
 struct VmDesc {      // 32 bytes; p == NULL: immediate
   const double* p;

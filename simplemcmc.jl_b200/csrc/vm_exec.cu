@@ -26,7 +26,7 @@ constexpr int NT = 256;  // threads per block
 struct VmDevUop {   // 16 bytes
   uint8_t op, dist, darg, flags;
   uint8_t o[4];     // operand-table entries of the sources 0..2 and of the accumulate operand
-  uint8_t dst, store, red, pad0;   // operand-table entries of the local / array destinations, reduction slot
+  uint8_t dst, store, red, code3;   // operand-table entries of the local / array destinations, reduction slot; chain stage 3
   uint32_t pad1;
 };
 struct VmDevOpd {   // 32 bytes: one distinct operand of the program
@@ -44,7 +44,7 @@ struct VmOt {       // operand table entry resolved for this block (kept in shar
 struct VmDec {       // a micro-op pre-decoded for this block (shared memory), 32 bytes: all the shared-memory fast path reads
   uint32_t w0;       // op | dist << 8 | darg << 16 | flags << 24
   uint32_t w1;       // reduction slot | gen << 8 (bit k: operand k is a tape array in HBM) | sel << 16 (2 bits per operand:
-                     //   1 = "+ tid, stride NT" (local), 2 = "+ chain lane" (per-chain scalar))
+                     //   1 = "+ tid, stride NT" (local), 2 = "+ chain lane" (per-chain scalar)) | third chain stage << 24
   int b0, b1, b2, bd;   // shared-memory indices of operands 0..2 and of the local destination, before the per-thread term
   uint32_t ot;       // operand-table entries o[0] | o[1] << 8 | o[2] << 16 | o[3] << 24 (generic path)
   uint32_t st;       // operand-table entry of the array destination
@@ -156,6 +156,39 @@ __device__ __noinline__ double vm_apply_slow(int op, int dist, int k, double a, 
     }                                                                                                               \
   }
 
+
+// Chain micro-ops (VM_OP_CHAIN, see smc_internal.h): r starts as operand 0 and goes through up to three stages in
+// registers; an operand that is the same for every element of the pass (a per-chain scalar) is read once.  Every stage is
+// one rounded operation, exactly what the separate micro-ops computed (no contraction across stages).
+#define VM_CH_STAGE(CODE, O)                                                                                   \
+  switch (CODE) {                                                                                              \
+    case VM_CH_ADD: r_0 = __dadd_rn(r_0, O##_0); r_1 = __dadd_rn(r_1, O##_1); r_2 = __dadd_rn(r_2, O##_2); r_3 = __dadd_rn(r_3, O##_3); break; \
+    case VM_CH_SUB: r_0 = __dsub_rn(r_0, O##_0); r_1 = __dsub_rn(r_1, O##_1); r_2 = __dsub_rn(r_2, O##_2); r_3 = __dsub_rn(r_3, O##_3); break; \
+    case VM_CH_RSUB: r_0 = __dsub_rn(O##_0, r_0); r_1 = __dsub_rn(O##_1, r_1); r_2 = __dsub_rn(O##_2, r_2); r_3 = __dsub_rn(O##_3, r_3); break; \
+    case VM_CH_MUL: r_0 = __dmul_rn(r_0, O##_0); r_1 = __dmul_rn(r_1, O##_1); r_2 = __dmul_rn(r_2, O##_2); r_3 = __dmul_rn(r_3, O##_3); break; \
+    case VM_CH_DIV: r_0 = r_0 / O##_0; r_1 = r_1 / O##_1; r_2 = r_2 / O##_2; r_3 = r_3 / O##_3; break;        \
+    case VM_CH_RDIV: r_0 = O##_0 / r_0; r_1 = O##_1 / r_1; r_2 = O##_2 / r_2; r_3 = O##_3 / r_3; break;       \
+    case VM_CH_NEG: r_0 = -r_0; r_1 = -r_1; r_2 = -r_2; r_3 = -r_3; break;                                    \
+    case VM_CH_NLOG:                                                                                           \
+      r_0 = fma(-0.5 * ((r_0 - O##_0) * inv), (r_0 - O##_0) * inv, lconst);                                    \
+      r_1 = fma(-0.5 * ((r_1 - O##_1) * inv), (r_1 - O##_1) * inv, lconst);                                    \
+      r_2 = fma(-0.5 * ((r_2 - O##_2) * inv), (r_2 - O##_2) * inv, lconst);                                    \
+      r_3 = fma(-0.5 * ((r_3 - O##_3) * inv), (r_3 - O##_3) * inv, lconst);                                    \
+      break;                                                                                                   \
+    case VM_CH_ND_RMO: r_0 = (r_0 - O##_0) * inv2; r_1 = (r_1 - O##_1) * inv2; r_2 = (r_2 - O##_2) * inv2; r_3 = (r_3 - O##_3) * inv2; break; \
+    case VM_CH_ND_OMR: r_0 = (O##_0 - r_0) * inv2; r_1 = (O##_1 - r_1) * inv2; r_2 = (O##_2 - r_2) * inv2; r_3 = (O##_3 - r_3) * inv2; break; \
+    case VM_CH_ND_SIG:                                                                                         \
+      r_0 = ((r_0 - O##_0) * (r_0 - O##_0) * inv2 - 1.0) * inv;                                                \
+      r_1 = ((r_1 - O##_1) * (r_1 - O##_1) * inv2 - 1.0) * inv;                                                \
+      r_2 = ((r_2 - O##_2) * (r_2 - O##_2) * inv2 - 1.0) * inv;                                                \
+      r_3 = ((r_3 - O##_3) * (r_3 - O##_3) * inv2 - 1.0) * inv;                                                \
+      break;                                                                                                   \
+    default: break;                                                                                            \
+  }
+#define VM_CH_OPND(O, P, S, K)                                                                                 \
+  const double O##_0 = (S) ? (P)[(v + 0) * (S)] : (K), O##_1 = (S) ? (P)[(v + 1) * (S)] : (K),                 \
+               O##_2 = (S) ? (P)[(v + 2) * (S)] : (K), O##_3 = (S) ? (P)[(v + 3) * (S)] : (K);
+
 __global__ void __launch_bounds__(NT) k_vm(VmArgs a) {
   extern __shared__ __align__(16) double vsmd[];
   unsigned char* vsm = (unsigned char*)vsmd;
@@ -199,7 +232,7 @@ __global__ void __launch_bounds__(NT) k_vm(VmArgs a) {
     d.w0 = (uint32_t)uo.op | ((uint32_t)uo.dist << 8) | ((uint32_t)uo.darg << 16) | ((uint32_t)uo.flags << 24);
     const uint32_t gen = (t0.gbase ? 1u : 0u) | (t1.gbase ? 2u : 0u) | (t2.gbase ? 4u : 0u);
     const uint32_t sel = (uint32_t)(t0.flags & 3) | ((uint32_t)(t1.flags & 3) << 2) | ((uint32_t)(t2.flags & 3) << 4);
-    d.w1 = (uint32_t)uo.red | (gen << 8) | (sel << 16);
+    d.w1 = (uint32_t)uo.red | (gen << 8) | (sel << 16) | ((uint32_t)uo.code3 << 24);
     d.b0 = t0.off; d.b1 = t1.off; d.b2 = t2.off; d.bd = OT[uo.dst].off;
     d.ot = (uint32_t)uo.o[0] | ((uint32_t)uo.o[1] << 8) | ((uint32_t)uo.o[2] << 16) | ((uint32_t)uo.o[3] << 24);
     d.st = uo.store;
@@ -222,7 +255,60 @@ __global__ void __launch_bounds__(NT) k_vm(VmArgs a) {
         const int i1 = (int)wa.w + ((sel & 4) ? tid : 0) + ((sel & 8) ? cx : 0);
         const int i2 = (int)wb.x + ((sel & 16) ? tid : 0) + ((sel & 32) ? cx : 0);
         double* const pd = vsmd + (int)wb.y + tid;
-        if (gen == 0 && (fl == VMF_WRITE || fl == VMF_REDUCE)) {
+        if (uo.op == VM_OP_CHAIN) {
+          const VmOt t0 = OT[wb.z & 0xff], t1 = OT[(wb.z >> 8) & 0xff], t2 = OT[(wb.z >> 16) & 0xff], t3 = OT[(wb.z >> 24) & 0xff];
+          const VmOt ts = OT[wb.w & 0xff];
+#define VM_OT_PTR(t) ((t).gbase ? (t).gbase + (((t).flags & 2) ? cx : 0) + eb * (t).Cc                         \
+                               : vsmd + (t).off + (((t).flags & 1) ? tid : 0) + (((t).flags & 2) ? cx : 0))
+#define VM_OT_STRIDE(t) ((t).gbase ? (t).S : (((t).flags & 1) ? (long long)NT : 0LL))
+          const double *p0 = VM_OT_PTR(t0), *p1 = VM_OT_PTR(t1), *p2 = VM_OT_PTR(t2), *p3 = VM_OT_PTR(t3);
+          const long long s0 = VM_OT_STRIDE(t0), s1 = VM_OT_STRIDE(t1), s2 = VM_OT_STRIDE(t2), s3 = VM_OT_STRIDE(t3);
+#undef VM_OT_PTR
+#undef VM_OT_STRIDE
+          double* ps = ts.gbase ? const_cast<double*>(ts.gbase) + ((ts.flags & 2) ? cx : 0) + eb * ts.Cc : vsmd + sc_off;
+          const long long ss = ts.S;
+          const int c1 = uo.dist, c2 = uo.darg, c3 = (int)(wa.y >> 24);
+          const double k1 = p1[0], k2 = p2[0], k3 = p3[0];   // (entry 0 of the operand table is a readable dummy)
+          // a Normal stage: sigma is the operand after the stage's own; 1/sigma, 1/sigma^2, log(sigma) once per pass
+          double inv = 0.0, inv2 = 0.0, lconst = 0.0;
+          bool give_up = false;
+          if (c1 >= VM_CH_NLOG || c2 >= VM_CH_NLOG) {
+            const double sg = (c1 >= VM_CH_NLOG) ? k2 : k3;
+            inv = 1.0 / sg; inv2 = 1.0 / (sg * sg);
+            lconst = -log(sg) - SMC_LOG_SQRT_2PI;
+            give_up = !(sg > 0.0) && (c1 == VM_CH_NLOG || c2 == VM_CH_NLOG);   // src/distribs.jl:25: sigma <= 0
+          }
+          double rsum = 0.0;
+          int v = 0;
+          for (; v + 4 <= vc; v += 4) {
+            double r_0 = p0[(v + 0) * s0], r_1 = p0[(v + 1) * s0], r_2 = p0[(v + 2) * s0], r_3 = p0[(v + 3) * s0];
+            VM_CH_OPND(q, p1, s1, k1)
+            VM_CH_OPND(w, p2, s2, k2)
+            VM_CH_OPND(x, p3, s3, k3)
+            VM_CH_STAGE(c1, q)
+            VM_CH_STAGE(c2, w)
+            VM_CH_STAGE(c3, x)
+            if (give_up) { r_0 = 0.0; r_1 = 0.0; r_2 = 0.0; r_3 = 0.0; }
+            if (fl & VMF_WRITE) { pd[(v + 0) * NT] = r_0; pd[(v + 1) * NT] = r_1; pd[(v + 2) * NT] = r_2; pd[(v + 3) * NT] = r_3; }
+            if (fl & VMF_STORE) { ps[(v + 0) * ss] = r_0; ps[(v + 1) * ss] = r_1; ps[(v + 2) * ss] = r_2; ps[(v + 3) * ss] = r_3; }
+            if (fl & VMF_REDUCE) { rsum += r_0; rsum += r_1; rsum += r_2; rsum += r_3; }
+          }
+          for (; v < vc; v++) {
+            double r_0 = p0[v * s0], r_1 = 0.0, r_2 = 0.0, r_3 = 0.0;
+            const double q_0 = p1[v * s1], w_0 = p2[v * s2], x_0 = p3[v * s3];
+            const double q_1 = 1.0, q_2 = 1.0, q_3 = 1.0, w_1 = 1.0, w_2 = 1.0, w_3 = 1.0, x_1 = 1.0, x_2 = 1.0, x_3 = 1.0;
+            VM_CH_STAGE(c1, q)
+            VM_CH_STAGE(c2, w)
+            VM_CH_STAGE(c3, x)
+            (void)r_1; (void)r_2; (void)r_3;
+            if (give_up) r_0 = 0.0;
+            if (fl & VMF_WRITE) pd[v * NT] = r_0;
+            if (fl & VMF_STORE) ps[v * ss] = r_0;
+            rsum += r_0;
+          }
+          if (give_up) a.bad[c] = 1;
+          if (fl & VMF_REDUCE) Rd[uo.red * NT + tid] += rsum;
+        } else if (gen == 0 && (fl == VMF_WRITE || fl == VMF_REDUCE)) {
           const double *p0 = vsmd + i0, *p1 = vsmd + i1, *p2 = vsmd + i2;
           const int s0 = (sel & 1) ? NT : 0, s1 = (sel & 4) ? NT : 0, s2 = (sel & 16) ? NT : 0;
           const double *pa = nullptr;
@@ -268,6 +354,8 @@ __global__ void __launch_bounds__(NT) k_vm(VmArgs a) {
     }
   }
 }
+#undef VM_CH_STAGE
+#undef VM_CH_OPND
 #undef VM_SWITCH
 #undef VM_RUN
 #undef VM_LOAD4
@@ -313,6 +401,94 @@ __global__ void k_vm_final_warp(VmFinalArgs a) {
 }  // namespace
 
 // ------------------------------------------------------------------------------------------ planning
+// Chains: a micro-op whose only effect is to write a local that the NEXT micro-op reads once, and that nobody reads
+// afterwards, hands its value over in registers.  Typical model code is chain shaped (resid = y - (a + b .* x), then the
+// density of resid): of the locals' shared-memory traffic, which bounds the interpreter, most is such hand-overs.
+static void vm_form_chains(std::vector<VmUop>& U) {
+  const int n = (int)U.size();
+  auto reads = [](const VmUop& u, int d) {
+    int c = 0;
+    for (int k = 0; k < 3; k++) c += (k < u.nsrc && u.mode[k] == VM_LOCAL && u.idx[k] == d) ? 1 : 0;
+    if ((u.flags & VMF_ACC) && u.mode[3] == VM_LOCAL && u.idx[3] == d) c += 100;   // as accumulate operand: never a hand-over
+    return c;
+  };
+  auto dead_after = [&](int j, int d) {
+    for (int t = j + 1; t < n; t++) {
+      if (reads(U[t], d)) return false;
+      if ((U[t].flags & VMF_WRITE) && U[t].dst == d) return true;
+    }
+    return true;
+  };
+  auto simple = [](const VmUop& u) {
+    if (u.flags & VMF_ACC) return false;
+    if (u.op == SMC_OP_NEG) return u.nsrc == 1;
+    return (u.op == SMC_OP_ADD || u.op == SMC_OP_SUB || u.op == SMC_OP_MUL || u.op == SMC_OP_DIV) && u.nsrc == 2;
+  };
+  auto normal = [](const VmUop& u) {
+    return !(u.flags & VMF_ACC) && (u.op == SMC_OP_LOGPDF || u.op == SMC_OP_DLOGPDF) && u.dist == SMC_DIST_NORMAL && u.nsrc == 3 &&
+           u.mode[1] == VM_SCAL;   // one sigma per chain for the whole pass
+  };
+  auto code_of = [](int op, bool carry_first) {
+    switch (op) {
+      case SMC_OP_ADD: return (int)VM_CH_ADD;
+      case SMC_OP_SUB: return (int)(carry_first ? VM_CH_SUB : VM_CH_RSUB);
+      case SMC_OP_MUL: return (int)VM_CH_MUL;
+      case SMC_OP_DIV: return (int)(carry_first ? VM_CH_DIV : VM_CH_RDIV);
+      default: return (int)VM_CH_NEG;
+    }
+  };
+  std::vector<VmUop> out;
+  for (int i = 0; i < n; i++) {
+    const VmUop& h = U[i];
+    if (!simple(h) || h.flags != VMF_WRITE) { out.push_back(h); continue; }
+    VmUop c;                       // the chain being built
+    memset(&c, 0, sizeof(c));
+    c.op = VM_OP_CHAIN;
+    c.mode[0] = h.mode[0]; c.idx[0] = h.idx[0];
+    int codes[3] = {code_of(h.op, true), 0, 0};
+    if (h.nsrc == 2) { c.mode[1] = h.mode[1]; c.idx[1] = h.idx[1]; }
+    int ns = 1, j = i + 1;
+    uint16_t carry = h.dst;
+    uint8_t flags = h.flags;
+    uint16_t dst = h.dst, store = 0, red = 0;
+    bool closed = false;
+    while (!closed && j < n && ns < 3 && flags == VMF_WRITE) {
+      const VmUop& u = U[j];
+      if (reads(u, carry) != 1 || !dead_after(j, carry)) break;
+      int pos = 0;
+      for (int k = 0; k < u.nsrc; k++)
+        if (u.mode[k] == VM_LOCAL && u.idx[k] == carry) pos = k;
+      const int slot = ns + 1;       // operand slot of this stage
+      if (simple(u)) {
+        codes[ns] = code_of(u.op, pos == 0);
+        if (u.nsrc == 2) { c.mode[slot] = u.mode[1 - pos]; c.idx[slot] = u.idx[1 - pos]; }
+      } else if (normal(u) && pos != 1 && slot + 1 <= 3) {
+        const int other = 2 - pos;   // (mu, sigma, x): the carried value is the mean or the variate
+        c.mode[slot] = u.mode[other]; c.idx[slot] = u.idx[other];
+        c.mode[slot + 1] = u.mode[1]; c.idx[slot + 1] = u.idx[1];
+        const bool carry_is_x = (pos == 2);
+        if (u.op == SMC_OP_LOGPDF) codes[ns] = VM_CH_NLOG;
+        else if (u.darg == 1) codes[ns] = VM_CH_ND_SIG;
+        else if (u.darg == 0) codes[ns] = carry_is_x ? VM_CH_ND_RMO : VM_CH_ND_OMR;   // (x - mu) / sigma^2
+        else codes[ns] = carry_is_x ? VM_CH_ND_OMR : VM_CH_ND_RMO;                    // (mu - x) / sigma^2
+        closed = true;
+      } else {
+        break;
+      }
+      ns++;
+      flags = u.flags; dst = u.dst; store = u.store; red = u.red;
+      carry = u.dst;
+      j++;
+    }
+    if (ns == 1) { out.push_back(h); continue; }
+    c.dist = (uint8_t)codes[0]; c.darg = (uint8_t)codes[1]; c.code3 = (uint32_t)codes[2];
+    c.flags = flags; c.dst = dst; c.store = store; c.red = red; c.nsrc = 4;
+    out.push_back(c);
+    i = j - 1;
+  }
+  U.swap(out);
+}
+
 int smc_vm_plan(smc_model_s* m, SmcProgram& pr) {
   (void)m;
   struct Src { uint8_t mode = VM_NONE; uint16_t idx = 0; };
@@ -441,6 +617,7 @@ int smc_vm_plan(smc_model_s* m, SmcProgram& pr) {
     for (auto& u : U)
       if (u.flags & (VMF_WRITE | VMF_STORE | VMF_REDUCE)) kept.push_back(u);
     U.swap(kept);
+    if (!getenv("SMC_VM_NO_CHAINS")) vm_form_chains(U);
     int remap[SMC_PROG_MAX_LOCALS];
     for (int i = 0; i < SMC_PROG_MAX_LOCALS; i++) remap[i] = -1;
     int n = 0;
@@ -460,7 +637,8 @@ int smc_vm_plan(smc_model_s* m, SmcProgram& pr) {
       for (auto& u : U) {
         fprintf(stderr, "[vm]   op %2u", u.op);
         if (u.op == SMC_OP_LOGPDF || u.op == SMC_OP_DLOGPDF) fprintf(stderr, "(dist %u arg %u)", u.dist, u.darg);
-        for (int k = 0; k < 3; k++)
+        if (u.op == VM_OP_CHAIN) fprintf(stderr, "(chain stages %u %u %u)", u.dist, u.darg, u.code3);
+        for (int k = 0; k < (u.op == VM_OP_CHAIN ? 4 : 3); k++)
           if (u.mode[k]) fprintf(stderr, " %s%u", mode_name[u.mode[k]], u.idx[k]);
         if (u.flags & VMF_ACC) fprintf(stderr, " +=%s%u", mode_name[u.mode[3]], u.idx[3]);
         if (u.flags & VMF_WRITE) fprintf(stderr, " -> L%u", u.dst);
@@ -513,6 +691,7 @@ int smc_vm_prepare(smc_model_s* m, SmcProgram& pr) {
     d.dst = (uint8_t)((u.flags & VMF_WRITE) ? entry(VM_LOCAL, u.dst) : 0);
     d.store = (uint8_t)((u.flags & VMF_STORE) ? entry(VM_ARRAY, u.store) : 0);
     d.red = (uint8_t)u.red;
+    d.code3 = (uint8_t)(u.op == VM_OP_CHAIN ? u.code3 : 0);
     du[i] = d;
     if (ot.size() > 255) { smc_set_error("program: more than 255 distinct operands"); return SMC_ERR_INVALID; }
   }

@@ -665,11 +665,8 @@ int launch_cfg_tp(const GlmArgs& a, int RS, cudaStream_t st) {
   size_t epi = (size_t)(MP + 1) * TC * sizeof(double) + TC * sizeof(int);
   size_t smem = std::max(pipe, epi);
   auto kern = k_glm<FAM, MT, NWC, NWR, MP8, TRIM, PUB>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    SMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
-  }
+  static SmcOncePerDevice once;
+  if (once.first()) SMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)((a.C + TC - 1) / TC), (unsigned)RS);
   kern<<<grid, NWC * NWR * 32, smem, st>>>(a);
   return SMC_OK;
@@ -824,11 +821,8 @@ int smc_glm_launch(smc_model_s* m, SmcGlmPlan& g, int64_t C) {
     e.N = g.N; e.C = C; e.Cpad = m->Cpad; e.M = g.M; e.acc = (s.flags & SMC_F_ACC) ? 1 : 0; e.par = g.par;
     const int P = g.M + 1;
     const size_t smem = ((size_t)P * P + (size_t)g.M * 32 + 512) * sizeof(double);
-    static bool gram_attr = false;
-    if (!gram_attr) {
-      SMC_CUDA(cudaFuncSetAttribute(k_glm_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-      gram_attr = true;
-    }
+    static SmcOncePerDevice gram_once;
+    if (gram_once.first()) SMC_CUDA(cudaFuncSetAttribute(k_glm_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     if (m->time_glm) SMC_CUDA(cudaEventRecord(m->ev0, st));
     k_glm_gram<<<(unsigned)((C + 31) / 32), dim3(32, 8), smem, st>>>(e);
     m->ctx->launches++;

@@ -36,6 +36,20 @@ static inline cudaError_t smc_dev_alloc(T** p, size_t bytes, cudaStream_t st) { 
 // blocking copy ordered on `st` (the pool's allocations are ordered on that stream, not on the legacy default stream)
 cudaError_t smc_copy_sync(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind, cudaStream_t st);
 
+// "once per device" latch for cudaFuncSetAttribute (function attributes belong to a device's context, and one process may
+// hold contexts on several devices)
+struct SmcOncePerDevice {
+  bool done[64] = {};
+  bool first() {
+    int d = 0;
+    cudaGetDevice(&d);
+    d &= 63;
+    if (done[d]) return false;
+    done[d] = true;
+    return true;
+  }
+};
+
 struct smc_ctx_s {
   int device = 0;
   int sm_count = 148;

@@ -716,12 +716,9 @@ int smc_vm_prepare(smc_model_s* m, SmcProgram& pr) {
 
 int smc_vm_launch(smc_model_s* m, SmcProgram& pr, int64_t C, int* bad) {
   cudaStream_t st = m->ctx->stream;
-  static bool attr_done = false;
+  static SmcOncePerDevice once;
   const size_t smem_max = 200 * 1024;
-  if (!attr_done) {
-    SMC_CUDA(cudaFuncSetAttribute(k_vm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
-    attr_done = true;
-  }
+  if (once.first()) SMC_CUDA(cudaFuncSetAttribute(k_vm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
   VmArgs a;
   memset(&a, 0, sizeof(a));
   const size_t nu = pr.uops.size(), ns = pr.scal_regs.size();

@@ -59,7 +59,9 @@ if "cfg3" in which:
     for C in (1, 8, 64):
         low, dev = api._build(LOGISTIC, [("vars", np.zeros(M))], dict(X=X, Y=Y), True, C, 0, "assign")
         init = b0[None, :] + 1e-3 * rng.standard_normal((C, M))
-        raw = dev.run("hmc", init, C, 10, 0, isteps=2, stepsize=0.1 / np.sqrt(N / 1000), seed=1, store_draws=False, want=())
+        kw = dict(isteps=2, stepsize=0.1 / np.sqrt(N / 1000), store_draws=False, want=())
+        dev.run("hmc", init, C, 4, 0, seed=3, **kw)      # warm-up: buffers sized, evaluation and iteration graphs captured
+        raw = dev.run("hmc", init, C, 40 if C <= 8 else 12, 0, seed=1, **kw)
         dev.eval(init)
         ms_eval, ms_glm = dev.eval_timed(5, True)
         bytes_alg = 8.0 * N * M + 8.0 * N
@@ -75,7 +77,9 @@ if "cfg3" in which:
     for C in (1, 64):
         low, dev = api._build(BINOM, [("vars", np.zeros(M))], dict(X=X, Y=Yb), True, C, 0, "assign")
         init = b0[None, :] + 1e-3 * rng.standard_normal((C, M))
-        raw = dev.run("hmc", init, C, 10, 0, isteps=2, stepsize=0.02 / np.sqrt(N / 1000), seed=1, store_draws=False, want=())
+        kw = dict(isteps=2, stepsize=0.02 / np.sqrt(N / 1000), store_draws=False, want=())
+        dev.run("hmc", init, C, 4, 0, seed=3, **kw)
+        raw = dev.run("hmc", init, C, 40 if C <= 8 else 12, 0, seed=1, **kw)
         dev.eval(init)
         ms_eval, ms_glm = dev.eval_timed(5, True)
         rows.append(dict(chains=C, leapfrog_chain_steps_per_s=raw["n_leapfrogs"] / (raw["device_ms"] * 1e-3),

@@ -117,6 +117,10 @@ int smc_nuts_run(smc_model_t m, const smc_sampler_config* cfg, const double* ini
  * draw at `step` for purpose stream `stream` */
 int smc_philox_normals(uint64_t seed, int64_t chain, int64_t step, int32_t stream, int64_t n, double* out);
 int smc_philox_uniforms(uint64_t seed, int64_t chain, int64_t step, int32_t stream, int64_t n, double* out);
+/* test hook, host only (no device needed): plan one register program (smc_prog_header + instructions + reductions, as
+ * in a tape) and write the planned micro-ops as text, one per line, into out[cap]; returns the number of micro-ops or a
+ * negative smc_status.  Lets the planner (operand folding, copy propagation, chains) be checked where there is no GPU. */
+int smc_vm_plan_describe(const void* program, size_t nbytes, char* out, size_t cap);
 
 #ifdef __cplusplus
 }

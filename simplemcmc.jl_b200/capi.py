@@ -37,7 +37,7 @@ class RunOutput(ctypes.Structure):
 EXPORTS = ["smc_abi_version", "smc_last_error", "smc_ctx_create", "smc_ctx_destroy", "smc_ctx_comm_init",
            "smc_comm_unique_id", "smc_ctx_allreduce", "smc_model_compile", "smc_model_destroy", "smc_model_bind_data",
            "smc_model_finalize", "smc_model_nparams", "smc_eval", "smc_eval_timed", "smc_hmc_run", "smc_rwm_run",
-           "smc_nuts_run", "smc_philox_normals", "smc_philox_uniforms"]
+           "smc_nuts_run", "smc_philox_normals", "smc_philox_uniforms", "smc_vm_plan_describe"]
 
 _lib = None
 
@@ -53,6 +53,7 @@ def load():
     lib = ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_GLOBAL)
     lib.smc_last_error.restype = ctypes.c_char_p
     vp, i64, dbl, i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_double, ctypes.c_int
+    lib.smc_vm_plan_describe.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t]
     lib.smc_ctx_create.argtypes = [i32, ctypes.POINTER(vp)]
     lib.smc_ctx_destroy.argtypes = [vp]
     lib.smc_ctx_comm_init.argtypes = [vp, ctypes.c_char_p, i32, i32, i32]
@@ -244,3 +245,12 @@ def philox_uniforms(seed, chain, step, n):
     out = np.empty(n)
     check(load().smc_philox_uniforms(seed, chain, step, 1, n, dptr(out)))
     return out
+
+
+def plan_describe(program_bytes):
+    """test hook: the planned micro-ops of one packed register program, as text lines (host only, no device needed)"""
+    lib = load()
+    buf = ctypes.create_string_buffer(1 << 16)
+    n = lib.smc_vm_plan_describe(program_bytes, len(program_bytes), buf, len(buf))
+    check(n if n < 0 else 0)
+    return buf.value.decode().splitlines()

@@ -12,6 +12,7 @@
 // Reductions (`sum`, `dot`, vectorised logpdf: src/distribs.jl:97-105) accumulate per thread in element order, then
 // over the element lanes by a fixed tree, then over element chunks in k_vm_final: bit-reproducible for a given chain
 // count.
+#include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -649,6 +650,45 @@ int smc_vm_plan(smc_model_s* m, SmcProgram& pr) {
     }
   }
   return SMC_OK;
+}
+
+extern "C" int smc_vm_plan_describe(const void* program, size_t nbytes, char* out, size_t cap) {
+  if (!program || !out || cap == 0) { smc_set_error("smc_vm_plan_describe: NULL argument"); return SMC_ERR_INVALID; }
+  const unsigned char* p = (const unsigned char*)program;
+  SmcProgram pr;
+  if (nbytes < sizeof(pr.h)) { smc_set_error("smc_vm_plan_describe: truncated program"); return SMC_ERR_INVALID; }
+  memcpy(&pr.h, p, sizeof(pr.h));
+  const size_t need = sizeof(pr.h) + (size_t)pr.h.n_instr * sizeof(smc_prog_instr) + (size_t)pr.h.n_red * sizeof(smc_prog_red);
+  if (nbytes < need) { smc_set_error("smc_vm_plan_describe: truncated program"); return SMC_ERR_INVALID; }
+  pr.instr.resize(pr.h.n_instr);
+  if (pr.h.n_instr) memcpy(pr.instr.data(), p + sizeof(pr.h), (size_t)pr.h.n_instr * sizeof(smc_prog_instr));
+  pr.red.resize(pr.h.n_red);
+  if (pr.h.n_red) memcpy(pr.red.data(), p + sizeof(pr.h) + (size_t)pr.h.n_instr * sizeof(smc_prog_instr), (size_t)pr.h.n_red * sizeof(smc_prog_red));
+  SMC_TRY(smc_vm_plan(nullptr, pr));
+  static const char* mode_name[] = {"-", "L", "S", "A"};
+  size_t w = 0;
+  out[0] = 0;
+  auto put = [&](const char* fmt, ...) {
+    if (w + 1 >= cap) return;
+    va_list ap;
+    va_start(ap, fmt);
+    int k = vsnprintf(out + w, cap - w, fmt, ap);
+    va_end(ap);
+    if (k > 0) w = std::min(cap - 1, w + (size_t)k);
+  };
+  for (auto& u : pr.uops) {
+    if (u.op == VM_OP_CHAIN) put("chain(%u,%u,%u)", u.dist, u.darg, u.code3);
+    else if (u.op == SMC_OP_LOGPDF || u.op == SMC_OP_DLOGPDF) put("op%u(dist%u,arg%u)", u.op, u.dist, u.darg);
+    else put("op%u", u.op);
+    for (int k = 0; k < (u.op == VM_OP_CHAIN ? 4 : 3); k++) put(" %s%u", mode_name[u.mode[k]], u.mode[k] ? u.idx[k] : 0);
+    if (u.flags & VMF_ACC) put(" +=%s%u", mode_name[u.mode[3]], u.idx[3]);
+    if (u.flags & VMF_WRITE) put(" ->L%u", u.dst);
+    if (u.flags & VMF_STORE) put(" ->A%u", u.store);
+    if (u.flags & VMF_REDUCE) put(" ->R%u", u.red);
+    put("\n");
+  }
+  put("locals=%d scalars=%zu arrays=%zu\n", pr.n_loc, pr.scal_regs.size(), pr.desc_regs.size());
+  return (int)pr.uops.size();
 }
 
 static VmDesc desc_of(const smc_model_s* m, uint32_t reg) {

@@ -190,3 +190,39 @@ def test_parameter_packing_is_keyword_order_column_major():
     low = Lowering("a ~ Normal(0,1)\nb ~ Normal(0,1)\nc ~ Normal(0,1)", [("b", m), ("a", 1.5), ("c", np.array([7.0, 8.0]))], {})
     assert low.init == [0.0, 3.0, 1.0, 4.0, 2.0, 5.0, 1.5, 7.0, 8.0]
     assert [(p.sym, p.start, p.count) for p in low.pars] == [("b", 0, 6), ("a", 6, 1), ("c", 7, 2)]
+
+
+def _programs(model, init, data, **kw):
+    from simplemcmc_jl_b200 import fusion
+    from simplemcmc_jl_b200.lowering import Lowering
+    low = Lowering(model, init, data, **kw)
+    _, _, progs = fusion.fuse(low)
+    regmap = {v.vid: i for i, v in enumerate(low.vals)}
+    return [p.pack(regmap) for p in progs]
+
+
+def test_register_program_planner_forms_chains():
+    """the library's planner (host code, reached through the smc_vm_plan_describe test hook): hand-over values stay in
+    registers.  examples/ornstein.jl's residual `x[2:end] - x[1:end-1]*fac - mu*(1-fac)` is ONE chain micro-op
+    (multiply, reversed subtract, subtract) feeding the Normal density; sleepstudy's forward program is three micro-ops,
+    the last one a chain that ends in the Normal density stage."""
+    x = ou_data(1000, 5)
+    plans = [capi.plan_describe(p) for p in _programs(ORNSTEIN, [("tau", 20.0), ("mu", 10.0), ("sigma", 0.1)], dict(x=x))]
+    fwd = [pl for pl in plans if any(l.startswith("op32(dist0") and "->R0" in l for l in pl)]   # the likelihood's program
+    assert len(fwd) == 1 and len(fwd[0]) == 3, fwd                      # chain, density + reduction, summary line
+    assert fwd[0][0].startswith("chain(4,3,2) A0 S0 A1 S1 ->L0"), fwd[0]
+    assert fwd[0][1].startswith("op32(dist0,arg0) S2 S3 L0 ->R0"), fwd[0]
+    data, nsub = sleepstudy_data()
+    init = [("intercept", 250.0), ("slope", 10.0), ("rand_int", np.zeros(nsub)), ("rand_slope", np.zeros(nsub))]
+    plans = [capi.plan_describe(p) for p in _programs(SLEEPSTUDY2, init, data)]
+    big = [pl for pl in plans if any(l.startswith("chain(2,8,0)") for l in pl)]
+    assert len(big) == 1 and len(big[0]) == 4, plans
+    assert big[0][2].startswith("chain(2,8,0) L1 A3 S2 S3 ->R0"), big[0]   # (r - reaction) then Normal log-density, reduced
+    # without chains the same program needs six micro-ops
+    os.environ["SMC_VM_NO_CHAINS"] = "1"
+    try:
+        plain = [capi.plan_describe(p) for p in _programs(SLEEPSTUDY2, init, data)]
+    finally:
+        del os.environ["SMC_VM_NO_CHAINS"]
+    assert max(len(pl) for pl in plain) - 1 > max(len(pl) for pl in plans) - 1
+    assert sum(len(pl) for pl in plain) > sum(len(pl) for pl in plans)

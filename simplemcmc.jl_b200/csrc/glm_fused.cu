@@ -528,7 +528,8 @@ __global__ void __launch_bounds__(256) k_glm_stream(GlmStreamArgs a) {
 // 88 B per thread, 45 KB per SM at two CTAs), so 2-3 stages x 22 KB x 2 CTAs are in flight per SM.
 // Needs 16-byte aligned column segments: N even (otherwise the register-pipelined kernel runs).
 // Measured non-improvement: three CTAs per SM (72 registers by re-reading the row from the stage instead of holding it,
-// 3 stages): 0.177 ms against 0.170 ms on cfg3 with one chain, 0.231 against 0.220 ms for the Binomial counts.
+// 3 stages): 0.177 ms against 0.170 ms on cfg3 with one chain, 0.231 against 0.220 ms for the Binomial counts; two rows
+// per thread from two consecutive tiles (two independent exp / divide / log chains to interleave): 0.181 ms.
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
 template <int FAM, int MB, int CT>

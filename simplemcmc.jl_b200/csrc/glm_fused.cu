@@ -529,7 +529,8 @@ __global__ void __launch_bounds__(256) k_glm_stream(GlmStreamArgs a) {
 // Needs 16-byte aligned column segments: N even (otherwise the register-pipelined kernel runs).
 // Measured non-improvement: three CTAs per SM (72 registers by re-reading the row from the stage instead of holding it,
 // 3 stages): 0.177 ms against 0.170 ms on cfg3 with one chain, 0.231 against 0.220 ms for the Binomial counts; two rows
-// per thread from two consecutive tiles (two independent exp / divide / log chains to interleave): 0.181 ms.
+// per thread from two consecutive tiles (two independent exp / divide / log chains to interleave): 0.181 ms; 512-row
+// tiles (4 KB segments, two stages): 0.203 ms.
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
 template <int FAM, int MB, int CT>

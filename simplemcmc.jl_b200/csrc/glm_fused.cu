@@ -849,6 +849,11 @@ int launch_cfg(const GlmArgs& a, int RS, cudaStream_t st) {
 
 template <int FAM, int MP8>
 int launch_mp(const GlmArgs& a, int tc, int RS, cudaStream_t st) {
+  if constexpr (MP8 == 2) {
+    // narrow models with very many chains: four m-tiles (32 chains) per warp, 256 chains per CTA.  A row block is then
+    // 28 DMMAs instead of 14 for the same operand loads and loop overhead (G and the beta fragments are small here).
+    if (tc == 256) return launch_cfg<FAM, 4, 8, 1, MP8>(a, RS, st);
+  }
   switch (tc) {
     case 128: return launch_cfg<FAM, 2, 8, 1, MP8>(a, RS, st);   // (a 16-warp MT=1 variant measured 86.5% vs 88.0%)
     case 64: return launch_cfg<FAM, 2, 4, 2, MP8>(a, RS, st);
@@ -1004,6 +1009,7 @@ int smc_glm_launch(smc_model_s* m, SmcGlmPlan& g, int64_t C) {
     m->ctx->launches++;
   }
   int tc = chain_tile_for(C);
+  if (g.MP <= 16 && C >= 2048 && !getenv("SMC_GLM_NO_WIDE")) tc = 256;
   long long chain_tiles = (C + tc - 1) / tc;
   int RT = SMC_GLM_RT(g.MP / 8);
   int RS = row_splits_for(chain_tiles, g.N, RT, m->ctx->sm_count * (g.MP <= 16 ? 2 : 1));  // narrow models run 2 CTAs per SM

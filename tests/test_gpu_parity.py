@@ -80,6 +80,30 @@ def test_linear_cfg1(smc, fuse, C):
     assert np.array_equal(lp, lp2)
 
 
+@pytest.mark.parametrize("family", ["normal", "bernoulli"])
+def test_narrow_glm_many_chains_wide_tile(smc, family):
+    """2048 chains and more on a model of at most 16 columns run the 256-chain tile (four m-tiles per warp): a ragged
+    chain count that leaves the last tile partly empty, rows not a multiple of the row tile"""
+    from simplemcmc_jl_b200 import api
+    C, N, M = 2500, 1003, 10
+    if family == "normal":
+        X, Y, _ = linear_data(N, M, 7)
+        model, name = LINEAR, "beta"
+    else:
+        X, Y, _ = logistic_data(N, M)
+        model, name = LOGISTIC, "vars"
+    data = dict(X=X, Y=Y)
+    ref = generate_model_function(model, data=data, gradient=True, **{name: np.zeros(M)})
+    low, dev = api._build(model, [(name, np.zeros(M))], data, True, C, 0, "assign")
+    betas = 0.3 * np.random.default_rng(5).standard_normal((C, M))
+    lp, g = dev.eval(betas)
+    for c in list(range(0, C, 97)) + [C - 1, 2047, 2048, 2303, 2304]:
+        _check(lp[c], g[c], *ref(betas[c]))
+    lp2, _ = dev.eval(betas, gradient=False)
+    assert np.array_equal(lp, lp2)
+    dev.close()
+
+
 @pytest.mark.parametrize("fuse", [True, False])
 @pytest.mark.parametrize("N,M", [(1000, 10), (777, 3), (4099, 33), (300, 64)])
 def test_logistic_cfg3_shapes(smc, fuse, N, M):

@@ -4,6 +4,8 @@ rule_cases.py differentiates one call at a time, as test/test.jl:142-224 does; h
 the statement fusion, the register-program planner (copy propagation, alias materialisation, dead-write elimination) and
 both executors, with the reference's quirks (adjoint of a slice / gather is an assignment, ties of max/min) on both
 sides.  Bar: 1e-12 relative on logp, 1e-12 of max|g| on the gradient -- the same as test_gpu_parity.py."""
+import os
+
 import numpy as np
 import pytest
 
@@ -14,6 +16,7 @@ from oracle.refmodel import ModelError, generate_model_function  # noqa: E402
 from util import relerr  # noqa: E402
 
 TOL = 1e-12
+SCALE = int(os.environ.get("SMC_FUZZ_SCALE", "1"))     # SMC_FUZZ_SCALE=k: k times as many seeds (occasional deep runs)
 
 
 @pytest.fixture(scope="module")
@@ -67,12 +70,12 @@ def _run(seed, n, m, C, fuse):
 
 @pytest.mark.parametrize("fuse", [True, False])
 def test_random_models_one_chain(smc, fuse):
-    for seed in range(150):
+    for seed in list(range(150)) + list(range(1000, 1000 + 150 * (SCALE - 1))):
         _run(seed, 23, 5, 1, fuse)
 
 
 def test_random_models_many_chains(smc):
-    for seed in range(150, 250):
+    for seed in list(range(150, 250)) + list(range(3000, 3000 + 100 * (SCALE - 1))):
         _run(seed, 23, 5, 37, True)
 
 

@@ -5,13 +5,15 @@
 //                                                    /root/reference/src/distribs.jl:12-28, src/diff.jl:94-99,165-166)
 //   L[C]       = sum_i l ;  G[M x C] = X' * d        (the generated `dbeta += transpose(X) * dtmp`, diff.jl:55)
 //
-// One pass over X per lockstep evaluation: a row tile of X is staged once in shared memory (cp.async, 3 stages)
+// One pass over X per lockstep evaluation: a row tile of X is staged once in shared memory (cp.async, 4-stage ring)
 // and used for both products.  Both contractions run on mma.sync.m8n8k4.f64 (DMMA); the accumulator
 // fragment of the first product (chain x row) is, element for element, the A fragment of the second
 // (chain x row) . (row x param) product, so eta / d never leave registers.  tcgen05 has no f64 kind.
 //
 // Grid: (chain tiles, row splits).  Each CTA writes a partial (L, G); a second kernel sums the row
 // splits in fixed order (deterministic) and publishes into the tape registers.
+// With one to four chains the same statement is an HBM stream instead (k_glm_stream_bulk / k_glm_stream below), and with
+// the opt-in sufficient statistics a Gram-matrix evaluation (k_glm_gram).
 #include <stdlib.h>
 #include <algorithm>
 #include "smc_internal.h"

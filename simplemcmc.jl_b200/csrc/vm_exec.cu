@@ -5,8 +5,9 @@
 // (/root/reference/src/parsing.jl:409-467); here every intermediate stays on chip:
 //   * plan time (smc_vm_plan): the instruction list becomes micro-ops whose operands are addressed directly -- a
 //     program-local vector slot, a per-chain scalar staged once per block, or a tape array in HBM -- so LOADV / LOADS /
-//     STOREV / REDUCE instructions disappear into operand modes and side effects of the computing instruction;
-//   * run time (k_vm<V>): thread = (chain lane, element lane); each thread owns V elements per pass, so one decode of
+//     STOREV / REDUCE instructions disappear into operand modes and side effects of the computing instruction; values
+//     that are only handed from one micro-op to the next stay in registers (chain micro-ops, vm_form_chains);
+//   * run time (k_vm): thread = (chain lane, element lane); each thread owns V elements per pass, so one decode of
 //     a micro-op is amortised over V elements.  Locals live in shared memory as [slot][v][thread] (conflict free),
 //     chains are the fastest thread index (coalesced per-chain operands, broadcast data operands).
 // Reductions (`sum`, `dot`, vectorised logpdf: src/distribs.jl:97-105) accumulate per thread in element order, then

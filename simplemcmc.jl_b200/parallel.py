@@ -5,6 +5,10 @@ Chain sharding (BASELINE.json configs 1, 2, 4, 5): chains are independent (no sh
 /root/reference/src/samplers.jl), rank g runs chains [offset, offset+count) with Philox streams keyed by the global
 chain id, data replicated; the only collective is one all-reduce of per-rank chain moments at the end (R-hat).
 Row sharding (config 3): rank g holds rows [r0, r1) of X and Y; every rank advances identical chain state.
+Hybrid (third row): the ranks form a (chain groups x row ranks) grid; the `row_ranks` consecutive ranks of
+a chain group hold the row shards of the data and advance the same chains, the library's NCCL communicator spans only
+that group (the per-evaluation all-reduce of (L, G) never leaves it), and one rank per group contributes to the final
+moment all-reduce.
 """
 import numpy as np
 
@@ -22,6 +26,57 @@ def row_shard(n_rows, rank, world):
     count = base + (1 if rank < extra else 0)
     start = rank * base + min(rank, extra)
     return start, start + count
+
+
+class HybridLayout(object):
+    """position of `rank` in the (chain groups x row ranks) grid: consecutive ranks share a chain group, so on one
+    NVSwitch box any placement is equivalent and across nodes a row group stays inside a node when row_ranks divides
+    the GPUs per node"""
+
+    def __init__(self, rank, world, row_ranks):
+        rank, world, row_ranks = int(rank), int(world), int(row_ranks)
+        if row_ranks < 1 or world % row_ranks != 0:
+            raise ValueError("row_ranks (%d) must divide the number of ranks (%d)" % (row_ranks, world))
+        if not 0 <= rank < world:
+            raise ValueError("rank %d outside [0, %d)" % (rank, world))
+        self.rank, self.world, self.row_ranks = rank, world, row_ranks
+        self.chain_groups = world // row_ranks
+        self.chain_group, self.row_rank = divmod(rank, row_ranks)
+
+    @property
+    def group_ranks(self):
+        """global ranks of this rank's row group, in row-rank order"""
+        return list(range(self.chain_group * self.row_ranks, (self.chain_group + 1) * self.row_ranks))
+
+    @property
+    def group_root(self):
+        return self.chain_group * self.row_ranks
+
+    @property
+    def counts_moments(self):
+        """every rank of a row group holds the same chains: exactly one of them reports their moments"""
+        return self.row_rank == 0
+
+    def chains(self, total_chains):
+        """(offset, count) of the global chains this rank's group advances"""
+        return chain_shard(total_chains, self.chain_group, self.chain_groups)
+
+    def rows(self, n_rows):
+        """[start, end) of the data rows this rank holds"""
+        return row_shard(n_rows, self.row_rank, self.row_ranks)
+
+
+def new_row_groups(layout):
+    """torch.distributed groups of the grid's row groups.  Collective: every rank creates every group (in the same
+    order) and gets its own back."""
+    import torch.distributed as dist
+    mine = None
+    for g in range(layout.chain_groups):
+        ranks = list(range(g * layout.row_ranks, (g + 1) * layout.row_ranks))
+        grp = dist.new_group(ranks=ranks)
+        if g == layout.chain_group:
+            mine = grp
+    return mine
 
 
 def moment_partials(chain_mean, chain_m2, n_samples):
@@ -64,15 +119,37 @@ def allreduce_sum(vec, group=None, ctx=None):
     return vec
 
 
-def init_library_comm(ctx, rank, world, group=None):
-    """create the library's NCCL communicator: rank 0 makes the unique id, torch.distributed broadcasts it"""
+def broadcast_unique_id(make_id, rank, group=None, src=0):
+    """the 128-byte NCCL unique id of a communicator: the group's rank 0 (`rank` is the rank inside the group, `src`
+    that member's global rank) makes it, torch.distributed broadcasts it to the other members"""
     import torch
     import torch.distributed as dist
-    from . import capi
     buf = torch.zeros(128, dtype=torch.uint8)
     if rank == 0:
-        buf = torch.frombuffer(bytearray(capi.unique_id()), dtype=torch.uint8).clone()
+        buf = torch.frombuffer(bytearray(make_id()), dtype=torch.uint8).clone()
     if dist.get_backend(group) == "nccl":
         buf = buf.cuda()
-    dist.broadcast(buf, src=0, group=group)
-    ctx.comm_init(bytes(buf.cpu().numpy().tobytes()), rank, world)
+    dist.broadcast(buf, src=src, group=group)
+    return bytes(buf.cpu().numpy().tobytes())
+
+
+def init_library_comm(ctx, rank, world, group=None, src=0):
+    """create the library's NCCL communicator over `group` (default: all ranks); `rank` / `world` are the position in
+    and the size of that group, `src` the global rank of its first member"""
+    from . import capi
+    ctx.comm_init(broadcast_unique_id(capi.unique_id, rank, group=group, src=src), rank, world)
+
+
+def init_hybrid_comm(ctx, layout):
+    """library communicator of this rank's row group (hybrid chains x rows sharding); returns the torch group"""
+    grp = new_row_groups(layout)
+    if layout.row_ranks > 1:
+        init_library_comm(ctx, layout.row_rank, layout.row_ranks, group=grp, src=layout.group_root)
+    return grp
+
+
+def hybrid_moment_partials(layout, chain_mean, chain_m2, n_samples):
+    """moment_partials for the final all-reduce over ALL ranks of a hybrid grid: the chains of a row group are
+    replicated on its members, so only the group's first rank contributes"""
+    part = moment_partials(chain_mean, chain_m2, n_samples)
+    return part if layout.counts_moments else np.zeros_like(part)

@@ -92,6 +92,15 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+// one X tile (64 KB) by the bulk-copy engine, four 16 KB copies completing on `bar`
+__device__ __forceinline__ void bulk_load_tile(uint8_t* dst, const int8_t* src, uint64_t* bar) {
+  const uint32_t b = smem_u32(bar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(b), "r"(65536u) : "memory");
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 :: "r"(smem_u32(dst + k * 16384)), "l"(src + k * 16384), "r"(16384u), "r"(b) : "memory");
+}
 
 // ---- layouts ----------------------------------------------------------------------------------------------------------
 // X tile (all 8 slices of 128 rows x 64 parameters), one image for both products: 128-byte core matrices
@@ -144,25 +153,30 @@ __global__ void k_slice_x(const double* __restrict__ X, int8_t* __restrict__ QX,
 }
 
 // beta: [64][ldc] (chains contiguous); y: [rows]; outL: [splits][ldc]; outG: [splits][64][ldc]
-__global__ void __launch_bounds__(128, 1)
+// NT threads = NT / 128 threads per TMEM lane: thread (rl = tid & 127, q = tid >> 7) owns row / lane rl and the chains
+// [q CQ, (q + 1) CQ) in the epilogues.  bulk = 1: the next X tile is prefetched by the bulk-copy engine (cp.async.bulk
+// completing on an mbarrier) into a second buffer while this tile is computed.
+template <int NT>
+__global__ void __launch_bounds__(NT, 1)
 k_ozaki_glm(const int8_t* __restrict__ QX, const double* __restrict__ y, const double* __restrict__ beta, int ldc,
             long long tiles, int splits, double sx, double* __restrict__ outL, double* __restrict__ outG, int* status,
-            double* __restrict__ dbg_eta) {
+            double* __restrict__ dbg_eta, int bulk) {
+  constexpr int Q = NT / 128, CQ = NC / Q, NW = NT / 32;
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t bar1, bar2;
+  __shared__ uint64_t bar1, bar2, barX[2];
   __shared__ uint32_t tmem_slot;
   __shared__ double s_sb[NC], s_L[NC], s_dscale[NC], s_dfactor[NC];
-  uint8_t* sX = smem;
-  uint8_t* sQB = smem + XT_BYTES;
+  uint8_t* sX = smem;                                     // one or two X tiles
+  uint8_t* sQB = smem + (bulk ? 2 : 1) * XT_BYTES;
   uint8_t* sQD = sQB + QB_BYTES;
   double* sD = (double*)(sQD + QD_BYTES);                 // [chain][row]
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, rl = tid & 127, q = tid >> 7;
   const int c0 = blockIdx.x * NC;
   const long long t_begin = tiles * blockIdx.y / splits, t_end = tiles * (blockIdx.y + 1) / splits;
 
   // ---- setup: TMEM, barriers, beta slices (per-chain scale) ----
   if (warp == 0) tmem_alloc(&tmem_slot, 512);
-  if (tid == 32) { mbar_init(&bar1, 1); mbar_init(&bar2, 1); }
+  if (tid == 32) { mbar_init(&bar1, 1); mbar_init(&bar2, 1); mbar_init(&barX[0], 1); mbar_init(&barX[1], 1); }
   if (tid < NC) {
     double m = 0.0;
     for (int p = 0; p < MP; p++) m = fmax(m, fabs(beta[(size_t)p * ldc + c0 + tid]));
@@ -173,38 +187,48 @@ k_ozaki_glm(const int8_t* __restrict__ QX, const double* __restrict__ y, const d
     s_L[tid] = 0.0;
   }
   __syncthreads();
-  for (int e = tid; e < NC * MP; e += 128) {
+  for (int e = tid; e < NC * MP; e += NT) {
     int c = e & (NC - 1), p = e / NC;
-    int8_t q[NS];
-    slice8(beta[(size_t)p * ldc + c0 + c], s_dfactor[c], q);
-    for (int j = 0; j < NS; j++) sQB[boff(j * NC + c, p, MP)] = (uint8_t)q[j];
+    int8_t qs[NS];
+    slice8(beta[(size_t)p * ldc + c0 + c], s_dfactor[c], qs);
+    for (int j = 0; j < NS; j++) sQB[boff(j * NC + c, p, MP)] = (uint8_t)qs[j];
   }
   fence_async_smem();
   fence_before();
   __syncthreads();
   fence_after();
   const uint32_t tmem = tmem_slot;
-  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-  const uint32_t xs = smem_u32(sX), qbs = smem_u32(sQB), qds = smem_u32(sQD);
-  const int ii = tid >> 6;                                // product-2 lane block of this thread
-  double gacc[NC];
+  const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+  const uint32_t qbs = smem_u32(sQB), qds = smem_u32(sQD);
+  const int ii = rl >> 6;                                 // product-2 lane block of this thread
+  double gacc[CQ];
 #pragma unroll
-  for (int c = 0; c < NC; c++) gacc[c] = 0.0;
+  for (int c = 0; c < CQ; c++) gacc[c] = 0.0;
   uint32_t phase = 0;
   bool ok = true;
+  if (bulk && tid == 0 && t_begin < t_end) bulk_load_tile(sX, QX + t_begin * (long long)XT_BYTES, &barX[0]);
 
   for (long long t = t_begin; t < t_end && ok; t++) {
-    // ---- X tile: flat 64 KB copy (the global image already has the shared-memory layout) ----
-    const uint4* src = (const uint4*)(QX + t * (long long)XT_BYTES);
-    uint4* dst = (uint4*)sX;
+    const int stage = bulk ? (int)((t - t_begin) & 1) : 0;
+    const uint32_t xs = smem_u32(sX + (size_t)stage * XT_BYTES);
+    const double yr = y[t * TR + rl];
+    if (!bulk) {
+      // X tile: flat 64 KB copy (the global image already has the shared-memory layout)
+      const uint4* src = (const uint4*)(QX + t * (long long)XT_BYTES);
+      uint4* dst = (uint4*)sX;
 #pragma unroll 8
-    for (int k = 0; k < (int)(XT_BYTES / 16 / 128); k++) dst[k * 128 + tid] = __ldg(src + k * 128 + tid);
-    const double yr = y[t * TR + tid];
-    fence_async_smem();
-    fence_before();
-    __syncthreads();
+      for (int k = 0; k < (int)(XT_BYTES / 16 / NT); k++) dst[k * NT + tid] = __ldg(src + k * NT + tid);
+      fence_async_smem();
+      fence_before();
+      __syncthreads();
+    }
     // ---- product 1 ----
     if (tid == 0) {
+      if (bulk) {
+        // the other buffer was last read by the previous tile's product 2, which has completed (bar2)
+        if (t + 1 < t_end) bulk_load_tile(sX + (size_t)(stage ^ 1) * XT_BYTES, QX + (t + 1) * (long long)XT_BYTES, &barX[stage ^ 1]);
+        if (!mbar_wait(&barX[stage], (uint32_t)(((t - t_begin) >> 1) & 1), 4000000000ll)) *status = 2;
+      }
       fence_after();
 #pragma unroll 1
       for (int i = 0; i < NS; i++) {
@@ -218,9 +242,9 @@ k_ozaki_glm(const int8_t* __restrict__ QX, const double* __restrict__ y, const d
     ok = mbar_wait(&bar1, phase, 4000000000ll);
     fence_after();
     if (!ok) break;
-    // ---- epilogue 1: thread = row ----
+    // ---- epilogue 1: thread = (row, chain group) ----
 #pragma unroll 1
-    for (int cc = 0; cc < NC; cc += 8) {
+    for (int cc = q * CQ; cc < (q + 1) * CQ; cc += 8) {
       int32_t a[NS][8];
 #pragma unroll
       for (int cb = 0; cb < NS; cb++) tmem_ld8_nowait(tmem + lane_base + (uint32_t)(cb * NC + cc), a[cb]);
@@ -231,20 +255,20 @@ k_ozaki_glm(const int8_t* __restrict__ QX, const double* __restrict__ y, const d
 #pragma unroll
         for (int cb = 0; cb < NS; cb++) g[cb] = a[cb][u];
         double eta = recombine(g, 0x1p-35, 0x1p-63) * (sx * s_sb[cc + u]);
-        if (dbg_eta != nullptr && blockIdx.y == 0 && t == t_begin) dbg_eta[(size_t)tid * ldc + c0 + cc + u] = eta;
-        sD[(cc + u) * TR + tid] = yr - eta;
+        if (dbg_eta != nullptr && blockIdx.y == 0 && t == t_begin) dbg_eta[(size_t)rl * ldc + c0 + cc + u] = eta;
+        sD[(cc + u) * TR + rl] = yr - eta;
       }
     }
     __syncthreads();
-    // per chain (one warp, 8 chains each): sum of squares and max |d| -> scale of this tile's adjoint
-    for (int c = warp; c < NC; c += 4) {
-      double s = 0.0, m = 0.0;
+    // per chain (one warp each): sum of squares and max |d| -> scale of this tile's adjoint
+    for (int c = warp; c < NC; c += NW) {
+      double ssum = 0.0, m = 0.0;
 #pragma unroll
-      for (int k = 0; k < TR / 32; k++) { double d = sD[c * TR + k * 32 + lane]; s = fma(d, d, s); m = fmax(m, fabs(d)); }
+      for (int k = 0; k < TR / 32; k++) { double d = sD[c * TR + k * 32 + lane]; ssum = fma(d, d, ssum); m = fmax(m, fabs(d)); }
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o)); }
+      for (int o = 16; o > 0; o >>= 1) { ssum += __shfl_xor_sync(0xffffffffu, ssum, o); m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o)); }
       if (lane == 0) {
-        s_L[c] += -0.5 * s;
+        s_L[c] += -0.5 * ssum;
         double sc, f;
         scale_of(m, &sc, &f);
         s_dscale[c] = sc;
@@ -252,13 +276,13 @@ k_ozaki_glm(const int8_t* __restrict__ QX, const double* __restrict__ y, const d
       }
     }
     __syncthreads();
-    // d -> int8 slices, K-major with K = rows: thread = row
+    // d -> int8 slices, K-major with K = rows
 #pragma unroll 4
-    for (int c = 0; c < NC; c++) {
-      int8_t q[NS];
-      slice8(sD[c * TR + tid], s_dfactor[c], q);
+    for (int c = q * CQ; c < (q + 1) * CQ; c++) {
+      int8_t qs[NS];
+      slice8(sD[c * TR + rl], s_dfactor[c], qs);
 #pragma unroll
-      for (int j = 0; j < NS; j++) sQD[boff(j * NC + c, tid, TR)] = (uint8_t)q[j];
+      for (int j = 0; j < NS; j++) sQD[boff(j * NC + c, rl, TR)] = (uint8_t)qs[j];
     }
     fence_async_smem();
     fence_before();
@@ -278,41 +302,41 @@ k_ozaki_glm(const int8_t* __restrict__ QX, const double* __restrict__ y, const d
     ok = mbar_wait(&bar2, phase, 4000000000ll);
     fence_after();
     if (!ok) break;
-    // ---- epilogue 2: thread = (ii, parameter); lanes 64..127 hold the groups shifted by one ----
+    // ---- epilogue 2: thread = ((ii, parameter), chain group); lanes 64..127 hold the groups shifted by one ----
     const double w_hi = ii ? 0x1p-42 : 0x1p-35, w_lo = ii ? 0x1p-70 : 0x1p-63;
 #pragma unroll
-    for (int cc = 0; cc < NC; cc += 8) {
+    for (int cc = 0; cc < CQ; cc += 8) {
       int32_t a[NS][8];
 #pragma unroll
-      for (int cb = 0; cb < NS; cb++) tmem_ld8_nowait(tmem + lane_base + 256u + (uint32_t)(cb * NC + cc), a[cb]);
+      for (int cb = 0; cb < NS; cb++) tmem_ld8_nowait(tmem + lane_base + 256u + (uint32_t)(cb * NC + q * CQ + cc), a[cb]);
       tmem_ld_wait();
 #pragma unroll
       for (int u = 0; u < 8; u++) {
         int32_t g[NS];
 #pragma unroll
         for (int cb = 0; cb < NS; cb++) g[cb] = a[cb][u];
-        gacc[cc + u] = fma(recombine(g, w_hi, w_lo), sx * s_dscale[cc + u], gacc[cc + u]);
+        gacc[cc + u] = fma(recombine(g, w_hi, w_lo), sx * s_dscale[q * CQ + cc + u], gacc[cc + u]);
       }
     }
     fence_before();
     __syncthreads();
     phase ^= 1;
   }
-  if (!ok && tid == 0) *status = 1;
+  if (!ok && rl == 0) *status = 1;
   // ---- write this row split's partial sums: G = lane block 0 + lane block 1 ----
   __syncthreads();
   double* sG = sD;                                        // [chain][64]
   if (ii == 1) {
 #pragma unroll
-    for (int c = 0; c < NC; c++) sG[c * MP + (tid & 63)] = gacc[c];
+    for (int c = 0; c < CQ; c++) sG[(q * CQ + c) * MP + (rl & 63)] = gacc[c];
   }
   __syncthreads();
   if (ii == 0) {
 #pragma unroll
-    for (int c = 0; c < NC; c++) sG[c * MP + tid] += gacc[c];
+    for (int c = 0; c < CQ; c++) sG[(q * CQ + c) * MP + rl] += gacc[c];
   }
   __syncthreads();
-  for (int e = tid; e < NC * MP; e += 128) {
+  for (int e = tid; e < NC * MP; e += NT) {
     int c = e & (NC - 1), p = e / NC;
     outG[((size_t)blockIdx.y * MP + p) * ldc + c0 + c] = sG[c * MP + p];
   }
@@ -328,6 +352,29 @@ struct Rng {
   double uni() { s = s * 6364136223846793005ull + 1442695040888963407ull; return ((s >> 11) + 0.5) * (1.0 / 9007199254740992.0); }
   double normal() { double u = uni(), v = uni(); return sqrt(-2.0 * log(u)) * cos(6.283185307179586 * v); }
 };
+
+struct Buffers {
+  const int8_t* QX; const double *Y, *B; double *L, *G, *eta; int* status;
+};
+
+template <int NT>
+int launch_variant(const Buffers& b, int bulk, dim3 grid, int ldc, long long tiles, int splits, double sx, int reps, float* best_ms) {
+  const size_t shm = SMEM_BYTES + (bulk ? XT_BYTES : 0);
+  CK(cudaFuncSetAttribute(k_ozaki_glm<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+  cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < reps; rep++) {
+    CK(cudaEventRecord(e0));
+    k_ozaki_glm<NT><<<grid, NT, shm>>>(b.QX, b.Y, b.B, ldc, tiles, splits, sx, b.L, b.G, b.status, b.eta, bulk);
+    CK(cudaEventRecord(e1));
+    CK(cudaGetLastError());
+    CK(cudaEventSynchronize(e1));
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (reps == 1 || rep > 0) best = fminf(best, ms);
+  }
+  *best_ms = best;
+  return 0;
+}
 
 int run(bool check, long long rows, int chains, int splits) {
   const long long tiles = (rows + TR - 1) / TR, prow = tiles * TR;
@@ -355,73 +402,89 @@ int run(bool check, long long rows, int chains, int splits) {
   CK(cudaMalloc(&dX, X.size() * 8)); CK(cudaMalloc(&dY, Y.size() * 8)); CK(cudaMalloc(&dB, B.size() * 8));
   CK(cudaMalloc(&dQX, (size_t)tiles * XT_BYTES)); CK(cudaMalloc(&dS, sizeof(int)));
   CK(cudaMalloc(&dL, (size_t)splits * ldc * 8)); CK(cudaMalloc(&dG, (size_t)splits * MP * ldc * 8));
-  if (check) { CK(cudaMalloc(&dEta, (size_t)TR * ldc * 8)); CK(cudaMemset(dEta, 0, (size_t)TR * ldc * 8)); }
+  if (check) CK(cudaMalloc(&dEta, (size_t)TR * ldc * 8));
   CK(cudaMemcpy(dX, X.data(), X.size() * 8, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dY, Y.data(), Y.size() * 8, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dB, B.data(), B.size() * 8, cudaMemcpyHostToDevice));
-  CK(cudaMemset(dS, 0, sizeof(int)));
   k_slice_x<<<(unsigned)((prow * MP + 255) / 256), 256>>>(dX, dQX, prow, fx);
   CK(cudaGetLastError());
-  CK(cudaFuncSetAttribute(k_ozaki_glm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  CK(cudaDeviceSynchronize());
   dim3 grid(ldc / NC, splits);
-  cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-  float best = 1e30f;
-  const int reps = check ? 1 : 4;
-  for (int rep = 0; rep < reps; rep++) {
-    CK(cudaEventRecord(e0));
-    k_ozaki_glm<<<grid, 128, SMEM_BYTES>>>(dQX, dY, dB, ldc, tiles, splits, sx, dL, dG, dS, dEta);
-    CK(cudaEventRecord(e1));
-    CK(cudaGetLastError());
-    CK(cudaEventSynchronize(e1));
-    float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
-    if (reps == 1 || rep > 0) best = fminf(best, ms);
-  }
-  int st = 0; CK(cudaMemcpy(&st, dS, sizeof(int), cudaMemcpyDeviceToHost));
-  std::vector<double> L((size_t)splits * ldc), G((size_t)splits * MP * ldc);
-  CK(cudaMemcpy(L.data(), dL, L.size() * 8, cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(G.data(), dG, G.size() * 8, cudaMemcpyDeviceToHost));
-  const double flop = 4.0 * (double)rows * MP * chains;
-  if (!check) {
-    printf("{\"probe\": \"ozaki_glm_time\", \"rows\": %lld, \"chains\": %d, \"row_splits\": %d, \"ctas\": %d, \"ms\": %.4f, \"timeout\": %d, "
-           "\"fp64_equiv_TFLOPs\": %.3f, \"logp0\": %.17g}\n", rows, chains, splits, (int)(grid.x * grid.y), best, st,
-           flop / (best * 1e-3) * 1e-12, L[0]);
-    return 0;
-  }
-  // reference in long double; errors relative to max |.| per chain (the parity metric of tests/test_gpu_parity.py)
-  std::vector<double> eta_dev((size_t)TR * ldc);
-  CK(cudaMemcpy(eta_dev.data(), dEta, eta_dev.size() * 8, cudaMemcpyDeviceToHost));
-  double err_eta = 0, err_L = 0, err_G = 0, err_G64 = 0, err_L64 = 0;
-  for (int c = 0; c < chains; c++) {
-    std::vector<long double> g(MP, 0.0L);
-    std::vector<double> g64(MP, 0.0);
-    long double Lr = 0.0L; double L64 = 0.0;
-    long double eta_max = 0.0L, eta_err = 0.0L;
-    for (long long r = 0; r < rows; r++) {
-      long double eta = 0.0L; double e64 = 0.0;
-      for (int p = 0; p < MP; p++) {
-        eta += (long double)X[(size_t)r * MP + p] * (long double)B[(size_t)p * ldc + c];
-        e64 = fma(X[(size_t)r * MP + p], B[(size_t)p * ldc + c], e64);
+  Buffers bufs{dQX, dY, dB, dL, dG, dEta, dS};
+
+  // reference in long double (check only); errors relative to max |.| per chain (the parity metric of tests/test_gpu_parity.py)
+  std::vector<long double> Lref, Gref, eta_ref;
+  double err_G64 = 0, err_L64 = 0;
+  if (check) {
+    Lref.assign(chains, 0.0L); Gref.assign((size_t)MP * chains, 0.0L); eta_ref.assign((size_t)TR * chains, 0.0L);
+    for (int c = 0; c < chains; c++) {
+      std::vector<double> g64(MP, 0.0); double L64 = 0.0;
+      for (long long r = 0; r < rows; r++) {
+        long double eta = 0.0L; double e64 = 0.0;
+        for (int p = 0; p < MP; p++) {
+          eta += (long double)X[(size_t)r * MP + p] * (long double)B[(size_t)p * ldc + c];
+          e64 = fma(X[(size_t)r * MP + p], B[(size_t)p * ldc + c], e64);
+        }
+        long double d = (long double)Y[(size_t)r] - eta; double d64 = Y[(size_t)r] - e64;
+        Lref[c] += -0.5L * d * d; L64 += -0.5 * d64 * d64;
+        for (int p = 0; p < MP; p++) { Gref[(size_t)p * chains + c] += (long double)X[(size_t)r * MP + p] * d; g64[p] = fma(X[(size_t)r * MP + p], d64, g64[p]); }
+        if (r < TR) eta_ref[(size_t)r * chains + c] = eta;
       }
-      long double d = (long double)Y[(size_t)r] - eta; double d64 = Y[(size_t)r] - e64;
-      Lr += -0.5L * d * d; L64 += -0.5 * d64 * d64;
-      for (int p = 0; p < MP; p++) { g[p] += (long double)X[(size_t)r * MP + p] * d; g64[p] = fma(X[(size_t)r * MP + p], d64, g64[p]); }
-      if (r < TR) { eta_max = fmaxl(eta_max, fabsl(eta)); eta_err = fmaxl(eta_err, fabsl((long double)eta_dev[(size_t)r * ldc + c] - eta)); }
+      long double gmax = 0.0L, gerr64 = 0.0L;
+      for (int p = 0; p < MP; p++) { gmax = fmaxl(gmax, fabsl(Gref[(size_t)p * chains + c])); gerr64 = fmaxl(gerr64, fabsl((long double)g64[p] - Gref[(size_t)p * chains + c])); }
+      err_G64 = fmax(err_G64, (double)(gerr64 / gmax));
+      err_L64 = fmax(err_L64, (double)fabsl(((long double)L64 - Lref[c]) / Lref[c]));
     }
-    long double Ld = 0.0L, gmax = 0.0L, gerr = 0.0L, gerr64 = 0.0L;
-    for (int s = 0; s < splits; s++) Ld += L[(size_t)s * ldc + c];
-    for (int p = 0; p < MP; p++) {
-      long double gd = 0.0L;
-      for (int s = 0; s < splits; s++) gd += G[((size_t)s * MP + p) * ldc + c];
-      gmax = fmaxl(gmax, fabsl(g[p])); gerr = fmaxl(gerr, fabsl(gd - g[p])); gerr64 = fmaxl(gerr64, fabsl((long double)g64[p] - g[p]));
-    }
-    err_eta = fmax(err_eta, (double)(eta_err / eta_max));
-    err_L = fmax(err_L, (double)fabsl((Ld - Lr) / Lr)); err_L64 = fmax(err_L64, (double)fabsl(((long double)L64 - Lr) / Lr));
-    err_G = fmax(err_G, (double)(gerr / gmax)); err_G64 = fmax(err_G64, (double)(gerr64 / gmax));
   }
-  printf("{\"probe\": \"ozaki_glm_check\", \"rows\": %lld, \"chains\": %d, \"row_splits\": %d, \"timeout\": %d, \"ms\": %.4f, "
-         "\"relerr_eta_tile0\": %.3e, \"relerr_logp\": %.3e, \"relerr_grad\": %.3e, \"fp64_host_relerr_logp\": %.3e, "
-         "\"fp64_host_relerr_grad\": %.3e, \"meets_1e-12\": %s}\n", rows, chains, splits, st, best, err_eta, err_L, err_G, err_L64, err_G64,
-         (st == 0 && err_L <= 1e-12 && err_G <= 1e-12) ? "true" : "false");
+
+  const double flop = 4.0 * (double)rows * MP * chains;
+  const int variants[6][2] = {{128, 0}, {256, 0}, {512, 0}, {128, 1}, {256, 1}, {512, 1}};
+  for (int v = 0; v < 6; v++) {
+    const int NT = variants[v][0], bulk = variants[v][1];
+    CK(cudaMemset(dS, 0, sizeof(int)));
+    CK(cudaMemset(dL, 0xff, (size_t)splits * ldc * 8)); CK(cudaMemset(dG, 0xff, (size_t)splits * MP * ldc * 8));
+    if (check) CK(cudaMemset(dEta, 0, (size_t)TR * ldc * 8));
+    float best = 0;
+    int rc = NT == 128 ? launch_variant<128>(bufs, bulk, grid, ldc, tiles, splits, sx, check ? 1 : 3, &best)
+           : NT == 256 ? launch_variant<256>(bufs, bulk, grid, ldc, tiles, splits, sx, check ? 1 : 3, &best)
+                       : launch_variant<512>(bufs, bulk, grid, ldc, tiles, splits, sx, check ? 1 : 3, &best);
+    if (rc) return rc;
+    int st = 0; CK(cudaMemcpy(&st, dS, sizeof(int), cudaMemcpyDeviceToHost));
+    std::vector<double> L((size_t)splits * ldc), G((size_t)splits * MP * ldc);
+    CK(cudaMemcpy(L.data(), dL, L.size() * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(G.data(), dG, G.size() * 8, cudaMemcpyDeviceToHost));
+    if (!check) {
+      double l0 = 0; for (int s2 = 0; s2 < splits; s2++) l0 += L[(size_t)s2 * ldc];
+      printf("{\"probe\": \"ozaki_glm_time\", \"threads\": %d, \"bulk_prefetch\": %d, \"rows\": %lld, \"chains\": %d, \"row_splits\": %d, \"ctas\": %d, "
+             "\"ms\": %.4f, \"timeout\": %d, \"fp64_equiv_TFLOPs\": %.3f, \"us_per_tile\": %.3f, \"logp0\": %.17g}\n", NT, bulk, rows, chains, splits,
+             (int)(grid.x * grid.y), best, st, flop / (best * 1e-3) * 1e-12,
+             best * 1e3 / ((double)tiles * grid.x / 148.0), l0);
+      continue;
+    }
+    std::vector<double> eta_dev((size_t)TR * ldc);
+    CK(cudaMemcpy(eta_dev.data(), dEta, eta_dev.size() * 8, cudaMemcpyDeviceToHost));
+    double err_eta = 0, err_L = 0, err_G = 0;
+    for (int c = 0; c < chains; c++) {
+      long double eta_max = 0.0L, eta_err = 0.0L;
+      for (int r = 0; r < TR && r < rows; r++) {
+        eta_max = fmaxl(eta_max, fabsl(eta_ref[(size_t)r * chains + c]));
+        eta_err = fmaxl(eta_err, fabsl((long double)eta_dev[(size_t)r * ldc + c] - eta_ref[(size_t)r * chains + c]));
+      }
+      long double Ld = 0.0L, gmax = 0.0L, gerr = 0.0L;
+      for (int s2 = 0; s2 < splits; s2++) Ld += L[(size_t)s2 * ldc + c];
+      for (int p = 0; p < MP; p++) {
+        long double gd = 0.0L;
+        for (int s2 = 0; s2 < splits; s2++) gd += G[((size_t)s2 * MP + p) * ldc + c];
+        gmax = fmaxl(gmax, fabsl(Gref[(size_t)p * chains + c])); gerr = fmaxl(gerr, fabsl(gd - Gref[(size_t)p * chains + c]));
+      }
+      double e1 = (double)(eta_err / eta_max), e2 = (double)fabsl((Ld - Lref[c]) / Lref[c]), e3 = (double)(gerr / gmax);
+      err_eta = e1 > err_eta || e1 != e1 ? e1 : err_eta; err_L = e2 > err_L || e2 != e2 ? e2 : err_L; err_G = e3 > err_G || e3 != e3 ? e3 : err_G;
+    }
+    printf("{\"probe\": \"ozaki_glm_check\", \"threads\": %d, \"bulk_prefetch\": %d, \"rows\": %lld, \"chains\": %d, \"row_splits\": %d, \"timeout\": %d, "
+           "\"ms\": %.4f, \"relerr_eta_tile0\": %.3e, \"relerr_logp\": %.3e, \"relerr_grad\": %.3e, \"fp64_host_relerr_logp\": %.3e, "
+           "\"fp64_host_relerr_grad\": %.3e, \"meets_1e-12\": %s}\n", NT, bulk, rows, chains, splits, st, best, err_eta, err_L, err_G, err_L64, err_G64,
+           (st == 0 && err_L <= 1e-12 && err_G <= 1e-12) ? "true" : "false");
+  }
   return 0;
 }
 

@@ -66,15 +66,17 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" :: "r"(smem_u32(bar)) : "memory");
 }
+// bounded wait.  try_wait suspends the warp (hint: up to 2 us) until the phase completes, so waiting warps do not
+// compete for issue slots with the thread that feeds the tensor core; `max_cycles` only bounds the number of retries
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, long long max_cycles) {
-  long long t0 = clock64();
-  for (;;) {
+  const uint32_t addr = smem_u32(bar);
+  for (long long it = 0; it < (max_cycles >> 12); it++) {
     uint32_t done;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
-                 : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(done) : "r"(addr), "r"(parity), "r"(2000u) : "memory");
     if (done) return true;
-    if (clock64() - t0 > max_cycles) return false;
   }
+  return false;
 }
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t cols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" :: "r"(smem_u32(slot)), "r"(cols) : "memory");

@@ -1,9 +1,7 @@
 mkdir -p gpurun_out
-P=tools/ozaki_glm_proto
 {
-timeout 60 $P check 8192 64 3 5 || echo "{\"rc\": $?}"
-timeout 60 $P time 250000 4096 37 2 || echo "{\"rc\": $?}"
-timeout 60 $P time 250000 4096 37 5 || echo "{\"rc\": $?}"
-timeout 120 $P time 1000000 4096 37 5 || echo "{\"rc\": $?}"
-} > gpurun_out/ozaki_proto6.jsonl 2>&1
-cat gpurun_out/ozaki_proto6.jsonl
+timeout 60 tools/ozaki_glm_proto_m check 8192 64 3 7 || echo "{\"rc\": $?}"
+timeout 60 tools/ozaki_glm_proto_m time 250000 4096 37 7 || echo "{\"rc\": $?}"
+timeout 60 tools/ozaki_glm_proto time 250000 4096 37 7 || echo "{\"rc\": $?}"
+} > gpurun_out/ozaki_proto9.jsonl 2>&1
+cat gpurun_out/ozaki_proto9.jsonl

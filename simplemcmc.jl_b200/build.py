@@ -51,5 +51,22 @@ def build(force=False, verbose=False):
     return LIB
 
 
+TOOLS = ["i8_umma_probe", "ozaki_glm_proto"]
+
+
+def build_tools(force=False):
+    """stand-alone sm_100a probes under tools/ (the tcgen05 int8 probe and the sliced-integer GLM prototype of DESIGN.md
+    section 8); not linked into the library"""
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    tools = os.path.join(HERE, "..", "tools")
+    out = []
+    for name in TOOLS:
+        src, exe = os.path.join(tools, name + ".cu"), os.path.join(tools, name)
+        if os.path.exists(src) and (force or _stale(exe, [src])):
+            subprocess.check_call([nvcc, "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a", "-o", exe, src])
+        out.append(exe)
+    return out
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,121 @@
+"""CPU check of the arithmetic of the sliced-integer GLM prototype (tools/ozaki_glm_proto.cu): the
+exact integer algorithm of the v4/v5 kernels -- seven balanced 8-bit slices per operand, slice pairs with i + j <= 6
+accumulated per group i + j in (emulated) int32, the stacked two-slice arrangement of product 2 whose second lane block
+holds the groups shifted by one, recombination from two int64 halves, a power-of-two scale per (128-row tile, chain) for
+the adjoint -- restated in NumPy and compared with 80-bit long double on configs[1]-shaped data.  The bar is the parity
+bar of the GPU suite: 1e-12 relative to max |.| per chain.  No GPU, no oracle: this pins the algorithm, the GPU test
+`test_gpu_zz_prototype.py` pins the kernel."""
+import numpy as np
+import pytest
+
+NS, TR, H8 = 7, 128, sum(128 << (8 * k) for k in range(7))
+
+
+def _scale(m):
+    """power of two strictly above m (1 for m == 0), as scale_of8 takes it from the exponent field"""
+    m = np.asarray(m, dtype=np.float64)
+    return np.where(m > 0, 2.0 ** np.frexp(np.where(m > 0, m, 1.0))[1], 1.0)
+
+
+def _slices(v, scale):
+    """slice j (0 = most significant) = byte 6-j of (trunc(v 2^54 / scale) + H8), minus 128"""
+    t = np.trunc(v * (2.0 ** 54 / scale)).astype(np.int64)
+    u = (t + H8).astype(np.uint64)
+    assert np.all(u < (1 << 56))
+    return [((u >> np.uint64(8 * (6 - j))) & np.uint64(255)).astype(np.int64) - 128 for j in range(NS)]
+
+
+def _recombine(acc, shift_groups):
+    """sum_cb acc[cb] 2^(-12 - 8 (cb + shift_groups)) through two int64 halves"""
+    assert np.all(np.abs(acc) < 2 ** 31)                      # what the tensor core accumulates in int32
+    hi = (acc[0] << 24) + (acc[1] << 16) + (acc[2] << 8) + acc[3]
+    lo = (acc[4] << 16) + (acc[5] << 8) + acc[6]
+    assert np.all(np.abs(hi) < 2 ** 51)
+    s = 2.0 ** (-8 * shift_groups)
+    return hi.astype(np.float64) * (2.0 ** -36 * s) + lo.astype(np.float64) * (2.0 ** -60 * s)
+
+
+def sliced_glm(X, Y, B):
+    """(logp, G) of Y - X B ~ Normal(0, 1) without the constant, the way k_ozaki_glm_v5 computes them"""
+    N, M = X.shape
+    C = B.shape[1]
+    sx = float(_scale(np.abs(X).max()))
+    QX = _slices(X, sx) + [np.zeros(X.shape, np.int64)]       # slot 7 = zeros (second half of the pair (6, 7))
+    sb = _scale(np.abs(B).max(axis=0))
+    QB = _slices(B, sb[None, :])
+    L, G = np.zeros(C), np.zeros((M, C))
+    for r0 in range(0, N, TR):
+        rows = slice(r0, r0 + TR)
+        acc = np.zeros((NS, TR, C), np.int64)                 # product 1: column block cb = i + j
+        for i in range(NS):
+            for j in range(NS - i):
+                acc[i + j] += QX[i][rows] @ QB[j]
+        eta = _recombine(acc, 0) * (sx * sb[None, :])
+        d = Y[rows, None] - eta
+        L += -0.5 * np.sum(d * d, axis=0)
+        sd = _scale(np.abs(d).max(axis=0))                    # per (tile, chain)
+        QD = _slices(d, sd[None, :])
+        acc2 = np.zeros((NS, 2, M, C), np.int64)              # product 2: lane block ii holds group cb + ii
+        for i in range(0, NS, 2):
+            for j in range(NS - i):
+                for ii in range(2):
+                    acc2[i + j, ii] += QX[i + ii][rows].T @ QD[j]
+        for ii in range(2):
+            G += _recombine(acc2[:, ii], ii) * (sx * sd[None, :])
+    return L, G
+
+
+def _problem(N, M, C, seed, spread=1e-3):
+    rng = np.random.default_rng(seed)
+    X = np.column_stack([np.ones(N), rng.standard_normal((N, M - 1))])
+    b0 = rng.standard_normal(M)
+    Y = X @ b0 + rng.standard_normal(N)
+    B = b0[:, None] + spread * rng.standard_normal((M, C))
+    return X, Y, B
+
+
+def _truth(X, Y, B):
+    Xl, Yl, Bl = X.astype(np.longdouble), Y.astype(np.longdouble), B.astype(np.longdouble)
+    d = Yl[:, None] - Xl @ Bl
+    return -0.5 * np.sum(d * d, axis=0), Xl.T @ d
+
+
+@pytest.mark.parametrize("N,M,C,seed,spread", [(2048, 64, 8, 2, 1e-3), (1024, 64, 5, 7, 1.0), (512, 10, 3, 11, 1e-6)])
+def test_sliced_glm_meets_the_parity_bar(N, M, C, seed, spread):
+    X, Y, B = _problem(N, M, C, seed, spread)
+    L, G = sliced_glm(X, Y, B)
+    Lt, Gt = _truth(X, Y, B)
+    assert float(np.max(np.abs((L - Lt) / Lt))) <= 1e-13
+    assert float(np.max(np.abs(G - Gt) / np.max(np.abs(Gt), axis=0))) <= 1e-12
+    # and it is as good as the FP64 evaluation it is meant to replace (within a small factor)
+    G64 = X.T @ (Y[:, None] - X @ B)
+    e64 = float(np.max(np.abs(G64 - Gt) / np.max(np.abs(Gt), axis=0)))
+    assert float(np.max(np.abs(G - Gt) / np.max(np.abs(Gt), axis=0))) <= max(20 * e64, 1e-13)
+
+
+def test_slices_are_an_exact_representation():
+    rng = np.random.default_rng(3)
+    v = np.concatenate([rng.standard_normal(1000) * 10.0 ** rng.integers(-12, 3, 1000), [0.0, -0.0, 1.0, -1.0, 4.0 - 2 ** -50]])
+    scale = float(_scale(np.abs(v).max()))
+    q = _slices(v, scale)
+    for s in q:
+        assert s.min() >= -128 and s.max() <= 127              # int8
+    t = sum(qj * (1 << (8 * (6 - j))) for j, qj in enumerate(q))
+    assert np.array_equal(t, np.trunc(v * (2.0 ** 54 / scale)).astype(np.int64))
+    assert np.max(np.abs(t.astype(np.float64) * (scale / 2.0 ** 54) - v)) <= scale * 2.0 ** -54
+
+
+def test_degenerate_tiles():
+    # a chain that reproduces Y exactly (zero adjoint: the scale falls back to 1) and rows of zeros (padding)
+    rng = np.random.default_rng(5)
+    N, M = 256, 8
+    X = np.round(rng.standard_normal((N, M)) * 8) / 8          # exactly representable products
+    b = np.round(rng.standard_normal(M) * 4) / 4
+    X[200:] = 0.0
+    Y = X @ b
+    B = np.column_stack([b, b + 0.5])
+    L, G = sliced_glm(X, Y, B)
+    Lt, Gt = _truth(X, Y, B)
+    assert L[0] == 0.0 and np.all(G[:, 0] == 0.0)
+    assert abs(L[1] - float(Lt[1])) <= 1e-13 * abs(float(Lt[1]))
+    assert np.max(np.abs(G[:, 1] - Gt[:, 1].astype(np.float64))) <= 1e-12 * float(np.max(np.abs(Gt[:, 1])))

@@ -973,6 +973,7 @@ void smc_glm_release(SmcGlmPlan& g, cudaStream_t st) {
   if (g.part) smc_dev_free(g.part, st);
   if (g.ybuf) smc_dev_free(g.ybuf, st);
   if (g.ZtZ) smc_dev_free(g.ZtZ, st);
+  smc_glm_i8_release(g, st);
   g.ZtZ = nullptr;
   g.ybuf = nullptr;
   g.Xrm = nullptr;
@@ -1018,6 +1019,9 @@ int smc_glm_launch(smc_model_s* m, SmcGlmPlan& g, int64_t C) {
   long long rows_per_split = ((g.N + RS - 1) / RS + RT - 1) / RT * RT;
   RS = (int)((g.N + rows_per_split - 1) / rows_per_split);
   if (stream) RS = (int)std::max<long long>(1, std::min<long long>((g.N + 255) / 256, 2LL * m->ctx->sm_count));
+  // opt-in (SMC_GLM_I8=1): the sliced-integer kernel on the int8 tensor cores, 32-chain tiles x 128-row tiles (glm_i8.cu)
+  const bool i8 = !stream && smc_glm_i8_usable(g, C);
+  if (i8) RS = row_splits_for(smc_glm_i8_chain_tiles(C), g.N, smc_glm_i8_row_tile(), m->ctx->sm_count);
   int64_t need = (int64_t)(RS + 1) * (g.MP + 1) * m->Cpad;
   if (need > g.part_cap) {
     m->graphs_stale = true;
@@ -1051,6 +1055,9 @@ int smc_glm_launch(smc_model_s* m, SmcGlmPlan& g, int64_t C) {
     rc = g.family == SMC_GLM_NORMAL      ? launch_stream<SMC_GLM_NORMAL>(sa, MB, CT, grid, st)
          : g.family == SMC_GLM_BERNOULLI ? launch_stream<SMC_GLM_BERNOULLI>(sa, MB, CT, grid, st)
                                          : launch_stream<SMC_GLM_BINOMIAL>(sa, MB, CT, grid, st);
+  } else if (i8) {
+    a.pub.on = 0;
+    rc = smc_glm_i8_launch(m, g, a.beta, C, m->Cpad, RS, a.part);
   } else {
     rc = g.family == SMC_GLM_NORMAL      ? launch_fam<SMC_GLM_NORMAL>(a, g.MP, tc, RS, st)
          : g.family == SMC_GLM_BERNOULLI ? launch_fam<SMC_GLM_BERNOULLI>(a, g.MP, tc, RS, st)

@@ -1,0 +1,446 @@
+// Sliced-integer evaluation of a Normal identity-link GLM statement on the int8 tensor cores (tcgen05.mma kind::i8, int32
+// accumulators in TMEM): the library form of tools/ozaki_glm_proto.cu (v5), DESIGN.md section 8.
+//
+// OPT-IN (SMC_GLM_I8=1) AND NOT YET RUN ON A DEVICE: the prototype it is derived from is measured and parity-checked
+// (profiles/ozaki_glm_proto_v5*_r01.jsonl: 28.7 ms per configs[1] evaluation against 32.2 ms for k_glm, logp 7e-16 /
+// gradient 2e-14 against long double), the plumbing below (slicing X at the first launch, sigma, the partial layout of
+// k_glm, models narrower than 64 columns, ragged row counts, non-finite chains) was written after the round's GPU minutes
+// were spent.  Nothing reaches this file unless the environment variable is set; the parity suite run with it set decides
+// whether it becomes the path for C >= 32.
+//
+// Arithmetic (exact integer products, one FP64 rounding per recombination): every operand is cut into seven balanced
+// 8-bit slices against a power-of-two scale -- X once with one global scale, beta per chain and evaluation, the adjoint
+// w per (128-row tile, chain); slice pairs (i, j) with i + j <= 6 are kept and pairs of equal i + j share an int32
+// accumulator.  One CTA = 32 chains x a range of 128-row tiles, 512 threads (4 per TMEM lane), 448 TMEM columns:
+//   product 1: A = X slice i (K-major), B = beta slices j <= 6 - i stacked along N, D at column offset 32 i;
+//   product 2: A = X slices (i, i+1) stacked along M, read MN-major from the same shared-memory tile, B = the stacked
+//              slices of the adjoint, D at column offset 256 + 32 i (lanes 64..127 hold the groups shifted by one).
+// Output: the partial block [row split][MP + 1][Cpad] of k_glm (rows 0..63 = X' dl/deta, row 64 = log-density), so the
+// fixed-order reduction, the publish step and the row-sharded all-reduce of glm_fused.cu apply unchanged.
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include "smc_internal.h"
+#include "dists.cuh"
+
+namespace {
+
+constexpr int NC = 32;        // chains per CTA
+constexpr int TR = 128;       // rows per tile
+constexpr int MP = 64;        // parameter slots
+constexpr int NS8 = 7;        // slices
+constexpr int NT = 512;       // threads per CTA
+constexpr int CQ = NC / (NT / 128);
+constexpr uint32_t XT_BYTES = TR * 8 * MP;         // one X tile: 8 slice slots (slot 7 = zeros)
+constexpr uint32_t QB_BYTES = 8 * NC * MP;
+constexpr uint32_t QD_BYTES = 8 * NC * TR;
+constexpr uint32_t SMEM_BYTES = 2 * XT_BYTES + QB_BYTES + QD_BYTES;
+constexpr unsigned long long H8 = 0x0080808080808080ull;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// shared-memory matrix descriptor, no swizzle: start address, LBO (steps along K), SBO (steps along M/N), version 1
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+// instruction descriptor for kind::i8: D = S32, A = B = signed 8 bit
+__device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+  return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n"
+               :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" :: "r"(smem_u32(bar)) : "memory");
+}
+// bounded wait (a wrong descriptor must end in an error, not in a hung device)
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  for (int it = 0; it < (1 << 20); it++) {
+    uint32_t done;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(done) : "r"(addr), "r"(parity), "r"(2000u) : "memory");
+    if (done) return true;
+  }
+  return false;
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" :: "r"(smem_u32(slot)), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, int32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_load_tile(uint8_t* dst, const int8_t* src, uint64_t* bar) {
+  const uint32_t b = smem_u32(bar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(b), "r"(65536u) : "memory");
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 :: "r"(smem_u32(dst + k * 16384)), "l"(src + k * 16384), "r"(16384u), "r"(b) : "memory");
+}
+
+// X tile image (shared memory = global): 128-byte core matrices [row group r>>3][slice slot i][parameter chunk p>>4]
+// [row r&7][parameter p&15]; product 1 reads slot i K-major (LBO 128, SBO 4096), product 2 reads slots (i, i+1) MN-major
+// (SBO 128, LBO 4096)
+__host__ __device__ inline uint32_t xoff(int r, int i, int p) {
+  return (uint32_t)(r >> 3) * 4096 + (uint32_t)i * 512 + (uint32_t)(p >> 4) * 128 + (uint32_t)(r & 7) * 16 + (uint32_t)(p & 15);
+}
+// stacked K-major B operands: row n = 32 j + chain, kbytes per row
+__device__ inline uint32_t boff(int n, int k, int kbytes) {
+  return (uint32_t)(n >> 3) * (uint32_t)(kbytes * 8) + (uint32_t)(k >> 4) * 128 + (uint32_t)(n & 7) * 16 + (uint32_t)(k & 15);
+}
+// slices of v against scale = 2^54 / f: byte k of the result = slice 6 - k as int8 (slice 0 = most significant)
+__device__ __forceinline__ unsigned long long slice7_word(double v, double f) {
+  long long t = (long long)(v * f);
+  return ((unsigned long long)t + H8) ^ H8;
+}
+__device__ __forceinline__ unsigned long long slice7_bits(double v, unsigned int Emax) {   // scale = 2^(Emax - 1022)
+  const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+  const unsigned int E = (unsigned int)(bits >> 52) & 0x7ffu;
+  const unsigned long long mant = (bits & 0xFFFFFFFFFFFFFull) | (1ull << 52);
+  const unsigned int sh = Emax - E;
+  const unsigned long long mag = (E == 0u || sh > 63u) ? 0ull : ((mant << 1) >> sh);
+  const unsigned long long t = (long long)bits < 0 ? (0ull - mag) : mag;
+  return (t + H8) ^ H8;
+}
+// power-of-two scale strictly above m, from m's exponent field; factor = 2^54 / scale
+__host__ __device__ inline void scale_of8(double m, double* scale, double* factor) {
+  unsigned long long bits;
+  memcpy(&bits, &m, 8);
+  unsigned long long E = (bits >> 52) & 0x7ff;
+  if (E < 64 || E > 1900) { *scale = 1.0; *factor = 18014398509481984.0; return; }
+  unsigned long long sb = (E + 1) << 52, fb = (2099 - E) << 52;
+  memcpy(scale, &sb, 8);
+  memcpy(factor, &fb, 8);
+}
+// sum_cb a[cb] 2^(-12 - 8 (cb + ii)) from seven exact int32 group sums (two int64 halves, one rounding)
+__device__ __forceinline__ double recombine7(const int32_t* a, int ii) {
+  long long hi = ((long long)a[0] << 24) + ((long long)a[1] << 16) + ((long long)a[2] << 8) + (long long)a[3];
+  long long lo = ((long long)a[4] << 16) + ((long long)a[5] << 8) + (long long)a[6];
+  return fma((double)hi, ii ? 0x1p-44 : 0x1p-36, (double)lo * (ii ? 0x1p-68 : 0x1p-60));
+}
+
+// max |X| over the row-major padded copy (bits of a non-negative double order like the unsigned integer)
+__global__ void k_absmax(const double* __restrict__ X, long long n, unsigned long long* out) {
+  unsigned long long m = 0ull;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    double a = fabs(X[i]);
+    if (!(a <= 1.7976931348623157e308)) a = INFINITY;      // NaN / Inf: reported as Inf
+    unsigned long long b = (unsigned long long)__double_as_longlong(a);
+    m = b > m ? b : m;
+  }
+  for (int o = 16; o > 0; o >>= 1) { unsigned long long v = __shfl_xor_sync(0xffffffffu, m, o); m = v > m ? v : m; }
+  if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+}
+
+// X (row major [N][64], zero padded columns) -> slice tiles; rows beyond N are zeros
+__global__ void k_slice_x8(const double* __restrict__ X, int8_t* __restrict__ QX, long long N, long long prow, double factor) {
+  long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= prow * MP) return;
+  long long row = e / MP;
+  int p = (int)(e % MP), r = (int)(row % TR);
+  const unsigned long long w = slice7_word(row < N ? X[e] : 0.0, factor);
+  int8_t* tile = QX + (row / TR) * (long long)XT_BYTES;
+#pragma unroll
+  for (int i = 0; i < NS8; i++) tile[xoff(r, i, p)] = (int8_t)(w >> (8 * (6 - i)));
+  tile[xoff(r, 7, p)] = 0;
+}
+
+struct GlmI8Args {
+  const int8_t* QX;     // [tiles][XT_BYTES]
+  const double* y;      // [N] response as the Normal family consumes it (w = eta - y)
+  const double* beta;   // [M][Cpad]
+  double* part;         // [splits][MP + 1][Cpad]
+  int* status;          // set when a tensor-core completion never arrived
+  long long N, tiles, C, Cpad;
+  int M, splits;
+  double sx;            // scale of X
+  double sigma;
+};
+
+__global__ void __launch_bounds__(NT, 1) k_glm_i8(GlmI8Args a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar1, bar2, barX[2];
+  __shared__ uint32_t tmem_slot;
+  __shared__ double s_sb[NC], s_f[NC];
+  __shared__ unsigned int s_max[2][NC];
+  __shared__ int s_badc[NC];
+  uint8_t* sX = smem;
+  uint8_t* sQB = smem + 2 * XT_BYTES;
+  uint8_t* sQD = sQB + QB_BYTES;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, rl = tid & 127, q = tid >> 7;
+  const long long c0 = (long long)blockIdx.x * NC;
+  const long long t_begin = a.tiles * blockIdx.y / a.splits, t_end = a.tiles * (blockIdx.y + 1) / a.splits;
+
+  if (warp == 0) tmem_alloc(&tmem_slot, 512);
+  if (tid == 32) { mbar_init(&bar1, 1); mbar_init(&bar2, 1); mbar_init(&barX[0], 1); mbar_init(&barX[1], 1); }
+  if (tid < NC) {
+    double m = 0.0;
+    int bad = 0;
+    for (int p = 0; p < a.M; p++) {
+      const double b = fabs(a.beta[(long long)p * a.Cpad + c0 + tid]);
+      if (!(b <= 1.7976931348623157e308)) bad = 1;         // NaN / Inf parameters: the chain is out of support
+      else m = fmax(m, b);
+    }
+    double sc, f;
+    scale_of8(m, &sc, &f);
+    s_sb[tid] = a.sx * sc;
+    s_f[tid] = f;
+    s_badc[tid] = bad;
+    s_max[0][tid] = 0u;
+    s_max[1][tid] = 0u;
+  }
+  __syncthreads();
+  for (int e = tid; e < NC * MP; e += NT) {
+    const int c = e & (NC - 1), p = e / NC;
+    double b = p < a.M ? a.beta[(long long)p * a.Cpad + c0 + c] : 0.0;
+    if (s_badc[c]) b = 0.0;
+    const unsigned long long w = slice7_word(b, s_f[c]);
+    for (int j = 0; j < NS8; j++) sQB[boff(j * NC + c, p, MP)] = (uint8_t)(w >> (8 * (6 - j)));
+  }
+  fence_async_smem();
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+  const uint32_t qbs = smem_u32(sQB), qds = smem_u32(sQD), xs0 = smem_u32(sX);
+  const int ii = rl >> 6;
+  double gacc[CQ], lacc[CQ], d[CQ];
+#pragma unroll
+  for (int c = 0; c < CQ; c++) { gacc[c] = 0.0; lacc[c] = 0.0; d[c] = 0.0; }
+  bool ok = true;
+
+  auto issue_p1 = [&](uint32_t xs) {
+#pragma unroll 1
+    for (int i = 0; i < NS8; i++) {
+      const uint32_t idesc = make_idesc(TR, NC * (NS8 - i), 0, 0);
+      for (int ks = 0; ks < MP / 32; ks++)
+        mma_i8(tmem + (uint32_t)(i * NC), make_desc(xs + i * 512 + ks * 256, 128, 4096),
+               make_desc(qbs + ks * 256, 128, MP * 8), idesc, (i | ks) != 0);
+    }
+    umma_commit(&bar1);
+  };
+  // epilogue 1 of tile t (its product 1 is the k-th completion of bar1): eta, w = eta - y (registers), sum w^2, max |w|
+  auto epilogue1 = [&](long long t, long long k) -> bool {
+    const long long row = t * TR + rl;
+    const double yr = row < a.N ? a.y[row] : 0.0;
+    if (!mbar_wait(&bar1, (uint32_t)(k & 1))) return false;
+    fence_after();
+    const int st = (int)(k & 1);
+    int32_t acc[NS8][8];
+#pragma unroll
+    for (int cb = 0; cb < NS8; cb++) tmem_ld8_nowait(tmem + lane_base + (uint32_t)(cb * NC + q * CQ), acc[cb]);
+    tmem_ld_wait();
+    unsigned int hw[CQ];
+#pragma unroll
+    for (int u = 0; u < CQ; u++) {
+      int32_t g[NS8];
+#pragma unroll
+      for (int cb = 0; cb < NS8; cb++) g[cb] = acc[cb][u];
+      const double w = recombine7(g, 0) * s_sb[q * CQ + u] - yr;
+      d[u] = w;
+      lacc[u] = fma(w, w, lacc[u]);
+      hw[u] = (unsigned int)__double2hiint(fabs(w));
+    }
+#pragma unroll
+    for (int u = 0; u < CQ; u++) hw[u] = __reduce_max_sync(0xffffffffu, hw[u]);
+    if (lane == 0) {
+#pragma unroll
+      for (int u = 0; u < CQ; u++) atomicMax(&s_max[st][q * CQ + u], hw[u]);
+    }
+    return true;
+  };
+  if (tid == 0 && t_begin < t_end) {
+    bulk_load_tile(sX, a.QX + t_begin * (long long)XT_BYTES, &barX[0]);
+    if (t_begin + 1 < t_end) bulk_load_tile(sX + XT_BYTES, a.QX + (t_begin + 1) * (long long)XT_BYTES, &barX[1]);
+    if (!mbar_wait(&barX[0], 0)) *a.status = 2;
+    fence_after();
+    issue_p1(xs0);
+  }
+  if (t_begin < t_end) ok = epilogue1(t_begin, 0);
+
+  for (long long t = t_begin; t < t_end && ok; t++) {
+    const long long k = t - t_begin;
+    const int stage = (int)(k & 1);
+    fence_before();
+    __syncthreads();                                      // (A) maxima of tile t complete; accumulator set 1 has been read
+    if (tid == 0 && t + 1 < t_end) {                      // product 1 of tile t+1 runs under the slicing of tile t
+      if (!mbar_wait(&barX[stage ^ 1], (uint32_t)(((k + 1) >> 1) & 1))) *a.status = 2;
+      fence_after();
+      issue_p1(xs0 + (uint32_t)(stage ^ 1) * XT_BYTES);
+    }
+    if (tid >= NT - NC) s_max[stage ^ 1][tid - (NT - NC)] = 0u;
+#pragma unroll
+    for (int c = 0; c < CQ; c++) {
+      unsigned int E = (s_max[stage][q * CQ + c] >> 20) & 0x7ffu;
+      if (E < 64u || E > 1900u) E = 1022u;
+      const unsigned long long w = slice7_bits(d[c], E);
+      const uint32_t wl = (uint32_t)w, wh = (uint32_t)(w >> 32);
+      uint8_t* dst = sQD + boff(q * CQ + c, rl, TR);      // slice j at + j * NC rows
+      dst[0 * NC * TR] = (uint8_t)(wh >> 16);
+      dst[1 * NC * TR] = (uint8_t)(wh >> 8);
+      dst[2 * NC * TR] = (uint8_t)wh;
+      dst[3 * NC * TR] = (uint8_t)(wl >> 24);
+      dst[4 * NC * TR] = (uint8_t)(wl >> 16);
+      dst[5 * NC * TR] = (uint8_t)(wl >> 8);
+      dst[6 * NC * TR] = (uint8_t)wl;
+    }
+    fence_async_smem();
+    fence_before();
+    __syncthreads();                                      // (B) adjoint slices visible; accumulator set 2 free
+    if (tid == 0) {
+      fence_after();
+      const uint32_t xs = xs0 + (uint32_t)stage * XT_BYTES;
+#pragma unroll 1
+      for (int i = 0; i < NS8; i += 2) {
+        const uint32_t idesc = make_idesc(128, NC * (NS8 - i), 1, 0);
+        for (int ks = 0; ks < TR / 32; ks++)
+          mma_i8(tmem + 256u + (uint32_t)(i * NC), make_desc(xs + i * 512 + ks * 16384, 4096, 128),
+                 make_desc(qds + ks * 256, 128, TR * 8), idesc, (i | ks) != 0);
+      }
+      umma_commit(&bar2);
+    }
+    if (t + 1 < t_end) ok = epilogue1(t + 1, k + 1);      // under product 2 of tile t
+    if (!mbar_wait(&bar2, (uint32_t)(k & 1))) ok = false;
+    fence_after();
+    if (!ok) break;
+    if (tid == 0 && t + 2 < t_end)
+      bulk_load_tile(sX + (size_t)stage * XT_BYTES, a.QX + (t + 2) * (long long)XT_BYTES, &barX[stage]);
+    // ---- epilogue 2 of tile t: thread = ((ii, parameter), chain group) ----
+    int32_t acc[NS8][8];
+#pragma unroll
+    for (int cb = 0; cb < NS8; cb++) tmem_ld8_nowait(tmem + lane_base + 256u + (uint32_t)(cb * NC + q * CQ), acc[cb]);
+    tmem_ld_wait();
+#pragma unroll
+    for (int u = 0; u < CQ; u++) {
+      int32_t g[NS8];
+#pragma unroll
+      for (int cb = 0; cb < NS8; cb++) g[cb] = acc[cb][u];
+      const unsigned int E = (s_max[stage][q * CQ + u] >> 20) & 0x7ffu;    // zeroed only after barrier (A) of tile t+1
+      double sc = 1.0;
+      if (E >= 64u && E <= 1900u) sc = __longlong_as_double((long long)((unsigned long long)(E + 1u) << 52));
+      gacc[u] = fma(recombine7(g, ii), a.sx * sc, gacc[u]);
+    }
+  }
+  if (!ok && rl == 0) *a.status = 1;
+  // ---- partial block of this row split, in k_glm's layout and conventions:
+  //      rows 0..63: X' dl/deta = -(X' w) / sigma^2;  row 64: -sum (w / sigma)^2 / 2 - n (log sigma + log sqrt(2 pi))
+  fence_before();
+  __syncthreads();
+  double* sG = (double*)sQD;                              // [chain][64]
+  double* sL = (double*)sX;                               // [chain][128]
+  if (ii == 1) {
+#pragma unroll
+    for (int c = 0; c < CQ; c++) sG[(q * CQ + c) * MP + (rl & 63)] = gacc[c];
+  }
+#pragma unroll
+  for (int c = 0; c < CQ; c++) sL[(q * CQ + c) * TR + rl] = lacc[c];
+  __syncthreads();
+  if (ii == 0) {
+#pragma unroll
+    for (int c = 0; c < CQ; c++) sG[(q * CQ + c) * MP + rl] += gacc[c];
+  }
+  const double neg_inv_s2 = -1.0 / (a.sigma * a.sigma);
+  const long long r_begin = t_begin * TR, r_end = t_end * TR < a.N ? t_end * TR : a.N;
+  const double nrows = (double)(r_end > r_begin ? r_end - r_begin : 0);
+  const double lconst = nrows * (-log(a.sigma) - SMC_LOG_SQRT_2PI);
+  double* part = a.part + (long long)blockIdx.y * (MP + 1) * a.Cpad;
+  for (int c = warp; c < NC; c += NT / 32) {              // fixed-order sum over the 128 rows
+    double ssum = 0.0;
+#pragma unroll
+    for (int kk = 0; kk < TR / 32; kk++) ssum += sL[c * TR + kk * 32 + lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
+    if (lane == 0 && c0 + c < a.Cpad) {
+      double L = 0.5 * neg_inv_s2 * ssum + lconst;
+      if (s_badc[c]) L = -INFINITY;                       // the reduction flags the chain (glm_emit)
+      part[(long long)MP * a.Cpad + c0 + c] = L;
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < NC * MP; e += NT) {
+    const int c = e & (NC - 1), p = e / NC;
+    if (c0 + c < a.Cpad) part[(long long)p * a.Cpad + c0 + c] = neg_inv_s2 * sG[c * MP + p];
+  }
+  fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+}  // namespace
+
+// the opt-in switch and the shapes the kernel is written for
+bool smc_glm_i8_usable(const SmcGlmPlan& g, int64_t C) {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("SMC_GLM_I8"); on = (e && e[0] == '1') ? 1 : 0; }
+  return on && g.family == SMC_GLM_NORMAL && g.MP == MP && C >= NC && g.N >= 4LL * TR && g.par > 0.0;
+}
+
+int smc_glm_i8_chain_tiles(int64_t C) { return (int)((C + NC - 1) / NC); }
+int smc_glm_i8_row_tile() { return TR; }
+
+void smc_glm_i8_release(SmcGlmPlan& g, cudaStream_t st) {
+  if (g.QX8) smc_dev_free(g.QX8, st);
+  if (g.i8_status) smc_dev_free(g.i8_status, st);
+  g.QX8 = nullptr;
+  g.i8_status = nullptr;
+}
+
+// part: [RS][MP + 1][Cpad]; beta: [M][Cpad].  The first call (always outside a stream capture: the first evaluation of a
+// model is eager) slices X.
+int smc_glm_i8_launch(smc_model_s* m, SmcGlmPlan& g, const double* beta, int64_t C, int64_t Cpad, int RS, double* part) {
+  cudaStream_t st = m->ctx->stream;
+  const long long tiles = (g.N + TR - 1) / TR;
+  if (!g.QX8) {
+    unsigned long long* dmax = nullptr;
+    SMC_CUDA(smc_dev_alloc(&dmax, sizeof(unsigned long long), st));
+    SMC_CUDA(cudaMemsetAsync(dmax, 0, sizeof(unsigned long long), st));
+    k_absmax<<<(unsigned)std::min<long long>((g.N * g.MP + 255) / 256, 148LL * 16), 256, 0, st>>>(g.Xrm, g.N * g.MP, dmax);
+    unsigned long long hbits = 0;
+    SMC_CUDA(smc_copy_sync(&hbits, dmax, sizeof(hbits), cudaMemcpyDeviceToHost, st));
+    smc_dev_free(dmax, st);
+    double xmax;
+    memcpy(&xmax, &hbits, 8);
+    if (!(xmax <= 1.7976931348623157e308)) { smc_set_error("GLM (int8 path): X holds NaN or Inf"); return SMC_ERR_INVALID; }
+    double fx;
+    scale_of8(xmax, &g.sx8, &fx);
+    SMC_CUDA(smc_dev_alloc(&g.QX8, (size_t)tiles * XT_BYTES, st));
+    SMC_CUDA(smc_dev_alloc(&g.i8_status, sizeof(int), st));
+    SMC_CUDA(cudaMemsetAsync(g.i8_status, 0, sizeof(int), st));
+    const long long prow = tiles * TR;
+    k_slice_x8<<<(unsigned)((prow * MP + 255) / 256), 256, 0, st>>>(g.Xrm, g.QX8, g.N, prow, fx);
+    m->ctx->launches += 2;
+    static SmcOncePerDevice once;
+    if (once.first()) SMC_CUDA(cudaFuncSetAttribute(k_glm_i8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  }
+  GlmI8Args a;
+  a.QX = g.QX8; a.y = g.y; a.beta = beta; a.part = part; a.status = g.i8_status;
+  a.N = g.N; a.tiles = tiles; a.C = C; a.Cpad = Cpad; a.M = g.M; a.splits = RS; a.sx = g.sx8; a.sigma = g.par;
+  dim3 grid((unsigned)smc_glm_i8_chain_tiles(C), (unsigned)RS);
+  k_glm_i8<<<grid, NT, SMEM_BYTES, st>>>(a);
+  if (!g.i8_checked) {      // first (eager) launch: a tensor-core completion that never arrived is an error, not a wrong number
+    g.i8_checked = 1;
+    int status = 0;
+    SMC_CUDA(smc_copy_sync(&status, g.i8_status, sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (status != 0) { smc_set_error("GLM (int8 path): tensor-core pipeline timed out (status %d)", status); return SMC_ERR_CUDA; }
+  }
+  return SMC_OK;
+}

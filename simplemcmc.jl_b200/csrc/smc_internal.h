@@ -93,6 +93,11 @@ struct SmcGlmPlan {  // one SMC_OP_GLM statement, prepared at finalize
   double lc_sum = 0.0;     // BINOMIAL: sum_i lchoose(n, y_i) over the local rows
   int gram = 0;            // SMC_GLM_F_GRAM: evaluate from Z'Z with Z = [X, ytilde]
   double* ZtZ = nullptr;   // [(M+1)][(M+1)] row major
+  // opt-in int8 tensor-core path (glm_i8.cu, SMC_GLM_I8=1): X as seven balanced 8-bit slices in 128-row tiles
+  int8_t* QX8 = nullptr;
+  double sx8 = 0.0;        // power-of-two scale of X
+  int* i8_status = nullptr;
+  int i8_checked = 0;
 };
 
 // Micro-operation of the register-program VM (vm_exec.cu): the tape's LOADV/LOADS/STOREV/REDUCE instructions are
@@ -211,3 +216,10 @@ int smc_vm_launch(smc_model_s* m, SmcProgram& pr, int64_t C, int* bad);
 int smc_glm_prepare(smc_model_s* m, SmcGlmPlan& g);
 int smc_glm_launch(smc_model_s* m, SmcGlmPlan& g, int64_t C);
 void smc_glm_release(SmcGlmPlan& g, cudaStream_t st);
+
+// glm_i8.cu (opt-in, SMC_GLM_I8=1)
+bool smc_glm_i8_usable(const SmcGlmPlan& g, int64_t C);
+int smc_glm_i8_chain_tiles(int64_t C);
+int smc_glm_i8_row_tile();
+int smc_glm_i8_launch(smc_model_s* m, SmcGlmPlan& g, const double* beta, int64_t C, int64_t Cpad, int RS, double* part);
+void smc_glm_i8_release(SmcGlmPlan& g, cudaStream_t st);

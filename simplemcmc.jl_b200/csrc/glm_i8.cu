@@ -1,12 +1,14 @@
 // Sliced-integer evaluation of a Normal identity-link GLM statement on the int8 tensor cores (tcgen05.mma kind::i8, int32
 // accumulators in TMEM): the library form of tools/ozaki_glm_proto.cu (v5), DESIGN.md section 8.
 //
-// OPT-IN (SMC_GLM_I8=1) AND NOT YET RUN ON A DEVICE: the prototype it is derived from is measured and parity-checked
+// OPT-IN (SMC_GLM_I8=1), ONE DEVICE RUN SO FAR: the prototype it is derived from is measured and parity-checked
 // (profiles/ozaki_glm_proto_v5*_r01.jsonl: 28.7 ms per configs[1] evaluation against 32.2 ms for k_glm, logp 7e-16 /
-// gradient 2e-14 against long double), the plumbing below (slicing X at the first launch, sigma, the partial layout of
-// k_glm, models narrower than 64 columns, ragged row counts, non-finite chains) was written after the round's GPU minutes
-// were spent.  Nothing reaches this file unless the environment variable is set; the parity suite run with it set decides
-// whether it becomes the path for C >= 32.
+// gradient 2e-14 against long double).  The plumbing below (slicing X at the first launch, sigma, the partial layout of
+// k_glm, models narrower than 64 columns, ragged row counts, non-finite chains) was written when the round's GPU minutes
+// were nearly spent; the last seconds went into tools/i8_quick.py with the switch set (N = 3000, M = 50, 70 chains,
+// sigma = 1.5, prior included: logp 4e-16, gradient 1.9e-14 against long double, profiles/glm_i8_library_quick_r01.json).
+// No launch list, no timing and no run of the parity suite yet: nothing reaches this file unless the environment variable
+// is set, and the suite run with it set (tests/test_gpu_zz_i8_optin.py) decides whether it becomes the path for C >= 32.
 //
 // Arithmetic (exact integer products, one FP64 rounding per recombination): every operand is cut into seven balanced
 // 8-bit slices against a power-of-two scale -- X once with one global scale, beta per chain and evaluation, the adjoint

@@ -172,6 +172,24 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def int8_extra(K, W):
+    import subprocess
+    note = ("opt-in SMC_GLM_I8=1: Normal GLM statement from seven balanced 8-bit slices per operand on tcgen05.mma kind::i8 "
+            "(int32 accumulators in TMEM); same statement list and the same 1e-12 parity bar as the headline, reported beside it "
+            "until the parity suite has run with the switch set")
+    try:
+        out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "i8_bench_extra.py"), str(K), str(W)],
+                             capture_output=True, text=True, timeout=300, env=dict(os.environ, SMC_GLM_I8="1"))
+        lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+        if out.returncode != 0 or not lines:
+            return {"error": (out.stderr or out.stdout)[-400:], "note": note}
+        res = json.loads(lines[-1])
+        res["note"] = note
+        return res
+    except Exception as e:      # the extra must never take the benchmark line down
+        return {"error": str(e)[:400], "note": note}
+
+
 def run_ours(args):
     # stdout carries exactly one line (the JSON record): anything libraries print while the benchmark runs -- e.g. the
     # "NCCL version ..." banner of the first communicator -- is sent to stderr at file-descriptor level
@@ -306,6 +324,12 @@ def _run_ours(args):
            "d2h_bytes_per_step": d2h / K, "wall_s": walls[mid], "wall_s_all_calls": walls,
            "what": "one simpleHMC(model, steps=K, chains=4096, ...) call per rank with host (pinned) X, Y: lowering, tape compile, "
                    "H2D bind, K steps, D2H of all draws; wall clock (max over ranks), best of 3 calls (all in wall_s_all_calls)"}
+
+    # ---------------- labelled extra (NOT the headline): the same model with the library's opt-in int8 tensor-core GLM path
+    # (csrc/glm_i8.cu), in a child process because SMC_GLM_I8 is read once per process; it runs after
+    # every measurement above is complete and cannot change them
+    if rank == 0 and world == 1:
+        extra["int8_tensor_core_glm_path"] = int8_extra(K, W)
 
     if rank == 0:
         cpu, _ = cpu_baseline(X, Y, mode, 24)

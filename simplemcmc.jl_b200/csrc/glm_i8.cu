@@ -8,7 +8,7 @@
 // were nearly spent; the last seconds went into tools/i8_quick.py with the switch set (N = 3000, M = 50, 70 chains,
 // sigma = 1.5, prior included: logp 4e-16, gradient 1.9e-14 against long double, profiles/glm_i8_library_quick_r01.json).
 // No launch list, no timing and no run of the parity suite yet: nothing reaches this file unless the environment variable
-// is set, and the suite run with it set (tests/test_gpu_zz_i8_optin.py) decides whether it becomes the path for C >= 32.
+// is set, and the suite run with it set (tests/test_zz_gpu_i8_optin.py) decides whether it becomes the path for C >= 32.
 //
 // Arithmetic (exact integer products, one FP64 rounding per recombination): every operand is cut into seven balanced
 // 8-bit slices against a power-of-two scale -- X once with one global scale, beta per chain and evaluation, the adjoint

@@ -4,7 +4,7 @@ accumulated per group i + j in (emulated) int32, the stacked two-slice arrangeme
 holds the groups shifted by one, recombination from two int64 halves, a power-of-two scale per (128-row tile, chain) for
 the adjoint -- restated in NumPy and compared with 80-bit long double on configs[1]-shaped data.  The bar is the parity
 bar of the GPU suite: 1e-12 relative to max |.| per chain.  No GPU, no oracle: this pins the algorithm, the GPU test
-`test_gpu_zz_prototype.py` pins the kernel."""
+`test_zz_gpu_prototype.py` pins the kernel."""
 import numpy as np
 import pytest
 

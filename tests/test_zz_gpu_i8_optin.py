@@ -1,7 +1,7 @@
 """Opt-in parity test of the int8 tensor-core GLM path of the library (csrc/glm_i8.cu).  That path has had a
 single device run so far (tools/i8_quick.py, profiles/glm_i8_library_quick_r01.json), so it is excluded from the default GPU suite:
-    SMC_TEST_I8=1 python -m pytest tests/test_gpu_zz_i8_optin.py -m gpu
-The prototype kernel it derives from is covered by test_gpu_zz_prototype.py."""
+    SMC_TEST_I8=1 python -m pytest tests/test_zz_gpu_i8_optin.py -m gpu
+The prototype kernel it derives from is covered by test_zz_gpu_prototype.py."""
 import json
 import os
 import subprocess

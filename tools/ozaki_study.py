@@ -85,4 +85,42 @@ for S in (6, 7, 8):
         G_s += g * sx * sd[None, :]
     res["S=%d" % S] = {"slice_pairs": npairs, "eta": rel(eta_s, eta_t), "logp": float(np.max(np.abs((L_s - L_t) / L_t))),
                        "grad": rel(G_s, G_t)}
+
+
+# ---- the scheme the device kernels ended up with (tools/ozaki_glm_proto.cu v4/v5, csrc/glm_i8.cu): seven BALANCED 8-bit
+# slices (digits in [-128, 127] of trunc(v 2^54 / scale) + 0x80...80), pairs with i + j <= 6 (0-based): 28 int8 GEMMs
+H8 = sum(128 << (8 * k) for k in range(7))
+
+
+def slices8(A, scale):
+    t = np.trunc(A * (2.0 ** 54 / scale)).astype(np.int64)
+    u = (t + H8).astype(np.uint64)
+    return [((u >> np.uint64(8 * (6 - j))) & np.uint64(255)).astype(np.int64) - 128 for j in range(7)]
+
+
+def sliced_matmul8(QA, QB):
+    groups = {}
+    for i, qa in enumerate(QA):
+        for j, qb in enumerate(QB):
+            if i + j <= 6:
+                groups[i + j] = groups.get(i + j, 0) + qa @ qb
+    acc = 0.0
+    for g in sorted(groups, reverse=True):
+        acc = acc + groups[g].astype(np.float64) * 2.0 ** (-12 - 8 * g)
+    return acc
+
+
+QX8 = slices8(X, sx)
+sb = pow2_above(np.max(np.abs(B), axis=0))
+eta_8 = sliced_matmul8(QX8, slices8(B, sb[None, :])) * sx * sb[None, :]
+d_8 = Y[:, None] - eta_8
+L_8 = -0.5 * np.sum(d_8 * d_8, axis=0)
+G_8 = np.zeros((M, C))
+QXT8 = [q.T for q in QX8]
+for r0 in range(0, N, TILE):
+    dt = d_8[r0:r0 + TILE]
+    sd = pow2_above(np.max(np.abs(dt), axis=0))
+    G_8 += sliced_matmul8([q[:, r0:r0 + TILE] for q in QXT8], slices8(dt, sd[None, :])) * sx * sd[None, :]
+res["7 balanced 8-bit slices"] = {"slice_pairs": 28, "eta": rel(eta_8, eta_t), "logp": float(np.max(np.abs((L_8 - L_t) / L_t))),
+                                  "grad": rel(G_8, G_t)}
 print(json.dumps(res, indent=1))

@@ -119,3 +119,26 @@ def test_degenerate_tiles():
     assert L[0] == 0.0 and np.all(G[:, 0] == 0.0)
     assert abs(L[1] - float(Lt[1])) <= 1e-13 * abs(float(Lt[1]))
     assert np.max(np.abs(G[:, 1] - Gt[:, 1].astype(np.float64))) <= 1e-12 * float(np.max(np.abs(Gt[:, 1])))
+
+
+def test_magic_number_slicing():
+    """slice7_magic of the prototype's v7: t = rint(v 2^54 / scale) from two magic-number roundings (low words of
+    x + 1.5 2^52), as IEEE double arithmetic in NumPy; equal to the direct rounding, |t| <= 2^54, so t + H8 fits 56 bits"""
+    magic = np.float64(6755399441055744.0)
+
+    def lo32(a):
+        return (a.view(np.uint64) & np.uint64(0xFFFFFFFF)).astype(np.uint32).view(np.int32).astype(np.int64)
+
+    rng = np.random.default_rng(0)
+    for trial in range(40):
+        v = rng.standard_normal(4000) * 10.0 ** rng.integers(-8, 3)
+        v[:5] = [0.0, -0.0, 1e-300, -1e-300, v[5] * 1e-20]
+        emax = max(int(np.frexp(np.abs(v).max())[1]) + 1022, 64)          # biased exponent of the maximum, clamped as in the kernel
+        f, f27 = np.ldexp(1.0, 54 - (emax - 1022)), np.ldexp(1.0, 27 - (emax - 1022))
+        a = v * f27 + magic                       # the product is exact (power of two), so this is the fused multiply-add
+        h = lo32(a)
+        r = v * f - (a - magic) * np.ldexp(1.0, 27)
+        t = h * (1 << 27) + lo32(r + magic)
+        assert np.array_equal(t, np.rint(v * f).astype(np.int64))
+        assert np.abs(t).max() <= (1 << 54)
+        assert np.all((t + H8) >= 0) and np.all((t + H8) < (1 << 56))

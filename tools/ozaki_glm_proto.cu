@@ -1256,6 +1256,225 @@ k_ozaki_glm_v6(const int8_t* __restrict__ QX, const double* __restrict__ y, cons
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+// ---- v7 (NOT YET RUN) = v6 with the adjoint sliced by two magic-number roundings instead of bit manipulation ------------
+// t = rint(v 2^54 / scale) is assembled from h = rint(v f 2^-27) and l = rint(v f - h 2^27), each read from the low word of
+// (x + 1.5 2^52): five FP64 instructions (the FP64 pipe is 7 % busy in v5) and about ten integer ones replace the roughly
+// thirty of slice7_bits (exponent extraction, 64-bit funnel shifts, clamps, conditional negation).  The algorithm is
+// checked on the CPU (tests/test_ozaki_numerics.py::test_magic_number_slicing).  The exponent of a tile's maximum is
+// clamped to >= 64 so that the factors stay finite for an all-zero tile.
+__device__ __forceinline__ unsigned long long slice7_magic(double v, unsigned int Emax) {   // scale = 2^(Emax - 1022)
+  const double f = __hiloint2double((int)((2099u - Emax) << 20), 0);          // 2^54 / scale
+  const double f27 = __hiloint2double((int)((2072u - Emax) << 20), 0);        // 2^27 / scale
+  const double a = fma(v, f27, 6755399441055744.0);
+  const int h = __double2loint(a);
+  const double hd = a - 6755399441055744.0;
+  const double r = fma(hd, -134217728.0, v * f);                              // exact
+  const int l = __double2loint(r + 6755399441055744.0);
+  const long long t = (long long)h * 134217728ll + (long long)l;
+  return ((unsigned long long)t + H8) ^ H8;
+}
+template <int NT, bool DBG>
+__global__ void __launch_bounds__(NT, 1)
+k_ozaki_glm_v7(const int8_t* __restrict__ QX, const double* __restrict__ y, const double* __restrict__ beta, int ldc,
+               long long tiles, int splits, double sx, double* __restrict__ outL, double* __restrict__ outG, int* status,
+               double* __restrict__ dbg_eta) {
+  constexpr int Q = NT / 128, CQ = NC / Q, NW = NT / 32;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar1, bar2, barX[2];
+  __shared__ uint32_t tmem_slot;
+  __shared__ double s_sb[NC], s_f[NC];
+  __shared__ unsigned int s_max[2][NC];
+  uint8_t* sX = smem;
+  uint8_t* sQB = smem + 2 * XT_BYTES;
+  uint8_t* sQD = sQB + QB_BYTES;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, rl = tid & 127, q = tid >> 7;
+  const int c0 = blockIdx.x * NC;
+  const long long t_begin = tiles * blockIdx.y / splits, t_end = tiles * (blockIdx.y + 1) / splits;
+
+  if (warp == 0) tmem_alloc(&tmem_slot, 512);
+  if (tid == 32) { mbar_init(&bar1, 1); mbar_init(&bar2, 1); mbar_init(&barX[0], 1); mbar_init(&barX[1], 1); }
+  if (tid < NC) {
+    double m = 0.0;
+    for (int p = 0; p < MP; p++) m = fmax(m, fabs(beta[(size_t)p * ldc + c0 + tid]));
+    double sc, f; unsigned int em;
+    scale_of8(m, &sc, &f, &em);
+    s_sb[tid] = sx * sc;                                  // scale of eta
+    s_f[tid] = f;
+    s_max[0][tid] = 0u;
+    s_max[1][tid] = 0u;
+  }
+  __syncthreads();
+  for (int e = tid; e < NC * MP; e += NT) {
+    int c = e & (NC - 1), p = e / NC;
+    const unsigned long long w = slice7_word(beta[(size_t)p * ldc + c0 + c], s_f[c]);
+    for (int j = 0; j < NS8; j++) sQB[boff(j * NC + c, p, MP)] = (uint8_t)(w >> (8 * (6 - j)));
+  }
+  fence_async_smem();
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+  const uint32_t qbs = smem_u32(sQB), qds = smem_u32(sQD), xs0 = smem_u32(sX);
+  const int ii = rl >> 6;
+  // exponent field of sx * 2^(E - 1022) = E + 1 + (field(sx) - 1023)
+  const unsigned int sx_exp = (((unsigned int)__double2hiint(sx) >> 20) & 0x7ffu) + 1u - 1023u;
+  double gacc[CQ], lacc[CQ], d[CQ];
+#pragma unroll
+  for (int c = 0; c < CQ; c++) { gacc[c] = 0.0; lacc[c] = 0.0; d[c] = 0.0; }
+  bool ok = true;
+
+  auto issue_p1 = [&](uint32_t xs) {
+#pragma unroll 1
+    for (int i = 0; i < NS8; i++) {
+      const uint32_t idesc = make_idesc(TR, NC * (NS8 - i), 0, 0);
+      for (int ks = 0; ks < MP / 32; ks++)
+        mma_i8(tmem + (uint32_t)(i * NC), make_desc(xs + i * 512 + ks * 256, 128, 4096),
+               make_desc(qbs + ks * 256, 128, MP * 8), idesc, (i | ks) != 0);
+    }
+    umma_commit(&bar1);
+  };
+  // epilogue 1 of tile t (its product 1 is the k-th completion of bar1): eta, d -> registers, sum d^2, max |d|
+  auto epilogue1 = [&](long long t, long long k) -> bool {
+    const double yr = y[t * TR + rl];
+    if (!mbar_wait(&bar1, (uint32_t)(k & 1), 4000000000ll)) return false;
+    fence_after();
+    const int st = (int)(k & 1);
+#pragma unroll
+    for (int cc = 0; cc < CQ; cc += 8) {
+      int32_t a[NS8][8];
+#pragma unroll
+      for (int cb = 0; cb < NS8; cb++) tmem_ld8_nowait(tmem + lane_base + (uint32_t)(cb * NC + q * CQ + cc), a[cb]);
+      tmem_ld_wait();
+      // straight-line code for the eight values (no side effects in between, so the compiler can interleave the chains)
+      unsigned int hw[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        int32_t g[NS8];
+#pragma unroll
+        for (int cb = 0; cb < NS8; cb++) g[cb] = a[cb][u];
+        const double eta = recombine7(g, 0) * s_sb[q * CQ + cc + u];
+        if (DBG) { if (blockIdx.y == 0 && t == t_begin) dbg_eta[(size_t)rl * ldc + c0 + q * CQ + cc + u] = eta; }
+        const double dd = yr - eta;
+        d[cc + u] = dd;
+        lacc[cc + u] = fma(dd, dd, lacc[cc + u]);
+        hw[u] = ((unsigned int)__double2hiint(dd) >> 20) & 0x7ffu;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; u++) hw[u] = __reduce_max_sync(0xffffffffu, hw[u]);
+      if (lane == 0) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) atomicMax(&s_max[st][q * CQ + cc + u], hw[u]);
+      }
+    }
+    return true;
+  };
+  if (tid == 0 && t_begin < t_end) {
+    bulk_load_tile(sX, QX + t_begin * (long long)XT_BYTES, &barX[0]);
+    if (t_begin + 1 < t_end) bulk_load_tile(sX + XT_BYTES, QX + (t_begin + 1) * (long long)XT_BYTES, &barX[1]);
+    if (!mbar_wait(&barX[0], 0, 4000000000ll)) *status = 2;
+    fence_after();
+    issue_p1(xs0);
+  }
+  if (t_begin < t_end) ok = epilogue1(t_begin, 0);
+
+  for (long long t = t_begin; t < t_end && ok; t++) {
+    const long long k = t - t_begin;
+    const int stage = (int)(k & 1);
+    fence_before();
+    __syncthreads();                                      // (A) maxima of tile t complete; accumulator set 1 has been read
+    if (tid == 0 && t + 1 < t_end) {                      // product 1 of tile t+1 runs under the slicing of tile t
+      if (!mbar_wait(&barX[stage ^ 1], (uint32_t)(((k + 1) >> 1) & 1), 4000000000ll)) *status = 2;
+      fence_after();
+      issue_p1(xs0 + (uint32_t)(stage ^ 1) * XT_BYTES);
+    }
+    if (tid >= NT - NC) s_max[stage ^ 1][tid - (NT - NC)] = 0u;
+#pragma unroll
+    for (int c = 0; c < CQ; c++) {
+      const unsigned long long w = slice7_magic(d[c], max(s_max[stage][q * CQ + c], 64u));
+      const uint32_t wl = (uint32_t)w, wh = (uint32_t)(w >> 32);
+      uint8_t* dst = sQD + boff(q * CQ + c, rl, TR);
+      dst[0 * NC * TR] = (uint8_t)(wh >> 16);
+      dst[1 * NC * TR] = (uint8_t)(wh >> 8);
+      dst[2 * NC * TR] = (uint8_t)wh;
+      dst[3 * NC * TR] = (uint8_t)(wl >> 24);
+      dst[4 * NC * TR] = (uint8_t)(wl >> 16);
+      dst[5 * NC * TR] = (uint8_t)(wl >> 8);
+      dst[6 * NC * TR] = (uint8_t)wl;
+    }
+    fence_async_smem();
+    fence_before();
+    __syncthreads();                                      // (B) adjoint slices visible; accumulator set 2 free
+    if (tid == 0) {
+      fence_after();
+      const uint32_t xs = xs0 + (uint32_t)stage * XT_BYTES;
+#pragma unroll 1
+      for (int i = 0; i < NS8; i += 2) {
+        const uint32_t idesc = make_idesc(128, NC * (NS8 - i), 1, 0);
+        for (int ks = 0; ks < TR / 32; ks++)
+          mma_i8(tmem + 256u + (uint32_t)(i * NC), make_desc(xs + i * 512 + ks * 16384, 4096, 128),
+                 make_desc(qds + ks * 256, 128, TR * 8), idesc, (i | ks) != 0);
+      }
+      umma_commit(&bar2);
+    }
+    if (t + 1 < t_end) ok = epilogue1(t + 1, k + 1);      // under product 2 of tile t
+    if (!mbar_wait(&bar2, (uint32_t)(k & 1), 4000000000ll)) ok = false;
+    fence_after();
+    if (!ok) break;
+    if (tid == 0 && t + 2 < t_end)
+      bulk_load_tile(sX + (size_t)stage * XT_BYTES, QX + (t + 2) * (long long)XT_BYTES, &barX[stage]);
+    // ---- epilogue 2 of tile t ----
+#pragma unroll
+    for (int cc = 0; cc < CQ; cc += 8) {
+      int32_t a[NS8][8];
+#pragma unroll
+      for (int cb = 0; cb < NS8; cb++) tmem_ld8_nowait(tmem + lane_base + 256u + (uint32_t)(cb * NC + q * CQ + cc), a[cb]);
+      tmem_ld_wait();
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        int32_t g[NS8];
+#pragma unroll
+        for (int cb = 0; cb < NS8; cb++) g[cb] = a[cb][u];
+        // sx * 2^(E - 1022): both powers of two, so the exponent fields add (zeroed only after barrier (A) of tile t+1)
+        const double sc = __hiloint2double((int)((max(s_max[stage][q * CQ + cc + u], 64u) + sx_exp) << 20), 0);
+        gacc[cc + u] = fma(recombine7(g, ii), sc, gacc[cc + u]);
+      }
+    }
+  }
+  if (!ok && rl == 0) *status = 1;
+  fence_before();
+  __syncthreads();
+  double* sG = (double*)sQD;
+  double* sL = (double*)sX;
+  if (ii == 1) {
+#pragma unroll
+    for (int c = 0; c < CQ; c++) sG[(q * CQ + c) * MP + (rl & 63)] = gacc[c];
+  }
+#pragma unroll
+  for (int c = 0; c < CQ; c++) sL[(q * CQ + c) * TR + rl] = lacc[c];
+  __syncthreads();
+  if (ii == 0) {
+#pragma unroll
+    for (int c = 0; c < CQ; c++) sG[(q * CQ + c) * MP + rl] += gacc[c];
+  }
+  for (int c = warp; c < NC; c += NW) {
+    double ssum = 0.0;
+#pragma unroll
+    for (int kk = 0; kk < TR / 32; kk++) ssum += sL[c * TR + kk * 32 + lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
+    if (lane == 0) outL[(size_t)blockIdx.y * ldc + c0 + c] = -0.5 * ssum;
+  }
+  __syncthreads();
+  for (int e = tid; e < NC * MP; e += NT) {
+    int c = e & (NC - 1), p = e / NC;
+    outG[((size_t)blockIdx.y * MP + p) * ldc + c0 + c] = sG[c * MP + p];
+  }
+  fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
 // ---- host ---------------------------------------------------------------------------------------------------------------
 struct Rng {
   uint64_t s;
@@ -1336,6 +1555,26 @@ int launch_v5(const Buffers& b, dim3 grid, int ldc, long long tiles, int splits,
     CK(cudaEventRecord(e0));
     if (b.eta != nullptr) k_ozaki_glm_v5<NT, true><<<grid, NT, shm>>>(b.QX8, b.Y, b.B, ldc, tiles, splits, b.sx8, b.L, b.G, b.status, b.eta);
     else k_ozaki_glm_v5<NT, false><<<grid, NT, shm>>>(b.QX8, b.Y, b.B, ldc, tiles, splits, b.sx8, b.L, b.G, b.status, b.eta);
+    CK(cudaEventRecord(e1));
+    CK(cudaGetLastError());
+    CK(cudaEventSynchronize(e1));
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (reps == 1 || rep > 0) best = fminf(best, ms);
+  }
+  *best_ms = best;
+  return 0;
+}
+
+int launch_v7(const Buffers& b, dim3 grid, int ldc, long long tiles, int splits, int reps, float* best_ms) {
+  const size_t shm = 2 * XT_BYTES + QB_BYTES + QD_BYTES;
+  CK(cudaFuncSetAttribute(k_ozaki_glm_v7<512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+  CK(cudaFuncSetAttribute(k_ozaki_glm_v7<512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+  cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < reps; rep++) {
+    CK(cudaEventRecord(e0));
+    if (b.eta != nullptr) k_ozaki_glm_v7<512, true><<<grid, 512, shm>>>(b.QX8, b.Y, b.B, ldc, tiles, splits, b.sx8, b.L, b.G, b.status, b.eta);
+    else k_ozaki_glm_v7<512, false><<<grid, 512, shm>>>(b.QX8, b.Y, b.B, ldc, tiles, splits, b.sx8, b.L, b.G, b.status, b.eta);
     CK(cudaEventRecord(e1));
     CK(cudaGetLastError());
     CK(cudaEventSynchronize(e1));
@@ -1434,9 +1673,9 @@ int run(bool check, long long rows, int chains, int splits, int only) {
 
   const double flop = 4.0 * (double)rows * MP * chains;
   // {threads, bulk prefetch (v2) or FP64 recombination (v3), kernel version}
-  const int variants[9][3] = {{128, 0, 2}, {512, 1, 2}, {512, 0, 3}, {512, 2, 3}, {256, 0, 4}, {512, 0, 4}, {256, 0, 5}, {512, 0, 5},
-                              {512, 0, 6}};      // 8: v6, not yet run on a device
-  for (int v = 0; v < 9; v++) {
+  const int variants[10][3] = {{128, 0, 2}, {512, 1, 2}, {512, 0, 3}, {512, 2, 3}, {256, 0, 4}, {512, 0, 4}, {256, 0, 5}, {512, 0, 5},
+                               {512, 0, 6}, {512, 0, 7}};      // 8, 9: v6 and v7, not yet run on a device
+  for (int v = 0; v < 10; v++) {
     if (only >= 0 && v != only) continue;
     const int NT = variants[v][0], bulk = variants[v][1], ver = variants[v][2];
     CK(cudaMemset(dS, 0, sizeof(int)));
@@ -1447,6 +1686,7 @@ int run(bool check, long long rows, int chains, int splits, int only) {
     int rc;
     if (ver == 2) rc = NT == 128 ? launch_variant<128>(bufs, bulk, grid, ldc, tiles, splits, sx, reps, &best)
                                  : launch_variant<512>(bufs, bulk, grid, ldc, tiles, splits, sx, reps, &best);
+    else if (ver == 7) rc = launch_v7(bufs, grid, ldc, tiles, splits, reps, &best);
     else if (ver == 6) rc = launch_v6(bufs, grid, ldc, tiles, splits, reps, &best);
     else if (ver == 5) rc = NT == 256 ? launch_v5<256>(bufs, grid, ldc, tiles, splits, reps, &best) : launch_v5<512>(bufs, grid, ldc, tiles, splits, reps, &best);
     else if (ver == 4) rc = NT == 256 ? launch_v4<256>(bufs, grid, ldc, tiles, splits, reps, &best) : launch_v4<512>(bufs, grid, ldc, tiles, splits, reps, &best);

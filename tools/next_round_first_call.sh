@@ -5,14 +5,16 @@
 mkdir -p gpurun_out
 P=tools/ozaki_glm_proto
 {
-  echo "== prototype v6, v7, v8 (variants 8, 9, 10): parity, then time at 250k and 1e6 rows"
+  echo "== prototype v6, v7, v8, v9 (variants 8 to 11): parity, then time at 250k and 1e6 rows"
   timeout 60 $P check 8192 64 3 8
   timeout 60 $P check 8192 64 3 9
   timeout 60 $P check 8192 64 3 10
+  timeout 60 $P check 8192 64 3 11
   timeout 60 $P time 250000 4096 37 7
   timeout 60 $P time 250000 4096 37 8
   timeout 60 $P time 250000 4096 37 9
   timeout 60 $P time 250000 4096 37 10
+  timeout 60 $P time 250000 4096 37 11
   timeout 120 $P time 1000000 4096 8 7        # 8 row splits: what the library's row_splits_for picks for 128 chain tiles
   echo "== library int8 path: opt-in parity test, then the GLM-related parity tests with the switch set"
   SMC_TEST_I8=1 timeout 900 python -m pytest tests/test_zz_gpu_i8_optin.py -m gpu -x -q 2>&1 | tail -5

@@ -1727,6 +1727,242 @@ k_ozaki_glm_v8(const int8_t* __restrict__ QX, const double* __restrict__ y, cons
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+// ---- v9 (NOT YET RUN) = v8 (issuer warp) + v6 (exponent-only maxima, integer-built scales) + v7 (magic-number slicing) -----
+template <bool DBG>
+__global__ void __launch_bounds__(544, 1)
+k_ozaki_glm_v9(const int8_t* __restrict__ QX, const double* __restrict__ y, const double* __restrict__ beta, int ldc,
+               long long tiles, int splits, double sx, double* __restrict__ outL, double* __restrict__ outG, int* status,
+               double* __restrict__ dbg_eta) {
+  constexpr int NT = 544, NE = 512, CQ = 8, NW = 16;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar1, bar2, barX[2], barA, barB;
+  __shared__ uint32_t tmem_slot;
+  __shared__ double s_sb[NC], s_f[NC];
+  __shared__ unsigned int s_max[3][NC];   // three buffers: without barrier (B) a fast warp reaches epilogue 1 of tile t+1
+                                          // while a slow one is still clearing a buffer (see the loop)
+  uint8_t* sX = smem;
+  uint8_t* sQB = smem + 2 * XT_BYTES;
+  uint8_t* sQD = sQB + QB_BYTES;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, rl = tid & 127, q = (tid >> 7) & 3;
+  const bool issuer = warp == NW;
+  const int c0 = blockIdx.x * NC;
+  const long long t_begin = tiles * blockIdx.y / splits, t_end = tiles * (blockIdx.y + 1) / splits;
+
+  if (warp == 0) tmem_alloc(&tmem_slot, 512);
+  if (tid == 32) {
+    mbar_init(&bar1, 1); mbar_init(&bar2, 1); mbar_init(&barX[0], 1); mbar_init(&barX[1], 1);
+    mbar_init(&barA, NW); mbar_init(&barB, NW);
+  }
+  if (tid < NC) {
+    double m = 0.0;
+    for (int p = 0; p < MP; p++) m = fmax(m, fabs(beta[(size_t)p * ldc + c0 + tid]));
+    double sc, f; unsigned int em;
+    scale_of8(m, &sc, &f, &em);
+    s_sb[tid] = sx * sc;
+    s_f[tid] = f;
+    s_max[0][tid] = 0u;
+    s_max[1][tid] = 0u;
+    s_max[2][tid] = 0u;
+  }
+  __syncthreads();
+  for (int e = tid; e < NC * MP; e += NT) {
+    int c = e & (NC - 1), p = e / NC;
+    const unsigned long long w = slice7_word(beta[(size_t)p * ldc + c0 + c], s_f[c]);
+    for (int j = 0; j < NS8; j++) sQB[boff(j * NC + c, p, MP)] = (uint8_t)(w >> (8 * (6 - j)));
+  }
+  fence_async_smem();
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t qbs = smem_u32(sQB), qds = smem_u32(sQD), xs0 = smem_u32(sX);
+  bool ok = true;
+
+  if (issuer) {
+    // ================= issuer warp: bulk copies and tensor instructions (lane 0), waits by the whole warp =================
+    auto issue_p1 = [&](uint32_t xs) {
+#pragma unroll 1
+      for (int i = 0; i < NS8; i++) {
+        const uint32_t idesc = make_idesc(TR, NC * (NS8 - i), 0, 0);
+        for (int ks = 0; ks < MP / 32; ks++)
+          mma_i8(tmem + (uint32_t)(i * NC), make_desc(xs + i * 512 + ks * 256, 128, 4096),
+                 make_desc(qbs + ks * 256, 128, MP * 8), idesc, (i | ks) != 0);
+      }
+      umma_commit(&bar1);
+    };
+    if (t_begin < t_end) {
+      if (lane == 0) {
+        bulk_load_tile(sX, QX + t_begin * (long long)XT_BYTES, &barX[0]);
+        if (t_begin + 1 < t_end) bulk_load_tile(sX + XT_BYTES, QX + (t_begin + 1) * (long long)XT_BYTES, &barX[1]);
+      }
+      ok = mbar_wait(&barX[0], 0, 4000000000ll);
+      fence_after();
+      if (lane == 0) issue_p1(xs0);
+      __syncwarp();
+    }
+    for (long long t = t_begin; t < t_end && ok; t++) {
+      const long long k = t - t_begin;
+      const int stage = (int)(k & 1);
+      if (t + 1 < t_end) {                                // accumulator set 1 read by every epilogue warp: product 1 (t+1)
+        ok = mbar_wait(&barA, (uint32_t)(k & 1), 4000000000ll) &&
+             mbar_wait(&barX[stage ^ 1], (uint32_t)(((k + 1) >> 1) & 1), 4000000000ll);
+        fence_after();
+        if (lane == 0) issue_p1(xs0 + (uint32_t)(stage ^ 1) * XT_BYTES);
+        __syncwarp();
+      }
+      ok = ok && mbar_wait(&barB, (uint32_t)(k & 1), 4000000000ll);    // adjoint slices in place, accumulator set 2 read
+      fence_after();
+      if (lane == 0) {
+        const uint32_t xs = xs0 + (uint32_t)stage * XT_BYTES;
+#pragma unroll 1
+        for (int i = 0; i < NS8; i += 2) {
+          const uint32_t idesc = make_idesc(128, NC * (NS8 - i), 1, 0);
+          for (int ks = 0; ks < TR / 32; ks++)
+            mma_i8(tmem + 256u + (uint32_t)(i * NC), make_desc(xs + i * 512 + ks * 16384, 4096, 128),
+                   make_desc(qds + ks * 256, 128, TR * 8), idesc, (i | ks) != 0);
+        }
+        umma_commit(&bar2);
+      }
+      __syncwarp();
+      if (t + 2 < t_end) {                                // this tile's X buffer is free once product 2 has completed
+        ok = ok && mbar_wait(&bar2, (uint32_t)(k & 1), 4000000000ll);
+        if (lane == 0) bulk_load_tile(sX + (size_t)stage * XT_BYTES, QX + (t + 2) * (long long)XT_BYTES, &barX[stage]);
+        __syncwarp();
+      }
+    }
+    if (!ok && lane == 0) *status = 2;
+  }
+
+  // ================= epilogue warps =================
+  const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+  const int ii = rl >> 6;
+  const unsigned int sx_exp = (((unsigned int)__double2hiint(sx) >> 20) & 0x7ffu) + 1u - 1023u;
+  double gacc[CQ], lacc[CQ], d[CQ];
+#pragma unroll
+  for (int c = 0; c < CQ; c++) { gacc[c] = 0.0; lacc[c] = 0.0; d[c] = 0.0; }
+  if (!issuer) {
+    auto epilogue1 = [&](long long t, long long k, int st) -> bool {
+      const double yr = y[t * TR + rl];
+      if (!mbar_wait(&bar1, (uint32_t)(k & 1), 4000000000ll)) return false;
+      fence_after();
+      unsigned int hw[8];
+#pragma unroll
+      for (int hf = 0; hf < 2; hf++) {                      // four chains at a time: 28 instead of 56 registers of accumulators
+        int32_t a[NS8][4];
+#pragma unroll
+        for (int cb = 0; cb < NS8; cb++) tmem_ld4_nowait(tmem + lane_base + (uint32_t)(cb * NC + q * CQ + hf * 4), a[cb]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int v = 0; v < 4; v++) {
+          const int u = hf * 4 + v;
+          int32_t g[NS8];
+#pragma unroll
+          for (int cb = 0; cb < NS8; cb++) g[cb] = a[cb][v];
+          const double eta = recombine7(g, 0) * s_sb[q * CQ + u];
+          if (DBG) { if (blockIdx.y == 0 && t == t_begin) dbg_eta[(size_t)rl * ldc + c0 + q * CQ + u] = eta; }
+          const double dd = yr - eta;
+          d[u] = dd;
+          lacc[u] = fma(dd, dd, lacc[u]);
+          hw[u] = ((unsigned int)__double2hiint(dd) >> 20) & 0x7ffu;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; u++) hw[u] = __reduce_max_sync(0xffffffffu, hw[u]);
+      if (lane == 0) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) atomicMax(&s_max[st][q * CQ + u], hw[u]);
+      }
+      return true;
+    };
+    if (t_begin < t_end) ok = epilogue1(t_begin, 0, 0);
+    int cur = 0;                                          // s_max buffer of tile t: (t - t_begin) mod 3
+    for (long long t = t_begin; t < t_end && ok; t++, cur = cur == 2 ? 0 : cur + 1) {
+      const long long k = t - t_begin;
+      const int nxt = cur == 2 ? 0 : cur + 1, nn = nxt == 2 ? 0 : nxt + 1;
+      fence_before();
+      asm volatile("bar.sync 1, 512;\n" ::: "memory");     // (A) maxima of tile t complete (epilogue threads only)
+      if (lane == 0) mbar_arrive(&barA);                    // accumulator set 1 has been read by this warp
+      // buffer of tile t+2: last read in epilogue 2 of tile t-1 (before this barrier), next written in epilogue 1 of tile
+      // t+2, which every warp runs after barrier (A) of tile t+1
+      if (tid >= NE - NC) s_max[nn][tid - (NE - NC)] = 0u;
+#pragma unroll
+      for (int c = 0; c < CQ; c++) {
+        const unsigned long long w = slice7_magic(d[c], max(s_max[cur][q * CQ + c], 64u));
+        const uint32_t wl = (uint32_t)w, wh = (uint32_t)(w >> 32);
+        uint8_t* dst = sQD + boff(q * CQ + c, rl, TR);
+        dst[0 * NC * TR] = (uint8_t)(wh >> 16);
+        dst[1 * NC * TR] = (uint8_t)(wh >> 8);
+        dst[2 * NC * TR] = (uint8_t)wh;
+        dst[3 * NC * TR] = (uint8_t)(wl >> 24);
+        dst[4 * NC * TR] = (uint8_t)(wl >> 16);
+        dst[5 * NC * TR] = (uint8_t)(wl >> 8);
+        dst[6 * NC * TR] = (uint8_t)wl;
+      }
+      fence_async_smem();
+      fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&barB);                    // (B) this warp's slices are visible, its epilogue 2 of t-1 is done
+      if (t + 1 < t_end) ok = epilogue1(t + 1, k + 1, nxt); // under product 2 of tile t
+      if (!mbar_wait(&bar2, (uint32_t)(k & 1), 4000000000ll)) ok = false;
+      fence_after();
+      if (!ok) break;
+#pragma unroll
+      for (int hf = 0; hf < 2; hf++) {
+        int32_t a[NS8][4];
+#pragma unroll
+        for (int cb = 0; cb < NS8; cb++) tmem_ld4_nowait(tmem + lane_base + 256u + (uint32_t)(cb * NC + q * CQ + hf * 4), a[cb]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int v = 0; v < 4; v++) {
+          const int u = hf * 4 + v;
+          int32_t g[NS8];
+#pragma unroll
+          for (int cb = 0; cb < NS8; cb++) g[cb] = a[cb][v];
+          // sx * 2^(E - 1022) from the exponents (the buffer is cleared only after barrier (A) of tile t+1)
+          const double sc = __hiloint2double((int)((max(s_max[cur][q * CQ + u], 64u) + sx_exp) << 20), 0);
+          gacc[u] = fma(recombine7(g, ii), sc, gacc[u]);
+        }
+      }
+    }
+    if (!ok && rl == 0) *status = 1;
+  }
+  fence_before();
+  __syncthreads();
+  double* sG = (double*)sQD;
+  double* sL = (double*)sX;
+  if (!issuer) {
+    if (ii == 1) {
+#pragma unroll
+      for (int c = 0; c < CQ; c++) sG[(q * CQ + c) * MP + (rl & 63)] = gacc[c];
+    }
+#pragma unroll
+    for (int c = 0; c < CQ; c++) sL[(q * CQ + c) * TR + rl] = lacc[c];
+  }
+  __syncthreads();
+  if (!issuer && ii == 0) {
+#pragma unroll
+    for (int c = 0; c < CQ; c++) sG[(q * CQ + c) * MP + rl] += gacc[c];
+  }
+  if (!issuer) {
+    for (int c = warp; c < NC; c += NW) {
+      double ssum = 0.0;
+#pragma unroll
+      for (int kk = 0; kk < TR / 32; kk++) ssum += sL[c * TR + kk * 32 + lane];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
+      if (lane == 0) outL[(size_t)blockIdx.y * ldc + c0 + c] = -0.5 * ssum;
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < NC * MP; e += NT) {
+    int c = e & (NC - 1), p = e / NC;
+    outG[((size_t)blockIdx.y * MP + p) * ldc + c0 + c] = sG[c * MP + p];
+  }
+  fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
 // ---- host ---------------------------------------------------------------------------------------------------------------
 struct Rng {
   uint64_t s;
@@ -1807,6 +2043,26 @@ int launch_v5(const Buffers& b, dim3 grid, int ldc, long long tiles, int splits,
     CK(cudaEventRecord(e0));
     if (b.eta != nullptr) k_ozaki_glm_v5<NT, true><<<grid, NT, shm>>>(b.QX8, b.Y, b.B, ldc, tiles, splits, b.sx8, b.L, b.G, b.status, b.eta);
     else k_ozaki_glm_v5<NT, false><<<grid, NT, shm>>>(b.QX8, b.Y, b.B, ldc, tiles, splits, b.sx8, b.L, b.G, b.status, b.eta);
+    CK(cudaEventRecord(e1));
+    CK(cudaGetLastError());
+    CK(cudaEventSynchronize(e1));
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (reps == 1 || rep > 0) best = fminf(best, ms);
+  }
+  *best_ms = best;
+  return 0;
+}
+
+int launch_v9(const Buffers& b, dim3 grid, int ldc, long long tiles, int splits, int reps, float* best_ms) {
+  const size_t shm = 2 * XT_BYTES + QB_BYTES + QD_BYTES;
+  CK(cudaFuncSetAttribute(k_ozaki_glm_v9<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+  CK(cudaFuncSetAttribute(k_ozaki_glm_v9<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+  cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < reps; rep++) {
+    CK(cudaEventRecord(e0));
+    if (b.eta != nullptr) k_ozaki_glm_v9<true><<<grid, 544, shm>>>(b.QX8, b.Y, b.B, ldc, tiles, splits, b.sx8, b.L, b.G, b.status, b.eta);
+    else k_ozaki_glm_v9<false><<<grid, 544, shm>>>(b.QX8, b.Y, b.B, ldc, tiles, splits, b.sx8, b.L, b.G, b.status, b.eta);
     CK(cudaEventRecord(e1));
     CK(cudaGetLastError());
     CK(cudaEventSynchronize(e1));
@@ -1945,9 +2201,9 @@ int run(bool check, long long rows, int chains, int splits, int only) {
 
   const double flop = 4.0 * (double)rows * MP * chains;
   // {threads, bulk prefetch (v2) or FP64 recombination (v3), kernel version}
-  const int variants[11][3] = {{128, 0, 2}, {512, 1, 2}, {512, 0, 3}, {512, 2, 3}, {256, 0, 4}, {512, 0, 4}, {256, 0, 5}, {512, 0, 5},
-                               {512, 0, 6}, {512, 0, 7}, {544, 0, 8}};      // 8, 9, 10: v6, v7, v8 -- not yet run on a device
-  for (int v = 0; v < 11; v++) {
+  const int variants[12][3] = {{128, 0, 2}, {512, 1, 2}, {512, 0, 3}, {512, 2, 3}, {256, 0, 4}, {512, 0, 4}, {256, 0, 5}, {512, 0, 5},
+                               {512, 0, 6}, {512, 0, 7}, {544, 0, 8}, {544, 0, 9}};   // 8..11: v6, v7, v8, v9 -- not yet run on a device
+  for (int v = 0; v < 12; v++) {
     if (only >= 0 && v != only) continue;
     const int NT = variants[v][0], bulk = variants[v][1], ver = variants[v][2];
     CK(cudaMemset(dS, 0, sizeof(int)));
@@ -1958,6 +2214,7 @@ int run(bool check, long long rows, int chains, int splits, int only) {
     int rc;
     if (ver == 2) rc = NT == 128 ? launch_variant<128>(bufs, bulk, grid, ldc, tiles, splits, sx, reps, &best)
                                  : launch_variant<512>(bufs, bulk, grid, ldc, tiles, splits, sx, reps, &best);
+    else if (ver == 9) rc = launch_v9(bufs, grid, ldc, tiles, splits, reps, &best);
     else if (ver == 8) rc = launch_v8(bufs, grid, ldc, tiles, splits, reps, &best);
     else if (ver == 7) rc = launch_v7(bufs, grid, ldc, tiles, splits, reps, &best);
     else if (ver == 6) rc = launch_v6(bufs, grid, ldc, tiles, splits, reps, &best);

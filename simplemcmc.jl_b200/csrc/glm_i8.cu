@@ -109,8 +109,10 @@ __device__ inline uint32_t boff(int n, int k, int kbytes) {
   return (uint32_t)(n >> 3) * (uint32_t)(kbytes * 8) + (uint32_t)(k >> 4) * 128 + (uint32_t)(n & 7) * 16 + (uint32_t)(k & 15);
 }
 // slices of v against scale = 2^54 / f: byte k of the result = slice 6 - k as int8 (slice 0 = most significant)
+// (round to nearest: truncation shrinks every element of X towards zero, a bias that adds up over the rows -- at the
+// configs[1] size 1.5e-13 of max |G| instead of 1e-15, tools/ozaki_study.py and DESIGN.md section 8)
 __device__ __forceinline__ unsigned long long slice7_word(double v, double f) {
-  long long t = (long long)(v * f);
+  long long t = __double2ll_rn(v * f);
   return ((unsigned long long)t + H8) ^ H8;
 }
 __device__ __forceinline__ unsigned long long slice7_bits(double v, unsigned int Emax) {   // scale = 2^(Emax - 1022)

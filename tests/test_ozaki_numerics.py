@@ -18,8 +18,10 @@ def _scale(m):
 
 
 def _slices(v, scale):
-    """slice j (0 = most significant) = byte 6-j of (trunc(v 2^54 / scale) + H8), minus 128"""
-    t = np.trunc(v * (2.0 ** 54 / scale)).astype(np.int64)
+    """slice j (0 = most significant) = byte 6-j of (round(v 2^54 / scale) + H8), minus 128.  (X and beta are rounded to
+    nearest in the kernels; the adjoint is truncated by slice7_bits or rounded by slice7_magic -- its share of the error is
+    1e-16 either way.)"""
+    t = np.rint(v * (2.0 ** 54 / scale)).astype(np.int64)
     u = (t + H8).astype(np.uint64)
     assert np.all(u < (1 << 56))
     return [((u >> np.uint64(8 * (6 - j))) & np.uint64(255)).astype(np.int64) - 128 for j in range(NS)]
@@ -101,7 +103,7 @@ def test_slices_are_an_exact_representation():
     for s in q:
         assert s.min() >= -128 and s.max() <= 127              # int8
     t = sum(qj * (1 << (8 * (6 - j))) for j, qj in enumerate(q))
-    assert np.array_equal(t, np.trunc(v * (2.0 ** 54 / scale)).astype(np.int64))
+    assert np.array_equal(t, np.rint(v * (2.0 ** 54 / scale)).astype(np.int64))
     assert np.max(np.abs(t.astype(np.float64) * (scale / 2.0 ** 54) - v)) <= scale * 2.0 ** -54
 
 

@@ -595,7 +595,7 @@ k_ozaki_glm_v3(const int8_t* __restrict__ QX, const double* __restrict__ y, cons
 constexpr int NS8 = 7;
 constexpr unsigned long long H8 = 0x0080808080808080ull;
 __host__ __device__ inline unsigned long long slice7_word(double v, double f) {       // f = 2^54 / scale
-  long long t = (long long)(v * f);
+  long long t = llrint(v * f);      // to nearest: truncating X biases every element towards zero (1.5e-13 of max |G| at N = 1e6)
   return ((unsigned long long)t + H8) ^ H8;               // byte k = slice 6 - k (slice 0 = most significant)
 }
 __device__ __forceinline__ unsigned long long slice7_bits(double v, unsigned int Emax) {   // scale = 2^(Emax - 1022)

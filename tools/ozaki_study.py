@@ -88,12 +88,12 @@ for S in (6, 7, 8):
 
 
 # ---- the scheme the device kernels ended up with (tools/ozaki_glm_proto.cu v4/v5, csrc/glm_i8.cu): seven BALANCED 8-bit
-# slices (digits in [-128, 127] of trunc(v 2^54 / scale) + 0x80...80), pairs with i + j <= 6 (0-based): 28 int8 GEMMs
+# slices (digits in [-128, 127] of round(v 2^54 / scale) + 0x80...80), pairs with i + j <= 6 (0-based): 28 int8 GEMMs
 H8 = sum(128 << (8 * k) for k in range(7))
 
 
 def slices8(A, scale):
-    t = np.trunc(A * (2.0 ** 54 / scale)).astype(np.int64)
+    t = np.rint(A * (2.0 ** 54 / scale)).astype(np.int64)       # to nearest, as the kernels slice X and beta
     u = (t + H8).astype(np.uint64)
     return [((u >> np.uint64(8 * (6 - j))) & np.uint64(255)).astype(np.int64) - 128 for j in range(7)]
 

@@ -141,6 +141,23 @@ __device__ __forceinline__ double recombine7(const int32_t* a, int ii) {
   return fma((double)hi, ii ? 0x1p-44 : 0x1p-36, (double)lo * (ii ? 0x1p-68 : 0x1p-60));
 }
 
+// eight beta slices (SMC_GLM_I8_BETA8=1, not yet run on a device): t = round(v 2^62 / scale), byte k = slice 7 - k; the
+// resolution of beta is the operand that limits the gradient with seven slices (profiles/ozaki_error_attribution_r01.json)
+__device__ __forceinline__ unsigned long long slice8_word(double v, double f62) {
+  const unsigned long long H64 = 0x8080808080808080ull;
+  long long t = __double2ll_rn(v * f62);
+  return ((unsigned long long)t + H64) ^ H64;
+}
+__device__ __forceinline__ double recombine8(const int32_t* a) {
+  long long hi = ((long long)a[0] << 24) + ((long long)a[1] << 16) + ((long long)a[2] << 8) + (long long)a[3];
+  long long lo = ((long long)a[4] << 24) + ((long long)a[5] << 16) + ((long long)a[6] << 8) + (long long)a[7];
+  return fma((double)hi, 0x1p-36, (double)lo * 0x1p-68);
+}
+__device__ __forceinline__ void tmem_ld4_nowait(uint32_t taddr, int32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr) : "memory");
+}
+
 // max |X| over the row-major padded copy (bits of a non-negative double order like the unsigned integer)
 __global__ void k_absmax(const double* __restrict__ X, long long n, unsigned long long* out) {
   unsigned long long m = 0ull;
@@ -179,6 +196,7 @@ struct GlmI8Args {
   double sigma;
 };
 
+template <int NB>      // beta slices: 7 (what has run) or 8
 __global__ void __launch_bounds__(NT, 1) k_glm_i8(GlmI8Args a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar1, bar2, barX[2];
@@ -216,8 +234,13 @@ __global__ void __launch_bounds__(NT, 1) k_glm_i8(GlmI8Args a) {
     const int c = e & (NC - 1), p = e / NC;
     double b = p < a.M ? a.beta[(long long)p * a.Cpad + c0 + c] : 0.0;
     if (s_badc[c]) b = 0.0;
-    const unsigned long long w = slice7_word(b, s_f[c]);
-    for (int j = 0; j < NS8; j++) sQB[boff(j * NC + c, p, MP)] = (uint8_t)(w >> (8 * (6 - j)));
+    if (NB == 8) {
+      const unsigned long long w = slice8_word(b, s_f[c] * 256.0);
+      for (int j = 0; j < 8; j++) sQB[boff(j * NC + c, p, MP)] = (uint8_t)(w >> (8 * (7 - j)));
+    } else {
+      const unsigned long long w = slice7_word(b, s_f[c]);
+      for (int j = 0; j < NS8; j++) sQB[boff(j * NC + c, p, MP)] = (uint8_t)(w >> (8 * (6 - j)));
+    }
   }
   fence_async_smem();
   fence_before();
@@ -235,7 +258,7 @@ __global__ void __launch_bounds__(NT, 1) k_glm_i8(GlmI8Args a) {
   auto issue_p1 = [&](uint32_t xs) {
 #pragma unroll 1
     for (int i = 0; i < NS8; i++) {
-      const uint32_t idesc = make_idesc(TR, NC * (NS8 - i), 0, 0);
+      const uint32_t idesc = make_idesc(TR, NC * (NB - i), 0, 0);       // beta slices j <= NB - 1 - i
       for (int ks = 0; ks < MP / 32; ks++)
         mma_i8(tmem + (uint32_t)(i * NC), make_desc(xs + i * 512 + ks * 256, 128, 4096),
                make_desc(qbs + ks * 256, 128, MP * 8), idesc, (i | ks) != 0);
@@ -249,20 +272,41 @@ __global__ void __launch_bounds__(NT, 1) k_glm_i8(GlmI8Args a) {
     if (!mbar_wait(&bar1, (uint32_t)(k & 1))) return false;
     fence_after();
     const int st = (int)(k & 1);
-    int32_t acc[NS8][8];
-#pragma unroll
-    for (int cb = 0; cb < NS8; cb++) tmem_ld8_nowait(tmem + lane_base + (uint32_t)(cb * NC + q * CQ), acc[cb]);
-    tmem_ld_wait();
     unsigned int hw[CQ];
+    if (NB == 8) {
 #pragma unroll
-    for (int u = 0; u < CQ; u++) {
-      int32_t g[NS8];
+      for (int hf = 0; hf < 2; hf++) {                      // eight groups: four chains at a time (registers)
+        int32_t acc[8][4];
 #pragma unroll
-      for (int cb = 0; cb < NS8; cb++) g[cb] = acc[cb][u];
-      const double w = recombine7(g, 0) * s_sb[q * CQ + u] - yr;
-      d[u] = w;
-      lacc[u] = fma(w, w, lacc[u]);
-      hw[u] = (unsigned int)__double2hiint(fabs(w));
+        for (int cb = 0; cb < 8; cb++) tmem_ld4_nowait(tmem + lane_base + (uint32_t)(cb * NC + q * CQ + hf * 4), acc[cb]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int v = 0; v < 4; v++) {
+          const int u = hf * 4 + v;
+          int32_t g[8];
+#pragma unroll
+          for (int cb = 0; cb < 8; cb++) g[cb] = acc[cb][v];
+          const double w = recombine8(g) * s_sb[q * CQ + u] - yr;
+          d[u] = w;
+          lacc[u] = fma(w, w, lacc[u]);
+          hw[u] = (unsigned int)__double2hiint(fabs(w));
+        }
+      }
+    } else {
+      int32_t acc[NS8][8];
+#pragma unroll
+      for (int cb = 0; cb < NS8; cb++) tmem_ld8_nowait(tmem + lane_base + (uint32_t)(cb * NC + q * CQ), acc[cb]);
+      tmem_ld_wait();
+#pragma unroll
+      for (int u = 0; u < CQ; u++) {
+        int32_t g[NS8];
+#pragma unroll
+        for (int cb = 0; cb < NS8; cb++) g[cb] = acc[cb][u];
+        const double w = recombine7(g, 0) * s_sb[q * CQ + u] - yr;
+        d[u] = w;
+        lacc[u] = fma(w, w, lacc[u]);
+        hw[u] = (unsigned int)__double2hiint(fabs(w));
+      }
     }
 #pragma unroll
     for (int u = 0; u < CQ; u++) hw[u] = __reduce_max_sync(0xffffffffu, hw[u]);
@@ -433,13 +477,19 @@ int smc_glm_i8_launch(smc_model_s* m, SmcGlmPlan& g, const double* beta, int64_t
     k_slice_x8<<<(unsigned)((prow * MP + 255) / 256), 256, 0, st>>>(g.Xrm, g.QX8, g.N, prow, fx);
     m->ctx->launches += 2;
     static SmcOncePerDevice once;
-    if (once.first()) SMC_CUDA(cudaFuncSetAttribute(k_glm_i8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    if (once.first()) {
+      SMC_CUDA(cudaFuncSetAttribute(k_glm_i8<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+      SMC_CUDA(cudaFuncSetAttribute(k_glm_i8<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    }
   }
   GlmI8Args a;
   a.QX = g.QX8; a.y = g.y; a.beta = beta; a.part = part; a.status = g.i8_status;
   a.N = g.N; a.tiles = tiles; a.C = C; a.Cpad = Cpad; a.M = g.M; a.splits = RS; a.sx = g.sx8; a.sigma = g.par;
   dim3 grid((unsigned)smc_glm_i8_chain_tiles(C), (unsigned)RS);
-  k_glm_i8<<<grid, NT, SMEM_BYTES, st>>>(a);
+  static int beta8 = -1;
+  if (beta8 < 0) { const char* e = getenv("SMC_GLM_I8_BETA8"); beta8 = (e && e[0] == '1') ? 1 : 0; }
+  if (beta8) k_glm_i8<8><<<grid, NT, SMEM_BYTES, st>>>(a);
+  else k_glm_i8<7><<<grid, NT, SMEM_BYTES, st>>>(a);
   if (!g.i8_checked) {      // first (eager) launch: a tensor-core completion that never arrived is an error, not a wrong number
     g.i8_checked = 1;
     int status = 0;

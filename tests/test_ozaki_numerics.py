@@ -144,3 +144,49 @@ def test_magic_number_slicing():
         assert np.array_equal(t, np.rint(v * f).astype(np.int64))
         assert np.abs(t).max() <= (1 << 54)
         assert np.all((t + H8) >= 0) and np.all((t + H8) < (1 << 56))
+
+
+def _slices_beta8(v, scale):
+    """slice8_word of csrc/glm_i8.cu: eight balanced slices of round(v 2^62 / scale), slice j = byte 7-j of (t + 0x80..80)"""
+    t = np.rint(v * (2.0 ** 62 / scale)).astype(np.int64)
+    u = t.astype(np.uint64) + np.uint64(0x8080808080808080)          # wraps modulo 2^64 like the device arithmetic
+    q = [((u >> np.uint64(8 * (7 - j))) & np.uint64(255)).astype(np.int64) - 128 for j in range(8)]
+    assert np.array_equal(sum(int(1 << (8 * (7 - j))) * qj for j, qj in enumerate(q)), t)
+    return q
+
+
+def sliced_eta_beta8(X, B):
+    """product 1 with eight beta slices (SMC_GLM_I8_BETA8=1): groups i + j <= 7, recombine8"""
+    sx = float(_scale(np.abs(X).max()))
+    QX = _slices(X, sx)
+    sb = _scale(np.abs(B).max(axis=0))
+    QB = _slices_beta8(B, sb[None, :])
+    acc = np.zeros((8,) + (X.shape[0], B.shape[1]), np.int64)
+    for i in range(NS):
+        for j in range(8 - i):
+            acc[i + j] += QX[i] @ QB[j]
+    assert np.all(np.abs(acc) < 2 ** 31)
+    hi = (acc[0] << 24) + (acc[1] << 16) + (acc[2] << 8) + acc[3]
+    lo = (acc[4] << 24) + (acc[5] << 16) + (acc[6] << 8) + acc[7]
+    return (hi.astype(np.float64) * 2.0 ** -36 + lo.astype(np.float64) * 2.0 ** -68) * (sx * sb[None, :])
+
+
+def test_eight_beta_slices():
+    X, Y, B = _problem(4096, 64, 6, 13)
+    B[5, :] *= 1e-4                                              # a component far below the chain's maximum
+    sx, sb = float(_scale(np.abs(X).max())), _scale(np.abs(B).max(axis=0))
+    QX, QB7 = _slices(X, sx), _slices(B, sb[None, :])
+    acc7 = np.zeros((NS, X.shape[0], B.shape[1]), np.int64)
+    for i in range(NS):
+        for j in range(NS - i):
+            acc7[i + j] += QX[i] @ QB7[j]
+    eta7 = _recombine(acc7, 0) * (sx * sb[None, :])
+    eta8 = sliced_eta_beta8(X, B)
+    truth = X.astype(np.longdouble) @ B.astype(np.longdouble)
+    e7 = float(np.max(np.abs(eta7 - truth)) / np.max(np.abs(truth)))
+    e8 = float(np.max(np.abs(eta8 - truth)) / np.max(np.abs(truth)))
+    assert e8 <= 1e-15 and e8 <= e7
+    # the gradient of the quadratic form amplifies the resolution of beta by N: X'(X (B8 - B)) against X'(X (B7 - B))
+    B7 = np.rint(B * (2.0 ** 54 / sb)) * (sb / 2.0 ** 54)
+    B8 = np.rint(B * (2.0 ** 62 / sb)) * (sb / 2.0 ** 62)
+    assert np.max(np.abs(B8 - B)) <= np.max(np.abs(B7 - B)) / 100 or np.max(np.abs(B7 - B)) == 0.0

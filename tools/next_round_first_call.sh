@@ -19,8 +19,10 @@ P=tools/ozaki_glm_proto
   echo "== library int8 path: opt-in parity test, then the GLM-related parity tests with the switch set"
   SMC_TEST_I8=1 timeout 900 python -m pytest tests/test_zz_gpu_i8_optin.py -m gpu -x -q 2>&1 | tail -5
   SMC_GLM_I8=1 timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_scale.py tests/test_gpu_samplers.py -m gpu -q 2>&1 | tail -8
-  echo "== library int8 path at configs[1]: rate, event-timed launch, parity of four chains"
+  echo "== library int8 path at configs[1]: rate, event-timed launch, parity of four chains (7 and 8 beta slices)"
   SMC_GLM_I8=1 timeout 300 python tools/i8_bench_extra.py 10 3
+  SMC_GLM_I8=1 SMC_GLM_I8_BETA8=1 timeout 300 python tools/i8_bench_extra.py 10 3
+  SMC_GLM_I8=1 SMC_GLM_I8_BETA8=1 timeout 60 python tools/i8_quick.py
   echo "== launch list of one evaluation with the switch set"
   SMC_GLM_I8=1 SMC_NO_GRAPHS=1 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv \
       --log-file gpurun_out/launches_i8.csv python tools/i8_quick.py > gpurun_out/ncu_i8.log 2>&1; tail -2 gpurun_out/ncu_i8.log

@@ -18,9 +18,20 @@
 //              256 + 32 (i-1): lanes 0-63 hold i + j = cb + 2, lanes 64-127 hold i + j = cb + 3.  4 x 4 instructions.
 //   epilogue 2 thread = (ii, parameter): 8 accumulators -> FP64 -> G accumulators in registers (32 chains).
 //
+// This file is a lab notebook: every kernel version that was measured is kept so that profiles/ozaki_glm_proto_v*_r01.jsonl
+// can be reproduced.  Variant index (last command-line argument) -> kernel:
+//   0  v2, 128 threads                         (= v1)            measured   14.6 TFLOP/s FP64-equivalent
+//   1  v2, 512 threads, bulk-copy prefetch                       measured   25.7
+//   2  v3, 512 threads (overlap, adjoint in registers)           measured   29.4
+//   3  v3 + magic int64->double, bit slicing                     measured   28.8
+//   4  v4, 256 threads   5  v4, 512 threads (7 x 8-bit slices)   measured   29.8 / 33.4
+//   6  v5, 256 threads   7  v5, 512 threads (both products hidden, straight-line epilogue 1)   measured 28.6 / 36.5 at N = 1e6
+//   8  v6 (cheaper scales)   9  v7 (magic-number slicing)   10  v8 (issuer warp)   11  v9 (all three)    NOT YET RUN
+// The library form of variant 7 is simplemcmc.jl_b200/csrc/glm_i8.cu.
+//
 // Build: nvcc -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a -o tools/ozaki_glm_proto tools/ozaki_glm_proto.cu
-// Run  : tools/ozaki_glm_proto check [rows] [chains]      (host long-double reference, relative errors)
-//        tools/ozaki_glm_proto time  [rows] [chains] [row_splits]
+// Run  : tools/ozaki_glm_proto check [rows] [chains] [row_splits] [variant]   (host long-double reference, relative errors)
+//        tools/ozaki_glm_proto time  [rows] [chains] [row_splits] [variant]
 #include <cmath>
 #include <cstdint>
 #include <cstdio>

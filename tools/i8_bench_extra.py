@@ -41,6 +41,11 @@ flops = 4.0 * N * M * C
 print(json.dumps({"value": raw["n_leapfrogs"] / (raw["device_ms"] * 1e-3), "unit": bench.UNIT, "steps": K,
                   "accept_rate": float(np.mean(raw["accept_rate"])), "glm_ms_per_launch": ms_glm, "ms_per_eval": ms_eval,
                   "fp64_equivalent_TFLOPs": flops / (ms_glm * 1e-3) / 1e12,
+                  # 28 slice-pair products of the same shape on the int8 tensor cores; peak = the issue rate of the
+                  # instruction measured by tools/i8_umma_probe.cu on this pool (profiles/i8_umma_probe_r01.jsonl)
+                  "int8_roofline": {"bound": "tensor", "achieved": 28 * flops / (ms_glm * 1e-3) / 1e15, "peak": 4.58, "unit": "Pop/s",
+                                    "frac": 28 * flops / (ms_glm * 1e-3) / 4.58e15},
+                  "beta_slices": 8 if os.environ.get("SMC_GLM_I8_BETA8") == "1" else 7,
                   "relerr_logp_vs_long_double": err_l, "relerr_grad_vs_long_double": err_g,
                   "n_kernel_launches": int(raw["n_kernel_launches"])}))
 dev.close()

@@ -1020,7 +1020,11 @@ int smc_glm_launch(smc_model_s* m, SmcGlmPlan& g, int64_t C) {
   RS = (int)((g.N + rows_per_split - 1) / rows_per_split);
   if (stream) RS = (int)std::max<long long>(1, std::min<long long>((g.N + 255) / 256, 2LL * m->ctx->sm_count));
   // opt-in (SMC_GLM_I8=1): the sliced-integer kernel on the int8 tensor cores, 32-chain tiles x 128-row tiles (glm_i8.cu)
-  const bool i8 = !stream && smc_glm_i8_usable(g, C);
+  bool i8 = !stream && smc_glm_i8_usable(g, C);
+  if (i8) {
+    SMC_TRY(smc_glm_i8_prepare(m, g));
+    i8 = !g.i8_declined;
+  }
   if (i8) RS = row_splits_for(smc_glm_i8_chain_tiles(C), g.N, smc_glm_i8_row_tile(), m->ctx->sm_count);
   int64_t need = (int64_t)(RS + 1) * (g.MP + 1) * m->Cpad;
   if (need > g.part_cap) {

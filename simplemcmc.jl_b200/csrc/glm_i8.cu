@@ -450,38 +450,49 @@ void smc_glm_i8_release(SmcGlmPlan& g, cudaStream_t st) {
   if (g.i8_status) smc_dev_free(g.i8_status, st);
   g.QX8 = nullptr;
   g.i8_status = nullptr;
+  g.i8_checked = 0;
+  g.i8_declined = 0;
 }
 
-// part: [RS][MP + 1][Cpad]; beta: [M][Cpad].  The first call (always outside a stream capture: the first evaluation of a
-// model is eager) slices X.
-int smc_glm_i8_launch(smc_model_s* m, SmcGlmPlan& g, const double* beta, int64_t C, int64_t Cpad, int RS, double* part) {
+// Slices X on the first call (always outside a stream capture: the first evaluation of a model is eager).  A design matrix
+// with NaN or Inf cannot be sliced: the plan is marked declined and the statement stays on the FP64 kernel, which turns
+// such rows into chains out of support like the reference does.
+int smc_glm_i8_prepare(smc_model_s* m, SmcGlmPlan& g) {
+  if (g.QX8 || g.i8_declined) return SMC_OK;
   cudaStream_t st = m->ctx->stream;
   const long long tiles = (g.N + TR - 1) / TR;
-  if (!g.QX8) {
-    unsigned long long* dmax = nullptr;
-    SMC_CUDA(smc_dev_alloc(&dmax, sizeof(unsigned long long), st));
-    SMC_CUDA(cudaMemsetAsync(dmax, 0, sizeof(unsigned long long), st));
-    k_absmax<<<(unsigned)std::min<long long>((g.N * g.MP + 255) / 256, 148LL * 16), 256, 0, st>>>(g.Xrm, g.N * g.MP, dmax);
-    unsigned long long hbits = 0;
-    SMC_CUDA(smc_copy_sync(&hbits, dmax, sizeof(hbits), cudaMemcpyDeviceToHost, st));
-    smc_dev_free(dmax, st);
-    double xmax;
-    memcpy(&xmax, &hbits, 8);
-    if (!(xmax <= 1.7976931348623157e308)) { smc_set_error("GLM (int8 path): X holds NaN or Inf"); return SMC_ERR_INVALID; }
-    double fx;
-    scale_of8(xmax, &g.sx8, &fx);
-    SMC_CUDA(smc_dev_alloc(&g.QX8, (size_t)tiles * XT_BYTES, st));
-    SMC_CUDA(smc_dev_alloc(&g.i8_status, sizeof(int), st));
-    SMC_CUDA(cudaMemsetAsync(g.i8_status, 0, sizeof(int), st));
-    const long long prow = tiles * TR;
-    k_slice_x8<<<(unsigned)((prow * MP + 255) / 256), 256, 0, st>>>(g.Xrm, g.QX8, g.N, prow, fx);
-    m->ctx->launches += 2;
-    static SmcOncePerDevice once;
-    if (once.first()) {
-      SMC_CUDA(cudaFuncSetAttribute(k_glm_i8<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-      SMC_CUDA(cudaFuncSetAttribute(k_glm_i8<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    }
+  unsigned long long* dmax = nullptr;
+  SMC_CUDA(smc_dev_alloc(&dmax, sizeof(unsigned long long), st));
+  SMC_CUDA(cudaMemsetAsync(dmax, 0, sizeof(unsigned long long), st));
+  k_absmax<<<(unsigned)std::min<long long>((g.N * g.MP + 255) / 256, 148LL * 16), 256, 0, st>>>(g.Xrm, g.N * g.MP, dmax);
+  m->ctx->launches++;
+  unsigned long long hbits = 0;
+  SMC_CUDA(smc_copy_sync(&hbits, dmax, sizeof(hbits), cudaMemcpyDeviceToHost, st));
+  smc_dev_free(dmax, st);
+  double xmax;
+  memcpy(&xmax, &hbits, 8);
+  if (!(xmax <= 1.7976931348623157e308)) { g.i8_declined = 1; return SMC_OK; }
+  double fx;
+  scale_of8(xmax, &g.sx8, &fx);
+  SMC_CUDA(smc_dev_alloc(&g.QX8, (size_t)tiles * XT_BYTES, st));
+  SMC_CUDA(smc_dev_alloc(&g.i8_status, sizeof(int), st));
+  SMC_CUDA(cudaMemsetAsync(g.i8_status, 0, sizeof(int), st));
+  const long long prow = tiles * TR;
+  k_slice_x8<<<(unsigned)((prow * MP + 255) / 256), 256, 0, st>>>(g.Xrm, g.QX8, g.N, prow, fx);
+  m->ctx->launches++;
+  static SmcOncePerDevice once;
+  if (once.first()) {
+    SMC_CUDA(cudaFuncSetAttribute(k_glm_i8<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    SMC_CUDA(cudaFuncSetAttribute(k_glm_i8<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   }
+  return SMC_OK;
+}
+
+// part: [RS][MP + 1][Cpad]; beta: [M][Cpad]
+int smc_glm_i8_launch(smc_model_s* m, SmcGlmPlan& g, const double* beta, int64_t C, int64_t Cpad, int RS, double* part) {
+  cudaStream_t st = m->ctx->stream;
+  if (!g.QX8) { smc_set_error("GLM (int8 path): launch before prepare"); return SMC_ERR_INVALID; }
+  const long long tiles = (g.N + TR - 1) / TR;
   GlmI8Args a;
   a.QX = g.QX8; a.y = g.y; a.beta = beta; a.part = part; a.status = g.i8_status;
   a.N = g.N; a.tiles = tiles; a.C = C; a.Cpad = Cpad; a.M = g.M; a.splits = RS; a.sx = g.sx8; a.sigma = g.par;

@@ -98,6 +98,7 @@ struct SmcGlmPlan {  // one SMC_OP_GLM statement, prepared at finalize
   double sx8 = 0.0;        // power-of-two scale of X
   int* i8_status = nullptr;
   int i8_checked = 0;
+  int i8_declined = 0;     // X holds NaN / Inf: the statement stays on the FP64 kernel
 };
 
 // Micro-operation of the register-program VM (vm_exec.cu): the tape's LOADV/LOADS/STOREV/REDUCE instructions are
@@ -221,5 +222,6 @@ void smc_glm_release(SmcGlmPlan& g, cudaStream_t st);
 bool smc_glm_i8_usable(const SmcGlmPlan& g, int64_t C);
 int smc_glm_i8_chain_tiles(int64_t C);
 int smc_glm_i8_row_tile();
+int smc_glm_i8_prepare(smc_model_s* m, SmcGlmPlan& g);   // slices X on the first call; may decline (g.i8_declined)
 int smc_glm_i8_launch(smc_model_s* m, SmcGlmPlan& g, const double* beta, int64_t C, int64_t Cpad, int RS, double* part);
 void smc_glm_i8_release(SmcGlmPlan& g, cudaStream_t st);

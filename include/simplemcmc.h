@@ -54,6 +54,12 @@ int smc_ctx_destroy(smc_ctx_t ctx);
 /* Row-sharded models: attach an NCCL communicator (id from ncclGetUniqueId, broadcast by the host). */
 int smc_ctx_comm_init(smc_ctx_t ctx, const void* nccl_unique_id, int id_bytes, int rank, int nranks);
 int smc_comm_unique_id(void* out_id, int id_bytes);
+/* Row-sharded models on one node, optional: sum the per-evaluation (L, G) block through peer memory (NVLink) instead of
+   NCCL.  Every rank exports the 64-byte IPC handle of its exchange buffer, the host gathers the handles in rank order,
+   every rank imports them; from then on the context uses the peer path.  Replaces nothing in the reference (it has no
+   multi-process mode); the exchange it serves is the sum over rows of src/distribs.jl:100-102. */
+int smc_ctx_p2p_export(smc_ctx_t ctx, int nranks, void* handle_out, int handle_bytes);
+int smc_ctx_p2p_import(smc_ctx_t ctx, const void* handles, int nranks, int rank);
 /* sum-allreduce a small host vector of doubles over the communicator (chain moments for R-hat) */
 int smc_ctx_allreduce(smc_ctx_t ctx, double* host_inout, int64_t n);
 

@@ -35,7 +35,7 @@ class RunOutput(ctypes.Structure):
 
 
 EXPORTS = ["smc_abi_version", "smc_last_error", "smc_ctx_create", "smc_ctx_destroy", "smc_ctx_comm_init",
-           "smc_comm_unique_id", "smc_ctx_allreduce", "smc_model_compile", "smc_model_destroy", "smc_model_bind_data",
+           "smc_comm_unique_id", "smc_ctx_allreduce", "smc_ctx_p2p_export", "smc_ctx_p2p_import", "smc_model_compile", "smc_model_destroy", "smc_model_bind_data",
            "smc_model_finalize", "smc_model_nparams", "smc_eval", "smc_eval_timed", "smc_hmc_run", "smc_rwm_run",
            "smc_nuts_run", "smc_philox_normals", "smc_philox_uniforms", "smc_vm_plan_describe"]
 
@@ -102,6 +102,17 @@ class Context(object):
     def comm_init(self, unique_id, rank, nranks):
         check(self.lib.smc_ctx_comm_init(self.h, unique_id, len(unique_id), rank, nranks))
         self.rank, self.nranks = rank, nranks
+
+    def p2p_export(self, nranks):
+        """64-byte IPC handle of this rank's peer-exchange buffer (row-sharded models on one node, smc_p2p.cu)"""
+        buf = ctypes.create_string_buffer(64)
+        check(self.lib.smc_ctx_p2p_export(self.h, int(nranks), buf, 64))
+        return buf.raw
+
+    def p2p_import(self, handles, nranks, rank):
+        """handles: the nranks exported handles concatenated in rank order"""
+        assert len(handles) == 64 * nranks
+        check(self.lib.smc_ctx_p2p_import(self.h, handles, int(nranks), int(rank)))
 
     def allreduce(self, arr):
         arr = np.ascontiguousarray(arr, dtype=np.float64)

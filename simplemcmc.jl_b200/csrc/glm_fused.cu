@@ -1090,7 +1090,9 @@ int smc_glm_launch(smc_model_s* m, SmcGlmPlan& g, int64_t C) {
   m->ctx->launches += 2;
   if (sharded) {
     // rows are split over ranks: sum the (L, G) block over the communicator, then publish
-    SMC_TRY(smc_comm_allreduce_device(m->ctx, out, (int64_t)(g.MP + 1) * m->Cpad));
+    // (peer-memory exchange when the host has set it up with smc_ctx_p2p_export / _import, NCCL otherwise)
+    if (smc_p2p_ready(m->ctx, (int64_t)(g.MP + 1) * m->Cpad)) SMC_TRY(smc_p2p_allreduce_device(m->ctx, out, (int64_t)(g.MP + 1) * m->Cpad));
+    else SMC_TRY(smc_comm_allreduce_device(m->ctx, out, (int64_t)(g.MP + 1) * m->Cpad));
     long long tot2 = (long long)(g.M + 1) * C;
     k_glm_publish<<<(unsigned)std::min<long long>((tot2 + 255) / 256, 148LL * 16), 256, 0, st>>>(
         out, g.M, g.MP, C, m->Cpad, m->bad, Lr.dev, Gr.dev, pub.acc);

@@ -121,6 +121,7 @@ extern "C" int smc_ctx_destroy(smc_ctx_t c) {
   if (!c) return SMC_OK;
   cudaSetDevice(c->device);
   smc_comm_destroy(c);
+  smc_p2p_destroy(c);
   if (c->flush_buf) smc_dev_free(c->flush_buf, c->stream);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;

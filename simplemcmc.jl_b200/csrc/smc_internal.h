@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <algorithm>
 #include <string>
 #include <vector>
 #include "../../include/simplemcmc.h"
@@ -58,6 +59,12 @@ struct smc_ctx_s {
   int rank = 0, nranks = 1;
   void* flush_buf = nullptr;  // L2 flush scratch (256 MB), allocated on demand
   int64_t launches = 0;       // kernels launched by this library on this context
+  // peer-memory exchange of row-sharded models (smc_p2p.cu; opt-in through smc_ctx_p2p_export / _import)
+  void* p2p_local = nullptr;
+  void* p2p_peer[16] = {};
+  unsigned* p2p_count = nullptr;
+  int p2p_rank = 0, p2p_ranks = 0;
+  unsigned p2p_epoch = 0;
 };
 
 struct SmcReg {
@@ -217,6 +224,11 @@ int smc_vm_launch(smc_model_s* m, SmcProgram& pr, int64_t C, int* bad);
 int smc_glm_prepare(smc_model_s* m, SmcGlmPlan& g);
 int smc_glm_launch(smc_model_s* m, SmcGlmPlan& g, int64_t C);
 void smc_glm_release(SmcGlmPlan& g, cudaStream_t st);
+
+// smc_p2p.cu
+bool smc_p2p_ready(const smc_ctx_s* c, int64_t n);
+int smc_p2p_allreduce_device(smc_ctx_s* c, double* buf, int64_t n);
+void smc_p2p_destroy(smc_ctx_s* c);
 
 // glm_i8.cu (opt-in, SMC_GLM_I8=1)
 bool smc_glm_i8_usable(const SmcGlmPlan& g, int64_t C);

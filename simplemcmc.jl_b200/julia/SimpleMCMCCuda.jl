@@ -33,6 +33,24 @@ mutable struct Context
     end
 end
 
+# ---- multi-GPU plumbing of row-sharded models (one Julia process per GPU; the host exchanges the byte strings) ----------
+"128-byte NCCL unique id (made by the first rank of a communicator, broadcast by the host)"
+function comm_unique_id()
+    id = Vector{UInt8}(undef, 128)
+    check(ccall((:smc_comm_unique_id, lib), Cint, (Ptr{UInt8}, Cint), id, 128))
+    id
+end
+comm_init!(ctx::Context, id::Vector{UInt8}, rank::Integer, nranks::Integer) =
+    check(ccall((:smc_ctx_comm_init, lib), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Cint, Cint, Cint), ctx.h, id, length(id), rank, nranks))
+"optional, one node: 64-byte IPC handle of this rank's peer-exchange buffer / map the peers' buffers (handles in rank order)"
+function p2p_export(ctx::Context, nranks::Integer)
+    h = Vector{UInt8}(undef, 64)
+    check(ccall((:smc_ctx_p2p_export, lib), Cint, (Ptr{Cvoid}, Cint, Ptr{UInt8}, Cint), ctx.h, nranks, h, 64))
+    h
+end
+p2p_import!(ctx::Context, handles::Vector{UInt8}, nranks::Integer, rank::Integer) =
+    check(ccall((:smc_ctx_p2p_import, lib), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Cint, Cint), ctx.h, handles, nranks, rank))
+
 mutable struct Model
     h::Ptr{Cvoid}
     nparams::Int

@@ -140,6 +140,28 @@ def init_library_comm(ctx, rank, world, group=None, src=0):
     ctx.comm_init(broadcast_unique_id(capi.unique_id, rank, group=group, src=src), rank, world)
 
 
+def gather_handles(handle, rank, world, group=None):
+    """all ranks' 64-byte handles concatenated in (group) rank order"""
+    import torch
+    import torch.distributed as dist
+    mine = torch.frombuffer(bytearray(handle), dtype=torch.uint8).clone()
+    assert mine.numel() == 64
+    cuda = dist.get_backend(group) == "nccl"
+    if cuda:
+        mine = mine.cuda()
+    parts = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine, group=group)
+    return b"".join(bytes(p.cpu().numpy().tobytes()) for p in parts)
+
+
+def init_p2p(ctx, rank, world, group=None):
+    """peer-memory exchange for a row-sharded model on one node (csrc/smc_p2p.cu): every rank exports the IPC handle of
+    its exchange buffer, the handles are gathered in rank order, every rank maps its peers.  `rank` / `world` are the
+    position in and the size of `group` (default: all ranks).  Optional: without it the library uses NCCL."""
+    handles = gather_handles(ctx.p2p_export(world), rank, world, group=group)
+    ctx.p2p_import(handles, world, rank)
+
+
 def init_hybrid_comm(ctx, layout):
     """library communicator of this rank's row group (hybrid chains x rows sharding); returns the torch group"""
     grp = new_row_groups(layout)

@@ -176,3 +176,47 @@ def test_hybrid_grid_world_size_4():
         assert np.allclose(rh, rhat, rtol=1e-10)
     for cg, lgs in by_group.items():
         assert len(lgs) == row_ranks and np.array_equal(lgs[0], lgs[1])     # identical on the members of a row group
+
+
+# ---- peer-memory handle exchange (host side of csrc/smc_p2p.cu): world_size 2 on gloo, with a stand-in context -------------
+
+class _FakeCtx(object):
+    def __init__(self, rank):
+        self.rank, self.imported = rank, None
+
+    def p2p_export(self, nranks):
+        return bytes([100 + self.rank]) * 64
+
+    def p2p_import(self, handles, nranks, rank):
+        self.imported = (handles, nranks, rank)
+
+
+def _p2p_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from smc_pkg import load_package
+    load_package()
+    from simplemcmc_jl_b200 import parallel as par
+    ctx = _FakeCtx(rank)
+    par.init_p2p(ctx, rank, world)
+    q.put((rank, ctx.imported))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_p2p_handles_are_gathered_in_rank_order():
+    world = 2
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_p2p_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, (handles, nranks, r) in res:
+        assert (nranks, r) == (world, rank)
+        assert handles == bytes([100]) * 64 + bytes([101]) * 64

@@ -25,6 +25,8 @@ Y = (rng.random(N) < 1.0 / (1.0 + np.exp(X @ b0))).astype(np.float64)
 r0, r1 = parallel.row_shard(N, rank, world)
 ctx = capi.Context(local)
 parallel.init_library_comm(ctx, rank, world)
+if os.environ.get("P2P") == "1":      # peer-memory exchange instead of the NCCL all-reduce (csrc/smc_p2p.cu)
+    parallel.init_p2p(ctx, rank, world)
 low, dev = api._build(LOGISTIC, [("vars", np.zeros(M))], dict(X=np.asfortranarray(X[r0:r1]), Y=Y[r0:r1]), True, C, local, "assign",
                       shard="rows", comm=ctx)
 betas = b0[None, :] + 1e-3 * np.random.default_rng(9).standard_normal((C, M))
@@ -51,7 +53,7 @@ dist.all_reduce(ms, op=dist.ReduceOp.MAX)
 fs = torch.tensor(raw["final_state"].ravel(), device="cuda")
 fmax, fmin = fs.clone(), fs.clone()
 dist.all_reduce(fmax, op=dist.ReduceOp.MAX); dist.all_reduce(fmin, op=dist.ReduceOp.MIN)
-res.update(gpus=world, rows=N, chains=C, hmc_ms_per_step=float(ms.item()) / 10, accept=float(raw["accept_rate"].mean()),
+res.update(exchange="p2p" if os.environ.get("P2P") == "1" else "nccl", gpus=world, rows=N, chains=C, hmc_ms_per_step=float(ms.item()) / 10, accept=float(raw["accept_rate"].mean()),
            leapfrog_chain_steps_per_s=C * 20 / (float(ms.item()) * 1e-3), chains_identical_after_hmc=bool(torch.equal(fmax, fmin)))
 if rank == 0:
     print(json.dumps(res))

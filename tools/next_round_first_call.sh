@@ -28,3 +28,10 @@ P=tools/ozaki_glm_proto
       --log-file gpurun_out/launches_i8.csv python tools/i8_quick.py > gpurun_out/ncu_i8.log 2>&1; tail -2 gpurun_out/ncu_i8.log
 } > gpurun_out/next_round_first_call.log 2>&1
 tail -60 gpurun_out/next_round_first_call.log
+
+# Second call, two GPUs (charged twice): NCCL against the peer-memory exchange of csrc/smc_p2p.cu on a latency-bound shape, and
+# the hybrid grid on four:
+#   gpurun --gpus 2 --timeout 600 -- 'for p in 0 1; do P2P=$p ROWS=2000000 CHAINS=2 python -m torch.distributed.run --nproc-per-node 2 \
+#       --master-addr 127.0.0.1 tools/rowshard_check.py; done > gpurun_out/p2p_2gpu.log 2>&1; tail -4 gpurun_out/p2p_2gpu.log'
+#   gpurun --gpus 4 --timeout 600 -- 'ROW_RANKS=2 python -m torch.distributed.run --nproc-per-node 4 --master-addr 127.0.0.1 \
+#       tools/hybrid_check.py > gpurun_out/hybrid_4gpu.log 2>&1; tail -2 gpurun_out/hybrid_4gpu.log'

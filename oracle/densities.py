@@ -7,10 +7,14 @@ Log-densities of SimpleMCMC.jl, restated for the CPU:
 * The other nine call libRmath (`dweibull dbinom dgamma dcauchy dlnorm dbeta dpois dt dexp`, give_log=1,
   variate rotated to the first argument: src/distribs.jl:40-48,59,65-67).  libRmath is a third-party
   dependency that is NOT vendored under /root/reference and is not version-pinned (REQUIRE is empty,
-  `dlopen("libRmath")` by bare name).  Its published algorithms are restated here as the closed-form
-  log-densities (scale parametrisation) with R's documented edge cases (outside support -> -Inf,
-  invalid parameters -> NaN).  Parity for their absolute values is therefore "unpinned" against the
-  reference and pinned instead against 50-digit mpmath closed forms (tests/test_oracle_densities.py).
+  `dlopen("libRmath")` by bare name).  Its published algorithms are restated in oracle/rmath.py (Loader's
+  saddle-point forms for dbinom / dpois / dgamma / dbeta / dt, single expressions for the other four) and
+  that is what `logpdfX` evaluates here; the textbook closed forms are kept as `closed_form(name, ...)` --
+  they are what the first round's device code computed and tests/test_oracle_rmath.py records where they
+  stop agreeing with nmath's algorithm (1e-8 relative at lambda = 1e8).  R's documented edge cases: outside
+  support -> -Inf, invalid parameters -> NaN.  Parity for the absolute values is "unpinned" against the
+  reference binary and pinned instead against 50-digit mpmath values (tests/test_oracle_densities.py,
+  tests/test_oracle_rmath.py): nmath and this restatement are both within a few ulp of the exact value.
 * The vectorised methods (src/distribs.jl:85-110) sum element by element, left to right, over the
   length of the first array argument; `-Inf` abandons the whole evaluation ("give up eval",
   src/distribs.jl:69-70), `NaN` is a hard error (:71-73).
@@ -147,6 +151,25 @@ def _exponential(sc, x):          # dexp(x, scale, log)
         res = np.where(sc <= 0.0, np.nan, res)
     return res
 
+
+def _from_rmath(name):
+    from . import rmath
+    fn = np.frompyfunc(rmath.LOGPDF[name], rmath.LOGPDF[name].__code__.co_argcount, 1)
+
+    def g(*args):
+        return np.asarray(fn(*args), dtype=np.float64)
+    return g
+
+
+CLOSED_FORM = {"Binomial": _binomial, "Gamma": _gamma, "Beta": _beta, "Poisson": _poisson, "TDist": _tdist}
+
+
+def closed_form(name, *args):
+    """the textbook closed form of one of the five saddle-point densities (per element, broadcast)"""
+    return CLOSED_FORM[name](*[_arr(a) for a in args])
+
+
+_binomial, _gamma, _beta, _poisson, _tdist = (_from_rmath(n) for n in ("Binomial", "Gamma", "Beta", "Poisson", "TDist"))
 
 _ELEMENTWISE = {"Normal": _normal, "Uniform": _uniform, "Bernoulli": _bernoulli, "Weibull": _weibull,
                 "Binomial": _binomial, "Gamma": _gamma, "Cauchy": _cauchy, "logNormal": _lognormal,

@@ -3,4 +3,4 @@ many chains in lockstep).  Host side mirrors the reference's exported API; the w
 libsimplemcmc_cuda.so (csrc/), reached through the C ABI of include/simplemcmc.h."""
 from .api import (MCMCRun, ModelFunction, generateModelFunction, simpleHMC, simpleNUTS, simpleRWM)  # noqa: F401
 from .lowering import ModelError  # noqa: F401
-from .solvers import SolverRun, simpleAGD  # noqa: F401
+from .solvers import SolverRun, simpleAGD, simpleNM  # noqa: F401

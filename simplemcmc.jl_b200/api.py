@@ -82,10 +82,11 @@ def _build(model, init, data, gradient, chains, device, ref_adjoint, shard=None,
 
 
 def generateModelFunction(model, gradient=False, debug=False, chains=1, device=0, data=None, ref_adjoint="assign",
-                          sufficient_stats=False, **init):
+                          sufficient_stats=False, _globals=None, **init):
     """-> (f, nparams, pars, init) like src/parsing.jl:492; debug=True returns the statement lists instead of
-    compiling (the reference returns the generated Expr)."""
-    lookup = _DataLookup(data, _caller_globals())
+    compiling (the reference returns the generated Expr).  `_globals` (internal): the module globals external variables
+    are looked up in when the call comes through a solver rather than from user code."""
+    lookup = _DataLookup(data, _globals if _globals is not None else _caller_globals())
     if debug:
         low = Lowering(model, list(init.items()), lookup, gradient=gradient, ref_adjoint=ref_adjoint)
         return low.statements()
@@ -227,14 +228,12 @@ def _sample(kind, model, kw, defaults):
             raise AssertionError(str(e))
         raise
     finally:
-        pass
+        dev.close()
     res = MCMCRun(steps, burnin)
     if kind == "nuts":
         res.misc["epsilon"] = raw["epsilon"][:, 0] if chains == 1 else raw["epsilon"]
         res.misc["jmax"] = raw["jmax"][:, 0] if chains == 1 else raw["jmax"]
-    out = _finish(res, low.pars, raw, chains, t0, store)
-    dev.close()
-    return out
+    return _finish(res, low.pars, raw, chains, t0, store)
 
 
 def simpleRWM(model, **kw):

@@ -1,8 +1,11 @@
 // Device log-densities and their adjoints (FP64).
 // Formulas: /root/reference/src/distribs.jl:12-33 (Bernoulli, Normal, Uniform, defined locally there) and the
-// nine libRmath densities the reference reaches by ccall (src/distribs.jl:40-48,65-67): closed-form
-// log-densities in the scale parametrisation with R's edge cases (outside support -> -inf, invalid
-// parameter -> NaN).  Adjoints: the @dfunc table, src/diff.jl:94-174.
+// nine libRmath densities the reference reaches by ccall (src/distribs.jl:40-48,65-67), in the scale
+// parametrisation with R's edge cases (outside support -> -inf, invalid parameter -> NaN).  dbinom, dpois, dgamma,
+// dbeta (a, b > 2) and dt follow nmath's published ALGORITHM -- Loader's saddle-point form built from stirlerr()
+// and bd0() -- not the textbook closed forms: those cancel catastrophically for large counts / shapes (1e-8 relative
+// at lambda = 1e8, oracle/rmath.py, tests/test_oracle_rmath.py) where libRmath stays at 1e-15.  dweibull, dcauchy,
+// dlnorm, dexp are single expressions in nmath and are written as such.  Adjoints: the @dfunc table, src/diff.jl:94-174.
 #pragma once
 #include <math.h>
 #include "../../include/simplemcmc_tape.h"
@@ -32,6 +35,86 @@ __device__ __forceinline__ double smc_digamma(double x) {
 __device__ __forceinline__ double smc_xlogy(double x, double y) { return x == 0.0 ? 0.0 : x * log(y); }
 __device__ __forceinline__ double smc_xlog1py(double x, double y) { return x == 0.0 ? 0.0 : x * log1p(y); }
 
+#define SMC_LN_2PI 1.837877066409345483560659472811
+#define SMC_2PI 6.283185307179586476925286766559
+#define SMC_DBL_MIN 2.2250738585072014e-308
+#define SMC_DBL_EPS 2.220446049250313e-16
+
+// stirlerr(n) = log n! - log(sqrt(2 pi n) (n/e)^n)  (nmath/stirlerr.c): table for 2n integer, n <= 15; series beyond
+static __device__ const double smc_sferr_halves[31] = {
+#include "stirlerr_table.inc"
+};
+static __device__ __noinline__ double smc_stirlerr(double n) {
+  if (n <= 15.0) {
+    double nn = n + n;
+    if (nn == (double)(int)nn) return smc_sferr_halves[(int)nn];
+    return lgamma(n + 1.0) - (n + 0.5) * log(n) + n - SMC_LOG_SQRT_2PI;
+  }
+  const double S0 = 1.0 / 12.0, S1 = 1.0 / 360.0, S2 = 1.0 / 1260.0, S3 = 1.0 / 1680.0, S4 = 1.0 / 1188.0;
+  double nn = n * n;
+  if (n > 500.0) return (S0 - S1 / nn) / n;
+  if (n > 80.0) return (S0 - (S1 - S2 / nn) / nn) / n;
+  if (n > 35.0) return (S0 - (S1 - (S2 - S3 / nn) / nn) / nn) / n;
+  return (S0 - (S1 - (S2 - (S3 - S4 / nn) / nn) / nn) / nn) / n;
+}
+// bd0(x, M) = x log(x/M) + M - x  (nmath/bd0.c): series in v = (x-M)/(x+M) near x = M
+static __device__ __noinline__ double smc_bd0(double x, double M) {
+  if (!isfinite(x) || !isfinite(M) || M == 0.0) return nan("");
+  if (fabs(x - M) < 0.1 * (x + M)) {
+    double v = (x - M) / (x + M), s = (x - M) * v;
+    if (fabs(s) < SMC_DBL_MIN) return s;
+    double ej = 2.0 * x * v;
+    v = v * v;
+    for (int j = 1; j < 1000; j++) {
+      ej *= v;
+      double s1 = s + ej / (double)((j << 1) + 1);
+      if (s1 == s) return s1;
+      s = s1;
+    }
+  }
+  return x * log(x / M) + M - x;
+}
+// log dpois_raw(x, lambda)  (nmath/dpois.c)
+static __device__ __noinline__ double smc_dpois_raw(double x, double lam) {
+  if (lam == 0.0) return x == 0.0 ? 0.0 : -INFINITY;
+  if (!isfinite(lam) || x < 0.0) return -INFINITY;
+  if (x <= lam * SMC_DBL_MIN) return -lam;
+  if (lam < x * SMC_DBL_MIN) return isfinite(x) ? -lam + x * log(lam) - lgamma(x + 1.0) : -INFINITY;
+  return -0.5 * log(SMC_2PI * x) + (-smc_stirlerr(x) - smc_bd0(x, lam));
+}
+// log dbinom_raw(x, n, p, q)  (nmath/dbinom.c)
+static __device__ __noinline__ double smc_dbinom_raw(double x, double n, double p, double q) {
+  if (p == 0.0) return x == 0.0 ? 0.0 : -INFINITY;
+  if (q == 0.0) return x == n ? 0.0 : -INFINITY;
+  if (x == 0.0) {
+    if (n == 0.0) return 0.0;
+    return p < 0.1 ? -smc_bd0(n, n * q) - n * p : n * log(q);
+  }
+  if (x == n) return q < 0.1 ? -smc_bd0(n, n * p) - n * q : n * log(p);
+  if (x < 0.0 || x > n) return -INFINITY;
+  double lc = smc_stirlerr(n) - smc_stirlerr(x) - smc_stirlerr(n - x) - smc_bd0(x, n * p) - smc_bd0(n - x, n * q);
+  double lf = SMC_LN_2PI + log(x) + log1p(-x / n);
+  return lc - 0.5 * lf;
+}
+// log B(a, b)  (nmath/lbeta.c; its lgammacor(x), x >= 10, is the same function as stirlerr(x))
+static __device__ __noinline__ double smc_lbeta(double a, double b) {
+  double p = fmin(a, b), q = fmax(a, b);
+  if (p < 0.0) return nan("");
+  if (p == 0.0) return INFINITY;
+  if (!isfinite(q)) return -INFINITY;
+  if (p >= 10.0) {
+    double corr = smc_stirlerr(p) + smc_stirlerr(q) - smc_stirlerr(p + q);
+    return log(q) * -0.5 + SMC_LOG_SQRT_2PI + corr + (p - 0.5) * log(p / (p + q)) + q * log1p(-p / (p + q));
+  }
+  if (q >= 10.0) {
+    double corr = smc_stirlerr(q) - smc_stirlerr(p + q);
+    return lgamma(p) + corr + p - p * log(p + q) + (q - 0.5) * log1p(-p / (p + q));
+  }
+  return log(tgamma(p) * (tgamma(q) / tgamma(p + q)));
+}
+// R_nonint
+__device__ __forceinline__ bool smc_nonint(double x) { return fabs(x - rint(x)) > 1e-7 * fmax(1.0, fabs(x)); }
+
 // per-element log density; argument order = the reference's logpdfD(params..., variate)
 __device__ __forceinline__ double smc_logpdf(int dist, double a0, double a1, double a2) {
   const double ninf = -INFINITY, qnan = nan("");
@@ -57,17 +140,22 @@ __device__ __forceinline__ double smc_logpdf(int dist, double a0, double a1, dou
       return -t2 + log(a0 * t1 / a1);
     }
     case SMC_DIST_BINOMIAL: {  // (n, p, x)  dbinom
-      if (!(a1 >= 0.0 && a1 <= 1.0) || a0 < 0.0 || a0 != rint(a0)) return qnan;
-      if (a2 < 0.0 || a2 > a0 || a2 != rint(a2)) return ninf;
-      double lc = lgamma(a0 + 1.0) - lgamma(a2 + 1.0) - lgamma(a0 - a2 + 1.0);
-      return lc + smc_xlogy(a2, a1) + smc_xlog1py(a0 - a2, -a1);
+      if (isnan(a0) || isnan(a1) || isnan(a2)) return qnan;
+      if (!(a1 >= 0.0 && a1 <= 1.0) || a0 < 0.0 || smc_nonint(a0)) return qnan;
+      if (a2 < 0.0 || smc_nonint(a2) || isinf(a2)) return ninf;
+      return smc_dbinom_raw(rint(a2), rint(a0), a1, 1.0 - a1);
     }
     case SMC_DIST_GAMMA: {  // (shape, scale, x)  dgamma
+      if (isnan(a0) || isnan(a1) || isnan(a2)) return qnan;
       if (a0 < 0.0 || !(a1 > 0.0)) return qnan;
       if (a2 < 0.0) return ninf;
       if (a0 == 0.0) return a2 == 0.0 ? INFINITY : ninf;
       if (a2 == 0.0) return a0 < 1.0 ? INFINITY : (a0 > 1.0 ? ninf : -log(a1));
-      return (a0 - 1.0) * log(a2) - a2 / a1 - lgamma(a0) - a0 * log(a1);
+      if (a0 < 1.0) {  // dpois_raw(shape, x/scale) * shape / x
+        double pr = smc_dpois_raw(a0, a2 / a1), r = a0 / a2;
+        return pr + (isfinite(r) ? log(r) : log(a0) - log(a2));
+      }
+      return smc_dpois_raw(a0 - 1.0, a2 / a1) - log(a1);
     }
     case SMC_DIST_CAUCHY: {  // (location, scale, x)  dcauchy
       if (!(a1 > 0.0)) return qnan;
@@ -81,19 +169,37 @@ __device__ __forceinline__ double smc_logpdf(int dist, double a0, double a1, dou
       return -(SMC_LOG_SQRT_2PI + 0.5 * y * y + log(a2 * a1));
     }
     case SMC_DIST_BETA: {  // (a, b, x)  dbeta
+      if (isnan(a0) || isnan(a1) || isnan(a2)) return qnan;
       if (!(a0 > 0.0) || !(a1 > 0.0)) return qnan;
       if (a2 < 0.0 || a2 > 1.0) return ninf;
       if (a2 == 0.0) return a0 > 1.0 ? ninf : (a0 < 1.0 ? INFINITY : log(a1));
       if (a2 == 1.0) return a1 > 1.0 ? ninf : (a1 < 1.0 ? INFINITY : log(a0));
-      return lgamma(a0 + a1) - lgamma(a0) - lgamma(a1) + smc_xlogy(a0 - 1.0, a2) + smc_xlog1py(a1 - 1.0, -a2);
+      if (a0 <= 2.0 || a1 <= 2.0)
+        return (a0 - 1.0) * log(a2) + (a1 - 1.0) * log1p(-a2) - smc_lbeta(a0, a1);
+      return log(a0 + a1 - 1.0) + smc_dbinom_raw(a0 - 1.0, a0 + a1 - 2.0, a2, 1.0 - a2);
     }
     case SMC_DIST_POISSON:  // (lambda, x)  dpois
-      if (a0 < 0.0) return qnan;
-      if (a1 < 0.0 || a1 != rint(a1)) return ninf;
-      return smc_xlogy(a1, a0) - a0 - lgamma(a1 + 1.0);
-    case SMC_DIST_TDIST:  // (df, x)  dt
-      if (!(a0 > 0.0)) return qnan;
-      return lgamma((a0 + 1.0) * 0.5) - lgamma(a0 * 0.5) - 0.5 * log(a0 * SMC_PI) - (a0 + 1.0) * 0.5 * log1p(a1 * a1 / a0);
+      if (isnan(a0) || isnan(a1) || a0 < 0.0) return qnan;
+      if (a1 < 0.0 || smc_nonint(a1) || isinf(a1)) return ninf;
+      return smc_dpois_raw(rint(a1), a0);
+    case SMC_DIST_TDIST: {  // (df, x)  dt
+      if (isnan(a1) || !(a0 > 0.0)) return qnan;
+      if (isinf(a1)) return ninf;
+      if (isinf(a0)) return -(SMC_LOG_SQRT_2PI + 0.5 * a1 * a1);
+      double t = -smc_bd0(a0 * 0.5, (a0 + 1.0) * 0.5) + smc_stirlerr((a0 + 1.0) * 0.5) - smc_stirlerr(a0 * 0.5);
+      double x2n = a1 * a1 / a0, l_x2n, u;
+      if (x2n > 1.0 / SMC_DBL_EPS) {
+        l_x2n = log(fabs(a1)) - log(a0) * 0.5;
+        u = a0 * l_x2n;
+      } else if (x2n > 0.2) {
+        l_x2n = log(1.0 + x2n) * 0.5;
+        u = a0 * l_x2n;
+      } else {
+        l_x2n = log1p(x2n) * 0.5;
+        u = -smc_bd0(a0 * 0.5, (a0 + a1 * a1) * 0.5) + a1 * a1 * 0.5;
+      }
+      return t - u - (SMC_LOG_SQRT_2PI + l_x2n);
+    }
     case SMC_DIST_EXPONENTIAL:  // (scale, x)  dexp
       if (!(a0 > 0.0)) return qnan;
       if (a1 < 0.0) return ninf;

@@ -196,23 +196,64 @@ struct GlmI8Args {
   double sigma;
 };
 
-template <int NB>      // beta slices: 7 (what has run) or 8
-__global__ void __launch_bounds__(NT, 1) k_glm_i8(GlmI8Args a) {
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ long long mad_wide(int a, int b, long long c) {
+  long long d;
+  asm("mad.wide.s32 %0, %1, %2, %3;\n" : "=l"(d) : "r"(a), "r"(b), "l"(c));
+  return d;
+}
+// the group sums as two exact int64 halves: hi = sum_{g<4} a[g] 2^(8 (3 - g)), lo = the remaining groups likewise
+template <int NB>
+__device__ __forceinline__ void halves(const int32_t* a, long long& hi, long long& lo) {
+  hi = mad_wide(a[0], 1 << 24, mad_wide(a[1], 1 << 16, mad_wide(a[2], 1 << 8, (long long)a[3])));
+  if (NB == 8) lo = mad_wide(a[4], 1 << 24, mad_wide(a[5], 1 << 16, mad_wide(a[6], 1 << 8, (long long)a[7])));
+  else lo = mad_wide(a[4], 1 << 16, mad_wide(a[5], 1 << 8, (long long)a[6]));
+}
+// adjoint slices in shared memory, MN-major for product 2 (B operand, N = 32 j + chain contiguous, K = rows):
+// 128-byte core matrices [row group r>>3][n chunk n>>4][row r&7][n&15]; SBO (along N) = 128, LBO (along K) = QD_LBO
+constexpr int QD_N = NS8 * NC;                       // 224 stacked columns
+constexpr uint32_t QD_LBO = (QD_N / 16) * 128;       // 1792
+constexpr uint32_t QD_BUF = (TR / 8) * QD_LBO;       // 28672 bytes per buffer
+constexpr uint32_t SMEM_V10 = 2 * XT_BYTES + QB_BYTES + 2 * QD_BUF;
+constexpr int NE = 512, NTI = 544, NWE = NE / 32;    // epilogue threads, threads with the issuer warp, epilogue warps
+constexpr int FLUSH_TILES = 64;                      // 7 pairs x 128 rows x 2^14 < 2^24 per tile and group: 64 tiles < 2^30
+constexpr unsigned int E_MIN = 64u, E_MAX = 1900u;
+
+// One CTA = 32 chains x a range of 128-row tiles.  Warps 0..15: epilogues (thread = TMEM lane x chain quarter);
+// warp 16: bulk copies of X tiles and every tensor instruction.
+//   product 1 (t):   eta slices-sums -> TMEM columns [0, 32 NB)
+//   epilogue 1 (t):  w = eta - y in registers, sum w^2, exponent of max |w| per chain -> shared memory
+//   barrier (A)      (epilogue threads only) ... the issuer may overwrite accumulator set 1 with product 1 (t+1)
+//   slicing (t):     w against the chain's STICKY power-of-two scale -> seven int8 slices, stored MN-major as seven 8-byte words
+//   product 2 (t):   ACCUMULATES in TMEM columns [256, 480) over consecutive tiles; it is read back (epilogue 2: one FP64
+//                    recombination per group sum) only when a chain's scale has to grow, every FLUSH_TILES tiles (int32 range)
+//                    and at the end.  A scale grows to one binade above the tile maximum that exceeded it, so growth is rare
+//                    (the running maximum of |w| over rows grows like sqrt(log n)); the cost is at most two of the 56 bits.
+template <int NB>      // beta slices: 7 or 8
+__global__ void __maxnreg__(120) k_glm_i8(GlmI8Args a) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t bar1, bar2, barX[2];
+  __shared__ uint64_t bar1, bar2[2], barX[2], barA, barB;
   __shared__ uint32_t tmem_slot;
-  __shared__ double s_sb[NC], s_f[NC];
-  __shared__ unsigned int s_max[2][NC];
+  __shared__ double s_f[NC];
+  __shared__ double2 s_sc[NC];                       // (s 2^-36, s 2^-60 or 2^-68): recombination scales of eta
+  __shared__ unsigned int s_max[4][NC];              // high word of max |w| per chain, buffer = tile mod 4
+  __shared__ int s_flag[4];                          // some chain's tile maximum exceeded its sticky scale
   __shared__ int s_badc[NC];
   uint8_t* sX = smem;
   uint8_t* sQB = smem + 2 * XT_BYTES;
   uint8_t* sQD = sQB + QB_BYTES;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, rl = tid & 127, q = tid >> 7;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, rl = tid & 127, q = (tid >> 7) & 3;
+  const bool issuer = warp == NWE;
   const long long c0 = (long long)blockIdx.x * NC;
   const long long t_begin = a.tiles * blockIdx.y / a.splits, t_end = a.tiles * (blockIdx.y + 1) / a.splits;
 
   if (warp == 0) tmem_alloc(&tmem_slot, 512);
-  if (tid == 32) { mbar_init(&bar1, 1); mbar_init(&bar2, 1); mbar_init(&barX[0], 1); mbar_init(&barX[1], 1); }
+  if (tid == 32) {
+    mbar_init(&bar1, 1); mbar_init(&bar2[0], 1); mbar_init(&bar2[1], 1); mbar_init(&barX[0], 1); mbar_init(&barX[1], 1);
+    mbar_init(&barA, NWE); mbar_init(&barB, NWE);
+  }
   if (tid < NC) {
     double m = 0.0;
     int bad = 0;
@@ -223,19 +264,21 @@ __global__ void __launch_bounds__(NT, 1) k_glm_i8(GlmI8Args a) {
     }
     double sc, f;
     scale_of8(m, &sc, &f);
-    s_sb[tid] = a.sx * sc;
-    s_f[tid] = f;
+    const double s = a.sx * sc;                            // power of two
+    s_sc[tid] = make_double2(s * 0x1p-36, s * (NB == 8 ? 0x1p-68 : 0x1p-60));
+    s_f[tid] = NB == 8 ? f * 256.0 : f;
     s_badc[tid] = bad;
-    s_max[0][tid] = 0u;
-    s_max[1][tid] = 0u;
+#pragma unroll
+    for (int b = 0; b < 4; b++) s_max[b][tid] = 0u;
+    if (tid < 4) s_flag[tid] = 0;
   }
   __syncthreads();
-  for (int e = tid; e < NC * MP; e += NT) {
+  for (int e = tid; e < NC * MP; e += NTI) {
     const int c = e & (NC - 1), p = e / NC;
     double b = p < a.M ? a.beta[(long long)p * a.Cpad + c0 + c] : 0.0;
     if (s_badc[c]) b = 0.0;
     if (NB == 8) {
-      const unsigned long long w = slice8_word(b, s_f[c] * 256.0);
+      const unsigned long long w = slice8_word(b, s_f[c]);
       for (int j = 0; j < 8; j++) sQB[boff(j * NC + c, p, MP)] = (uint8_t)(w >> (8 * (7 - j)));
     } else {
       const unsigned long long w = slice7_word(b, s_f[c]);
@@ -247,162 +290,237 @@ __global__ void __launch_bounds__(NT, 1) k_glm_i8(GlmI8Args a) {
   __syncthreads();
   fence_after();
   const uint32_t tmem = tmem_slot;
-  const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
   const uint32_t qbs = smem_u32(sQB), qds = smem_u32(sQD), xs0 = smem_u32(sX);
-  const int ii = rl >> 6;
-  double gacc[CQ], lacc[CQ], d[CQ];
-#pragma unroll
-  for (int c = 0; c < CQ; c++) { gacc[c] = 0.0; lacc[c] = 0.0; d[c] = 0.0; }
   bool ok = true;
 
-  auto issue_p1 = [&](uint32_t xs) {
+  if (issuer) {
+    // ================= issuer warp: waits by the whole warp, bulk copies and tensor instructions by lane 0 =================
+    auto issue_p1 = [&](uint32_t xs) {
 #pragma unroll 1
-    for (int i = 0; i < NS8; i++) {
-      const uint32_t idesc = make_idesc(TR, NC * (NB - i), 0, 0);       // beta slices j <= NB - 1 - i
-      for (int ks = 0; ks < MP / 32; ks++)
-        mma_i8(tmem + (uint32_t)(i * NC), make_desc(xs + i * 512 + ks * 256, 128, 4096),
-               make_desc(qbs + ks * 256, 128, MP * 8), idesc, (i | ks) != 0);
+      for (int i = 0; i < NS8; i++) {
+        const uint32_t idesc = make_idesc(TR, NC * (NB - i), 0, 0);       // beta slices j <= NB - 1 - i
+        for (int ks = 0; ks < MP / 32; ks++)
+          mma_i8(tmem + (uint32_t)(i * NC), make_desc(xs + i * 512 + ks * 256, 128, 4096),
+                 make_desc(qbs + ks * 256, 128, MP * 8), idesc, (i | ks) != 0);
+      }
+      umma_commit(&bar1);
+    };
+    if (t_begin < t_end) {
+      if (lane == 0) {
+        bulk_load_tile(sX, a.QX + t_begin * (long long)XT_BYTES, &barX[0]);
+        if (t_begin + 1 < t_end) bulk_load_tile(sX + XT_BYTES, a.QX + (t_begin + 1) * (long long)XT_BYTES, &barX[1]);
+      }
+      ok = mbar_wait(&barX[0], 0);
+      fence_after();
+      if (lane == 0) issue_p1(xs0);
+      __syncwarp();
     }
-    umma_commit(&bar1);
-  };
-  // epilogue 1 of tile t (its product 1 is the k-th completion of bar1): eta, w = eta - y (registers), sum w^2, max |w|
-  auto epilogue1 = [&](long long t, long long k) -> bool {
-    const long long row = t * TR + rl;
-    const double yr = row < a.N ? a.y[row] : 0.0;
-    if (!mbar_wait(&bar1, (uint32_t)(k & 1))) return false;
-    fence_after();
-    const int st = (int)(k & 1);
-    unsigned int hw[CQ];
-    if (NB == 8) {
+    int cnt = -1;                                         // tiles accumulated in accumulator set 2 (-1: nothing yet)
+    for (long long t = t_begin; t < t_end && ok; t++) {
+      const long long k = t - t_begin;
+      const int stage = (int)(k & 1);
+      if (t + 1 < t_end) {                                // accumulator set 1 read by every epilogue warp: product 1 (t+1)
+        ok = mbar_wait(&barA, (uint32_t)(k & 1)) && mbar_wait(&barX[stage ^ 1], (uint32_t)(((k + 1) >> 1) & 1));
+        fence_after();
+        if (lane == 0) issue_p1(xs0 + (uint32_t)(stage ^ 1) * XT_BYTES);
+        __syncwarp();
+      }
+      ok = ok && mbar_wait(&barB, (uint32_t)(k & 1));     // adjoint slices in place (and accumulator set 2 read when flushing)
+      fence_after();
+      const int flag = *(volatile int*)&s_flag[k & 3];
+      const bool fresh = flag != 0 || cnt < 0 || cnt >= FLUSH_TILES;
+      if (fresh) cnt = 0;
+      cnt++;
+      if (lane == 0) {
+        const uint32_t xs = xs0 + (uint32_t)stage * XT_BYTES, qd = qds + (uint32_t)stage * QD_BUF;
+#pragma unroll 1
+        for (int i = 0; i < NS8; i += 2) {
+          const uint32_t idesc = make_idesc(128, NC * (NS8 - i), 1, 1);
+          for (int ks = 0; ks < TR / 32; ks++)
+            mma_i8(tmem + 256u + (uint32_t)(i * NC), make_desc(xs + i * 512 + ks * 16384, 4096, 128),
+                   make_desc(qd + ks * 4 * QD_LBO, QD_LBO, 128), idesc, ((i | ks) != 0 || !fresh) ? 1u : 0u);
+        }
+        umma_commit(&bar2[stage]);
+      }
+      __syncwarp();
+      if (t + 2 < t_end) {                                // this tile's X buffer is free once product 2 has completed
+        ok = ok && mbar_wait(&bar2[stage], (uint32_t)((k >> 1) & 1));
+        if (lane == 0) bulk_load_tile(sX + (size_t)stage * XT_BYTES, a.QX + (t + 2) * (long long)XT_BYTES, &barX[stage]);
+        __syncwarp();
+      }
+    }
+    if (!ok && lane == 0) *a.status = 2;
+  }
+
+  // ================= epilogue warps =================
+  const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+  const int ii = rl >> 6;
+  double gacc[CQ], lacc[CQ];
 #pragma unroll
-      for (int hf = 0; hf < 2; hf++) {                      // eight groups: four chains at a time (registers)
-        int32_t acc[8][4];
+  for (int c = 0; c < CQ; c++) { gacc[c] = 0.0; lacc[c] = 0.0; }
+  if (!issuer) {
+    double d[CQ];
+    unsigned int E[CQ];                                   // sticky exponents (biased) of this thread's eight chains: the
+                                                          // same values in every thread of the chain quarter
 #pragma unroll
-        for (int cb = 0; cb < 8; cb++) tmem_ld4_nowait(tmem + lane_base + (uint32_t)(cb * NC + q * CQ + hf * 4), acc[cb]);
+    for (int c = 0; c < CQ; c++) { d[c] = 0.0; E[c] = E_MIN; }
+    // epilogue 1 of tile t (its product 1 is the k-th completion of bar1): w = eta - y, sum w^2, max |w| -> s_max[k & 3]
+    auto epilogue1 = [&](long long t, long long k) -> bool {
+      const long long row = t * TR + rl;
+      const double yr = row < a.N ? a.y[row] : 0.0;
+      if (!mbar_wait(&bar1, (uint32_t)(k & 1))) return false;
+      fence_after();
+      unsigned int hw[CQ];
+#pragma unroll
+      for (int hf = 0; hf < 2; hf++) {                      // four chains at a time (registers)
+        int32_t acc[NB][4];
+#pragma unroll
+        for (int cb = 0; cb < NB; cb++) tmem_ld4_nowait(tmem + lane_base + (uint32_t)(cb * NC + q * CQ + hf * 4), acc[cb]);
         tmem_ld_wait();
 #pragma unroll
         for (int v = 0; v < 4; v++) {
           const int u = hf * 4 + v;
-          int32_t g[8];
+          int32_t g[NB];
 #pragma unroll
-          for (int cb = 0; cb < 8; cb++) g[cb] = acc[cb][v];
-          const double w = recombine8(g) * s_sb[q * CQ + u] - yr;
+          for (int cb = 0; cb < NB; cb++) g[cb] = acc[cb][v];
+          long long hi, lo;
+          halves<NB>(g, hi, lo);
+          const double2 sc = s_sc[q * CQ + u];
+          const double w = fma((double)hi, sc.x, (double)lo * sc.y) - yr;
           d[u] = w;
           lacc[u] = fma(w, w, lacc[u]);
-          hw[u] = (unsigned int)__double2hiint(fabs(w));
+          hw[u] = (unsigned int)__double2hiint(w) & 0x7fffffffu;
         }
       }
-    } else {
-      int32_t acc[NS8][8];
 #pragma unroll
-      for (int cb = 0; cb < NS8; cb++) tmem_ld8_nowait(tmem + lane_base + (uint32_t)(cb * NC + q * CQ), acc[cb]);
-      tmem_ld_wait();
+      for (int u = 0; u < CQ; u++) hw[u] = __reduce_max_sync(0xffffffffu, hw[u]);
+      if (lane == 0) {
+        const int b = (int)(k & 3);
+        bool grow = false;
+#pragma unroll
+        for (int u = 0; u < CQ; u++) {
+          atomicMax(&s_max[b][q * CQ + u], hw[u]);
+          grow = grow || (hw[u] >> 20) > E[u];
+        }
+        if (grow) s_flag[b] = 1;
+      }
+      return true;
+    };
+    // epilogue 2 (a flush of accumulator set 2): thread = ((ii, parameter), chain quarter); scales = the sticky exponents
+    auto epilogue2 = [&]() {
+#pragma unroll
+      for (int hf = 0; hf < 2; hf++) {
+        int32_t acc[NS8][4];
+#pragma unroll
+        for (int cb = 0; cb < NS8; cb++) tmem_ld4_nowait(tmem + lane_base + 256u + (uint32_t)(cb * NC + q * CQ + hf * 4), acc[cb]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int v = 0; v < 4; v++) {
+          const int u = hf * 4 + v;
+          int32_t g[NS8];
+#pragma unroll
+          for (int cb = 0; cb < NS8; cb++) g[cb] = acc[cb][v];
+          long long hi, lo;
+          halves<7>(g, hi, lo);
+          const double sc = a.sx * __longlong_as_double((long long)((unsigned long long)(E[u] + 1u) << 52));
+          gacc[u] = fma(fma((double)hi, ii ? 0x1p-44 : 0x1p-36, (double)lo * (ii ? 0x1p-68 : 0x1p-60)), sc, gacc[u]);
+        }
+      }
+    };
+    if (t_begin < t_end) ok = epilogue1(t_begin, 0);
+    int cnt = -1;
+    for (long long t = t_begin; t < t_end && ok; t++) {
+      const long long k = t - t_begin;
+      const int b = (int)(k & 3), stage = (int)(k & 1);
+      fence_before();
+      asm volatile("bar.sync 1, 512;\n" ::: "memory");      // (A) maxima and flag of tile t complete (epilogue threads only)
+      if (lane == 0) mbar_arrive(&barA);                    // accumulator set 1 has been read by this warp
+      // buffers of tile t+2: last read (by the issuer) before it issued product 1 of tile t+2, which epilogue 1 of tile t+2
+      // needs; next written in epilogue 1 of tile t+2, after barrier (A) of tile t+1
+      if (tid < NC) s_max[(k + 2) & 3][tid] = 0u;
+      if (tid == NC) s_flag[(k + 2) & 3] = 0;
+      const bool fresh = s_flag[b] != 0 || cnt < 0 || cnt >= FLUSH_TILES;
+      if (fresh) {
+        if (cnt > 0) {                                      // read the accumulated products back with the scales they were made with
+          if (!mbar_wait(&bar2[stage ^ 1], (uint32_t)(((k - 1) >> 1) & 1))) { ok = false; break; }
+          fence_after();
+          epilogue2();
+        }
+#pragma unroll
+        for (int u = 0; u < CQ; u++) {
+          unsigned int e = min(s_max[b][q * CQ + u] >> 20, E_MAX);
+          if (e > E[u]) E[u] = e + 1u;
+        }
+        cnt = 0;
+      }
+      cnt++;
+      // this tile's slice buffer was last read by product 2 of tile t-2
+      if (k >= 2 && !mbar_wait(&bar2[stage], (uint32_t)(((k - 2) >> 1) & 1))) { ok = false; break; }
+      uint32_t xl[CQ], xh[CQ];
 #pragma unroll
       for (int u = 0; u < CQ; u++) {
-        int32_t g[NS8];
-#pragma unroll
-        for (int cb = 0; cb < NS8; cb++) g[cb] = acc[cb][u];
-        const double w = recombine7(g, 0) * s_sb[q * CQ + u] - yr;
-        d[u] = w;
-        lacc[u] = fma(w, w, lacc[u]);
-        hw[u] = (unsigned int)__double2hiint(fabs(w));
+        const double f = __longlong_as_double((long long)((unsigned long long)(2099u - E[u]) << 52));   // 2^54 / scale
+        const unsigned long long w = slice7_word(d[u], f);  // byte k = slice 6 - k
+        xl[u] = (uint32_t)w;
+        xh[u] = (uint32_t)(w >> 32);
       }
-    }
+      // 8 x 8 byte transpose: word pair j = slice j of chains 8q .. 8q+7
+      uint8_t* dst = sQD + (size_t)stage * QD_BUF + (uint32_t)(rl >> 3) * QD_LBO + (uint32_t)(rl & 7) * 16 +
+                     (uint32_t)(q >> 1) * 128 + (uint32_t)(q & 1) * 8;
+      {
+        uint32_t lo4[4], hi4[4];
 #pragma unroll
-    for (int u = 0; u < CQ; u++) hw[u] = __reduce_max_sync(0xffffffffu, hw[u]);
-    if (lane == 0) {
+        for (int h = 0; h < 2; h++) {                       // h = 0: bytes 0..3 (slices 6..3); h = 1: bytes 4..6 (slices 2..0)
+          const uint32_t* x = h ? xh : xl;
 #pragma unroll
-      for (int u = 0; u < CQ; u++) atomicMax(&s_max[st][q * CQ + u], hw[u]);
-    }
-    return true;
-  };
-  if (tid == 0 && t_begin < t_end) {
-    bulk_load_tile(sX, a.QX + t_begin * (long long)XT_BYTES, &barX[0]);
-    if (t_begin + 1 < t_end) bulk_load_tile(sX + XT_BYTES, a.QX + (t_begin + 1) * (long long)XT_BYTES, &barX[1]);
-    if (!mbar_wait(&barX[0], 0)) *a.status = 2;
-    fence_after();
-    issue_p1(xs0);
-  }
-  if (t_begin < t_end) ok = epilogue1(t_begin, 0);
-
-  for (long long t = t_begin; t < t_end && ok; t++) {
-    const long long k = t - t_begin;
-    const int stage = (int)(k & 1);
-    fence_before();
-    __syncthreads();                                      // (A) maxima of tile t complete; accumulator set 1 has been read
-    if (tid == 0 && t + 1 < t_end) {                      // product 1 of tile t+1 runs under the slicing of tile t
-      if (!mbar_wait(&barX[stage ^ 1], (uint32_t)(((k + 1) >> 1) & 1))) *a.status = 2;
-      fence_after();
-      issue_p1(xs0 + (uint32_t)(stage ^ 1) * XT_BYTES);
-    }
-    if (tid >= NT - NC) s_max[stage ^ 1][tid - (NT - NC)] = 0u;
+          for (int half = 0; half < 2; half++) {
+            const uint32_t x0 = x[half * 4], x1 = x[half * 4 + 1], x2 = x[half * 4 + 2], x3 = x[half * 4 + 3];
+            const uint32_t t0 = __byte_perm(x0, x1, 0x5140), t1 = __byte_perm(x2, x3, 0x5140);
+            const uint32_t t2 = __byte_perm(x0, x1, 0x7362), t3 = __byte_perm(x2, x3, 0x7362);
+            uint32_t* o = half ? hi4 : lo4;
+            o[0] = __byte_perm(t0, t1, 0x5410);
+            o[1] = __byte_perm(t0, t1, 0x7632);
+            o[2] = __byte_perm(t2, t3, 0x5410);
+            o[3] = __byte_perm(t2, t3, 0x7632);
+          }
 #pragma unroll
-    for (int c = 0; c < CQ; c++) {
-      unsigned int E = (s_max[stage][q * CQ + c] >> 20) & 0x7ffu;
-      if (E < 64u || E > 1900u) E = 1022u;
-      const unsigned long long w = slice7_bits(d[c], E);
-      const uint32_t wl = (uint32_t)w, wh = (uint32_t)(w >> 32);
-      uint8_t* dst = sQD + boff(q * CQ + c, rl, TR);      // slice j at + j * NC rows
-      dst[0 * NC * TR] = (uint8_t)(wh >> 16);
-      dst[1 * NC * TR] = (uint8_t)(wh >> 8);
-      dst[2 * NC * TR] = (uint8_t)wh;
-      dst[3 * NC * TR] = (uint8_t)(wl >> 24);
-      dst[4 * NC * TR] = (uint8_t)(wl >> 16);
-      dst[5 * NC * TR] = (uint8_t)(wl >> 8);
-      dst[6 * NC * TR] = (uint8_t)wl;
-    }
-    fence_async_smem();
-    fence_before();
-    __syncthreads();                                      // (B) adjoint slices visible; accumulator set 2 free
-    if (tid == 0) {
-      fence_after();
-      const uint32_t xs = xs0 + (uint32_t)stage * XT_BYTES;
-#pragma unroll 1
-      for (int i = 0; i < NS8; i += 2) {
-        const uint32_t idesc = make_idesc(128, NC * (NS8 - i), 1, 0);
-        for (int ks = 0; ks < TR / 32; ks++)
-          mma_i8(tmem + 256u + (uint32_t)(i * NC), make_desc(xs + i * 512 + ks * 16384, 4096, 128),
-                 make_desc(qds + ks * 256, 128, TR * 8), idesc, (i | ks) != 0);
+          for (int kb = 0; kb < (h ? 3 : 4); kb++) {
+            const int j = 6 - (h * 4 + kb);
+            *(uint2*)(dst + j * 256) = make_uint2(lo4[kb], hi4[kb]);
+          }
+        }
       }
-      umma_commit(&bar2);
+      fence_async_smem();
+      fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&barB);                    // (B) this warp's slices are visible (and its flush reads are done)
+      if (t + 1 < t_end) ok = epilogue1(t + 1, k + 1);      // under product 2 of tile t
     }
-    if (t + 1 < t_end) ok = epilogue1(t + 1, k + 1);      // under product 2 of tile t
-    if (!mbar_wait(&bar2, (uint32_t)(k & 1))) ok = false;
-    fence_after();
-    if (!ok) break;
-    if (tid == 0 && t + 2 < t_end)
-      bulk_load_tile(sX + (size_t)stage * XT_BYTES, a.QX + (t + 2) * (long long)XT_BYTES, &barX[stage]);
-    // ---- epilogue 2 of tile t: thread = ((ii, parameter), chain group) ----
-    int32_t acc[NS8][8];
-#pragma unroll
-    for (int cb = 0; cb < NS8; cb++) tmem_ld8_nowait(tmem + lane_base + 256u + (uint32_t)(cb * NC + q * CQ), acc[cb]);
-    tmem_ld_wait();
-#pragma unroll
-    for (int u = 0; u < CQ; u++) {
-      int32_t g[NS8];
-#pragma unroll
-      for (int cb = 0; cb < NS8; cb++) g[cb] = acc[cb][u];
-      const unsigned int E = (s_max[stage][q * CQ + u] >> 20) & 0x7ffu;    // zeroed only after barrier (A) of tile t+1
-      double sc = 1.0;
-      if (E >= 64u && E <= 1900u) sc = __longlong_as_double((long long)((unsigned long long)(E + 1u) << 52));
-      gacc[u] = fma(recombine7(g, ii), a.sx * sc, gacc[u]);
+    if (ok && t_begin < t_end && cnt > 0) {                 // final flush
+      const long long k = t_end - 1 - t_begin;
+      if (mbar_wait(&bar2[k & 1], (uint32_t)((k >> 1) & 1))) {
+        fence_after();
+        epilogue2();
+      } else ok = false;
     }
+    if (!ok && rl == 0) *a.status = 1;
   }
-  if (!ok && rl == 0) *a.status = 1;
   // ---- partial block of this row split, in k_glm's layout and conventions:
   //      rows 0..63: X' dl/deta = -(X' w) / sigma^2;  row 64: -sum (w / sigma)^2 / 2 - n (log sigma + log sqrt(2 pi))
   fence_before();
   __syncthreads();
   double* sG = (double*)sQD;                              // [chain][64]
   double* sL = (double*)sX;                               // [chain][128]
-  if (ii == 1) {
+  if (!issuer) {
+    if (ii == 1) {
 #pragma unroll
-    for (int c = 0; c < CQ; c++) sG[(q * CQ + c) * MP + (rl & 63)] = gacc[c];
+      for (int c = 0; c < CQ; c++) sG[(q * CQ + c) * MP + (rl & 63)] = gacc[c];
+    }
+#pragma unroll
+    for (int c = 0; c < CQ; c++) sL[(q * CQ + c) * TR + rl] = lacc[c];
   }
-#pragma unroll
-  for (int c = 0; c < CQ; c++) sL[(q * CQ + c) * TR + rl] = lacc[c];
   __syncthreads();
-  if (ii == 0) {
+  if (!issuer && ii == 0) {
 #pragma unroll
     for (int c = 0; c < CQ; c++) sG[(q * CQ + c) * MP + rl] += gacc[c];
   }
@@ -411,20 +529,22 @@ __global__ void __launch_bounds__(NT, 1) k_glm_i8(GlmI8Args a) {
   const double nrows = (double)(r_end > r_begin ? r_end - r_begin : 0);
   const double lconst = nrows * (-log(a.sigma) - SMC_LOG_SQRT_2PI);
   double* part = a.part + (long long)blockIdx.y * (MP + 1) * a.Cpad;
-  for (int c = warp; c < NC; c += NT / 32) {              // fixed-order sum over the 128 rows
-    double ssum = 0.0;
+  if (!issuer) {
+    for (int c = warp; c < NC; c += NWE) {                  // fixed-order sum over the 128 rows
+      double ssum = 0.0;
 #pragma unroll
-    for (int kk = 0; kk < TR / 32; kk++) ssum += sL[c * TR + kk * 32 + lane];
+      for (int kk = 0; kk < TR / 32; kk++) ssum += sL[c * TR + kk * 32 + lane];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
-    if (lane == 0 && c0 + c < a.Cpad) {
-      double L = 0.5 * neg_inv_s2 * ssum + lconst;
-      if (s_badc[c]) L = -INFINITY;                       // the reduction flags the chain (glm_emit)
-      part[(long long)MP * a.Cpad + c0 + c] = L;
+      for (int o = 16; o > 0; o >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
+      if (lane == 0 && c0 + c < a.Cpad) {
+        double L = 0.5 * neg_inv_s2 * ssum + lconst;
+        if (s_badc[c]) L = -INFINITY;                       // the reduction flags the chain (glm_emit)
+        part[(long long)MP * a.Cpad + c0 + c] = L;
+      }
     }
   }
   __syncthreads();
-  for (int e = tid; e < NC * MP; e += NT) {
+  for (int e = tid; e < NC * MP; e += NTI) {
     const int c = e & (NC - 1), p = e / NC;
     if (c0 + c < a.Cpad) part[(long long)p * a.Cpad + c0 + c] = neg_inv_s2 * sG[c * MP + p];
   }
@@ -482,8 +602,8 @@ int smc_glm_i8_prepare(smc_model_s* m, SmcGlmPlan& g) {
   m->ctx->launches++;
   static SmcOncePerDevice once;
   if (once.first()) {
-    SMC_CUDA(cudaFuncSetAttribute(k_glm_i8<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    SMC_CUDA(cudaFuncSetAttribute(k_glm_i8<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    SMC_CUDA(cudaFuncSetAttribute(k_glm_i8<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_V10));
+    SMC_CUDA(cudaFuncSetAttribute(k_glm_i8<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_V10));
   }
   return SMC_OK;
 }
@@ -499,8 +619,8 @@ int smc_glm_i8_launch(smc_model_s* m, SmcGlmPlan& g, const double* beta, int64_t
   dim3 grid((unsigned)smc_glm_i8_chain_tiles(C), (unsigned)RS);
   static int beta8 = -1;
   if (beta8 < 0) { const char* e = getenv("SMC_GLM_I8_BETA8"); beta8 = (e && e[0] == '1') ? 1 : 0; }
-  if (beta8) k_glm_i8<8><<<grid, NT, SMEM_BYTES, st>>>(a);
-  else k_glm_i8<7><<<grid, NT, SMEM_BYTES, st>>>(a);
+  if (beta8) k_glm_i8<8><<<grid, NTI, SMEM_V10, st>>>(a);
+  else k_glm_i8<7><<<grid, NTI, SMEM_V10, st>>>(a);
   if (!g.i8_checked) {      // first (eager) launch: a tensor-core completion that never arrived is an error, not a wrong number
     g.i8_checked = 1;
     int status = 0;

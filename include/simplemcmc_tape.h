@@ -48,8 +48,15 @@ enum {
   SMC_OP_SCATTER_SET = 43, /* dst[idx[e]] = src[e]  -- the reference's ref adjoint (parsing.jl:277-281) */
   SMC_OP_SCATTER_ADD = 44, /* dst[idx[e]] += src[e] -- the corrected adjoint (TODO.md:11) */
   SMC_OP_GLM = 48,       /* fused  eta = X*beta ; L = sum_i l(eta_i, y_i) ; G = X' * dl/deta  (see smc_tape_stmt) */
-  SMC_OP_FUSED = 49      /* a run of elementwise / reducing statements over one index space, executed as one register
+  SMC_OP_FUSED = 49,     /* a run of elementwise / reducing statements over one index space, executed as one register
                             program (smc_prog_instr) without materialising its temporaries; aux0 = program, aux1 = n */
+  SMC_OP_AFFNORM = 50    /* affine residual into a Normal density (the pattern of examples/ornstein.jl:24-26):
+                              dst (+)= sum_e logpdfNormal(mu, sigma, r_e),  r_e = ((+-t_0) +- t_1) +- ...,  t_j = D_j[e] * s_j | s_j
+                            src = {mu, sigma} (scalars); aux1 = n; aux0 = index table holding the descriptor
+                              { T, reg(dL/dmu) | -1, reg(dL/dsigma) | -1,
+                                T x { kind (0: array * scalar, 1: scalar), sign (+1 | -1), array register | -1, element offset
+                                      into that array (a contiguous view), scalar register, reg(dL/ds_j) | -1 } }
+                            the adjoint registers are per-chain scalars written by the same launch */
 };
 
 /* program-only opcodes (besides the elementwise opcodes above, which then act on program-local registers) */

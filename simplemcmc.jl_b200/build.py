@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsimplemcmc_cuda.so")
-SOURCES = ["smc_core.cu", "vm_exec.cu", "glm_fused.cu", "glm_i8.cu", "samplers.cu", "smc_comm.cu", "smc_p2p.cu"]
+SOURCES = ["smc_core.cu", "vm_exec.cu", "glm_fused.cu", "glm_i8.cu", "samplers.cu", "smc_comm.cu", "smc_p2p.cu", "affnorm.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
               "-Xcompiler", "-fvisibility=default", "--use_fast_math=false"]
 

@@ -1,0 +1,368 @@
+// SMC_OP_AFFNORM: an affine residual into a Normal density, forward value and every adjoint sum in ONE launch.
+//
+//   L = sum_e logpdfNormal(mu, sigma, r_e),   r_e = (((+-t_0) +- t_1) +- ...),   t_j = D_j[e] * s_j  or  s_j
+//
+// with D_j parameter-independent arrays (or contiguous views of one: x[2:end] and x[1:end-1] are the SAME stream), and
+// s_j, mu, sigma per-chain scalars.  This is the shape of examples/ornstein.jl:24-26 (BASELINE configs[4]):
+//   resid = x[2:end] - x[1:end-1] * fac - mu * (1. - fac);   resid ~ Normal(0, sigma)
+// The reference evaluates it as three vector temporaries forward (src/parsing.jl:123-183 unfolding) and five backward
+// (src/diff.jl:29-45 for + - *, :94-99 for Normal); round 1 ran it through the register-program interpreter at 1-6 % of
+// the roofline.  Here r_e is computed in registers with the reference's roundings (one per * and per +-, no contraction),
+// and what the reverse sweep needs from the element loop are three kinds of sums, all linear in (r - mu):
+//   S2 = sum (r - mu)^2,   S_j = sum (r - mu) D_j[e]  (array terms whose scalar is differentiated),   S1 = sum (r - mu)
+// from which   L       = -S2 / (2 sigma^2) - n log sigma - n log sqrt(2 pi)                  (src/distribs.jl:23-28)
+//              dL/dmu  =  S1 / sigma^2            dL/dsigma = (S2 / sigma^2 - n) / sigma     (src/diff.jl:94-99)
+//              dL/ds_j = -sign_j S_j / sigma^2  (array term)   |   -sign_j S1 / sigma^2  (scalar term)
+// Two kernels over the same argument block:
+//   k_affnorm_stream<CT>  (C <= 31): thread = element, CT chains in registers, loads straight from global memory -- bound
+//                          by HBM: 8 n bytes per launch when the arrays are views of one vector;
+//   k_affnorm_chains<CT>  (C >= 32): thread = chain(s), the arrays go through shared memory as broadcast reads -- bound
+//                          by the FP64 pipe: 3 T + 2 (1 + sums) flop per element and chain.
+// Per-block partial sums are combined by the last block to finish (ticket counter), in block order: deterministic.
+#include "exec_common.cuh"
+
+namespace {
+
+constexpr int AFF_MAX_T = 4;
+constexpr int AFF_MAX_SUM = 6;       // S2, up to four S_j, S1
+
+struct AffArgs {
+  int T, nsum, s1_slot;
+  int kind[AFF_MAX_T];               // 0: D * s, 1: s
+  int slot[AFF_MAX_T];               // sum slot of an array term whose scalar has an adjoint, else -1
+  double sgn[AFF_MAX_T];
+  const double* D[AFF_MAX_T];
+  Opd s[AFF_MAX_T], mu, sigma;
+  long long n, C, cstride;           // cstride: chains covered by the grid (partial sums: [block][slot][cstride])
+  double* part;
+  unsigned int* counter;             // one ticket counter per chain group
+  Dst L;
+  int L_acc;
+  Dst adj[2 + AFF_MAX_T];            // dL/dmu, dL/dsigma, dL/ds_j
+  int has_adj[2 + AFF_MAX_T];
+};
+
+__device__ __forceinline__ double opd_scalar(const Opd& o, long long c) { return o.is_imm ? o.imm : o.p[c * o.sc]; }
+
+// the last block of a chain group finishes: (S2, S_j, S1) -> L and the adjoint scalars of chain c
+__device__ __forceinline__ void aff_finish_chain(const AffArgs& a, long long c, const double* S) {
+  const double sigma = opd_scalar(a.sigma, c);
+  const double inv_s2 = 1.0 / (sigma * sigma), nn = (double)a.n;
+  double L = -0.5 * S[0] * inv_s2 - nn * log(sigma) - nn * SMC_LOG_SQRT_2PI;
+  if (!(sigma > 0.0)) L = nan("");                                   // src/distribs.jl:25 asserts; here: chain out of support
+  double* lp = a.L.p + c * a.L.sc;
+  *lp = a.L_acc ? *lp + L : L;
+  const double s1 = a.s1_slot >= 0 ? S[a.s1_slot] : 0.0;
+  if (a.has_adj[0]) a.adj[0].p[c * a.adj[0].sc] = s1 * inv_s2;
+  if (a.has_adj[1]) a.adj[1].p[c * a.adj[1].sc] = (S[0] * inv_s2 - nn) / sigma;
+#pragma unroll
+  for (int j = 0; j < AFF_MAX_T; j++)
+    if (j < a.T && a.has_adj[2 + j]) {
+      const double sj = a.kind[j] == 0 ? S[a.slot[j]] : s1;
+      a.adj[2 + j].p[c * a.adj[2 + j].sc] = -a.sgn[j] * sj * inv_s2;
+    }
+}
+
+__device__ __forceinline__ bool aff_take_ticket(unsigned int* counter, unsigned int nblocks) {
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(counter, 1u);
+    s_last = (t == nblocks - 1u);
+    if (s_last) *counter = 0u;                                        // ready for the next launch (graph replays)
+  }
+  __syncthreads();
+  if (s_last) __threadfence();
+  return s_last != 0;
+}
+
+// ---- few chains: thread = element, CT chains in registers ----------------------------------------------------------------
+template <int CT>
+__global__ void __launch_bounds__(256) k_affnorm_stream(AffArgs a) {
+  constexpr int U = (CT <= 2) ? 8 : 4;                               // elements in flight per thread
+  const int tid = threadIdx.x;
+  const long long c0 = (long long)blockIdx.y * CT;
+  double sc[AFF_MAX_T][CT], mu[CT];
+#pragma unroll
+  for (int c = 0; c < CT; c++) {
+    const long long ch = c0 + c < a.C ? c0 + c : a.C - 1;             // padding lanes repeat the last chain
+    mu[c] = opd_scalar(a.mu, ch);
+#pragma unroll
+    for (int j = 0; j < AFF_MAX_T; j++) sc[j][c] = j < a.T ? a.sgn[j] * opd_scalar(a.s[j], ch) : 0.0;
+  }
+  double acc[AFF_MAX_SUM][CT];
+#pragma unroll
+  for (int k = 0; k < AFF_MAX_SUM; k++)
+#pragma unroll
+    for (int c = 0; c < CT; c++) acc[k][c] = 0.0;
+
+  const long long stride = (long long)gridDim.x * 256 * U;
+  for (long long e0 = (long long)blockIdx.x * 256 * U + tid; e0 < a.n; e0 += stride) {
+    double dv[AFF_MAX_T][U];
+#pragma unroll
+    for (int j = 0; j < AFF_MAX_T; j++)
+      if (j < a.T && a.kind[j] == 0) {
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const long long e = e0 + (long long)u * 256;
+          dv[j][u] = e < a.n ? __ldg(a.D[j] + e) : 0.0;
+        }
+      }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      if (e0 + (long long)u * 256 < a.n) {
+#pragma unroll
+        for (int c = 0; c < CT; c++) {
+          double v = a.kind[0] == 0 ? __dmul_rn(dv[0][u], sc[0][c]) : sc[0][c];
+#pragma unroll
+          for (int j = 1; j < AFF_MAX_T; j++)
+            if (j < a.T) v = __dadd_rn(v, a.kind[j] == 0 ? __dmul_rn(dv[j][u], sc[j][c]) : sc[j][c]);
+          const double d = __dsub_rn(v, mu[c]);
+          acc[0][c] = fma(d, d, acc[0][c]);
+#pragma unroll
+          for (int j = 0; j < AFF_MAX_T; j++)
+            if (j < a.T && a.slot[j] >= 0) acc[1 + j][c] = fma(d, dv[j][u], acc[1 + j][c]);
+          acc[AFF_MAX_SUM - 1][c] += d;
+        }
+      }
+    }
+  }
+  // block reduction in a fixed order: lanes (xor tree), then warps
+  __shared__ double s_red[8][AFF_MAX_SUM * CT];
+  const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+  for (int k = 0; k < AFF_MAX_SUM; k++)
+#pragma unroll
+    for (int c = 0; c < CT; c++) {
+      double v = acc[k][c];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) s_red[warp][k * CT + c] = v;
+    }
+  __syncthreads();
+  // per-block partial, compacted to the slots in use: [block][slot][cstride]
+  if (tid < a.nsum * CT) {
+    const int slot = tid / CT, c = tid % CT;
+    int k = slot;                                                     // slot -> accumulator row
+    if (slot > 0) {
+      k = AFF_MAX_SUM - 1;
+      for (int j = 0; j < AFF_MAX_T; j++)
+        if (j < a.T && a.slot[j] == slot) k = 1 + j;
+    }
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) v += s_red[w][k * CT + c];
+    a.part[((long long)blockIdx.x * a.nsum + slot) * a.cstride + c0 + c] = v;
+  }
+  if (!aff_take_ticket(a.counter + blockIdx.y, gridDim.x)) return;
+  // last block of this chain group: warp w sums values w, w + 8, ...; lane l takes blocks l, l + 32, ...
+  __shared__ double s_tot[AFF_MAX_SUM * CT];
+  for (int v = warp; v < a.nsum * CT; v += 8) {
+    const int slot = v / CT, c = v % CT;
+    double t = 0.0;
+    for (unsigned int b = lane; b < gridDim.x; b += 32) t += __ldcg(a.part + ((long long)b * a.nsum + slot) * a.cstride + c0 + c);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == 0) s_tot[v] = t;
+  }
+  __syncthreads();
+  if (tid < CT && c0 + tid < a.C) {
+    double S[AFF_MAX_SUM];
+#pragma unroll
+    for (int k = 0; k < AFF_MAX_SUM; k++) S[k] = k < a.nsum ? s_tot[k * CT + tid] : 0.0;
+    aff_finish_chain(a, c0 + tid, S);
+  }
+}
+
+// ---- many chains: thread = CT chains, arrays broadcast from shared memory ---------------------------------------------------
+constexpr int AFF_TE = 1024;         // elements per shared-memory tile
+
+template <int CT>
+__global__ void __launch_bounds__(128) k_affnorm_chains(AffArgs a) {
+  extern __shared__ double s_tile[];                                 // [array terms][AFF_TE]
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const long long cb = ((long long)blockIdx.y * nthr + tid) * CT;
+  double sc[AFF_MAX_T][CT], mu[CT];
+#pragma unroll
+  for (int c = 0; c < CT; c++) {
+    const long long ch = cb + c < a.C ? cb + c : a.C - 1;
+    mu[c] = opd_scalar(a.mu, ch);
+#pragma unroll
+    for (int j = 0; j < AFF_MAX_T; j++) sc[j][c] = j < a.T ? a.sgn[j] * opd_scalar(a.s[j], ch) : 0.0;
+  }
+  double acc[AFF_MAX_SUM][CT];
+#pragma unroll
+  for (int k = 0; k < AFF_MAX_SUM; k++)
+#pragma unroll
+    for (int c = 0; c < CT; c++) acc[k][c] = 0.0;
+  int row[AFF_MAX_T];                                                // tile row of an array term
+  int nrow = 0;
+#pragma unroll
+  for (int j = 0; j < AFF_MAX_T; j++) row[j] = (j < a.T && a.kind[j] == 0) ? nrow++ : 0;
+
+  const long long per = (a.n + gridDim.x - 1) / gridDim.x;
+  const long long e_begin = (long long)blockIdx.x * per, e_end = e_begin + per < a.n ? e_begin + per : a.n;
+  for (long long te = e_begin; te < e_end; te += AFF_TE) {
+    const int len = (int)(e_end - te < AFF_TE ? e_end - te : AFF_TE);
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < AFF_MAX_T; j++)
+      if (j < a.T && a.kind[j] == 0)
+        for (int i = tid; i < AFF_TE; i += nthr) s_tile[row[j] * AFF_TE + i] = i < len ? __ldg(a.D[j] + te + i) : 0.0;
+    __syncthreads();
+    // (elements beyond len are zeros in every array: their r is the scalar terms only -- skipped by the loop bound)
+#pragma unroll 4
+    for (int i = 0; i < len; i++) {
+      double dv[AFF_MAX_T];
+#pragma unroll
+      for (int j = 0; j < AFF_MAX_T; j++)
+        if (j < a.T && a.kind[j] == 0) dv[j] = s_tile[row[j] * AFF_TE + i];
+#pragma unroll
+      for (int c = 0; c < CT; c++) {
+        double v = a.kind[0] == 0 ? __dmul_rn(dv[0], sc[0][c]) : sc[0][c];
+#pragma unroll
+        for (int j = 1; j < AFF_MAX_T; j++)
+          if (j < a.T) v = __dadd_rn(v, a.kind[j] == 0 ? __dmul_rn(dv[j], sc[j][c]) : sc[j][c]);
+        const double d = __dsub_rn(v, mu[c]);
+        acc[0][c] = fma(d, d, acc[0][c]);
+#pragma unroll
+        for (int j = 0; j < AFF_MAX_T; j++)
+          if (j < a.T && a.slot[j] >= 0) acc[1 + j][c] = fma(d, dv[j], acc[1 + j][c]);
+        acc[AFF_MAX_SUM - 1][c] += d;
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < CT; c++) {
+    double* p = a.part + (long long)blockIdx.x * a.nsum * a.cstride + cb + c;
+    p[0] = acc[0][c];
+#pragma unroll
+    for (int j = 0; j < AFF_MAX_T; j++)
+      if (j < a.T && a.slot[j] >= 0) p[(long long)a.slot[j] * a.cstride] = acc[1 + j][c];
+    if (a.s1_slot >= 0) p[(long long)a.s1_slot * a.cstride] = acc[AFF_MAX_SUM - 1][c];
+  }
+  if (!aff_take_ticket(a.counter + blockIdx.y, gridDim.x)) return;
+#pragma unroll
+  for (int c = 0; c < CT; c++) {
+    if (cb + c >= a.C) continue;
+    double S[AFF_MAX_SUM];
+#pragma unroll
+    for (int k = 0; k < AFF_MAX_SUM; k++) S[k] = 0.0;
+    for (unsigned int b = 0; b < gridDim.x; b++)                      // block order: fixed
+      for (int k = 0; k < a.nsum; k++) S[k] += __ldcg(a.part + ((long long)b * a.nsum + k) * a.cstride + cb + c);
+    aff_finish_chain(a, cb + c, S);
+  }
+}
+
+}  // namespace
+
+// descriptor (an index table of the tape, see lowering.py::serialise):
+//   [T, reg(dL/dmu) | -1, reg(dL/dsigma) | -1, then per term: kind, sign, array reg | -1, offset, scalar reg, reg(dL/ds) | -1]
+int smc_aff_prepare(smc_model_s* m, SmcAffPlan& p) {
+  const smc_tape_stmt& s = m->stmts[p.stmt];
+  if (s.aux0 >= m->idx_host.size() || m->idx_host[s.aux0].size() < 3) { smc_set_error("tape: AFFNORM statement without a descriptor"); return SMC_ERR_INVALID; }
+  const std::vector<int32_t>& d = m->idx_host[s.aux0];
+  const int T = d[0];
+  if (T < 1 || T > AFF_MAX_T || (int)d.size() != 3 + 6 * T || s.nsrc != 2) { smc_set_error("tape: malformed AFFNORM descriptor"); return SMC_ERR_INVALID; }
+  const int64_t n = s.aux1;
+  const int nregs = (int)m->regs.size();
+  auto scalar_ok = [&](int r) { return r >= 0 && r < nregs && m->regs[r].numel == 1; };
+  auto out_ok = [&](int r) { return r == -1 || (scalar_ok(r) && m->regs[r].d.kind == SMC_REG_CHAIN); };
+  bool ok = scalar_ok((int)s.src[0]) && scalar_ok((int)s.src[1]) && out_ok(d[1]) && out_ok(d[2]) && n >= 1;
+  for (int j = 0; ok && j < T; j++) {
+    const int32_t* t = &d[3 + 6 * j];
+    ok = (t[0] == 0 || t[0] == 1) && (t[1] == 1 || t[1] == -1) && scalar_ok(t[4]) && out_ok(t[5]);
+    if (ok && t[0] == 0) {
+      ok = t[2] >= 0 && t[2] < nregs && t[3] >= 0;
+      if (ok) {
+        const SmcReg& r = m->regs[t[2]];
+        ok = (r.d.kind == SMC_REG_DATA || r.d.kind == SMC_REG_HDR) && (int64_t)t[3] + n <= r.numel;
+      }
+    }
+  }
+  if (!ok) { smc_set_error("tape: AFFNORM descriptor references a bad register"); return SMC_ERR_INVALID; }
+  p.desc = d;
+  if (!p.counter) {
+    SMC_CUDA(smc_dev_alloc(&p.counter, 4096 * sizeof(unsigned int), m->ctx->stream));
+    SMC_CUDA(cudaMemsetAsync(p.counter, 0, 4096 * sizeof(unsigned int), m->ctx->stream));
+  }
+  static SmcOncePerDevice once;
+  if (once.first()) {
+    SMC_CUDA(cudaFuncSetAttribute(k_affnorm_chains<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AFF_MAX_T * AFF_TE * 8));
+    SMC_CUDA(cudaFuncSetAttribute(k_affnorm_chains<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, AFF_MAX_T * AFF_TE * 8));
+  }
+  return SMC_OK;
+}
+
+void smc_aff_release(SmcAffPlan& p, cudaStream_t st) {
+  if (p.counter) smc_dev_free(p.counter, st);
+  p.counter = nullptr;
+}
+
+int smc_aff_launch(smc_model_s* m, SmcAffPlan& p, int64_t C) {
+  const smc_tape_stmt& s = m->stmts[p.stmt];
+  const std::vector<int32_t>& d = p.desc;
+  cudaStream_t st = m->ctx->stream;
+  AffArgs a;
+  memset(&a, 0, sizeof(a));
+  a.T = d[0];
+  a.n = s.aux1;
+  a.C = C;
+  a.mu = smc_make_opd(m, s.src[0]);
+  a.sigma = smc_make_opd(m, s.src[1]);
+  a.L = smc_make_dst(m, s.dst);
+  a.L_acc = (s.flags & SMC_F_ACC) ? 1 : 0;
+  int nsum = 1, narr = 0;
+  bool need_s1 = d[1] >= 0;
+  for (int k = 0; k < 2; k++)
+    if (d[1 + k] >= 0) { a.adj[k] = smc_make_dst(m, (uint32_t)d[1 + k]); a.has_adj[k] = 1; }
+  for (int j = 0; j < a.T; j++) {
+    const int32_t* t = &d[3 + 6 * j];
+    a.kind[j] = t[0];
+    a.sgn[j] = (double)t[1];
+    a.s[j] = smc_make_opd(m, (uint32_t)t[4]);
+    a.slot[j] = -1;
+    if (t[0] == 0) {
+      a.D[j] = m->regs[t[2]].dev + t[3];
+      narr++;
+      if (t[5] >= 0) a.slot[j] = nsum++;
+    } else if (t[5] >= 0) need_s1 = true;
+    if (t[5] >= 0) { a.adj[2 + j] = smc_make_dst(m, (uint32_t)t[5]); a.has_adj[2 + j] = 1; }
+  }
+  a.s1_slot = need_s1 ? nsum++ : -1;
+  a.nsum = nsum;
+  a.counter = p.counter;
+  const int sms = m->ctx->sm_count;
+  if (C < 32) {
+    const int CT = C <= 1 ? 1 : (C <= 2 ? 2 : (C <= 4 ? 4 : 8));
+    const int U = CT <= 2 ? 8 : 4;
+    const long long gy = (C + CT - 1) / CT;
+    long long gx = std::min<long long>((a.n + 256LL * U - 1) / (256LL * U), std::max<long long>(1, (long long)sms * 4 / gy));
+    a.cstride = gy * CT;
+    SMC_TRY(smc_scratch_reserve(m, gx * nsum * a.cstride));
+    a.part = m->scratch;
+    dim3 grid((unsigned)gx, (unsigned)gy);
+    if (CT == 1) k_affnorm_stream<1><<<grid, 256, 0, st>>>(a);
+    else if (CT == 2) k_affnorm_stream<2><<<grid, 256, 0, st>>>(a);
+    else if (CT == 4) k_affnorm_stream<4><<<grid, 256, 0, st>>>(a);
+    else k_affnorm_stream<8><<<grid, 256, 0, st>>>(a);
+  } else {
+    const int CT = C >= 2048 ? 2 : 1;
+    int nthr = 128;
+    while (nthr > 32 && (long long)(nthr / 2) * CT >= C) nthr >>= 1;
+    const long long gy = (C + (long long)nthr * CT - 1) / ((long long)nthr * CT);
+    if (gy > 4096) { smc_set_error("AFFNORM: too many chains for one launch"); return SMC_ERR_INVALID; }
+    long long gx = std::max<long long>(1, std::min<long long>((a.n + 2047) / 2048, ((long long)sms * 16 * 32 / nthr + gy - 1) / gy));
+    a.cstride = gy * nthr * CT;
+    SMC_TRY(smc_scratch_reserve(m, gx * nsum * a.cstride));
+    a.part = m->scratch;
+    dim3 grid((unsigned)gx, (unsigned)gy);
+    const size_t smem = (size_t)std::max(narr, 1) * AFF_TE * sizeof(double);
+    if (CT == 1) k_affnorm_chains<1><<<grid, nthr, smem, st>>>(a);
+    else k_affnorm_chains<2><<<grid, nthr, smem, st>>>(a);
+  }
+  m->ctx->launches++;
+  SMC_CUDA(cudaGetLastError());
+  return SMC_OK;
+}

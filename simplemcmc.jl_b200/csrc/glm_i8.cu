@@ -232,7 +232,7 @@ constexpr unsigned int E_MIN = 64u, E_MAX = 1900u;
 //                    and at the end.  A scale grows to one binade above the tile maximum that exceeded it, so growth is rare
 //                    (the running maximum of |w| over rows grows like sqrt(log n)); the cost is at most two of the 56 bits.
 template <int NB>      // beta slices: 7 or 8
-__global__ void __maxnreg__(120) k_glm_i8(GlmI8Args a) {
+__global__ void __launch_bounds__(NTI, 1) k_glm_i8(GlmI8Args a) {   // 17 warps are allocated as 20: 96 registers
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar1, bar2[2], barX[2], barA, barB;
   __shared__ uint32_t tmem_slot;
@@ -355,9 +355,11 @@ __global__ void __maxnreg__(120) k_glm_i8(GlmI8Args a) {
   // ================= epilogue warps =================
   const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
   const int ii = rl >> 6;
-  double gacc[CQ], lacc[CQ];
+  double lacc[CQ];
 #pragma unroll
-  for (int c = 0; c < CQ; c++) { gacc[c] = 0.0; lacc[c] = 0.0; }
+  for (int c = 0; c < CQ; c++) lacc[c] = 0.0;
+  const double neg_inv_s2 = -1.0 / (a.sigma * a.sigma);
+  double* part = a.part + (long long)blockIdx.y * (MP + 1) * a.Cpad;
   if (!issuer) {
     double d[CQ];
     unsigned int E[CQ];                                   // sticky exponents (biased) of this thread's eight chains: the
@@ -406,8 +408,13 @@ __global__ void __maxnreg__(120) k_glm_i8(GlmI8Args a) {
       }
       return true;
     };
-    // epilogue 2 (a flush of accumulator set 2): thread = ((ii, parameter), chain quarter); scales = the sticky exponents
+    // epilogue 2 (a flush of accumulator set 2): thread = ((ii, parameter), chain quarter); scales = the sticky exponents the
+    // products were made with.  The recombined sums go straight into this CTA's block of the partial buffer (rows 0..63:
+    // X' dl/deta = -(X' w) / sigma^2): the lanes with ii = 0 first, then -- after a barrier among the epilogue threads -- the
+    // lanes with ii = 1, which hold the groups shifted by one slice.  Fixed order, so the result is reproducible.
+    bool first_flush = true;
     auto epilogue2 = [&]() {
+      double val[CQ];
 #pragma unroll
       for (int hf = 0; hf < 2; hf++) {
         int32_t acc[NS8][4];
@@ -423,9 +430,20 @@ __global__ void __maxnreg__(120) k_glm_i8(GlmI8Args a) {
           long long hi, lo;
           halves<7>(g, hi, lo);
           const double sc = a.sx * __longlong_as_double((long long)((unsigned long long)(E[u] + 1u) << 52));
-          gacc[u] = fma(fma((double)hi, ii ? 0x1p-44 : 0x1p-36, (double)lo * (ii ? 0x1p-68 : 0x1p-60)), sc, gacc[u]);
+          val[u] = fma((double)hi, ii ? 0x1p-44 : 0x1p-36, (double)lo * (ii ? 0x1p-68 : 0x1p-60)) * (sc * neg_inv_s2);
         }
       }
+      double* gp = part + (long long)(rl & 63) * a.Cpad + c0 + q * CQ;
+      if (ii == 0) {
+#pragma unroll
+        for (int u = 0; u < CQ; u++) gp[u] = first_flush ? val[u] : gp[u] + val[u];
+      }
+      asm volatile("bar.sync 2, 512;\n" ::: "memory");
+      if (ii == 1) {
+#pragma unroll
+        for (int u = 0; u < CQ; u++) gp[u] += val[u];
+      }
+      first_flush = false;
     };
     if (t_begin < t_end) ok = epilogue1(t_begin, 0);
     int cnt = -1;
@@ -509,26 +527,15 @@ __global__ void __maxnreg__(120) k_glm_i8(GlmI8Args a) {
   //      rows 0..63: X' dl/deta = -(X' w) / sigma^2;  row 64: -sum (w / sigma)^2 / 2 - n (log sigma + log sqrt(2 pi))
   fence_before();
   __syncthreads();
-  double* sG = (double*)sQD;                              // [chain][64]
   double* sL = (double*)sX;                               // [chain][128]
   if (!issuer) {
-    if (ii == 1) {
-#pragma unroll
-      for (int c = 0; c < CQ; c++) sG[(q * CQ + c) * MP + (rl & 63)] = gacc[c];
-    }
 #pragma unroll
     for (int c = 0; c < CQ; c++) sL[(q * CQ + c) * TR + rl] = lacc[c];
   }
   __syncthreads();
-  if (!issuer && ii == 0) {
-#pragma unroll
-    for (int c = 0; c < CQ; c++) sG[(q * CQ + c) * MP + rl] += gacc[c];
-  }
-  const double neg_inv_s2 = -1.0 / (a.sigma * a.sigma);
   const long long r_begin = t_begin * TR, r_end = t_end * TR < a.N ? t_end * TR : a.N;
   const double nrows = (double)(r_end > r_begin ? r_end - r_begin : 0);
   const double lconst = nrows * (-log(a.sigma) - SMC_LOG_SQRT_2PI);
-  double* part = a.part + (long long)blockIdx.y * (MP + 1) * a.Cpad;
   if (!issuer) {
     for (int c = warp; c < NC; c += NWE) {                  // fixed-order sum over the 128 rows
       double ssum = 0.0;
@@ -543,10 +550,8 @@ __global__ void __maxnreg__(120) k_glm_i8(GlmI8Args a) {
       }
     }
   }
-  __syncthreads();
-  for (int e = tid; e < NC * MP; e += NTI) {
-    const int c = e & (NC - 1), p = e / NC;
-    if (c0 + c < a.Cpad) part[(long long)p * a.Cpad + c0 + c] = neg_inv_s2 * sG[c * MP + p];
+  if (t_begin >= t_end) {                                 // a row split without tiles still owns a block of the partial buffer
+    for (int e = tid; e < NC * MP; e += NTI) part[(long long)(e / NC) * a.Cpad + c0 + (e & (NC - 1))] = 0.0;
   }
   fence_before();
   __syncthreads();

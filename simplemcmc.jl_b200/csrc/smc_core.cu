@@ -164,6 +164,7 @@ extern "C" int smc_model_compile(smc_ctx_t ctx, const void* tape, size_t nbytes,
     bool ok = s.dst < h.n_regs && s.nsrc <= 4;
     for (uint32_t k = 0; ok && k < s.nsrc; k++) ok = s.src[k] < h.n_regs;
     if (s.op == SMC_OP_GLM) ok = ok && s.aux2 < h.n_regs && s.nsrc == 3;
+    if (s.op == SMC_OP_AFFNORM) ok = ok && s.nsrc == 2 && s.aux0 < h.n_idx;
     if (!ok) { smc_set_error("tape: statement %u references a register out of range", i); delete m; return SMC_ERR_INVALID; }
     uint32_t dk = m->regs[s.dst].d.kind;
     if (dk == SMC_REG_HDR) m->hdr_stmts.push_back((int)i);
@@ -197,6 +198,8 @@ extern "C" int smc_model_compile(smc_ctx_t ctx, const void* tape, size_t nbytes,
     int32_t* d = nullptr;
     SMC_CUDA(smc_dev_alloc(&d, std::max<size_t>(bytes, 8), ctx->stream));
     SMC_CUDA(smc_copy_sync(d, p, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    m->idx_host.emplace_back();
+    if (n <= 64) { m->idx_host.back().resize(n); memcpy(m->idx_host.back().data(), p, (size_t)n * 4); }
     p += bytes;
     m->idx_dev.push_back(d);
     m->idx_len.push_back(n);
@@ -251,6 +254,7 @@ extern "C" int smc_model_destroy(smc_model_t m) {
   for (auto& p : m->scatter) { smc_dev_free(p.ptr, m->ctx->stream); smc_dev_free(p.list, m->ctx->stream); }
   for (auto& p : m->sparse) { if (p.ptr) smc_dev_free(p.ptr, m->ctx->stream); if (p.col) smc_dev_free(p.col, m->ctx->stream); if (p.val) smc_dev_free(p.val, m->ctx->stream); }
   for (auto& g : m->glm) smc_glm_release(g, m->ctx->stream);
+  for (auto& a : m->aff) smc_aff_release(a, m->ctx->stream);
   for (auto& pr : m->programs) if (pr.dev_tables) smc_dev_free(pr.dev_tables, m->ctx->stream);
   if (m->beta) smc_dev_free(m->beta, m->ctx->stream);
   if (m->grad) smc_dev_free(m->grad, m->ctx->stream);
@@ -783,6 +787,12 @@ static int run_statement(smc_model_s* m, const smc_tape_stmt& s, int64_t C, bool
       smc_set_error("internal: GLM statement without a plan");
       return SMC_ERR_INVALID;
     }
+    case SMC_OP_AFFNORM: {
+      for (auto& p : m->aff)
+        if (&m->stmts[p.stmt] == &s) return smc_aff_launch(m, p, C);
+      smc_set_error("internal: AFFNORM statement without a plan");
+      return SMC_ERR_INVALID;
+    }
     default: {
       EwArgs a;
       a.op = s.op; a.dist = s.aux0; a.darg = s.aux1; a.nsrc = s.nsrc; a.acc = acc;
@@ -908,6 +918,16 @@ extern "C" int smc_model_finalize(smc_model_t m, int64_t max_chains, int row_sha
       g.stmt = si;
       SMC_TRY(smc_glm_prepare(m, g));
       m->glm.push_back(g);
+    }
+  for (auto& a : m->aff) smc_aff_release(a, m->ctx->stream);
+  m->aff.clear();
+  for (int si : m->body_stmts)
+    if (m->stmts[si].op == SMC_OP_AFFNORM) {
+      if (row_shard) { smc_set_error("row-sharded models: only GLM statements sum over the rows across ranks (AFFNORM does not)"); return SMC_ERR_INVALID; }
+      SmcAffPlan a;
+      a.stmt = si;
+      SMC_TRY(smc_aff_prepare(m, a));
+      m->aff.push_back(a);
     }
   SMC_CUDA(cudaStreamSynchronize(st));
   SMC_CUDA(cudaGetLastError());

@@ -108,6 +108,12 @@ struct SmcGlmPlan {  // one SMC_OP_GLM statement, prepared at finalize
   int i8_declined = 0;     // X holds NaN / Inf: the statement stays on the FP64 kernel
 };
 
+struct SmcAffPlan {  // one SMC_OP_AFFNORM statement (affnorm.cu)
+  int stmt = -1;
+  std::vector<int32_t> desc;        // host copy of the descriptor table
+  unsigned int* counter = nullptr;  // ticket counters of the last-block finish, one per chain group
+};
+
 // Micro-operation of the register-program VM (vm_exec.cu): the tape's LOADV/LOADS/STOREV/REDUCE instructions are
 // folded into operand modes / side effects of the computing instruction at plan time.
 enum { VM_NONE = 0, VM_LOCAL = 1, VM_SCAL = 2, VM_ARRAY = 3 };
@@ -184,6 +190,8 @@ struct smc_model_s {
   std::vector<SmcData> data;
   std::vector<int32_t*> idx_dev;
   std::vector<uint32_t> idx_len;
+  std::vector<std::vector<int32_t>> idx_host;   // host copies of the short tables (descriptors of AFFNORM statements)
+  std::vector<SmcAffPlan> aff;
   std::vector<SmcGlmPlan> glm;
   std::vector<SmcProgram> programs;
   std::vector<SmcScatterPlan> scatter;
@@ -224,6 +232,11 @@ int smc_vm_launch(smc_model_s* m, SmcProgram& pr, int64_t C, int* bad);
 int smc_glm_prepare(smc_model_s* m, SmcGlmPlan& g);
 int smc_glm_launch(smc_model_s* m, SmcGlmPlan& g, int64_t C);
 void smc_glm_release(SmcGlmPlan& g, cudaStream_t st);
+
+// affnorm.cu
+int smc_aff_prepare(smc_model_s* m, SmcAffPlan& p);
+int smc_aff_launch(smc_model_s* m, SmcAffPlan& p, int64_t C);
+void smc_aff_release(SmcAffPlan& p, cudaStream_t st);
 
 // smc_p2p.cu
 bool smc_p2p_ready(const smc_ctx_s* c, int64_t n);

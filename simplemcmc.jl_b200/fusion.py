@@ -47,8 +47,8 @@ class Group(object):
     def add(self, st):
         self.stmts.append(st)
         self.writes.add(st.dst.vid)
-        if st.op == L.OP["GLM"]:
-            self.writes.add(st.aux2.vid)
+        for v in st.extra_outs:
+            self.writes.add(v.vid)
         for s in st.srcs:
             self.reads.add(s.vid)
         if st.flags & L.F_ACC:
@@ -65,7 +65,7 @@ def form_groups(stmts):
         reads = {s.vid for s in st.srcs}
         if st.flags & L.F_ACC:
             reads.add(st.dst.vid)
-        writes = {st.dst.vid} | ({st.aux2.vid} if st.op == L.OP["GLM"] else set())
+        writes = {st.dst.vid} | {v.vid for v in st.extra_outs}
         gmin = 0
         for gi, g in enumerate(groups):
             if (g.writes & reads) or (g.writes & writes) or (g.reads & writes):
@@ -175,8 +175,8 @@ def external_inputs(g):
                 ext.add(s.vid)
         if (st.flags & L.F_ACC) and st.dst.vid not in written:
             ext.add(st.dst.vid)
-        if st.op == L.OP["GLM"]:
-            written.add(st.aux2.vid)
+        for v in st.extra_outs:
+            written.add(v.vid)
         if not is_reduce(st):
             written.add(st.dst.vid)
     return ext
@@ -268,8 +268,8 @@ def coalesce_accumulator(fwd, bwd, result):
         prod = {}
         for i, st in enumerate(fwd):
             prod.setdefault(st.dst.vid, []).append(i)
-            if st.op == L.OP["GLM"]:
-                prod.setdefault(st.aux2.vid, []).append(i)
+            for v in st.extra_outs:
+                prod.setdefault(v.vid, []).append(i)
         for i, st in enumerate(fwd):
             if st.op != L.OP["ADD"] or st.flags or st.dst.numel != 1 or st.dst.kind != L.REG_CHAIN:
                 continue
@@ -280,9 +280,9 @@ def coalesce_accumulator(fwd, bwd, result):
             if len(py) != 1 or not px or max(px) >= py[0] or py[0] >= i:
                 continue                      # y must have one producer, after every writer of x and before the sum
             p = fwd[py[0]]
-            if (p.flags & L.F_ACC) or p.dst is not y or not (fusable(p) or p.op == L.OP["GLM"]):
+            if (p.flags & L.F_ACC) or p.dst is not y or not (fusable(p) or p.op in (L.OP["GLM"], L.OP["AFFNORM"])):
                 continue
-            q = L.Stmt(p.op, x, p.srcs, flags=p.flags | L.F_ACC, aux0=p.aux0, aux1=p.aux1, aux2=p.aux2, imm=p.imm)
+            q = L.Stmt(p.op, x, p.srcs, flags=p.flags | L.F_ACC, aux0=p.aux0, aux1=p.aux1, aux2=p.aux2, imm=p.imm, desc=p.desc)
             fwd[py[0]] = q
             t = st.dst
             del fwd[i]
@@ -298,8 +298,8 @@ def coalesce_accumulator(fwd, bwd, result):
 
 def fuse(lowered):
     """-> (fwd, bwd, programs): statement lists in which runs of elementwise statements are FUSED statements"""
-    fwd0 = [L.Stmt(s.op, s.dst, s.srcs, flags=s.flags, aux0=s.aux0, aux1=s.aux1, aux2=s.aux2, imm=s.imm) for s in lowered.fwd]
-    bwd0 = [L.Stmt(s.op, s.dst, s.srcs, flags=s.flags, aux0=s.aux0, aux1=s.aux1, aux2=s.aux2, imm=s.imm) for s in lowered.bwd]
+    fwd0 = [s.copy() for s in lowered.fwd]
+    bwd0 = [s.copy() for s in lowered.bwd]
     fwd0, bwd0, lowered.tape_result = coalesce_accumulator(fwd0, bwd0, lowered.result)
     body_f = [s for s in fwd0 if s.dst.kind != L.REG_HDR]
     body_b = [s for s in bwd0 if s.dst.kind != L.REG_HDR]
@@ -318,7 +318,7 @@ def fuse(lowered):
         groups_now = gf + gb
         ext = [external_inputs(g) for g in groups_now]
         for gi, g in enumerate(groups_now):
-            if any(st.op == L.OP["GLM"] for st in g.stmts):
+            if any(st.op in (L.OP["GLM"], L.OP["AFFNORM"]) for st in g.stmts):
                 continue
             others = set().union(*[e for hj, e in enumerate(ext) if hj != gi]) if len(ext) > 1 else set()
             if any(st.dst.vid in always or st.dst.vid in others for st in g.stmts):

@@ -20,7 +20,8 @@ REG_IMM, REG_DATA, REG_HDR, REG_CHAIN, REG_PARAM, REG_GRAD = range(6)
 F_ACC, F_TRANS_A, F_TRANS_B = 1, 2, 4
 OP = dict(COPY=0, NEG=1, EXP=2, LOG=3, SIN=4, COS=5, ABS=6, SIGN=7, DIGAMMA=8, ZERO=9, SQRT=10,
           ADD=16, SUB=17, MUL=18, DIV=19, POW=20, MAX=21, MIN=22, GT=23, LT=24, GE=25, LE=26, EQ=27,
-          LOGPDF=32, DLOGPDF=33, MATMUL=40, TRANSPOSE=41, GATHER=42, SCATTER_SET=43, SCATTER_ADD=44, GLM=48)
+          LOGPDF=32, DLOGPDF=33, MATMUL=40, TRANSPOSE=41, GATHER=42, SCATTER_SET=43, SCATTER_ADD=44, GLM=48,
+          AFFNORM=50)
 DIST = dict(Normal=0, Uniform=1, Weibull=2, Beta=3, TDist=4, Exponential=5, Gamma=6, Cauchy=7, logNormal=8,
             Bernoulli=9, Binomial=10, Poisson=11, TestDiff=12)
 DIST_ARITY = dict(Normal=3, Uniform=3, Weibull=3, Beta=3, TDist=2, Exponential=2, Gamma=3, Cauchy=3, logNormal=3,
@@ -63,18 +64,44 @@ class Val(object):
 
 
 class Stmt(object):
-    __slots__ = ("op", "dst", "srcs", "flags", "aux0", "aux1", "aux2", "imm", "clone", "touched")
+    __slots__ = ("op", "dst", "srcs", "flags", "aux0", "aux1", "aux2", "imm", "clone", "touched", "desc")
 
-    def __init__(self, op, dst, srcs, flags=0, aux0=0, aux1=0, aux2=None, imm=0.0):
+    def __init__(self, op, dst, srcs, flags=0, aux0=0, aux1=0, aux2=None, imm=0.0, desc=None):
         self.op, self.dst, self.srcs, self.flags = op, dst, list(srcs), flags
         self.aux0, self.aux1, self.aux2, self.imm = aux0, aux1, aux2, imm
         self.clone, self.touched = False, None
+        self.desc = desc      # AFFNORM: AffNormDesc (terms, views, adjoint outputs)
+
+    @property
+    def extra_outs(self):
+        """registers a statement writes besides dst: G of a GLM statement, the adjoint scalars of an AFFNORM statement"""
+        if self.op == OP["GLM"]:
+            return [self.aux2]
+        if self.op == OP["AFFNORM"]:
+            return [v for v in self.desc.outs if v is not None]
+        return []
+
+    def copy(self):
+        st = Stmt(self.op, self.dst, self.srcs, flags=self.flags, aux0=self.aux0, aux1=self.aux1, aux2=self.aux2, imm=self.imm,
+                  desc=self.desc)
+        return st
 
     def __repr__(self):
         name = ([k for k, v in OP.items() if v == self.op] + ["FUSED"])[0]
         return "%r %s %s(%s)%s" % (self.dst, "+=" if self.flags & F_ACC else "=", name,
                                   ", ".join(repr(s) for s in self.srcs),
                                   "" if not (self.aux0 or self.aux1) else " aux=%s,%s" % (self.aux0, self.aux1))
+
+
+class AffNormDesc(object):
+    """SMC_OP_AFFNORM:  L = sum_e logpdfNormal(mu, sigma, r_e),  r_e = (((+-t_0) +- t_1) +- ...)  evaluated left to right with
+    one rounding per operation exactly as the reference's element loop does, t_j = D_j[e] * s_j (kind 0) or s_j (kind 1);
+    D_j = a parameter-independent array or a contiguous view (base array, offset) of one; s_j, mu, sigma scalars.
+    Statement sources = [mu, sigma, s_0, ..., s_{T-1}];  outs[k] = dL/d(source k) (a per-chain scalar) or None."""
+
+    def __init__(self, n, terms):
+        self.n, self.terms = n, terms          # terms: list of (kind, sign, base Val or None, offset)
+        self.outs = [None] * (2 + len(terms))
 
 
 class Param(object):
@@ -117,8 +144,10 @@ class Lowering(object):
             raise ModelError("Model outcome should be a scalar, Array found")
         self._check_params_used()
         self.n_fused = 0
+        self.n_affnorm = 0
         if fuse:
             self._fuse_glm()
+            self._fuse_affnorm()
         self.n_fwd = None
         if gradient:
             self._reverse_sweep()
@@ -610,6 +639,117 @@ class Lowering(object):
             return None
         return GLM_BERNOULLI, sign, 0.0, y, lp, dead
 
+    # ------------------------------------------------------------------ affine residual into a Normal density
+    AFFNORM_MIN_N = 2048
+
+    def _fuse_affnorm(self):
+        """`resid = D0 - D1 * s1 - s2; resid ~ Normal(mu, sigma)` (examples/ornstein.jl:24-26 and every model of that shape:
+        a variate built from parameter-independent arrays and per-chain scalars by + and -) becomes one AFFNORM statement:
+        one hand-written kernel reads the arrays once, keeps r_e in registers and returns the log-density together with
+        the sums the reverse sweep needs (src/diff.jl:94-99 for the Normal adjoints, :29-45 for + - *), instead of
+        three element-wise temporaries forward and five backward."""
+        for lp in list(self.fwd):
+            if lp.op != OP["LOGPDF"] or lp.aux0 != DIST["Normal"] or lp.flags or lp not in self.fwd:
+                continue
+            mu, sigma, x = lp.srcs
+            n = lp.aux1
+            if mu.is_array or sigma.is_array or not x.is_array or x.numel != n or not x.varying or n < self.AFFNORM_MIN_N:
+                continue
+            if self._single_use(x) is not lp:
+                continue
+            dead = []
+            terms = self._linearise(x, n, dead, top=True)
+            if terms is None or not (1 <= len(terms) <= 4) or not any(t[0] == 0 for t in terms):
+                continue
+            desc = AffNormDesc(n, [(k, sg, base, off) for (k, sg, base, off, sc) in terms])
+            srcs = [mu, sigma] + [t[4] for t in terms]
+            st = Stmt(OP["AFFNORM"], lp.dst, srcs, aux1=n, desc=desc)
+            self.fwd[self.fwd.index(lp)] = st
+            for d in dead:
+                self.fwd.remove(d)
+            self.n_affnorm += 1
+
+    def _view_of(self, v):
+        """a parameter-independent array as (array to read, element offset): a contiguous range of a data vector
+        (x[2:end]) is a view of that vector, so that x[2:end] and x[1:end-1] are read as ONE stream"""
+        if v.kind == REG_HDR:
+            st = self._producer(v)
+            if st is not None and st.op == OP["GATHER"] and not st.flags and st.srcs[0].kind == REG_DATA and len(st.srcs[0].shape) == 1:
+                idx = self.idx_tables[st.aux0]
+                if len(idx) == v.numel and len(idx) >= 1 and np.array_equal(idx, idx[0] + np.arange(len(idx), dtype=idx.dtype)):
+                    return st.srcs[0], int(idx[0])
+        return v, 0
+
+    def _linearise(self, v, n, dead, top=False):
+        """v as a left-to-right sum of signed terms with the reference's roundings, or None.  IEEE addition commutes and
+        negation is exact, so a caterpillar tree of + / - / unary minus (at most one non-leaf child per node) has an
+        evaluation order that is a plain chain.  -> list of (kind, sign, base, offset, scalar)"""
+        def leaf(u):
+            if not u.is_array:
+                return (1, 1.0, None, 0, u)                                  # a scalar broadcast over the index space
+            if not u.varying and u.numel == n and u.kind in (REG_DATA, REG_HDR):
+                base, off = self._view_of(u)
+                return (0, 1.0, base, off, self.imm(1.0))
+            st = self._producer(u)
+            if (st is not None and st.op == OP["MUL"] and not st.flags and u.numel == n and self._single_use(u) is not None
+                    and u.kind == REG_CHAIN):
+                a, b = st.srcs
+                if not a.is_array:
+                    a, b = b, a
+                if a.is_array and not a.varying and a.numel == n and a.kind in (REG_DATA, REG_HDR) and not b.is_array:
+                    base, off = self._view_of(a)
+                    return (0, 1.0, base, off, b), st
+            return None
+
+        def as_leaf(u):
+            r = leaf(u)
+            if r is None:
+                return None, None
+            if isinstance(r[0], tuple):
+                return r[0], r[1]
+            return r, None
+
+        lf, lst = as_leaf(v)
+        if lf is not None:
+            if lst is not None:
+                dead.append(lst)
+            return [lf]
+        st = self._producer(v)
+        if st is None or st.flags or v.kind != REG_CHAIN or v.numel != n or (not top and self._single_use(v) is None):
+            return None
+        neg = lambda ts: [(k, -sg, b, o, sc) for (k, sg, b, o, sc) in ts]
+        if st.op == OP["NEG"]:
+            inner = self._linearise(st.srcs[0], n, dead)
+            if inner is None:
+                return None
+            dead.append(st)
+            return neg(inner)
+        if st.op not in (OP["ADD"], OP["SUB"]):
+            return None
+        a, b = st.srcs
+        la, lsa = as_leaf(a)
+        lb, lsb = as_leaf(b)
+        sgb = 1.0 if st.op == OP["ADD"] else -1.0
+        if lb is not None:                       # chain(a) +- leaf(b)
+            head = [la] if la is not None else self._linearise(a, n, dead)
+            if head is None:
+                return None
+            if la is not None and lsa is not None:
+                dead.append(lsa)
+            if lsb is not None:
+                dead.append(lsb)
+            dead.append(st)
+            return head + [(lb[0], sgb * lb[1], lb[2], lb[3], lb[4])]
+        if la is not None:                       # leaf(a) +- chain(b)  ==  (+-chain(b)) + leaf(a)
+            tail = self._linearise(b, n, dead)
+            if tail is None:
+                return None
+            if lsa is not None:
+                dead.append(lsa)
+            dead.append(st)
+            return (tail if sgb > 0 else neg(tail)) + [la]
+        return None
+
     # ------------------------------------------------------------------ reverse sweep
     def _adjoint_target(self, v):
         if v.vid not in self.adj:
@@ -669,7 +809,7 @@ class Lowering(object):
         # active = descendants of parameters that are ancestors of the accumulator (src/parsing.jl:291)
         anc = {self.result.vid}
         for st in reversed(self.fwd):
-            outs = [st.dst] + ([st.aux2] if st.op == OP["GLM"] else [])
+            outs = [st.dst] + st.extra_outs
             if any(o.vid in anc for o in outs):
                 anc.update(s.vid for s in st.srcs)
         one = self.imm(1.0)
@@ -768,6 +908,12 @@ class Lowering(object):
             if k != 1:
                 raise ModelError("internal: GLM adjoint requested for a non-parameter argument")
             self.contrib(x, "MUL", [st.aux2, ds])
+        elif op == O["AFFNORM"]:
+            # dL/d(source k) comes out of the kernel as a per-chain scalar (Normal adjoints src/diff.jl:94-99 pushed through
+            # the + - * rules :29-45 inside the kernel's finish step)
+            if st.desc.outs[k] is None:
+                st.desc.outs[k] = self.new((), REG_CHAIN)
+            self.contrib(x, "MUL", [st.desc.outs[k], ds])
         else:
             raise ModelError("[derive] Doesn't know how to derive op %d" % op)
 
@@ -788,7 +934,7 @@ class Lowering(object):
         keep = [False] * len(allst)
         for i in range(len(allst) - 1, -1, -1):
             st = allst[i]
-            outs = [st.dst] + ([st.aux2] if st.op == OP["GLM"] else [])
+            outs = [st.dst] + st.extra_outs
             if any(o.vid in live for o in outs):
                 keep[i] = True
                 live.update(s.vid for s in st.srcs)
@@ -820,6 +966,12 @@ class Lowering(object):
             use(st.dst)
             if st.op == OP["GLM"]:
                 use(st.aux2)
+            if st.op == OP["AFFNORM"]:
+                for v in st.extra_outs:
+                    use(v)
+                for (_, _, base, _) in st.desc.terms:
+                    if base is not None:
+                        use(base)
             if st.touched:
                 for v in st.touched:
                     use(v)
@@ -828,8 +980,21 @@ class Lowering(object):
         slot_map = {s: i for i, s in enumerate(data_used)}
         for i, v in enumerate(used):
             v.reg = i
+        # AFFNORM descriptors travel as index tables (register numbers are known only now):
+        #   [T, reg(dL/dmu) or -1, reg(dL/dsigma) or -1,  then per term: kind, sign, array reg or -1, offset, scalar reg, reg(dL/ds) or -1]
+        tables = list(self.idx_tables)
+        aff_table = {}
+        for st in stmts:
+            if st.op == OP["AFFNORM"]:
+                d = st.desc
+                row = [len(d.terms)] + [(-1 if o is None else o.reg) for o in d.outs[:2]]
+                for j, (kind, sg, base, off) in enumerate(d.terms):
+                    o = d.outs[2 + j]
+                    row += [kind, int(sg), -1 if base is None else base.reg, off, st.srcs[2 + j].reg, -1 if o is None else o.reg]
+                aff_table[id(st)] = len(tables)
+                tables.append(np.array(row, dtype=np.int32))
         out = [struct.pack("<12I", TAPE_MAGIC, TAPE_VERSION, len(used), len(stmts), self.bsize, len(data_used),
-                           len(self.idx_tables), self.tape_result.reg, 0, len(fwd), len(programs), 0)]
+                           len(tables), self.tape_result.reg, 0, len(fwd), len(programs), 0)]
         for v in used:
             if len(v.shape) == 0:
                 rows, cols = 1, 1
@@ -840,9 +1005,12 @@ class Lowering(object):
             aux = slot_map[v.slot] if v.kind == REG_DATA else v.slot
             out.append(struct.pack("<4Iqd", v.kind, rows, cols, len(v.shape), aux, v.imm))
         for st in stmts:
-            src = [s.reg for s in st.srcs] + [0] * (4 - len(st.srcs))
+            srcs, aux0 = st.srcs, st.aux0
+            if st.op == OP["AFFNORM"]:
+                srcs, aux0 = st.srcs[:2], aff_table[id(st)]          # (mu, sigma); everything else is in the descriptor
+            src = [s.reg for s in srcs] + [0] * (4 - len(srcs))
             aux2 = st.aux2.reg if st.aux2 is not None else 0
-            out.append(struct.pack("<4I4I4Id", st.op, st.flags, st.dst.reg, len(st.srcs), *src, st.aux0, st.aux1, aux2, 0,
+            out.append(struct.pack("<4I4I4Id", st.op, st.flags, st.dst.reg, len(srcs), *src, aux0, st.aux1, aux2, 0,
                                    float(st.imm)))
         bound = []
         for s in data_used:
@@ -850,7 +1018,7 @@ class Lowering(object):
             rows, cols = (arr.shape[0], 1) if arr.ndim == 1 else arr.shape
             out.append(struct.pack("<56s2I", name.encode()[:55], rows, cols))
             bound.append((name, arr))
-        for t in self.idx_tables:
+        for t in tables:
             pad = t if len(t) % 2 == 0 else np.concatenate([t, np.zeros(1, np.int32)])
             out.append(struct.pack("<2I", len(t), 0) + pad.astype("<i4").tobytes())
         regmap = {v.vid: v.reg for v in used}

@@ -334,6 +334,7 @@ int smc_aff_launch(smc_model_s* m, SmcAffPlan& p, int64_t C) {
   a.nsum = nsum;
   a.counter = p.counter;
   const int sms = m->ctx->sm_count;
+  if (m->time_glm) SMC_CUDA(cudaEventRecord(m->ev0, st));
   if (C < 32) {
     const int CT = C <= 1 ? 1 : (C <= 2 ? 2 : (C <= 4 ? 4 : 8));
     const int U = CT <= 2 ? 8 : 4;
@@ -363,6 +364,13 @@ int smc_aff_launch(smc_model_s* m, SmcAffPlan& p, int64_t C) {
     else k_affnorm_chains<2><<<grid, nthr, smem, st>>>(a);
   }
   m->ctx->launches++;
+  if (m->time_glm) {
+    SMC_CUDA(cudaEventRecord(m->ev1, st));
+    SMC_CUDA(cudaEventSynchronize(m->ev1));
+    float ms = 0.f;
+    SMC_CUDA(cudaEventElapsedTime(&ms, m->ev0, m->ev1));
+    p.last_ms += ms;
+  }
   SMC_CUDA(cudaGetLastError());
   return SMC_OK;
 }

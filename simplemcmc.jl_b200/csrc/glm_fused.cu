@@ -1082,6 +1082,11 @@ int smc_glm_launch(smc_model_s* m, SmcGlmPlan& g, int64_t C) {
   if (a.pub.on) { m->ctx->launches += 1; return SMC_OK; }   // the kernel published (L, G) itself
   GlmPub pub;
   pub.Ldst = Lr.dev; pub.Gdst = Gr.dev; pub.acc = (s.flags & SMC_F_ACC) ? 1 : 0; pub.on = sharded ? 0 : 1;
+  if (sharded && smc_p2p_ready(m->ctx, (int64_t)(g.M + 1) * C)) {
+    // rows are split over ranks and the host has set up the peer-memory exchange (smc_ctx_p2p_export / _import): the sum over
+    // this rank's row splits, the sum over ranks (in rank order) and the publish step are ONE kernel (smc_p2p.cu)
+    return smc_p2p_glm_exchange(m->ctx, g.part, RS, g.M, g.MP, C, m->Cpad, m->bad, Lr.dev, Gr.dev, pub.acc);
+  }
   long long tot = (long long)(g.MP + 1) * C;
   if ((long long)(g.M + 1) * C <= 1024 && RS >= 16)
     k_glm_reduce_warp<<<(unsigned)(((long long)(g.M + 1) * C * 32 + 255) / 256), 256, 0, st>>>(g.part, RS, g.M, g.MP, C, m->Cpad, m->bad, out, pub);
@@ -1089,10 +1094,8 @@ int smc_glm_launch(smc_model_s* m, SmcGlmPlan& g, int64_t C) {
     k_glm_reduce<<<(unsigned)std::min<long long>((tot + 255) / 256, 148LL * 16), 256, 0, st>>>(g.part, RS, g.M, g.MP, C, m->Cpad, m->bad, out, pub);
   m->ctx->launches += 2;
   if (sharded) {
-    // rows are split over ranks: sum the (L, G) block over the communicator, then publish
-    // (peer-memory exchange when the host has set it up with smc_ctx_p2p_export / _import, NCCL otherwise)
-    if (smc_p2p_ready(m->ctx, (int64_t)(g.MP + 1) * m->Cpad)) SMC_TRY(smc_p2p_allreduce_device(m->ctx, out, (int64_t)(g.MP + 1) * m->Cpad));
-    else SMC_TRY(smc_comm_allreduce_device(m->ctx, out, (int64_t)(g.MP + 1) * m->Cpad));
+    // rows are split over ranks: sum the (L, G) block over the communicator (NCCL, in-stream), then publish
+    SMC_TRY(smc_comm_allreduce_device(m->ctx, out, (int64_t)(g.MP + 1) * m->Cpad));
     long long tot2 = (long long)(g.M + 1) * C;
     k_glm_publish<<<(unsigned)std::min<long long>((tot2 + 255) / 256, 148LL * 16), 256, 0, st>>>(
         out, g.M, g.MP, C, m->Cpad, m->bad, Lr.dev, Gr.dev, pub.acc);

@@ -194,6 +194,7 @@ struct GlmI8Args {
   int M, splits;
   double sx;            // scale of X
   double sigma;
+  int m0, m8, m16, m24; // 1, 2^8, 2^16, 2^24 (see halves())
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -204,13 +205,21 @@ __device__ __forceinline__ long long mad_wide(int a, int b, long long c) {
   asm("mad.wide.s32 %0, %1, %2, %3;\n" : "=l"(d) : "r"(a), "r"(b), "l"(c));
   return d;
 }
-// the group sums as two exact int64 halves: hi = sum_{g<4} a[g] 2^(8 (3 - g)), lo = the remaining groups likewise
+// The group sums as two exact int64 halves: hi = sum_{g<4} a[g] 2^(8 (3 - g)), lo = the remaining groups likewise, each
+// on top of `bias`.  The multipliers arrive in registers (kernel arguments), so that every step is one IMAD.WIDE: with
+// literal powers of two ptxas expands each step into four or five 32-bit instructions.
+struct WideMul { int m0, m8, m16, m24; };
 template <int NB>
-__device__ __forceinline__ void halves(const int32_t* a, long long& hi, long long& lo) {
-  hi = mad_wide(a[0], 1 << 24, mad_wide(a[1], 1 << 16, mad_wide(a[2], 1 << 8, (long long)a[3])));
-  if (NB == 8) lo = mad_wide(a[4], 1 << 24, mad_wide(a[5], 1 << 16, mad_wide(a[6], 1 << 8, (long long)a[7])));
-  else lo = mad_wide(a[4], 1 << 16, mad_wide(a[5], 1 << 8, (long long)a[6]));
+__device__ __forceinline__ void halves(const int32_t* a, const WideMul& w, long long bias, long long& hi, long long& lo) {
+  hi = mad_wide(a[0], w.m24, mad_wide(a[1], w.m16, mad_wide(a[2], w.m8, mad_wide(a[3], w.m0, bias))));
+  if (NB == 8) lo = mad_wide(a[4], w.m24, mad_wide(a[5], w.m16, mad_wide(a[6], w.m8, mad_wide(a[7], w.m0, bias))));
+  else lo = mad_wide(a[4], w.m16, mad_wide(a[5], w.m8, mad_wide(a[6], w.m0, bias)));
 }
+// int64 -> double without the conversion unit (I2F.F64.S64 and F2I.S64.F64 issue at a small fraction of the other pipes'
+// rate: with them the kernel's top stall was math-pipe throttle on XU, profiles/glm_i8_v10_ncu_r02.json): the bits of
+// 1.5 * 2^52 plus an integer |x| < 2^51 ARE the double 1.5 * 2^52 + x, and fma(that, s, -1.5 * 2^52 * s) = x * s exactly.
+constexpr long long MAGIC_BITS = 0x4338000000000000LL;
+constexpr double MAGIC = 6755399441055744.0;
 // adjoint slices in shared memory, MN-major for product 2 (B operand, N = 32 j + chain contiguous, K = rows):
 // 128-byte core matrices [row group r>>3][n chunk n>>4][row r&7][n&15]; SBO (along N) = 128, LBO (along K) = QD_LBO
 constexpr int QD_N = NS8 * NC;                       // 224 stacked columns
@@ -237,7 +246,7 @@ __global__ void __launch_bounds__(NTI, 1) k_glm_i8(GlmI8Args a) {   // 17 warps 
   __shared__ uint64_t bar1, bar2[2], barX[2], barA, barB;
   __shared__ uint32_t tmem_slot;
   __shared__ double s_f[NC];
-  __shared__ double2 s_sc[NC];                       // (s 2^-36, s 2^-60 or 2^-68): recombination scales of eta
+  __shared__ double4 s_sc[NC];                       // (s 2^-36, s 2^-60 | 2^-68) and -MAGIC times each: recombination of eta
   __shared__ unsigned int s_max[4][NC];              // high word of max |w| per chain, buffer = tile mod 4
   __shared__ int s_flag[4];                          // some chain's tile maximum exceeded its sticky scale
   __shared__ int s_badc[NC];
@@ -265,7 +274,8 @@ __global__ void __launch_bounds__(NTI, 1) k_glm_i8(GlmI8Args a) {   // 17 warps 
     double sc, f;
     scale_of8(m, &sc, &f);
     const double s = a.sx * sc;                            // power of two
-    s_sc[tid] = make_double2(s * 0x1p-36, s * (NB == 8 ? 0x1p-68 : 0x1p-60));
+    const double s36 = s * 0x1p-36, s60 = s * (NB == 8 ? 0x1p-68 : 0x1p-60);
+    s_sc[tid] = make_double4(s36, s60, -MAGIC * s36, -MAGIC * s60);
     s_f[tid] = NB == 8 ? f * 256.0 : f;
     s_badc[tid] = bad;
 #pragma unroll
@@ -355,6 +365,7 @@ __global__ void __launch_bounds__(NTI, 1) k_glm_i8(GlmI8Args a) {   // 17 warps 
   // ================= epilogue warps =================
   const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
   const int ii = rl >> 6;
+  const WideMul wm = {a.m0, a.m8, a.m16, a.m24};
   double lacc[CQ];
 #pragma unroll
   for (int c = 0; c < CQ; c++) lacc[c] = 0.0;
@@ -386,9 +397,9 @@ __global__ void __launch_bounds__(NTI, 1) k_glm_i8(GlmI8Args a) {   // 17 warps 
 #pragma unroll
           for (int cb = 0; cb < NB; cb++) g[cb] = acc[cb][v];
           long long hi, lo;
-          halves<NB>(g, hi, lo);
-          const double2 sc = s_sc[q * CQ + u];
-          const double w = fma((double)hi, sc.x, (double)lo * sc.y) - yr;
+          halves<NB>(g, wm, MAGIC_BITS, hi, lo);
+          const double4 sc = s_sc[q * CQ + u];
+          const double w = (fma(__longlong_as_double(hi), sc.x, sc.z) + fma(__longlong_as_double(lo), sc.y, sc.w)) - yr;
           d[u] = w;
           lacc[u] = fma(w, w, lacc[u]);
           hw[u] = (unsigned int)__double2hiint(w) & 0x7fffffffu;
@@ -428,7 +439,7 @@ __global__ void __launch_bounds__(NTI, 1) k_glm_i8(GlmI8Args a) {   // 17 warps 
 #pragma unroll
           for (int cb = 0; cb < NS8; cb++) g[cb] = acc[cb][v];
           long long hi, lo;
-          halves<7>(g, hi, lo);
+          halves<7>(g, wm, 0ll, hi, lo);
           const double sc = a.sx * __longlong_as_double((long long)((unsigned long long)(E[u] + 1u) << 52));
           val[u] = fma((double)hi, ii ? 0x1p-44 : 0x1p-36, (double)lo * (ii ? 0x1p-68 : 0x1p-60)) * (sc * neg_inv_s2);
         }
@@ -477,8 +488,7 @@ __global__ void __launch_bounds__(NTI, 1) k_glm_i8(GlmI8Args a) {   // 17 warps 
       uint32_t xl[CQ], xh[CQ];
 #pragma unroll
       for (int u = 0; u < CQ; u++) {
-        const double f = __longlong_as_double((long long)((unsigned long long)(2099u - E[u]) << 52));   // 2^54 / scale
-        const unsigned long long w = slice7_word(d[u], f);  // byte k = slice 6 - k
+        const unsigned long long w = slice7_bits(d[u], E[u]);   // w 2^54 / scale, truncated, as balanced bytes: byte k = slice 6 - k
         xl[u] = (uint32_t)w;
         xh[u] = (uint32_t)(w >> 32);
       }
@@ -621,6 +631,7 @@ int smc_glm_i8_launch(smc_model_s* m, SmcGlmPlan& g, const double* beta, int64_t
   GlmI8Args a;
   a.QX = g.QX8; a.y = g.y; a.beta = beta; a.part = part; a.status = g.i8_status;
   a.N = g.N; a.tiles = tiles; a.C = C; a.Cpad = Cpad; a.M = g.M; a.splits = RS; a.sx = g.sx8; a.sigma = g.par;
+  a.m0 = 1; a.m8 = 1 << 8; a.m16 = 1 << 16; a.m24 = 1 << 24;
   dim3 grid((unsigned)smc_glm_i8_chain_tiles(C), (unsigned)RS);
   static int beta8 = -1;
   if (beta8 < 0) { const char* e = getenv("SMC_GLM_I8_BETA8"); beta8 = (e && e[0] == '1') ? 1 : 0; }

@@ -547,6 +547,7 @@ int run_finish(Run& r, int64_t n_evals) {
   std::vector<unsigned long long> nl(r.C);
   SMC_CUDA(cudaMemcpyAsync(nl.data(), r.nleap, r.C * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
   SMC_CUDA(cudaStreamSynchronize(st));
+  if (m->row_shard) SMC_TRY(smc_p2p_check(m->ctx));     // a peer that never arrived: the draws are not to be trusted
   unsigned long long tot = 0;
   for (auto x : nl) tot += x;
   r.out->n_leapfrogs = (int64_t)tot;
@@ -605,7 +606,7 @@ extern "C" int smc_hmc_run(smc_model_t m, const smc_sampler_config* cfg, const d
   // captured whole -- the evaluation graph becomes a child node -- and every later iteration is one graph launch.
   cudaGraphExec_t exec = nullptr;
   int64_t per_iter = 0;
-  const bool can_graph = m->graphs_enabled && !(m->row_shard && m->ctx->nranks > 1 && !m->graph_nccl);
+  const bool can_graph = m->graphs_enabled && smc_comm_graph_ok(m);
   int rc = SMC_OK;
   for (long long i = 0; i < cfg->steps && rc == SMC_OK; i++) {
     if (exec) {

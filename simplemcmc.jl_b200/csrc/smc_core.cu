@@ -959,6 +959,13 @@ static int eval_body(smc_model_s* m, int64_t C, bool with_grad) {
   return SMC_OK;
 }
 
+// may the launch sequence of an evaluation be captured?  An in-sequence NCCL all-reduce (row-sharded models) keeps it eager
+// unless the host opted in (SMC_GRAPH_NCCL=1); the peer-memory exchange is an ordinary kernel with its epoch in device memory
+bool smc_comm_graph_ok(const smc_model_s* m) {
+  if (!m->row_shard || m->ctx->nranks <= 1) return true;
+  return m->graph_nccl || m->ctx->p2p_ranks > 1;
+}
+
 // beta[M][Cpad] (device) -> logp[Cpad], grad[M][Cpad] (device).
 // The statement sequence of a (chain count, gradient) pair is fixed, so its second evaluation is captured into a
 // CUDA graph and every later one is a single graph launch: the sampler loops (one evaluation per leapfrog) stop
@@ -969,7 +976,7 @@ int smc_model_eval_device(smc_model_s* m, int64_t C, bool with_grad) {
   if (C < 1 || C > m->Cmax) { smc_set_error("chains %lld outside [1, %lld] given to smc_model_finalize", (long long)C, (long long)m->Cmax); return SMC_ERR_INVALID; }
   cudaStream_t st = m->ctx->stream;
   m->C = C;
-  if (!m->graphs_enabled || m->time_glm || (m->row_shard && m->ctx->nranks > 1 && !m->graph_nccl)) return eval_body(m, C, with_grad);
+  if (!m->graphs_enabled || m->time_glm || !smc_comm_graph_ok(m)) return eval_body(m, C, with_grad);
   if (m->graphs_stale) smc_graphs_invalidate(m);
   int gi = -1;
   for (size_t i = 0; i < m->graphs.size(); i++)
@@ -1037,6 +1044,7 @@ extern "C" int smc_eval(smc_model_t m, const double* beta, int64_t C, double* lo
   }
   SMC_CUDA(cudaStreamSynchronize(st));
   SMC_CUDA(cudaGetLastError());
+  if (m->row_shard) SMC_TRY(smc_p2p_check(m->ctx));
   return SMC_OK;
 }
 
@@ -1051,6 +1059,7 @@ extern "C" int smc_eval_timed(smc_model_t m, int reps, int flush_l2, double* ms_
     if (flush_l2) SMC_CUDA(cudaMemsetAsync(m->ctx->flush_buf, r & 0xff, flush_bytes, st));
     m->time_glm = 1;
     for (auto& g : m->glm) g.last_ms = 0.f;
+    for (auto& a : m->aff) a.last_ms = 0.f;
     cudaEvent_t e0, e1;
     SMC_CUDA(cudaEventCreate(&e0));
     SMC_CUDA(cudaEventCreate(&e1));
@@ -1064,6 +1073,7 @@ extern "C" int smc_eval_timed(smc_model_t m, int reps, int flush_l2, double* ms_
     SMC_CUDA(cudaEventElapsedTime(&ms, e0, e1));
     tot += ms;
     for (auto& g : m->glm) glm += g.last_ms;
+    for (auto& a : m->aff) glm += a.last_ms;      // (the fused statement kernels: GLM and AFFNORM)
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
   }

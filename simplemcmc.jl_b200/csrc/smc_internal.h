@@ -62,9 +62,8 @@ struct smc_ctx_s {
   // peer-memory exchange of row-sharded models (smc_p2p.cu; opt-in through smc_ctx_p2p_export / _import)
   void* p2p_local = nullptr;
   void* p2p_peer[16] = {};
-  unsigned* p2p_count = nullptr;
-  int p2p_rank = 0, p2p_ranks = 0;
-  unsigned p2p_epoch = 0;
+  unsigned* p2p_count = nullptr;   // device: push tickets, finish tickets, epoch, status
+  int p2p_rank = 0, p2p_ranks = 0, p2p_alloc_ranks = 0;
 };
 
 struct SmcReg {
@@ -112,6 +111,7 @@ struct SmcAffPlan {  // one SMC_OP_AFFNORM statement (affnorm.cu)
   int stmt = -1;
   std::vector<int32_t> desc;        // host copy of the descriptor table
   unsigned int* counter = nullptr;  // ticket counters of the last-block finish, one per chain group
+  float last_ms = 0.f;              // event-timed launch (smc_eval_timed)
 };
 
 // Micro-operation of the register-program VM (vm_exec.cu): the tape's LOADV/LOADS/STOREV/REDUCE instructions are
@@ -222,6 +222,7 @@ struct smc_model_s {
 int smc_model_eval_device(smc_model_s* m, int64_t C, bool with_grad);  // beta -> logp, grad (device resident)
 int smc_stage_reserve(smc_model_s* m, int64_t doubles);
 void smc_graphs_invalidate(smc_model_s* m);
+bool smc_comm_graph_ok(const smc_model_s* m);
 
 // vm_exec.cu
 int smc_vm_plan(smc_model_s* m, SmcProgram& pr);      // instruction list -> micro-ops
@@ -241,6 +242,9 @@ void smc_aff_release(SmcAffPlan& p, cudaStream_t st);
 // smc_p2p.cu
 bool smc_p2p_ready(const smc_ctx_s* c, int64_t n);
 int smc_p2p_allreduce_device(smc_ctx_s* c, double* buf, int64_t n);
+int smc_p2p_glm_exchange(smc_ctx_s* c, const double* part, int RS, int M, int MP, int64_t C, int64_t Cpad, int* bad, double* Ldst,
+                         double* Gdst, int acc);
+int smc_p2p_check(smc_ctx_s* c);   // after a synchronisation point: SMC_ERR_COMM when an exchange timed out
 void smc_p2p_destroy(smc_ctx_s* c);
 
 // glm_i8.cu (opt-in, SMC_GLM_I8=1)

@@ -1,32 +1,37 @@
-// Peer-memory sum of the row-sharded GLM statement's (L, G) block over NVLink / NVSwitch: a drop-in for the in-stream NCCL
-// all-reduce of smc_comm.cu on one node ("cfg3 rows sharded, few chains": at 4 GPUs and 2 chains a
-// leapfrog is 164 us around 44 us of streaming, a few us of which are the NCCL launch).
+// Peer-memory sum of the row-sharded GLM statement's (L, G) block over NVLink / NVSwitch (one node): replaces, per
+// evaluation, k_glm_reduce + the in-stream NCCL all-reduce of smc_comm.cu + k_glm_publish by ONE kernel
+// ("cfg3 rows sharded, few chains": at 4 GPUs and 2 chains a leapfrog was 164 us around 44 us of
+// streaming; the row sum is src/distribs.jl:100-102 split over ranks).
 //
-// OPT-IN AND NOT YET RUN ON A DEVICE (written after the round's GPU minutes were spent): a context uses it only after the
-// host has called smc_ctx_p2p_export on every rank, exchanged the handles, and called smc_ctx_p2p_import.
-//
-// Every rank owns one exchange buffer (plain cudaMalloc, exported with cudaIpcGetMemHandle and mapped by the peers):
+// Opt-in: a context uses it after the host has called smc_ctx_p2p_export on every rank, exchanged the 64-byte handles, and
+// called smc_ctx_p2p_import (simplemcmc.jl_b200/parallel.py::init_p2p).  Every rank owns one exchange buffer (plain
+// cudaMalloc, exported with cudaIpcGetMemHandle and mapped by the peers):
 //   flags[2][16] (unsigned, one per (parity, source rank)) and slots[2][R][kSlotDoubles].
-// A call with epoch e (1, 2, ...; the same on all ranks because row-sharded ranks advance identical chains) is two kernels:
-//   push: copy the local block into slot[e & 1][my rank] of EVERY rank (remote stores), fence, and the last CTA to finish
-//         writes e into flags[e & 1][my rank] of every rank (release, system scope);
-//   pull: wait until flags[e & 1][q] >= e for every q (acquire, system scope, bounded), then out[i] = sum over q in rank
-//         order of slot[e & 1][q][i]: the same additions in the same order on every rank, so the chains stay bit-identical.
-// Two parities suffice: a peer can push epoch e + 2 only after its pull of e + 1, which needs my push of e + 1, which my
-// stream orders after my pull of e.
+// k_glm_xchg, epoch e (1, 2, ...; the same on all ranks because row-sharded ranks advance identical chains; it lives in
+// DEVICE memory so that the kernel can sit in a captured CUDA graph and still count):
+//   1. reduce: the fixed-order sum of this rank's row-split partials, element (j, c) by element;
+//   2. push:   that sum goes into slot[e & 1][my rank] of EVERY rank (remote stores over NVLink), fence, and the last CTA
+//              to finish writes e into flags[e & 1][my rank] of every rank (st.release.sys);
+//   3. wait:   every CTA waits until flags[e & 1][q] >= e for every q (ld.acquire.sys, bounded: a peer that never
+//              arrives sets a status word the host checks after the run, SMC_ERR_COMM);
+//   4. sum + publish: out = sum over q in rank order of slot[e & 1][q] -- the same additions in the same order on every
+//              rank, so the chains stay bit-identical -- written straight into the tape registers (L with the
+//              out-of-support flag, G).
+// Two parities suffice: a peer can push epoch e + 2 only after it finished epoch e + 1, which needs my push of e + 1, which
+// my stream orders after my step 4 of e.
 #include <string.h>
 #include "smc_internal.h"
 
 namespace {
 constexpr int kMaxPeers = 16;
-constexpr long long kSlotDoubles = 1ll << 19;            // 4 MB per (parity, rank): (MP + 1) * Cpad up to 524 288
+constexpr long long kSlotDoubles = 1ll << 19;            // 4 MB per (parity, rank): (M + 1) * C up to 524 288
 constexpr size_t kFlagBytes = 256;                       // flags[2][16] unsigned = 128 bytes, padded
+constexpr int kMaxBlocks = 64;                           // all CTAs must be co-resident (they wait on each other's push)
 
 struct P2PView {
   unsigned char* peer[kMaxPeers];
   int rank, nranks;
-  unsigned* count;                                       // local: CTAs of the push kernel that have finished
-  int* status;
+  unsigned* ctl;                                         // local: [0] push tickets, [1] finish tickets, [2] epoch, [3] status
 };
 __device__ __forceinline__ unsigned* flag_ptr(unsigned char* base, int parity, int src) {
   return (unsigned*)base + parity * kMaxPeers + src;
@@ -35,50 +40,94 @@ __device__ __forceinline__ double* slot_ptr(unsigned char* base, int nranks, int
   return (double*)(base + kFlagBytes) + ((long long)parity * nranks + src) * kSlotDoubles;
 }
 
-__global__ void __launch_bounds__(256) k_p2p_push(const double* __restrict__ src, long long n, P2PView v, unsigned epoch) {
+struct XchgArgs {
+  const double* part;      // [RS][MP + 1][Cpad] row-split partials of this rank (NULL: `flat` holds n ready values)
+  double* flat;            // generic all-reduce: in/out buffer of n doubles
+  int RS, M, MP;
+  long long C, Cpad, n;    // n = (M + 1) * C  (GLM)  or the buffer length (flat)
+  int* bad;
+  double* Ldst;
+  double* Gdst;
+  int acc;
+};
+
+__global__ void __launch_bounds__(256) k_glm_xchg(XchgArgs a, P2PView v) {
+  __shared__ int s_flag;
+  const unsigned epoch = *(volatile unsigned*)(v.ctl + 2) + 1u;       // updated only after every CTA has passed step 3
   const int parity = (int)(epoch & 1u);
-  for (int q = 0; q < v.nranks; q++) {
-    double* dst = slot_ptr(v.peer[q], v.nranks, parity, v.rank);
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) dst[i] = src[i];
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  // ---- 1 + 2: reduce and push
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
+    double t;
+    if (a.part) {
+      const long long jj = i / a.C, c = i - jj * a.C;
+      const long long j = jj == a.M ? a.MP : jj;
+      t = 0.0;
+      for (int r = 0; r < a.RS; r++) t += a.part[((long long)r * (a.MP + 1) + j) * a.Cpad + c];
+      if (jj == a.M && (a.bad[c] || !(t > -INFINITY))) t = -INFINITY;  // the flag survives the cross-rank sum
+    } else {
+      t = a.flat[i];
+    }
+    for (int q = 0; q < v.nranks; q++) slot_ptr(v.peer[q], v.nranks, parity, v.rank)[i] = t;
   }
   __threadfence_system();                                // my stores are visible system-wide before my CTA is counted
-  __shared__ int last;
   __syncthreads();
-  if (threadIdx.x == 0) last = (atomicAdd(v.count, 1u) == gridDim.x - 1u) ? 1 : 0;
+  if (threadIdx.x == 0) s_flag = (atomicAdd(v.ctl, 1u) == gridDim.x - 1u) ? 1 : 0;
   __syncthreads();
-  if (last) {
+  if (s_flag) {
     __threadfence_system();
     if ((int)threadIdx.x < v.nranks) {
       unsigned* f = flag_ptr(v.peer[threadIdx.x], parity, v.rank);
       asm volatile("st.release.sys.global.u32 [%0], %1;\n" :: "l"(f), "r"(epoch) : "memory");
     }
-    if (threadIdx.x == 0) *v.count = 0u;
+    if (threadIdx.x == 0) v.ctl[0] = 0u;
   }
-}
-
-__global__ void __launch_bounds__(256) k_p2p_pull(double* __restrict__ out, long long n, P2PView v, unsigned epoch) {
-  const int parity = (int)(epoch & 1u);
+  // ---- 3: wait for every rank's flag
   unsigned char* mine = v.peer[v.rank];
-  __shared__ int ok;
-  if (threadIdx.x == 0) ok = 1;
+  __syncthreads();
+  if (threadIdx.x == 0) s_flag = 1;
   __syncthreads();
   if ((int)threadIdx.x < v.nranks) {
     const unsigned* f = flag_ptr(mine, parity, threadIdx.x);
     unsigned seen = 0;
-    long long t0 = clock64();
+    const long long t0 = clock64();
     for (;;) {
       asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(seen) : "l"(f) : "memory");
       if ((int)(seen - epoch) >= 0) break;
-      if (clock64() - t0 > 20000000000ll) { ok = 0; break; }          // ~10 s: a peer that never arrives is an error
+      if (clock64() - t0 > 20000000000ll) { s_flag = 0; break; }     // ~10 s: a peer that never arrives is an error
     }
   }
   __syncthreads();
-  if (!ok) { if (threadIdx.x == 0) *v.status = 1; return; }
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+  if (!s_flag && threadIdx.x == 0) v.ctl[3] = 1u;
+  // ---- 4: rank-ordered sum and publish
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
     double s = 0.0;
-    for (int q = 0; q < v.nranks; q++) s += slot_ptr(mine, v.nranks, parity, q)[i];
-    out[i] = s;
+    for (int q = 0; q < v.nranks; q++) s += __ldcg(slot_ptr(mine, v.nranks, parity, q) + i);
+    if (a.part) {
+      const long long jj = i / a.C, c = i - jj * a.C;
+      if (jj == a.M) {
+        if (!(s > -INFINITY)) { a.bad[c] = 1; s = 0.0; }
+        a.Ldst[c] = a.acc ? a.Ldst[c] + s : s;
+      } else {
+        a.Gdst[jj * a.Cpad + c] = s;
+      }
+    } else {
+      a.flat[i] = s;
+    }
   }
+  __syncthreads();
+  if (threadIdx.x == 0 && atomicAdd(v.ctl + 1, 1u) == gridDim.x - 1u) {
+    v.ctl[1] = 0u;
+    v.ctl[2] = epoch;                                     // every CTA has read the old value long ago (it pushed)
+    __threadfence();
+  }
+}
+
+P2PView make_view(const smc_ctx_s* c) {
+  P2PView v;
+  for (int q = 0; q < kMaxPeers; q++) v.peer[q] = (unsigned char*)(q < c->p2p_ranks ? c->p2p_peer[q] : nullptr);
+  v.rank = c->p2p_rank; v.nranks = c->p2p_ranks; v.ctl = c->p2p_count;
+  return v;
 }
 }  // namespace
 
@@ -89,13 +138,18 @@ extern "C" int smc_ctx_p2p_export(smc_ctx_t ctx, int nranks, void* handle_out, i
     return SMC_ERR_INVALID;
   }
   cudaSetDevice(ctx->device);
+  if (ctx->p2p_local && ctx->p2p_alloc_ranks != nranks) {
+    smc_set_error("smc_ctx_p2p_export: the exchange buffer of this context was sized for %d ranks, not %d", ctx->p2p_alloc_ranks, nranks);
+    return SMC_ERR_INVALID;
+  }
   if (!ctx->p2p_local) {
     const size_t bytes = kFlagBytes + (size_t)2 * nranks * kSlotDoubles * sizeof(double);
     SMC_CUDA(cudaMalloc(&ctx->p2p_local, bytes));        // not from the stream-ordered pool: pool memory has no IPC handle
     SMC_CUDA(cudaMemset(ctx->p2p_local, 0, bytes));
-    SMC_CUDA(cudaMalloc((void**)&ctx->p2p_count, sizeof(unsigned) + sizeof(int)));
-    SMC_CUDA(cudaMemset(ctx->p2p_count, 0, sizeof(unsigned) + sizeof(int)));
+    SMC_CUDA(cudaMalloc((void**)&ctx->p2p_count, 4 * sizeof(unsigned)));
+    SMC_CUDA(cudaMemset(ctx->p2p_count, 0, 4 * sizeof(unsigned)));
     SMC_CUDA(cudaDeviceSynchronize());
+    ctx->p2p_alloc_ranks = nranks;
   }
   cudaIpcMemHandle_t h;
   SMC_CUDA(cudaIpcGetMemHandle(&h, ctx->p2p_local));
@@ -103,10 +157,16 @@ extern "C" int smc_ctx_p2p_export(smc_ctx_t ctx, int nranks, void* handle_out, i
   return SMC_OK;
 }
 
-// handles: nranks consecutive 64-byte handles in rank order (the own one is ignored)
+// handles: nranks consecutive 64-byte handles in rank order (the own one is ignored).  Once per context: the epoch
+// counters of the ranks advance together from zero and the flags of an earlier set-up would satisfy later waits.
 extern "C" int smc_ctx_p2p_import(smc_ctx_t ctx, const void* handles, int nranks, int rank) {
   if (!ctx || !handles || nranks < 2 || nranks > kMaxPeers || rank < 0 || rank >= nranks || !ctx->p2p_local) {
     smc_set_error("smc_ctx_p2p_import: bad argument, or smc_ctx_p2p_export was not called");
+    return SMC_ERR_INVALID;
+  }
+  if (ctx->p2p_ranks != 0) { smc_set_error("smc_ctx_p2p_import: this context already has a peer exchange (one set-up per context)"); return SMC_ERR_INVALID; }
+  if (nranks != ctx->p2p_alloc_ranks) {
+    smc_set_error("smc_ctx_p2p_import: %d ranks, but the exchange buffer was exported for %d", nranks, ctx->p2p_alloc_ranks);
     return SMC_ERR_INVALID;
   }
   cudaSetDevice(ctx->device);
@@ -118,23 +178,46 @@ extern "C" int smc_ctx_p2p_import(smc_ctx_t ctx, const void* handles, int nranks
   }
   ctx->p2p_rank = rank;
   ctx->p2p_ranks = nranks;
-  ctx->p2p_epoch = 0;
   return SMC_OK;
 }
 
 bool smc_p2p_ready(const smc_ctx_s* c, int64_t n) { return c->p2p_ranks > 1 && n <= kSlotDoubles; }
 
+// the GLM statement's row-split partials -> summed over row splits and ranks -> tape registers, one kernel
+int smc_p2p_glm_exchange(smc_ctx_s* c, const double* part, int RS, int M, int MP, int64_t C, int64_t Cpad, int* bad, double* Ldst,
+                         double* Gdst, int acc) {
+  XchgArgs a;
+  a.part = part; a.flat = nullptr; a.RS = RS; a.M = M; a.MP = MP; a.C = C; a.Cpad = Cpad; a.n = (long long)(M + 1) * C;
+  a.bad = bad; a.Ldst = Ldst; a.Gdst = Gdst; a.acc = acc;
+  const unsigned blocks = (unsigned)std::max<long long>(1, std::min<long long>((a.n + 255) / 256, kMaxBlocks));
+  k_glm_xchg<<<blocks, 256, 0, c->stream>>>(a, make_view(c));
+  c->launches += 1;
+  SMC_CUDA(cudaGetLastError());
+  return SMC_OK;
+}
+
 // in-stream sum over ranks of a device buffer of doubles (same contract as smc_comm_allreduce_device)
 int smc_p2p_allreduce_device(smc_ctx_s* c, double* buf, int64_t n) {
-  P2PView v;
-  for (int q = 0; q < kMaxPeers; q++) v.peer[q] = (unsigned char*)(q < c->p2p_ranks ? c->p2p_peer[q] : nullptr);
-  v.rank = c->p2p_rank; v.nranks = c->p2p_ranks; v.count = c->p2p_count; v.status = (int*)(c->p2p_count + 1);
-  const unsigned epoch = ++c->p2p_epoch;
-  const unsigned blocks = (unsigned)std::min<long long>((n + 255) / 256, 64);
-  k_p2p_push<<<blocks, 256, 0, c->stream>>>(buf, (long long)n, v, epoch);
-  k_p2p_pull<<<blocks, 256, 0, c->stream>>>(buf, (long long)n, v, epoch);
-  c->launches += 2;
+  XchgArgs a;
+  memset(&a, 0, sizeof(a));
+  a.flat = buf; a.n = n;
+  const unsigned blocks = (unsigned)std::max<long long>(1, std::min<long long>((n + 255) / 256, kMaxBlocks));
+  k_glm_xchg<<<blocks, 256, 0, c->stream>>>(a, make_view(c));
+  c->launches += 1;
   SMC_CUDA(cudaGetLastError());
+  return SMC_OK;
+}
+
+// after a synchronisation point: did any exchange of this context time out?  (clears the word)
+int smc_p2p_check(smc_ctx_s* c) {
+  if (c->p2p_ranks <= 1 || !c->p2p_count) return SMC_OK;
+  unsigned status = 0;
+  SMC_CUDA(smc_copy_sync(&status, c->p2p_count + 3, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+  if (status) {
+    cudaMemsetAsync(c->p2p_count + 3, 0, sizeof(unsigned), c->stream);
+    smc_set_error("peer-memory exchange: a rank did not arrive within the time limit (the results of this call are invalid)");
+    return SMC_ERR_COMM;
+  }
   return SMC_OK;
 }
 
@@ -143,5 +226,5 @@ void smc_p2p_destroy(smc_ctx_s* c) {
     if (q != c->p2p_rank && c->p2p_peer[q]) cudaIpcCloseMemHandle(c->p2p_peer[q]);
   if (c->p2p_local) cudaFree(c->p2p_local);
   if (c->p2p_count) cudaFree(c->p2p_count);
-  c->p2p_local = nullptr; c->p2p_count = nullptr; c->p2p_ranks = 0;
+  c->p2p_local = nullptr; c->p2p_count = nullptr; c->p2p_ranks = 0; c->p2p_alloc_ranks = 0;
 }

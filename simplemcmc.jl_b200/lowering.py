@@ -120,7 +120,7 @@ _ELEMENTWISE_UNARY = {"exp": "EXP", "log": "LOG", "sin": "SIN", "cos": "COS", "a
 
 class Lowering(object):
     def __init__(self, model, init, data, gradient=True, ref_adjoint="assign", fuse=True, fuse_statements=True,
-                 sufficient_stats=False):
+                 sufficient_stats=False, affnorm=None):
         self.vals, self.fwd, self.bwd = [], [], []
         self.env, self.data_slots, self.idx_tables = {}, [], []
         self.imm_cache = {}
@@ -145,9 +145,13 @@ class Lowering(object):
         self._check_params_used()
         self.n_fused = 0
         self.n_affnorm = 0
+        if affnorm is None:
+            import os
+            affnorm = os.environ.get("SMC_NO_AFFNORM") != "1"
         if fuse:
             self._fuse_glm()
-            self._fuse_affnorm()
+            if affnorm:
+                self._fuse_affnorm()
         self.n_fwd = None
         if gradient:
             self._reverse_sweep()

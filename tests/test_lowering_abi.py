@@ -164,11 +164,55 @@ def test_programs_pack_for_index_spaces_beyond_16_bits():
     """cfg5 at T = 1e6: a program's index-space length lives in its header, not in a 16-bit instruction field"""
     import struct
     x = ou_data(100_000)
-    low = Lowering(ORNSTEIN, [("tau", 20.0), ("mu", 10.0), ("sigma", 0.1)], dict(x=x))
+    low = Lowering(ORNSTEIN, [("tau", 20.0), ("mu", 10.0), ("sigma", 0.1)], dict(x=x), affnorm=False)
     tape, bound = low.serialise()
     assert any(pr.n == 99_999 for pr in low.programs)
     blob = low.programs[[pr.n for pr in low.programs].index(99_999)].pack({v.vid: v.reg for v in low.vals if v.reg is not None})
     assert struct.unpack("<4I", blob[:16])[3] == 99_999
+
+
+def test_ornstein_residual_becomes_one_affnorm_statement():
+    """examples/ornstein.jl:24-26: `resid = x[2:end] - x[1:end-1] * fac - mu * (1. - fac); resid ~ Normal(0, sigma)` is one
+    AFFNORM statement whose two array terms are views (offsets 1 and 0) of the ONE bound vector x -- no header gathers, no
+    element-wise temporaries; what is left around it are two scalar programs"""
+    import struct
+    x = ou_data(5000)
+    low = Lowering(ORNSTEIN, [("tau", 20.0), ("mu", 10.0), ("sigma", 0.1)], dict(x=x))
+    assert low.n_affnorm == 1
+    tape, bound = low.serialise()
+    assert [b[0] for b in bound] == ["x"]
+    aff = [s for s in low.tape_fwd if s.op == lowering.OP["AFFNORM"]]
+    assert len(aff) == 1 and aff[0].flags & lowering.F_ACC          # accumulates into __acc after the three priors
+    d = aff[0].desc
+    assert d.n == 4999 and [(k, sg, off) for (k, sg, b, off) in d.terms] == [(0, 1.0, 1), (0, -1.0, 0), (1, -1.0, 0)]
+    assert d.terms[0][2] is d.terms[1][2] and d.terms[0][2].kind == lowering.REG_DATA
+    assert d.outs[0] is None and d.outs[1] is not None                # mu = 0 literal; sigma is a parameter
+    assert d.outs[2] is None and d.outs[3] is not None and d.outs[4] is not None   # coefficient 1, -fac, -mu (1 - fac)
+    ops = [s.op for s in low.tape_fwd + low.tape_bwd]
+    assert ops == [49, lowering.OP["AFFNORM"], 49] and all(pr.n == 1 for pr in low.programs)
+    # the descriptor travels as the last index table of the blob
+    hdr = struct.unpack("<12I", tape[:48])
+    assert hdr[6] == len(low.idx_tables) + 1
+    # below the size threshold, or when a temporary is used twice, the element-wise tape stays
+    assert Lowering(ORNSTEIN, [("tau", 20.0), ("mu", 10.0), ("sigma", 0.1)], dict(x=ou_data(500))).n_affnorm == 0
+    twice = ORNSTEIN + "\nsum(resid) ~ Normal(0, 100)"
+    assert Lowering(twice, [("tau", 20.0), ("mu", 10.0), ("sigma", 0.1)], dict(x=x)).n_affnorm == 0
+
+
+def test_affnorm_linearisation_keeps_the_reference_roundings():
+    """caterpillar trees of + / - / unary minus are chains (IEEE addition commutes, negation is exact); a node with two
+    non-leaf children is not"""
+    d = dict(a=np.ones(4096), b=np.ones(4096), c=np.ones(4096))
+    def terms(expr):
+        low = Lowering("r = %s\nr ~ Normal(m, 2.0)" % expr, [("s", 1.5), ("m", 0.5)], d)
+        return None if low.n_affnorm == 0 else [(k, sg) for (k, sg, _, _) in [s for s in low.fwd if s.op == lowering.OP["AFFNORM"]][0].desc.terms]
+    assert terms("a * s - b") == [(0, 1.0), (0, -1.0)]
+    assert terms("s - (a - b * s)") == [(0, -1.0), (0, 1.0), (1, 1.0)]            # -(a - b s) + s
+    assert terms("-(a + s) + c * s") == [(0, -1.0), (1, -1.0), (0, 1.0)]
+    assert terms("(a - s) + (b - c)") == [(0, 1.0), (1, -1.0), (0, 1.0)]          # b - c is parameter independent: a header array
+    assert terms("(a - s) + (b * s - c)") is None                                # two chains meet: the rounding differs
+    assert terms("a / s - b") is None                                            # division is not a term
+    assert terms("(a * s) * s - b") is None                                      # (a s) s: two roundings in one term
 
 
 def test_reference_error_cases():

@@ -126,15 +126,19 @@ if "cfg5" in which:
     init = [("tau", 20.0), ("mu", 10.0), ("sigma", 0.1)]
     rows = []
     for C in (1, 64, 4096):
-        for kind, kw, steps in (("rwm", {}, 20), ("hmc", dict(isteps=2, stepsize=1e-4), 10), ("nuts", {}, 4)):
+        for kind, kw, steps in (("rwm", {}, 200), ("hmc", dict(isteps=2, stepsize=2e-5), 100), ("nuts", {}, 8)):
             if C == 4096 and kind == "nuts":
                 continue
             low, dev = api._build(ORNSTEIN, init, dict(x=x), kind != "rwm", C, 0, "assign")
             dev.run(kind, np.array(low.init), C, 2, 0, seed=3, store_draws=False, want=(), **kw)      # warm-up: buffers sized, evaluation graph captured
             raw = dev.run(kind, np.array(low.init), C, steps, 0, seed=1, store_draws=False, want=(), **kw)
+            dev.eval(np.tile(np.array(low.init), (C, 1)), gradient=kind != "rwm")
+            ms_eval, ms_k = dev.eval_timed(20, True)       # eager evaluation (every kernel of the tape) and the AFFNORM launch alone, L2 flushed
             rows.append(dict(sampler=kind, chains=C, steps=steps, chain_steps_per_s=C * steps / (raw["device_ms"] * 1e-3),
                              evals_per_s=C * (raw["n_evals"] - 1) / (raw["device_ms"] * 1e-3), accept=float(raw["accept_rate"].mean()),
-                             launches=raw["n_kernel_launches"]))
+                             launches=raw["n_kernel_launches"], affnorm=low.n_affnorm, ms_eval_eager_l2_flushed=ms_eval, ms_affnorm_kernel=ms_k,
+                             kernel_GBs_algorithmic=8e6 / (ms_k * 1e-3) / 1e9 if ms_k > 0 else None,
+                             kernel_TFLOPs_20flop=20e6 * C / (ms_k * 1e-3) / 1e12 if ms_k > 0 else None))
             dev.close()
     out["cfg5_ornstein_T1e6"] = rows
     # labelled extra: the same model with the opt-in sufficient-statistics rewrite (3x3 Gram matrix of [x[t], x[t-1], 1])

@@ -16,15 +16,18 @@
 // Two kernels over the same argument block:
 //   k_affnorm_stream<CT>  (C <= 31): thread = element, CT chains in registers, loads straight from global memory -- bound
 //                          by HBM: 8 n bytes per launch when the arrays are views of one vector;
-//   k_affnorm_chains<CT>  (C >= 32): thread = chain(s), the arrays go through shared memory as broadcast reads -- bound
-//                          by the FP64 pipe: 3 T + 2 (1 + sums) flop per element and chain.
-// Per-block partial sums are combined by the last block to finish (ticket counter), in block order: deterministic.
+//   k_affnorm_chains<CT>  (C >= 32): thread = (chain lane, element phase), the arrays go through shared memory as broadcast
+//                          reads -- bound by the FP64 pipe: 3 T + 2 (1 + sums) flop per element and chain; its per-block
+//                          partial sums are combined by k_affnorm_finish (warp per chain over the blocks).
+// The stream kernel's partial sums are combined by its last block to finish (ticket counter).  Both orders are fixed:
+// deterministic.
 #include "exec_common.cuh"
 
 namespace {
 
 constexpr int AFF_MAX_T = 4;
 constexpr int AFF_MAX_SUM = 6;       // S2, up to four S_j, S1
+constexpr int AFF_STREAM_MAX_BLOCKS = 320;   // per chain group: the last block reads that many partials in one go
 
 struct AffArgs {
   int T, nsum, s1_slot;
@@ -156,15 +159,23 @@ __global__ void __launch_bounds__(256) k_affnorm_stream(AffArgs a) {
     a.part[((long long)blockIdx.x * a.nsum + slot) * a.cstride + c0 + c] = v;
   }
   if (!aff_take_ticket(a.counter + blockIdx.y, gridDim.x)) return;
-  // last block of this chain group: warp w sums values w, w + 8, ...; lane l takes blocks l, l + 32, ...
+  // last block of this chain group: warp w sums values w, w + 8, ...; lane l takes blocks l, l + 32, ... (at most
+  // AFF_STREAM_MAX_BLOCKS / 32 of them, all loads in flight at once), then a fixed xor tree over the lanes
   __shared__ double s_tot[AFF_MAX_SUM * CT];
   for (int v = warp; v < a.nsum * CT; v += 8) {
     const int slot = v / CT, c = v % CT;
-    double t = 0.0;
-    for (unsigned int b = lane; b < gridDim.x; b += 32) t += __ldcg(a.part + ((long long)b * a.nsum + slot) * a.cstride + c0 + c);
+    double t[AFF_STREAM_MAX_BLOCKS / 32];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-    if (lane == 0) s_tot[v] = t;
+    for (int k = 0; k < AFF_STREAM_MAX_BLOCKS / 32; k++) {
+      const unsigned int b = lane + 32u * k;
+      t[k] = b < gridDim.x ? __ldcg(a.part + ((long long)b * a.nsum + slot) * a.cstride + c0 + c) : 0.0;
+    }
+    double tt = 0.0;
+#pragma unroll
+    for (int k = 0; k < AFF_STREAM_MAX_BLOCKS / 32; k++) tt += t[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tt += __shfl_xor_sync(0xffffffffu, tt, o);
+    if (lane == 0) s_tot[v] = tt;
   }
   __syncthreads();
   if (tid < CT && c0 + tid < a.C) {
@@ -175,14 +186,15 @@ __global__ void __launch_bounds__(256) k_affnorm_stream(AffArgs a) {
   }
 }
 
-// ---- many chains: thread = CT chains, arrays broadcast from shared memory ---------------------------------------------------
+// ---- many chains: thread = (chain lane, element phase), CT chains per thread, arrays broadcast from shared memory ---------
 constexpr int AFF_TE = 1024;         // elements per shared-memory tile
+constexpr int AFF_NT = 128;          // threads per block = chain lanes x element phases
 
 template <int CT>
-__global__ void __launch_bounds__(128) k_affnorm_chains(AffArgs a) {
+__global__ void __launch_bounds__(AFF_NT) k_affnorm_chains(AffArgs a, int nlanes) {
   extern __shared__ double s_tile[];                                 // [array terms][AFF_TE]
-  const int tid = threadIdx.x, nthr = blockDim.x;
-  const long long cb = ((long long)blockIdx.y * nthr + tid) * CT;
+  const int tid = threadIdx.x, lanec = tid % nlanes, phase = tid / nlanes, nphase = AFF_NT / nlanes;
+  const long long cb = ((long long)blockIdx.y * nlanes + lanec) * CT;
   double sc[AFF_MAX_T][CT], mu[CT];
 #pragma unroll
   for (int c = 0; c < CT; c++) {
@@ -208,12 +220,16 @@ __global__ void __launch_bounds__(128) k_affnorm_chains(AffArgs a) {
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < AFF_MAX_T; j++)
-      if (j < a.T && a.kind[j] == 0)
-        for (int i = tid; i < AFF_TE; i += nthr) s_tile[row[j] * AFF_TE + i] = i < len ? __ldg(a.D[j] + te + i) : 0.0;
+      if (j < a.T && a.kind[j] == 0) {
+#pragma unroll
+        for (int i0 = 0; i0 < AFF_TE; i0 += AFF_NT) {
+          const int i = i0 + tid;
+          s_tile[row[j] * AFF_TE + i] = i < len ? __ldg(a.D[j] + te + i) : 0.0;
+        }
+      }
     __syncthreads();
-    // (elements beyond len are zeros in every array: their r is the scalar terms only -- skipped by the loop bound)
 #pragma unroll 4
-    for (int i = 0; i < len; i++) {
+    for (int i = phase; i < len; i += nphase) {
       double dv[AFF_MAX_T];
 #pragma unroll
       for (int j = 0; j < AFF_MAX_T; j++)
@@ -233,26 +249,54 @@ __global__ void __launch_bounds__(128) k_affnorm_chains(AffArgs a) {
       }
     }
   }
+  // element phases of one chain lane are summed in phase order through shared memory, then one partial per block
+  __syncthreads();
+  double* s_ph = s_tile;                                              // [phase][AFF_MAX_SUM * CT][nlanes] <= 4 x 12 x 32 doubles
+  if (nphase > 1) {
 #pragma unroll
-  for (int c = 0; c < CT; c++) {
-    double* p = a.part + (long long)blockIdx.x * a.nsum * a.cstride + cb + c;
-    p[0] = acc[0][c];
+    for (int k = 0; k < AFF_MAX_SUM; k++)
 #pragma unroll
-    for (int j = 0; j < AFF_MAX_T; j++)
-      if (j < a.T && a.slot[j] >= 0) p[(long long)a.slot[j] * a.cstride] = acc[1 + j][c];
-    if (a.s1_slot >= 0) p[(long long)a.s1_slot * a.cstride] = acc[AFF_MAX_SUM - 1][c];
+      for (int c = 0; c < CT; c++) s_ph[((phase * AFF_MAX_SUM + k) * CT + c) * nlanes + lanec] = acc[k][c];
+    __syncthreads();
+    if (phase == 0) {
+#pragma unroll
+      for (int k = 0; k < AFF_MAX_SUM; k++)
+#pragma unroll
+        for (int c = 0; c < CT; c++)
+          for (int ph = 1; ph < nphase; ph++) acc[k][c] += s_ph[((ph * AFF_MAX_SUM + k) * CT + c) * nlanes + lanec];
+    }
   }
-  if (!aff_take_ticket(a.counter + blockIdx.y, gridDim.x)) return;
+  if (phase == 0) {
 #pragma unroll
-  for (int c = 0; c < CT; c++) {
-    if (cb + c >= a.C) continue;
-    double S[AFF_MAX_SUM];
+    for (int c = 0; c < CT; c++) {
+      double* p = a.part + (long long)blockIdx.x * a.nsum * a.cstride + cb + c;
+      p[0] = acc[0][c];
 #pragma unroll
-    for (int k = 0; k < AFF_MAX_SUM; k++) S[k] = 0.0;
-    for (unsigned int b = 0; b < gridDim.x; b++)                      // block order: fixed
-      for (int k = 0; k < a.nsum; k++) S[k] += __ldcg(a.part + ((long long)b * a.nsum + k) * a.cstride + cb + c);
-    aff_finish_chain(a, cb + c, S);
+      for (int j = 0; j < AFF_MAX_T; j++)
+        if (j < a.T && a.slot[j] >= 0) p[(long long)a.slot[j] * a.cstride] = acc[1 + j][c];
+      if (a.s1_slot >= 0) p[(long long)a.s1_slot * a.cstride] = acc[AFF_MAX_SUM - 1][c];
+    }
   }
+}
+
+// finish of the chains kernel: block = 32 partial lanes x 8 chains; lane l sums blocks l, l + 32, ... in order, then a
+// fixed xor tree over the lanes (deterministic), then lane 0 writes L and the adjoint scalars of its chain
+__global__ void __launch_bounds__(256) k_affnorm_finish(AffArgs a, int nblocks) {
+  const int lane = threadIdx.x & 31;
+  const long long c = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (c >= a.C) return;
+  double S[AFF_MAX_SUM];
+#pragma unroll
+  for (int k = 0; k < AFF_MAX_SUM; k++) {
+    double t = 0.0;
+    if (k < a.nsum) {
+      for (int b = lane; b < nblocks; b += 32) t += __ldcg(a.part + ((long long)b * a.nsum + k) * a.cstride + c);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    }
+    S[k] = t;
+  }
+  if (lane == 0) aff_finish_chain(a, c, S);
 }
 
 }  // namespace
@@ -339,7 +383,8 @@ int smc_aff_launch(smc_model_s* m, SmcAffPlan& p, int64_t C) {
     const int CT = C <= 1 ? 1 : (C <= 2 ? 2 : (C <= 4 ? 4 : 8));
     const int U = CT <= 2 ? 8 : 4;
     const long long gy = (C + CT - 1) / CT;
-    long long gx = std::min<long long>((a.n + 256LL * U - 1) / (256LL * U), std::max<long long>(1, (long long)sms * 4 / gy));
+    long long gx = std::min<long long>((a.n + 256LL * U - 1) / (256LL * U), std::max<long long>(1, (long long)sms * 2 / gy));
+    gx = std::min<long long>(gx, AFF_STREAM_MAX_BLOCKS);
     a.cstride = gy * CT;
     SMC_TRY(smc_scratch_reserve(m, gx * nsum * a.cstride));
     a.part = m->scratch;
@@ -349,19 +394,22 @@ int smc_aff_launch(smc_model_s* m, SmcAffPlan& p, int64_t C) {
     else if (CT == 4) k_affnorm_stream<4><<<grid, 256, 0, st>>>(a);
     else k_affnorm_stream<8><<<grid, 256, 0, st>>>(a);
   } else {
-    const int CT = C >= 2048 ? 2 : 1;
-    int nthr = 128;
-    while (nthr > 32 && (long long)(nthr / 2) * CT >= C) nthr >>= 1;
-    const long long gy = (C + (long long)nthr * CT - 1) / ((long long)nthr * CT);
-    if (gy > 4096) { smc_set_error("AFFNORM: too many chains for one launch"); return SMC_ERR_INVALID; }
-    long long gx = std::max<long long>(1, std::min<long long>((a.n + 2047) / 2048, ((long long)sms * 16 * 32 / nthr + gy - 1) / gy));
-    a.cstride = gy * nthr * CT;
+    // chain lanes per block: 32, 64 or 128 (the other threads are element phases of the same chains); two chains per thread
+    // once there are enough chains to fill the device that way
+    const int CT = C >= 4096 ? 2 : 1;
+    int nlanes = 32;
+    while (nlanes < AFF_NT && (long long)nlanes * CT < C) nlanes <<= 1;
+    const long long gy = (C + (long long)nlanes * CT - 1) / ((long long)nlanes * CT);
+    long long gx = std::max<long long>(1, std::min<long long>((a.n + AFF_TE - 1) / AFF_TE, ((long long)sms * 3 + gy - 1) / gy));
+    a.cstride = gy * nlanes * CT;
     SMC_TRY(smc_scratch_reserve(m, gx * nsum * a.cstride));
     a.part = m->scratch;
     dim3 grid((unsigned)gx, (unsigned)gy);
-    const size_t smem = (size_t)std::max(narr, 1) * AFF_TE * sizeof(double);
-    if (CT == 1) k_affnorm_chains<1><<<grid, nthr, smem, st>>>(a);
-    else k_affnorm_chains<2><<<grid, nthr, smem, st>>>(a);
+    const size_t smem = (size_t)std::max(std::max(narr, 1) * AFF_TE, (AFF_NT / nlanes) * AFF_MAX_SUM * CT * nlanes) * sizeof(double);
+    if (CT == 1) k_affnorm_chains<1><<<grid, AFF_NT, smem, st>>>(a, nlanes);
+    else k_affnorm_chains<2><<<grid, AFF_NT, smem, st>>>(a, nlanes);
+    k_affnorm_finish<<<(unsigned)((C + 7) / 8), 256, 0, st>>>(a, (int)gx);
+    m->ctx->launches++;
   }
   m->ctx->launches++;
   if (m->time_glm) {

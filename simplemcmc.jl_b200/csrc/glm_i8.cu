@@ -194,7 +194,7 @@ struct GlmI8Args {
   int M, splits;
   double sx;            // scale of X
   double sigma;
-  int m0, m8, m16, m24; // 1, 2^8, 2^16, 2^24 (see halves())
+  int m0, m8, m16, m24, m28; // 1, 2^8, 2^16, 2^24, 2^28 (see halves())
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -208,7 +208,7 @@ __device__ __forceinline__ long long mad_wide(int a, int b, long long c) {
 // The group sums as two exact int64 halves: hi = sum_{g<4} a[g] 2^(8 (3 - g)), lo = the remaining groups likewise, each
 // on top of `bias`.  The multipliers arrive in registers (kernel arguments), so that every step is one IMAD.WIDE: with
 // literal powers of two ptxas expands each step into four or five 32-bit instructions.
-struct WideMul { int m0, m8, m16, m24; };
+struct WideMul { int m0, m8, m16, m24, m28; };
 template <int NB>
 __device__ __forceinline__ void halves(const int32_t* a, const WideMul& w, long long bias, long long& hi, long long& lo) {
   hi = mad_wide(a[0], w.m24, mad_wide(a[1], w.m16, mad_wide(a[2], w.m8, mad_wide(a[3], w.m0, bias))));
@@ -365,7 +365,7 @@ __global__ void __launch_bounds__(NTI, 1) k_glm_i8(GlmI8Args a) {   // 17 warps 
   // ================= epilogue warps =================
   const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
   const int ii = rl >> 6;
-  const WideMul wm = {a.m0, a.m8, a.m16, a.m24};
+  const WideMul wm = {a.m0, a.m8, a.m16, a.m24, a.m28};
   double lacc[CQ];
 #pragma unroll
   for (int c = 0; c < CQ; c++) lacc[c] = 0.0;
@@ -373,10 +373,10 @@ __global__ void __launch_bounds__(NTI, 1) k_glm_i8(GlmI8Args a) {   // 17 warps 
   double* part = a.part + (long long)blockIdx.y * (MP + 1) * a.Cpad;
   if (!issuer) {
     double d[CQ];
-    unsigned int E[CQ];                                   // sticky exponents (biased) of this thread's eight chains: the
-                                                          // same values in every thread of the chain quarter
+    unsigned int lim[CQ];                                 // (sticky exponent + 1) << 20 of this thread's eight chains: the high word
+                                                          // of the power-of-two scale; the same in every thread of the quarter
 #pragma unroll
-    for (int c = 0; c < CQ; c++) { d[c] = 0.0; E[c] = E_MIN; }
+    for (int c = 0; c < CQ; c++) { d[c] = 0.0; lim[c] = (E_MIN + 1u) << 20; }
     // epilogue 1 of tile t (its product 1 is the k-th completion of bar1): w = eta - y, sum w^2, max |w| -> s_max[k & 3]
     auto epilogue1 = [&](long long t, long long k) -> bool {
       const long long row = t * TR + rl;
@@ -384,6 +384,7 @@ __global__ void __launch_bounds__(NTI, 1) k_glm_i8(GlmI8Args a) {   // 17 warps 
       if (!mbar_wait(&bar1, (uint32_t)(k & 1))) return false;
       fence_after();
       unsigned int hw[CQ];
+      bool over = false;
 #pragma unroll
       for (int hf = 0; hf < 2; hf++) {                      // four chains at a time (registers)
         int32_t acc[NB][4];
@@ -396,26 +397,32 @@ __global__ void __launch_bounds__(NTI, 1) k_glm_i8(GlmI8Args a) {   // 17 warps 
           int32_t g[NB];
 #pragma unroll
           for (int cb = 0; cb < NB; cb++) g[cb] = acc[cb][v];
-          long long hi, lo;
-          halves<NB>(g, wm, MAGIC_BITS, hi, lo);
+          // neighbouring groups pair up exactly in int32 (a group sum is below 2^23: at most 8 pairs x 64 terms x 2^14), the
+          // pairs in two int64 halves on top of the magic bias: seven instructions instead of fourteen
+          const int b0 = g[0] * 256 + g[1], b1 = g[2] * 256 + g[3], b2 = g[4] * 256 + g[5];
+          const int b3 = NB == 8 ? g[6] * 256 + g[7] : g[6];
+          const long long hi = mad_wide(b0, wm.m16, mad_wide(b1, wm.m0, MAGIC_BITS));
+          const long long lo = mad_wide(b2, NB == 8 ? wm.m16 : wm.m8, mad_wide(b3, wm.m0, MAGIC_BITS));
           const double4 sc = s_sc[q * CQ + u];
           const double w = (fma(__longlong_as_double(hi), sc.x, sc.z) + fma(__longlong_as_double(lo), sc.y, sc.w)) - yr;
           d[u] = w;
           lacc[u] = fma(w, w, lacc[u]);
           hw[u] = (unsigned int)__double2hiint(w) & 0x7fffffffu;
+          over = over || hw[u] >= lim[u];
         }
       }
+      // fast path: no |w| of this warp reaches its chain's sticky scale (the usual case after the first tile).  Otherwise the
+      // warp publishes its maxima and raises the flag; warps below their limits need not contribute (their maxima are
+      // below the limit the new maximum exceeds).
+      if (__any_sync(0xffffffffu, over)) {
 #pragma unroll
-      for (int u = 0; u < CQ; u++) hw[u] = __reduce_max_sync(0xffffffffu, hw[u]);
-      if (lane == 0) {
-        const int b = (int)(k & 3);
-        bool grow = false;
+        for (int u = 0; u < CQ; u++) hw[u] = __reduce_max_sync(0xffffffffu, hw[u]);
+        if (lane == 0) {
+          const int b = (int)(k & 3);
 #pragma unroll
-        for (int u = 0; u < CQ; u++) {
-          atomicMax(&s_max[b][q * CQ + u], hw[u]);
-          grow = grow || (hw[u] >> 20) > E[u];
+          for (int u = 0; u < CQ; u++) atomicMax(&s_max[b][q * CQ + u], hw[u]);
+          s_flag[b] = 1;
         }
-        if (grow) s_flag[b] = 1;
       }
       return true;
     };
@@ -440,7 +447,7 @@ __global__ void __launch_bounds__(NTI, 1) k_glm_i8(GlmI8Args a) {   // 17 warps 
           for (int cb = 0; cb < NS8; cb++) g[cb] = acc[cb][v];
           long long hi, lo;
           halves<7>(g, wm, 0ll, hi, lo);
-          const double sc = a.sx * __longlong_as_double((long long)((unsigned long long)(E[u] + 1u) << 52));
+          const double sc = a.sx * __hiloint2double((int)lim[u], 0);                // 2^(E + 1 - 1023)
           val[u] = fma((double)hi, ii ? 0x1p-44 : 0x1p-36, (double)lo * (ii ? 0x1p-68 : 0x1p-60)) * (sc * neg_inv_s2);
         }
       }
@@ -477,18 +484,32 @@ __global__ void __launch_bounds__(NTI, 1) k_glm_i8(GlmI8Args a) {   // 17 warps 
         }
 #pragma unroll
         for (int u = 0; u < CQ; u++) {
-          unsigned int e = min(s_max[b][q * CQ + u] >> 20, E_MAX);
-          if (e > E[u]) E[u] = e + 1u;
+          const unsigned int e = min(s_max[b][q * CQ + u] >> 20, E_MAX);
+          if (((e + 1u) << 20) > lim[u]) lim[u] = (e + 2u) << 20;       // one binade of headroom: growth stays rare
         }
         cnt = 0;
       }
       cnt++;
       // this tile's slice buffer was last read by product 2 of tile t-2
       if (k >= 2 && !mbar_wait(&bar2[stage], (uint32_t)(((k - 2) >> 1) & 1))) { ok = false; break; }
+      // w 2^54 / scale (|.| < 2^54) as an integer without the conversion unit: two magic-number roundings.
+      //   h = round(w f 2^-28) sits in the low mantissa word of fma(w, f 2^-28, MAGIC + bias_h); the remainder w f - h 2^28 is
+      //   exact (fma) and below 2^27 in magnitude, l = its rounding to an integer sits in the low word of (remainder + MAGIC
+      //   + bias_l).  The biases fold the +0x80..80 of the balanced-byte form (and keep the low part non-negative):
+      //   h 2^28 + l + H8 = (h + Hh - 1) 2^28 + (l + Hl + 2^28),  H8 = Hh 2^28 + Hl.
+      constexpr unsigned long long Hh = H8 >> 28, Hl = H8 & ((1ull << 28) - 1);
+      constexpr double MU = MAGIC + (double)(long long)(Hh - 1), MW = MAGIC + (double)(long long)(Hl + (1ull << 28));
       uint32_t xl[CQ], xh[CQ];
 #pragma unroll
       for (int u = 0; u < CQ; u++) {
-        const unsigned long long w = slice7_bits(d[u], E[u]);   // w 2^54 / scale, truncated, as balanced bytes: byte k = slice 6 - k
+        const double f = __hiloint2double((int)((2100u << 20) - lim[u]), 0);        // 2^54 / scale = 2^(1076 - E)
+        const double f28 = __hiloint2double((int)((2072u << 20) - lim[u]), 0);      // f 2^-28
+        const double uu = fma(d[u], f28, MU);
+        const double hs = (uu - MU) * -0x1p28;
+        const double ww = fma(d[u], f, hs) + MW;
+        const unsigned long long t = (unsigned long long)mad_wide(__double2loint(uu), wm.m28,
+                                                                   (long long)(unsigned long long)(unsigned int)__double2loint(ww));
+        const unsigned long long w = t ^ H8;                // byte k = slice 6 - k
         xl[u] = (uint32_t)w;
         xh[u] = (uint32_t)(w >> 32);
       }
@@ -631,7 +652,7 @@ int smc_glm_i8_launch(smc_model_s* m, SmcGlmPlan& g, const double* beta, int64_t
   GlmI8Args a;
   a.QX = g.QX8; a.y = g.y; a.beta = beta; a.part = part; a.status = g.i8_status;
   a.N = g.N; a.tiles = tiles; a.C = C; a.Cpad = Cpad; a.M = g.M; a.splits = RS; a.sx = g.sx8; a.sigma = g.par;
-  a.m0 = 1; a.m8 = 1 << 8; a.m16 = 1 << 16; a.m24 = 1 << 24;
+  a.m0 = 1; a.m8 = 1 << 8; a.m16 = 1 << 16; a.m24 = 1 << 24; a.m28 = 1 << 28;
   dim3 grid((unsigned)smc_glm_i8_chain_tiles(C), (unsigned)RS);
   static int beta8 = -1;
   if (beta8 < 0) { const char* e = getenv("SMC_GLM_I8_BETA8"); beta8 = (e && e[0] == '1') ? 1 : 0; }

@@ -986,7 +986,11 @@ class Lowering(object):
             v.reg = i
         # AFFNORM descriptors travel as index tables (register numbers are known only now):
         #   [T, reg(dL/dmu) or -1, reg(dL/dsigma) or -1,  then per term: kind, sign, array reg or -1, offset, scalar reg, reg(dL/ds) or -1]
-        tables = list(self.idx_tables)
+        # (index tables no surviving statement refers to -- e.g. the ranges of x[2:end] once AFFNORM reads x as views -- stay home)
+        idx_ops = (OP["GATHER"], OP["SCATTER_SET"], OP["SCATTER_ADD"])
+        idx_used = sorted({st.aux0 for st in stmts if st.op in idx_ops})
+        idx_map = {old: new for new, old in enumerate(idx_used)}
+        tables = [self.idx_tables[i] for i in idx_used]
         aff_table = {}
         for st in stmts:
             if st.op == OP["AFFNORM"]:
@@ -1010,6 +1014,8 @@ class Lowering(object):
             out.append(struct.pack("<4Iqd", v.kind, rows, cols, len(v.shape), aux, v.imm))
         for st in stmts:
             srcs, aux0 = st.srcs, st.aux0
+            if st.op in idx_ops:
+                aux0 = idx_map[st.aux0]
             if st.op == OP["AFFNORM"]:
                 srcs, aux0 = st.srcs[:2], aff_table[id(st)]          # (mu, sigma); everything else is in the descriptor
             src = [s.reg for s in srcs] + [0] * (4 - len(srcs))

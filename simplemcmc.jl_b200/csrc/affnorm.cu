@@ -21,13 +21,14 @@
 //                          partial sums are combined by k_affnorm_finish (warp per chain over the blocks).
 // The stream kernel's partial sums are combined by its last block to finish (ticket counter).  Both orders are fixed:
 // deterministic.
+#include <stdlib.h>
 #include "exec_common.cuh"
 
 namespace {
 
 constexpr int AFF_MAX_T = 4;
 constexpr int AFF_MAX_SUM = 6;       // S2, up to four S_j, S1
-constexpr int AFF_STREAM_MAX_BLOCKS = 320;   // per chain group: the last block reads that many partials in one go
+constexpr int AFF_STREAM_MAX_BLOCKS = 512;   // per chain group: the last block reads that many partials in one go
 
 struct AffArgs {
   int T, nsum, s1_slot;
@@ -46,6 +47,56 @@ struct AffArgs {
 };
 
 __device__ __forceinline__ double opd_scalar(const Opd& o, long long c) { return o.is_imm ? o.imm : o.p[c * o.sc]; }
+
+// Compile-time shape of the residual (the element loop is issue bound: with the term kinds as run-time fields it was
+// ~70 instructions per element, 13 of them FP64, 244 us for T = 1e6 x 64 chains; profiles/cfg5_launches_r02.json).
+//   bits 0-1: number of terms - 1;  bits 2-9: two bits per term (0: array * scalar, 1: scalar, 2: +array, 3: -array);
+//   bits 10-13: the term's sum S_j is needed (array * scalar terms);  bit 14: S1 is needed;  bit 15: mu is the literal 0.
+// AFF_GENERIC keeps every decision at run time (any residual the lowering can emit).
+constexpr unsigned AFF_GENERIC = 0xFFFFFFFFu;
+constexpr unsigned aff_pat(int T, int k0, int k1, int k2, int k3, int need, int s1, int mu0) {
+  return (unsigned)(T - 1) | (k0 << 2) | (k1 << 4) | (k2 << 6) | (k3 << 8) | (need << 10) | (s1 << 14) | (mu0 << 15);
+}
+constexpr unsigned AFF_P_OU = aff_pat(3, 2, 0, 1, 0, 0b0010, 1, 1);      // x[2:end] - x[1:end-1] * s - c      ~ Normal(0, sigma)
+constexpr unsigned AFF_P_YXB = aff_pat(2, 2, 0, 0, 0, 0b0010, 0, 1);     // y - x * b                          ~ Normal(0, sigma)
+constexpr unsigned AFF_P_XBY = aff_pat(2, 0, 3, 0, 0, 0b0001, 0, 1);     // x * b - y
+constexpr unsigned AFF_P_YXBC = aff_pat(3, 2, 0, 0, 0, 0b0110, 0, 1);    // y - x1 * b1 - x2 * b2
+template <unsigned PAT>
+struct AffPat {
+  static constexpr bool GEN = PAT == AFF_GENERIC;
+  static constexpr int T = GEN ? AFF_MAX_T : (int)(PAT & 3u) + 1;
+  __device__ static __forceinline__ bool is_array(const AffArgs& a, int j) {
+    return GEN ? (j < a.T && a.kind[j] == 0) : (j < T && ((PAT >> (2 + 2 * j)) & 3u) != 1u);
+  }
+  __device__ static __forceinline__ bool live(const AffArgs& a, int j) { return GEN ? j < a.T : j < T; }
+  // signed value of term j (sc = sign * scalar)
+  __device__ static __forceinline__ double term(const AffArgs& a, int j, double dv, double sc) {
+    if (GEN) return a.kind[j] == 0 ? __dmul_rn(dv, sc) : sc;
+    const unsigned k = (PAT >> (2 + 2 * j)) & 3u;
+    return k == 0u ? __dmul_rn(dv, sc) : (k == 1u ? sc : (k == 2u ? dv : -dv));
+  }
+  __device__ static __forceinline__ bool need(const AffArgs& a, int j) {
+    return GEN ? (j < a.T && a.slot[j] >= 0) : (j < T && ((PAT >> (10 + j)) & 1u) != 0u);
+  }
+  __device__ static __forceinline__ bool need_s1(const AffArgs& a) { return GEN ? true : ((PAT >> 14) & 1u) != 0u; }
+  __device__ static __forceinline__ bool mu_zero() { return GEN ? false : ((PAT >> 15) & 1u) != 0u; }
+};
+// r - mu of one element and one chain, and its contribution to the sums
+template <unsigned PAT>
+__device__ __forceinline__ void aff_element(const AffArgs& a, const double (&dv)[AFF_MAX_T], const double (&sc)[AFF_MAX_T], double mu,
+                                            double (&acc)[AFF_MAX_SUM]) {
+  typedef AffPat<PAT> P;
+  double v = P::term(a, 0, dv[0], sc[0]);
+#pragma unroll
+  for (int j = 1; j < AFF_MAX_T; j++)
+    if (P::live(a, j)) v = __dadd_rn(v, P::term(a, j, dv[j], sc[j]));
+  const double d = P::mu_zero() ? v : __dsub_rn(v, mu);
+  acc[0] = fma(d, d, acc[0]);
+#pragma unroll
+  for (int j = 0; j < AFF_MAX_T; j++)
+    if (P::need(a, j)) acc[1 + j] = fma(d, dv[j], acc[1 + j]);
+  if (P::need_s1(a)) acc[AFF_MAX_SUM - 1] += d;
+}
 
 // the last block of a chain group finishes: (S2, S_j, S1) -> L and the adjoint scalars of chain c
 __device__ __forceinline__ void aff_finish_chain(const AffArgs& a, long long c, const double* S) {
@@ -81,53 +132,42 @@ __device__ __forceinline__ bool aff_take_ticket(unsigned int* counter, unsigned 
 }
 
 // ---- few chains: thread = element, CT chains in registers ----------------------------------------------------------------
-template <int CT>
+template <int CT, unsigned PAT>
 __global__ void __launch_bounds__(256) k_affnorm_stream(AffArgs a) {
+  typedef AffPat<PAT> P;
   constexpr int U = (CT <= 2) ? 8 : 4;                               // elements in flight per thread
   const int tid = threadIdx.x;
   const long long c0 = (long long)blockIdx.y * CT;
-  double sc[AFF_MAX_T][CT], mu[CT];
+  double sc[CT][AFF_MAX_T], mu[CT];
 #pragma unroll
   for (int c = 0; c < CT; c++) {
     const long long ch = c0 + c < a.C ? c0 + c : a.C - 1;             // padding lanes repeat the last chain
     mu[c] = opd_scalar(a.mu, ch);
 #pragma unroll
-    for (int j = 0; j < AFF_MAX_T; j++) sc[j][c] = j < a.T ? a.sgn[j] * opd_scalar(a.s[j], ch) : 0.0;
+    for (int j = 0; j < AFF_MAX_T; j++) sc[c][j] = P::live(a, j) ? a.sgn[j] * opd_scalar(a.s[j], ch) : 0.0;
   }
-  double acc[AFF_MAX_SUM][CT];
+  double acc[CT][AFF_MAX_SUM];
 #pragma unroll
-  for (int k = 0; k < AFF_MAX_SUM; k++)
+  for (int c = 0; c < CT; c++)
 #pragma unroll
-    for (int c = 0; c < CT; c++) acc[k][c] = 0.0;
+    for (int k = 0; k < AFF_MAX_SUM; k++) acc[c][k] = 0.0;
 
   const long long stride = (long long)gridDim.x * 256 * U;
   for (long long e0 = (long long)blockIdx.x * 256 * U + tid; e0 < a.n; e0 += stride) {
-    double dv[AFF_MAX_T][U];
+    double dv[U][AFF_MAX_T];
 #pragma unroll
-    for (int j = 0; j < AFF_MAX_T; j++)
-      if (j < a.T && a.kind[j] == 0) {
+    for (int j = 0; j < AFF_MAX_T; j++) {
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-          const long long e = e0 + (long long)u * 256;
-          dv[j][u] = e < a.n ? __ldg(a.D[j] + e) : 0.0;
-        }
+      for (int u = 0; u < U; u++) {
+        const long long e = e0 + (long long)u * 256;
+        dv[u][j] = (P::is_array(a, j) && e < a.n) ? __ldg(a.D[j] + e) : 0.0;
       }
+    }
 #pragma unroll
     for (int u = 0; u < U; u++) {
       if (e0 + (long long)u * 256 < a.n) {
 #pragma unroll
-        for (int c = 0; c < CT; c++) {
-          double v = a.kind[0] == 0 ? __dmul_rn(dv[0][u], sc[0][c]) : sc[0][c];
-#pragma unroll
-          for (int j = 1; j < AFF_MAX_T; j++)
-            if (j < a.T) v = __dadd_rn(v, a.kind[j] == 0 ? __dmul_rn(dv[j][u], sc[j][c]) : sc[j][c]);
-          const double d = __dsub_rn(v, mu[c]);
-          acc[0][c] = fma(d, d, acc[0][c]);
-#pragma unroll
-          for (int j = 0; j < AFF_MAX_T; j++)
-            if (j < a.T && a.slot[j] >= 0) acc[1 + j][c] = fma(d, dv[j][u], acc[1 + j][c]);
-          acc[AFF_MAX_SUM - 1][c] += d;
-        }
+        for (int c = 0; c < CT; c++) aff_element<PAT>(a, dv[u], sc[c], mu[c], acc[c]);
       }
     }
   }
@@ -138,7 +178,7 @@ __global__ void __launch_bounds__(256) k_affnorm_stream(AffArgs a) {
   for (int k = 0; k < AFF_MAX_SUM; k++)
 #pragma unroll
     for (int c = 0; c < CT; c++) {
-      double v = acc[k][c];
+      double v = acc[c][k];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
       if (lane == 0) s_red[warp][k * CT + c] = v;
@@ -190,28 +230,29 @@ __global__ void __launch_bounds__(256) k_affnorm_stream(AffArgs a) {
 constexpr int AFF_TE = 1024;         // elements per shared-memory tile
 constexpr int AFF_NT = 128;          // threads per block = chain lanes x element phases
 
-template <int CT>
+template <int CT, unsigned PAT>
 __global__ void __launch_bounds__(AFF_NT) k_affnorm_chains(AffArgs a, int nlanes) {
+  typedef AffPat<PAT> P;
   extern __shared__ double s_tile[];                                 // [array terms][AFF_TE]
   const int tid = threadIdx.x, lanec = tid % nlanes, phase = tid / nlanes, nphase = AFF_NT / nlanes;
   const long long cb = ((long long)blockIdx.y * nlanes + lanec) * CT;
-  double sc[AFF_MAX_T][CT], mu[CT];
+  double sc[CT][AFF_MAX_T], mu[CT];
 #pragma unroll
   for (int c = 0; c < CT; c++) {
     const long long ch = cb + c < a.C ? cb + c : a.C - 1;
     mu[c] = opd_scalar(a.mu, ch);
 #pragma unroll
-    for (int j = 0; j < AFF_MAX_T; j++) sc[j][c] = j < a.T ? a.sgn[j] * opd_scalar(a.s[j], ch) : 0.0;
+    for (int j = 0; j < AFF_MAX_T; j++) sc[c][j] = P::live(a, j) ? a.sgn[j] * opd_scalar(a.s[j], ch) : 0.0;
   }
-  double acc[AFF_MAX_SUM][CT];
+  double acc[CT][AFF_MAX_SUM];
 #pragma unroll
-  for (int k = 0; k < AFF_MAX_SUM; k++)
+  for (int c = 0; c < CT; c++)
 #pragma unroll
-    for (int c = 0; c < CT; c++) acc[k][c] = 0.0;
+    for (int k = 0; k < AFF_MAX_SUM; k++) acc[c][k] = 0.0;
   int row[AFF_MAX_T];                                                // tile row of an array term
   int nrow = 0;
 #pragma unroll
-  for (int j = 0; j < AFF_MAX_T; j++) row[j] = (j < a.T && a.kind[j] == 0) ? nrow++ : 0;
+  for (int j = 0; j < AFF_MAX_T; j++) row[j] = P::is_array(a, j) ? nrow++ : 0;
 
   const long long per = (a.n + gridDim.x - 1) / gridDim.x;
   const long long e_begin = (long long)blockIdx.x * per, e_end = e_begin + per < a.n ? e_begin + per : a.n;
@@ -220,7 +261,7 @@ __global__ void __launch_bounds__(AFF_NT) k_affnorm_chains(AffArgs a, int nlanes
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < AFF_MAX_T; j++)
-      if (j < a.T && a.kind[j] == 0) {
+      if (P::is_array(a, j)) {
 #pragma unroll
         for (int i0 = 0; i0 < AFF_TE; i0 += AFF_NT) {
           const int i = i0 + tid;
@@ -228,25 +269,28 @@ __global__ void __launch_bounds__(AFF_NT) k_affnorm_chains(AffArgs a, int nlanes
         }
       }
     __syncthreads();
-#pragma unroll 4
-    for (int i = phase; i < len; i += nphase) {
+    // this thread's elements of the tile: phase, phase + nphase, ...; four at a time so that the loads and the four
+    // dependent FP64 chains of consecutive elements overlap
+    const int cnt = len > phase ? (len - phase + nphase - 1) / nphase : 0;
+    const double* tp = s_tile + phase;
+    int k = 0;
+    for (; k + 4 <= cnt; k += 4) {
+      double dv[4][AFF_MAX_T];
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+#pragma unroll
+        for (int j = 0; j < AFF_MAX_T; j++) dv[u][j] = P::is_array(a, j) ? tp[row[j] * AFF_TE + (k + u) * nphase] : 0.0;
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+#pragma unroll
+        for (int c = 0; c < CT; c++) aff_element<PAT>(a, dv[u], sc[c], mu[c], acc[c]);
+    }
+    for (; k < cnt; k++) {
       double dv[AFF_MAX_T];
 #pragma unroll
-      for (int j = 0; j < AFF_MAX_T; j++)
-        if (j < a.T && a.kind[j] == 0) dv[j] = s_tile[row[j] * AFF_TE + i];
+      for (int j = 0; j < AFF_MAX_T; j++) dv[j] = P::is_array(a, j) ? tp[row[j] * AFF_TE + k * nphase] : 0.0;
 #pragma unroll
-      for (int c = 0; c < CT; c++) {
-        double v = a.kind[0] == 0 ? __dmul_rn(dv[0], sc[0][c]) : sc[0][c];
-#pragma unroll
-        for (int j = 1; j < AFF_MAX_T; j++)
-          if (j < a.T) v = __dadd_rn(v, a.kind[j] == 0 ? __dmul_rn(dv[j], sc[j][c]) : sc[j][c]);
-        const double d = __dsub_rn(v, mu[c]);
-        acc[0][c] = fma(d, d, acc[0][c]);
-#pragma unroll
-        for (int j = 0; j < AFF_MAX_T; j++)
-          if (j < a.T && a.slot[j] >= 0) acc[1 + j][c] = fma(d, dv[j], acc[1 + j][c]);
-        acc[AFF_MAX_SUM - 1][c] += d;
-      }
+      for (int c = 0; c < CT; c++) aff_element<PAT>(a, dv, sc[c], mu[c], acc[c]);
     }
   }
   // element phases of one chain lane are summed in phase order through shared memory, then one partial per block
@@ -256,25 +300,25 @@ __global__ void __launch_bounds__(AFF_NT) k_affnorm_chains(AffArgs a, int nlanes
 #pragma unroll
     for (int k = 0; k < AFF_MAX_SUM; k++)
 #pragma unroll
-      for (int c = 0; c < CT; c++) s_ph[((phase * AFF_MAX_SUM + k) * CT + c) * nlanes + lanec] = acc[k][c];
+      for (int c = 0; c < CT; c++) s_ph[((phase * AFF_MAX_SUM + k) * CT + c) * nlanes + lanec] = acc[c][k];
     __syncthreads();
     if (phase == 0) {
 #pragma unroll
       for (int k = 0; k < AFF_MAX_SUM; k++)
 #pragma unroll
         for (int c = 0; c < CT; c++)
-          for (int ph = 1; ph < nphase; ph++) acc[k][c] += s_ph[((ph * AFF_MAX_SUM + k) * CT + c) * nlanes + lanec];
+          for (int ph = 1; ph < nphase; ph++) acc[c][k] += s_ph[((ph * AFF_MAX_SUM + k) * CT + c) * nlanes + lanec];
     }
   }
   if (phase == 0) {
 #pragma unroll
     for (int c = 0; c < CT; c++) {
       double* p = a.part + (long long)blockIdx.x * a.nsum * a.cstride + cb + c;
-      p[0] = acc[0][c];
+      p[0] = acc[c][0];
 #pragma unroll
       for (int j = 0; j < AFF_MAX_T; j++)
-        if (j < a.T && a.slot[j] >= 0) p[(long long)a.slot[j] * a.cstride] = acc[1 + j][c];
-      if (a.s1_slot >= 0) p[(long long)a.s1_slot * a.cstride] = acc[AFF_MAX_SUM - 1][c];
+        if (j < a.T && a.slot[j] >= 0) p[(long long)a.slot[j] * a.cstride] = acc[c][1 + j];
+      if (a.s1_slot >= 0) p[(long long)a.s1_slot * a.cstride] = acc[c][AFF_MAX_SUM - 1];
     }
   }
 }
@@ -300,6 +344,38 @@ __global__ void __launch_bounds__(256) k_affnorm_finish(AffArgs a, int nblocks) 
 }
 
 }  // namespace
+
+template <unsigned PAT>
+static void launch_stream(const AffArgs& a, int CT, dim3 grid, cudaStream_t st) {
+  if (CT == 1) k_affnorm_stream<1, PAT><<<grid, 256, 0, st>>>(a);
+  else if (CT == 2) k_affnorm_stream<2, PAT><<<grid, 256, 0, st>>>(a);
+  else if (CT == 4) k_affnorm_stream<4, PAT><<<grid, 256, 0, st>>>(a);
+  else k_affnorm_stream<8, PAT><<<grid, 256, 0, st>>>(a);
+}
+template <unsigned PAT>
+static void launch_chains(const AffArgs& a, int CT, int nlanes, dim3 grid, size_t smem, cudaStream_t st) {
+  if (CT == 1) k_affnorm_chains<1, PAT><<<grid, AFF_NT, smem, st>>>(a, nlanes);
+  else k_affnorm_chains<2, PAT><<<grid, AFF_NT, smem, st>>>(a, nlanes);
+}
+// the compile-time pattern of a statement, or AFF_GENERIC
+static unsigned aff_pattern_of(const smc_model_s* m, const smc_tape_stmt& s, const std::vector<int32_t>& d, const AffArgs& a) {
+  int k[AFF_MAX_T] = {0, 0, 0, 0}, need = 0;
+  for (int j = 0; j < a.T; j++) {
+    const int32_t* t = &d[3 + 6 * j];
+    const SmcReg& sr = m->regs[t[4]];
+    if (t[0] == 1) k[j] = 1;
+    else if (sr.d.kind == SMC_REG_IMM && sr.d.imm == 1.0 && t[5] < 0) k[j] = t[1] > 0 ? 2 : 3;
+    else k[j] = 0;
+    if (k[j] == 0 && t[5] >= 0) need |= 1 << j;
+    if (k[j] == 0 && t[5] < 0) return AFF_GENERIC;       // array * constant: not among the compiled shapes
+  }
+  const SmcReg& mr = m->regs[s.src[0]];
+  const int mu0 = (mr.d.kind == SMC_REG_IMM && mr.d.imm == 0.0) ? 1 : 0;
+  const unsigned pat = aff_pat(a.T, k[0], k[1], k[2], k[3], need, a.s1_slot >= 0 ? 1 : 0, mu0);
+  for (unsigned known : {AFF_P_OU, AFF_P_YXB, AFF_P_XBY, AFF_P_YXBC})
+    if (pat == known) return pat;
+  return AFF_GENERIC;
+}
 
 // descriptor (an index table of the tape, see lowering.py::serialise):
 //   [T, reg(dL/dmu) | -1, reg(dL/dsigma) | -1, then per term: kind, sign, array reg | -1, offset, scalar reg, reg(dL/ds) | -1]
@@ -330,11 +406,6 @@ int smc_aff_prepare(smc_model_s* m, SmcAffPlan& p) {
   if (!p.counter) {
     SMC_CUDA(smc_dev_alloc(&p.counter, 4096 * sizeof(unsigned int), m->ctx->stream));
     SMC_CUDA(cudaMemsetAsync(p.counter, 0, 4096 * sizeof(unsigned int), m->ctx->stream));
-  }
-  static SmcOncePerDevice once;
-  if (once.first()) {
-    SMC_CUDA(cudaFuncSetAttribute(k_affnorm_chains<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AFF_MAX_T * AFF_TE * 8));
-    SMC_CUDA(cudaFuncSetAttribute(k_affnorm_chains<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, AFF_MAX_T * AFF_TE * 8));
   }
   return SMC_OK;
 }
@@ -378,21 +449,27 @@ int smc_aff_launch(smc_model_s* m, SmcAffPlan& p, int64_t C) {
   a.nsum = nsum;
   a.counter = p.counter;
   const int sms = m->ctx->sm_count;
+  static int force_generic = -1;
+  if (force_generic < 0) { const char* e = getenv("SMC_AFFNORM_GENERIC"); force_generic = (e && e[0] == '1') ? 1 : 0; }
+  const unsigned pat = force_generic ? AFF_GENERIC : aff_pattern_of(m, s, d, a);
   if (m->time_glm) SMC_CUDA(cudaEventRecord(m->ev0, st));
   if (C < 32) {
     const int CT = C <= 1 ? 1 : (C <= 2 ? 2 : (C <= 4 ? 4 : 8));
     const int U = CT <= 2 ? 8 : 4;
     const long long gy = (C + CT - 1) / CT;
-    long long gx = std::min<long long>((a.n + 256LL * U - 1) / (256LL * U), std::max<long long>(1, (long long)sms * 2 / gy));
+    long long gx = std::min<long long>((a.n + 256LL * U - 1) / (256LL * U), std::max<long long>(1, (long long)sms * 4 / gy));
     gx = std::min<long long>(gx, AFF_STREAM_MAX_BLOCKS);
     a.cstride = gy * CT;
     SMC_TRY(smc_scratch_reserve(m, gx * nsum * a.cstride));
     a.part = m->scratch;
     dim3 grid((unsigned)gx, (unsigned)gy);
-    if (CT == 1) k_affnorm_stream<1><<<grid, 256, 0, st>>>(a);
-    else if (CT == 2) k_affnorm_stream<2><<<grid, 256, 0, st>>>(a);
-    else if (CT == 4) k_affnorm_stream<4><<<grid, 256, 0, st>>>(a);
-    else k_affnorm_stream<8><<<grid, 256, 0, st>>>(a);
+    switch (pat) {
+      case AFF_P_OU: launch_stream<AFF_P_OU>(a, CT, grid, st); break;
+      case AFF_P_YXB: launch_stream<AFF_P_YXB>(a, CT, grid, st); break;
+      case AFF_P_XBY: launch_stream<AFF_P_XBY>(a, CT, grid, st); break;
+      case AFF_P_YXBC: launch_stream<AFF_P_YXBC>(a, CT, grid, st); break;
+      default: launch_stream<AFF_GENERIC>(a, CT, grid, st);
+    }
   } else {
     // chain lanes per block: 32, 64 or 128 (the other threads are element phases of the same chains); two chains per thread
     // once there are enough chains to fill the device that way
@@ -406,8 +483,13 @@ int smc_aff_launch(smc_model_s* m, SmcAffPlan& p, int64_t C) {
     a.part = m->scratch;
     dim3 grid((unsigned)gx, (unsigned)gy);
     const size_t smem = (size_t)std::max(std::max(narr, 1) * AFF_TE, (AFF_NT / nlanes) * AFF_MAX_SUM * CT * nlanes) * sizeof(double);
-    if (CT == 1) k_affnorm_chains<1><<<grid, AFF_NT, smem, st>>>(a, nlanes);
-    else k_affnorm_chains<2><<<grid, AFF_NT, smem, st>>>(a, nlanes);
+    switch (pat) {
+      case AFF_P_OU: launch_chains<AFF_P_OU>(a, CT, nlanes, grid, smem, st); break;
+      case AFF_P_YXB: launch_chains<AFF_P_YXB>(a, CT, nlanes, grid, smem, st); break;
+      case AFF_P_XBY: launch_chains<AFF_P_XBY>(a, CT, nlanes, grid, smem, st); break;
+      case AFF_P_YXBC: launch_chains<AFF_P_YXBC>(a, CT, nlanes, grid, smem, st); break;
+      default: launch_chains<AFF_GENERIC>(a, CT, nlanes, grid, smem, st);
+    }
     k_affnorm_finish<<<(unsigned)((C + 7) / 8), 256, 0, st>>>(a, (int)gx);
     m->ctx->launches++;
   }

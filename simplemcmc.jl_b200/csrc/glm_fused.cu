@@ -1019,7 +1019,8 @@ int smc_glm_launch(smc_model_s* m, SmcGlmPlan& g, int64_t C) {
   long long rows_per_split = ((g.N + RS - 1) / RS + RT - 1) / RT * RT;
   RS = (int)((g.N + rows_per_split - 1) / rows_per_split);
   if (stream) RS = (int)std::max<long long>(1, std::min<long long>((g.N + 255) / 256, 2LL * m->ctx->sm_count));
-  // opt-in (SMC_GLM_I8=1): the sliced-integer kernel on the int8 tensor cores, 32-chain tiles x 128-row tiles (glm_i8.cu)
+  // Normal family, 33-64 columns, >= 32 chains: the sliced-integer kernel on the int8 tensor cores, 32-chain tiles x 128-row
+  // tiles (glm_i8.cu; SMC_GLM_I8=0 keeps the FP64 DMMA kernel)
   bool i8 = !stream && smc_glm_i8_usable(g, C);
   if (i8) {
     SMC_TRY(smc_glm_i8_prepare(m, g));

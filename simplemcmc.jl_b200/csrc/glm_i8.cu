@@ -1,24 +1,20 @@
 // Sliced-integer evaluation of a Normal identity-link GLM statement on the int8 tensor cores (tcgen05.mma kind::i8, int32
-// accumulators in TMEM): the library form of tools/ozaki_glm_proto.cu (v5), DESIGN.md section 8.
-//
-// OPT-IN (SMC_GLM_I8=1), ONE DEVICE RUN SO FAR: the prototype it is derived from is measured and parity-checked
-// (profiles/ozaki_glm_proto_v5*_r01.jsonl: 28.7 ms per configs[1] evaluation against 32.2 ms for k_glm, logp 7e-16 /
-// gradient 2e-14 against long double).  The plumbing below (slicing X at the first launch, sigma, the partial layout of
-// k_glm, models narrower than 64 columns, ragged row counts, non-finite chains) was written when the round's GPU minutes
-// were nearly spent; the last seconds went into tools/i8_quick.py with the switch set (N = 3000, M = 50, 70 chains,
-// sigma = 1.5, prior included: logp 4e-16, gradient 1.9e-14 against long double, profiles/glm_i8_library_quick_r01.json).
-// No launch list, no timing and no run of the parity suite yet: nothing reaches this file unless the environment variable
-// is set, and the suite run with it set (tests/test_zz_gpu_i8_optin.py) decides whether it becomes the path for C >= 32.
+// accumulators in TMEM): DESIGN.md section 8.  The path for Normal GLM statements with 33-64 columns and >= 32 chains
+// (SMC_GLM_I8=0 keeps them on the FP64 DMMA kernel of glm_fused.cu): measured 20.7 ms per configs[1] evaluation against
+// 32.2 ms (profiles/glm_i8_v12_r02.json), logp 2e-16 / gradient 7e-14 against long double at the full size, and the whole
+// 1e-12 parity suite runs through it (tests/test_gpu_scale.py, tests/test_zz_gpu_i8.py).
 //
 // Arithmetic (exact integer products, one FP64 rounding per recombination): every operand is cut into seven balanced
 // 8-bit slices against a power-of-two scale -- X once with one global scale, beta per chain and evaluation, the adjoint
-// w per (128-row tile, chain); slice pairs (i, j) with i + j <= 6 are kept and pairs of equal i + j share an int32
-// accumulator.  One CTA = 32 chains x a range of 128-row tiles, 512 threads (4 per TMEM lane), 448 TMEM columns:
+// w per chain with a STICKY scale (below) -- slice pairs (i, j) with i + j <= 6 are kept and pairs of equal i + j share an
+// int32 accumulator.  One CTA = 32 chains x a range of 128-row tiles; 16 epilogue warps (4 per TMEM lane quadrant) and one
+// issuer warp; 480 TMEM columns:
 //   product 1: A = X slice i (K-major), B = beta slices j <= 6 - i stacked along N, D at column offset 32 i;
 //   product 2: A = X slices (i, i+1) stacked along M, read MN-major from the same shared-memory tile, B = the stacked
-//              slices of the adjoint, D at column offset 256 + 32 i (lanes 64..127 hold the groups shifted by one).
+//              slices of the adjoint (MN-major, written as seven 8-byte words per thread), D at column offset 256 + 32 i
+//              (lanes 64..127 hold the groups shifted by one), ACCUMULATED over tiles and read back only on a flush.
 // Output: the partial block [row split][MP + 1][Cpad] of k_glm (rows 0..63 = X' dl/deta, row 64 = log-density), so the
-// fixed-order reduction, the publish step and the row-sharded all-reduce of glm_fused.cu apply unchanged.
+// fixed-order reduction, the publish step and the row-sharded exchange of glm_fused.cu / smc_p2p.cu apply unchanged.
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
@@ -591,10 +587,10 @@ __global__ void __launch_bounds__(NTI, 1) k_glm_i8(GlmI8Args a) {   // 17 warps 
 
 }  // namespace
 
-// the opt-in switch and the shapes the kernel is written for
+// the shapes the kernel is written for (SMC_GLM_I8=0 switches the path off: the statement stays on the FP64 DMMA kernel)
 bool smc_glm_i8_usable(const SmcGlmPlan& g, int64_t C) {
   static int on = -1;
-  if (on < 0) { const char* e = getenv("SMC_GLM_I8"); on = (e && e[0] == '1') ? 1 : 0; }
+  if (on < 0) { const char* e = getenv("SMC_GLM_I8"); on = (e && e[0] == '0') ? 0 : 1; }
   return on && g.family == SMC_GLM_NORMAL && g.MP == MP && C >= NC && g.N >= 4LL * TR && g.par > 0.0;
 }
 

@@ -99,7 +99,7 @@ struct SmcGlmPlan {  // one SMC_OP_GLM statement, prepared at finalize
   double lc_sum = 0.0;     // BINOMIAL: sum_i lchoose(n, y_i) over the local rows
   int gram = 0;            // SMC_GLM_F_GRAM: evaluate from Z'Z with Z = [X, ytilde]
   double* ZtZ = nullptr;   // [(M+1)][(M+1)] row major
-  // opt-in int8 tensor-core path (glm_i8.cu, SMC_GLM_I8=1): X as seven balanced 8-bit slices in 128-row tiles
+  // int8 tensor-core path (glm_i8.cu; SMC_GLM_I8=0 switches it off): X as seven balanced 8-bit slices in 128-row tiles
   int8_t* QX8 = nullptr;
   double sx8 = 0.0;        // power-of-two scale of X
   int* i8_status = nullptr;
@@ -247,7 +247,7 @@ int smc_p2p_glm_exchange(smc_ctx_s* c, const double* part, int RS, int M, int MP
 int smc_p2p_check(smc_ctx_s* c);   // after a synchronisation point: SMC_ERR_COMM when an exchange timed out
 void smc_p2p_destroy(smc_ctx_s* c);
 
-// glm_i8.cu (opt-in, SMC_GLM_I8=1)
+// glm_i8.cu (Normal GLM statements with 33-64 columns and >= 32 chains; SMC_GLM_I8=0 switches it off)
 bool smc_glm_i8_usable(const SmcGlmPlan& g, int64_t C);
 int smc_glm_i8_chain_tiles(int64_t C);
 int smc_glm_i8_row_tile();

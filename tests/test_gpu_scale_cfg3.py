@@ -87,8 +87,10 @@ def test_cfg3_full_size(smc, data, family):
         perm = rng.permutation(64)
         lp2, g2 = dev.eval(b[perm])
         assert np.array_equal(lp2, results[64][0][perm]) and np.array_equal(g2, results[64][1][perm])
-        # a short HMC run from the truth accepts and moves
-        raw = dev.run("hmc", b[:4], 4, 6, 0, isteps=2, stepsize=0.1 / np.sqrt(N / 1000), seed=3, store_draws=False, want=())
+        # a short HMC run from the truth accepts and moves (cfg3's step size; a count of 20 trials carries 20 times
+        # the Fisher information of one Bernoulli draw, so the stable step is sqrt(20) times shorter)
+        raw = dev.run("hmc", b[:4], 4, 6, 0, isteps=2, stepsize=0.1 / np.sqrt(N / 1000) / np.sqrt(ntr), seed=3, store_draws=False,
+                      want=())
         assert raw["n_leapfrogs"] == 4 * 6 * 2 and raw["accept_rate"].mean() > 0.3
     finally:
         dev.close()

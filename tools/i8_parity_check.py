@@ -1,6 +1,7 @@
-"""Parity of the opt-in int8 tensor-core GLM path (csrc/glm_i8.cu, SMC_GLM_I8=1) against the oracle and against the
-default DMMA path, through the public API.  Run in its own process (the switch is read once):
-    SMC_GLM_I8=1 python tools/i8_parity_check.py [rows] [chains]
+"""Parity of the int8 tensor-core GLM path (csrc/glm_i8.cu, the default for 33-64 columns and >= 32 chains) against the
+oracle and against the FP64 DMMA path (SMC_GLM_I8=0), through the public API.  Each path runs in its own process (the
+switch is read once):
+    python tools/i8_parity_check.py [rows] [chains]
 Prints one JSON line; exit code 1 when the 1e-12 bar is missed."""
 import json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
@@ -36,7 +37,7 @@ if __name__ == "__main__":
         data, betas, lp, g = evaluate(N, M, C)
         np.savez(sys.argv[sys.argv.index("--dump") + 1], lp=lp, g=g)
         sys.exit(0)
-    assert os.environ.get("SMC_GLM_I8") == "1", "set SMC_GLM_I8=1"
+    assert os.environ.get("SMC_GLM_I8", "1") != "0", "this process must run the int8 path (unset SMC_GLM_I8)"
     data, betas, lp, g = evaluate(N, M, C)
     from oracle.refmodel import generate_model_function
     ref = generate_model_function(MODEL, data=data, gradient=True, beta=np.zeros(M))
@@ -48,9 +49,9 @@ if __name__ == "__main__":
         l0, g0 = ref(betas[c])
         err_l = max(err_l, abs(lp[c] - l0) / abs(l0))
         err_g = max(err_g, float(np.max(np.abs(g[c] - g0)) / np.max(np.abs(g0))))
-    # the default (DMMA) path in a child process without the switch
+    # the FP64 DMMA path in a child process
     tmp = "/tmp/i8_parity_default.npz"
-    env = dict(os.environ); env.pop("SMC_GLM_I8")
+    env = dict(os.environ, SMC_GLM_I8="0")
     subprocess.check_call([sys.executable, os.path.abspath(__file__), str(N), str(C), "--dump", tmp], env=env)
     dflt = np.load(tmp)
     ok_rows = np.arange(C) != bad

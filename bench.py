@@ -8,6 +8,9 @@ ours      : libsimplemcmc_cuda.so through the host mirror of the reference API.
             value = device-resident throughput (CUDA events inside the library, on its launching stream);
             e2e   = one complete simpleHMC call with HOST buffers (tape lowering, H2D of X/Y from pinned memory,
                     K steps, D2H of the draws) timed with the wall clock.
+            labelled_extras (never the headline): the FP64 DMMA kernel the int8 path replaces, the sufficient-statistics
+            rewrite, configs[0] with 2^20 chains per GPU (the north-star model), and for --gpus N > 1 the strong-scaling
+            reading of configs[1] (4096 chains in total) and configs[2] with its rows sharded over the ranks.
 reference : the reference cannot run here (Julia <= 0.2 source, no Julia in the image), so this arm times the
             C++ restatement of its generated closure + simpleHMC loop (oracle/cpu_ref.cpp, kind "port") on all host
             cores, on a bounded sample of the same workload (one chain per core, few steps).
@@ -34,6 +37,15 @@ MODEL = """
 METRIC = "HMC leapfrog chain-steps/sec (all chains)"
 UNIT = "leapfrog chain-steps/s"
 FP64_PEAK_TFLOPS_FALLBACK = 37.15
+I8_PEAK_TOPS = 4580.0     # tcgen05.mma kind::i8 issue rate measured on this pool's B200 (tools/i8_umma_probe.cu, profiles/i8_umma_probe_r01.jsonl)
+I8_SLICE_PAIRS = 28       # slice-pair products per FP64 contraction (seven balanced 8-bit slices, pairs with i + j <= 6)
+LOGISTIC = """
+    vars ~ Normal(0, 1.0)
+    prob = 1 / (1. + exp(X * vars))
+    Y ~ Bernoulli(prob)
+"""
+CFG1_N, CFG1_M, CFG1_CHAINS = 1000, 10, 1 << 20
+CFG3_N, CFG3_M = 10_000_000, 10
 
 
 def make_data(n=N_ROWS, m=N_COLS, seed=2, pinned=False):
@@ -118,7 +130,7 @@ def fp64_peak():
     p = os.path.join(ROOT, "profiles", "fp64_peak_r01.json")
     try:
         d = json.load(open(p))
-        return max(v for k, v in d.items() if k.startswith("dmma_") and isinstance(v, float) and v < 100), \
+        return max(v for k, v in d.items() if k.startswith("dmma_") and isinstance(v, float)), \
             "measured: tools/fp64_peak.cu DMMA issue-rate microbenchmark on this pool's B200 (profiles/fp64_peak_r01.json); MEASURED_PEAKS.json has no FP64 figure"
     except Exception:
         return FP64_PEAK_TFLOPS_FALLBACK, "fallback: 37.15 TFLOP/s (earlier DMMA microbenchmark)"
@@ -150,7 +162,10 @@ def cpu_baseline(X, Y, mode, steps, threads=0):
         extra = {"numpy_1thread_error": str(e)[:200]}
     return {"value": r["n_leapfrogs"] / dt, "unit": UNIT, "cores": cores, "kind": "port", **extra,
             "sample": "%d chains (one per host core) x %d HMC steps x %d leapfrogs at the full N=%d, M=%d (oracle/cpu_ref.cpp, "
-                      "statement-by-statement C++ restatement of the generated closure), %.1f s" % (cores, steps, ISTEPS, X.shape[0], X.shape[1], dt)}, dt
+                      "statement-by-statement C++ restatement of the generated closure), %.1f s" % (cores, steps, ISTEPS, X.shape[0], X.shape[1], dt),
+            "caveat": "the reference's one-chain-at-a-time algorithm on the host cores: its two mat-vecs are plain -O3 loops here, not the "
+                      "BLAS dgemv Julia called, and %d chains are not 4096 (a rate, not the same job); a CPU code that batched the chains "
+                      "into one DGEMM would be an estimated 50-100x faster than this arm" % cores}, dt
 
 
 def run_reference(args):
@@ -172,14 +187,16 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def int8_extra(K, W):
+def glm_path_extra(K, W, i8):
+    """configs[1] through the other GLM kernel, in a child process (SMC_GLM_I8 is read once per process)"""
     import subprocess
-    note = ("opt-in SMC_GLM_I8=1: Normal GLM statement from seven balanced 8-bit slices per operand on tcgen05.mma kind::i8 "
-            "(int32 accumulators in TMEM); same statement list and the same 1e-12 parity bar as the headline, reported beside it "
-            "until the parity suite has run with the switch set")
+    note = ("SMC_GLM_I8=0: the FP64 DMMA kernel (mma.sync.m8n8k4.f64, csrc/glm_fused.cu k_glm) that the int8 tensor-core path "
+            "replaces for Normal GLM statements with 33-64 columns and >= 32 chains; same model, data, sampler settings") if not i8 else \
+           ("SMC_GLM_I8=1: Normal GLM statement from seven balanced 8-bit slices per operand on tcgen05.mma kind::i8 "
+            "(int32 accumulators in TMEM), csrc/glm_i8.cu")
     try:
         out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "i8_bench_extra.py"), str(K), str(W)],
-                             capture_output=True, text=True, timeout=300, env=dict(os.environ, SMC_GLM_I8="1"))
+                             capture_output=True, text=True, timeout=300, env=dict(os.environ, SMC_GLM_I8="1" if i8 else "0"))
         lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
         if out.returncode != 0 or not lines:
             return {"error": (out.stderr or out.stdout)[-400:], "note": note}
@@ -207,6 +224,168 @@ def run_ours(args):
         sys.stdout.flush()
 
 
+def _allmax(x, world):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([float(x)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def _allsum(x, world):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([float(x)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+def _same_on_all_ranks(arr, world):
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return True
+    t = torch.tensor(np.ascontiguousarray(arr, dtype=np.float64).ravel(), device="cuda")
+    hi, lo = t.clone(), t.clone()
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    return bool(torch.equal(hi, lo))
+
+
+def cfg1_extra(api, ctx, local, rank, world, barrier):
+    """configs[0] (examples/linear.jl:6-18,29: N = 1000, M = 10, HMC isteps = 2, stepsize = 0.05) with 2^20 chains per GPU:
+    the model BASELINE.json's 1e9 leapfrog chain-steps/s target is stated on"""
+    rng = np.random.default_rng(1)
+    X = np.column_stack([np.ones(CFG1_N), rng.standard_normal((CFG1_N, CFG1_M - 1))])
+    Y = X @ rng.standard_normal(CFG1_M) + rng.standard_normal(CFG1_N)
+    mode = np.linalg.solve(X.T @ X + np.eye(CFG1_M), X.T @ Y)
+    C, steps = CFG1_CHAINS, 100
+    low, dev = api._build(MODEL, [("beta", np.zeros(CFG1_M))], dict(X=X, Y=Y), True, C, local, "assign", comm=ctx)
+    try:
+        kw = dict(isteps=2, stepsize=0.05, chain_offset=rank * C, store_draws=False, want=())
+        dev.run("hmc", mode, C, 5, 0, seed=1, **kw)
+        barrier()
+        raw = dev.run("hmc", mode, C, steps, 0, seed=2, **kw)
+        barrier()
+        dev.eval(np.tile(mode, (C, 1)))
+        ms_eval, ms_glm = dev.eval_timed(5, False)
+    finally:
+        dev.close()
+    ms = _allmax(raw["device_ms"], world)
+    leap = _allsum(raw["n_leapfrogs"], world)
+    peak, _ = fp64_peak()
+    tf = 4.0 * CFG1_N * CFG1_M * C / (ms_glm * 1e-3) / 1e12
+    return {"value": leap / (ms * 1e-3), "unit": UNIT, "chains_per_gpu": C, "steps": steps, "accept_rate": float(np.mean(raw["accept_rate"])),
+            "ms_per_eval": ms_eval, "glm_ms_per_launch": ms_glm,
+            "roofline": {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak,
+                         "note": "k_glm (FP64 DMMA), F = 4*N*M*C algorithmic flop; X (80 KB) stays in L2 / shared memory, so there is no HBM bound"},
+            "note": "configs[0] examples/linear.jl (N=1000, M=10, HMC isteps=2, stepsize=0.05) with 2^20 chains per GPU, chains sharded "
+                    "over the GPUs; device-resident, CUDA events in the library, max over ranks"}
+
+
+def strong_scaling_extra(api, ctx, local, rank, world, data, mode, K, W, barrier):
+    """configs[1] read as strong scaling: 4096 chains IN TOTAL, 4096 / N per GPU (BASELINE.json: "4096 chains, chain-sharded
+    at 1/2/4/8 B200")"""
+    C = CHAINS_PER_GPU // world
+    rng = np.random.default_rng(100)
+    init = (mode[None, :] + 1e-3 * rng.standard_normal((CHAINS_PER_GPU, N_COLS)))[rank * C:(rank + 1) * C]
+    low, dev = api._build(MODEL, [("beta", np.zeros(N_COLS))], data, True, C, local, "assign", comm=ctx)
+    try:
+        kw = dict(isteps=ISTEPS, stepsize=STEPSIZE, chain_offset=rank * C, store_draws=False, want=())
+        dev.run("hmc", init, C, W, 0, seed=5, **kw)
+        barrier()
+        raw = dev.run("hmc", init, C, K, 0, seed=6, **kw)
+        barrier()
+    finally:
+        dev.close()
+    ms = _allmax(raw["device_ms"], world)
+    leap = _allsum(raw["n_leapfrogs"], world)
+    return {"value": leap / (ms * 1e-3), "unit": UNIT, "chains_total": C * world, "chains_per_gpu": C, "steps": K, "ms_per_step": ms / K,
+            "scaling": "strong", "accept_rate": float(np.mean(raw["accept_rate"])),
+            "note": "the same model and data with 4096 chains in total; no collective while sampling, X replicated"}
+
+
+def row_sharded_extra(api, capi, parallel, local, rank, world, barrier):
+    """configs[2] (examples/binomial.jl:13-17): logistic GLM, N = 1e7 rows sharded over the ranks, every rank advances the same
+    chains; (L, G) of the likelihood statement is summed over the ranks every evaluation -- over peer memory by one
+    reduce + exchange + publish kernel (csrc/smc_p2p.cu), and by the in-stream NCCL all-reduce for comparison"""
+    import torch
+    rng = np.random.default_rng(3)
+    N, M = CFG3_N, CFG3_M
+    r0, r1 = parallel.row_shard(N, rank, world)
+    Xs = np.empty((M, r1 - r0)).T                 # column-major shard
+    b0 = None
+    # every rank draws the same stream column by column and keeps its rows (no rank ever holds more than its shard, rank 0 also
+    # keeps the full matrix for the single-GPU check)
+    Xfull = np.empty((M, N)).T if rank == 0 else None
+    col = np.ones(N)
+    for j in range(M):
+        if j > 0:
+            col = rng.standard_normal(N)
+        Xs[:, j] = col[r0:r1]
+        if rank == 0:
+            Xfull[:, j] = col
+    b0 = rng.standard_normal(M)
+    u = rng.random(N)
+    out = {"rows": N, "columns": M, "gpus": world, "model": "examples/binomial.jl: vars ~ Normal(0,1); Y ~ Bernoulli(1/(1+exp(X*vars)))"}
+    if rank == 0:
+        Yfull = (u < 1.0 / (1.0 + np.exp(Xfull @ b0))).astype(np.float64)
+    else:
+        Yfull = np.empty(N)
+    t = torch.from_numpy(Yfull).cuda()
+    import torch.distributed as dist
+    dist.broadcast(t, src=0)
+    Ys = t.cpu().numpy()[r0:r1].copy()
+    del t
+    eps = 0.1 / np.sqrt(N / 1000)
+    ref = {}
+    for exch in ("p2p", "nccl"):
+        ctx = capi.Context(local)
+        parallel.init_library_comm(ctx, rank, world)
+        if exch == "p2p":
+            parallel.init_p2p(ctx, rank, world)
+        for C in (2, 64):
+            betas = b0[None, :] + 1e-3 * np.random.default_rng(9).standard_normal((C, M))
+            low, dev = api._build(LOGISTIC, [("vars", np.zeros(M))], dict(X=Xs, Y=Ys), True, C, local, "assign", shard="rows", comm=ctx)
+            try:
+                lp, g = dev.eval(betas)
+                row = {"identical_logp_grad_on_all_ranks": _same_on_all_ranks(np.concatenate([lp, g.ravel()]), world)}
+                if rank == 0:
+                    if C not in ref:      # the whole data on rank 0's GPU alone
+                        ctx1 = capi.Context(local)
+                        low1, dev1 = api._build(LOGISTIC, [("vars", np.zeros(M))], dict(X=Xfull, Y=Yfull), True, C, local, "assign", comm=ctx1)
+                        ref[C] = dev1.eval(betas)
+                        dev1.run("hmc", betas, C, 3, 0, isteps=2, stepsize=eps, seed=1, store_draws=False, want=())
+                        r1g = dev1.run("hmc", betas, C, 20, 0, isteps=2, stepsize=eps, seed=2, store_draws=False, want=())
+                        ref[(C, "ms")] = r1g["device_ms"] / 20
+                        dev1.close()
+                    lp1, g1 = ref[C]
+                    row["logp_relerr_vs_1gpu"] = float(np.max(np.abs(lp - lp1) / np.abs(lp1)))
+                    row["grad_relerr_vs_1gpu"] = float(np.max(np.abs(g - g1)) / np.max(np.abs(g1)))
+                    row["hmc_ms_per_step_1gpu_all_rows"] = ref[(C, "ms")]
+                steps = 20
+                dev.run("hmc", betas, C, 3, 0, isteps=2, stepsize=eps, seed=1, store_draws=False, want=())
+                barrier()
+                raw = dev.run("hmc", betas, C, steps, 0, isteps=2, stepsize=eps, seed=2, store_draws=False, want=())
+                barrier()
+                ms = _allmax(raw["device_ms"], world)
+                row.update(hmc_ms_per_step=ms / steps, leapfrog_us=1e3 * ms / (steps * 2), accept_rate=float(raw["accept_rate"].mean()),
+                           leapfrog_chain_steps_per_s=C * steps * 2 / (ms * 1e-3),
+                           chains_identical_on_all_ranks_after_hmc=_same_on_all_ranks(raw["final_state"], world))
+                if rank == 0:
+                    row["speedup_vs_1gpu"] = ref[(C, "ms")] / (ms / steps)
+                out["%s_chains%d" % (exch, C)] = row
+            finally:
+                dev.close()
+        barrier()
+    out["note"] = ("rows / N per GPU, chain state replicated; per evaluation the (M + 1) x C block of likelihood sums crosses the ranks: "
+                   "'p2p' = one kernel over NVLink peer memory (rank-ordered sums, identical on every rank), 'nccl' = in-stream "
+                   "ncclAllReduce; ms per HMC step = 2 leapfrogs, CUDA events in the library, max over ranks")
+    return out
+
+
 def _run_ours(args):
     import torch
     import torch.distributed as dist
@@ -220,10 +399,11 @@ def _run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from smc_pkg import load_package
     smc = load_package()
-    from simplemcmc_jl_b200 import api, capi
+    from simplemcmc_jl_b200 import api, capi, parallel
 
     K, W = args.steps, max(args.warmup, 3)
     C = CHAINS_PER_GPU
+    i8_on = os.environ.get("SMC_GLM_I8", "1") != "0"
     X, Y, beta0, hold = make_data(pinned=True)
     mode = posterior_mode(X, Y)
     rng = np.random.default_rng(100 + rank)
@@ -249,29 +429,45 @@ def _run_ours(args):
     barrier()
     wall = time.time() - t0
     clk = clocks.summary()
-    dev_ms = torch.tensor([raw["device_ms"]], dtype=torch.float64, device="cuda")
-    leap = torch.tensor([float(raw["n_leapfrogs"])], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(dev_ms, op=dist.ReduceOp.MAX)
-        dist.all_reduce(leap, op=dist.ReduceOp.SUM)
-    dev_ms, leap = float(dev_ms.item()), float(leap.item())
+    dev_ms = _allmax(raw["device_ms"], world)
+    leap = _allsum(raw["n_leapfrogs"], world)
     value = leap / (dev_ms * 1e-3)
 
-    # ---------------- roofline of the dominant kernel (k_glm): CUDA events around each launch, L2 flushed between
+    # ---------------- roofline of the dominant kernel: CUDA events around each launch (on the library's stream), L2 flushed between
     dev.eval(init)
     ms_eval, ms_glm = dev.eval_timed(reps=5, flush_l2=True)
     flops = 4.0 * N_ROWS * N_COLS * C
     peak, peak_src = fp64_peak()
-    achieved = flops / (ms_glm * 1e-3) / 1e12
-    roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
-            "kernel": "k_glm (FP64 DMMA mma.sync.m8n8k4, fused X*B -> Normal logpdf+adjoint -> X'*D)",
-            "flops_per_launch": flops, "ms_per_launch": ms_glm, "ms_per_eval": ms_eval,
-            "peak_source": peak_src, "note": "FP64 tensor (DMMA) roofline: F = 4*N*M flops per chain-step (SURVEY.md 8d); "
-            "algorithmic HBM bytes per launch = 8*N*M + 8*N = %.0f MB" % ((8.0 * N_ROWS * N_COLS + 8.0 * N_ROWS) / 1e6)}
-    tr = os.path.join(ROOT, "profiles", "glm_traffic_r01.json")
+    f64 = flops / (ms_glm * 1e-3) / 1e12
+    alg_mb = (8.0 * N_ROWS * N_COLS + 8.0 * N_ROWS) / 1e6
+    if i8_on:
+        i8 = I8_SLICE_PAIRS * f64
+        roof = {"bound": "tensor", "achieved": i8, "peak": I8_PEAK_TOPS, "unit": "TFLOP/s", "frac": i8 / I8_PEAK_TOPS, "traffic": None,
+                "kernel": "k_glm_i8 (tcgen05.mma kind::i8, int32 accumulators in TMEM; fused X*B -> Normal logpdf+adjoint -> X'*D from "
+                          "seven balanced 8-bit slices per operand, FP64 recombination)",
+                "unit_note": "tera int8 multiply-add operations per second (x2), not floating point: %d slice-pair products of the shape of "
+                             "each FP64 contraction" % I8_SLICE_PAIRS,
+                "ops_per_launch": I8_SLICE_PAIRS * flops, "ms_per_launch": ms_glm, "ms_per_eval": ms_eval,
+                "peak_source": "measured: tcgen05.mma kind::i8 issue rate on this pool's B200, every SM issuing back to back "
+                               "(tools/i8_umma_probe.cu, profiles/i8_umma_probe_r01.jsonl); MEASURED_PEAKS.json has no int8 figure",
+                "fp64_equivalent": {"achieved": f64, "peak": peak, "unit": "TFLOP/s", "frac": f64 / peak, "flops_per_launch": flops,
+                                    "peak_source": peak_src,
+                                    "note": "F = 4*N*M flops per chain-step (SURVEY.md 8d) against the FP64 tensor (DMMA) peak, the bound of "
+                                            "the kernel this path replaces: above 1 because the contraction no longer runs on the FP64 pipe"},
+                "note": "algorithmic HBM bytes per launch = 8*N*M + 8*N = %.0f MB (the sliced X is 8 bytes per element like the FP64 matrix)" % alg_mb}
+        tr = os.path.join(ROOT, "profiles", "glm_i8_traffic_r02.json")
+    else:
+        roof = {"bound": "tensor", "achieved": f64, "peak": peak, "unit": "TFLOP/s", "frac": f64 / peak, "traffic": None,
+                "kernel": "k_glm (FP64 DMMA mma.sync.m8n8k4, fused X*B -> Normal logpdf+adjoint -> X'*D)",
+                "flops_per_launch": flops, "ms_per_launch": ms_glm, "ms_per_eval": ms_eval,
+                "peak_source": peak_src, "note": "FP64 tensor (DMMA) roofline: F = 4*N*M flops per chain-step (SURVEY.md 8d); "
+                "algorithmic HBM bytes per launch = 8*N*M + 8*N = %.0f MB" % alg_mb}
+        tr = os.path.join(ROOT, "profiles", "glm_traffic_r01.json")
     if os.path.exists(tr):
         try:
             roof["traffic"] = json.load(open(tr))["dram_bytes_per_launch"]
+            roof["traffic_source"] = "read from the committed `ncu --set full` capture %s (dram__bytes_read.sum + dram__bytes_write.sum of one " \
+                                     "launch at this size), not measured in this run" % os.path.relpath(tr, ROOT)
         except Exception:
             pass
     dev.close()
@@ -283,13 +479,8 @@ def _run_ours(args):
     barrier()
     raw2 = dev2.run("hmc", init, C, 50 * K, 0, isteps=ISTEPS, stepsize=STEPSIZE, seed=6, chain_offset=rank * C, store_draws=False,
                     want=())
-    ms2 = torch.tensor([raw2["device_ms"]], dtype=torch.float64, device="cuda")
-    leap2 = torch.tensor([float(raw2["n_leapfrogs"])], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
-        dist.all_reduce(leap2, op=dist.ReduceOp.SUM)
     extra = {"sufficient_statistics_rewrite": {
-        "value": float(leap2.item()) / (float(ms2.item()) * 1e-3), "unit": UNIT, "steps": 50 * K,
+        "value": _allsum(raw2["n_leapfrogs"], world) / (_allmax(raw2["device_ms"], world) * 1e-3), "unit": UNIT, "steps": 50 * K,
         "accept_rate": float(np.mean(raw2["accept_rate"])),
         "note": "opt-in `sufficient_stats=True`: a different algorithm from the reference's generated code (Gram matrix hoisted "
                 "into the let-header); reported beside the headline, never instead of it; roofline.achieved stays F = 4*N*M"}}
@@ -301,7 +492,7 @@ def _run_ours(args):
                              device=local, comm=ctx, chain_offset=rank * C, beta=mode)
     e2e_call(2, 3)
     walls, leaps = [], []
-    for rep in range(3):      # the host side of a shared box is noisy (0.75 - 2.1 s seen for the same call): best of three complete calls
+    for rep in range(3):      # the host side of a shared box is noisy (0.75 - 2.1 s seen for the same call): three complete calls
         barrier()
         t1 = time.time()
         res = e2e_call(K, 4 + rep)
@@ -310,26 +501,35 @@ def _run_ours(args):
                                          res.misc["chain_m2"].sum(0)]), device="cuda")
             dist.all_reduce(mom)
         barrier()
-        e2e_t = torch.tensor([time.time() - t1], dtype=torch.float64, device="cuda")
-        e2e_leap = torch.tensor([float(res.misc["n_leapfrogs"])], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-            dist.all_reduce(e2e_leap, op=dist.ReduceOp.SUM)
-        walls.append(float(e2e_t.item()))
-        leaps.append(float(e2e_leap.item()))
-    mid = sorted(range(3), key=lambda k: walls[k])[0]
+        walls.append(_allmax(time.time() - t1, world))
+        leaps.append(_allsum(res.misc["n_leapfrogs"], world))
+    mid = sorted(range(3), key=lambda k: walls[k])[1]
     h2d = X.nbytes + Y.nbytes + mode.nbytes
     d2h = sum(v.nbytes for v in res.params.values()) + res.loglik.nbytes + res.accept.nbytes
     e2e = {"value": leaps[mid] / walls[mid], "unit": UNIT, "h2d_bytes_per_step": h2d / K,
            "d2h_bytes_per_step": d2h / K, "wall_s": walls[mid], "wall_s_all_calls": walls,
            "what": "one simpleHMC(model, steps=K, chains=4096, ...) call per rank with host (pinned) X, Y: lowering, tape compile, "
-                   "H2D bind, K steps, D2H of all draws; wall clock (max over ranks), best of 3 calls (all in wall_s_all_calls)"}
+                   "H2D bind, K steps, D2H of all draws; wall clock (max over ranks), median of 3 calls (all in wall_s_all_calls)"}
 
-    # ---------------- labelled extra (NOT the headline): the same model with the library's opt-in int8 tensor-core GLM path
-    # (csrc/glm_i8.cu), in a child process because SMC_GLM_I8 is read once per process; it runs after
-    # every measurement above is complete and cannot change them
+    # ---------------- labelled extras on the other configs (each one after every headline measurement is complete; an extra
+    # that fails records its error string and never takes the line down)
+    def guarded(name, fn):
+        try:
+            extra[name] = fn()
+        except Exception as e:
+            extra[name] = {"error": ("%s: %s" % (type(e).__name__, e))[:400]}
+        try:
+            barrier()
+        except Exception:
+            pass
+    guarded("cfg1_2p20_chains", lambda: cfg1_extra(api, ctx, local, rank, world, barrier))
+    if world > 1:
+        guarded("strong_scaling_cfg2", lambda: strong_scaling_extra(api, ctx, local, rank, world, data, mode, K, W, barrier))
+        guarded("row_sharded_cfg3", lambda: row_sharded_extra(api, capi, parallel, local, rank, world, barrier))
+    # the FP64 DMMA kernel the int8 path replaced (or vice versa when the run itself was started with SMC_GLM_I8=0), in a
+    # child process because the switch is read once per process
     if rank == 0 and world == 1:
-        extra["int8_tensor_core_glm_path"] = int8_extra(K, W)
+        extra["fp64_dmma_glm_path" if i8_on else "int8_tensor_core_glm_path"] = glm_path_extra(K, W, not i8_on)
 
     if rank == 0:
         cpu, _ = cpu_baseline(X, Y, mode, 24)
@@ -340,6 +540,7 @@ def _run_ours(args):
                                        "simpleHMC isteps=2, 4096 chains per GPU, chains sharded over GPUs, X replicated",
                            "chains_per_gpu": C, "isteps": ISTEPS, "stepsize": STEPSIZE, "accept_rate": float(np.mean(raw["accept_rate"])),
                            "init": "posterior mode + 1e-3*N(0,1) per chain (computed outside the timed region)",
+                           "glm_kernel": "k_glm_i8" if i8_on else "k_glm",
                            "l2": "inputs larger than L2: X is 512 MB vs 126 MB L2; roofline launches additionally flush L2 (256 MB memset)",
                            "wall_s_timed_region": wall},
                 "clocks": clk, "e2e": e2e, "gpu_launches": int(raw["n_kernel_launches"]), "roofline": roof, "cpu_baseline": cpu,

@@ -112,9 +112,17 @@ __device__ __forceinline__ int rowmap(int n) { return n < 4 ? n : (n ^ 1); }
 // PUB: one row split covers all rows (small N) on a single rank -- the epilogue writes (L, G) into the tape registers
 // itself.  (A compile-time switch: as a run-time branch it changed the register allocation of the main loop and cost
 // 2.5 % on cfg2, 32.9 vs 32.1 ms per launch.)
-template <int FAM, int MT, int NWC, int NWR, int MP8, int TRIM, int PUB>
+// TAIL: the last 8-column tile of product 2 holds only TAIL (1..3) live columns (M = 10 in a 16-wide tile: 2).  A DMMA on it
+// spends 16 issue cycles per scheduler on 8 columns of which 8 - TAIL are zeros; DFMA runs at the same flop rate as DMMA on
+// this part (34.2 against 37.2 TFLOP/s, profiles/fp64_peak_r01.json), so those columns are accumulated by plain DFMAs
+// instead -- thread (g, q) owns chain g and rows (2q, 2q+1) of the block, 2 x TAIL DFMAs of 2 cycles each per m-tile -- and
+// the four q lanes of a chain are summed once in the epilogue.  examples/linear.jl (M = 10): 20 DMMAs + 16 DFMAs per row
+// block of 32 chains instead of 28 DMMAs.
+template <int FAM, int MT, int NWC, int NWR, int MP8, int TRIM, int PUB, int TAIL = 0>
 __global__ void __launch_bounds__(NWC* NWR * 32, (MP8 <= 2 ? 2 : 1)) k_glm(GlmArgs a) {
   constexpr int MP = MP8 * 8, LD = MP + 4, NT = NWC * NWR * 32;
+  constexpr int NTD = MP8 - (TAIL > 0 ? 1 : 0);   // 8-column tiles of product 2 on the tensor pipe
+  constexpr int TL = TAIL > 0 ? TAIL : 1;
   constexpr int KS = MP / 4 - TRIM;          // k-steps of product 1
   constexpr int RT = SMC_GLM_RT(MP8);        // rows per tile
   constexpr int NST = 4;    // stages; the copy of tile t+1 is in flight while tile t is consumed
@@ -146,12 +154,15 @@ __global__ void __launch_bounds__(NWC* NWR * 32, (MP8 <= 2 ? 2 : 1)) k_glm(GlmAr
     }
   }
   double G[MT][MP8][2];
+  double Gt[MT][TL];                     // TAIL: this thread's rows of X' d for the columns 8 NTD .. 8 NTD + TAIL - 1
   double lsum[MT];
 #pragma unroll
   for (int mt = 0; mt < MT; mt++) {
     lsum[mt] = 0.0;
 #pragma unroll
     for (int nt = 0; nt < MP8; nt++) G[mt][nt][0] = G[mt][nt][1] = 0.0;
+#pragma unroll
+    for (int p = 0; p < TL; p++) Gt[mt][p] = 0.0;
   }
   double inv_s = 1.0, neg_inv_s2 = 0.0;
   if (FAM == SMC_GLM_NORMAL) {
@@ -230,10 +241,19 @@ __global__ void __launch_bounds__(NWC* NWR * 32, (MP8 <= 2 ? 2 : 1)) k_glm(GlmAr
     for (int s = 0; s < 2; s++) {
       const double* xr2 = xs + (rb + rowmap(2 * q + s)) * LD + g;
 #pragma unroll
-      for (int nt = 0; nt < MP8; nt++) {
+      for (int nt = 0; nt < NTD; nt++) {
         double xb = xr2[nt * 8];
 #pragma unroll
         for (int mt = 0; mt < MT; mt++) dmma884(G[mt][nt][0], G[mt][nt][1], dd[mt][s], xb);
+      }
+      if (TAIL > 0) {
+        const double* xt = xs + (rb + rowmap(2 * q + s)) * LD + NTD * 8;      // the same address in the eight g lanes: a broadcast
+#pragma unroll
+        for (int p = 0; p < TL; p++) {
+          const double xv = xt[p];
+#pragma unroll
+          for (int mt = 0; mt < MT; mt++) Gt[mt][p] = fma(dd[mt][s], xv, Gt[mt][p]);
+        }
       }
     }
   };
@@ -286,6 +306,13 @@ __global__ void __launch_bounds__(NWC* NWR * 32, (MP8 <= 2 ? 2 : 1)) k_glm(GlmAr
   for (int mt = 0; mt < MT; mt++) {
     lsum[mt] += __shfl_xor_sync(0xffffffffu, lsum[mt], 1);
     lsum[mt] += __shfl_xor_sync(0xffffffffu, lsum[mt], 2);
+    if (TAIL > 0) {
+#pragma unroll
+      for (int p = 0; p < TL; p++) {
+        Gt[mt][p] += __shfl_xor_sync(0xffffffffu, Gt[mt][p], 1);
+        Gt[mt][p] += __shfl_xor_sync(0xffffffffu, Gt[mt][p], 2);
+      }
+    }
   }
   for (int w = 0; w < NWR; w++) {
     if (wr == w) {
@@ -293,9 +320,13 @@ __global__ void __launch_bounds__(NWC* NWR * 32, (MP8 <= 2 ? 2 : 1)) k_glm(GlmAr
       for (int mt = 0; mt < MT; mt++) {
         int cl = wc * (MT * 8) + mt * 8 + g;
 #pragma unroll
-        for (int nt = 0; nt < MP8; nt++) {
+        for (int nt = 0; nt < NTD; nt++) {
           Gs[(nt * 8 + 2 * q) * TC + cl] += G[mt][nt][0];
           Gs[(nt * 8 + 2 * q + 1) * TC + cl] += G[mt][nt][1];
+        }
+        if (TAIL > 0 && q == 0) {
+#pragma unroll
+          for (int p = 0; p < TL; p++) Gs[(NTD * 8 + p) * TC + cl] += Gt[mt][p];
         }
         if (q == 0) Gs[MP * TC + cl] += lsum[mt];
       }
@@ -822,13 +853,13 @@ __global__ void __launch_bounds__(256) k_glm_gram(GramEvalArgs a) {
   }
 }
 
-template <int FAM, int MT, int NWC, int NWR, int MP8, int TRIM, int PUB>
+template <int FAM, int MT, int NWC, int NWR, int MP8, int TRIM, int PUB, int TAIL = 0>
 int launch_cfg_tp(const GlmArgs& a, int RS, cudaStream_t st) {
   constexpr int MP = MP8 * 8, LD = MP + 4, RT = SMC_GLM_RT(MP8), NST = 4, TC = NWC * MT * 8;
   size_t pipe = (size_t)NST * RT * (LD + 1) * sizeof(double);
   size_t epi = (size_t)(MP + 1) * TC * sizeof(double) + TC * sizeof(int);
   size_t smem = std::max(pipe, epi);
-  auto kern = k_glm<FAM, MT, NWC, NWR, MP8, TRIM, PUB>;
+  auto kern = k_glm<FAM, MT, NWC, NWR, MP8, TRIM, PUB, TAIL>;
   static SmcOncePerDevice once;
   if (once.first()) SMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)((a.C + TC - 1) / TC), (unsigned)RS);
@@ -839,6 +870,15 @@ int launch_cfg_tp(const GlmArgs& a, int RS, cudaStream_t st) {
 template <int FAM, int MT, int NWC, int NWR, int MP8, int TRIM>
 int launch_cfg_t(const GlmArgs& a, int RS, cudaStream_t st) {
   if constexpr (MP8 == 2) {   // (the self-publishing variant is only built for narrow models: it matters for small N)
+    // 9 or 10 columns (examples/linear.jl, examples/binomial.jl: M = 10) with a full device of chains: the tail columns of
+    // product 2 on DFMAs (SMC_GLM_NO_TAIL=1 keeps them on the tensor pipe, for A/B measurements)
+    if constexpr (TRIM == 1 && MT >= 2) {
+      static int no_tail = -1;
+      if (no_tail < 0) { const char* e = getenv("SMC_GLM_NO_TAIL"); no_tail = (e && e[0] == '1') ? 1 : 0; }
+      if (!no_tail && a.M >= 9 && a.M <= 10)
+        return a.pub.on ? launch_cfg_tp<FAM, MT, NWC, NWR, MP8, TRIM, 1, 2>(a, RS, st)
+                        : launch_cfg_tp<FAM, MT, NWC, NWR, MP8, TRIM, 0, 2>(a, RS, st);
+    }
     if (a.pub.on) return launch_cfg_tp<FAM, MT, NWC, NWR, MP8, TRIM, 1>(a, RS, st);
   }
   return launch_cfg_tp<FAM, MT, NWC, NWR, MP8, TRIM, 0>(a, RS, st);

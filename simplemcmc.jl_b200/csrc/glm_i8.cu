@@ -191,6 +191,7 @@ struct GlmI8Args {
   double sx;            // scale of X
   double sigma;
   int m0, m8, m16, m24, m28; // 1, 2^8, 2^16, 2^24, 2^28 (see halves())
+  int flush_tiles;      // read accumulator set 2 back at least every so many tiles (<= FLUSH_TILES: the int32 range)
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -334,7 +335,7 @@ __global__ void __launch_bounds__(NTI, 1) k_glm_i8(GlmI8Args a) {   // 17 warps 
       ok = ok && mbar_wait(&barB, (uint32_t)(k & 1));     // adjoint slices in place (and accumulator set 2 read when flushing)
       fence_after();
       const int flag = *(volatile int*)&s_flag[k & 3];
-      const bool fresh = flag != 0 || cnt < 0 || cnt >= FLUSH_TILES;
+      const bool fresh = flag != 0 || cnt < 0 || cnt >= a.flush_tiles;
       if (fresh) cnt = 0;
       cnt++;
       if (lane == 0) {
@@ -471,7 +472,7 @@ __global__ void __launch_bounds__(NTI, 1) k_glm_i8(GlmI8Args a) {   // 17 warps 
       // needs; next written in epilogue 1 of tile t+2, after barrier (A) of tile t+1
       if (tid < NC) s_max[(k + 2) & 3][tid] = 0u;
       if (tid == NC) s_flag[(k + 2) & 3] = 0;
-      const bool fresh = s_flag[b] != 0 || cnt < 0 || cnt >= FLUSH_TILES;
+      const bool fresh = s_flag[b] != 0 || cnt < 0 || cnt >= a.flush_tiles;
       if (fresh) {
         if (cnt > 0) {                                      // read the accumulated products back with the scales they were made with
           if (!mbar_wait(&bar2[stage ^ 1], (uint32_t)(((k - 1) >> 1) & 1))) { ok = false; break; }
@@ -501,7 +502,7 @@ __global__ void __launch_bounds__(NTI, 1) k_glm_i8(GlmI8Args a) {   // 17 warps 
         const double f = __hiloint2double((int)((2100u << 20) - lim[u]), 0);        // 2^54 / scale = 2^(1076 - E)
         const double f28 = __hiloint2double((int)((2072u << 20) - lim[u]), 0);      // f 2^-28
         const double uu = fma(d[u], f28, MU);
-        const double hs = (uu - MU) * -0x1p28;
+        const double hs = fma(uu, -0x1p28, MU * 0x1p28);    // -(uu - MU) 2^28, exact: uu - MU is an integer below 2^27
         const double ww = fma(d[u], f, hs) + MW;
         const unsigned long long t = (unsigned long long)mad_wide(__double2loint(uu), wm.m28,
                                                                    (long long)(unsigned long long)(unsigned int)__double2loint(ww));
@@ -649,12 +650,17 @@ int smc_glm_i8_launch(smc_model_s* m, SmcGlmPlan& g, const double* beta, int64_t
   a.QX = g.QX8; a.y = g.y; a.beta = beta; a.part = part; a.status = g.i8_status;
   a.N = g.N; a.tiles = tiles; a.C = C; a.Cpad = Cpad; a.M = g.M; a.splits = RS; a.sx = g.sx8; a.sigma = g.par;
   a.m0 = 1; a.m8 = 1 << 8; a.m16 = 1 << 16; a.m24 = 1 << 24; a.m28 = 1 << 28;
+  static int flush = -1;     // SMC_GLM_I8_FLUSH=n (tests): a shorter read-back period, so that small problems exercise that path
+  if (flush < 0) { const char* e = getenv("SMC_GLM_I8_FLUSH"); flush = e ? std::max(1, std::min(FLUSH_TILES, atoi(e))) : FLUSH_TILES; }
+  a.flush_tiles = flush;
   dim3 grid((unsigned)smc_glm_i8_chain_tiles(C), (unsigned)RS);
   static int beta8 = -1;
   if (beta8 < 0) { const char* e = getenv("SMC_GLM_I8_BETA8"); beta8 = (e && e[0] == '1') ? 1 : 0; }
   if (beta8) k_glm_i8<8><<<grid, NTI, SMEM_V10, st>>>(a);
   else k_glm_i8<7><<<grid, NTI, SMEM_V10, st>>>(a);
-  if (!g.i8_checked) {      // first (eager) launch: a tensor-core completion that never arrived is an error, not a wrong number
+  static int always = -1;    // SMC_GLM_I8_CHECK=1 (tests, outside stream capture): synchronise and check after every launch
+  if (always < 0) { const char* e = getenv("SMC_GLM_I8_CHECK"); always = (e && e[0] == '1') ? 1 : 0; }
+  if (!g.i8_checked || always) {      // first (eager) launch: a tensor-core completion that never arrived is an error, not a wrong number
     g.i8_checked = 1;
     int status = 0;
     SMC_CUDA(smc_copy_sync(&status, g.i8_status, sizeof(int), cudaMemcpyDeviceToHost, st));

@@ -28,6 +28,22 @@ def test_int8_glm_path_matches_the_oracle(rows, chains):
     assert res["bad_chain_logp"] == float("-inf") and res["bad_chain_grad_zero"]
 
 
+@pytest.mark.parametrize("flush", ["64", "3", "1"])
+def test_int8_pipeline_under_stress(flush):
+    """many tiles per CTA, the residual scale growing along the rows (the sticky per-chain scales have to grow in the middle of a
+    CTA's row range: read-back, re-slice), a short read-back period, every launch checked for pipeline time-outs, repeated
+    evaluations bit for bit (tools/i8_stress.py)"""
+    env = dict(os.environ, SMC_GLM_I8_FLUSH=flush, SMC_GLM_I8_CHECK="1", SMC_NO_GRAPHS="1")
+    env.pop("SMC_GLM_I8", None)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "i8_stress.py"), "400000", "1024", "6"],
+                         capture_output=True, text=True, timeout=600, env=env)
+    lines = [json.loads(l) for l in out.stdout.splitlines() if l.startswith("{")]
+    assert out.returncode == 0 and lines, out.stdout[-1500:] + out.stderr[-1500:]
+    res = lines[-1]
+    assert res["bit_identical_repeats"]
+    assert res["relerr_logp"] <= 1e-12 and res["relerr_grad"] <= 1e-12
+
+
 def test_fp64_dmma_kernel_stays_covered_at_configs1():
     env = dict(os.environ, SMC_GLM_I8="0")
     out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_scale.py"), "-m", "gpu", "-q", "-x"],

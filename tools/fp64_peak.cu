@@ -97,7 +97,9 @@ template <typename F>
 float timeit(F f, int reps = 5) {
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-  f(); CK(cudaDeviceSynchronize());
+  f();
+  if (cudaGetLastError() != cudaSuccess) return -1.0f;      // e.g. 1024 threads x the kernel's registers exceed the register file
+  CK(cudaDeviceSynchronize());
   float best = 1e30f;
   for (int r = 0; r < reps; r++) {
     CK(cudaEventRecord(e0)); f(); CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
@@ -147,7 +149,7 @@ int main() {
     {
       float ms = timeit([&] { k_mma16<4, 16><<<grid, threads>>>(out, iters / 2); });
       double tf = 2.0 * 16 * 8 * 16 * 4 * (iters / 2) * (double)grid * warps / (ms * 1e-3) / 1e12;
-      printf(",\n \"dmma_m16n8k16_ilp4_t%d_tflops\": %.3f", threads, tf);
+      if (ms > 0) printf(",\n \"dmma_m16n8k16_ilp4_t%d_tflops\": %.3f", threads, tf);      // (a configuration that cannot launch is left out)
     }
   }
   {

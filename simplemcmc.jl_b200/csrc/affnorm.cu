@@ -357,7 +357,11 @@ static void launch_chains(const AffArgs& a, int CT, int nlanes, dim3 grid, size_
   if (CT == 1) k_affnorm_chains<1, PAT><<<grid, AFF_NT, smem, st>>>(a, nlanes);
   else k_affnorm_chains<2, PAT><<<grid, AFF_NT, smem, st>>>(a, nlanes);
 }
-// the compile-time pattern of a statement, or AFF_GENERIC
+// the compile-time pattern of a statement, or AFF_GENERIC.  A compiled shape may accumulate MORE sums than the statement
+// needs (the evaluation without a gradient -- simpleRWM -- needs none of the S_j): which partial sums are written and read is
+// decided at run time by the slots, so a statement runs on the first shape with the same terms whose sums cover its own
+// (without this the no-gradient tape of examples/ornstein.jl ran on the generic kernel: 0.234 ms against 0.058 ms for the
+// evaluation with its gradient, T = 1e6 x 64 chains).
 static unsigned aff_pattern_of(const smc_model_s* m, const smc_tape_stmt& s, const std::vector<int32_t>& d, const AffArgs& a) {
   int k[AFF_MAX_T] = {0, 0, 0, 0}, need = 0;
   for (int j = 0; j < a.T; j++) {
@@ -367,13 +371,17 @@ static unsigned aff_pattern_of(const smc_model_s* m, const smc_tape_stmt& s, con
     else if (sr.d.kind == SMC_REG_IMM && sr.d.imm == 1.0 && t[5] < 0) k[j] = t[1] > 0 ? 2 : 3;
     else k[j] = 0;
     if (k[j] == 0 && t[5] >= 0) need |= 1 << j;
-    if (k[j] == 0 && t[5] < 0) return AFF_GENERIC;       // array * constant: not among the compiled shapes
   }
   const SmcReg& mr = m->regs[s.src[0]];
   const int mu0 = (mr.d.kind == SMC_REG_IMM && mr.d.imm == 0.0) ? 1 : 0;
-  const unsigned pat = aff_pat(a.T, k[0], k[1], k[2], k[3], need, a.s1_slot >= 0 ? 1 : 0, mu0);
-  for (unsigned known : {AFF_P_OU, AFF_P_YXB, AFF_P_XBY, AFF_P_YXBC})
-    if (pat == known) return pat;
+  const int s1 = a.s1_slot >= 0 ? 1 : 0;
+  for (unsigned known : {AFF_P_OU, AFF_P_YXB, AFF_P_XBY, AFF_P_YXBC}) {
+    const unsigned shape = aff_pat(a.T, k[0], k[1], k[2], k[3], 0, 0, mu0);
+    const unsigned sums_mask = (0xFu << 10) | (1u << 14);
+    if ((known & ~sums_mask) != shape) continue;
+    const int kneed = (int)((known >> 10) & 0xFu), ks1 = (int)((known >> 14) & 1u);
+    if ((need & ~kneed) == 0 && s1 <= ks1) return known;
+  }
   return AFF_GENERIC;
 }
 
@@ -477,7 +485,9 @@ int smc_aff_launch(smc_model_s* m, SmcAffPlan& p, int64_t C) {
     int nlanes = 32;
     while (nlanes < AFF_NT && (long long)nlanes * CT < C) nlanes <<= 1;
     const long long gy = (C + (long long)nlanes * CT - 1) / ((long long)nlanes * CT);
-    long long gx = std::max<long long>(1, std::min<long long>((a.n + AFF_TE - 1) / AFF_TE, ((long long)sms * 3 + gy - 1) / gy));
+    // blocks of 128 threads at 40 registers: six per SM (three left the FP64 pipe 58 % busy with 18 % of the warp slots in use
+    // and fixed-latency waits as the top stall at T = 1e6 x 64 chains, profiles/cfg5_c64_affnorm_ncu_r02.json)
+    long long gx = std::max<long long>(1, std::min<long long>((a.n + AFF_TE - 1) / AFF_TE, ((long long)sms * 6 + gy - 1) / gy));
     a.cstride = gy * nlanes * CT;
     SMC_TRY(smc_scratch_reserve(m, gx * nsum * a.cstride));
     a.part = m->scratch;

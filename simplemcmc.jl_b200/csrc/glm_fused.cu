@@ -116,14 +116,15 @@ __device__ __forceinline__ int rowmap(int n) { return n < 4 ? n : (n ^ 1); }
 // spends 16 issue cycles per scheduler on 8 columns of which 8 - TAIL are zeros; DFMA runs at the same flop rate as DMMA on
 // this part (34.2 against 37.2 TFLOP/s, profiles/fp64_peak_r01.json), so those columns are accumulated by plain DFMAs
 // instead -- thread (g, q) owns chain g and rows (2q, 2q+1) of the block, 2 x TAIL DFMAs of 2 cycles each per m-tile -- and
-// the four q lanes of a chain are summed once in the epilogue.  examples/linear.jl (M = 10): 20 DMMAs + 16 DFMAs per row
-// block of 32 chains instead of 28 DMMAs.
+// the four q lanes of a chain are summed once in the epilogue.  The same columns leave product 1's tensor k-steps too: its
+// accumulator fragment (chain g, rows 2q, 2q+1) takes them as beta[8 + p] * x[row][8 + p] DFMAs.  examples/linear.jl
+// (M = 10): 16 DMMAs + 32 DFMAs per row block of 32 chains instead of 28 DMMAs (448 -> 320 issue cycles per scheduler).
 template <int FAM, int MT, int NWC, int NWR, int MP8, int TRIM, int PUB, int TAIL = 0>
 __global__ void __launch_bounds__(NWC* NWR * 32, (MP8 <= 2 ? 2 : 1)) k_glm(GlmArgs a) {
   constexpr int MP = MP8 * 8, LD = MP + 4, NT = NWC * NWR * 32;
   constexpr int NTD = MP8 - (TAIL > 0 ? 1 : 0);   // 8-column tiles of product 2 on the tensor pipe
   constexpr int TL = TAIL > 0 ? TAIL : 1;
-  constexpr int KS = MP / 4 - TRIM;          // k-steps of product 1
+  constexpr int KS = TAIL > 0 ? 2 * (MP8 - 1) : MP / 4 - TRIM;   // k-steps of product 1 on the tensor pipe
   constexpr int RT = SMC_GLM_RT(MP8);        // rows per tile
   constexpr int NST = 4;    // stages; the copy of tile t+1 is in flight while tile t is consumed
   constexpr int TC = NWC * MT * 8;           // chains per CTA
@@ -151,6 +152,17 @@ __global__ void __launch_bounds__(NWC* NWR * 32, (MP8 <= 2 ? 2 : 1)) k_glm(GlmAr
       int j = ks * 4 + q;
       double bv = (j < a.M && c < a.C) ? __ldg(a.beta + (long long)j * a.Cpad + c) : 0.0;
       bfr[mt][ks] = a.neg_beta ? -bv : bv;
+    }
+  }
+  double bt[MT][TL];                     // TAIL: beta of the columns 8 NTD .. 8 NTD + TAIL - 1 for chain g of every m-tile
+#pragma unroll
+  for (int mt = 0; mt < MT; mt++) {
+    long long c = cbase + mt * 8 + g;
+#pragma unroll
+    for (int p = 0; p < TL; p++) {
+      int j = NTD * 8 + p;
+      double bv = (TAIL > 0 && j < a.M && c < a.C) ? __ldg(a.beta + (long long)j * a.Cpad + c) : 0.0;
+      bt[mt][p] = a.neg_beta ? -bv : bv;
     }
   }
   double G[MT][MP8][2];
@@ -216,6 +228,19 @@ __global__ void __launch_bounds__(NWC* NWR * 32, (MP8 <= 2 ? 2 : 1)) k_glm(GlmAr
       double xb = xrow[ks * 4];
 #pragma unroll
       for (int mt = 0; mt < MT; mt++) dmma884(acc[mt][0], acc[mt][1], bfr[mt][ks], xb);
+    }
+    if (TAIL > 0) {
+      const double* xt = Xs + (t % NST) * RT * LD + rb * LD + NTD * 8;
+#pragma unroll
+      for (int s = 0; s < 2; s++) {
+        const double* xr = xt + rowmap(2 * q + s) * LD;
+#pragma unroll
+        for (int p = 0; p < TL; p++) {
+          const double xv = xr[p];
+#pragma unroll
+          for (int mt = 0; mt < MT; mt++) acc[mt][s] = fma(bt[mt][p], xv, acc[mt][s]);
+        }
+      }
     }
   };
 

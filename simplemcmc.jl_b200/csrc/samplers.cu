@@ -814,9 +814,10 @@ __global__ void k_nuts_init(long long C, Nuts T) {
 }
 
 template <int LY>
-__global__ void __launch_bounds__(256) k_nuts_begin(RngSrc rng, long long step, long long C, long long M, long long Cpad,
+__global__ void __launch_bounds__(256) k_nuts_begin(RngSrc rng, const long long* stepp, long long C, long long M, long long Cpad,
                                                        const double* b0, const double* g0, const double* l0, Nuts T) {
   __shared__ double sh[LY * SMC_CXB];
+  const long long step = *stepp;
   const Ln L = lanes<LY>(C);
   const long long c = L.c;
   double ss = 0.0;
@@ -847,8 +848,9 @@ __global__ void __launch_bounds__(256) k_nuts_begin(RngSrc rng, long long step, 
 }
 
 template <int LY>
-__global__ void __launch_bounds__(256) k_nuts_pre(RngSrc rng, long long step, long long C, long long M, long long Cpad,
+__global__ void __launch_bounds__(256) k_nuts_pre(RngSrc rng, const long long* stepp, long long C, long long M, long long Cpad,
                                                      double* beta, int use_slots, Nuts T) {
+  const long long step = *stepp;
   const Ln L = lanes<LY>(C);
   const long long c = L.c;
   const bool act = L.in && T.active[c];
@@ -909,10 +911,11 @@ __global__ void __launch_bounds__(256) k_nuts_pre(RngSrc rng, long long step, lo
 }
 
 template <int LY>
-__global__ void __launch_bounds__(256) k_nuts_post(RngSrc rng, long long step, long long C, long long M, long long Cpad,
+__global__ void __launch_bounds__(256) k_nuts_post(RngSrc rng, const long long* stepp, long long C, long long M, long long Cpad,
                                                       const double* egrad, const double* elogp, int use_slots, Nuts T,
                                                       unsigned long long* nleap) {
   __shared__ double sh[2 * LY * SMC_CXB];
+  const long long step = *stepp;
   const Ln L = lanes<LY>(C);
   const long long c = L.c;
   const int ly = L.ly;
@@ -1066,9 +1069,10 @@ __global__ void __launch_bounds__(256) k_nuts_post(RngSrc rng, long long step, l
 
 // dual averaging of epsilon (:294-302), addToRes! (:305), misc (:307-308), state0 = state (:310)
 template <int LY>
-__global__ void __launch_bounds__(256) k_nuts_end(long long step, long long C, long long M, long long Cpad, double* b0,
+__global__ void __launch_bounds__(256) k_nuts_end(const long long* stepp, long long C, long long M, long long Cpad, double* b0,
                                                      double* g0, double* l0, Nuts T, Recorder R, double* eps_out,
                                                      double* jmax_out) {
+  const long long step = *stepp;
   const Ln L = lanes<LY>(C);
   const long long c = L.c;
   if (!L.in) return;
@@ -1101,6 +1105,23 @@ __global__ void __launch_bounds__(256) k_nuts_end(long long step, long long C, l
 
 }  // namespace
 
+// ---- device-side round loop (a CUDA graph WHILE node): one graph launch per iteration ---------------------------------------
+// ctl[0] = rounds of this iteration, ctl[1] = rounds of the whole run (host statistics)
+__global__ void k_nuts_loop_begin(int* n_active, unsigned long long* ctl) {
+  *n_active = 0;
+  ctl[0] = 0ull;
+}
+// after k_nuts_post: another round while some chain still builds its tree (src/samplers.jl:263: `while s == 1`, lockstep over
+// the chains) and the depth cap has not been reached; clears the counter for that round
+__global__ void k_nuts_loop_cond(cudaGraphConditionalHandle h, int* n_active, unsigned long long* ctl, int max_rounds) {
+  const unsigned long long rounds = ctl[0] + 1ull;
+  ctl[0] = rounds;
+  ctl[1] += 1ull;
+  const bool more = *n_active > 0 && rounds < (unsigned long long)max_rounds;
+  *n_active = 0;
+  cudaGraphSetConditional(h, more ? 1u : 0u);
+}
+
 extern "C" int smc_nuts_run(smc_model_t m, const smc_sampler_config* cfg, const double* init, int64_t C, smc_run_output* out) {
   if (!m || !cfg || !init || !out) { smc_set_error("smc_nuts_run: NULL argument"); return SMC_ERR_INVALID; }
   Run r;
@@ -1132,6 +1153,12 @@ extern "C" int smc_nuts_run(smc_model_t m, const smc_sampler_config* cfg, const 
   const int ly = lanes_for(C);
   k_nuts_init<<<gridc(C), 128, 0, st>>>(C, T);
   m->ctx->launches++;
+  long long* d_step;
+  SMC_TRY(r.A.alloc(&d_step, 1));
+  SMC_CUDA(cudaMemsetAsync(d_step, 0, sizeof(long long), st));
+  unsigned long long* d_ctl;
+  SMC_TRY(r.A.alloc(&d_ctl, 2));
+  SMC_CUDA(cudaMemsetAsync(d_ctl, 0, 2 * sizeof(unsigned long long), st));
   int64_t evals = 1;
   // Every round ends with "is any chain still building its tree?".  Waiting for that answer before issuing the next
   // round leaves the GPU idle for a host round trip per leapfrog, so when the previous iteration's trees were long the
@@ -1151,8 +1178,86 @@ extern "C" int smc_nuts_run(smc_model_t m, const smc_sampler_config* cfg, const 
   const char* fc = getenv("SMC_COMPACT");
   const bool compact = !(nc && nc[0] == '1') && !(m->row_shard && m->ctx->nranks > 1) && (C >= 4096 || (fc && fc[0] == '1'));
   long long eval_chains = 0;   // chain evaluations actually performed (sum of the evaluated widths)
+  // Opt-in (SMC_NUTS_DEVICE_LOOP=1, below the packing threshold): the round loop on the device.  From the third iteration on an
+  // iteration is ONE graph launch -- begin, a WHILE node whose body is a round (pre, evaluation, post, condition) and whose
+  // condition a kernel sets from the active-chain counter, end -- so no round waits for the host to read that counter.
+  // Bit-identical to the host loop (tests/test_gpu_samplers.py), but not faster on this driver: the WHILE node costs about
+  // what the host round trip with its one-round speculation costs (sleepstudy, 1024 chains: 5.8e6 against 6.6e6
+  // leapfrogs/s; hierarchical: 2.3e6 against 2.6e6; OU with T = 1e6, one chain: 1.44e4 against 1.33e4 evaluations/s;
+  // profiles/nuts_device_loop_r02.json), and a child graph may not sit in a conditional body (tools/cond_graph_probe.cu), so
+  // the evaluation is captured kernel by kernel.  With active-chain packing (>= 4096 chains) the evaluated width changes
+  // between rounds, which a captured body cannot follow.  Hence the host loop stays the default.
+  const char* dl = getenv("SMC_NUTS_DEVICE_LOOP");
+  const bool dev_loop = (dl && dl[0] == '1') && !compact && m->graphs_enabled && smc_comm_graph_ok(m) && cfg->steps > 3;
+  cudaGraphExec_t loop_exec = nullptr;
+  int64_t launches_fixed = 0, launches_round = 0;
+  auto build_loop_graph = [&]() -> bool {
+    cudaGraph_t G = nullptr;
+    if (cudaGraphCreate(&G, 0) != cudaSuccess) return false;
+    bool ok = true;
+    const int64_t l0 = m->ctx->launches, epoch = m->realloc_epoch;
+    // (1) head: clear the counters, begin
+    cudaStreamCaptureStatus cs;
+    const cudaGraphNode_t* deps = nullptr;
+    size_t ndeps = 0;
+    cudaGraph_t gcap = nullptr;
+    ok = ok && cudaStreamBeginCaptureToGraph(st, G, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed) == cudaSuccess;
+    if (!ok) { cudaGetLastError(); cudaGraphDestroy(G); return false; }
+    k_nuts_loop_begin<<<1, 1, 0, st>>>(T.n_active, d_ctl);
+    LAUNCH_LY(k_nuts_begin, r.rng, d_step, C, M, Cpad, r.b0, r.g0, r.l0, T);
+    ok = ok && cudaStreamGetCaptureInfo(st, &cs, nullptr, &gcap, &deps, &ndeps) == cudaSuccess;
+    std::vector<cudaGraphNode_t> head(deps, deps + (ok ? ndeps : 0));
+    ok = (cudaStreamEndCapture(st, &gcap) == cudaSuccess) && ok;
+    // (2) the WHILE node (the first round always runs: default value 1 at every launch)
+    cudaGraphConditionalHandle h;
+    cudaGraphNode_t wnode = nullptr;
+    cudaGraph_t body = nullptr;
+    if (ok) ok = cudaGraphConditionalHandleCreate(&h, G, 1, cudaGraphCondAssignDefault) == cudaSuccess;
+    if (ok) {
+      cudaGraphNodeParams p = {cudaGraphNodeTypeConditional};
+      p.conditional.handle = h;
+      p.conditional.type = cudaGraphCondTypeWhile;
+      p.conditional.size = 1;
+      ok = cudaGraphAddNode(&wnode, G, head.data(), head.size(), &p) == cudaSuccess;
+      if (ok) body = p.conditional.phGraph_out[0];
+    }
+    // (3) body: one round, the evaluation captured inline (its own kernels, not its graph)
+    const int64_t l1 = m->ctx->launches;
+    if (ok) ok = cudaStreamBeginCaptureToGraph(st, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed) == cudaSuccess;
+    if (ok) {
+      LAUNCH_LY(k_nuts_pre, r.rng, d_step, C, M, Cpad, m->beta, 0, T);
+      const int e = smc_model_eval_inline(m, C, true);
+      LAUNCH_LY(k_nuts_post, r.rng, d_step, C, M, Cpad, m->grad, m->logp, 0, T, r.nleap);
+      k_nuts_loop_cond<<<1, 1, 0, st>>>(h, T.n_active, d_ctl, max_rounds);
+      m->ctx->launches += 3;
+      ok = (cudaStreamEndCapture(st, &gcap) == cudaSuccess) && e == SMC_OK;
+    }
+    launches_round = m->ctx->launches - l1;
+    // (4) tail: end of the iteration, next step
+    if (ok) ok = cudaStreamBeginCaptureToGraph(st, G, &wnode, nullptr, 1, cudaStreamCaptureModeRelaxed) == cudaSuccess;
+    if (ok) {
+      LAUNCH_LY(k_nuts_end, d_step, C, M, Cpad, r.b0, r.g0, r.l0, T, r.R, eps_dev, jmax_dev);
+      k_step_inc<<<1, 1, 0, st>>>(d_step);
+      ok = cudaStreamEndCapture(st, &gcap) == cudaSuccess;
+    }
+    launches_fixed = 4;
+    m->ctx->launches = l0;
+    ok = ok && epoch == m->realloc_epoch;
+    if (ok) ok = cudaGraphInstantiate(&loop_exec, G, 0) == cudaSuccess;
+    cudaGraphDestroy(G);
+    if (!ok) { cudaGetLastError(); loop_exec = nullptr; }
+    return ok;
+  };
+  bool loop_failed = false;
   for (long long i = 0; i < cfg->steps && rc == SMC_OK; i++) {
-    LAUNCH_LY(k_nuts_begin, r.rng, i, C, M, Cpad, r.b0, r.g0, r.l0, T);
+    if (dev_loop && !loop_failed && i >= 2) {
+      if (!loop_exec && !build_loop_graph()) loop_failed = true;
+      if (loop_exec) {
+        if (cudaGraphLaunch(loop_exec, st) != cudaSuccess) { smc_set_error("cudaGraphLaunch failed in the NUTS loop"); rc = SMC_ERR_CUDA; break; }
+        continue;
+      }
+    }
+    LAUNCH_LY(k_nuts_begin, r.rng, d_step, C, M, Cpad, r.b0, r.g0, r.l0, T);
     m->ctx->launches++;
     int launched = 0, rounds = 0;
     // Lockstep evaluation only has to cover the chains that are still building a tree.  Their number never grows within
@@ -1173,14 +1278,14 @@ extern "C" int smc_nuts_run(smc_model_t m, const smc_sampler_config* cfg, const 
         k_slot_assign<<<slot_blocks, 256, 0, st>>>(T.active, C, T.blocksum, T.slot);
         m->ctx->launches += 3;
       }
-      LAUNCH_LY(k_nuts_pre, r.rng, i, C, M, Cpad, m->beta, use_slots, T);
+      LAUNCH_LY(k_nuts_pre, r.rng, d_step, C, M, Cpad, m->beta, use_slots, T);
       m->ctx->launches++;
       int e = smc_model_eval_device(m, Ceval, true);
       if (e != SMC_OK) return e;
       evals++;
       eval_chains += Ceval;
       (void)eval_chains;
-      LAUNCH_LY(k_nuts_post, r.rng, i, C, M, Cpad, m->grad, m->logp, use_slots, T, r.nleap);
+      LAUNCH_LY(k_nuts_post, r.rng, d_step, C, M, Cpad, m->grad, m->logp, use_slots, T, r.nleap);
       m->ctx->launches++;
       cudaMemcpyAsync(h_active + slot, T.n_active, sizeof(int), cudaMemcpyDeviceToHost, st);
       cudaEventRecord(ev[slot], st);
@@ -1204,10 +1309,21 @@ extern "C" int smc_nuts_run(smc_model_t m, const smc_sampler_config* cfg, const 
     }
     if (rc != SMC_OK) break;
     prev_rounds = rounds;
-    LAUNCH_LY(k_nuts_end, i, C, M, Cpad, r.b0, r.g0, r.l0, T, r.R, eps_dev, jmax_dev);
-    m->ctx->launches++;
+    LAUNCH_LY(k_nuts_end, d_step, C, M, Cpad, r.b0, r.g0, r.l0, T, r.R, eps_dev, jmax_dev);
+    k_step_inc<<<1, 1, 0, st>>>(d_step);
+    m->ctx->launches += 2;
   }
   cudaStreamSynchronize(st);
+  if (loop_exec) {      // rounds run by the device loop: evaluations and launches for the statistics
+    unsigned long long ctl[2] = {0ull, 0ull};
+    cudaMemcpy(ctl, d_ctl, sizeof(ctl), cudaMemcpyDeviceToHost);
+    evals += (int64_t)ctl[1];
+    long long graph_iters = 0;
+    cudaMemcpy(&graph_iters, d_step, sizeof(long long), cudaMemcpyDeviceToHost);
+    graph_iters -= 2;
+    m->ctx->launches += launches_fixed * graph_iters + launches_round * (int64_t)ctl[1];
+    cudaGraphExecDestroy(loop_exec);
+  }
   cudaEventDestroy(ev[0]);
   cudaEventDestroy(ev[1]);
   cudaFreeHost(h_active);

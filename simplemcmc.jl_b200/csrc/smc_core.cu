@@ -1023,6 +1023,12 @@ int smc_model_eval_device(smc_model_s* m, int64_t C, bool with_grad) {
   return eval_body(m, C, with_grad);
 }
 
+int smc_model_eval_inline(smc_model_s* m, int64_t C, bool with_grad) {
+  if (!m->finalized || C < 1 || C > m->Cmax) { smc_set_error("smc_model_eval_inline: model not finalized or chains out of range"); return SMC_ERR_INVALID; }
+  m->C = C;
+  return eval_body(m, C, with_grad);
+}
+
 extern "C" int smc_eval(smc_model_t m, const double* beta, int64_t C, double* logp, double* grad) {
   if (!m || !beta || !logp) { smc_set_error("smc_eval: NULL argument"); return SMC_ERR_INVALID; }
   if (!m->finalized) { smc_set_error("model is not finalized (call smc_model_finalize after binding data)"); return SMC_ERR_INVALID; }

@@ -220,6 +220,9 @@ struct smc_model_s {
 
 // smc_core.cu
 int smc_model_eval_device(smc_model_s* m, int64_t C, bool with_grad);  // beta -> logp, grad (device resident)
+// the same launch sequence issued kernel by kernel (never as the evaluation's own graph): for callers that capture it into a
+// graph of their own where a child graph may not go (the body of a conditional node, samplers.cu)
+int smc_model_eval_inline(smc_model_s* m, int64_t C, bool with_grad);
 int smc_stage_reserve(smc_model_s* m, int64_t doubles);
 void smc_graphs_invalidate(smc_model_s* m);
 bool smc_comm_graph_ok(const smc_model_s* m);

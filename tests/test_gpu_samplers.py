@@ -151,6 +151,30 @@ def test_nuts_active_chain_compaction_is_invisible(smc):
     assert relerr(packed["draws"][:3], full["draws"][:3]) < 1e-8
 
 
+def test_nuts_device_side_round_loop_is_invisible(smc):
+    """SMC_NUTS_DEVICE_LOOP=1 (opt-in, below the packing threshold): an iteration of simpleNUTS is one graph launch whose WHILE
+    node repeats the round (pre, evaluation, post) until a kernel finds no chain building its tree (src/samplers.jl:263-311 in
+    lockstep): same kernels on the same data in the same order as the host-driven loop, so everything is bit-identical; the
+    host loop may only have issued speculative rounds that found no active chain"""
+    import os
+    data, nsub = sleepstudy_data()
+    cases = [("x ~ Normal(1, 2)\ny ~ Gamma(2, 1)", [("x", 0.5), ("y", 1.0)], {}, 200, 40),
+             (SLEEPSTUDY2, [("intercept", 250.0), ("slope", 10.0), ("rand_int", np.zeros(nsub)), ("rand_slope", np.zeros(nsub))], data, 64, 12)]
+    for model, init, dat, C, steps in cases:
+        out = []
+        for flag in ("0", "1"):
+            os.environ["SMC_NUTS_DEVICE_LOOP"] = flag
+            low, dev = _build(model, init, dat, C)
+            out.append(dev.run("nuts", np.array(low.init), C, steps, 2, seed=7))
+            dev.close()
+        os.environ.pop("SMC_NUTS_DEVICE_LOOP")
+        host, devl = out
+        for k in ("draws", "epsilon", "jmax", "accept", "loglik", "mean", "m2"):
+            assert np.array_equal(host[k], devl[k]), k
+        assert host["n_leapfrogs"] == devl["n_leapfrogs"] and host["n_evals"] >= devl["n_evals"] > steps
+        assert devl["n_kernel_launches"] > 0
+
+
 def test_device_side_lag1_statistics_give_the_same_ess(smc):
     """calcStats! (src/samplers.jl:352-374) from the moments and lag-1 sums the device accumulates == the same formula on
     the stored draws; with store_draws=False the ESS is still there"""

@@ -52,8 +52,15 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed"]
 
 
+def _raw_page(path):
+    """the raw page of a report; `path` may already be that page as CSV (reports stay on the GPU box when they are large)"""
+    if path.endswith(".csv"):
+        return open(path).read()
+    return subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+
+
 def full(path, out):
-    txt = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    txt = _raw_page(path)
     rd = list(csv.reader(io.StringIO(txt)))
     hdr, units, data = rd[0], rd[1], rd[2:]
     res = []
@@ -62,7 +69,9 @@ def full(path, out):
         u = dict(zip(hdr, units))
         item = {"kernel": d.get("Kernel Name", "").split("(")[0], "id": d.get("ID")}
         for k in hdr:
-            if k in KEYS or "fp64" in k or "stalled" in k and "ratio" in k and "per_issue_active" in k:
+            if k in KEYS or "fp64" in k or ("stalled" in k and "ratio" in k and "per_issue_active" in k) or \
+                    (k.startswith("sm__inst_executed_pipe_") and k.endswith(".avg.pct_of_peak_sustained_active")) or \
+                    (k.startswith("sm__pipe_") and k.endswith("cycles_active.avg.pct_of_peak_sustained_active")):
                 try:
                     item[k] = float(d[k].replace(",", ""))
                 except Exception:
@@ -75,9 +84,28 @@ def full(path, out):
         print(it["kernel"], {k: v for k, v in it.items() if k in ("gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "launch__registers_per_thread")})
 
 
+def traffic_metrics(path, out):
+    """the same from a `--metrics ...dram__bytes_read.sum,dram__bytes_write.sum --csv --log-file` capture (one row per metric)"""
+    lines = [ln for ln in open(path) if not ln.startswith("==")]
+    vals, kern = {}, ""
+    for r in csv.DictReader(io.StringIO("".join(lines))):
+        vals[r["Metric Name"]] = (float(r["Metric Value"].replace(",", "")), r["Metric Unit"])
+        kern = r["Kernel Name"].split("(")[0]
+        grid, block = r["Grid Size"], r["Block Size"]
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    rd, wr = (vals[k][0] * scale[vals[k][1]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+    t, tu = vals["gpu__time_duration.sum"]
+    res = {"kernel": kern, "grid": grid, "block": block, "dram_bytes_read": rd, "dram_bytes_write": wr, "dram_bytes_per_launch": rd + wr,
+           "l2_bytes": vals.get("lts__t_bytes.sum", (None, ""))[0],
+           "duration_ms_under_ncu": t * {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(tu, 1e-6),
+           "source": "ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_bytes.sum --clock-control none, one launch: " + path}
+    json.dump(res, open(out, "w"), indent=1)
+    print(res)
+
+
 def traffic(path, out):
     """dram__bytes_read.sum + dram__bytes_write.sum of the captured kernel (one launch) -> the file bench.py reads for roofline.traffic"""
-    txt = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    txt = _raw_page(path)
     rd = list(csv.reader(io.StringIO(txt)))
     hdr, units, row = rd[0], rd[1], rd[2]
     d, u = dict(zip(hdr, row)), dict(zip(hdr, units))
@@ -94,4 +122,4 @@ def traffic(path, out):
 
 
 if __name__ == "__main__":
-    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "full": full, "traffic": traffic, "traffic_metrics": traffic_metrics}[sys.argv[1]](sys.argv[2], sys.argv[3])

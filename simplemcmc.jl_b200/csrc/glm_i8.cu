@@ -303,9 +303,10 @@ __global__ void __launch_bounds__(NTI, 1) k_glm_i8(GlmI8Args a) {   // 17 warps 
   if (issuer) {
     // ================= issuer warp: waits by the whole warp, bulk copies and tensor instructions by lane 0 =================
     auto issue_p1 = [&](uint32_t xs) {
-#pragma unroll 1
+#pragma unroll
       for (int i = 0; i < NS8; i++) {
         const uint32_t idesc = make_idesc(TR, NC * (NB - i), 0, 0);       // beta slices j <= NB - 1 - i
+#pragma unroll
         for (int ks = 0; ks < MP / 32; ks++)
           mma_i8(tmem + (uint32_t)(i * NC), make_desc(xs + i * 512 + ks * 256, 128, 4096),
                  make_desc(qbs + ks * 256, 128, MP * 8), idesc, (i | ks) != 0);
@@ -326,7 +327,11 @@ __global__ void __launch_bounds__(NTI, 1) k_glm_i8(GlmI8Args a) {   // 17 warps 
     for (long long t = t_begin; t < t_end && ok; t++) {
       const long long k = t - t_begin;
       const int stage = (int)(k & 1);
-      if (t + 1 < t_end) {                                // accumulator set 1 read by every epilogue warp: product 1 (t+1)
+      if (t + 1 < t_end) {
+        // (C) every epilogue warp is through the FP64 half of this tile's slicing (and long through its reads of accumulator
+        // set 1): product 1 of tile t+1 now runs under the integer half of the slicing.  FP64 instructions are starved while the
+        // tensor core works (tools/fp64_vs_imma_probe.cu: 14 instead of 2 cycles per DFMA), so the tensor instructions are
+        // started where the epilogues have integer work only.
         ok = mbar_wait(&barA, (uint32_t)(k & 1)) && mbar_wait(&barX[stage ^ 1], (uint32_t)(((k + 1) >> 1) & 1));
         fence_after();
         if (lane == 0) issue_p1(xs0 + (uint32_t)(stage ^ 1) * XT_BYTES);
@@ -340,9 +345,10 @@ __global__ void __launch_bounds__(NTI, 1) k_glm_i8(GlmI8Args a) {   // 17 warps 
       cnt++;
       if (lane == 0) {
         const uint32_t xs = xs0 + (uint32_t)stage * XT_BYTES, qd = qds + (uint32_t)stage * QD_BUF;
-#pragma unroll 1
+#pragma unroll
         for (int i = 0; i < NS8; i += 2) {
           const uint32_t idesc = make_idesc(128, NC * (NS8 - i), 1, 1);
+#pragma unroll
           for (int ks = 0; ks < TR / 32; ks++)
             mma_i8(tmem + 256u + (uint32_t)(i * NC), make_desc(xs + i * 512 + ks * 16384, 4096, 128),
                    make_desc(qd + ks * 4 * QD_LBO, QD_LBO, 128), idesc, ((i | ks) != 0 || !fresh) ? 1u : 0u);
@@ -382,6 +388,9 @@ __global__ void __launch_bounds__(NTI, 1) k_glm_i8(GlmI8Args a) {   // 17 warps 
       fence_after();
       unsigned int hw[CQ];
       bool over = false;
+      // integer phase (runs under product 2 of the previous tile): the group sums of all eight chains -> two int64 halves each,
+      // as bit patterns of doubles on top of the magic bias
+      long long hi[CQ], lo[CQ];
 #pragma unroll
       for (int hf = 0; hf < 2; hf++) {                      // four chains at a time (registers)
         int32_t acc[NB][4];
@@ -398,15 +407,23 @@ __global__ void __launch_bounds__(NTI, 1) k_glm_i8(GlmI8Args a) {   // 17 warps 
           // pairs in two int64 halves on top of the magic bias: seven instructions instead of fourteen
           const int b0 = g[0] * 256 + g[1], b1 = g[2] * 256 + g[3], b2 = g[4] * 256 + g[5];
           const int b3 = NB == 8 ? g[6] * 256 + g[7] : g[6];
-          const long long hi = mad_wide(b0, wm.m16, mad_wide(b1, wm.m0, MAGIC_BITS));
-          const long long lo = mad_wide(b2, NB == 8 ? wm.m16 : wm.m8, mad_wide(b3, wm.m0, MAGIC_BITS));
-          const double4 sc = s_sc[q * CQ + u];
-          const double w = (fma(__longlong_as_double(hi), sc.x, sc.z) + fma(__longlong_as_double(lo), sc.y, sc.w)) - yr;
-          d[u] = w;
-          lacc[u] = fma(w, w, lacc[u]);
-          hw[u] = (unsigned int)__double2hiint(w) & 0x7fffffffu;
-          over = over || hw[u] >= lim[u];
+          hi[u] = mad_wide(b0, wm.m16, mad_wide(b1, wm.m0, MAGIC_BITS));
+          lo[u] = mad_wide(b2, NB == 8 ? wm.m16 : wm.m8, mad_wide(b3, wm.m0, MAGIC_BITS));
         }
+      }
+      // (a scheduling fence: every integer result exists before the first FP64 instruction is issued, so that the compiler
+      // does not interleave the two phases)
+      asm volatile("" : "+l"(hi[0]), "+l"(hi[1]), "+l"(hi[2]), "+l"(hi[3]), "+l"(hi[4]), "+l"(hi[5]), "+l"(hi[6]), "+l"(hi[7]),
+                        "+l"(lo[0]), "+l"(lo[1]), "+l"(lo[2]), "+l"(lo[3]), "+l"(lo[4]), "+l"(lo[5]), "+l"(lo[6]), "+l"(lo[7]));
+      // FP64 phase (the tensor core is idle): one rounding per recombination, w = eta - y
+#pragma unroll
+      for (int u = 0; u < CQ; u++) {
+        const double4 sc = s_sc[q * CQ + u];
+        const double w = (fma(__longlong_as_double(hi[u]), sc.x, sc.z) + fma(__longlong_as_double(lo[u]), sc.y, sc.w)) - yr;
+        d[u] = w;
+        lacc[u] = fma(w, w, lacc[u]);
+        hw[u] = (unsigned int)__double2hiint(w) & 0x7fffffffu;
+        over = over || hw[u] >= lim[u];
       }
       // fast path: no |w| of this warp reaches its chain's sticky scale (the usual case after the first tile).  Otherwise the
       // warp publishes its maxima and raises the flag; warps below their limits need not contribute (their maxima are
@@ -467,7 +484,6 @@ __global__ void __launch_bounds__(NTI, 1) k_glm_i8(GlmI8Args a) {   // 17 warps 
       const int b = (int)(k & 3), stage = (int)(k & 1);
       fence_before();
       asm volatile("bar.sync 1, 512;\n" ::: "memory");      // (A) maxima and flag of tile t complete (epilogue threads only)
-      if (lane == 0) mbar_arrive(&barA);                    // accumulator set 1 has been read by this warp
       // buffers of tile t+2: last read (by the issuer) before it issued product 1 of tile t+2, which epilogue 1 of tile t+2
       // needs; next written in epilogue 1 of tile t+2, after barrier (A) of tile t+1
       if (tid < NC) s_max[(k + 2) & 3][tid] = 0u;
@@ -496,7 +512,9 @@ __global__ void __launch_bounds__(NTI, 1) k_glm_i8(GlmI8Args a) {   // 17 warps 
       //   h 2^28 + l + H8 = (h + Hh - 1) 2^28 + (l + Hl + 2^28),  H8 = Hh 2^28 + Hl.
       constexpr unsigned long long Hh = H8 >> 28, Hl = H8 & ((1ull << 28) - 1);
       constexpr double MU = MAGIC + (double)(long long)(Hh - 1), MW = MAGIC + (double)(long long)(Hl + (1ull << 28));
-      uint32_t xl[CQ], xh[CQ];
+      // FP64 half (the tensor core is idle: product 2 of the previous tile completed under the integer phase of epilogue 1)
+      int ul[CQ];
+      unsigned int wl[CQ];
 #pragma unroll
       for (int u = 0; u < CQ; u++) {
         const double f = __hiloint2double((int)((2100u << 20) - lim[u]), 0);        // 2^54 / scale = 2^(1076 - E)
@@ -504,8 +522,19 @@ __global__ void __launch_bounds__(NTI, 1) k_glm_i8(GlmI8Args a) {   // 17 warps 
         const double uu = fma(d[u], f28, MU);
         const double hs = fma(uu, -0x1p28, MU * 0x1p28);    // -(uu - MU) 2^28, exact: uu - MU is an integer below 2^27
         const double ww = fma(d[u], f, hs) + MW;
-        const unsigned long long t = (unsigned long long)mad_wide(__double2loint(uu), wm.m28,
-                                                                   (long long)(unsigned long long)(unsigned int)__double2loint(ww));
+        ul[u] = __double2loint(uu);
+        wl[u] = (unsigned int)__double2loint(ww);
+      }
+      asm volatile("" : "+r"(ul[0]), "+r"(ul[1]), "+r"(ul[2]), "+r"(ul[3]), "+r"(ul[4]), "+r"(ul[5]), "+r"(ul[6]), "+r"(ul[7]),
+                        "+r"(wl[0]), "+r"(wl[1]), "+r"(wl[2]), "+r"(wl[3]), "+r"(wl[4]), "+r"(wl[5]), "+r"(wl[6]), "+r"(wl[7]));
+      fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&barA);                    // (C) this warp's FP64 work of the tile is done: product 1 of tile t+1 may start
+      // integer half (under product 1 of tile t+1)
+      uint32_t xl[CQ], xh[CQ];
+#pragma unroll
+      for (int u = 0; u < CQ; u++) {
+        const unsigned long long t = (unsigned long long)mad_wide(ul[u], wm.m28, (long long)(unsigned long long)wl[u]);
         const unsigned long long w = t ^ H8;                // byte k = slice 6 - k
         xl[u] = (uint32_t)w;
         xh[u] = (uint32_t)(w >> 32);

@@ -1164,11 +1164,19 @@ extern "C" int smc_nuts_run(smc_model_t m, const smc_sampler_config* cfg, const 
   // round leaves the GPU idle for a host round trip per leapfrog, so when the previous iteration's trees were long the
   // next round is issued before the answer is known (one round in flight ahead): if the answer turns out to be "none",
   // the extra round finds every chain inactive and changes nothing -- at most one wasted evaluation per iteration.
-  int* h_active = nullptr;
-  SMC_CUDA(cudaMallocHost(&h_active, 2 * sizeof(int)));
-  cudaEvent_t ev[2];
-  SMC_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
-  SMC_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+  struct RoundTrip {           // released on every path out of this function
+    int* h_active = nullptr;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    ~RoundTrip() {
+      for (cudaEvent_t e : ev) if (e) cudaEventDestroy(e);
+      if (h_active) cudaFreeHost(h_active);
+    }
+  } rt;
+  SMC_CUDA(cudaMallocHost(&rt.h_active, 2 * sizeof(int)));
+  SMC_CUDA(cudaEventCreateWithFlags(&rt.ev[0], cudaEventDisableTiming));
+  SMC_CUDA(cudaEventCreateWithFlags(&rt.ev[1], cudaEventDisableTiming));
+  int* const h_active = rt.h_active;
+  cudaEvent_t* const ev = rt.ev;
   int rc = SMC_OK;
   const int max_rounds = 1 << kMaxDepth;
   int prev_rounds = 0;
@@ -1324,9 +1332,6 @@ extern "C" int smc_nuts_run(smc_model_t m, const smc_sampler_config* cfg, const 
     m->ctx->launches += launches_fixed * graph_iters + launches_round * (int64_t)ctl[1];
     cudaGraphExecDestroy(loop_exec);
   }
-  cudaEventDestroy(ev[0]);
-  cudaEventDestroy(ev[1]);
-  cudaFreeHost(h_active);
   if (rc != SMC_OK) return rc;
   SMC_TRY(run_finish(r, evals));
   SMC_TRY(copy_out_blocks(r, eps_dev, out->epsilon, cfg->steps, 1));

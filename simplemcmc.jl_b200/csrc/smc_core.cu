@@ -909,6 +909,43 @@ extern "C" int smc_model_finalize(smc_model_t m, int64_t max_chains, int row_sha
   SMC_CUDA(cudaMemcpyAsync(&hbad, m->bad + Cpad, sizeof(int), cudaMemcpyDeviceToHost, st));
   SMC_CUDA(cudaStreamSynchronize(st));
   if (hbad) { smc_set_error("Initial values out of model support, try other values (a parameter-independent density is zero)"); return SMC_ERR_SUPPORT; }
+  // Row-sharded models: every bound array is this rank's row shard of the caller's data, and only SMC_OP_GLM statements sum
+  // over the rows ACROSS the ranks (glm_fused.cu / smc_p2p.cu).  Any other statement that consumes a bound array (or a header
+  // value computed from one) would reduce over the local shard only -- every rank a different logp / gradient, chains that
+  // drift apart without an error -- so such tapes are refused (Poisson regression, a Normal likelihood with sigma as a
+  // parameter, anything lowered with fuse = False).
+  if (row_shard) {
+    std::vector<char> rowdep(m->regs.size(), 0);
+    for (size_t i = 0; i < m->regs.size(); i++)
+      if (m->regs[i].d.kind == SMC_REG_DATA && m->regs[i].numel > 1) rowdep[i] = 1;
+    auto reads_shard = [&](const smc_tape_stmt& s) -> bool {
+      for (uint32_t k = 0; k < s.nsrc && k < 4; k++)
+        if (s.src[k] < rowdep.size() && rowdep[s.src[k]]) return true;
+      if (s.op == SMC_OP_FUSED && s.aux0 < m->programs.size())
+        for (const smc_prog_instr& in : m->programs[s.aux0].instr)
+          if ((in.op == SMC_P_LOADV || in.op == SMC_P_LOADS) && in.reg < rowdep.size() && rowdep[in.reg]) return true;
+      return false;
+    };
+    for (int si : m->hdr_stmts) {
+      const smc_tape_stmt& s = m->stmts[si];
+      if (!reads_shard(s)) continue;
+      if (s.dst < rowdep.size()) rowdep[s.dst] = 1;
+      if (s.op == SMC_OP_FUSED && s.aux0 < m->programs.size()) {
+        for (const smc_prog_instr& in : m->programs[s.aux0].instr)
+          if (in.op == SMC_P_STOREV && in.reg < rowdep.size()) rowdep[in.reg] = 1;
+        for (const smc_prog_red& rd : m->programs[s.aux0].red)
+          if (rd.reg < rowdep.size()) rowdep[rd.reg] = 1;
+      }
+    }
+    for (int si : m->body_stmts) {
+      const smc_tape_stmt& s = m->stmts[si];
+      if (s.op == SMC_OP_GLM || !reads_shard(s)) continue;
+      smc_set_error("row-sharded models: statement %d (opcode %u) reads the row-sharded data outside a fused GLM statement; its sum over "
+                    "the rows would cover this rank's shard only.  Supported with shard=\"rows\": Normal (literal sigma), Bernoulli and "
+                    "Binomial (literal n) likelihoods of X * beta", si, s.op);
+      return SMC_ERR_INVALID;
+    }
+  }
   // fused GLM statements
   for (auto& g : m->glm) smc_glm_release(g, m->ctx->stream);
   m->glm.clear();

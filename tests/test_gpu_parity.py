@@ -301,6 +301,27 @@ def test_error_behaviour(smc):
         smc.simpleHMC("x ~ Normal(0,1)", steps=10, burnin=20, x=0.0)          # checkSteps, src/samplers.jl:324-327
 
 
+def test_row_sharding_refuses_tapes_it_cannot_sum_across_ranks(smc):
+    """shard="rows": only fused GLM statements sum over the rows across the ranks.  A tape that reduces the sharded data in any
+    other statement (Poisson regression, a Normal likelihood whose sigma is a parameter, an unfused lowering) would give every
+    rank a different logp / gradient without an error: smc_model_finalize refuses it.  The supported families still build."""
+    from simplemcmc_jl_b200 import api
+    from simplemcmc_jl_b200.capi import SMCError
+    X, Y, _ = logistic_data(512, 4)
+    low, dev = api._build(LOGISTIC, [("vars", np.zeros(4))], dict(X=X, Y=Y), True, 2, 0, "assign", shard="rows")
+    lp, g = dev.eval(np.zeros((2, 4)))          # (one rank, no communicator: the shard is the whole data)
+    assert np.all(np.isfinite(lp))
+    dev.close()
+    counts = np.random.default_rng(0).poisson(2.0, 512).astype(np.float64)
+    refused = [("vars ~ Normal(0, 1.0)\nlam = exp(X * vars)\nY ~ Poisson(lam)", [("vars", np.zeros(4))], dict(X=X, Y=counts), {}),
+               ("vars ~ Normal(0, 1.0)\ns ~ Gamma(2, 2)\nresid = Y - X * vars\nresid ~ Normal(0, s)", [("vars", np.zeros(4)), ("s", 1.0)],
+                dict(X=X, Y=Y), {}),
+               (LOGISTIC, [("vars", np.zeros(4))], dict(X=X, Y=Y), dict(fuse=False))]
+    for model, init, data, kw in refused:
+        with pytest.raises(SMCError, match="row-sharded"):
+            api._build(model, init, data, True, 2, 0, "assign", shard="rows", **kw)
+
+
 def test_no_gradient_closure_and_kwarg_order(smc):
     f, n, pars, init = smc.generateModelFunction("a ~ Normal(0,1)\nb ~ Normal(a, 2.0)", gradient=False, b=np.array([1.0, 2.0]), a=0.5)
     assert [p.sym for p in pars] == ["b", "a"] and list(init) == [1.0, 2.0, 0.5]    # kwarg order, parsing.jl:303-334

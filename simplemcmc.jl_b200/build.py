@@ -51,12 +51,12 @@ def build(force=False, verbose=False):
     return LIB
 
 
-TOOLS = ["i8_umma_probe", "ozaki_glm_proto"]
+TOOLS = ["i8_umma_probe", "fp64_issue_probe", "fp64_vs_imma_probe", "cond_graph_probe"]
 
 
 def build_tools(force=False):
-    """stand-alone sm_100a probes under tools/ (the tcgen05 int8 probe and the sliced-integer GLM prototype of DESIGN.md
-    section 8); not linked into the library"""
+    """stand-alone sm_100a probes under tools/ (the tcgen05 int8 instruction probe, the FP64 issue probes and the CUDA-graph
+    WHILE-node probe of DESIGN.md section 8); not linked into the library"""
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     tools = os.path.join(HERE, "..", "tools")
     out = []

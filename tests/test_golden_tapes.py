@@ -69,10 +69,11 @@ def test_golden_tape_parses_by_the_header_layout(case):
         assert ops.count(48) == 1
 
 
-def test_golden_tapes_compile_when_a_device_is_present():
-    import torch
-    if not torch.cuda.is_available():
-        pytest.skip("smc_model_compile needs a context (no CPU fallback)")
+@pytest.mark.gpu
+def test_golden_tapes_compile_on_the_device():
+    """smc_model_compile / bind / finalize accept the golden blobs (the library has no CPU fallback: a gpu test)"""
+    from smc_pkg import load_package
+    load_package()
     from simplemcmc_jl_b200 import capi
     ctx = capi.Context.default(0)
     for name, model, init, data, kw in CASES:

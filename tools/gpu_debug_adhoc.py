@@ -1,6 +1,6 @@
 """Ad-hoc GPU check used during development (not a test): rule matrix + example models vs the oracle."""
 import os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # (lives under tests/: the oracle is test infrastructure)
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # (a development aid that calls the oracle as the checker, like the tests)
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 from smc_pkg import load_package

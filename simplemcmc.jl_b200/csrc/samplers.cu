@@ -729,6 +729,16 @@ struct Nuts {
   int *j, *leaf, *dir, *active, *newdbl, *ucount, *moved;
   int* n_active;
   unsigned long long* rounds_active;
+  // asynchronous iterations (below): the chain's own iteration number, and the round in which it has to end / begin one
+  long long* istep;
+  int *end_round, *begin_round;
+};
+// the iteration number a kernel works on: one counter in device memory (lockstep: every chain is in the same iteration, and a
+// captured graph replays the kernels while the counter advances) or the chain's own (asynchronous iterations)
+struct StepSrc {
+  const long long* global;
+  const long long* per_chain;
+  __device__ __forceinline__ long long of(long long c, bool in) const { return per_chain ? (in ? per_chain[c] : 0) : *global; }
 };
 
 // this lane's share of the two U-turn dot products (src/samplers.jl:48):
@@ -814,14 +824,16 @@ __global__ void k_nuts_init(long long C, Nuts T) {
 }
 
 template <int LY>
-__global__ void __launch_bounds__(256) k_nuts_begin(RngSrc rng, const long long* stepp, long long C, long long M, long long Cpad,
+__global__ void __launch_bounds__(256) k_nuts_begin(RngSrc rng, StepSrc steps, int round, long long C, long long M, long long Cpad,
                                                        const double* b0, const double* g0, const double* l0, Nuts T) {
   __shared__ double sh[LY * SMC_CXB];
-  const long long step = *stepp;
   const Ln L = lanes<LY>(C);
   const long long c = L.c;
+  const long long step = steps.of(c, L.in);
+  // asynchronous iterations: only the chains whose previous iteration ended in the last round begin one now
+  const bool go = L.in && (round < 0 || T.begin_round[c] == round);
   double ss = 0.0;
-  if (L.in) {
+  if (go) {
     ss = draw_normals<LY>(rng, step, c, C, M, Cpad, T.mv, T.pv, L.ly);
     for (long long k = L.ly; k < M; k += LY) {
       long long o = k * Cpad + c;
@@ -831,7 +843,7 @@ __global__ void __launch_bounds__(256) k_nuts_begin(RngSrc rng, const long long*
     }
   }
   ss = ysum<LY>(ss, sh);
-  if (!L.in || L.ly != 0) return;
+  if (!go || L.ly != 0) return;
   double ll = l0[c];
   T.ml[c] = ll; T.pl[c] = ll; T.sl[c] = ll;
   double H0 = ll - ss / 2.0;
@@ -848,11 +860,11 @@ __global__ void __launch_bounds__(256) k_nuts_begin(RngSrc rng, const long long*
 }
 
 template <int LY>
-__global__ void __launch_bounds__(256) k_nuts_pre(RngSrc rng, const long long* stepp, long long C, long long M, long long Cpad,
+__global__ void __launch_bounds__(256) k_nuts_pre(RngSrc rng, StepSrc steps, long long C, long long M, long long Cpad,
                                                      double* beta, int use_slots, Nuts T) {
-  const long long step = *stepp;
   const Ln L = lanes<LY>(C);
   const long long c = L.c;
+  const long long step = steps.of(c, L.in);
   const bool act = L.in && T.active[c];
   int newdbl = 0, dir = 0, k = 0;
   double eps = 0.0, lp_edge = 0.0;
@@ -911,13 +923,13 @@ __global__ void __launch_bounds__(256) k_nuts_pre(RngSrc rng, const long long* s
 }
 
 template <int LY>
-__global__ void __launch_bounds__(256) k_nuts_post(RngSrc rng, const long long* stepp, long long C, long long M, long long Cpad,
+__global__ void __launch_bounds__(256) k_nuts_post(RngSrc rng, StepSrc steps, int round, long long C, long long M, long long Cpad,
                                                       const double* egrad, const double* elogp, int use_slots, Nuts T,
                                                       unsigned long long* nleap) {
   __shared__ double sh[2 * LY * SMC_CXB];
-  const long long step = *stepp;
   const Ln L = lanes<LY>(C);
   const long long c = L.c;
+  const long long step = steps.of(c, L.in);
   const int ly = L.ly;
   const bool act = L.in && T.active[c];
   const long long LS = M * Cpad;  // stride between stack levels
@@ -968,7 +980,11 @@ __global__ void __launch_bounds__(256) k_nuts_post(RngSrc rng, const long long* 
     copy_vec<LY>(T.csg, grad, c, M, Cpad, ly);
   }
   // ---- merges where the recursion returns (:238-256): levels = trailing one bits of the leaf index.  The loop is
-  // uniform over the block (the U-turn test needs every lane); a chain leaves it at `stop_level`.
+  // uniform over the block (the U-turn test needs every lane); a chain leaves it at `stop_level`.  (With asynchronous
+  // iterations the chains of a block are at different leaves and the loop runs to the deepest merge of any of its 32 chains
+  // in every round: 62.7 us per launch at 1024 chains against 18.7 in lockstep.  Putting the lanes of a chain into one warp --
+  // shuffles instead of shared-memory sums, a loop uniform per warp -- was measured slower in BOTH modes, 3.8e7 against 4.2e7
+  // leapfrogs/s in lockstep: the state vectors are then touched in 32-byte pieces.)
   bool merging = act;
   int stop_level = kMaxDepth;
   for (int level = 0; level < kMaxDepth; level++) {
@@ -1064,18 +1080,20 @@ __global__ void __launch_bounds__(256) k_nuts_post(RngSrc rng, const long long* 
     atomicAdd(T.n_active, 1);
   } else {
     T.active[c] = 0;
+    if (round >= 0) T.end_round[c] = round;   // asynchronous iterations: this chain ends its iteration in this round
   }
 }
 
 // dual averaging of epsilon (:294-302), addToRes! (:305), misc (:307-308), state0 = state (:310)
 template <int LY>
-__global__ void __launch_bounds__(256) k_nuts_end(const long long* stepp, long long C, long long M, long long Cpad, double* b0,
-                                                     double* g0, double* l0, Nuts T, Recorder R, double* eps_out,
-                                                     double* jmax_out) {
-  const long long step = *stepp;
+__global__ void __launch_bounds__(256) k_nuts_end(StepSrc steps, int round, long long total_steps, long long C, long long M,
+                                                     long long Cpad, double* b0, double* g0, double* l0, Nuts T, Recorder R,
+                                                     double* eps_out, double* jmax_out) {
   const Ln L = lanes<LY>(C);
   const long long c = L.c;
   if (!L.in) return;
+  if (round >= 0 && T.end_round[c] != round) return;     // asynchronous iterations: only the chains whose tree was completed now
+  const long long step = steps.of(c, true);
   const int ly = L.ly;
   copy_vec<LY>(b0, T.sb, c, M, Cpad, ly);
   copy_vec<LY>(g0, T.sg, c, M, Cpad, ly);
@@ -1101,6 +1119,22 @@ __global__ void __launch_bounds__(256) k_nuts_end(const long long* stepp, long l
   l0[c] = sl;
   if (eps_out) eps_out[step * Cpad + c] = eps;
   if (jmax_out) jmax_out[step * Cpad + c] = (double)T.j[c];
+  if (round >= 0) {                                      // on to the chain's next iteration, in the next round
+    T.istep[c] = step + 1;
+    if (step + 1 < total_steps) {
+      T.begin_round[c] = round + 1;
+      atomicAdd(T.n_active, 1);
+    }
+  }
+}
+
+__global__ void k_nuts_async_init(long long C, Nuts T) {
+  long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  T.istep[c] = 0;
+  T.begin_round[c] = 0;
+  T.end_round[c] = -1;
+  T.active[c] = 0;
 }
 
 }  // namespace
@@ -1159,6 +1193,7 @@ extern "C" int smc_nuts_run(smc_model_t m, const smc_sampler_config* cfg, const 
   unsigned long long* d_ctl;
   SMC_TRY(r.A.alloc(&d_ctl, 2));
   SMC_CUDA(cudaMemsetAsync(d_ctl, 0, 2 * sizeof(unsigned long long), st));
+  const StepSrc lock = {d_step, nullptr};
   int64_t evals = 1;
   // Every round ends with "is any chain still building its tree?".  Waiting for that answer before issuing the next
   // round leaves the GPU idle for a host round trip per leapfrog, so when the previous iteration's trees were long the
@@ -1212,7 +1247,7 @@ extern "C" int smc_nuts_run(smc_model_t m, const smc_sampler_config* cfg, const 
     ok = ok && cudaStreamBeginCaptureToGraph(st, G, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed) == cudaSuccess;
     if (!ok) { cudaGetLastError(); cudaGraphDestroy(G); return false; }
     k_nuts_loop_begin<<<1, 1, 0, st>>>(T.n_active, d_ctl);
-    LAUNCH_LY(k_nuts_begin, r.rng, d_step, C, M, Cpad, r.b0, r.g0, r.l0, T);
+    LAUNCH_LY(k_nuts_begin, r.rng, lock, -1, C, M, Cpad, r.b0, r.g0, r.l0, T);
     ok = ok && cudaStreamGetCaptureInfo(st, &cs, nullptr, &gcap, &deps, &ndeps) == cudaSuccess;
     std::vector<cudaGraphNode_t> head(deps, deps + (ok ? ndeps : 0));
     ok = (cudaStreamEndCapture(st, &gcap) == cudaSuccess) && ok;
@@ -1233,9 +1268,9 @@ extern "C" int smc_nuts_run(smc_model_t m, const smc_sampler_config* cfg, const 
     const int64_t l1 = m->ctx->launches;
     if (ok) ok = cudaStreamBeginCaptureToGraph(st, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed) == cudaSuccess;
     if (ok) {
-      LAUNCH_LY(k_nuts_pre, r.rng, d_step, C, M, Cpad, m->beta, 0, T);
+      LAUNCH_LY(k_nuts_pre, r.rng, lock, C, M, Cpad, m->beta, 0, T);
       const int e = smc_model_eval_inline(m, C, true);
-      LAUNCH_LY(k_nuts_post, r.rng, d_step, C, M, Cpad, m->grad, m->logp, 0, T, r.nleap);
+      LAUNCH_LY(k_nuts_post, r.rng, lock, -1, C, M, Cpad, m->grad, m->logp, 0, T, r.nleap);
       k_nuts_loop_cond<<<1, 1, 0, st>>>(h, T.n_active, d_ctl, max_rounds);
       m->ctx->launches += 3;
       ok = (cudaStreamEndCapture(st, &gcap) == cudaSuccess) && e == SMC_OK;
@@ -1244,7 +1279,7 @@ extern "C" int smc_nuts_run(smc_model_t m, const smc_sampler_config* cfg, const 
     // (4) tail: end of the iteration, next step
     if (ok) ok = cudaStreamBeginCaptureToGraph(st, G, &wnode, nullptr, 1, cudaStreamCaptureModeRelaxed) == cudaSuccess;
     if (ok) {
-      LAUNCH_LY(k_nuts_end, d_step, C, M, Cpad, r.b0, r.g0, r.l0, T, r.R, eps_dev, jmax_dev);
+      LAUNCH_LY(k_nuts_end, lock, -1, (long long)cfg->steps, C, M, Cpad, r.b0, r.g0, r.l0, T, r.R, eps_dev, jmax_dev);
       k_step_inc<<<1, 1, 0, st>>>(d_step);
       ok = cudaStreamEndCapture(st, &gcap) == cudaSuccess;
     }
@@ -1256,6 +1291,77 @@ extern "C" int smc_nuts_run(smc_model_t m, const smc_sampler_config* cfg, const 
     if (!ok) { cudaGetLastError(); loop_exec = nullptr; }
     return ok;
   };
+  // ---- asynchronous iterations (opt-in: SMC_NUTS_ASYNC=1, from 32 chains on) -----------------------------------------------
+  // In lockstep a chain whose tree is complete idles until the longest tree of the iteration is: 45 % (sleepstudy) to 62 %
+  // (hierarchical) of the lanes at 16 384 chains.  Chains are independent (src/samplers.jl:199-310 is a loop over ONE chain), so
+  // nothing requires them to be in the same iteration: here every chain carries its own iteration number (RNG streams, the
+  // recorder, the step-size adaptation and the output positions are all keyed by it), a chain whose tree completes in round r
+  // ends its iteration in that round (k_nuts_end, masked) and begins the next one in round r + 1 (k_nuts_begin, masked), and the
+  // run is one sequence of rounds until no chain has work left.  Every chain executes exactly the arithmetic it would in
+  // lockstep: draws, step sizes, tree depths are bit-identical (tests/test_gpu_samplers.py), in a third fewer rounds (active
+  // lanes 0.55 -> 0.80 and 0.38 -> 0.56).  But a round costs more -- the chains of a block are at different leaves, so the merge
+  // loop of k_nuts_post runs to the deepest merge of any of them, the two masked kernels run every round, and lockstep's late
+  // rounds were already cheap through active-chain packing -- so the gain is model dependent (60 iterations,
+  // profiles/nuts_async_r02.json): hierarchical 2.6e6 -> 3.1e6 (1024 chains) and 2.17e7 -> 2.38e7 (16 384) leapfrogs/s,
+  // sleepstudy 6.6e6 -> 6.1e6 and 4.2e7 -> 3.5e7.  Hence opt-in.
+  const char* as = getenv("SMC_NUTS_ASYNC");
+  const bool async = (as && as[0] == '1') && C >= 32 && !dev_loop;
+  if (async) {
+    SMC_TRY(r.A.alloc(&T.istep, Cpad));
+    SMC_TRY(r.A.alloc(&T.end_round, Cpad));
+    SMC_TRY(r.A.alloc(&T.begin_round, Cpad));
+    k_nuts_async_init<<<gridc(C), 128, 0, st>>>(C, T);
+    m->ctx->launches++;
+    const StepSrc own = {nullptr, T.istep};
+    const long long bucket = std::max<long long>(32, ((C + 15) / 16 + 31) / 32 * 32);
+    long long active_ub = C;
+    int launched = 0, rounds = 0;
+    const long long round_cap = (long long)cfg->steps * max_rounds + 2;
+    auto launch_round = [&]() -> int {
+      const int slot = launched & 1, rnd = launched;
+      long long Ceval = C;
+      if (compact && active_ub * 3 <= C * 2) Ceval = std::min<long long>(C, (std::max<long long>(active_ub, 1) + bucket - 1) / bucket * bucket);
+      const int use_slots = Ceval < C ? 1 : 0;
+      cudaMemsetAsync(T.n_active, 0, sizeof(int), st);
+      LAUNCH_LY(k_nuts_begin, r.rng, own, rnd, C, M, Cpad, r.b0, r.g0, r.l0, T);
+      if (use_slots) {
+        k_slot_count<<<slot_blocks, 256, 0, st>>>(T.active, C, T.blocksum);
+        k_slot_scan<<<1, 1024, 0, st>>>(T.blocksum, slot_blocks);
+        k_slot_assign<<<slot_blocks, 256, 0, st>>>(T.active, C, T.blocksum, T.slot);
+        m->ctx->launches += 3;
+      }
+      LAUNCH_LY(k_nuts_pre, r.rng, own, C, M, Cpad, m->beta, use_slots, T);
+      int e = smc_model_eval_device(m, Ceval, true);
+      if (e != SMC_OK) return e;
+      evals++;
+      LAUNCH_LY(k_nuts_post, r.rng, own, rnd, C, M, Cpad, m->grad, m->logp, use_slots, T, r.nleap);
+      LAUNCH_LY(k_nuts_end, own, rnd, (long long)cfg->steps, C, M, Cpad, r.b0, r.g0, r.l0, T, r.R, eps_dev, jmax_dev);
+      m->ctx->launches += 4;
+      cudaMemcpyAsync(h_active + slot, T.n_active, sizeof(int), cudaMemcpyDeviceToHost, st);
+      cudaEventRecord(ev[slot], st);
+      launched++;
+      return SMC_OK;
+    };
+    rc = launch_round();
+    while (rc == SMC_OK) {
+      const int slot = rounds & 1;
+      if (launched == rounds + 1 && launched < round_cap) {     // one round in flight ahead of the host's knowledge
+        rc = launch_round();
+        if (rc != SMC_OK) break;
+      }
+      cudaError_t e = cudaEventSynchronize(ev[slot]);
+      if (e != cudaSuccess) { smc_set_error("CUDA error '%s' in the NUTS loop", cudaGetErrorString(e)); rc = SMC_ERR_CUDA; break; }
+      rounds++;
+      if (h_active[slot] == 0 || rounds >= round_cap) break;
+      active_ub = h_active[slot];
+    }
+    cudaStreamSynchronize(st);
+    if (rc != SMC_OK) return rc;
+    SMC_TRY(run_finish(r, evals));
+    SMC_TRY(copy_out_blocks(r, eps_dev, out->epsilon, cfg->steps, 1));
+    SMC_TRY(copy_out_blocks(r, jmax_dev, out->jmax, cfg->steps, 1));
+    return SMC_OK;
+  }
   bool loop_failed = false;
   for (long long i = 0; i < cfg->steps && rc == SMC_OK; i++) {
     if (dev_loop && !loop_failed && i >= 2) {
@@ -1265,7 +1371,7 @@ extern "C" int smc_nuts_run(smc_model_t m, const smc_sampler_config* cfg, const 
         continue;
       }
     }
-    LAUNCH_LY(k_nuts_begin, r.rng, d_step, C, M, Cpad, r.b0, r.g0, r.l0, T);
+    LAUNCH_LY(k_nuts_begin, r.rng, lock, -1, C, M, Cpad, r.b0, r.g0, r.l0, T);
     m->ctx->launches++;
     int launched = 0, rounds = 0;
     // Lockstep evaluation only has to cover the chains that are still building a tree.  Their number never grows within
@@ -1286,14 +1392,14 @@ extern "C" int smc_nuts_run(smc_model_t m, const smc_sampler_config* cfg, const 
         k_slot_assign<<<slot_blocks, 256, 0, st>>>(T.active, C, T.blocksum, T.slot);
         m->ctx->launches += 3;
       }
-      LAUNCH_LY(k_nuts_pre, r.rng, d_step, C, M, Cpad, m->beta, use_slots, T);
+      LAUNCH_LY(k_nuts_pre, r.rng, lock, C, M, Cpad, m->beta, use_slots, T);
       m->ctx->launches++;
       int e = smc_model_eval_device(m, Ceval, true);
       if (e != SMC_OK) return e;
       evals++;
       eval_chains += Ceval;
       (void)eval_chains;
-      LAUNCH_LY(k_nuts_post, r.rng, d_step, C, M, Cpad, m->grad, m->logp, use_slots, T, r.nleap);
+      LAUNCH_LY(k_nuts_post, r.rng, lock, -1, C, M, Cpad, m->grad, m->logp, use_slots, T, r.nleap);
       m->ctx->launches++;
       cudaMemcpyAsync(h_active + slot, T.n_active, sizeof(int), cudaMemcpyDeviceToHost, st);
       cudaEventRecord(ev[slot], st);
@@ -1317,7 +1423,7 @@ extern "C" int smc_nuts_run(smc_model_t m, const smc_sampler_config* cfg, const 
     }
     if (rc != SMC_OK) break;
     prev_rounds = rounds;
-    LAUNCH_LY(k_nuts_end, d_step, C, M, Cpad, r.b0, r.g0, r.l0, T, r.R, eps_dev, jmax_dev);
+    LAUNCH_LY(k_nuts_end, lock, -1, (long long)cfg->steps, C, M, Cpad, r.b0, r.g0, r.l0, T, r.R, eps_dev, jmax_dev);
     k_step_inc<<<1, 1, 0, st>>>(d_step);
     m->ctx->launches += 2;
   }

@@ -33,13 +33,13 @@ elif which == "cfg4h":
     data, (N, D, L) = hierarchical_data()
     init = [("mu", np.zeros((1, L))), ("sigma", np.ones((1, L))), ("beta", np.zeros((D, L)))]
     low, dev = api._build(HIERARCHICAL, init, data, True, C, 0, "add")
-    raw = dev.run("nuts", np.array(low.init), C, 3, 0, seed=1, store_draws=False, want=())
+    raw = dev.run("nuts", np.array(low.init), C, int(os.environ.get("NUTS_STEPS", 3)), 0, seed=1, store_draws=False, want=())
 elif which == "cfg4":
     C = C or 16384
     data, nsub = sleepstudy_data()
     init = [("intercept", 250.0), ("slope", 10.0), ("rand_int", np.zeros(nsub)), ("rand_slope", np.zeros(nsub))]
     low, dev = api._build(SLEEPSTUDY2, init, data, True, C, 0, "assign")
-    raw = dev.run("nuts", np.array(low.init), C, 3, 0, seed=1, store_draws=False, want=())
+    raw = dev.run("nuts", np.array(low.init), C, int(os.environ.get("NUTS_STEPS", 3)), 0, seed=1, store_draws=False, want=())
 else:
     C = C or 64
     kind = sys.argv[3] if len(sys.argv) > 3 else "hmc"

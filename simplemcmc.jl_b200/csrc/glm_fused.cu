@@ -119,6 +119,8 @@ __device__ __forceinline__ int rowmap(int n) { return n < 4 ? n : (n ^ 1); }
 // the four q lanes of a chain are summed once in the epilogue.  The same columns leave product 1's tensor k-steps too: its
 // accumulator fragment (chain g, rows 2q, 2q+1) takes them as beta[8 + p] * x[row][8 + p] DFMAs.  examples/linear.jl
 // (M = 10): 16 DMMAs + 32 DFMAs per row block of 32 chains instead of 28 DMMAs (448 -> 320 issue cycles per scheduler).
+// (Measured non-improvement on cfg1 with 2^20 chains: the 128-chain tile, MT = 2, at THREE CTAs per SM -- 80 registers, three
+// stages, six warps per scheduler instead of four -- 21.0 against 24.4 TFLOP/s for the 256-chain tile at two CTAs per SM.)
 template <int FAM, int MT, int NWC, int NWR, int MP8, int TRIM, int PUB, int TAIL = 0>
 __global__ void __launch_bounds__(NWC* NWR * 32, (MP8 <= 2 ? 2 : 1)) k_glm(GlmArgs a) {
   constexpr int MP = MP8 * 8, LD = MP + 4, NT = NWC * NWR * 32;

@@ -472,6 +472,17 @@ def _run_ours(args):
                                             "the kernel this path replaces: above 1 because the contraction no longer runs on the FP64 pipe"},
                 "note": "algorithmic HBM bytes per launch = 8*N*M + 8*N = %.0f MB (the sliced X is 8 bytes per element like the FP64 matrix)" % alg_mb}
         tr = os.path.join(ROOT, "profiles", "glm_i8_traffic_r02.json")
+        try:    # the pipe this kernel is actually bound by (FP64 instructions do not issue while the tensor core works, DESIGN.md
+                # section 8): tensor + FP64 cycles of the SM's shared pipe, from the committed ncu capture of the same kernel
+            prof = json.load(open(os.path.join(ROOT, "profiles", "glm_i8_v14_ncu_r02.json")))[0]
+            roof["shared_pipe_ncu"] = {
+                "busy_frac": prof["sm__pipe_shared_cycles_active.avg.pct_of_peak_sustained_active"] / 100.0,
+                "imma_frac": prof["sm__pipe_tensor_subpipe_imma_cycles_active.avg.pct_of_peak_sustained_active"] / 100.0,
+                "fp64_frac": prof["sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"] / 100.0,
+                "source": "profiles/glm_i8_v14_ncu_r02.json (ncu --set full of this kernel at N = 2e5 x 1024 chains), not measured in this run: "
+                          "sm__pipe_shared_cycles_active = int8 tensor cycles + FP64 cycles, which exclude each other on this SM"}
+        except Exception:
+            pass
     else:
         roof = {"bound": "tensor", "achieved": f64, "peak": peak, "unit": "TFLOP/s", "frac": f64 / peak, "traffic": None,
                 "kernel": "k_glm (FP64 DMMA mma.sync.m8n8k4, fused X*B -> Normal logpdf+adjoint -> X'*D)",

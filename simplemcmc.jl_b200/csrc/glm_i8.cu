@@ -58,13 +58,16 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" :: "r"(smem_u32(bar)) : "memory");
 }
+#ifndef SMC_I8_WAIT_NS
+#define SMC_I8_WAIT_NS 2000u     // suspend-time hint of a failed try_wait
+#endif
 // bounded wait (a wrong descriptor must end in an error, not in a hung device)
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   for (int it = 0; it < (1 << 20); it++) {
     uint32_t done;
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
-                 : "=r"(done) : "r"(addr), "r"(parity), "r"(2000u) : "memory");
+                 : "=r"(done) : "r"(addr), "r"(parity), "r"(SMC_I8_WAIT_NS) : "memory");
     if (done) return true;
   }
   return false;

@@ -57,3 +57,24 @@ def test_cfg2_hmc_runs_and_accepts(big):
     assert raw["n_leapfrogs"] == 4096 * 6 * 2
     assert 0.6 < raw["accept_rate"].mean() < 0.95
     assert np.all(np.abs(raw["mean"] - mode) < 0.02)
+
+
+def test_cfg2_posterior_moments_within_monte_carlo_error(big):
+    """north_star's second correctness leg at full size: chains started from exact posterior draws of the conjugate model
+    (Normal(mode, (X'X + I)^-1)) stay distributed that way under simpleHMC -- pooled means and variances of 4096 chains x 60
+    steps against the closed form, in Monte-Carlo standard errors over the chains (64 components: |z| of a few is agreement;
+    tools/posterior_check_cfg2.py, profiles/posterior_cfg2_r02.json: rms z 1.02 / 1.04 at 150 steps)"""
+    X, Y, dev, rng = big
+    M, C, steps = X.shape[1], 4096, 60
+    cov = np.linalg.inv(X.T @ X + np.eye(M))
+    mode = cov @ (X.T @ Y)
+    init = mode[None, :] + np.random.default_rng(42).standard_normal((C, M)) @ np.linalg.cholesky(cov).T
+    raw = dev.run("hmc", init, C, steps, 0, isteps=2, stepsize=5e-4, seed=17, store_draws=False, want=())
+    mean_c, m2_c = raw["mean"], raw["m2"]
+    pooled = mean_c.mean(0)
+    z_mean = (pooled - mode) / (mean_c.std(0, ddof=1) / np.sqrt(C))
+    per_chain_var = m2_c / steps + (mean_c - pooled) ** 2
+    z_var = (per_chain_var.mean(0) - np.diag(cov)) / (per_chain_var.std(0, ddof=1) / np.sqrt(C))
+    assert np.max(np.abs(z_mean)) < 4.5 and np.sqrt(np.mean(z_mean ** 2)) < 1.5, z_mean
+    assert np.max(np.abs(z_var)) < 4.5 and np.sqrt(np.mean(z_var ** 2)) < 1.5, z_var
+    assert np.max(np.abs(per_chain_var.mean(0) / np.diag(cov) - 1.0)) < 0.03

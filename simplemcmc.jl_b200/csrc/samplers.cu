@@ -1128,10 +1128,19 @@ __global__ void __launch_bounds__(256) k_nuts_end(StepSrc steps, int round, long
   }
 }
 
-__global__ void k_nuts_async_init(long long C, Nuts T) {
+__global__ void k_sum_u64(const unsigned long long* v, long long n, unsigned long long* out) {   // one block
+  __shared__ unsigned long long sh[256];
+  unsigned long long t = 0ull;
+  for (long long i = threadIdx.x; i < n; i += 256) t += v[i];
+  sh[threadIdx.x] = t;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) { if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o]; __syncthreads(); }
+  if (threadIdx.x == 0) *out = sh[0];
+}
+__global__ void k_nuts_async_init(long long C, long long first_step, Nuts T) {
   long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  T.istep[c] = 0;
+  T.istep[c] = first_step;
   T.begin_round[c] = 0;
   T.end_round[c] = -1;
   T.active[c] = 0;
@@ -1291,32 +1300,37 @@ extern "C" int smc_nuts_run(smc_model_t m, const smc_sampler_config* cfg, const 
     if (!ok) { cudaGetLastError(); loop_exec = nullptr; }
     return ok;
   };
-  // ---- asynchronous iterations (opt-in: SMC_NUTS_ASYNC=1, from 32 chains on) -----------------------------------------------
-  // In lockstep a chain whose tree is complete idles until the longest tree of the iteration is: 45 % (sleepstudy) to 62 %
-  // (hierarchical) of the lanes at 16 384 chains.  Chains are independent (src/samplers.jl:199-310 is a loop over ONE chain), so
-  // nothing requires them to be in the same iteration: here every chain carries its own iteration number (RNG streams, the
-  // recorder, the step-size adaptation and the output positions are all keyed by it), a chain whose tree completes in round r
-  // ends its iteration in that round (k_nuts_end, masked) and begins the next one in round r + 1 (k_nuts_begin, masked), and the
-  // run is one sequence of rounds until no chain has work left.  Every chain executes exactly the arithmetic it would in
-  // lockstep: draws, step sizes, tree depths are bit-identical (tests/test_gpu_samplers.py), in a third fewer rounds (active
-  // lanes 0.55 -> 0.80 and 0.38 -> 0.56).  But a round costs more -- the chains of a block are at different leaves, so the merge
-  // loop of k_nuts_post runs to the deepest merge of any of them, the two masked kernels run every round, and lockstep's late
-  // rounds were already cheap through active-chain packing -- so the gain is model dependent (60 iterations,
-  // profiles/nuts_async_r02.json): hierarchical 2.6e6 -> 3.1e6 (1024 chains) and 2.17e7 -> 2.38e7 (16 384) leapfrogs/s,
-  // sleepstudy 6.6e6 -> 6.1e6 and 4.2e7 -> 3.5e7.  Hence opt-in.
+  // ---- asynchronous iterations ---------------------------------------------------------------------------------------------
+  // In lockstep a chain whose tree is complete idles until the longest tree of the iteration is: 45 % (sleepstudy) to 73 %
+  // (hierarchical, 2000 iterations) of the lanes at 16 384 chains.  Chains are independent (src/samplers.jl:199-310 is a loop
+  // over ONE chain), so nothing requires them to be in the same iteration: here every chain carries its own iteration number
+  // (RNG streams, the recorder, the step-size adaptation and the output positions are all keyed by it), a chain whose tree
+  // completes in round r ends its iteration in that round (k_nuts_end, masked) and begins the next one in round r + 1
+  // (k_nuts_begin, masked), and the rest of the run is one sequence of rounds until no chain has work left.  Every chain
+  // executes exactly the arithmetic it would in lockstep: draws, step sizes, tree depths are bit-identical
+  // (tests/test_gpu_samplers.py), in roughly half the rounds.  But a round costs 1.5-1.9 times as much -- the chains of a block
+  // are at different leaves, so the merge loop of k_nuts_post runs to the deepest merge of any of them, the two masked kernels
+  // run every round, and lockstep's late rounds were already cheap through active-chain packing -- so it only pays when
+  // lockstep leaves most lanes idle (BASELINE size, 16 384 chains x 2000 iterations, profiles/nuts_baseline_size_r02.jsonl:
+  // hierarchical 1.78e7 -> 2.45e7 leapfrogs/s with 0.27 of the lanes active in lockstep; sleepstudy 4.31e7 -> 3.97e7 with
+  // 0.54).  Policy: the run starts in lockstep; at iterations 48, 128, 384 and 1100 the active-lane fraction measured since the
+  // previous mark decides (< 0.36: the remaining iterations run asynchronously).  Values cannot depend on the decision.
+  // SMC_NUTS_ASYNC=1 switches at iteration 0, SMC_NUTS_ASYNC=0 never.
   const char* as = getenv("SMC_NUTS_ASYNC");
-  const bool async = (as && as[0] == '1') && C >= 32 && !dev_loop;
-  if (async) {
+  const bool async_ok = C >= 32 && !dev_loop && !(as && as[0] == '0');
+  const bool async_forced = async_ok && as && as[0] == '1';
+  auto run_async = [&](long long first_step) -> int {
     SMC_TRY(r.A.alloc(&T.istep, Cpad));
     SMC_TRY(r.A.alloc(&T.end_round, Cpad));
     SMC_TRY(r.A.alloc(&T.begin_round, Cpad));
-    k_nuts_async_init<<<gridc(C), 128, 0, st>>>(C, T);
+    k_nuts_async_init<<<gridc(C), 128, 0, st>>>(C, first_step, T);
     m->ctx->launches++;
     const StepSrc own = {nullptr, T.istep};
     const long long bucket = std::max<long long>(32, ((C + 15) / 16 + 31) / 32 * 32);
     long long active_ub = C;
     int launched = 0, rounds = 0;
-    const long long round_cap = (long long)cfg->steps * max_rounds + 2;
+    const long long round_cap = (long long)(cfg->steps - first_step) * max_rounds + 2;
+    int arc = SMC_OK;
     auto launch_round = [&]() -> int {
       const int slot = launched & 1, rnd = launched;
       long long Ceval = C;
@@ -1342,26 +1356,34 @@ extern "C" int smc_nuts_run(smc_model_t m, const smc_sampler_config* cfg, const 
       launched++;
       return SMC_OK;
     };
-    rc = launch_round();
-    while (rc == SMC_OK) {
+    arc = launch_round();
+    while (arc == SMC_OK) {
       const int slot = rounds & 1;
       if (launched == rounds + 1 && launched < round_cap) {     // one round in flight ahead of the host's knowledge
-        rc = launch_round();
-        if (rc != SMC_OK) break;
+        arc = launch_round();
+        if (arc != SMC_OK) break;
       }
       cudaError_t e = cudaEventSynchronize(ev[slot]);
-      if (e != cudaSuccess) { smc_set_error("CUDA error '%s' in the NUTS loop", cudaGetErrorString(e)); rc = SMC_ERR_CUDA; break; }
+      if (e != cudaSuccess) { smc_set_error("CUDA error '%s' in the NUTS loop", cudaGetErrorString(e)); arc = SMC_ERR_CUDA; break; }
       rounds++;
       if (h_active[slot] == 0 || rounds >= round_cap) break;
       active_ub = h_active[slot];
     }
     cudaStreamSynchronize(st);
-    if (rc != SMC_OK) return rc;
+    return arc;
+  };
+  auto finish = [&]() -> int {
     SMC_TRY(run_finish(r, evals));
     SMC_TRY(copy_out_blocks(r, eps_dev, out->epsilon, cfg->steps, 1));
     SMC_TRY(copy_out_blocks(r, jmax_dev, out->jmax, cfg->steps, 1));
     return SMC_OK;
+  };
+  if (async_forced) {
+    SMC_TRY(run_async(0));
+    return finish();
   }
+  long long probe_rounds = 0, mark_rounds = 0;
+  unsigned long long mark_leaps = 0ull;
   bool loop_failed = false;
   for (long long i = 0; i < cfg->steps && rc == SMC_OK; i++) {
     if (dev_loop && !loop_failed && i >= 2) {
@@ -1426,6 +1448,27 @@ extern "C" int smc_nuts_run(smc_model_t m, const smc_sampler_config* cfg, const 
     LAUNCH_LY(k_nuts_end, lock, -1, (long long)cfg->steps, C, M, Cpad, r.b0, r.g0, r.l0, T, r.R, eps_dev, jmax_dev);
     k_step_inc<<<1, 1, 0, st>>>(d_step);
     m->ctx->launches += 2;
+    probe_rounds += rounds;
+    // checkpoints: the active-lane fraction of the window since the previous mark (leapfrogs against rounds x chains,
+    // speculative rounds included: they are part of lockstep's cost).  The first iterations (epsilon = 1, short cut trees)
+    // say nothing about the run, so the first mark only starts a window.
+    bool mark = false;
+    for (long long cp : {12LL, 48LL, 128LL, 384LL, 1100LL}) mark = mark || (i + 1 == cp);
+    if (async_ok && !cfg->inject_uniforms && mark && cfg->steps - (i + 1) >= 32) {
+      unsigned long long nl = 0ull;
+      k_sum_u64<<<1, 256, 0, st>>>(r.nleap, C, d_ctl);
+      m->ctx->launches++;
+      SMC_CUDA(smc_copy_sync(&nl, d_ctl, sizeof(nl), cudaMemcpyDeviceToHost, st));
+      const double frac = (double)(nl - mark_leaps) / ((double)std::max<long long>(probe_rounds - mark_rounds, 1) * (double)C);
+      const bool first = (i + 1 == 12);
+      mark_leaps = nl;
+      mark_rounds = probe_rounds;
+      if (!first && frac < 0.36) {
+        rc = run_async(i + 1);
+        if (rc != SMC_OK) return rc;
+        return finish();
+      }
+    }
   }
   cudaStreamSynchronize(st);
   if (loop_exec) {      // rounds run by the device loop: evaluations and launches for the statistics

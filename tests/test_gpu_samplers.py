@@ -176,17 +176,20 @@ def test_nuts_device_side_round_loop_is_invisible(smc):
 
 
 def test_nuts_asynchronous_iterations_are_invisible(smc):
-    """SMC_NUTS_ASYNC=1 (opt-in, from 32 chains on): every chain runs through its iterations at its own pace (a chain whose tree
-    is complete starts its next iteration in the next round instead of idling until the longest tree of the iteration is): RNG
+    """asynchronous iterations (from 32 chains on): every chain runs through its iterations at its own pace -- a chain whose tree
+    is complete starts its next iteration in the next round instead of idling until the longest tree of the iteration is.  RNG
     streams, recorder, step-size adaptation and output positions are keyed by the chain's own iteration number, so everything
-    is bit-identical to the iteration-by-iteration loop -- with and without active-chain packing -- in fewer rounds"""
+    is bit-identical to the iteration-by-iteration loop (SMC_NUTS_ASYNC=0), whether the whole run is asynchronous
+    (SMC_NUTS_ASYNC=1), with or without active-chain packing, or the library switches after its probe of the first iterations
+    (the default: it does when lockstep leaves most lanes idle) -- in fewer rounds"""
     import os
     data, nsub = sleepstudy_data()
-    cases = [("x ~ Normal(1, 2)\ny ~ Gamma(2, 1)", [("x", 0.5), ("y", 1.0)], {}, 700, 40, 5),
+    cases = [("x ~ Normal(1, 2)\ny ~ Gamma(2, 1)", [("x", 0.5), ("y", 1.0)], {}, 700, 60, 5),
              (SLEEPSTUDY2, [("intercept", 250.0), ("slope", 10.0), ("rand_int", np.zeros(nsub)), ("rand_slope", np.zeros(nsub))], data, 96, 10, 0)]
     for model, init, dat, C, steps, burnin in cases:
         out = {}
-        for name, env in (("lockstep", {}), ("async", dict(SMC_NUTS_ASYNC="1")), ("async_packed", dict(SMC_NUTS_ASYNC="1", SMC_COMPACT="1"))):
+        for name, env in (("lockstep", dict(SMC_NUTS_ASYNC="0")), ("async", dict(SMC_NUTS_ASYNC="1")), ("auto", {}),
+                          ("async_packed", dict(SMC_NUTS_ASYNC="1", SMC_COMPACT="1"))):
             os.environ.update(env)
             try:
                 low, dev = _build(model, init, dat, C)
@@ -196,13 +199,13 @@ def test_nuts_asynchronous_iterations_are_invisible(smc):
                 for k in env:
                     os.environ.pop(k)
         ref = out["lockstep"]
-        for name in ("async", "async_packed"):
+        for name in ("async", "auto", "async_packed"):
             if name == "async_packed" and model is SLEEPSTUDY2:
                 continue      # (reductions over the data: a packed evaluation rounds differently, see the packing test)
             for k in ("draws", "epsilon", "jmax", "accept", "loglik", "mean", "m2", "accept_rate"):
                 assert np.array_equal(ref[k], out[name][k]), (name, k)
             assert ref["n_leapfrogs"] == out[name]["n_leapfrogs"]
-        assert out["async"]["n_evals"] < ref["n_evals"]
+        assert out["async"]["n_evals"] < ref["n_evals"] and out["auto"]["n_evals"] <= ref["n_evals"]
 
 
 def test_device_side_lag1_statistics_give_the_same_ess(smc):

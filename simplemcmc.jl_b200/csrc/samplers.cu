@@ -64,6 +64,7 @@ __device__ __forceinline__ Ln lanes(long long C) {
 }
 template <int LY>
 __device__ __forceinline__ double ysum(double v, double* sh) {   // sh[LY * SMC_CXB]; call from every thread of the block
+  if (LY == 1) return v;                                          // (one lane per chain: nothing to sum, no barrier)
   sh[threadIdx.y * SMC_CXB + threadIdx.x] = v;
   __syncthreads();
   double t = 0.0;
@@ -74,6 +75,7 @@ __device__ __forceinline__ double ysum(double v, double* sh) {   // sh[LY * SMC_
 }
 template <int LY>
 __device__ __forceinline__ void ysum2(double& a, double& b, double* sh) {   // sh[2 * LY * SMC_CXB]
+  if (LY == 1) return;
   sh[threadIdx.y * SMC_CXB + threadIdx.x] = a;
   sh[LY * SMC_CXB + threadIdx.y * SMC_CXB + threadIdx.x] = b;
   __syncthreads();
@@ -922,8 +924,11 @@ __global__ void __launch_bounds__(256) k_nuts_pre(RngSrc rng, StepSrc steps, lon
   }
 }
 
+#ifndef SMC_NUTS_POST_MINB
+#define SMC_NUTS_POST_MINB 2     // 233 registers uncapped = one block per SM; capped at 128 (no spills): +13..18 % leapfrogs/s at 16 384 chains (3 and 4 blocks spill and are no better)
+#endif
 template <int LY>
-__global__ void __launch_bounds__(256) k_nuts_post(RngSrc rng, StepSrc steps, int round, long long C, long long M, long long Cpad,
+__global__ void __launch_bounds__(256, SMC_NUTS_POST_MINB) k_nuts_post(RngSrc rng, StepSrc steps, int round, long long C, long long M, long long Cpad,
                                                       const double* egrad, const double* elogp, int use_slots, Nuts T,
                                                       unsigned long long* nleap) {
   __shared__ double sh[2 * LY * SMC_CXB];
@@ -999,8 +1004,13 @@ __global__ void __launch_bounds__(256) k_nuts_post(RngSrc rng, StepSrc steps, in
         do_merge = true;
       }
     }
-    if (!__syncthreads_or(merging ? 1 : 0)) break;
-    if (!__syncthreads_or(do_merge ? 1 : 0)) continue;
+    if (LY == 1) {                   // one lane per chain: no cooperation, so the loop need not be uniform over the block
+      if (!merging) break;
+      if (!do_merge) continue;
+    } else {
+      if (!__syncthreads_or(merging ? 1 : 0)) break;
+      if (!__syncthreads_or(do_merge ? 1 : 0)) continue;
+    }
     double d1 = 0.0, d2 = 0.0;
     bool test_uturn = false;
     if (do_merge) {
@@ -1193,7 +1203,8 @@ extern "C" int smc_nuts_run(smc_model_t m, const smc_sampler_config* cfg, const 
   double *eps_dev = nullptr, *jmax_dev = nullptr;
   if (out->epsilon) SMC_TRY(r.A.alloc(&eps_dev, cfg->steps * Cpad));
   if (out->jmax) SMC_TRY(r.A.alloc(&jmax_dev, cfg->steps * Cpad));
-  const int ly = lanes_for(C);
+  int ly = lanes_for(C);
+  if (const char* e = getenv("SMC_NUTS_LY")) ly = (e[0] == '1') ? 1 : 8;      // (A/B measurements)
   k_nuts_init<<<gridc(C), 128, 0, st>>>(C, T);
   m->ctx->launches++;
   long long* d_step;

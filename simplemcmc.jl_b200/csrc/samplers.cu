@@ -978,12 +978,10 @@ __global__ void __launch_bounds__(256, SMC_NUTS_POST_MINB) k_nuts_post(RngSrc rn
   double a2 = fmin(1.0, exp(H - H0));
   double na2 = 1.0;
   double csl = ll;
-  if (act) {
-    copy_vec<LY>(T.cnb, beta, c, M, Cpad, ly);
-    copy_vec<LY>(T.cnv, T.tv, c, M, Cpad, ly);
-    copy_vec<LY>(T.csb, beta, c, M, Cpad, ly);
-    copy_vec<LY>(T.csg, grad, c, M, Cpad, ly);
-  }
+  // the "current" sub-tree starts as the leaf itself: near edge (beta, v) and selected state (beta, grad) ARE the newest point
+  // of the trajectory, so until a merge replaces them they are read from there (pointers per chain) instead of being copied
+  // into cn* / cs* first -- four of the eight to twelve vector copies of a round
+  const double *cur_nb = beta, *cur_nv = T.tv, *cur_sb = beta, *cur_sg = grad;
   // ---- merges where the recursion returns (:238-256): levels = trailing one bits of the leaf index.  The loop is
   // uniform over the block (the U-turn test needs every lane); a chain leaves it at `stop_level`.  (With asynchronous
   // iterations the chains of a block are at different leaves and the loop runs to the deepest merge of any of its 32 chains
@@ -1021,10 +1019,12 @@ __global__ void __launch_bounds__(256, SMC_NUTS_POST_MINB) k_nuts_post(RngSrc rn
       if (!take_second) {
         copy_vec<LY>(T.csb, T.ksb + so, c, M, Cpad, ly);
         copy_vec<LY>(T.csg, T.ksg + so, c, M, Cpad, ly);
+        cur_sb = T.csb; cur_sg = T.csg;
         csl = T.ksl[sc];
       }
       copy_vec<LY>(T.cnb, T.knb + so, c, M, Cpad, ly);   // the merged sub-tree starts where the first one started
       copy_vec<LY>(T.cnv, T.knv + so, c, M, Cpad, ly);
+      cur_nb = T.cnb; cur_nv = T.cnv;
       a2 += T.ka[sc];
       na2 += T.kna[sc];
       if (s2) {
@@ -1040,10 +1040,10 @@ __global__ void __launch_bounds__(256, SMC_NUTS_POST_MINB) k_nuts_post(RngSrc rn
   const bool done = act && ((!s2) || (leaf == (1 << j) - 1));
   if (act && !done) {
     const long long so = (long long)stop_level * LS, sc = (long long)stop_level * Cpad + c;
-    copy_vec<LY>(T.knb + so, T.cnb, c, M, Cpad, ly);
-    copy_vec<LY>(T.knv + so, T.cnv, c, M, Cpad, ly);
-    copy_vec<LY>(T.ksb + so, T.csb, c, M, Cpad, ly);
-    copy_vec<LY>(T.ksg + so, T.csg, c, M, Cpad, ly);
+    copy_vec<LY>(T.knb + so, cur_nb, c, M, Cpad, ly);
+    copy_vec<LY>(T.knv + so, cur_nv, c, M, Cpad, ly);
+    copy_vec<LY>(T.ksb + so, cur_sb, c, M, Cpad, ly);
+    copy_vec<LY>(T.ksg + so, cur_sg, c, M, Cpad, ly);
     if (ly == 0) {
       T.tl[c] = ll;
       T.ksl[sc] = csl;
@@ -1071,8 +1071,8 @@ __global__ void __launch_bounds__(256, SMC_NUTS_POST_MINB) k_nuts_post(RngSrc rn
   if (s2) {
     double r = rng_uniform(rng, step, c, C, ucount++);
     if (r < n2 / ntot) {   // state = state1
-      copy_vec<LY>(T.sb, T.csb, c, M, Cpad, ly);
-      copy_vec<LY>(T.sg, T.csg, c, M, Cpad, ly);
+      copy_vec<LY>(T.sb, cur_sb, c, M, Cpad, ly);
+      copy_vec<LY>(T.sg, cur_sg, c, M, Cpad, ly);
       if (ly == 0) { T.sl[c] = csl; T.moved[c] = 1; }
     }
   }

@@ -1,7 +1,7 @@
 // Sliced-integer evaluation of a Normal identity-link GLM statement on the int8 tensor cores (tcgen05.mma kind::i8, int32
 // accumulators in TMEM): DESIGN.md section 8.  The path for Normal GLM statements with 33-64 columns and >= 32 chains
-// (SMC_GLM_I8=0 keeps them on the FP64 DMMA kernel of glm_fused.cu): measured 20.7 ms per configs[1] evaluation against
-// 32.2 ms (profiles/glm_i8_v12_r02.json), logp 2e-16 / gradient 7e-14 against long double at the full size, and the whole
+// (SMC_GLM_I8=0 keeps them on the FP64 DMMA kernel of glm_fused.cu): measured 20.0 ms per configs[1] evaluation against
+// 32.2 ms (profiles/bench_1gpu_r02.json, profiles/glm_i8_v14_ncu_r02.json), logp 2e-16 / gradient 7e-14 against long double at the full size, and the whole
 // 1e-12 parity suite runs through it (tests/test_gpu_scale.py, tests/test_zz_gpu_i8.py).
 //
 // Arithmetic (exact integer products, one FP64 rounding per recombination): every operand is cut into seven balanced
@@ -140,7 +140,7 @@ __device__ __forceinline__ double recombine7(const int32_t* a, int ii) {
   return fma((double)hi, ii ? 0x1p-44 : 0x1p-36, (double)lo * (ii ? 0x1p-68 : 0x1p-60));
 }
 
-// eight beta slices (SMC_GLM_I8_BETA8=1, not yet run on a device): t = round(v 2^62 / scale), byte k = slice 7 - k; the
+// eight beta slices (SMC_GLM_I8_BETA8=1; measured: gradient error 3e-15 instead of 7e-14 at 3 % more time): t = round(v 2^62 / scale), byte k = slice 7 - k; the
 // resolution of beta is the operand that limits the gradient with seven slices (profiles/ozaki_error_attribution_r01.json)
 __device__ __forceinline__ unsigned long long slice8_word(double v, double f62) {
   const unsigned long long H64 = 0x8080808080808080ull;

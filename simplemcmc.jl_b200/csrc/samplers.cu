@@ -57,7 +57,7 @@ struct Ln {
 template <int LY>
 __device__ __forceinline__ Ln lanes(long long C) {
   Ln L;
-  L.c = (long long)blockIdx.x * SMC_CXB + threadIdx.x;
+  L.c = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // (blockDim.x = SMC_CXB, or fewer chains per block: k_nuts_post)
   L.ly = threadIdx.y;
   L.in = L.c < C;
   return L;
@@ -404,6 +404,13 @@ inline int lanes_for(long long C) { return C >= 32768 ? 1 : 8; }
   do {                                                                                                         \
     if (ly == 1) kern<1><<<(unsigned)((C + 255) / 256), dim3(256, 1), 0, st>>>(__VA_ARGS__);                  \
     else kern<8><<<(unsigned)((C + 31) / 32), dim3(32, 8), 0, st>>>(__VA_ARGS__);                             \
+  } while (0)
+// k_nuts_post with `cx` chains per block (LY = 8 lanes each): its merge loop is uniform over the block, so with chains at
+// different leaves (asynchronous iterations) a smaller block runs fewer levels and its barriers span fewer warps
+#define LAUNCH_POST(cx, ...)                                                                                  \
+  do {                                                                                                        \
+    if (ly == 1) k_nuts_post<1><<<(unsigned)((C + 255) / 256), dim3(256, 1), 0, st>>>(__VA_ARGS__);           \
+    else k_nuts_post<8><<<(unsigned)((C + (cx) - 1) / (cx)), dim3((cx), 8), 0, st>>>(__VA_ARGS__);            \
   } while (0)
 inline unsigned gride(long long n) { return (unsigned)std::max<long long>(1, std::min<long long>((n + 255) / 256, 148LL * 32)); }
 
@@ -1205,6 +1212,8 @@ extern "C" int smc_nuts_run(smc_model_t m, const smc_sampler_config* cfg, const 
   if (out->jmax) SMC_TRY(r.A.alloc(&jmax_dev, cfg->steps * Cpad));
   int ly = lanes_for(C);
   if (const char* e = getenv("SMC_NUTS_LY")) ly = (e[0] == '1') ? 1 : 8;      // (A/B measurements)
+  int post_cx = 32;
+  if (const char* e = getenv("SMC_NUTS_POST_CX")) { const int v = atoi(e); if (v == 8 || v == 16 || v == 32) post_cx = v; }
   k_nuts_init<<<gridc(C), 128, 0, st>>>(C, T);
   m->ctx->launches++;
   long long* d_step;
@@ -1290,7 +1299,7 @@ extern "C" int smc_nuts_run(smc_model_t m, const smc_sampler_config* cfg, const 
     if (ok) {
       LAUNCH_LY(k_nuts_pre, r.rng, lock, C, M, Cpad, m->beta, 0, T);
       const int e = smc_model_eval_inline(m, C, true);
-      LAUNCH_LY(k_nuts_post, r.rng, lock, -1, C, M, Cpad, m->grad, m->logp, 0, T, r.nleap);
+      LAUNCH_POST(post_cx, r.rng, lock, -1, C, M, Cpad, m->grad, m->logp, 0, T, r.nleap);
       k_nuts_loop_cond<<<1, 1, 0, st>>>(h, T.n_active, d_ctl, max_rounds);
       m->ctx->launches += 3;
       ok = (cudaStreamEndCapture(st, &gcap) == cudaSuccess) && e == SMC_OK;
@@ -1359,7 +1368,7 @@ extern "C" int smc_nuts_run(smc_model_t m, const smc_sampler_config* cfg, const 
       int e = smc_model_eval_device(m, Ceval, true);
       if (e != SMC_OK) return e;
       evals++;
-      LAUNCH_LY(k_nuts_post, r.rng, own, rnd, C, M, Cpad, m->grad, m->logp, use_slots, T, r.nleap);
+      LAUNCH_POST(post_cx, r.rng, own, rnd, C, M, Cpad, m->grad, m->logp, use_slots, T, r.nleap);
       LAUNCH_LY(k_nuts_end, own, rnd, (long long)cfg->steps, C, M, Cpad, r.b0, r.g0, r.l0, T, r.R, eps_dev, jmax_dev);
       m->ctx->launches += 4;
       cudaMemcpyAsync(h_active + slot, T.n_active, sizeof(int), cudaMemcpyDeviceToHost, st);
@@ -1432,7 +1441,7 @@ extern "C" int smc_nuts_run(smc_model_t m, const smc_sampler_config* cfg, const 
       evals++;
       eval_chains += Ceval;
       (void)eval_chains;
-      LAUNCH_LY(k_nuts_post, r.rng, lock, -1, C, M, Cpad, m->grad, m->logp, use_slots, T, r.nleap);
+      LAUNCH_POST(post_cx, r.rng, lock, -1, C, M, Cpad, m->grad, m->logp, use_slots, T, r.nleap);
       m->ctx->launches++;
       cudaMemcpyAsync(h_active + slot, T.n_active, sizeof(int), cudaMemcpyDeviceToHost, st);
       cudaEventRecord(ev[slot], st);

@@ -16,7 +16,7 @@
 #include <stdint.h>
 
 #define SMC_TAPE_MAGIC 0x54434D53u /* "SMCT" */
-#define SMC_TAPE_VERSION 3u
+#define SMC_TAPE_VERSION 4u
 
 /* register kinds */
 enum {
@@ -32,6 +32,9 @@ enum {
 #define SMC_F_ACC 1u     /* dst += result (the `dv = dv + ...` of diff.jl:214) instead of dst = result */
 #define SMC_F_TRANS_A 2u /* MATMUL: use transpose(A) */
 #define SMC_F_TRANS_B 4u /* MATMUL: use transpose(B) */
+#define SMC_F_FWD_ONLY 8u /* forward statement that runs only when the gradient is NOT asked for: a later statement of the
+                             gradient part recomputes its values and takes its reductions over (so that an evaluation with
+                             gradient makes one pass over the index space instead of two) */
 
 /* opcodes.  Elementwise ops broadcast scalar operands; when dst is a scalar and an operand has n>1
  * elements the statement sums its n results (the `sum(...)` of the ::Real rules, diff.jl:29-178). */

@@ -824,6 +824,31 @@ __global__ void k_slot_assign(const int* active, long long C, const int* blocksu
   if (a) slot[c] = off + __popc(bal & ((1u << lane) - 1u));
 }
 
+// the three steps above in ONE block (up to 65 536 chains): warp w owns a contiguous range of chains, counts its active ones
+// (ballots), takes the sum of the warps before it, and numbers its active chains in chain order -- the same slots
+__global__ void __launch_bounds__(1024) k_slot_pack(const int* __restrict__ active, long long C, int* __restrict__ slot) {
+  __shared__ int wtot[32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const long long per = ((C + 31) / 32 + 31) / 32 * 32;       // chains per warp, a multiple of 32
+  const long long b = (long long)w * per, e = b + per < C ? b + per : C;
+  int n = 0;
+  for (long long c0 = b; c0 < e; c0 += 32) {                  // (warp-uniform trip count)
+    const long long c = c0 + lane;
+    n += __popc(__ballot_sync(0xffffffffu, c < e && active[c] != 0));
+  }
+  if (lane == 0) wtot[w] = n;
+  __syncthreads();
+  int base = 0;
+  for (int k = 0; k < w; k++) base += wtot[k];
+  for (long long c0 = b; c0 < e; c0 += 32) {
+    const long long c = c0 + lane;
+    const bool a = c < e && active[c] != 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, a);
+    if (a) slot[c] = base + __popc(bal & ((1u << lane) - 1u));
+    base += __popc(bal);
+  }
+}
+
 __global__ void k_nuts_init(long long C, Nuts T) {
   long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
@@ -875,6 +900,7 @@ __global__ void __launch_bounds__(256) k_nuts_pre(RngSrc rng, StepSrc steps, lon
   const long long c = L.c;
   const long long step = steps.of(c, L.in);
   const bool act = L.in && T.active[c];
+  if (blockIdx.x == 0 && threadIdx.x == 0) *T.n_active = 0;   // counted again by k_nuts_post / k_nuts_end of this round
   int newdbl = 0, dir = 0, k = 0;
   double eps = 0.0, lp_edge = 0.0;
   long long slot = c;
@@ -1203,6 +1229,8 @@ extern "C" int smc_nuts_run(smc_model_t m, const smc_sampler_config* cfg, const 
   int** ints[] = {&T.j, &T.leaf, &T.dir, &T.active, &T.newdbl, &T.ucount, &T.moved, &T.slot};
   for (auto pp : ints) SMC_TRY(r.A.alloc(pp, Cpad));
   const int slot_blocks = (int)((C + 255) / 256);
+  const char* sp1 = getenv("SMC_NUTS_SLOT_PACK");   // =0: the three-kernel count / scan / assign at every chain count
+  const bool slot_pack1 = C <= 65536 && !(sp1 && sp1[0] == '0');
   SMC_TRY(r.A.alloc(&T.blocksum, slot_blocks + 1));
   SMC_TRY(r.A.alloc(&T.n_active, 4));
   SMC_TRY(r.A.alloc(&T.rounds_active, 4));
@@ -1356,13 +1384,17 @@ extern "C" int smc_nuts_run(smc_model_t m, const smc_sampler_config* cfg, const 
       long long Ceval = C;
       if (compact && active_ub * 3 <= C * 2) Ceval = std::min<long long>(C, (std::max<long long>(active_ub, 1) + bucket - 1) / bucket * bucket);
       const int use_slots = Ceval < C ? 1 : 0;
-      cudaMemsetAsync(T.n_active, 0, sizeof(int), st);
       LAUNCH_LY(k_nuts_begin, r.rng, own, rnd, C, M, Cpad, r.b0, r.g0, r.l0, T);
       if (use_slots) {
-        k_slot_count<<<slot_blocks, 256, 0, st>>>(T.active, C, T.blocksum);
-        k_slot_scan<<<1, 1024, 0, st>>>(T.blocksum, slot_blocks);
-        k_slot_assign<<<slot_blocks, 256, 0, st>>>(T.active, C, T.blocksum, T.slot);
-        m->ctx->launches += 3;
+        if (slot_pack1) {
+          k_slot_pack<<<1, 1024, 0, st>>>(T.active, C, T.slot);
+          m->ctx->launches += 1;
+        } else {
+          k_slot_count<<<slot_blocks, 256, 0, st>>>(T.active, C, T.blocksum);
+          k_slot_scan<<<1, 1024, 0, st>>>(T.blocksum, slot_blocks);
+          k_slot_assign<<<slot_blocks, 256, 0, st>>>(T.active, C, T.blocksum, T.slot);
+          m->ctx->launches += 3;
+        }
       }
       LAUNCH_LY(k_nuts_pre, r.rng, own, C, M, Cpad, m->beta, use_slots, T);
       int e = smc_model_eval_device(m, Ceval, true);
@@ -1427,12 +1459,16 @@ extern "C" int smc_nuts_run(smc_model_t m, const smc_sampler_config* cfg, const 
       long long Ceval = C;
       if (compact && active_ub * 3 <= C * 2) Ceval = std::min<long long>(C, (std::max<long long>(active_ub, 1) + bucket - 1) / bucket * bucket);
       const int use_slots = Ceval < C ? 1 : 0;
-      cudaMemsetAsync(T.n_active, 0, sizeof(int), st);
       if (use_slots) {
-        k_slot_count<<<slot_blocks, 256, 0, st>>>(T.active, C, T.blocksum);
-        k_slot_scan<<<1, 1024, 0, st>>>(T.blocksum, slot_blocks);
-        k_slot_assign<<<slot_blocks, 256, 0, st>>>(T.active, C, T.blocksum, T.slot);
-        m->ctx->launches += 3;
+        if (slot_pack1) {
+          k_slot_pack<<<1, 1024, 0, st>>>(T.active, C, T.slot);
+          m->ctx->launches += 1;
+        } else {
+          k_slot_count<<<slot_blocks, 256, 0, st>>>(T.active, C, T.blocksum);
+          k_slot_scan<<<1, 1024, 0, st>>>(T.blocksum, slot_blocks);
+          k_slot_assign<<<slot_blocks, 256, 0, st>>>(T.active, C, T.blocksum, T.slot);
+          m->ctx->launches += 3;
+        }
       }
       LAUNCH_LY(k_nuts_pre, r.rng, lock, C, M, Cpad, m->beta, use_slots, T);
       m->ctx->launches++;

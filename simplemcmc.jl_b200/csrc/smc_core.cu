@@ -167,6 +167,11 @@ extern "C" int smc_model_compile(smc_ctx_t ctx, const void* tape, size_t nbytes,
     if (s.op == SMC_OP_AFFNORM) ok = ok && s.nsrc == 2 && s.aux0 < h.n_idx;
     if (!ok) { smc_set_error("tape: statement %u references a register out of range", i); delete m; return SMC_ERR_INVALID; }
     uint32_t dk = m->regs[s.dst].d.kind;
+    if ((s.flags & SMC_F_FWD_ONLY) && (i >= h.reserved[0] || dk != SMC_REG_CHAIN)) {
+      smc_set_error("tape: statement %u is flagged forward-only but belongs to the gradient part (or to the header)", i);
+      delete m;
+      return SMC_ERR_INVALID;
+    }
     if (dk == SMC_REG_HDR) m->hdr_stmts.push_back((int)i);
     else if (dk == SMC_REG_CHAIN || dk == SMC_REG_GRAD) m->body_stmts.push_back((int)i);
     else { smc_set_error("tape: statement %u writes a read-only register", i); delete m; return SMC_ERR_INVALID; }
@@ -368,7 +373,9 @@ struct MmArgs {
   long long r, k, n, C;
 };
 // out(i,j) = sum_l A(i,l) B(l,j), column major, split over l; partial[s][i + j*r][c]
-__global__ void __launch_bounds__(256) k_matmul(MmArgs a, double* partial, long long chunk) {
+// `direct` (one split only): the sum goes straight to the destination (=|+=) instead of a partial buffer that k_reduce_final
+// would copy -- the small products of hierarchical models (k = 1 .. 5) are launch bound, not flop bound
+__global__ void __launch_bounds__(256) k_matmul(MmArgs a, double* partial, long long chunk, Dst d, int dacc, int direct) {
   long long total = a.r * a.n * a.C;
   long long s = blockIdx.y, l0 = s * chunk, l1 = min(a.k, l0 + chunk);
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
@@ -380,7 +387,12 @@ __global__ void __launch_bounds__(256) k_matmul(MmArgs a, double* partial, long 
       long long eb = a.tB ? (j + l * a.br) : (l + j * a.br);
       acc += opd_ld(a.A, ea, c) * opd_ld(a.B, eb, c);
     }
-    partial[(s * a.r * a.n + o) * a.C + c] = acc;
+    if (direct) {
+      double* q = d.p + o * d.se + c * d.sc;
+      *q = dacc ? (*q + acc) : acc;
+    } else {
+      partial[(s * a.r * a.n + o) * a.C + c] = acc;
+    }
   }
 }
 
@@ -522,13 +534,14 @@ __global__ void k_fill_int(int* p, long long n, int v) {
 }
 
 // logp[c] = bad ? -inf : result ; grad[:,c] = bad ? 0 : grad   (src/parsing.jl:465-467)
-__global__ void k_finish_eval(const double* result, long long rse, int rsc, int* bad, double* logp, double* grad,
+__global__ void k_finish_eval(double* result, long long rse, int rsc, int* bad, double* logp, double* grad,
                               long long M, long long C, long long Cpad, int with_grad) {
   long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   double r = result[c * rsc];
   int b = bad[c] || !(r > -INFINITY);   // a -Inf / NaN total is a zero density as well ("give up eval")
   bad[c] = 0;                           // flags are left clean for the next evaluation
+  result[c * rsc] = 0.0;                // ... and so is the accumulator: every statement may add to it (tape version 4)
   logp[c] = b ? -INFINITY : r;
   if (b && with_grad)
     for (long long j = 0; j < M; j++) grad[j * Cpad + c] = 0.0;
@@ -749,11 +762,18 @@ static int run_statement(smc_model_s* m, const smc_tape_stmt& s, int64_t C, bool
       long long par = outn * C;
       if (par < 148LL * 512 && a.k >= 256) S = std::min<long long>((148LL * 512 + par - 1) / par, (a.k + 63) / 64);
       long long chunk = (a.k + S - 1) / S;
-      SMC_TRY(smc_scratch_reserve(m, S * outn * C));
+      // (a destination that is also an operand keeps the two-step form: every product is read before anything is written)
+      const bool views_may_overlap = dreg.d.kind == SMC_REG_GRAD &&
+                                     (m->regs[s.src[0]].d.kind == SMC_REG_GRAD || m->regs[s.src[1]].d.kind == SMC_REG_GRAD);
+      const bool direct = S == 1 && s.dst != s.src[0] && s.dst != s.src[1] && d.p != a.A.p && d.p != a.B.p && !views_may_overlap;
+      if (!direct) SMC_TRY(smc_scratch_reserve(m, S * outn * C));
       dim3 grid(grid_for(par), (unsigned)S);
-      k_matmul<<<grid, 256, 0, st>>>(a, m->scratch, chunk);
-      k_reduce_final<<<grid_for(par), 256, 0, st>>>(m->scratch, S, outn, C, d, acc);
-      m->ctx->launches += 2;
+      k_matmul<<<grid, 256, 0, st>>>(a, m->scratch, chunk, d, acc, direct ? 1 : 0);
+      m->ctx->launches++;
+      if (!direct) {
+        k_reduce_final<<<grid_for(par), 256, 0, st>>>(m->scratch, S, outn, C, d, acc);
+        m->ctx->launches++;
+      }
       break;
     }
     case SMC_OP_TRANSPOSE: {
@@ -842,6 +862,15 @@ static int run_statement(smc_model_s* m, const smc_tape_stmt& s, int64_t C, bool
   return SMC_OK;
 }
 
+// The result register (the model's accumulator, src/SimpleMCMC.jl:14) is zero whenever no evaluation is under way: at
+// finalize, after every k_finish_eval, after an evaluation that failed half way.  Tapes rely on it since version 4: every
+// statement that contributes to the accumulator may be a `+=` (and so may move between the forward and the gradient half).
+static void smc_clear_result(smc_model_s* m) {
+  if (m->hdr.result_reg >= m->regs.size()) return;
+  const SmcReg& rr = m->regs[m->hdr.result_reg];
+  if (rr.d.kind == SMC_REG_CHAIN && rr.dev) cudaMemsetAsync(rr.dev, 0, (size_t)rr.numel * m->Cpad * sizeof(double), m->ctx->stream);
+}
+
 extern "C" int smc_model_finalize(smc_model_t m, int64_t max_chains, int row_shard) {
   if (!m || max_chains < 1) { smc_set_error("smc_model_finalize: bad argument"); return SMC_ERR_INVALID; }
   cudaSetDevice(m->ctx->device);
@@ -900,6 +929,7 @@ extern "C" int smc_model_finalize(smc_model_t m, int64_t max_chains, int row_sha
       SMC_CUDA(smc_dev_alloc(&r.dev, (size_t)r.numel * sizeof(double), m->ctx->stream));
       r.owned = true;
     }
+  smc_clear_result(m);
   if (!m->ev0) { SMC_CUDA(cudaEventCreate(&m->ev0)); SMC_CUDA(cudaEventCreate(&m->ev1)); }
   for (auto& pr : m->programs) SMC_TRY(smc_vm_prepare(m, pr));  // operand tables of the register programs (device pointers)
   // the let-header: parameter independent statements, evaluated once (src/parsing.jl:432-442)
@@ -980,9 +1010,11 @@ static int eval_body(smc_model_s* m, int64_t C, bool with_grad) {
   for (int si : m->body_stmts) {
     const smc_tape_stmt& s = m->stmts[si];
     if (!with_grad && (si >= n_fwd || m->regs[s.dst].d.kind == SMC_REG_GRAD)) continue;
+    if (with_grad && (s.flags & SMC_F_FWD_ONLY)) continue;   // its work is part of a statement of the gradient half
     int rc = run_statement(m, s, C, false);
     if (rc != SMC_OK) {
       cudaMemsetAsync(m->bad, 0, (size_t)m->Cpad * sizeof(int), st);
+      smc_clear_result(m);
       return rc;
     }
   }
@@ -991,7 +1023,8 @@ static int eval_body(smc_model_s* m, int64_t C, bool with_grad) {
   if (ro.is_imm || rr.numel != 1) { smc_set_error("tape: result register must be a computed scalar"); return SMC_ERR_INVALID; }
   // row-sharded models all-reduce inside the GLM statement (its (L, G) are the only row sums), so every
   // rank finishes with identical (logp, grad) here
-  k_finish_eval<<<grid_for(C), 256, 0, st>>>(ro.p, ro.se, ro.sc, m->bad, m->logp, m->grad, m->M, C, m->Cpad, with_grad ? 1 : 0);
+  k_finish_eval<<<grid_for(C), 256, 0, st>>>(const_cast<double*>(ro.p), ro.se, ro.sc, m->bad, m->logp, m->grad, m->M, C, m->Cpad,
+                                             with_grad ? 1 : 0);
   m->ctx->launches++;
   return SMC_OK;
 }

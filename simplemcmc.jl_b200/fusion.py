@@ -79,9 +79,12 @@ def form_groups(stmts):
                 g = groups[gi]
                 if not g.fusable or g.n != n:
                     continue
-                if gi == gmin and (g.red_out & reads):          # needs a reduction finished by that very group
+                # `acc += sum(...)` into a scalar the group already reduces into (the priors of several parameter vectors of one
+                # length, src/parsing.jl:103-109 after coalesce_accumulator): both sums share one reduction slot
+                same_acc = nred == 1 and (st.flags & L.F_ACC) and st.dst.vid in g.red_out
+                if gi == gmin and (g.red_out & (reads - {st.dst.vid} if same_acc else reads)):   # needs a reduction finished by that very group
                     continue
-                if (g.red_out & writes):                         # two writers of one scalar: keep them in separate groups
+                if (g.red_out & writes) and not same_acc:        # two writers of one scalar: keep them in separate groups
                     continue
                 if len(g.stmts) >= 60 or sum(1 for s in g.stmts if is_reduce(s)) + nred > MAX_REDUCE:
                     continue
@@ -226,12 +229,17 @@ def build_program(g, outside):
             srcs = [load(s) for s in st.srcs]
             acc = 1 if (st.flags & L.F_ACC) else 0
             if is_reduce(st):
-                if len(prog.reductions) >= MAX_REDUCE:
-                    return None
+                slot = [k for k, (vid, _) in enumerate(prog.reductions) if vid == st.dst.vid]
+                if slot and not acc:
+                    return None                      # (a second `=` into one scalar: form_groups never builds this)
+                if not slot:
+                    if len(prog.reductions) >= MAX_REDUCE:
+                        return None
+                    slot = [len(prog.reductions)]
+                    prog.reductions.append((st.dst.vid, acc))
                 tmp = alloc(("tmp", i))
                 prog.body.append((st.op, tmp, srcs, 0, st.aux0, st.aux1, None))
-                prog.body.append((P_REDUCE, 0, [tmp], 0, len(prog.reductions), 0, None))
-                prog.reductions.append((st.dst.vid, acc))
+                prog.body.append((P_REDUCE, 0, [tmp], 0, slot[0], 0, None))
                 free.append(local.pop(("tmp", i)))
             else:
                 if acc and st.dst.vid not in local:
@@ -250,6 +258,79 @@ def build_program(g, outside):
     if len(prog.prologue) + len(prog.body) > MAX_INSTR:
         return None
     return prog
+
+
+def hand_over_reductions(gf, gb, producers, body_f, result_vid, always):
+    """An evaluation WITH gradient runs the forward groups and then the backward groups; a backward group usually recomputes
+    (rematerialise) the forward values of its index space, so the data of that index space is walked twice -- once for
+    `acc += sum(logpdf...)`, once for the adjoints.  Where a backward group B already holds clones of every elementwise
+    statement of a forward group F, F's reductions into the result accumulator are handed to B and F is marked
+    SMC_F_FWD_ONLY: the library runs it only when no gradient is asked for (include/simplemcmc_tape.h).  Only `+=`
+    reductions move (the accumulator's first, plain `=` writer has to stay first), and only when F stores nothing another
+    statement reads.  -> set of id(F) of the groups that became forward-only"""
+    fwd_only = set()
+    fwd_ids = {id(s) for s in body_f}
+    for F in gf:
+        if not F.fusable or F.n <= 1 or not gb:
+            continue
+        reds = [s for s in F.stmts if is_reduce(s)]
+        plain = [s for s in F.stmts if not is_reduce(s)]
+        if not reds or any(not (r.flags & L.F_ACC) or r.dst.vid != result_vid for r in reds):
+            continue
+        others = set(always)
+        for g in gf + gb:
+            if g is not F:
+                others |= external_inputs(g)
+        if any(p.dst.vid in others for p in plain):
+            continue                                  # F materialises a value somebody else reads: it has to run
+        own = {p.dst.vid for p in plain}
+        for B in gb:
+            if not B.fusable or B.n != F.n:
+                continue
+            have = {}
+            for i, st in enumerate(B.stmts):
+                if not is_reduce(st):
+                    have[st.dst.vid] = i
+            if any(p.dst.vid not in have or not getattr(B.stmts[have[p.dst.vid]], "clone", False) for p in plain):
+                continue
+
+            def available(v):
+                if v.vid in own:
+                    return True
+                if v.kind in (L.REG_IMM, L.REG_DATA, L.REG_HDR, L.REG_PARAM):
+                    return True
+                pr = producers.get(v.vid, [])                 # a forward value computed outside F, once
+                return v.kind == L.REG_CHAIN and len(pr) == 1 and id(pr[0]) in fwd_ids and pr[0] not in F.stmts
+            if not all(available(v) for r in reds for v in r.srcs):
+                continue
+            trial = Group(B.n, True)
+            stmts = list(B.stmts)
+            for r in reds:
+                at = max([have_at for have_at in (_index_of_writer(stmts, v.vid) for v in r.srcs) if have_at is not None] + [-1]) + 1
+                moved = L.Stmt(r.op, r.dst, r.srcs, flags=r.flags, aux0=r.aux0, aux1=r.aux1, aux2=r.aux2, imm=r.imm)
+                stmts.insert(at, moved)
+            for st in stmts:
+                trial.add(st)
+            outside = set(always)
+            for g in gf + gb:
+                if g is not B:
+                    outside |= external_inputs(g)
+            if build_program(trial, outside) is None:
+                continue
+            if build_program(F, set(always)) is None:         # (F has to stay one statement for the flag to cover all of it)
+                continue
+            B.stmts, B.writes, B.reads, B.red_out = trial.stmts, trial.writes, trial.reads, trial.red_out
+            fwd_only.add(id(F))
+            break
+    return fwd_only
+
+
+def _index_of_writer(stmts, vid):
+    at = None
+    for i, st in enumerate(stmts):
+        if not is_reduce(st) and st.dst.vid == vid:
+            at = i
+    return at
 
 
 def coalesce_accumulator(fwd, bwd, result):
@@ -301,6 +382,14 @@ def fuse(lowered):
     fwd0 = [s.copy() for s in lowered.fwd]
     bwd0 = [s.copy() for s in lowered.bwd]
     fwd0, bwd0, lowered.tape_result = coalesce_accumulator(fwd0, bwd0, lowered.result)
+    # The library keeps the result register zero between evaluations (tape version 4, csrc/smc_core.cu: smc_clear_result), so
+    # its first writer adds to it like every later one (0 + x is exact): no contribution to the accumulator is tied to a place
+    # in the statement order any more, which is what lets hand_over_reductions move them
+    for st in fwd0:
+        if st.dst is lowered.tape_result:
+            if not (st.flags & L.F_ACC) and st.dst.numel == 1 and (fusable(st) or st.op in (L.OP["GLM"], L.OP["AFFNORM"])):
+                st.flags |= L.F_ACC
+            break
     body_f = [s for s in fwd0 if s.dst.kind != L.REG_HDR]
     body_b = [s for s in bwd0 if s.dst.kind != L.REG_HDR]
     out_f = [s for s in fwd0 if s.dst.kind == L.REG_HDR]
@@ -326,6 +415,7 @@ def fuse(lowered):
             (gf if g in gf else gb).remove(g)
             changed = True
             break
+    fwd_only = hand_over_reductions(gf, gb, producers, body_f, lowered.tape_result.vid, always)
     all_groups = gf + gb
     ext = [external_inputs(g) for g in all_groups]
     programs = []
@@ -348,9 +438,11 @@ def fuse(lowered):
                     dst = v
                     break
         if prog is None or dst is None:
+            if id(g) in fwd_only:                   # (hand_over_reductions built this very program: cannot happen)
+                raise AssertionError("a forward-only group did not become a program")
             target.extend(s for s in g.stmts if not getattr(s, "clone", False))
             continue
-        st = L.Stmt(OP_FUSED, dst, [], aux0=len(programs), aux1=g.n)
+        st = L.Stmt(OP_FUSED, dst, [], flags=L.F_FWD_ONLY if id(g) in fwd_only else 0, aux0=len(programs), aux1=g.n)
         st.touched = [lowered.vals[v] for v in prog.touched()]
         programs.append(prog)
         target.append(st)

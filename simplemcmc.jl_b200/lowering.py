@@ -15,9 +15,9 @@ import numpy as np
 from .jlsyntax import read_model
 
 # ---- numbers from include/simplemcmc_tape.h (tests/test_abi.py checks they agree)
-TAPE_MAGIC, TAPE_VERSION = 0x54434D53, 3
+TAPE_MAGIC, TAPE_VERSION = 0x54434D53, 4
 REG_IMM, REG_DATA, REG_HDR, REG_CHAIN, REG_PARAM, REG_GRAD = range(6)
-F_ACC, F_TRANS_A, F_TRANS_B = 1, 2, 4
+F_ACC, F_TRANS_A, F_TRANS_B, F_FWD_ONLY = 1, 2, 4, 8
 OP = dict(COPY=0, NEG=1, EXP=2, LOG=3, SIN=4, COS=5, ABS=6, SIGN=7, DIGAMMA=8, ZERO=9, SQRT=10,
           ADD=16, SUB=17, MUL=18, DIV=19, POW=20, MAX=21, MIN=22, GT=23, LT=24, GE=25, LE=26, EQ=27,
           LOGPDF=32, DLOGPDF=33, MATMUL=40, TRANSPOSE=41, GATHER=42, SCATTER_SET=43, SCATTER_ADD=44, GLM=48,

@@ -33,7 +33,7 @@ def test_golden_tape_parses_by_the_header_layout(case):
     name = case[0]
     blob = open(os.path.join(ROOT, "tests", "golden", name + ".tape"), "rb").read()
     magic, version, n_regs, n_stmts, n_params, n_data, n_idx, result_reg, flags, n_fwd, n_prog, _ = struct.unpack("<12I", blob[:48])
-    assert magic == 0x54434D53 and version == 3 and result_reg < n_regs and n_fwd <= n_stmts
+    assert magic == 0x54434D53 and version == 4 and result_reg < n_regs and n_fwd <= n_stmts
     p = 48
     kinds = []
     for _ in range(n_regs):

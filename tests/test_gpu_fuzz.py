@@ -62,7 +62,9 @@ def _run(seed, n, m, C, fuse):
             assert np.isfinite(lp0)
             _check(lp[c], g[c], lp0, g0, (seed, c, model))
         lp2, _ = dev.eval(pts, gradient=False)
-        assert np.array_equal(lp, lp2), (seed, model)
+        # (the gradient evaluation sums the densities inside its adjoint programs: same terms, another order of summation)
+        with np.errstate(invalid="ignore"):
+            assert np.max(np.where(lp == lp2, 0.0, np.abs(lp - lp2) / np.maximum(np.abs(lp), 1e-300))) < 1e-13, (seed, model)
     finally:
         dev.close()
     return True

@@ -77,7 +77,8 @@ def test_linear_cfg1(smc, fuse, C):
     for c in range(C):
         _check(lp[c], g[c], *ref(betas[c]))
     lp2, _ = dev.eval(betas, gradient=False)
-    assert np.array_equal(lp, lp2)
+    # (since tape version 4 the gradient evaluation sums the densities inside its adjoint programs: same terms, another order)
+    assert np.max(np.abs(lp - lp2) / np.abs(lp)) < 1e-13
 
 
 @pytest.mark.parametrize("family", ["normal", "bernoulli"])
@@ -100,7 +101,8 @@ def test_narrow_glm_many_chains_wide_tile(smc, family):
     for c in list(range(0, C, 97)) + [C - 1, 2047, 2048, 2303, 2304]:
         _check(lp[c], g[c], *ref(betas[c]))
     lp2, _ = dev.eval(betas, gradient=False)
-    assert np.array_equal(lp, lp2)
+    # (since tape version 4 the gradient evaluation sums the densities inside its adjoint programs: same terms, another order)
+    assert np.max(np.abs(lp - lp2) / np.abs(lp)) < 1e-13
     dev.close()
 
 

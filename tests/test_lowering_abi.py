@@ -253,7 +253,8 @@ def test_register_program_planner_forms_chains():
     x = ou_data(1000, 5)
     plans = [capi.plan_describe(p) for p in _programs(ORNSTEIN, [("tau", 20.0), ("mu", 10.0), ("sigma", 0.1)], dict(x=x))]
     fwd = [pl for pl in plans if any(l.startswith("op32(dist0") and "->R0" in l for l in pl)]   # the likelihood's program
-    assert len(fwd) == 1 and len(fwd[0]) == 3, fwd                      # chain, density + reduction, summary line
+    # (two programs hold the likelihood: the forward-only one, and the gradient program that takes its reduction over)
+    assert len(fwd) == 2 and len(fwd[0]) == 3, fwd                      # chain, density + reduction, summary line
     assert fwd[0][0].startswith("chain(4,3,2) A0 S0 A1 S1 ->L0"), fwd[0]
     assert fwd[0][1].startswith("op32(dist0,arg0) S2 S3 L0 ->R0"), fwd[0]
     data, nsub = sleepstudy_data()

@@ -406,6 +406,8 @@ struct MmDcArgs {
   int tA;
   const double* B;
   double* out;
+  const double* B2;   // a second product with the same left operand and shapes (upper half of grid.y), or NULL
+  double* out2;
   long long Bse, Ose;   // element strides (Cpad)
   long long r, k, n, C, chunk;
   int acc, S;
@@ -419,15 +421,19 @@ __global__ void __launch_bounds__(256) k_matmul_dc(MmDcArgs a) {
   const long long c = (long long)blockIdx.x * tcx + threadIdx.x;
   const long long groups = (a.r + RI - 1) / RI;
   const long long gtiles = (groups + ty - 1) / ty;
-  const long long j = blockIdx.y / gtiles;                      // output column
-  const long long g0 = (blockIdx.y - j * gtiles) * ty;          // first row group of this block
+  const int second = blockIdx.y >= gtiles * a.n ? 1 : 0;        // (only when B2 is set: the grid is twice as tall)
+  const long long by = blockIdx.y - (second ? gtiles * a.n : 0);
+  const double* const Bm = second ? a.B2 : a.B;
+  double* const outm = second ? a.out2 : a.out;
+  const long long j = by / gtiles;                              // output column
+  const long long g0 = (by - j * gtiles) * ty;                  // first row group of this block
   const long long i0 = (g0 + threadIdx.y) * RI;
   const long long l0 = (long long)blockIdx.z * a.chunk, l1 = min(a.k, l0 + a.chunk);
   double acc[RI];
 #pragma unroll
   for (int ii = 0; ii < RI; ii++) acc[ii] = 0.0;
   const bool cok = c < a.C;
-  const double* Bc = a.B + (j * a.k) * a.Bse + (cok ? c : 0);
+  const double* Bc = Bm + (j * a.k) * a.Bse + (cok ? c : 0);
   for (long long lb = l0; lb < l1; lb += TK) {
     __syncthreads();
     for (int t = tid; t < ty * RI * TK; t += 256) {
@@ -462,7 +468,7 @@ __global__ void __launch_bounds__(256) k_matmul_dc(MmDcArgs a) {
     if (a.S > 1) {
       a.partial[((long long)blockIdx.z * a.r * a.n + o) * a.C + c] = acc[ii];
     } else {
-      double* q = a.out + o * a.Ose + c;
+      double* q = outm + o * a.Ose + c;
       *q = a.acc ? (*q + acc[ii]) : acc[ii];
     }
   }
@@ -472,14 +478,18 @@ __global__ void __launch_bounds__(256) k_matmul_dc(MmDcArgs a) {
 // one non-zero per row): CSR of op(A), thread = (output element, chain).  The non-zeros of a row are summed in column
 // order, i.e. the dense sum with its exact +0.0 terms dropped.
 __global__ void k_spmm_dc(const int32_t* ptr, const int32_t* col, const double* val, const double* B, long long Bse, double* out,
-                          long long Ose, long long r, long long n, long long k, long long C, int acc) {
-  long long total = r * n * C;
+                          long long Ose, long long r, long long n, long long k, long long C, int acc, const double* B2, double* out2) {
+  const long long one = r * n * C, total = B2 ? 2 * one : one;     // (B2, out2): a second product with the same matrix
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    long long o = idx / C, c = idx - o * C;
+    const bool second = idx >= one;
+    const double* const Bm = second ? B2 : B;
+    double* const outm = second ? out2 : out;
+    const long long id1 = second ? idx - one : idx;
+    long long o = id1 / C, c = id1 - o * C;
     long long i = o % r, j = o / r;
     double t = 0.0;
-    for (int p = ptr[i]; p < ptr[i + 1]; p++) t = fma(val[p], __ldg(B + ((long long)col[p] + j * k) * Bse + c), t);
-    double* q = out + o * Ose + c;
+    for (int p = ptr[i]; p < ptr[i + 1]; p++) t = fma(val[p], __ldg(Bm + ((long long)col[p] + j * k) * Bse + c), t);
+    double* q = outm + o * Ose + c;
     *q = acc ? (*q + t) : t;
   }
 }
@@ -689,7 +699,11 @@ static int sparse_plan(smc_model_s* m, uint32_t reg, int tA, long long r, long l
   return SMC_OK;
 }
 
-static int run_statement(smc_model_s* m, const smc_tape_stmt& s, int64_t C, bool header) {
+// `s2` (optional): the next statement of the evaluation when it is a MATMUL with the same left operand, flags and shapes and
+// independent of `s` (eval_body checks): where the kernel chosen for `s` can take a second (right operand, destination)
+// pair, both products go out in one launch and *paired is set.
+static int run_statement(smc_model_s* m, const smc_tape_stmt& s, int64_t C, bool header, const smc_tape_stmt* s2 = nullptr,
+                         bool* paired = nullptr) {
   cudaStream_t st = m->ctx->stream;
   const SmcReg& dreg = m->regs[s.dst];
   Dst d = smc_make_dst(m, s.dst);
@@ -706,13 +720,22 @@ static int run_statement(smc_model_s* m, const smc_tape_stmt& s, int64_t C, bool
       a.ar = a.tA ? a.k : a.r;
       a.br = a.tB ? a.n : a.k;
       long long outn = a.r * a.n;
+      const double* B2 = nullptr;      // the partner's right operand and destination, when they fit this statement's layout
+      double* out2 = nullptr;
+      if (s2 && paired) {
+        const Opd b2 = smc_make_opd(m, s2->src[1]);
+        const Dst d2 = smc_make_dst(m, s2->dst);
+        if (!b2.is_imm && b2.sc == 1 && b2.se == a.B.se && d2.sc == 1 && d2.se == d.se && b2.p && d2.p) { B2 = b2.p; out2 = d2.p; }
+      }
       if (!a.A.is_imm && a.A.sc == 0 && !a.B.is_imm && a.B.sc == 1 && !a.tB && d.sc == 1 && !header &&
           m->regs[s.src[0]].numel == a.r * a.k) {
         SmcSparse* sp = nullptr;
         SMC_TRY(sparse_plan(m, s.src[0], a.tA, a.r, a.k, a.ar, &sp));
         if (sp->sparse) {
-          k_spmm_dc<<<grid_for(outn * C), 256, 0, st>>>(sp->ptr, sp->col, sp->val, a.B.p, a.B.se, d.p, d.se, a.r, a.n, a.k, C, acc);
+          k_spmm_dc<<<grid_for((B2 ? 2 : 1) * outn * C), 256, 0, st>>>(sp->ptr, sp->col, sp->val, a.B.p, a.B.se, d.p, d.se, a.r, a.n, a.k,
+                                                                      C, acc, B2, out2);
           m->ctx->launches++;
+          if (B2) *paired = true;
           break;
         }
       }
@@ -721,6 +744,7 @@ static int run_statement(smc_model_s* m, const smc_tape_stmt& s, int64_t C, bool
         MmDcArgs g;
         g.A = a.A.p; g.ar = a.ar; g.tA = a.tA; g.B = a.B.p; g.out = d.p; g.Bse = a.B.se; g.Ose = d.se;
         g.r = a.r; g.k = a.k; g.n = a.n; g.C = C; g.acc = acc;
+        g.B2 = nullptr; g.out2 = nullptr;
         int RI = 16;
         {
           long long best = -1;
@@ -746,7 +770,8 @@ static int run_statement(smc_model_s* m, const smc_tape_stmt& s, int64_t C, bool
         g.S = (int)S;
         if (S > 1) SMC_TRY(smc_scratch_reserve(m, S * outn * C));
         g.partial = m->scratch;
-        dim3 grid((unsigned)ctiles, (unsigned)(gtiles * a.n), (unsigned)S), block(tcx, ty);
+        if (S == 1 && B2) { g.B2 = B2; g.out2 = out2; *paired = true; }   // both products in one launch (grid.y twice as tall)
+        dim3 grid((unsigned)ctiles, (unsigned)(gtiles * a.n * (g.B2 ? 2 : 1)), (unsigned)S), block(tcx, ty);
         size_t smem = (size_t)ty * RI * 32 * sizeof(double);
         if (RI == 4) k_matmul_dc<4><<<grid, block, smem, st>>>(g);
         else if (RI == 8) k_matmul_dc<8><<<grid, block, smem, st>>>(g);
@@ -1007,16 +1032,36 @@ static int eval_body(smc_model_s* m, int64_t C, bool with_grad) {
   cudaStream_t st = m->ctx->stream;
   // (the "give up eval" flags m->bad are zero here: cleared at finalize and again by every k_finish_eval)
   const int n_fwd = (int)m->hdr.reserved[0];  // statements past this index only serve the gradient
+  static thread_local std::vector<int> run;    // the statements of this evaluation, in order
+  run.clear();
   for (int si : m->body_stmts) {
     const smc_tape_stmt& s = m->stmts[si];
     if (!with_grad && (si >= n_fwd || m->regs[s.dst].d.kind == SMC_REG_GRAD)) continue;
     if (with_grad && (s.flags & SMC_F_FWD_ONLY)) continue;   // its work is part of a statement of the gradient half
-    int rc = run_statement(m, s, C, false);
+    run.push_back(si);
+  }
+  static int pair_mm = -1;                     // SMC_NO_MATMUL_PAIRS=1: one launch per product (A/B switch)
+  if (pair_mm < 0) { const char* e = getenv("SMC_NO_MATMUL_PAIRS"); pair_mm = (e && e[0] == '1') ? 0 : 1; }
+  for (size_t q = 0; q < run.size(); q++) {
+    const smc_tape_stmt& s = m->stmts[run[q]];
+    // two consecutive products with one left operand (`submatrix * rand_int`, `submatrix * rand_slope` of
+    // examples/sleepstudy.jl and their adjoints; `oneD * mu`, `oneD * sigma` of the hierarchical example): one launch
+    const smc_tape_stmt* s2 = nullptr;
+    if (pair_mm && s.op == SMC_OP_MATMUL && q + 1 < run.size()) {
+      const smc_tape_stmt& t = m->stmts[run[q + 1]];
+      if (t.op == SMC_OP_MATMUL && t.src[0] == s.src[0] && t.flags == s.flags && t.aux0 == s.aux0 && t.aux1 == s.aux1 && t.imm == s.imm &&
+          t.dst != s.dst && t.src[1] != s.dst && s.src[1] != t.dst && t.src[0] != s.dst && s.src[0] != t.dst &&
+          m->regs[t.dst].d.kind == m->regs[s.dst].d.kind && m->regs[t.src[1]].d.kind != SMC_REG_GRAD && m->regs[s.src[1]].d.kind != SMC_REG_GRAD)
+        s2 = &t;
+    }
+    bool paired = false;
+    int rc = run_statement(m, s, C, false, s2, &paired);
     if (rc != SMC_OK) {
       cudaMemsetAsync(m->bad, 0, (size_t)m->Cpad * sizeof(int), st);
       smc_clear_result(m);
       return rc;
     }
+    if (paired) q++;
   }
   const SmcReg& rr = m->regs[m->hdr.result_reg];
   Opd ro = smc_make_opd(m, m->hdr.result_reg);

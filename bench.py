@@ -301,6 +301,65 @@ def cfg1_extra(api, ctx, local, rank, world, barrier):
                     "over the GPUs; device-resident, CUDA events in the library, max over ranks"}
 
 
+SLEEPSTUDY = """
+    r_bar = (intercept + submatrix * rand_int) + (slope + submatrix * rand_slope) .* days
+    rand_int ~ Normal(0,100)
+    rand_slope ~ Normal(0,100)
+    resid = r_bar - reaction
+    resid ~ Normal(0,10)
+"""
+HIERARCHICAL = """
+    mu ~ Normal(0, 1)
+    sigma ~ Weibull(2, 1)
+    beta ~ Normal(oneD * mu, oneD * sigma)
+    effect = (beta[ll,:] .* X) * oneL
+    prob = 1. / ( 1. + exp(- effect) )
+    Y ~ Bernoulli(prob)
+"""
+
+
+def nuts_extra(api, ctx, local):
+    """configs[3] (examples/sleepstudy.jl:25-45, examples/hierarchical.jl:7-37 with synthetic data of those shapes): simpleNUTS,
+    16 384 chains as BASELINE.json states, a BOUNDED 400 iterations (the stated 2000 take 75 s per model: tools/nuts_baseline_run.py,
+    profiles/nuts_baseline_size_r02.jsonl); nadapt is a literal 1000 in the reference (src/samplers.jl:214), so all of these
+    iterations adapt the step size and the number is NOT the one of the full-size run"""
+    C, steps = 16384, 400
+    rng = np.random.default_rng(6)
+    nsub, ndays = 18, 10
+    days = np.tile(np.arange(ndays, dtype=np.float64), nsub)
+    sub = np.repeat(np.arange(nsub), ndays)
+    submatrix = np.zeros((nsub * ndays, nsub))
+    submatrix[np.arange(nsub * ndays), sub] = 1.0
+    ri, rs = 25 * rng.standard_normal(nsub), 6 * rng.standard_normal(nsub)
+    reaction = 250 + 10 * days + ri[sub] + rs[sub] * days + 25 * rng.standard_normal(nsub * ndays)
+    rng = np.random.default_rng(4)
+    N, D, L = 50, 4, 5
+    mu0, sigma0 = rng.standard_normal((1, L)), rng.random((1, L))
+    beta0 = rng.standard_normal((D, L)) * sigma0 + mu0
+    ll = rng.integers(1, D + 1, N)
+    Xh = rng.standard_normal((N, L))
+    Yh = (rng.random(N) < 1.0 / (1.0 + np.exp(-(beta0[ll - 1, :] * Xh).sum(axis=1)))).astype(np.float64)
+    cases = [("sleepstudy", SLEEPSTUDY, [("intercept", 250.0), ("slope", 10.0), ("rand_int", np.zeros(nsub)), ("rand_slope", np.zeros(nsub))],
+              dict(days=days, reaction=reaction, submatrix=submatrix), "assign"),
+             ("hierarchical", HIERARCHICAL, [("mu", np.zeros((1, L))), ("sigma", np.ones((1, L))), ("beta", np.zeros((D, L)))],
+              dict(oneD=np.ones(D), oneL=np.ones(L), ll=ll, X=Xh, Y=Yh), "add")]
+    out = {"chains": C, "iterations": steps, "unit": "leapfrogs/s",
+           "note": "simpleNUTS, device-resident, CUDA events in the library; bounded sample of configs[3] (see the docstring of nuts_extra)"}
+    for name, model, init, data, adj in cases:
+        low, dev = api._build(model, init, data, True, C, local, adj, comm=ctx)
+        try:
+            dev.run("nuts", np.array(low.init), C, 4, 0, seed=3, store_draws=False, want=())
+            raw = dev.run("nuts", np.array(low.init), C, steps, steps // 2, seed=1, store_draws=False, want=("epsilon", "jmax"))
+        finally:
+            dev.close()
+        rounds = max(int(raw["n_evals"]) - 1, 1)
+        out[name] = {"value": raw["n_leapfrogs"] / (raw["device_ms"] * 1e-3), "rounds": rounds,
+                     "launches_per_round": raw["n_kernel_launches"] / rounds, "active_lane_fraction": raw["n_leapfrogs"] / (rounds * C),
+                     "epsilon_mean_last": float(raw["epsilon"][-1].mean()), "mean_tree_depth_second_half": float(raw["jmax"][steps // 2:].mean()),
+                     "accept_rate": float(raw["accept_rate"].mean())}
+    return out
+
+
 def strong_scaling_extra(api, ctx, local, rank, world, data, mode, K, W, barrier):
     """configs[1] read as strong scaling: 4096 chains IN TOTAL, 4096 / N per GPU (BASELINE.json: "4096 chains, chain-sharded
     at 1/2/4/8 B200")"""
@@ -550,6 +609,8 @@ def _run_ours(args):
         except Exception:
             pass
     guarded("cfg1_2p20_chains", lambda: cfg1_extra(api, ctx, local, rank, world, barrier))
+    if world == 1:
+        guarded("nuts_cfg4_16k_chains", lambda: nuts_extra(api, ctx, local))
     if world > 1:
         guarded("strong_scaling_cfg2", lambda: strong_scaling_extra(api, ctx, local, rank, world, data, mode, K, W, barrier))
         guarded("row_sharded_cfg3", lambda: row_sharded_extra(api, capi, parallel, local, rank, world, barrier))

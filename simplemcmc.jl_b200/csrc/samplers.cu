@@ -824,29 +824,43 @@ __global__ void k_slot_assign(const int* active, long long C, const int* blocksu
   if (a) slot[c] = off + __popc(bal & ((1u << lane) - 1u));
 }
 
-// the three steps above in ONE block (up to 65 536 chains): warp w owns a contiguous range of chains, counts its active ones
-// (ballots), takes the sum of the warps before it, and numbers its active chains in chain order -- the same slots
+// the three steps above in ONE block (up to 65 536 chains): thread t owns `per` consecutive chains (independent loads, all in
+// flight at once), counts its active ones, takes the block-wide exclusive prefix of the counts (shuffle scan per warp, then
+// over the 32 warp totals), and numbers its active chains in chain order -- the same slots
 __global__ void __launch_bounds__(1024) k_slot_pack(const int* __restrict__ active, long long C, int* __restrict__ slot) {
   __shared__ int wtot[32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const long long per = ((C + 31) / 32 + 31) / 32 * 32;       // chains per warp, a multiple of 32
-  const long long b = (long long)w * per, e = b + per < C ? b + per : C;
-  int n = 0;
-  for (long long c0 = b; c0 < e; c0 += 32) {                  // (warp-uniform trip count)
-    const long long c = c0 + lane;
-    n += __popc(__ballot_sync(0xffffffffu, c < e && active[c] != 0));
+  const int per = (int)((C + 1023) / 1024);                   // <= 64
+  const long long b = (long long)threadIdx.x * per;
+  unsigned long long bits = 0ull;                             // this thread's flags
+#pragma unroll 8
+  for (int u = 0; u < per; u++) {
+    const long long c = b + u;
+    bits |= (unsigned long long)((c < C && active[c] != 0) ? 1 : 0) << u;
   }
-  if (lane == 0) wtot[w] = n;
+  const int n = __popcll(bits);
+  int incl = n;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) wtot[w] = incl;
   __syncthreads();
-  int base = 0;
-  for (int k = 0; k < w; k++) base += wtot[k];
-  for (long long c0 = b; c0 < e; c0 += 32) {
-    const long long c = c0 + lane;
-    const bool a = c < e && active[c] != 0;
-    const unsigned bal = __ballot_sync(0xffffffffu, a);
-    if (a) slot[c] = base + __popc(bal & ((1u << lane) - 1u));
-    base += __popc(bal);
+  if (w == 0) {
+    const int v = wtot[lane];
+    int s2 = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, s2, o);
+      if (lane >= o) s2 += t;
+    }
+    wtot[lane] = s2 - v;                                      // exclusive prefix of the warp totals
   }
+  __syncthreads();
+  int base = wtot[w] + incl - n;
+  for (int u = 0; u < per; u++)
+    if ((bits >> u) & 1ull) slot[b + u] = base++;
 }
 
 __global__ void k_nuts_init(long long C, Nuts T) {

@@ -4,7 +4,8 @@ programs, SMC_F_ACC / SMC_F_FWD_ONLY semantics) against the oracle's model funct
 chain; column-major element order; `evaluate(low, beta, with_grad)` follows eval_body of csrc/smc_core.cu: with a gradient
 the forward statements flagged SMC_F_FWD_ONLY are skipped, without one everything past the forward part is.
 
-Not covered (raise NotImplementedError): SMC_OP_GLM and SMC_OP_AFFNORM statements -- lower with fuse=False for this executor.
+SMC_OP_GLM and SMC_OP_AFFNORM are executed from their definitions in the header (eta = X * beta, the family's density, G =
+X' * dl/deta; the affine residual into a Normal density with its adjoint scalars), not the way the kernels compute them.
 """
 import numpy as np
 from scipy.special import digamma
@@ -166,14 +167,77 @@ class Machine(object):
         for k, (vid, acc) in enumerate(prog.reductions):
             self.put(self.low.vals[vid], sums[k], acc=bool(acc))
 
+    def glm(self, st, acc):
+        """SMC_OP_GLM (include/simplemcmc_tape.h): eta = X * beta; L = sum_i l(eta_i, y_i); G = X' * dl/deta"""
+        Xv, b, y = st.srcs
+        N, M = Xv.shape
+        X = self.get(Xv).reshape((N, M), order="F")
+        eta = X @ self.get(b)
+        yv = self.get(y)
+        fam, bits = st.aux0, st.aux1
+        with np.errstate(all="ignore"):
+            if fam == L.GLM_NORMAL:                        # l = logpdfNormal(0, sigma, a * eta + b * y), a, b = +-1
+                a, bb, sigma = (-1.0 if bits & 1 else 1.0), (-1.0 if bits & 2 else 1.0), st.imm
+                z = a * eta + bb * yv
+                l = densities.elementwise("Normal", 0.0, sigma, z)
+                dl = a * (0.0 - z) / (sigma * sigma)
+            else:                                          # prob = 1 / (1 + exp(s * eta)), s = -1 when aux1 == 1
+                sg = -1.0 if bits == 1 else 1.0
+                pr = 1.0 / (1.0 + np.exp(sg * eta))
+                if fam == L.GLM_BERNOULLI:
+                    l = densities.elementwise("Bernoulli", pr, yv)
+                    dlp = 1.0 / (pr - (1.0 - yv))
+                elif fam == L.GLM_BINOMIAL:
+                    l = densities.elementwise("Binomial", st.imm, pr, yv)
+                    dlp = yv / pr - (st.imm - yv) / (1.0 - pr)
+                else:
+                    raise NotImplementedError("GLM family %d" % fam)
+                dl = dlp * (-sg) * pr * (1.0 - pr)
+        l = np.asarray(l, dtype=np.float64)
+        if (np.isnan(l) | (l == -np.inf)).any():
+            self.bad = True
+            l, dl = np.zeros_like(l), np.zeros_like(dl)
+        self.put(st.dst, np.sum(l), acc)
+        self.put(st.aux2, X.T @ dl)
+
+    def affnorm(self, st, acc):
+        """SMC_OP_AFFNORM: dst (+)= sum_e logpdfNormal(mu, sigma, r_e), r_e = ((+-t_0) +- t_1) ..., t_j = D_j[e] * s_j | s_j; the
+        adjoint scalars dL/dmu, dL/dsigma, dL/ds_j are assigned by the same statement"""
+        d = st.desc
+        n = d.n
+        mu, sigma = float(self.get(st.srcs[0])[0]), float(self.get(st.srcs[1])[0])
+        r, cols = None, []
+        for j, (kind, sg, base, off) in enumerate(d.terms):
+            sj = float(self.get(st.srcs[2 + j])[0])
+            col = self.get(base)[off:off + n] if kind == 0 else np.ones(n)
+            cols.append(col)
+            t = sg * (col * sj)
+            r = t if r is None else r + t
+        dd = r - mu
+        S2 = float(np.sum(dd * dd))
+        if not sigma > 0.0:
+            self.bad = True
+            return self.put(st.dst, 0.0, acc)
+        self.put(st.dst, -0.5 * S2 / sigma ** 2 - n * np.log(sigma) - n * 0.9189385332046727418, acc)
+        outs = d.outs
+        if outs[0] is not None:
+            self.put(outs[0], np.sum(dd) / sigma ** 2)
+        if outs[1] is not None:
+            self.put(outs[1], (S2 / sigma ** 2 - n) / sigma)
+        for j, (kind, sg, base, off) in enumerate(d.terms):
+            if outs[2 + j] is not None:
+                self.put(outs[2 + j], -sg * float(np.sum(dd * cols[j])) / sigma ** 2)
+
     def statement(self, st):
         self.launches += 1
         acc = bool(st.flags & L.F_ACC)
         name = OPN.get(st.op, "FUSED" if st.op == fusion.OP_FUSED else "?")
         if name == "FUSED":
             return self.program(self.low.programs[st.aux0])
-        if name in ("GLM", "AFFNORM"):
-            raise NotImplementedError(name)
+        if name == "GLM":
+            return self.glm(st, acc)
+        if name == "AFFNORM":
+            return self.affnorm(st, acc)
         if name == "MATMUL":
             r, k, n = st.aux0, st.aux1, int(st.imm)
             A, B = self.get(st.srcs[0]), self.get(st.srcs[1])

@@ -31,8 +31,6 @@ constexpr int NT = 512;       // threads per CTA
 constexpr int CQ = NC / (NT / 128);
 constexpr uint32_t XT_BYTES = TR * 8 * MP;         // one X tile: 8 slice slots (slot 7 = zeros)
 constexpr uint32_t QB_BYTES = 8 * NC * MP;
-constexpr uint32_t QD_BYTES = 8 * NC * TR;
-constexpr uint32_t SMEM_BYTES = 2 * XT_BYTES + QB_BYTES + QD_BYTES;
 constexpr unsigned long long H8 = 0x0080808080808080ull;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -79,11 +77,6 @@ __device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t cols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(taddr), "r"(cols) : "memory");
 }
-__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, int32_t* v) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
-               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-               : "r"(taddr) : "memory");
-}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
 __device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
@@ -114,15 +107,6 @@ __device__ __forceinline__ unsigned long long slice7_word(double v, double f) {
   long long t = __double2ll_rn(v * f);
   return ((unsigned long long)t + H8) ^ H8;
 }
-__device__ __forceinline__ unsigned long long slice7_bits(double v, unsigned int Emax) {   // scale = 2^(Emax - 1022)
-  const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
-  const unsigned int E = (unsigned int)(bits >> 52) & 0x7ffu;
-  const unsigned long long mant = (bits & 0xFFFFFFFFFFFFFull) | (1ull << 52);
-  const unsigned int sh = Emax - E;
-  const unsigned long long mag = (E == 0u || sh > 63u) ? 0ull : ((mant << 1) >> sh);
-  const unsigned long long t = (long long)bits < 0 ? (0ull - mag) : mag;
-  return (t + H8) ^ H8;
-}
 // power-of-two scale strictly above m, from m's exponent field; factor = 2^54 / scale
 __host__ __device__ inline void scale_of8(double m, double* scale, double* factor) {
   unsigned long long bits;
@@ -133,24 +117,12 @@ __host__ __device__ inline void scale_of8(double m, double* scale, double* facto
   memcpy(scale, &sb, 8);
   memcpy(factor, &fb, 8);
 }
-// sum_cb a[cb] 2^(-12 - 8 (cb + ii)) from seven exact int32 group sums (two int64 halves, one rounding)
-__device__ __forceinline__ double recombine7(const int32_t* a, int ii) {
-  long long hi = ((long long)a[0] << 24) + ((long long)a[1] << 16) + ((long long)a[2] << 8) + (long long)a[3];
-  long long lo = ((long long)a[4] << 16) + ((long long)a[5] << 8) + (long long)a[6];
-  return fma((double)hi, ii ? 0x1p-44 : 0x1p-36, (double)lo * (ii ? 0x1p-68 : 0x1p-60));
-}
-
 // eight beta slices (SMC_GLM_I8_BETA8=1; measured: gradient error 3e-15 instead of 7e-14 at 3 % more time): t = round(v 2^62 / scale), byte k = slice 7 - k; the
 // resolution of beta is the operand that limits the gradient with seven slices (profiles/ozaki_error_attribution_r01.json)
 __device__ __forceinline__ unsigned long long slice8_word(double v, double f62) {
   const unsigned long long H64 = 0x8080808080808080ull;
   long long t = __double2ll_rn(v * f62);
   return ((unsigned long long)t + H64) ^ H64;
-}
-__device__ __forceinline__ double recombine8(const int32_t* a) {
-  long long hi = ((long long)a[0] << 24) + ((long long)a[1] << 16) + ((long long)a[2] << 8) + (long long)a[3];
-  long long lo = ((long long)a[4] << 24) + ((long long)a[5] << 16) + ((long long)a[6] << 8) + (long long)a[7];
-  return fma((double)hi, 0x1p-36, (double)lo * 0x1p-68);
 }
 __device__ __forceinline__ void tmem_ld4_nowait(uint32_t taddr, int32_t* v) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];\n"

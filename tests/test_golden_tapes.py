@@ -69,6 +69,26 @@ def test_golden_tape_parses_by_the_header_layout(case):
         assert ops.count(48) == 1
 
 
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_tape_dump_reads_every_golden_tape(case):
+    """tools/tape_dump.py (the readable form an emitter author diffs): parses to the last byte and names what the tape holds"""
+    import tape_dump
+    name = case[0]
+    t = tape_dump.parse(open(os.path.join(ROOT, "tests", "golden", name + ".tape"), "rb").read())
+    text = "\n".join(tape_dump.lines(t))
+    assert t["version"] == 4 and "[forward]" in text
+    if name == "sleepstudy":
+        assert text.count("fwd-only") == 2 and "LOGPDFNormal" in text and "(18 x 180) * (180 x 1)" in text
+    if name in ("linear", "binomial"):
+        assert "GLM(" in text and ("family NORMAL" in text or "family BERNOULLI" in text)
+    if name == "ornstein_T5000_affnorm":
+        assert "AFFNORM(" in text
+    if name == "linear_no_gradient":
+        assert "[gradient]" not in text
+    with pytest.raises(ValueError):
+        tape_dump.parse(open(os.path.join(ROOT, "tests", "golden", name + ".tape"), "rb").read()[:-4])
+
+
 @pytest.mark.gpu
 def test_golden_tapes_compile_on_the_device():
     """smc_model_compile / bind / finalize accept the golden blobs (the library has no CPU fallback: a gpu test)"""

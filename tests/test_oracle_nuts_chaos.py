@@ -2,8 +2,11 @@
 epsilon = 1 and adapts by dual averaging, overshooting the leapfrog stability limit again and again; rounding differences
 are amplified along the way.  Here the ORACLE runs against a copy of itself whose gradient is perturbed by one unit in the
 last place at every evaluation: the amplification over 30 iterations is about three orders of magnitude (1e-16 -> 4e-13).
-The device's elementary functions differ from glibc's by an ulp or two in the same way, so the whole-run bar of
-tests/test_gpu_samplers.py::test_nuts_trajectory_parity is set two orders above this measured growth, not looser."""
+The device's elementary functions differ from glibc's by an ulp or two in the same way (and its reductions sum in another
+order), so tests/test_gpu_samplers.py::test_nuts_trajectory_parity holds the first 12 iterations at 1e-10 and identical
+tree depths and accept decisions over the whole run; its whole-run bar on the values (1e-4) is a loose safety net for the
+second, scalar Normal x Gamma case, whose growth is larger than the linear model's measured here -- it is NOT a measured
+device discrepancy, and it has not been tightened to this test's 1e-11 because that needs a device run to confirm."""
 import numpy as np
 
 from oracle.refmodel import generate_model_function
